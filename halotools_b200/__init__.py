@@ -1,0 +1,13 @@
+"""halotools_b200 - B200-native (sm_100a) pair-counting engine with the call signatures of
+``halotools.mock_observables``: ``npairs_3d``, ``npairs_xy_z``, ``npairs_s_mu``, ``marked_npairs_3d``,
+``mean_delta_sigma`` and the statistics built on them (``tpcf``, ``wp``, ``rp_pi_tpcf``,
+``marked_tpcf``).  Host code is Python; the mesh sort and the pair loops are hand-written CUDA
+behind the C ABI of ``include/halotools_b200.h`` (``libhalotools_b200.so``).  No CPU fallback."""
+from .custom_exceptions import HalotoolsError
+from .pair_counters import npairs_3d, npairs_xy_z, npairs_s_mu, marked_npairs_3d
+from .surface_density import mean_delta_sigma
+from .two_point_clustering import tpcf, wp, rp_pi_tpcf, marked_tpcf
+
+__version__ = "0.1.0"
+__all__ = ("HalotoolsError", "npairs_3d", "npairs_xy_z", "npairs_s_mu", "marked_npairs_3d",
+           "mean_delta_sigma", "tpcf", "wp", "rp_pi_tpcf", "marked_tpcf")

@@ -1,0 +1,145 @@
+"""ctypes binding of the C ABI in include/halotools_b200.h (libhalotools_b200.so).
+
+The library is the product: there is NO CPU fallback.  Importing the package works
+without a GPU (so argument validation can be tested anywhere) but every compute
+call raises ``RuntimeError`` when the shared object is missing or no CUDA device
+is visible.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhalotools_b200.so")
+
+FLAG_DEVICE_INPUT = 1
+FLAG_NO_CULL = 2
+FLAG_GENERIC = 4
+FLAG_NO_TMA = 8
+
+EXPORTS = (
+    "htb_last_error", "htb_abi_version", "htb_device_count", "htb_set_device", "htb_set_stream",
+    "htb_npairs_3d_engine", "htb_npairs_xy_z_engine", "htb_npairs_s_mu_engine",
+    "htb_marked_npairs_3d_engine", "htb_mean_delta_sigma_engine",
+    "htb_mesh_cell_ids", "htb_mesh_cell_id_indices", "htb_cell1_work", "htb_measure_fp64_rate",
+)
+
+
+class MeshGeom(ctypes.Structure):
+    """htb_mesh_geom"""
+    _fields_ = [("ndim", ctypes.c_int32), ("pbc", ctypes.c_int32),
+                ("ndivs1", ctypes.c_int32 * 3), ("ndivs2", ctypes.c_int32 * 3),
+                ("cover", ctypes.c_int32 * 3), ("reserved", ctypes.c_int32),
+                ("period", ctypes.c_double * 3), ("cell1_size", ctypes.c_double * 3),
+                ("cell2_size", ctypes.c_double * 3), ("search", ctypes.c_double * 3)]
+
+
+class Stats(ctypes.Structure):
+    """htb_stats"""
+    _fields_ = [("pairs_evaluated", ctypes.c_double), ("pairs_reference", ctypes.c_double),
+                ("ms_h2d", ctypes.c_float), ("ms_mesh", ctypes.c_float),
+                ("ms_count", ctypes.c_float), ("ms_total", ctypes.c_float),
+                ("kernel_launches", ctypes.c_int32), ("tiles", ctypes.c_int32),
+                ("tiles_redone", ctypes.c_int32), ("refine1", ctypes.c_int32 * 3),
+                ("refine2", ctypes.c_int32 * 3), ("path", ctypes.c_int32)]
+
+    def as_dict(self):
+        return {"pairs_evaluated": self.pairs_evaluated, "pairs_reference": self.pairs_reference,
+                "ms_h2d": self.ms_h2d, "ms_mesh": self.ms_mesh, "ms_count": self.ms_count,
+                "ms_total": self.ms_total, "kernel_launches": self.kernel_launches,
+                "tiles": self.tiles, "tiles_redone": self.tiles_redone,
+                "refine1": list(self.refine1), "refine2": list(self.refine2), "path": self.path}
+
+
+_lib = None
+last_stats = None        # Stats of the most recent engine call (dict), for benchmarks / tests
+default_flags = 0        # OR-ed into every engine call (tests flip HTB_FLAG_GENERIC / NO_CULL here)
+collect_stats = True
+
+
+def library_present():
+    return os.path.exists(LIB_PATH)
+
+
+def load():
+    """Load the shared object (no CUDA call is made)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "halotools_b200: %s is missing - build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        lib.htb_last_error.restype = ctypes.c_char_p
+        for name in EXPORTS:
+            getattr(lib, name)  # AttributeError if the .so does not export what the header declares
+        _lib = lib
+    return _lib
+
+
+def require_gpu():
+    lib = load()
+    if lib.htb_device_count() < 1:
+        raise RuntimeError("halotools_b200: no CUDA device is visible; the pair counters only run on a GPU "
+                           "(there is no CPU fallback)")
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError("halotools_b200: " + load().htb_last_error().decode("utf-8", "replace"))
+
+
+def set_device(index):
+    check(require_gpu().htb_set_device(int(index)))
+
+
+def _dp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+class Columns(object):
+    """Column views of an (N, ndim) float64 sample: base pointers + common element stride.
+
+    A C-contiguous (N, 3) array is passed as ONE block (x = base, y = base + 1, z = base + 2,
+    stride 3) so the library uploads it with a single host->device copy.
+    """
+
+    def __init__(self, cols):
+        cols = [np.asarray(c) for c in cols]
+        n = cols[0].shape[0]
+        ok = all(c.dtype == np.float64 and c.ndim == 1 and c.shape[0] == n for c in cols)
+        stride = None
+        if ok and n > 0:
+            strides = set(c.strides[0] for c in cols)
+            ok = len(strides) == 1 and list(strides)[0] % 8 == 0 and list(strides)[0] > 0
+            if ok:
+                stride = list(strides)[0] // 8
+        if not ok or n == 0:
+            cols = [np.ascontiguousarray(c, dtype=np.float64) for c in cols]
+            stride = 1
+        self.cols = cols          # keep references alive for the duration of the call
+        self.n = n
+        self.stride = stride
+        self.ptrs = [_dp(c) for c in cols]
+
+
+def run_engine(func_name, *args):
+    """Call an engine entry point, appending (flags, stats) and recording the stats."""
+    global last_stats
+    lib = require_gpu()
+    st = Stats()
+    rc = getattr(lib, func_name)(*args, ctypes.c_uint32(default_flags),
+                                 ctypes.byref(st) if collect_stats else None)
+    check(rc)
+    last_stats = st.as_dict() if collect_stats else None
+    return last_stats
+
+
+def measure_fp64_rate():
+    lib = require_gpu()
+    rate = ctypes.c_double(0.0)
+    clk = ctypes.c_double(0.0)
+    check(lib.htb_measure_fp64_rate(ctypes.byref(rate), ctypes.byref(clk)))
+    return rate.value, clk.value

@@ -1,0 +1,712 @@
+// C ABI of libhalotools_b200.so (declared in include/halotools_b200.h).
+// Host-side orchestration of one engine call: H2D -> K1 mesh sort of both samples ->
+// tile list -> K2 counting kernel -> D2H of the (tiny) result.  Everything is issued on
+// one CUDA stream with stream-ordered allocations; the only host sync is the final one.
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <vector>
+
+#include "count.cuh"
+
+// ------------------------------------------------------------------ errors / globals
+static thread_local std::string g_err;
+static thread_local cudaStream_t g_user_stream = nullptr;
+static thread_local bool g_have_user_stream = false;
+static cudaStream_t g_lib_stream[64] = {nullptr};
+
+void htb_set_error(const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+
+extern "C" const char *htb_last_error(void) { return g_err.c_str(); }
+extern "C" int htb_abi_version(void) { return HTB_ABI_VERSION; }
+extern "C" int htb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+extern "C" int htb_set_device(int device)
+{
+    HTB_CUDA(cudaSetDevice(device));
+    return 0;
+}
+extern "C" int htb_set_stream(void *s)
+{
+    g_user_stream = (cudaStream_t)s;
+    g_have_user_stream = (s != nullptr);
+    return 0;
+}
+
+static int get_stream(cudaStream_t *out)
+{
+    if (g_have_user_stream) { *out = g_user_stream; return 0; }
+    int dev = 0;
+    HTB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) { htb_set_error("device index %d out of range", dev); return 1; }
+    if (!g_lib_stream[dev]) {
+        HTB_CUDA(cudaStreamCreateWithFlags(&g_lib_stream[dev], cudaStreamNonBlocking));
+        // keep freed blocks cached in the stream-ordered pool between calls
+        cudaMemPool_t pool;
+        HTB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+        uint64_t thresh = UINT64_MAX;
+        HTB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    }
+    *out = g_lib_stream[dev];
+    return 0;
+}
+
+int Workspace::alloc(void **p, size_t bytes)
+{
+    if (nptrs >= 256) { htb_set_error("workspace pointer table full"); return 1; }
+    if (bytes == 0) bytes = 16;
+    bytes = (bytes + 255) & ~(size_t)255;
+    cudaError_t e = cudaMallocAsync(p, bytes, st);
+    if (e != cudaSuccess) {
+        htb_set_error("cudaMallocAsync(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        return 1;
+    }
+    ptrs[nptrs++] = *p;
+    return 0;
+}
+void Workspace::release()
+{
+    for (int i = nptrs - 1; i >= 0; --i) cudaFreeAsync(ptrs[i], st);
+    nptrs = 0;
+}
+
+// ------------------------------------------------------------------ refinement heuristics
+static void env_triplet(const char *name, int *m, int dim)
+{
+    const char *e = getenv(name);
+    if (!e) return;
+    int a = 0, b = 0, c = 0;
+    int k = sscanf(e, "%d,%d,%d", &a, &b, &c);
+    int v[3] = {a, k > 1 ? b : a, k > 2 ? c : (k > 1 ? b : a)};
+    for (int d = 0; d < dim; ++d) if (v[d] >= 1 && v[d] <= 64) m[d] = v[d];
+}
+
+static int64_t cell_budget(int64_t n)
+{
+    int64_t b = 2 * n;
+    if (b < (1 << 16)) b = 1 << 16;
+    if (b > (1 << 25)) b = 1 << 25;
+    return b;
+}
+
+static int clampi(double v, int lo, int hi)
+{
+    if (!(v > lo)) return lo;
+    if (v > hi) return hi;
+    return (int)v;
+}
+
+static void choose_refinement(const htb_mesh_geom *g, int64_t n1, int64_t n2, int *m1, int *m2)
+{
+    const int dim = g->ndim, F = dim - 1, S = dim - 1;
+    double vol = 1.0;
+    for (int d = 0; d < dim; ++d) vol *= g->period[d];
+    const double dens1 = (double)(n1 > 0 ? n1 : 1) / vol, dens2 = (double)(n2 > 0 ? n2 : 1) / vol;
+    // sample1: a tile (HTB_TILE points) should be roughly a cube / square
+    const double side = pow((double)HTB_TILE / dens1, 1.0 / dim);
+    for (int d = 0; d < dim; ++d) {
+        if (d == F) m1[d] = clampi(floor(4.0 * g->cell1_size[d] / side + 0.5), 1, 16);
+        else m1[d] = clampi(floor(g->cell1_size[d] / side + 0.5), 1, 8);
+    }
+    // sample2: columns fine enough to prune, coarse enough that a span holds >= ~128 points
+    double colarea = 1.0;
+    for (int d = 0; d < S; ++d) colarea *= g->cell2_size[d];
+    const double span = dens2 * colarea * 1.6 * g->search[F];
+    const double scale = pow(span / 128.0, 1.0 / (S > 0 ? S : 1));
+    for (int d = 0; d < S; ++d) {
+        const int cap = clampi(floor(4.0 * g->cell2_size[d] / g->search[d] + 0.5), 1, 8);
+        m2[d] = clampi(floor(scale), 1, cap);
+    }
+    m2[F] = clampi(floor(8.0 * g->cell2_size[F] / g->search[F] + 0.5), 1, 16);
+    // respect the cell budgets
+    for (int which = 0; which < 2; ++which) {
+        int *m = which ? m2 : m1;
+        const int32_t *nd = which ? g->ndivs2 : g->ndivs1;
+        const int64_t budget = cell_budget(which ? n2 : n1);
+        while (true) {
+            int64_t nc = 1;
+            for (int d = 0; d < dim; ++d) nc *= (int64_t)nd[d] * m[d];
+            if (nc <= budget) break;
+            if (m[F] > 1) { m[F] = (m[F] + 1) / 2; continue; }
+            int big = 0;
+            for (int d = 0; d < S; ++d) if (m[d] > m[big]) big = d;
+            if (m[big] > 1) { m[big] -= 1; continue; }
+            break;
+        }
+    }
+    env_triplet("HTB_M1", m1, dim);
+    env_triplet("HTB_M2", m2, dim);
+}
+
+static FineGrid make_grid(const htb_mesh_geom *g, int which, const int *m)
+{
+    FineGrid f{};
+    f.dim = g->ndim;
+    f.ncells = 1;
+    for (int d = 0; d < g->ndim; ++d) {
+        f.nd[d] = which ? g->ndivs2[d] : g->ndivs1[d];
+        f.m[d] = m[d];
+        f.nf[d] = f.nd[d] * m[d];
+        f.cs[d] = which ? g->cell2_size[d] : g->cell1_size[d];
+        f.h[d] = f.cs[d] / m[d];
+        f.period[d] = g->period[d];
+        f.ncells *= f.nf[d];
+    }
+    for (int d = g->ndim; d < 3; ++d) { f.nd[d] = 1; f.m[d] = 1; f.nf[d] = 1; f.cs[d] = 1; f.h[d] = 1; f.period[d] = 1; }
+    return f;
+}
+
+// ------------------------------------------------------------------ one engine call
+struct Call {
+    cudaStream_t st = nullptr;
+    Workspace ws;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    int launches = 0;
+    WalkGeom G{};
+    WalkArrays A{};
+    SortedSample s1, s2;
+    int m1[3] = {1, 1, 1}, m2[3] = {1, 1, 1};
+    unsigned int *ctr = nullptr;          // [0] tile counter, [1] tiles redone, [2..3] pairs evaluated (u64)
+    int64_t max_tiles = 0;
+    uint32_t flags = 0;
+
+    ~Call()
+    {
+        ws.release();
+        for (int i = 0; i < 5; ++i) if (ev[i]) cudaEventDestroy(ev[i]);
+    }
+    int begin()
+    {
+        if (get_stream(&st)) return 1;
+        ws.st = st;
+        for (int i = 0; i < 5; ++i) HTB_CUDA(cudaEventCreate(&ev[i]));
+        HTB_CUDA(cudaEventRecord(ev[0], st));
+        return 0;
+    }
+    // bring `cnt` arrays of n elements (common element stride) to the device; returns device pointers + stride
+    int stage_coords(const double *const *src, int cnt, int64_t stride, int64_t n, const double **dst, int64_t *dstride)
+    {
+        if (flags & HTB_FLAG_DEVICE_INPUT) {
+            for (int k = 0; k < cnt; ++k) dst[k] = src[k];
+            *dstride = stride;
+            return 0;
+        }
+        if (n <= 0) { for (int k = 0; k < cnt; ++k) dst[k] = nullptr; *dstride = 1; return 0; }
+        bool interleaved = (stride == cnt);
+        for (int k = 1; k < cnt && interleaved; ++k) interleaved = (src[k] == src[0] + k);
+        if (interleaved && cnt > 1) {
+            double *buf = nullptr;
+            if (ws.alloc((void **)&buf, sizeof(double) * (size_t)n * cnt)) return 1;
+            HTB_CUDA(cudaMemcpyAsync(buf, src[0], sizeof(double) * (size_t)n * cnt, cudaMemcpyHostToDevice, st));
+            for (int k = 0; k < cnt; ++k) dst[k] = buf + k;
+            *dstride = cnt;
+            return 0;
+        }
+        for (int k = 0; k < cnt; ++k) {
+            double *buf = nullptr;
+            if (ws.alloc((void **)&buf, sizeof(double) * (size_t)n)) return 1;
+            if (stride == 1)
+                HTB_CUDA(cudaMemcpyAsync(buf, src[k], sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
+            else
+                HTB_CUDA(cudaMemcpy2DAsync(buf, sizeof(double), src[k], sizeof(double) * (size_t)stride, sizeof(double),
+                                           (size_t)n, cudaMemcpyHostToDevice, st));
+            dst[k] = buf;
+        }
+        *dstride = 1;
+        return 0;
+    }
+    int stage_rows(const double *src, int64_t n, int nw, const double **dst)
+    {
+        if (!src) { *dst = nullptr; return 0; }
+        if (flags & HTB_FLAG_DEVICE_INPUT) { *dst = src; return 0; }
+        double *buf = nullptr;
+        if (ws.alloc((void **)&buf, sizeof(double) * (size_t)(n > 0 ? n : 1) * nw)) return 1;
+        if (n > 0) HTB_CUDA(cudaMemcpyAsync(buf, src, sizeof(double) * (size_t)n * nw, cudaMemcpyHostToDevice, st));
+        *dst = buf;
+        return 0;
+    }
+    // full set-up: upload, sort both samples, tile list, walker geometry
+    int setup(const htb_mesh_geom *g, int sphere,
+              const double *const *c1, int64_t stride1, int64_t n1, const double *w1,
+              const double *const *c2, int64_t stride2, int64_t n2, const double *w2, int nw,
+              bool perm1, int64_t first_cell1, int64_t last_cell1, uint32_t fl)
+    {
+        flags = fl;
+        const int dim = g->ndim;
+        if (dim != 2 && dim != 3) { htb_set_error("mesh->ndim must be 2 or 3"); return 1; }
+        if (n1 < 0 || n2 < 0 || n1 > 2000000000LL || n2 > 2000000000LL) { htb_set_error("sample sizes must be in [0, 2e9]"); return 1; }
+        for (int d = 0; d < dim; ++d) {
+            if (g->ndivs1[d] < 1 || g->ndivs2[d] < g->ndivs1[d] || g->ndivs2[d] % g->ndivs1[d] != 0 || g->cover[d] < 0 ||
+                !(g->period[d] > 0) || !(g->cell1_size[d] > 0) || !(g->cell2_size[d] > 0) || !(g->search[d] >= 0)) {
+                htb_set_error("inconsistent mesh geometry in dimension %d", d);
+                return 1;
+            }
+        }
+        // ---- inputs
+        const double *d1[3] = {nullptr, nullptr, nullptr}, *d2[3] = {nullptr, nullptr, nullptr};
+        int64_t ds1 = 1, ds2 = 1;
+        const double *dw1 = nullptr, *dw2 = nullptr;
+        bool same = (n1 == n2 && stride1 == stride2);
+        for (int d = 0; d < dim && same; ++d) same = (c1[d] == c2[d]);
+        if (stage_coords(c1, dim, stride1, n1, d1, &ds1)) return 1;
+        if (same) { for (int d = 0; d < dim; ++d) d2[d] = d1[d]; ds2 = ds1; }
+        else if (stage_coords(c2, dim, stride2, n2, d2, &ds2)) return 1;
+        if (stage_rows(w1, n1, nw, &dw1)) return 1;
+        if (w2 == w1 && same) dw2 = dw1;
+        else if (stage_rows(w2, n2, nw, &dw2)) return 1;
+        HTB_CUDA(cudaEventRecord(ev[1], st));
+        // ---- K1
+        choose_refinement(g, n1, n2, m1, m2);
+        const FineGrid g1 = make_grid(g, 0, m1), g2 = make_grid(g, 1, m2);
+        if (htb_sort_sample(st, ws, g1, d1, ds1, n1, dw1, nw, perm1, s1, &launches)) return 1;
+        if (htb_sort_sample(st, ws, g2, d2, ds2, n2, dw2, nw, false, s2, &launches)) return 1;
+        // ---- walker geometry
+        G.dim = dim;
+        G.pbc = g->pbc ? 1 : 0;
+        G.sphere = sphere;
+        G.nocull = (fl & HTB_FLAG_NO_CULL) ? 1 : 0;
+        double rslow = 0.0;
+        for (int d = 0; d < 3; ++d) {
+            const bool on = d < dim;
+            G.nd1[d] = on ? g->ndivs1[d] : 1;
+            G.nd2[d] = on ? g->ndivs2[d] : 1;
+            G.per[d] = on ? g->ndivs2[d] / g->ndivs1[d] : 1;
+            G.cover[d] = on ? g->cover[d] : 0;
+            G.m1[d] = on ? m1[d] : 1;
+            G.m2[d] = on ? m2[d] : 1;
+            G.nf1[d] = G.nd1[d] * G.m1[d];
+            G.nf2[d] = G.nd2[d] * G.m2[d];
+            G.period[d] = on ? g->period[d] : 1.0;
+            G.h2[d] = on ? g2.h[d] : 1.0;
+            G.slop[d] = on ? 1e-9 * g->period[d] : 0.0;
+            G.reach[d] = on ? g->search[d] : 0.0;
+            if (on && d < dim - 1 && g->search[d] > rslow) rslow = g->search[d];
+        }
+        if (sphere && g->search[dim - 1] > rslow) rslow = g->search[dim - 1];
+        G.r2slow = rslow * rslow * (1.0 + 1e-9);
+        // ---- tiles + counters
+        uint2 *tiles = nullptr;
+        uint32_t *ntiles_dev = nullptr;
+        if (htb_build_tiles(st, ws, G, s1, first_cell1, last_cell1, &tiles, &ntiles_dev, &max_tiles, &launches)) return 1;
+        if (ws.alloc((void **)&ctr, 64)) return 1;
+        HTB_CUDA(cudaMemsetAsync(ctr, 0, 64, st));
+        for (int d = 0; d < 3; ++d) { A.c1[d] = s1.c[d]; A.c2[d] = s2.c[d]; }
+        A.off1 = s1.off; A.off2 = s2.off;
+        A.pay1 = s1.w; A.pay2 = s2.w; A.nw = nw;
+        A.flags1 = s1.flags; A.flags2 = s2.flags;
+        A.tiles = tiles; A.ntiles_dev = ntiles_dev;
+        A.tile_counter = ctr;
+        A.tiles_redone = ctr + 1;
+        A.pairs_evaluated = (unsigned long long *)(ctr + 2);
+        HTB_CUDA(cudaEventRecord(ev[2], st));
+        return 0;
+    }
+    int finish(htb_stats *stats, int path)
+    {
+        HTB_CUDA(cudaEventRecord(ev[3], st));
+        unsigned int h[4] = {0, 0, 0, 0};
+        uint32_t ntiles = 0;
+        std::vector<double> work;
+        int64_t nc1 = 0;
+        if (stats) {
+            double *work_dev = nullptr;
+            if (htb_reference_work(st, ws, G, s1, s2, &work_dev, &nc1, &launches)) return 1;
+            work.resize((size_t)nc1);
+            HTB_CUDA(cudaMemcpyAsync(work.data(), work_dev, sizeof(double) * (size_t)nc1, cudaMemcpyDeviceToHost, st));
+            HTB_CUDA(cudaMemcpyAsync(h, ctr, sizeof(h), cudaMemcpyDeviceToHost, st));
+            HTB_CUDA(cudaMemcpyAsync(&ntiles, A.ntiles_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        }
+        HTB_CUDA(cudaEventRecord(ev[4], st));
+        HTB_CUDA(cudaStreamSynchronize(st));
+        if (stats) {
+            memset(stats, 0, sizeof(*stats));
+            unsigned long long pe;
+            memcpy(&pe, &h[2], sizeof(pe));
+            stats->pairs_evaluated = (double)pe;
+            double wr = 0.0;
+            for (int64_t c = 0; c < nc1; ++c) wr += work[(size_t)c];
+            stats->pairs_reference = wr;
+            cudaEventElapsedTime(&stats->ms_h2d, ev[0], ev[1]);
+            cudaEventElapsedTime(&stats->ms_mesh, ev[1], ev[2]);
+            cudaEventElapsedTime(&stats->ms_count, ev[2], ev[3]);
+            cudaEventElapsedTime(&stats->ms_total, ev[0], ev[4]);
+            stats->kernel_launches = launches;
+            stats->tiles = (int32_t)ntiles;
+            stats->tiles_redone = (int32_t)h[1];
+            for (int d = 0; d < 3; ++d) { stats->refine1[d] = m1[d]; stats->refine2[d] = m2[d]; }
+            stats->path = path;
+        }
+        return 0;
+    }
+};
+
+static bool finite_all(const double *v, int n)
+{
+    for (int i = 0; i < n; ++i) if (!std::isfinite(v[i])) return false;
+    return true;
+}
+
+static unsigned long long dbits(double v)
+{
+    unsigned long long b;
+    memcpy(&b, &v, sizeof(b));
+    return b;
+}
+
+static int upload(Call &c, const void *host, size_t bytes, void **dev)
+{
+    if (c.ws.alloc(dev, bytes)) return 1;
+    HTB_CUDA(cudaMemcpyAsync(*dev, host, bytes, cudaMemcpyHostToDevice, c.st));
+    return 0;
+}
+
+#define HTB_GUARD_BEGIN try {
+#define HTB_GUARD_END                                                          \
+    } catch (const std::exception &e) { htb_set_error("exception: %s", e.what()); return 1; }
+
+// ------------------------------------------------------------------ npairs_3d
+extern "C" int htb_npairs_3d_engine(const htb_mesh_geom *mesh,
+                                    const double *x1, const double *y1, const double *z1, int64_t stride1, int64_t n1,
+                                    const double *x2, const double *y2, const double *z2, int64_t stride2, int64_t n2,
+                                    const double *rbins, int32_t nb, int64_t first_cell1, int64_t last_cell1,
+                                    int64_t *counts_out, uint32_t flags, htb_stats *stats)
+{
+    HTB_GUARD_BEGIN
+    if (!mesh || !rbins || !counts_out || nb < 1) { htb_set_error("htb_npairs_3d_engine: bad arguments"); return 1; }
+    if (mesh->ndim != 3) { htb_set_error("htb_npairs_3d_engine needs a 3-d mesh"); return 1; }
+    Call c;
+    if (c.begin()) return 1;
+    const double *c1[3] = {x1, y1, z1}, *c2[3] = {x2, y2, z2};
+    if (c.setup(mesh, 1, c1, stride1, n1, nullptr, c2, stride2, n2, nullptr, 0, false, first_cell1, last_cell1, flags)) return 1;
+    std::vector<double> rsq((size_t)nb);
+    for (int k = 0; k < nb; ++k) rsq[k] = rbins[k] * rbins[k];
+    // eligibility of the fast kernel: sane monotone edges whose 32-bit keys stay below 2^31
+    bool fast = !(flags & HTB_FLAG_GENERIC) && nb <= HTB_NBF && finite_all(rbins, nb) && rsq[nb - 1] < 1e290;
+    for (int k = 0; k + 1 < nb && fast; ++k) fast = rbins[k] >= 0.0 && rsq[k] <= rsq[k + 1];
+    if (fast && nb == 1) fast = rbins[0] >= 0.0;
+    Fast3Params fp{};
+    if (fast) {
+        fp.nb = nb;
+        fp.H_lo = (int)(dbits(rsq[0]) >> 32);
+        const unsigned long long base = (unsigned long long)(unsigned)fp.H_lo << 32;
+        fp.U_span = (unsigned)(dbits(rsq[nb - 1]) >> 32) - (unsigned)fp.H_lo;
+        const unsigned long long ktop = (dbits(rsq[nb - 1]) - base) >> 26;
+        if (ktop >= 0x7ffffff0ULL) fast = false;
+        const int pad = HTB_NBF - nb;
+        for (int s = 0; s < HTB_NBF; ++s) {
+            if (s < pad) { fp.F[s] = -1; fp.E[s] = 0; }
+            else {
+                fp.F[s] = (int)((dbits(rsq[s - pad]) - base) >> 26);
+                fp.E[s] = dbits(rsq[s - pad]);
+            }
+        }
+        fp.E_top = dbits(rsq[nb - 1]);
+    }
+    unsigned long long *counts_dev = nullptr;
+    if (c.ws.alloc((void **)&counts_dev, sizeof(unsigned long long) * (size_t)nb)) return 1;
+    HTB_CUDA(cudaMemsetAsync(counts_dev, 0, sizeof(unsigned long long) * (size_t)nb, c.st));
+    if (fast) {
+        fp.counts = counts_dev;
+        if (htb_launch_fast3(c.st, c.G, c.A, fp, &c.launches)) return 1;
+    } else {
+        GenParams gp{};
+        gp.n0 = nb; gp.n1 = 1; gp.nhist = nb;
+        void *e0 = nullptr;
+        if (upload(c, rsq.data(), sizeof(double) * (size_t)nb, &e0)) return 1;
+        gp.e0 = (const double *)e0;
+        gp.counts = counts_dev;
+        if (htb_launch_gen(c.st, 0, c.G, c.A, gp, &c.launches)) return 1;
+    }
+    HTB_CUDA(cudaMemcpyAsync(counts_out, counts_dev, sizeof(int64_t) * (size_t)nb, cudaMemcpyDeviceToHost, c.st));
+    return c.finish(stats, fast ? 1 : 0);
+    HTB_GUARD_END
+}
+
+// ------------------------------------------------------------------ npairs_xy_z
+extern "C" int htb_npairs_xy_z_engine(const htb_mesh_geom *mesh,
+                                      const double *x1, const double *y1, const double *z1, int64_t stride1, int64_t n1,
+                                      const double *x2, const double *y2, const double *z2, int64_t stride2, int64_t n2,
+                                      const double *rp_bins, int32_t nrp, const double *pi_bins, int32_t npi,
+                                      int64_t first_cell1, int64_t last_cell1,
+                                      int64_t *counts_out, uint32_t flags, htb_stats *stats)
+{
+    HTB_GUARD_BEGIN
+    if (!mesh || !rp_bins || !pi_bins || !counts_out || nrp < 1 || npi < 1) { htb_set_error("htb_npairs_xy_z_engine: bad arguments"); return 1; }
+    if (mesh->ndim != 3) { htb_set_error("htb_npairs_xy_z_engine needs a 3-d mesh"); return 1; }
+    Call c;
+    if (c.begin()) return 1;
+    const double *c1[3] = {x1, y1, z1}, *c2[3] = {x2, y2, z2};
+    if (c.setup(mesh, 0, c1, stride1, n1, nullptr, c2, stride2, n2, nullptr, 0, false, first_cell1, last_cell1, flags)) return 1;
+    std::vector<double> e((size_t)nrp + npi);
+    for (int k = 0; k < nrp; ++k) e[k] = rp_bins[k] * rp_bins[k];
+    for (int k = 0; k < npi; ++k) e[nrp + k] = pi_bins[k] * pi_bins[k];
+    void *edev = nullptr;
+    if (upload(c, e.data(), sizeof(double) * e.size(), &edev)) return 1;
+    const int nh = nrp * npi;
+    unsigned long long *counts_dev = nullptr;
+    if (c.ws.alloc((void **)&counts_dev, sizeof(unsigned long long) * (size_t)nh)) return 1;
+    HTB_CUDA(cudaMemsetAsync(counts_dev, 0, sizeof(unsigned long long) * (size_t)nh, c.st));
+    GenParams gp{};
+    gp.n0 = nrp; gp.n1 = npi; gp.nhist = nh;
+    gp.e0 = (const double *)edev; gp.e1 = (const double *)edev + nrp;
+    gp.counts = counts_dev;
+    if (htb_launch_gen(c.st, 1, c.G, c.A, gp, &c.launches)) return 1;
+    HTB_CUDA(cudaMemcpyAsync(counts_out, counts_dev, sizeof(int64_t) * (size_t)nh, cudaMemcpyDeviceToHost, c.st));
+    return c.finish(stats, 0);
+    HTB_GUARD_END
+}
+
+// ------------------------------------------------------------------ npairs_s_mu
+extern "C" int htb_npairs_s_mu_engine(const htb_mesh_geom *mesh,
+                                      const double *x1, const double *y1, const double *z1, int64_t stride1, int64_t n1,
+                                      const double *x2, const double *y2, const double *z2, int64_t stride2, int64_t n2,
+                                      const double *s_bins, int32_t ns, const double *mu_bins, int32_t nmu,
+                                      int64_t first_cell1, int64_t last_cell1,
+                                      int64_t *counts_out, uint32_t flags, htb_stats *stats)
+{
+    HTB_GUARD_BEGIN
+    if (!mesh || !s_bins || !mu_bins || !counts_out || ns < 1 || nmu < 1) { htb_set_error("htb_npairs_s_mu_engine: bad arguments"); return 1; }
+    if (mesh->ndim != 3) { htb_set_error("htb_npairs_s_mu_engine needs a 3-d mesh"); return 1; }
+    Call c;
+    if (c.begin()) return 1;
+    const double *c1[3] = {x1, y1, z1}, *c2[3] = {x2, y2, z2};
+    if (c.setup(mesh, 1, c1, stride1, n1, nullptr, c2, stride2, n2, nullptr, 0, false, first_cell1, last_cell1, flags)) return 1;
+    std::vector<double> e((size_t)ns + nmu);
+    double m0 = -INFINITY, m1 = -INFINITY;
+    for (int k = 0; k < ns; ++k) { e[k] = s_bins[k] * s_bins[k]; if (e[k] > m0) m0 = e[k]; }
+    for (int k = 0; k < nmu; ++k) { e[ns + k] = mu_bins[k] * mu_bins[k]; if (e[ns + k] > m1) m1 = e[ns + k]; }
+    void *edev = nullptr;
+    if (upload(c, e.data(), sizeof(double) * e.size(), &edev)) return 1;
+    const int nh = ns * nmu;
+    unsigned long long *counts_dev = nullptr;
+    if (c.ws.alloc((void **)&counts_dev, sizeof(unsigned long long) * (size_t)nh)) return 1;
+    HTB_CUDA(cudaMemsetAsync(counts_dev, 0, sizeof(unsigned long long) * (size_t)nh, c.st));
+    GenParams gp{};
+    gp.n0 = ns; gp.n1 = nmu; gp.nhist = nh;
+    gp.e0 = (const double *)edev; gp.e1 = (const double *)edev + ns;
+    gp.max0 = m0; gp.max1 = m1;
+    gp.counts = counts_dev;
+    if (htb_launch_gen(c.st, 2, c.G, c.A, gp, &c.launches)) return 1;
+    std::vector<long long> diff((size_t)nh);
+    HTB_CUDA(cudaMemcpyAsync(diff.data(), counts_dev, sizeof(int64_t) * (size_t)nh, cudaMemcpyDeviceToHost, c.st));
+    if (c.finish(stats, 0)) return 1;
+    // 2-D inclusive prefix sums (npairs_s_mu_engine.pyx:232-234) over the tiny histogram
+    for (int k = 0; k < ns; ++k)
+        for (int g = 0; g < nmu; ++g) {
+            long long s = diff[(size_t)k * nmu + g];
+            if (k > 0) s += counts_out[(size_t)(k - 1) * nmu + g];
+            if (g > 0) s += counts_out[(size_t)k * nmu + g - 1];
+            if (k > 0 && g > 0) s -= counts_out[(size_t)(k - 1) * nmu + g - 1];
+            counts_out[(size_t)k * nmu + g] = s;
+        }
+    return 0;
+    HTB_GUARD_END
+}
+
+// ------------------------------------------------------------------ marked_npairs_3d
+extern "C" int htb_marked_npairs_3d_engine(const htb_mesh_geom *mesh,
+                                           const double *x1, const double *y1, const double *z1, int64_t stride1, int64_t n1,
+                                           const double *x2, const double *y2, const double *z2, int64_t stride2, int64_t n2,
+                                           const double *w1, const double *w2, int32_t nw, int32_t weight_func_id,
+                                           const double *rbins, int32_t nb, int64_t first_cell1, int64_t last_cell1,
+                                           double *counts_out, uint32_t flags, htb_stats *stats)
+{
+    HTB_GUARD_BEGIN
+    if (!mesh || !rbins || !counts_out || nb < 1 || !w1 || !w2) { htb_set_error("htb_marked_npairs_3d_engine: bad arguments"); return 1; }
+    if (mesh->ndim != 3) { htb_set_error("htb_marked_npairs_3d_engine needs a 3-d mesh"); return 1; }
+    if (nw < 1 || nw > HTB_MAX_NW) { htb_set_error("weights per point must be in [1, %d]", HTB_MAX_NW); return 1; }
+    if (weight_func_id < 0 || weight_func_id > 17) { htb_set_error("marking function does not exist, id=%d", weight_func_id); return 1; }
+    Call c;
+    if (c.begin()) return 1;
+    const double *c1[3] = {x1, y1, z1}, *c2[3] = {x2, y2, z2};
+    if (c.setup(mesh, 1, c1, stride1, n1, w1, c2, stride2, n2, w2, nw, false, first_cell1, last_cell1, flags)) return 1;
+    std::vector<double> rsq((size_t)nb);
+    for (int k = 0; k < nb; ++k) rsq[k] = rbins[k] * rbins[k];
+    void *edev = nullptr;
+    if (upload(c, rsq.data(), sizeof(double) * (size_t)nb, &edev)) return 1;
+    double *counts_dev = nullptr;
+    if (c.ws.alloc((void **)&counts_dev, sizeof(double) * (size_t)nb)) return 1;
+    HTB_CUDA(cudaMemsetAsync(counts_dev, 0, sizeof(double) * (size_t)nb, c.st));
+    GenParams gp{};
+    gp.n0 = nb; gp.n1 = 1; gp.nhist = nb; gp.nw = nw; gp.wfunc = weight_func_id;
+    gp.e0 = (const double *)edev;
+    gp.fcounts = counts_dev;
+    if (htb_launch_gen(c.st, 3, c.G, c.A, gp, &c.launches)) return 1;
+    HTB_CUDA(cudaMemcpyAsync(counts_out, counts_dev, sizeof(double) * (size_t)nb, cudaMemcpyDeviceToHost, c.st));
+    return c.finish(stats, 0);
+    HTB_GUARD_END
+}
+
+// ------------------------------------------------------------------ mean_delta_sigma
+extern "C" int htb_mean_delta_sigma_engine(const htb_mesh_geom *mesh,
+                                           const double *x1, const double *y1, int64_t stride1, int64_t n1,
+                                           const double *x2, const double *y2, int64_t stride2, const double *m2, int64_t n2,
+                                           const double *rp_bins, int32_t nrp, int64_t first_cell1, int64_t last_cell1,
+                                           double *out, uint32_t flags, htb_stats *stats)
+{
+    HTB_GUARD_BEGIN
+    if (!mesh || !rp_bins || !out || nrp < 2 || !m2) { htb_set_error("htb_mean_delta_sigma_engine: bad arguments"); return 1; }
+    if (mesh->ndim != 2) { htb_set_error("htb_mean_delta_sigma_engine needs a 2-d mesh"); return 1; }
+    Call c;
+    if (c.begin()) return 1;
+    const double *c1[3] = {x1, y1, nullptr}, *c2[3] = {x2, y2, nullptr};
+    if (c.setup(mesh, 1, c1, stride1, n1, nullptr, c2, stride2, n2, m2, 1, true, first_cell1, last_cell1, flags)) return 1;
+    const int nbin = nrp - 1;
+    std::vector<double> e((size_t)nrp + nbin);
+    for (int k = 0; k < nrp; ++k) e[k] = rp_bins[k] * rp_bins[k];
+    for (int k = 0; k < nbin; ++k) e[nrp + k] = log(rp_bins[k + 1] / rp_bins[k]);
+    void *edev = nullptr;
+    if (upload(c, e.data(), sizeof(double) * e.size(), &edev)) return 1;
+    double *out_dev = nullptr;
+    const size_t nout = (size_t)(n1 > 0 ? n1 : 1) * nbin;
+    if (c.ws.alloc((void **)&out_dev, sizeof(double) * nout)) return 1;
+    HTB_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(double) * nout, c.st));
+    GenParams gp{};
+    gp.n0 = nrp; gp.n1 = nbin; gp.nhist = 0; gp.nw = 1;
+    gp.e0 = (const double *)edev; gp.e1 = (const double *)edev + nrp;
+    gp.fcounts = out_dev;
+    gp.perm1 = c.s1.perm;
+    if (htb_launch_gen(c.st, 4, c.G, c.A, gp, &c.launches)) return 1;
+    if (n1 > 0) HTB_CUDA(cudaMemcpyAsync(out, out_dev, sizeof(double) * (size_t)n1 * nbin, cudaMemcpyDeviceToHost, c.st));
+    return c.finish(stats, 0);
+    HTB_GUARD_END
+}
+
+// ------------------------------------------------------------------ mesh-only entry points
+extern "C" int htb_mesh_cell_ids(int32_t ndim, const double *x, const double *y, const double *z, int64_t stride, int64_t n,
+                                 const double *cell_size, const int32_t *ndivs, int64_t *ids_out, uint32_t flags)
+{
+    HTB_GUARD_BEGIN
+    if ((ndim != 2 && ndim != 3) || !cell_size || !ndivs || !ids_out) { htb_set_error("htb_mesh_cell_ids: bad arguments"); return 1; }
+    Call c;
+    if (c.begin()) return 1;
+    c.flags = flags;
+    const double *src[3] = {x, y, z}, *dev[3] = {nullptr, nullptr, nullptr};
+    int64_t ds = 1;
+    if (c.stage_coords(src, ndim, stride, n, dev, &ds)) return 1;
+    int64_t *ids = nullptr;
+    if (c.ws.alloc((void **)&ids, sizeof(int64_t) * (size_t)(n > 0 ? n : 1))) return 1;
+    int nd[3] = {ndivs[0], ndivs[1], ndim == 3 ? ndivs[2] : 1};
+    if (htb_ref_cell_ids(c.st, ndim, dev, ds, n, cell_size, nd, ids, &c.launches)) return 1;
+    if (n > 0) HTB_CUDA(cudaMemcpyAsync(ids_out, ids, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, c.st));
+    HTB_CUDA(cudaStreamSynchronize(c.st));
+    return 0;
+    HTB_GUARD_END
+}
+
+extern "C" int htb_mesh_cell_id_indices(int32_t ndim, const double *x, const double *y, const double *z, int64_t stride,
+                                        int64_t n, const double *cell_size, const int32_t *ndivs,
+                                        int64_t *out, uint32_t flags)
+{
+    HTB_GUARD_BEGIN
+    if ((ndim != 2 && ndim != 3) || !cell_size || !ndivs || !out) { htb_set_error("htb_mesh_cell_id_indices: bad arguments"); return 1; }
+    Call c;
+    if (c.begin()) return 1;
+    c.flags = flags;
+    const double *src[3] = {x, y, z}, *dev[3] = {nullptr, nullptr, nullptr};
+    int64_t ds = 1;
+    if (c.stage_coords(src, ndim, stride, n, dev, &ds)) return 1;
+    FineGrid f{};
+    f.dim = ndim;
+    f.ncells = 1;
+    for (int d = 0; d < 3; ++d) {
+        const bool on = d < ndim;
+        f.nd[d] = on ? ndivs[d] : 1; f.m[d] = 1; f.nf[d] = f.nd[d];
+        f.cs[d] = on ? cell_size[d] : 1.0; f.h[d] = f.cs[d];
+        f.period[d] = f.cs[d] * f.nd[d];
+        f.ncells *= f.nf[d];
+    }
+    SortedSample s;
+    if (htb_sort_sample(c.st, c.ws, f, dev, ds, n, nullptr, 0, false, s, &c.launches)) return 1;
+    std::vector<uint32_t> off((size_t)f.ncells + 1);
+    HTB_CUDA(cudaMemcpyAsync(off.data(), s.off, sizeof(uint32_t) * off.size(), cudaMemcpyDeviceToHost, c.st));
+    HTB_CUDA(cudaStreamSynchronize(c.st));
+    for (size_t i = 0; i < off.size(); ++i) out[i] = (int64_t)off[i];
+    return 0;
+    HTB_GUARD_END
+}
+
+extern "C" int htb_cell1_work(const htb_mesh_geom *mesh,
+                              const double *x1, const double *y1, const double *z1, int64_t stride1, int64_t n1,
+                              const double *x2, const double *y2, const double *z2, int64_t stride2, int64_t n2,
+                              double *work_out, uint32_t flags)
+{
+    HTB_GUARD_BEGIN
+    if (!mesh || !work_out) { htb_set_error("htb_cell1_work: bad arguments"); return 1; }
+    Call c;
+    if (c.begin()) return 1;
+    const double *c1[3] = {x1, y1, z1}, *c2[3] = {x2, y2, z2};
+    if (c.setup(mesh, 1, c1, stride1, n1, nullptr, c2, stride2, n2, nullptr, 0, false, 0, 0, flags)) return 1;
+    double *work_dev = nullptr;
+    int64_t nc1 = 0;
+    if (htb_reference_work(c.st, c.ws, c.G, c.s1, c.s2, &work_dev, &nc1, &c.launches)) return 1;
+    HTB_CUDA(cudaMemcpyAsync(work_out, work_dev, sizeof(double) * (size_t)nc1, cudaMemcpyDeviceToHost, c.st));
+    HTB_CUDA(cudaStreamSynchronize(c.st));
+    return 0;
+    HTB_GUARD_END
+}
+
+// ------------------------------------------------------------------ FP64 issue-rate microbenchmark
+// 8 independent dependent-chains of alternating DADD / DMUL per thread, no FMA (compiled with
+// -fmad=false): measures the non-FMA FP64 instruction-lane rate the roofline is quoted against.
+__global__ void __launch_bounds__(256) k_fp64_rate(double *out, int iters, double a, double b)
+{
+    double v0 = a + threadIdx.x, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3, v4 = v0 + 4, v5 = v0 + 5, v6 = v0 + 6, v7 = v0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            v0 = v0 + a; v1 = v1 + a; v2 = v2 + a; v3 = v3 + a; v4 = v4 + a; v5 = v5 + a; v6 = v6 + a; v7 = v7 + a;
+            v0 = v0 * b; v1 = v1 * b; v2 = v2 * b; v3 = v3 * b; v4 = v4 * b; v5 = v5 * b; v6 = v6 * b; v7 = v7 * b;
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((v0 + v1) + (v2 + v3)) + ((v4 + v5) + (v6 + v7));
+}
+
+extern "C" int htb_measure_fp64_rate(double *ops_per_second_out, double *sm_clock_mhz_out)
+{
+    HTB_GUARD_BEGIN
+    cudaStream_t st;
+    if (get_stream(&st)) return 1;
+    int dev = 0, sms = 0, clk = 0;
+    HTB_CUDA(cudaGetDevice(&dev));
+    HTB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    HTB_CUDA(cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, dev));
+    const int blocks = sms * 8, threads = 256, iters = 4096;
+    double *buf = nullptr;
+    HTB_CUDA(cudaMalloc((void **)&buf, sizeof(double) * (size_t)blocks * threads));
+    cudaEvent_t e0, e1;
+    HTB_CUDA(cudaEventCreate(&e0));
+    HTB_CUDA(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        HTB_CUDA(cudaEventRecord(e0, st));
+        k_fp64_rate<<<blocks, threads, 0, st>>>(buf, iters, 1.0000001, 0.9999999);
+        HTB_CUDA(cudaEventRecord(e1, st));
+        HTB_CUDA(cudaStreamSynchronize(st));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double ops = (double)blocks * threads * (double)iters * 8.0 * 16.0;
+        const double rate = ops / (ms * 1e-3);
+        if (rep > 0 && rate > best) best = rate;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(buf);
+    if (ops_per_second_out) *ops_per_second_out = best;
+    if (sm_clock_mhz_out) *sm_clock_mhz_out = clk / 1000.0;
+    return 0;
+    HTB_GUARD_END
+}

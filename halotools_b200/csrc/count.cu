@@ -1,0 +1,678 @@
+// K2 — the cell-pair kernel family (sm_100a).  Every kernel is a persistent grid of
+// warps pulling sample1 tiles from an atomic queue and running walk_tile<V>() with a
+// variant functor V:
+//   Fast3    npairs_3d, <= 16 monotone bins: strict-IEEE f64 distance, integer-pipe range
+//            test on the raw bit pattern, in-range pairs pushed as 32-bit monotone keys to a
+//            per-lane shared-memory queue and binned later at full lane occupancy; tiles
+//            that saw a key equal to an edge key are re-evaluated with exact 64-bit compares.
+//   Gen3     npairs_3d literal top-down scan (any bins)          npairs_3d_engine.pyx:171-182
+//   GenXYZ   npairs_xy_z literal nested scans                    npairs_xy_z_engine.pyx:178-194
+//   GenSMU   npairs_s_mu (differential histogram)                npairs_s_mu_engine.pyx:196-229
+//   Marked3  marked_npairs_3d, 17 weight functions               marked_npairs_3d_engine.pyx:204-216
+//   DSigma   mean_delta_sigma per-object accumulators (2-D)      mean_delta_sigma_engine.pyx:162-180
+#include "walk.cuh"
+#include "count.cuh"
+
+// ------------------------------------------------------------------ tile list
+__global__ void k_seg_tiles(const uint32_t *__restrict__ off1, WalkGeom G, int64_t nseg,
+                            int64_t first_cell1, int64_t last_cell1, uint32_t *__restrict__ ntile)
+{
+    const int F = G.dim - 1;
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < nseg; s += (int64_t)gridDim.x * blockDim.x) {
+        // seg = slowlin * nd1[F] + a_fast
+        const int af = (int)(s % G.nd1[F]);
+        int64_t slow = s / G.nd1[F];
+        int fsl[2] = {0, 0};
+        for (int d = F - 1; d >= 0; --d) { fsl[d] = (int)(slow % G.nf1[d]); slow /= G.nf1[d]; }
+        int64_t rid = 0;
+        for (int d = 0; d < F; ++d) rid = rid * G.nd1[d] + fsl[d] / G.m1[d];
+        rid = rid * G.nd1[F] + af;
+        uint32_t nt = 0;
+        if (rid >= first_cell1 && rid < last_cell1) {
+            const int64_t c0 = (s / G.nd1[F]) * G.nf1[F] + (int64_t)af * G.m1[F];
+            const uint32_t cnt = off1[c0 + G.m1[F]] - off1[c0];
+            nt = (cnt + HTB_TILE - 1) / HTB_TILE;
+        }
+        ntile[s] = nt;
+    }
+}
+
+__global__ void k_fill_tiles(const uint32_t *__restrict__ off1, WalkGeom G, int64_t nseg,
+                             const uint32_t *__restrict__ ntile, const uint32_t *__restrict__ tbase,
+                             uint2 *__restrict__ tiles)
+{
+    const int F = G.dim - 1;
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < nseg; s += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t nt = ntile[s];
+        if (!nt) continue;
+        const int af = (int)(s % G.nd1[F]);
+        const int64_t c0 = (s / G.nd1[F]) * G.nf1[F] + (int64_t)af * G.m1[F];
+        const uint32_t st = off1[c0];
+        const uint32_t b = tbase[s];
+        for (uint32_t t = 0; t < nt; ++t) tiles[b + t] = make_uint2(st + t * HTB_TILE, (uint32_t)s);
+    }
+}
+
+// pairs the reference loop nest visits, per reference cell1 (W_ref)
+__global__ void k_wref(const uint32_t *__restrict__ rc1, const uint32_t *__restrict__ rc2, WalkGeom G,
+                       int64_t ncell1, double *__restrict__ work)
+{
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < ncell1; c += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t n1 = rc1[c];
+        double w = 0.0;
+        if (n1) {
+            int a[3] = {0, 0, 0};
+            int64_t rem = c;
+            for (int d = G.dim - 1; d >= 0; --d) { a[d] = (int)(rem % G.nd1[d]); rem /= G.nd1[d]; }
+            int lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1};
+            for (int d = 0; d < G.dim; ++d) { lo[d] = a[d] * G.per[d] - G.cover[d]; hi[d] = (a[d] + 1) * G.per[d] + G.cover[d]; }
+            unsigned long long s = 0;
+            for (int ux = lo[0]; ux < hi[0]; ++ux) {
+                const int wx = ux - floor_div(ux, G.nd2[0]) * G.nd2[0];
+                for (int uy = lo[1]; uy < hi[1]; ++uy) {
+                    const int wy = uy - floor_div(uy, G.nd2[1]) * G.nd2[1];
+                    if (G.dim == 2) { s += rc2[(int64_t)wx * G.nd2[1] + wy]; continue; }
+                    for (int uz = lo[2]; uz < hi[2]; ++uz) {
+                        const int wz = uz - floor_div(uz, G.nd2[2]) * G.nd2[2];
+                        s += rc2[((int64_t)wx * G.nd2[1] + wy) * G.nd2[2] + wz];
+                    }
+                }
+            }
+            w = (double)n1 * (double)s;
+        }
+        work[c] = w;
+    }
+}
+
+// ------------------------------------------------------------------ kernel skeleton
+template <class V>
+__global__ void __launch_bounds__(V::WARPS * 32, V::MINBLOCKS)
+k_count(const __grid_constant__ WalkGeom G, const __grid_constant__ WalkArrays A,
+        const __grid_constant__ typename V::Params P, const int scratch_bytes_per_warp)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int DIM = V::DIM;
+    constexpr int F = DIM - 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    typedef WarpSmem<DIM, V::NPAY> WS;
+    unsigned char *mine = smem_raw + (size_t)warp * (WS::bytes() + (size_t)scratch_bytes_per_warp);
+    WS S;
+    for (int s = 0; s < HTB_NSTAGE; ++s) S.stage[s] = (double *)mine + s * WS::stage_doubles();
+    unsigned char *bars = mine + sizeof(double) * HTB_NSTAGE * WS::stage_doubles();
+    for (int s = 0; s < HTB_NSTAGE; ++s) S.bar[s] = smem_u32(bars + 16 * s);
+    S.span = (uint32_t *)(bars + 16 * HTB_NSTAGE);
+    void *scratch = mine + WS::bytes();
+    if (V::TMA) {
+        if (lane == 0) {
+            for (int s = 0; s < HTB_NSTAGE; ++s) mbar_init(S.bar[s], 1);
+            mbar_fence_init();
+        }
+    }
+    __syncwarp();
+
+    V v(P, scratch, lane);
+    uint32_t gchunk = 0;
+    unsigned long long pairs = 0;
+    unsigned int redone = 0;
+    const int ntiles = A.ntiles_dev[0];
+
+    while (true) {
+        int t = 0;
+        if (lane == 0) t = (int)atomicAdd(A.tile_counter, 1u);
+        t = __shfl_sync(HTB_FULL, t, 0);
+        if (t >= ntiles) break;
+        const uint2 td = A.tiles[t];
+        const uint32_t start = td.x;
+        const int64_t seg = td.y;
+        int fs[3] = {0, 0, 0};
+        fs[F] = (int)(seg % G.nd1[F]);
+        int64_t slow = seg / G.nd1[F];
+        const int64_t c0 = slow * G.nf1[F] + (int64_t)fs[F] * G.m1[F];
+#pragma unroll
+        for (int d = F - 1; d >= 0; --d) { fs[d] = (int)(slow % G.nf1[d]); slow /= G.nf1[d]; }
+        const uint32_t segend = A.off1[c0 + G.m1[F]];
+        const int cnt = (int)min((uint32_t)HTB_TILE, segend - start);
+        // this lane's two points (index clamped for the bounding box; invalid ones get a far sentinel)
+        const bool v0 = lane < cnt, v1 = lane + 32 < cnt;
+        const uint32_t i0 = start + (uint32_t)min(lane, cnt - 1), i1 = start + (uint32_t)min(lane + 32, cnt - 1);
+        double p0[3] = {0, 0, 0}, p1[3] = {0, 0, 0}, blo[3] = {0, 0, 0}, bhi[3] = {0, 0, 0};
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) {
+            p0[d] = A.c1[d][i0];
+            p1[d] = A.c1[d][i1];
+            blo[d] = warp_min(fmin(p0[d], p1[d]));
+            bhi[d] = warp_max(fmax(p0[d], p1[d]));
+        }
+        if (!v0) p0[0] = 1.0e150;
+        if (!v1) p1[0] = 1.0e150;
+        v.tile_begin(p0, p1, v0, v1, i0, i1, A);
+        bool redo = false;
+        for (int pass = 0; pass < 2; ++pass) {
+            walk_tile<V>(v, G, A, S, gchunk, blo, bhi, fs, pairs, cnt);
+            redo = v.tile_end(A, i0, i1, pass);
+            if (!redo) break;
+            ++redone;
+        }
+    }
+    v.kernel_end();
+    if (lane == 0) {
+        if (pairs) atomicAdd(A.pairs_evaluated, pairs);
+        if (redone) atomicAdd(A.tiles_redone, redone);
+    }
+}
+
+// ------------------------------------------------------------------ Fast3
+#define QCAP 32
+struct Fast3 {
+    static constexpr int DIM = 3, NPAY = 0, WARPS = 8, MINBLOCKS = 2;
+    static constexpr bool TMA = true;
+    typedef Fast3Params Params;
+    const Params &P;
+    uint32_t qbase;             // shared-space address of this lane's queue column
+    uint32_t qptr;              // next free slot (qbase + 128 * entries)
+    int lane;
+    double x0, y0, z0, x1, y1, z1;
+    unsigned c[HTB_NBF];
+    unsigned clow;
+    bool dirty, exact;
+    unsigned long long tot;
+
+    static size_t scratch_bytes(const Params &) { return sizeof(uint32_t) * QCAP * 32; }
+
+    __device__ __forceinline__ Fast3(const Params &p, void *scratch, int ln) : P(p), lane(ln)
+    {
+        qbase = smem_u32(scratch) + 4u * (uint32_t)ln;
+        qptr = qbase;
+        tot = 0; dirty = false; exact = false; clow = 0;
+#pragma unroll
+        for (int s = 0; s < HTB_NBF; ++s) c[s] = 0;
+    }
+    __device__ __forceinline__ void tile_begin(const double (&p0)[3], const double (&p1)[3], bool, bool, uint32_t, uint32_t,
+                                               const WalkArrays &)
+    {
+        x0 = p0[0]; y0 = p0[1]; z0 = p0[2];
+        x1 = p1[0]; y1 = p1[1]; z1 = p1[2];
+        exact = false; dirty = false;
+    }
+    // top-down cumulative scan of one key over slots S, S-1, then recurse while any lane is still inside
+    template <int S>
+    __device__ __forceinline__ void levels(int key)
+    {
+        const bool in_a = key <= P.F[S];
+        dirty |= (key == P.F[S]);
+        c[S] += in_a ? 1u : 0u;
+        if (S >= 1) {
+            const bool in_b = key <= P.F[S >= 1 ? S - 1 : 0];
+            dirty |= (key == P.F[S >= 1 ? S - 1 : 0]);
+            c[S >= 1 ? S - 1 : 0] += in_b ? 1u : 0u;
+            if (S >= 2) {
+                if (__any_sync(HTB_FULL, in_b)) levels<(S >= 2 ? S - 2 : 0)>(key);
+            }
+        }
+    }
+    __device__ __forceinline__ void flush()
+    {
+        const int qn = (int)((qptr - qbase) >> 7);
+        const int maxn = __reduce_max_sync(HTB_FULL, qn);
+        for (int e = 0; e < maxn; ++e) {
+            const int key = (e < qn) ? (int)lds_u32(qbase + 128u * (uint32_t)e) : 0x7fffffff;
+            levels<HTB_NBF - 1>(key);
+        }
+        qptr = qbase;
+    }
+    __device__ __forceinline__ void pair_fast(double xs, double ys, double zs, double xj, double yj, double zj)
+    {
+        const double dx = xs - xj, dy = ys - yj, dz = zs - zj;
+        const double dsq = dx * dx + dy * dy + dz * dz;
+        const int u = __double2hiint(dsq) - P.H_lo;
+        clow += (unsigned)u >> 31;
+        if ((unsigned)u <= P.U_span) {
+            sts_u32(qptr, __funnelshift_r((unsigned)__double2loint(dsq), (unsigned)u, 26));
+            qptr += 128u;
+        }
+    }
+    __device__ __forceinline__ void pair_exact(double xs, double ys, double zs, double xj, double yj, double zj)
+    {
+        const double dx = xs - xj, dy = ys - yj, dz = zs - zj;
+        const double dsq = dx * dx + dy * dy + dz * dz;
+        const unsigned long long b = (unsigned long long)__double_as_longlong(dsq);
+        if (b <= P.E_top) {
+#pragma unroll
+            for (int s = 0; s < HTB_NBF; ++s) c[s] += (b <= P.E[s]) ? 1u : 0u;
+        }
+    }
+    __device__ __forceinline__ void chunk(uint32_t stage, int lo, int hi, uint32_t, const double (&sh)[3])
+    {
+        const uint32_t bx = stage, by = stage + 8 * HTB_CH, bz = stage + 16 * HTB_CH;
+        const double xs0 = x0 - sh[0], ys0 = y0 - sh[1], zs0 = z0 - sh[2];
+        const double xs1 = x1 - sh[0], ys1 = y1 - sh[1], zs1 = z1 - sh[2];
+        if (!exact) {
+            int j = lo;
+            if ((j & 1) && j < hi) {
+                const double xj = lds_f64(bx + 8 * j), yj = lds_f64(by + 8 * j), zj = lds_f64(bz + 8 * j);
+                pair_fast(xs0, ys0, zs0, xj, yj, zj);
+                pair_fast(xs1, ys1, zs1, xj, yj, zj);
+                ++j;
+            }
+            for (; j + 4 <= hi; j += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; u += 2) {
+                    double xa, xb, ya, yb, za, zb;
+                    lds_f64x2(bx + 8 * (j + u), xa, xb);
+                    lds_f64x2(by + 8 * (j + u), ya, yb);
+                    lds_f64x2(bz + 8 * (j + u), za, zb);
+                    pair_fast(xs0, ys0, zs0, xa, ya, za);
+                    pair_fast(xs1, ys1, zs1, xa, ya, za);
+                    pair_fast(xs0, ys0, zs0, xb, yb, zb);
+                    pair_fast(xs1, ys1, zs1, xb, yb, zb);
+                }
+                if (__any_sync(HTB_FULL, qptr > qbase + 128u * (QCAP - 8))) flush();
+            }
+            for (; j < hi; ++j) {
+                const double xj = lds_f64(bx + 8 * j), yj = lds_f64(by + 8 * j), zj = lds_f64(bz + 8 * j);
+                pair_fast(xs0, ys0, zs0, xj, yj, zj);
+                pair_fast(xs1, ys1, zs1, xj, yj, zj);
+            }
+            if (__any_sync(HTB_FULL, qptr > qbase + 128u * (QCAP - 8))) flush();
+        } else {
+            for (int j = lo; j < hi; ++j) {
+                const double xj = lds_f64(bx + 8 * j), yj = lds_f64(by + 8 * j), zj = lds_f64(bz + 8 * j);
+                pair_exact(xs0, ys0, zs0, xj, yj, zj);
+                pair_exact(xs1, ys1, zs1, xj, yj, zj);
+            }
+        }
+    }
+    __device__ __forceinline__ bool tile_end(const WalkArrays &, uint32_t, uint32_t, int pass)
+    {
+        if (!exact) {
+            flush();
+            if (__any_sync(HTB_FULL, dirty) && pass == 0) {
+                // a key collided with an edge key: throw the tile's counts away and redo it exactly
+#pragma unroll
+                for (int s = 0; s < HTB_NBF; ++s) c[s] = 0;
+                clow = 0; dirty = false; exact = true;
+                return true;
+            }
+        }
+        const unsigned low = __reduce_add_sync(HTB_FULL, clow);
+#pragma unroll
+        for (int s = 0; s < HTB_NBF; ++s) {
+            const unsigned r = __reduce_add_sync(HTB_FULL, c[s]);
+            if (lane == s) tot += (unsigned long long)r + low;
+            c[s] = 0;
+        }
+        clow = 0;
+        return false;
+    }
+    __device__ __forceinline__ void kernel_end()
+    {
+        const int k = lane - (HTB_NBF - P.nb);
+        if (lane < HTB_NBF && k >= 0 && tot) atomicAdd(P.counts + k, tot);
+    }
+};
+
+// ------------------------------------------------------------------ generic integer-count variants
+// per-warp u32 histogram in shared memory (scratch), flushed to the global u64 histogram per tile
+template <int KIND>   // 0: 3-D r   1: (rp, pi)   2: (s, mu) differential
+struct GenCount {
+    static constexpr int DIM = 3, NPAY = 0, WARPS = 8, MINBLOCKS = 2;
+    static constexpr bool TMA = true;
+    typedef GenParams Params;
+    const Params &P;
+    uint32_t *hist;
+    int lane;
+    double x0, y0, z0, x1, y1, z1;
+    bool v0, v1;
+
+    static size_t scratch_bytes(const Params &p) { return sizeof(uint32_t) * (size_t)((p.nhist + 3) & ~3); }
+
+    __device__ GenCount(const Params &p, void *scratch, int ln) : P(p), hist((uint32_t *)scratch), lane(ln)
+    {
+        for (int k = lane; k < P.nhist; k += 32) hist[k] = 0;
+        __syncwarp();
+    }
+    __device__ __forceinline__ void tile_begin(const double (&p0)[3], const double (&p1)[3], bool a, bool b, uint32_t, uint32_t,
+                                               const WalkArrays &)
+    {
+        x0 = p0[0]; y0 = p0[1]; z0 = p0[2];
+        x1 = p1[0]; y1 = p1[1]; z1 = p1[2];
+        v0 = a; v1 = b;
+    }
+    __device__ __forceinline__ void pair(bool valid, double xs, double ys, double zs, double xj, double yj, double zj)
+    {
+        const double dx = xs - xj, dy = ys - yj, dz = zs - zj;
+        if (KIND == 0) {
+            const double dsq = dx * dx + dy * dy + dz * dz;
+            bool alive = valid;
+            for (int k = P.n0 - 1; k >= 0; --k) {
+                alive = alive && (dsq <= P.e0[k]);
+                const unsigned b = __ballot_sync(HTB_FULL, alive);
+                if (!b) break;
+                if (lane == 0) hist[k] += __popc(b);
+            }
+        } else if (KIND == 1) {
+            const double dxy_sq = dx * dx + dy * dy;
+            const double dz_sq = dz * dz;
+            bool ak = valid;
+            for (int k = P.n0 - 1; k >= 0; --k) {
+                ak = ak && (dxy_sq <= P.e0[k]);
+                if (!__any_sync(HTB_FULL, ak)) break;
+                bool ag = ak;
+                for (int g = P.n1 - 1; g >= 0; --g) {
+                    ag = ag && (dz_sq <= P.e1[g]);
+                    const unsigned b = __ballot_sync(HTB_FULL, ag);
+                    if (!b) break;
+                    if (lane == 0) hist[k * P.n1 + g] += __popc(b);
+                }
+            }
+        } else {
+            const double dxy_sq = dx * dx + dy * dy;
+            const double dz_sq = dz * dz;
+            const double sqr_s = dz_sq + dxy_sq;
+            if (valid && !(sqr_s > P.max0)) {
+                double sqr_mu = 0.0;
+                if (sqr_s > 0.0) sqr_mu = dxy_sq / sqr_s;
+                if (!(sqr_mu > P.max1)) {
+                    int k = P.n0 - 2;
+                    while (k != -1) { if (sqr_s > P.e0[k]) break; --k; }
+                    int g = P.n1 - 2;
+                    while (g != -1) { if (sqr_mu > P.e1[g]) break; --g; }
+                    atomicAdd(&hist[(k + 1) * P.n1 + (g + 1)], 1u);
+                }
+            }
+        }
+    }
+    __device__ __forceinline__ void chunk(uint32_t stage, int lo, int hi, uint32_t, const double (&sh)[3])
+    {
+        const uint32_t bx = stage, by = stage + 8 * HTB_CH, bz = stage + 16 * HTB_CH;
+        const double xs0 = x0 - sh[0], ys0 = y0 - sh[1], zs0 = z0 - sh[2];
+        const double xs1 = x1 - sh[0], ys1 = y1 - sh[1], zs1 = z1 - sh[2];
+        for (int j = lo; j < hi; ++j) {
+            const double xj = lds_f64(bx + 8 * j), yj = lds_f64(by + 8 * j), zj = lds_f64(bz + 8 * j);
+            pair(v0, xs0, ys0, zs0, xj, yj, zj);
+            pair(v1, xs1, ys1, zs1, xj, yj, zj);
+        }
+    }
+    __device__ __forceinline__ bool tile_end(const WalkArrays &, uint32_t, uint32_t, int)
+    {
+        __syncwarp();
+        for (int k = lane; k < P.nhist; k += 32) {
+            const uint32_t h = hist[k];
+            if (h) { atomicAdd(P.counts + k, (unsigned long long)h); hist[k] = 0; }
+        }
+        __syncwarp();
+        return false;
+    }
+    __device__ __forceinline__ void kernel_end() {}
+};
+
+// ------------------------------------------------------------------ Marked3
+__device__ __forceinline__ double htb_pair_weight(int id, const double *w1, const double *w2)
+{
+    // marking_functions.pyx:14-217 (id 8 keeps the reference's '+', :106), custom_marking_func.pyx:12-16
+    double d;
+    switch (id) {
+    case 0: case 1: return w1[0] * w2[0];
+    case 2:  return w1[0] + w2[0];
+    case 3:  return (w1[0] == w2[0]) ? w1[1] * w2[1] : 0.0;
+    case 4:  return (w1[0] != w2[0]) ? w1[1] * w2[1] : 0.0;
+    case 5:  return (w2[0] > w1[0]) ? w1[1] * w2[1] : 0.0;
+    case 6:  return (w2[0] < w1[0]) ? w1[1] * w2[1] : 0.0;
+    case 7:  return (w2[0] > (w1[0] + w1[1])) ? w2[1] : 0.0;
+    case 8:  return (w2[0] < (w1[0] + w1[1])) ? w2[1] : 0.0;
+    case 9:  return (fabs(w1[0] - w2[0]) < w1[1]) ? w2[1] : 0.0;
+    case 10: return (fabs(w1[0] - w2[0]) > w1[1]) ? w2[1] : 0.0;
+    case 11: return (w2[0] > w1[0] * w1[1]) ? w2[1] : 0.0;
+    case 12: return w1[0] * w2[0] * (w1[1] * w2[1] + w1[2] * w2[2] + w1[3] * w2[3]);
+    case 13: d = (w1[1] * w2[1] + w1[2] * w2[2] + w1[3] * w2[3]); return w1[0] * w2[0] * d * d;
+    case 14: return w1[0] * w2[0] * (w1[1] * w2[1] + w1[2] * w2[2]);
+    case 15: d = (w1[1] * w2[1] + w1[2] * w2[2]); return w1[0] * w2[0] * d * d;
+    case 16: d = (w1[1] * w2[1] + w1[2] * w2[2] + w1[3] * w2[3]);
+             return (w1[4] == w2[4]) ? w1[0] * w2[0] * d * d : 0.0;
+    case 17: d = (w1[1] * w2[1] + w1[2] * w2[2] + w1[3] * w2[3]);
+             return (w1[4] != w2[4]) ? w1[0] * w2[0] * d * d : 0.0;
+    default: return 0.0;
+    }
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(HTB_FULL, v, o);
+    return v;
+}
+
+struct Marked3 {
+    static constexpr int DIM = 3, NPAY = HTB_MAX_NW, WARPS = 8, MINBLOCKS = 2;
+    static constexpr bool TMA = true;
+    typedef GenParams Params;
+    const Params &P;
+    double *hist;
+    int lane;
+    double x0, y0, z0, x1, y1, z1;
+    double wa[HTB_MAX_NW], wb[HTB_MAX_NW];
+    bool v0, v1;
+
+    static size_t scratch_bytes(const Params &p) { return sizeof(double) * (size_t)((p.nhist + 1) & ~1); }
+
+    __device__ Marked3(const Params &p, void *scratch, int ln) : P(p), hist((double *)scratch), lane(ln)
+    {
+        for (int k = lane; k < P.nhist; k += 32) hist[k] = 0.0;
+        __syncwarp();
+    }
+    __device__ __forceinline__ void tile_begin(const double (&p0)[3], const double (&p1)[3], bool a, bool b,
+                                               uint32_t i0, uint32_t i1, const WalkArrays &A)
+    {
+        x0 = p0[0]; y0 = p0[1]; z0 = p0[2];
+        x1 = p1[0]; y1 = p1[1]; z1 = p1[2];
+        v0 = a; v1 = b;
+#pragma unroll
+        for (int k = 0; k < HTB_MAX_NW; ++k) {
+            wa[k] = (k < A.nw) ? A.pay1[(size_t)i0 * A.nw + k] : 0.0;
+            wb[k] = (k < A.nw) ? A.pay1[(size_t)i1 * A.nw + k] : 0.0;
+        }
+    }
+    __device__ __forceinline__ void pair(bool valid, const double *w1, double xs, double ys, double zs,
+                                         double xj, double yj, double zj, uint32_t w2)
+    {
+        const double dx = xs - xj, dy = ys - yj, dz = zs - zj;
+        const double dsq = dx * dx + dy * dy + dz * dz;
+        bool alive = valid && (dsq <= P.e0[P.n0 - 1]);
+        if (!__any_sync(HTB_FULL, alive)) return;
+        double w2l[HTB_MAX_NW];
+#pragma unroll
+        for (int k = 0; k < HTB_MAX_NW; ++k) w2l[k] = (k < P.nw) ? lds_f64(w2 + 8 * k) : 0.0;
+        const double w = alive ? htb_pair_weight(P.wfunc, w1, w2l) : 0.0;
+        for (int k = P.n0 - 1; k >= 0; --k) {
+            alive = alive && (dsq <= P.e0[k]);
+            if (!__any_sync(HTB_FULL, alive)) break;
+            const double s = warp_sum(alive ? w : 0.0);
+            if (lane == 0) hist[k] += s;
+        }
+    }
+    __device__ __forceinline__ void chunk(uint32_t stage, int lo, int hi, uint32_t, const double (&sh)[3])
+    {
+        const uint32_t bx = stage, by = stage + 8 * HTB_CH, bz = stage + 16 * HTB_CH, bw = stage + 24 * HTB_CH;
+        const double xs0 = x0 - sh[0], ys0 = y0 - sh[1], zs0 = z0 - sh[2];
+        const double xs1 = x1 - sh[0], ys1 = y1 - sh[1], zs1 = z1 - sh[2];
+        for (int j = lo; j < hi; ++j) {
+            const double xj = lds_f64(bx + 8 * j), yj = lds_f64(by + 8 * j), zj = lds_f64(bz + 8 * j);
+            pair(v0, wa, xs0, ys0, zs0, xj, yj, zj, bw + 8 * j * P.nw);
+            pair(v1, wb, xs1, ys1, zs1, xj, yj, zj, bw + 8 * j * P.nw);
+        }
+    }
+    __device__ __forceinline__ bool tile_end(const WalkArrays &, uint32_t, uint32_t, int)
+    {
+        __syncwarp();
+        for (int k = lane; k < P.nhist; k += 32) {
+            const double h = hist[k];
+            if (h != 0.0) { atomicAdd(P.fcounts + k, h); hist[k] = 0.0; }
+        }
+        __syncwarp();
+        return false;
+    }
+    __device__ __forceinline__ void kernel_end() {}
+};
+
+// ------------------------------------------------------------------ DSigma (2-D, per-object accumulators)
+// scratch layout per warp: acc[slot][64], slot 0 = mass inside rp[0]; slots 1..nbin = mass in bin b
+// (differential); slots nbin+1..2*nbin = sum m*(1 - ln(rp[b+1]^2 / d^2)) over pairs in bin b.
+struct DSigma {
+    static constexpr int DIM = 2, NPAY = 1, WARPS = 4, MINBLOCKS = 2;
+    static constexpr bool TMA = true;
+    typedef GenParams Params;
+    const Params &P;
+    double *acc;
+    int lane;
+    double x0, y0, x1, y1;
+    bool v0, v1;
+
+    static size_t scratch_bytes(const Params &p) { return sizeof(double) * 64 * (size_t)(2 * (p.n0 - 1) + 1); }
+
+    __device__ DSigma(const Params &p, void *scratch, int ln) : P(p), acc((double *)scratch), lane(ln) {}
+    __device__ __forceinline__ void tile_begin(const double (&p0)[3], const double (&p1)[3], bool a, bool b, uint32_t, uint32_t,
+                                               const WalkArrays &)
+    {
+        x0 = p0[0]; y0 = p0[1]; x1 = p1[0]; y1 = p1[1];
+        v0 = a; v1 = b;
+        const int nslot = 2 * (P.n0 - 1) + 1;
+        for (int s = 0; s < nslot; ++s) { acc[s * 64 + lane] = 0.0; acc[s * 64 + 32 + lane] = 0.0; }
+        __syncwarp();
+    }
+    __device__ __forceinline__ void pair(bool valid, int col, double xs, double ys, double xj, double yj, double mj)
+    {
+        const double dx = xs - xj, dy = ys - yj;
+        const double dxy_sq = dx * dx + dy * dy;
+        const int nbin = P.n0 - 1;
+        if (valid && dxy_sq <= P.e0[nbin]) {
+            int k = nbin - 1;
+            while (k >= 0 && dxy_sq <= P.e0[k]) --k;      // pair lies in bin k (rp[k] < d <= rp[k+1]); k == -1: inside rp[0]
+            acc[(k + 1) * 64 + col] += mj;
+            if (k >= 0) acc[(nbin + 1 + k) * 64 + col] += mj * (1 - log(P.e0[k + 1] / dxy_sq));
+        }
+    }
+    __device__ __forceinline__ void chunk(uint32_t stage, int lo, int hi, uint32_t, const double (&sh)[3])
+    {
+        const uint32_t bx = stage, by = stage + 8 * HTB_CH, bm = stage + 16 * HTB_CH;
+        const double xs0 = x0 - sh[0], ys0 = y0 - sh[1];
+        const double xs1 = x1 - sh[0], ys1 = y1 - sh[1];
+        for (int j = lo; j < hi; ++j) {
+            const double xj = lds_f64(bx + 8 * j), yj = lds_f64(by + 8 * j), mj = lds_f64(bm + 8 * j);
+            pair(v0, lane, xs0, ys0, xj, yj, mj);
+            pair(v1, 32 + lane, xs1, ys1, xj, yj, mj);
+        }
+    }
+    __device__ __forceinline__ void finish(bool valid, int col, uint32_t isorted, const WalkArrays &A)
+    {
+        if (!valid) return;
+        const int nbin = P.n0 - 1;
+        const int64_t row = P.perm1 ? (int64_t)P.perm1[isorted] : (int64_t)isorted;
+        double inside = acc[col];
+        for (int k = 0; k < nbin; ++k) {
+            // sum_{pairs inside rp[k]} m * 2 * dlog[k]  -  sum_{pairs in bin k} m (1 - ln(rp[k+1]^2/d^2))
+            const double ds = inside * 2 * P.e1[k] - acc[(nbin + 1 + k) * 64 + col];
+            P.fcounts[row * nbin + k] = ds / (3.14159265358979323846 * (P.e0[k + 1] - P.e0[k]));
+            inside += acc[(k + 1) * 64 + col];
+        }
+    }
+    __device__ __forceinline__ bool tile_end(const WalkArrays &A, uint32_t i0, uint32_t i1, int)
+    {
+        __syncwarp();
+        finish(v0, lane, i0, A);
+        finish(v1, 32 + lane, i1, A);
+        __syncwarp();
+        return false;
+    }
+    __device__ __forceinline__ void kernel_end() {}
+};
+
+// ------------------------------------------------------------------ host launchers
+template <class V>
+static int launch_count(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const typename V::Params &P,
+                        int *launches)
+{
+    typedef WarpSmem<V::DIM, V::NPAY> WS;
+    const size_t scratch = (V::scratch_bytes(P) + 15) & ~(size_t)15;
+    const size_t smem = V::WARPS * (WS::bytes() + scratch);
+    if (smem > 200 * 1024) {
+        htb_set_error("too many bins for the shared-memory accumulators (%zu bytes of shared memory per block needed)", smem);
+        return 1;
+    }
+    HTB_CUDA(cudaFuncSetAttribute(k_count<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, sms = 0, per_sm = 0;
+    HTB_CUDA(cudaGetDevice(&dev));
+    HTB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    HTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_count<V>, V::WARPS * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    k_count<V><<<sms * per_sm, V::WARPS * 32, smem, st>>>(G, A, P, (int)scratch);
+    if (launches) *launches += 1;
+    HTB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int htb_launch_fast3(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const Fast3Params &P, int *l)
+{ return launch_count<Fast3>(st, G, A, P, l); }
+int htb_launch_gen(cudaStream_t st, int kind, const WalkGeom &G, const WalkArrays &A, const GenParams &P, int *l)
+{
+    switch (kind) {
+    case 0: return launch_count<GenCount<0>>(st, G, A, P, l);
+    case 1: return launch_count<GenCount<1>>(st, G, A, P, l);
+    case 2: return launch_count<GenCount<2>>(st, G, A, P, l);
+    case 3: return launch_count<Marked3>(st, G, A, P, l);
+    case 4: return launch_count<DSigma>(st, G, A, P, l);
+    }
+    htb_set_error("unknown kernel kind %d", kind);
+    return 1;
+}
+
+int htb_build_tiles(cudaStream_t st, Workspace &ws, const WalkGeom &G, const SortedSample &s1,
+                    int64_t first_cell1, int64_t last_cell1, uint2 **tiles_out, uint32_t **ntiles_dev_out,
+                    int64_t *max_tiles_out, int *launches)
+{
+    const int F = G.dim - 1;
+    int64_t nseg = G.nd1[F];
+    for (int d = 0; d < F; ++d) nseg *= G.nf1[d];
+    uint32_t *ntile = nullptr, *tbase = nullptr, *total = nullptr;
+    if (ws.alloc((void **)&ntile, sizeof(uint32_t) * (size_t)(nseg + 1))) return 1;
+    if (ws.alloc((void **)&tbase, sizeof(uint32_t) * (size_t)(nseg + 1))) return 1;
+    if (ws.alloc((void **)&total, sizeof(uint32_t) * 4)) return 1;
+    const int64_t max_tiles = s1.n / HTB_TILE + nseg + 1;
+    uint2 *tiles = nullptr;
+    if (ws.alloc((void **)&tiles, sizeof(uint2) * (size_t)max_tiles)) return 1;
+    int blocks = (int)((nseg + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_seg_tiles<<<blocks, 256, 0, st>>>(s1.off, G, nseg, first_cell1, last_cell1, ntile);
+    if (launches) *launches += 1;
+    if (htb_exclusive_scan_u32(st, ws, ntile, tbase, nseg, total, launches)) return 1;
+    k_fill_tiles<<<blocks, 256, 0, st>>>(s1.off, G, nseg, ntile, tbase, tiles);
+    if (launches) *launches += 1;
+    HTB_CUDA(cudaGetLastError());
+    *tiles_out = tiles;
+    *ntiles_dev_out = total;
+    *max_tiles_out = max_tiles;
+    return 0;
+}
+
+int htb_reference_work(cudaStream_t st, Workspace &ws, const WalkGeom &G, const SortedSample &s1,
+                       const SortedSample &s2, double **work_dev_out, int64_t *ncell1_out, int *launches)
+{
+    int64_t nc1 = 1, nc2 = 1;
+    for (int d = 0; d < G.dim; ++d) { nc1 *= G.nd1[d]; nc2 *= G.nd2[d]; }
+    uint32_t *rc1 = nullptr, *rc2 = nullptr;
+    double *work = nullptr;
+    if (ws.alloc((void **)&rc1, sizeof(uint32_t) * (size_t)nc1)) return 1;
+    if (ws.alloc((void **)&rc2, sizeof(uint32_t) * (size_t)nc2)) return 1;
+    if (ws.alloc((void **)&work, sizeof(double) * (size_t)nc1)) return 1;
+    HTB_CUDA(cudaMemsetAsync(rc1, 0, sizeof(uint32_t) * (size_t)nc1, st));
+    HTB_CUDA(cudaMemsetAsync(rc2, 0, sizeof(uint32_t) * (size_t)nc2, st));
+    if (htb_ref_cell_counts(st, s1, rc1, launches)) return 1;
+    if (htb_ref_cell_counts(st, s2, rc2, launches)) return 1;
+    int blocks = (int)((nc1 + 127) / 128);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_wref<<<blocks, 128, 0, st>>>(rc1, rc2, G, nc1, work);
+    if (launches) *launches += 1;
+    HTB_CUDA(cudaGetLastError());
+    *work_dev_out = work;
+    *ncell1_out = nc1;
+    return 0;
+}

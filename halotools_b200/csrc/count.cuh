@@ -1,0 +1,35 @@
+// Parameter blocks of the counting kernels (passed by value as __grid_constant__).
+#pragma once
+#include "walk.cuh"
+
+#define HTB_NBF 16          // max bins of the fast npairs_3d kernel (one register counter per bin)
+#define HTB_MAX_NW 5        // max weights per point (marked_npairs_3d.py:281-326)
+
+struct Fast3Params {
+    int nb;                          // number of rbins (<= HTB_NBF); slot s holds bin s - (HTB_NBF - nb)
+    int H_lo;                        // high word of the lowest squared edge
+    unsigned U_span;                 // high word of the top squared edge minus H_lo
+    int F[HTB_NBF];                  // 32-bit monotone keys of the squared edges (pads = -1)
+    unsigned long long E[HTB_NBF];   // raw bit patterns of the squared edges (pads = 0)
+    unsigned long long E_top;
+    unsigned long long *counts;      // [nb] global accumulators
+};
+
+struct GenParams {
+    int n0, n1;                      // number of edges along the first / second bin axis
+    int nhist;                       // histogram length
+    int nw, wfunc;                   // marked: weights per point, weight_func_id
+    const double *e0, *e1;           // device arrays: squared edges (DSigma: e1 = ln(rp[k+1]/rp[k]))
+    double max0, max1;               // s_mu: max squared edges
+    unsigned long long *counts;      // integer histogram (global)
+    double *fcounts;                 // float histogram / per-object output (global)
+    const uint32_t *perm1;           // DSigma: sorted position -> input row
+};
+
+int htb_launch_fast3(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const Fast3Params &P, int *launches);
+int htb_launch_gen(cudaStream_t st, int kind, const WalkGeom &G, const WalkArrays &A, const GenParams &P, int *launches);
+int htb_build_tiles(cudaStream_t st, Workspace &ws, const WalkGeom &G, const SortedSample &s1,
+                    int64_t first_cell1, int64_t last_cell1, uint2 **tiles_out, uint32_t **ntiles_dev_out,
+                    int64_t *max_tiles_out, int *launches);
+int htb_reference_work(cudaStream_t st, Workspace &ws, const WalkGeom &G, const SortedSample &s1,
+                       const SortedSample &s2, double **work_dev_out, int64_t *ncell1_out, int *launches);

@@ -1,0 +1,102 @@
+// Internal declarations shared by the translation units of libhalotools_b200.so.
+// sm_100a only; compiled with -fmad=false so every f64 expression is evaluated
+// exactly as written (no FMA contraction) — required for bit-exact integer counts
+// against the reference's scalar SSE2 arithmetic.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/halotools_b200.h"
+
+#define HTB_TILE 64            // sample1 points per tile (one warp, 2 points per lane)
+#define HTB_MAX_DIM 3
+
+struct HtbError {
+    std::string msg;
+};
+void htb_set_error(const char *fmt, ...);
+
+#define HTB_CUDA(call)                                                                   \
+    do {                                                                                 \
+        cudaError_t e__ = (call);                                                        \
+        if (e__ != cudaSuccess) {                                                        \
+            htb_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call,                  \
+                          cudaGetErrorString(e__));                                      \
+            return 1;                                                                    \
+        }                                                                                \
+    } while (0)
+
+// One sample binned on a refinement of a reference mesh (RectangularMesh): every
+// reference cell is split into m[d] sub-cells per dimension; the LAST dimension is
+// the fastest in the cell id, as in the reference (rectangular_mesh.py:224-225).
+struct FineGrid {
+    int dim;
+    int nd[HTB_MAX_DIM];        // reference num_divs
+    int m[HTB_MAX_DIM];         // sub-divisions per reference cell
+    int nf[HTB_MAX_DIM];        // nd * m
+    double cs[HTB_MAX_DIM];     // reference cell size (python float handed down by the host layer)
+    double h[HTB_MAX_DIM];      // cs / m
+    double period[HTB_MAX_DIM];
+    int64_t ncells;             // prod nf
+};
+
+struct SortedSample {
+    int64_t n = 0;
+    int64_t npad = 0;           // allocation length of each coordinate array (even, >= n + 2)
+    FineGrid g{};
+    double *c[HTB_MAX_DIM] = {nullptr, nullptr, nullptr};   // SoA coordinates, sorted by fine cell
+    double *w = nullptr;        // row-major (n, nw) payload in sorted order (weights / masses) or null
+    int nw = 0;
+    uint32_t *off = nullptr;    // [ncells + 1] first sorted position of each fine cell
+    uint32_t *perm = nullptr;   // [n] sorted position -> input index
+    uint32_t *flags = nullptr;  // [1] bit0: some point lies outside [0, period] in some dimension
+    uint32_t *cell = nullptr;   // scratch [n]: fine cell id per input point
+    uint32_t *rank = nullptr;   // scratch [n]: arrival rank inside the cell
+};
+
+struct Workspace;   // stream-ordered allocations of one engine call (freed at the end)
+
+// ---- mesh.cu
+int htb_sort_sample(cudaStream_t st, Workspace &ws, const FineGrid &g,
+                    const double *const *coords_dev, int64_t stride, int64_t n,
+                    const double *w_dev, int nw, bool keep_perm, SortedSample &out, int *launches);
+int htb_exclusive_scan_u32(cudaStream_t st, Workspace &ws, const uint32_t *in, uint32_t *out,
+                           int64_t n, uint32_t *total_dev, int *launches);
+int htb_ref_cell_ids(cudaStream_t st, int dim, const double *const *coords_dev, int64_t stride, int64_t n,
+                     const double *cell_size, const int *ndivs, int64_t *ids_dev, int *launches);
+int htb_ref_cell_counts(cudaStream_t st, const SortedSample &s, uint32_t *counts_dev /* [prod nd] zeroed */,
+                        int *launches);
+
+// ---- workspace (capi.cu)
+struct Workspace {
+    cudaStream_t st = nullptr;
+    void *ptrs[256];
+    int nptrs = 0;
+    int alloc(void **p, size_t bytes);
+    void release();
+};
+
+// numpy's float64 floor-division followed by the reference's clip
+// (rectangular_mesh.py:19-22; numpy npy_divmod: fmod based, NOT floor(p / c)).
+__host__ __device__ inline int htb_ref_digitize(double p, double c, int ndivs)
+{
+    double mod = fmod(p, c);
+    double div = (p - mod) / c;
+    if (mod != 0.0) {
+        if ((c < 0) != (mod < 0)) { mod += c; div -= 1.0; }
+    }
+    double fl;
+    if (div != 0.0) {
+        fl = floor(div);
+        if (div - fl > 0.5) fl += 1.0;
+    } else {
+        fl = 0.0;
+    }
+    // astype(int) then np.where(ip >= num_divs, num_divs - 1, ip); negatives are undefined
+    // behaviour in the reference (they index before the first cell) — clamp to cell 0.
+    if (!(fl > -1.0)) return 0;
+    if (fl >= (double)ndivs) return ndivs - 1;
+    return (int)fl;
+}

@@ -1,0 +1,291 @@
+// K1 — spatial index on the GPU: reference cell assignment + counting sort into
+// contiguous SoA float64 per (refined) cell.
+//
+// Replaces RectangularMesh.__init__ (digitize -> argsort -> searchsorted,
+// /root/reference/halotools/mock_observables/pair_counters/rectangular_mesh.py:118-222)
+// by: k_assign (cell id + arrival rank through one atomicAdd per point), a 3-pass
+// exclusive scan of the per-cell counts, and k_scatter.  O(N) HBM traffic:
+// read 24 B + write 8 B per point in k_assign, read 32 B + write 28 B(+payload) in k_scatter.
+#include "htb_internal.cuh"
+
+#define SCAN_THREADS 256
+#define SCAN_ITEMS 8
+#define SCAN_BLOCK (SCAN_THREADS * SCAN_ITEMS)
+
+template <int DIM>
+__global__ void __launch_bounds__(256)
+k_assign(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z,
+         int64_t stride, int64_t n, FineGrid g, uint32_t *__restrict__ cell, uint32_t *__restrict__ rank,
+         uint32_t *__restrict__ count, uint32_t *__restrict__ flags)
+{
+    const double *src[3] = {x, y, z};
+    uint32_t bad = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t cid = 0;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) {
+            const double p = src[d][i * stride];
+            const int r = htb_ref_digitize(p, g.cs[d], g.nd[d]);
+            int f = r;
+            if (g.m[d] > 1) {
+                int sub = (int)floor((p - (double)r * g.cs[d]) * ((double)g.m[d] / g.cs[d]));
+                sub = sub < 0 ? 0 : (sub >= g.m[d] ? g.m[d] - 1 : sub);
+                f = r * g.m[d] + sub;
+            }
+            if (!(p >= 0.0 && p <= g.period[d])) bad = 1;
+            cid = cid * (uint32_t)g.nf[d] + (uint32_t)f;
+        }
+        cell[i] = cid;
+        rank[i] = atomicAdd(&count[cid], 1u);
+    }
+    if (bad) atomicOr(flags, 1u);
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(256)
+k_scatter(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z,
+          int64_t stride, int64_t n, const uint32_t *__restrict__ cell, const uint32_t *__restrict__ rank,
+          const uint32_t *__restrict__ off, double *__restrict__ ox, double *__restrict__ oy,
+          double *__restrict__ oz, uint32_t *__restrict__ perm,
+          const double *__restrict__ w, double *__restrict__ ow, int nw)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t pos = off[cell[i]] + rank[i];
+        ox[pos] = x[i * stride];
+        oy[pos] = y[i * stride];
+        if (DIM == 3) oz[pos] = z[i * stride];
+        if (perm) perm[pos] = (uint32_t)i;
+        if (ow) {
+            for (int k = 0; k < nw; ++k) ow[(int64_t)pos * nw + k] = w[i * nw + k];
+        }
+    }
+}
+
+// pad entries [n, npad) with a far-away sentinel so that staging reads past a span end are harmless
+__global__ void k_pad(double *a, double *b, double *c, int64_t n, int64_t npad)
+{
+    int64_t i = n + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < npad) {
+        a[i] = 1.0e150;
+        b[i] = 1.0e150;
+        if (c) c[i] = 1.0e150;
+    }
+}
+
+// ------------------------------------------------------------------ exclusive scan
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_partial(const uint32_t *__restrict__ in, int64_t n, uint32_t *__restrict__ bsum)
+{
+    __shared__ uint32_t red[SCAN_THREADS / 32];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_BLOCK;
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        int64_t i = base + (int64_t)k * SCAN_THREADS + threadIdx.x;
+        if (i < n) s += in[i];
+    }
+    s = __reduce_add_sync(0xffffffffu, s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < SCAN_THREADS / 32; ++w) t += red[w];
+        bsum[blockIdx.x] = t;
+    }
+}
+
+// single block: exclusive scan of the block sums in place, total to *total
+__global__ void __launch_bounds__(1024)
+k_scan_bsums(uint32_t *__restrict__ bsum, int64_t nb, uint32_t *__restrict__ total)
+{
+    __shared__ uint32_t sh[1024];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < nb; base += 1024) {
+        int64_t i = base + threadIdx.x;
+        uint32_t v = (i < nb) ? bsum[i] : 0u;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            uint32_t t = (threadIdx.x >= (unsigned)o) ? sh[threadIdx.x - o] : 0u;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        const uint32_t incl = sh[threadIdx.x];
+        const uint32_t c = carry;
+        if (i < nb) bsum[i] = c + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = c + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total) *total = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_final(const uint32_t *__restrict__ in, int64_t n, const uint32_t *__restrict__ bsum,
+             uint32_t *__restrict__ out)
+{
+    // block-local exclusive scan of SCAN_BLOCK items laid out [k][thread] is awkward; use a
+    // thread-contiguous layout instead: thread t owns items [t*ITEMS, (t+1)*ITEMS).
+    __shared__ uint32_t wsum[SCAN_THREADS / 32];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_BLOCK + (int64_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS];
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        v[k] = (base + k < n) ? in[base + k] : 0u;
+        s += v[k];
+    }
+    // warp inclusive scan of s
+    uint32_t inc = s;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[wid] = inc;
+    __syncthreads();
+    uint32_t wbase = 0;
+    for (int w = 0; w < wid; ++w) wbase += wsum[w];
+    uint32_t run = bsum[blockIdx.x] + wbase + inc - s;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (base + k < n) out[base + k] = run;
+        run += v[k];
+    }
+}
+
+__global__ void k_set_u32(uint32_t *dst, const uint32_t *src) { *dst = *src; }
+
+int htb_exclusive_scan_u32(cudaStream_t st, Workspace &ws, const uint32_t *in, uint32_t *out,
+                           int64_t n, uint32_t *total_dev, int *launches)
+{
+    if (n <= 0) {
+        if (total_dev) HTB_CUDA(cudaMemsetAsync(total_dev, 0, sizeof(uint32_t), st));
+        return 0;
+    }
+    const int64_t nblk = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    uint32_t *bsum = nullptr;
+    if (ws.alloc((void **)&bsum, sizeof(uint32_t) * (size_t)nblk)) return 1;
+    k_scan_partial<<<(unsigned)nblk, SCAN_THREADS, 0, st>>>(in, n, bsum);
+    k_scan_bsums<<<1, 1024, 0, st>>>(bsum, nblk, total_dev);
+    k_scan_final<<<(unsigned)nblk, SCAN_THREADS, 0, st>>>(in, n, bsum, out);
+    if (launches) *launches += 3;
+    HTB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int grid_for(int64_t n, int threads)
+{
+    int64_t b = (n + threads - 1) / threads;
+    const int64_t cap = 148 * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+int htb_sort_sample(cudaStream_t st, Workspace &ws, const FineGrid &g,
+                    const double *const *cd, int64_t stride, int64_t n,
+                    const double *w_dev, int nw, bool keep_perm, SortedSample &out, int *launches)
+{
+    out.n = n;
+    out.g = g;
+    out.nw = w_dev ? nw : 0;
+    out.npad = ((n + 1) & ~(int64_t)1) + 2;
+    for (int d = 0; d < g.dim; ++d)
+        if (ws.alloc((void **)&out.c[d], sizeof(double) * (size_t)out.npad)) return 1;
+    if (ws.alloc((void **)&out.off, sizeof(uint32_t) * (size_t)(g.ncells + 2))) return 1;
+    if (ws.alloc((void **)&out.flags, sizeof(uint32_t) * 4)) return 1;
+    if (keep_perm && ws.alloc((void **)&out.perm, sizeof(uint32_t) * (size_t)(n > 0 ? n : 1))) return 1;
+    if (w_dev && ws.alloc((void **)&out.w, sizeof(double) * (size_t)((n > 0 ? n : 1) * nw + 2))) return 1;
+    if (ws.alloc((void **)&out.cell, sizeof(uint32_t) * (size_t)(n > 0 ? n : 1))) return 1;
+    if (ws.alloc((void **)&out.rank, sizeof(uint32_t) * (size_t)(n > 0 ? n : 1))) return 1;
+    uint32_t *count = nullptr;
+    if (ws.alloc((void **)&count, sizeof(uint32_t) * (size_t)(g.ncells + 2))) return 1;
+    HTB_CUDA(cudaMemsetAsync(count, 0, sizeof(uint32_t) * (size_t)(g.ncells + 2), st));
+    HTB_CUDA(cudaMemsetAsync(out.flags, 0, sizeof(uint32_t) * 4, st));
+    if (n > 0) {
+        const int blocks = grid_for(n, 256);
+        if (g.dim == 3)
+            k_assign<3><<<blocks, 256, 0, st>>>(cd[0], cd[1], cd[2], stride, n, g, out.cell, out.rank, count, out.flags);
+        else
+            k_assign<2><<<blocks, 256, 0, st>>>(cd[0], cd[1], nullptr, stride, n, g, out.cell, out.rank, count, out.flags);
+        if (launches) *launches += 1;
+    }
+    // off[0..ncells] : exclusive scan over ncells+1 entries (the extra entry is zero) gives off[ncells] = n
+    if (htb_exclusive_scan_u32(st, ws, count, out.off, g.ncells + 1, nullptr, launches)) return 1;
+    if (n > 0) {
+        const int blocks = grid_for(n, 256);
+        if (g.dim == 3)
+            k_scatter<3><<<blocks, 256, 0, st>>>(cd[0], cd[1], cd[2], stride, n, out.cell, out.rank, out.off,
+                                                 out.c[0], out.c[1], out.c[2], out.perm, w_dev, out.w, nw);
+        else
+            k_scatter<2><<<blocks, 256, 0, st>>>(cd[0], cd[1], nullptr, stride, n, out.cell, out.rank, out.off,
+                                                 out.c[0], out.c[1], nullptr, out.perm, w_dev, out.w, nw);
+        if (launches) *launches += 1;
+    }
+    k_pad<<<1, 32, 0, st>>>(out.c[0], out.c[1], g.dim == 3 ? out.c[2] : nullptr, n, out.npad);
+    if (launches) *launches += 1;
+    HTB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------ reference cell ids only
+template <int DIM>
+__global__ void k_ref_ids(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z,
+                          int64_t stride, int64_t n, double c0, double c1, double c2, int n0, int n1, int n2,
+                          int64_t *__restrict__ ids)
+{
+    const double *src[3] = {x, y, z};
+    const double cs[3] = {c0, c1, c2};
+    const int nd[3] = {n0, n1, n2};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t cid = 0;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) cid = cid * nd[d] + htb_ref_digitize(src[d][i * stride], cs[d], nd[d]);
+        ids[i] = cid;
+    }
+}
+
+int htb_ref_cell_ids(cudaStream_t st, int dim, const double *const *cd, int64_t stride, int64_t n,
+                     const double *cell_size, const int *ndivs, int64_t *ids_dev, int *launches)
+{
+    if (n <= 0) return 0;
+    const int blocks = grid_for(n, 256);
+    if (dim == 3)
+        k_ref_ids<3><<<blocks, 256, 0, st>>>(cd[0], cd[1], cd[2], stride, n, cell_size[0], cell_size[1], cell_size[2],
+                                            ndivs[0], ndivs[1], ndivs[2], ids_dev);
+    else
+        k_ref_ids<2><<<blocks, 256, 0, st>>>(cd[0], cd[1], nullptr, stride, n, cell_size[0], cell_size[1], 1.0,
+                                            ndivs[0], ndivs[1], 1, ids_dev);
+    if (launches) *launches += 1;
+    HTB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// per reference-cell point counts from the fine offsets
+__global__ void k_ref_counts(const uint32_t *__restrict__ off, FineGrid g, uint32_t *__restrict__ counts)
+{
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < g.ncells; c += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t k = off[c + 1] - off[c];
+        if (!k) continue;
+        int64_t rem = c;
+        int f[3] = {0, 0, 0};
+        for (int d = g.dim - 1; d >= 0; --d) { f[d] = (int)(rem % g.nf[d]); rem /= g.nf[d]; }
+        int64_t rid = 0;
+        for (int d = 0; d < g.dim; ++d) rid = rid * g.nd[d] + f[d] / g.m[d];
+        atomicAdd(&counts[rid], k);
+    }
+}
+
+int htb_ref_cell_counts(cudaStream_t st, const SortedSample &s, uint32_t *counts_dev, int *launches)
+{
+    const int blocks = grid_for(s.g.ncells, 256);
+    k_ref_counts<<<blocks, 256, 0, st>>>(s.off, s.g, counts_dev);
+    if (launches) *launches += 1;
+    HTB_CUDA(cudaGetLastError());
+    return 0;
+}

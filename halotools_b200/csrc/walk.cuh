@@ -1,0 +1,303 @@
+// K2 skeleton — the cell-pair "walker" shared by every pair-counting kernel.
+//
+// One warp owns one TILE of <= 64 sample1 points (2 per lane, held in registers) that
+// lie in one fine column and one reference mesh1 cell.  For that tile the warp
+//   1. rebuilds the reference's neighbour window (npairs_3d_engine.pyx:113-153) in
+//      units of the refined sample2 grid, keeping the reference's per-cell periodic
+//      shift (-L / 0 / +L decided by the UNWRAPPED reference cell index),
+//   2. prunes columns / z-runs whose cells are provably farther than the search
+//      radius from the tile's bounding box (count-preserving),
+//   3. turns every surviving (column, wrap piece) into ONE contiguous span of the
+//      z-fastest sorted sample2 arrays,
+//   4. streams the spans through a per-warp shared-memory ring filled by 1-D TMA
+//      bulk copies (cp.async.bulk + mbarrier complete_tx), and
+//   5. hands each staged chunk to the variant's pair functor.
+// Variants differ only in the functor (bins, weights, accumulators).
+#pragma once
+#include "htb_internal.cuh"
+
+#define HTB_WARPS 8                 // warps per block of the counting kernels (overridable per variant)
+#define HTB_CH 64                   // sample2 points per staged chunk
+#define HTB_NSTAGE 2
+#define HTB_SPAN_CAP 128
+#define HTB_FULL 0xffffffffu
+
+struct WalkGeom {
+    int dim;
+    int pbc;
+    int sphere;                     // 1: fast-dim reach shrinks with slow-dim distance (3-D r / 2-D rp); 0: cylinder (rp, pi)
+    int nocull;
+    int nd1[3], nd2[3], per[3], cover[3];
+    int m1[3], m2[3], nf1[3], nf2[3];
+    double period[3], h2[3], slop[3], reach[3];
+    double r2slow;                  // (max separation over the slow dims)^2, with safety margin
+};
+
+struct WalkArrays {
+    const double *c1[3];            // sorted sample1 coords
+    const uint32_t *off1;
+    const double *c2[3];            // sorted sample2 coords
+    const uint32_t *off2;
+    const double *pay1;             // sorted sample1 payload rows (n1, nw) or null
+    const double *pay2;             // sorted sample2 payload rows (n2, nw) or null
+    int nw;
+    const uint32_t *flags1, *flags2;
+    const uint2 *tiles;             // {first sorted index, segment id}
+    const uint32_t *ntiles_dev;     // [1] number of tiles (device resident; no host sync)
+    unsigned int *tile_counter;
+    unsigned long long *pairs_evaluated;
+    unsigned int *tiles_redone;
+};
+
+// ------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+// explicit shared-space loads (the staging pointers reach the functors as generic pointers otherwise)
+__device__ __forceinline__ double lds_f64(uint32_t addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void lds_f64x2(uint32_t addr, double &a, double &b)
+{
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ double warp_min(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(HTB_FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(HTB_FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ int floor_div(int a, int b) { int q = a / b; return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q; }
+
+// Per-warp shared-memory context
+template <int DIM, int NPAY>
+struct WarpSmem {
+    // stage buffers: DIM coordinate rows of HTB_CH doubles + payload rows (HTB_CH * NPAY doubles)
+    double *stage[HTB_NSTAGE];      // base of each stage
+    uint32_t bar[HTB_NSTAGE];       // shared-space addresses of the mbarriers
+    uint32_t *span;                 // HTB_SPAN_CAP * 3 u32: {jb, je, code}
+    static __host__ __device__ constexpr int stage_doubles() { return HTB_CH * (DIM + NPAY); }
+    static __host__ __device__ constexpr size_t bytes()
+    {
+        return sizeof(double) * HTB_NSTAGE * stage_doubles() + 16 * HTB_NSTAGE + sizeof(uint32_t) * 3 * HTB_SPAN_CAP;
+    }
+};
+
+struct TileInfo {
+    int cnt;                // valid points in the tile
+    uint32_t start;         // first sorted index
+    bool v0, v1;            // validity of this lane's two points
+};
+
+// The walker.  V must provide:
+//   static constexpr int DIM, NPAY; static constexpr bool TMA;
+//   __device__ void chunk(uint32_t stage_smem_addr, int lo, int hi, uint32_t j0, const double (&sh)[3]) — evaluate
+//        pairs between the lane's points (shifted by sh) and staged sample2 entries [lo, hi).
+template <class V>
+__device__ __forceinline__ void walk_tile(V &v, const WalkGeom &G, const WalkArrays &A,
+                                          WarpSmem<V::DIM, V::NPAY> &S, uint32_t &gchunk,
+                                          const double (&blo)[3], const double (&bhi)[3],
+                                          const int (&fs)[3] /* tile's fine/ref indices: slow dims fine idx, fast dim ref cell */,
+                                          unsigned long long &pairs, int tile_cnt)
+{
+    constexpr int DIM = V::DIM;
+    constexpr int F = DIM - 1;                 // fast dimension
+    const int lane = threadIdx.x & 31;
+    const bool cull = !G.nocull && !((A.flags1[0] | A.flags2[0]) & 1u);
+
+    // reference cell1 index per dim and the window in fine-2 units
+    int a[3], wlo[3], wn[3];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+        a[d] = (d == F) ? fs[d] : fs[d] / G.m1[d];
+        wlo[d] = (a[d] * G.per[d] - G.cover[d]) * G.m2[d];
+        wn[d] = (G.per[d] + 2 * G.cover[d]) * G.m2[d];
+    }
+    const int ncol = (DIM == 3) ? wn[0] * wn[1] : wn[0];
+    const int kfmin = floor_div(wlo[F], G.nf2[F]);
+    const int kfmax = floor_div(wlo[F] + wn[F] - 1, G.nf2[F]);
+
+    int nspan = 0;
+
+    auto consume = [&]() {
+        // ---- stream the span list through the staging ring
+        int si = 0, sc = 0;                    // issue / compute span cursors
+        uint32_t ji = 0, jc = 0;               // aligned start of the next chunk
+        if (nspan > 0) { ji = jc = S.span[0] & ~1u; }
+        int inflight = 0;
+        while (sc < nspan) {
+            while (si < nspan && inflight < HTB_NSTAGE) {
+                const uint32_t je = S.span[3 * si + 1];
+                const uint32_t jend = (je + 1u) & ~1u;
+                const uint32_t cnt = min((uint32_t)HTB_CH, jend - ji);
+                const int stg = (gchunk + inflight) % HTB_NSTAGE;
+                double *dst = S.stage[stg];
+                if (V::TMA) {
+                    if (lane == 0) {
+                        const uint32_t bytes = cnt * 8u * (DIM + A.nw * (V::NPAY > 0 ? 1 : 0));
+                        mbar_expect_tx(S.bar[stg], bytes);
+#pragma unroll
+                        for (int d = 0; d < DIM; ++d)
+                            tma_bulk_g2s(smem_u32(dst + d * HTB_CH), A.c2[d] + ji, cnt * 8u, S.bar[stg]);
+                        if (V::NPAY > 0)
+                            tma_bulk_g2s(smem_u32(dst + DIM * HTB_CH), A.pay2 + (size_t)ji * A.nw, cnt * 8u * A.nw, S.bar[stg]);
+                    }
+                } else {
+                    for (uint32_t q = lane; q < cnt; q += 32) {
+#pragma unroll
+                        for (int d = 0; d < DIM; ++d) dst[d * HTB_CH + q] = A.c2[d][ji + q];
+                    }
+                    if (V::NPAY > 0)
+                        for (uint32_t q = lane; q < cnt * A.nw; q += 32) dst[DIM * HTB_CH + q] = A.pay2[(size_t)ji * A.nw + q];
+                }
+                ++inflight;
+                ji += HTB_CH;
+                if (ji >= je) { ++si; if (si < nspan) ji = S.span[3 * si] & ~1u; }
+            }
+            // ---- current chunk
+            const uint32_t jb = S.span[3 * sc], je = S.span[3 * sc + 1], code = S.span[3 * sc + 2];
+            const int stg = gchunk % HTB_NSTAGE;
+            if (V::TMA) mbar_wait(S.bar[stg], (gchunk / HTB_NSTAGE) & 1u);
+            else __syncwarp();
+            const int lo = (int)(max(jb, jc) - jc);
+            const int hi = (int)(min(je, jc + HTB_CH) - jc);
+            double sh[3];
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) {
+                const int k = (int)((code >> (2 * d)) & 3u) - 1;
+                sh[d] = (double)(k * G.pbc) * G.period[d];
+            }
+            v.chunk(smem_u32(S.stage[stg]), lo, hi, jc, sh);
+            pairs += (unsigned long long)(hi - lo) * (unsigned)tile_cnt;
+            __syncwarp();
+            ++gchunk;
+            --inflight;
+            jc += HTB_CH;
+            if (jc >= je) { ++sc; if (sc < nspan) jc = S.span[3 * sc] & ~1u; }
+        }
+        nspan = 0;
+    };
+
+    // generate spans (lane-parallel over columns) until the list is nearly full, then stream them
+    int base = 0, kf = kfmin;
+    bool more = ncol > 0;
+    while (more) {
+        while (true) {
+            if (base >= ncol) { more = false; break; }
+            const int col = base + lane;
+            const bool valid = col < ncol;
+            int U[3] = {0, 0, 0};
+            if (DIM == 3) { U[0] = wlo[0] + col / wn[1]; U[1] = wlo[1] + col % wn[1]; }
+            else { U[0] = wlo[0] + col; }
+            double d2 = 0.0;
+            uint32_t code = 0;
+            int64_t slowlin = 0;
+#pragma unroll
+            for (int d = 0; d < F; ++d) {
+                const int k = floor_div(U[d], G.nf2[d]);
+                const int w = U[d] - k * G.nf2[d];
+                const int kc = k < -1 ? -1 : (k > 1 ? 1 : k);   // the reference only distinguishes <0 / inside / >= ndivs2
+                const double elo = (double)w * G.h2[d] + (double)(kc * G.pbc) * G.period[d] - G.slop[d];
+                const double ehi = elo + G.h2[d] + 2.0 * G.slop[d];
+                const double gap = fmax(0.0, fmax(elo - bhi[d], blo[d] - ehi));
+                d2 += gap * gap;
+                code |= (uint32_t)(kc + 1) << (2 * d);
+                slowlin = slowlin * G.nf2[d] + w;
+            }
+            const bool keep = valid && (!cull || d2 <= G.r2slow);
+            double reach = 0.0;
+            if (cull) {
+                reach = G.sphere ? sqrt(fmax(G.r2slow - d2, 0.0)) : G.reach[F];
+                reach += G.slop[F];
+            }
+            {
+                const int k = kf;
+                const int kc = k < -1 ? -1 : (k > 1 ? 1 : k);
+                int plo = max(wlo[F], k * G.nf2[F]);
+                int phi = min(wlo[F] + wn[F], (k + 1) * G.nf2[F]) - 1;
+                bool has = keep && plo <= phi;
+                if (has && cull) {
+                    // effective coordinate of fine cell U in this piece: (U - k*nf2)*h2 + kc*pbc*L
+                    const double offc = -(double)k * G.period[F] + (double)(kc * G.pbc) * G.period[F];
+                    const double qlo = (blo[F] - reach - offc) / G.h2[F];
+                    const double qhi = (bhi[F] + reach - offc) / G.h2[F];
+                    plo = (int)fmax(floor(qlo), (double)plo);
+                    phi = (int)fmin(floor(qhi), (double)phi);
+                    has = plo <= phi;
+                }
+                uint32_t jb = 0, je = 0;
+                if (has) {
+                    const int64_t cbase = slowlin * G.nf2[F] - (int64_t)k * G.nf2[F];
+                    jb = A.off2[cbase + plo];
+                    je = A.off2[cbase + phi + 1];
+                    has = je > jb;
+                }
+                const uint32_t bal = __ballot_sync(HTB_FULL, has);
+                if (has) {
+                    const int pos = nspan + __popc(bal & ((1u << lane) - 1u));
+                    S.span[3 * pos] = jb;
+                    S.span[3 * pos + 1] = je;
+                    S.span[3 * pos + 2] = code | ((uint32_t)(kc + 1) << (2 * F));
+                }
+                nspan += __popc(bal);
+            }
+            if (++kf > kfmax) { kf = kfmin; base += 32; }
+            if (nspan + 32 > HTB_SPAN_CAP) break;
+        }
+        __syncwarp();
+        consume();
+        __syncwarp();
+    }
+}

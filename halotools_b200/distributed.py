@@ -1,0 +1,85 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), ``torch.distributed`` (NCCL on GPUs, gloo in
+the CPU tests).
+
+The pair-counting path shards the way the reference does (contiguous ranges of mesh1 cells,
+/root/reference/halotools/mock_observables/pair_counters/mesh_helpers.py:183-221, summed at the
+end, npairs_3d.py:145): every rank holds all of sample2, counts the pairs of ITS range of
+reference mesh1 cells, and the tiny count vectors are combined with ONE all-reduce (int64 sums are
+exact, so results stay bit-identical to a single-GPU run).
+
+Sharding is opt-in: call ``enable()`` after ``torch.distributed.init_process_group``; without it
+every call counts all cells (N independent replicas).
+"""
+import numpy as np
+
+_state = {"enabled": False, "group": None, "weights": None}
+
+
+def enable(group=None):
+    """Shard subsequent pair-counter calls over the ranks of ``group`` (default: world)."""
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        raise RuntimeError("torch.distributed is not initialised")
+    _state["enabled"] = True
+    _state["group"] = group
+
+
+def disable():
+    _state["enabled"] = False
+    _state["group"] = None
+
+
+def is_enabled():
+    return _state["enabled"]
+
+
+def _rank_world():
+    if not _state["enabled"]:
+        return 0, 1
+    import torch.distributed as dist
+    return dist.get_rank(_state["group"]), dist.get_world_size(_state["group"])
+
+
+def split_cells(ncells, world, work=None):
+    """Contiguous (first, last) mesh1-cell ranges for ``world`` ranks.
+
+    Without ``work`` this is the reference's np.array_split rule; with a per-cell predicted work
+    vector (htb_cell1_work) the cut points equalise cumulative work instead of cell counts."""
+    if world <= 1:
+        return [(0, ncells)]
+    if work is None:
+        parts = np.array_split(np.arange(ncells), world)
+        out, pos = [], 0
+        for p in parts:
+            out.append((pos, pos + len(p)))
+            pos += len(p)
+        return out
+    cum = np.concatenate([[0.0], np.cumsum(np.asarray(work, dtype=np.float64))])
+    total = cum[-1]
+    cuts = [0]
+    for r in range(1, world):
+        cuts.append(int(np.searchsorted(cum, total * r / world, side="left")))
+    cuts.append(ncells)
+    cuts = np.maximum.accumulate(np.clip(cuts, 0, ncells))
+    return [(int(cuts[r]), int(cuts[r + 1])) for r in range(world)]
+
+
+def cell1_range(ncells, work=None):
+    """This rank's (first_cell1, last_cell1)."""
+    rank, world = _rank_world()
+    return split_cells(ncells, world, work)[rank]
+
+
+def allreduce_sum(array):
+    """Sum a small numpy array over the ranks (NCCL when the GPUs are there, gloo otherwise)."""
+    rank, world = _rank_world()
+    if world <= 1:
+        return array
+    import torch
+    import torch.distributed as dist
+    backend = dist.get_backend(_state["group"])
+    t = torch.from_numpy(np.ascontiguousarray(array))
+    if backend == "nccl":
+        t = t.cuda()
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=_state["group"])
+    return t.cpu().numpy()

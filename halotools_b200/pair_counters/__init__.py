@@ -1,0 +1,8 @@
+"""Pair counters with the reference's names and signatures
+(/root/reference/halotools/mock_observables/pair_counters/__init__.py)."""
+from .npairs_3d import npairs_3d
+from .npairs_xy_z import npairs_xy_z
+from .npairs_s_mu import npairs_s_mu
+from .marked_npairs_3d import marked_npairs_3d
+
+__all__ = ("npairs_3d", "npairs_xy_z", "npairs_s_mu", "marked_npairs_3d")

@@ -1,0 +1,114 @@
+"""Drop-in for ``halotools.mock_observables.mean_delta_sigma``
+(/root/reference/halotools/mock_observables/surface_density/mean_delta_sigma.py:26-330)."""
+import ctypes
+
+import numpy as np
+
+from .. import _lib
+from .. import distributed as _dist
+from ..helpers import (custom_len, enforce_sample_has_correct_shape, enforce_sample_respects_pbcs,
+                       get_num_threads, get_period, get_separation_bins_array)
+from ..pair_counters.mesh_helpers import (_enclose_in_box, _enclose_in_square,
+                                          _set_approximate_2d_cell_sizes, double_mesh_geometry)
+
+__all__ = ("mean_delta_sigma",)
+
+
+def mean_delta_sigma(galaxies, particles, effective_particle_masses,
+                     rp_bins, period=None, verbose=False, num_threads=1,
+                     approx_cell1_size=None, approx_cell2_size=None, per_object=False):
+    """Excess surface density Delta Sigma(rp) of ``particles`` around ``galaxies`` (projection along
+    z), in the bins defined by ``rp_bins``: float64 (len(rp_bins)-1,), or (Ngal, len(rp_bins)-1)
+    rows in input order when ``per_object`` is True.  Semantics follow the reference engine
+    (surface_density/engines/mean_delta_sigma_engine.pyx:162-185)."""
+    result = _mean_delta_sigma_process_args(
+        galaxies, particles, effective_particle_masses, rp_bins,
+        period, num_threads, approx_cell1_size, approx_cell2_size)
+    x1in, y1in, x2in, y2in, w2in = result[0:5]
+    rp_bins, period, num_threads, PBCs, approx_cell1_size, approx_cell2_size = result[5:]
+    rp_max = np.max(rp_bins)
+    search = [rp_max, rp_max]
+
+    approx_cell1_size, approx_cell2_size = _set_approximate_2d_cell_sizes(
+        approx_cell1_size, approx_cell2_size, period)
+    geom = double_mesh_geometry(2, approx_cell1_size, approx_cell2_size, search, period[:2], PBCs)
+
+    n1 = len(x1in)
+    nbin = len(rp_bins) - 1
+    delta_sigma = np.zeros((n1, nbin), dtype=np.float64)
+    first, last = _dist.cell1_range(geom.ncells1)
+    c1 = _lib.Columns([x1in, y1in])
+    c2 = _lib.Columns([x2in, y2in])
+    m2 = np.ascontiguousarray(w2in, dtype=np.float64)
+    g = geom.as_struct()
+    rb = np.ascontiguousarray(rp_bins, dtype=np.float64)
+    _lib.run_engine(
+        "htb_mean_delta_sigma_engine", ctypes.byref(g),
+        c1.ptrs[0], c1.ptrs[1], ctypes.c_int64(c1.stride), ctypes.c_int64(c1.n),
+        c2.ptrs[0], c2.ptrs[1], ctypes.c_int64(c2.stride), _lib._dp(m2), ctypes.c_int64(c2.n),
+        _lib._dp(rb), ctypes.c_int32(len(rb)), ctypes.c_int64(first), ctypes.c_int64(last),
+        _lib._dp(delta_sigma))
+    if per_object:
+        return _dist.allreduce_sum(delta_sigma)
+    # rows outside this rank's mesh1 cells are zero, so the mean is the all-reduced column sum / N
+    colsum = _dist.allreduce_sum(np.sum(delta_sigma, axis=0))
+    return colsum / float(n1) if _dist.is_enabled() else np.mean(delta_sigma, axis=0)
+
+
+def _mean_delta_sigma_process_args(
+        galaxies, particles, effective_particle_masses, rp_bins,
+        period, num_threads, approx_cell1_size, approx_cell2_size):
+    """Same processing as mean_delta_sigma.py:258-330, including the reference's habit of writing
+    the shifted coordinates back into the caller's arrays when ``period`` is None (:263-273)."""
+    period, PBCs = get_period(period)
+
+    if PBCs is False:
+        _x1, _y1, _z1, _x2, _y2, _z2, period = _enclose_in_box(
+            galaxies[:, 0], galaxies[:, 1], galaxies[:, 2],
+            particles[:, 0], particles[:, 1], particles[:, 2])
+        galaxies[:, 0] = _x1
+        galaxies[:, 1] = _y1
+        galaxies[:, 2] = _z1
+        particles[:, 0] = _x2
+        particles[:, 1] = _y2
+        particles[:, 2] = _z2
+
+    galaxies = enforce_sample_has_correct_shape(galaxies)
+    particles = enforce_sample_has_correct_shape(particles)
+
+    effective_particle_masses = np.atleast_1d(effective_particle_masses)
+    if len(effective_particle_masses) == 1:
+        effective_particle_masses = np.zeros(particles.shape[0]) + effective_particle_masses[0]
+    else:
+        msg = "Must have same number of ``particle_masses`` as particles"
+        assert effective_particle_masses.shape[0] == particles.shape[0], msg
+
+    enforce_sample_respects_pbcs(galaxies[:, 0], galaxies[:, 1], galaxies[:, 2], period)
+    enforce_sample_respects_pbcs(particles[:, 0], particles[:, 1], particles[:, 2], period)
+
+    x1 = galaxies[:, 0]
+    y1 = galaxies[:, 1]
+    x2 = particles[:, 0]
+    y2 = particles[:, 1]
+
+    rp_bins = get_separation_bins_array(rp_bins)
+    rp_max = np.max(rp_bins)
+
+    if period is None:
+        PBCs = False
+        x1, y1, x2, y2, period = (
+            _enclose_in_square(x1, y1, x2, y2, min_size=[rp_max*3.0, rp_max*3.0]))
+
+    num_threads = get_num_threads(num_threads, enforce_max_cores=False)
+
+    if approx_cell1_size is None:
+        approx_cell1_size = [rp_max, rp_max]
+    elif custom_len(approx_cell1_size) == 1:
+        approx_cell1_size = [approx_cell1_size, approx_cell1_size]
+    if approx_cell2_size is None:
+        approx_cell2_size = [rp_max, rp_max]
+    elif custom_len(approx_cell2_size) == 1:
+        approx_cell2_size = [approx_cell2_size, approx_cell2_size]
+
+    return (x1, y1, x2, y2, effective_particle_masses, rp_bins,
+            period, num_threads, PBCs, approx_cell1_size, approx_cell2_size)

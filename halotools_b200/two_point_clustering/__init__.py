@@ -1,0 +1,6 @@
+from .tpcf import tpcf
+from .wp import wp
+from .rp_pi_tpcf import rp_pi_tpcf
+from .marked_tpcf import marked_tpcf
+
+__all__ = ("tpcf", "wp", "rp_pi_tpcf", "marked_tpcf")

@@ -1,0 +1,146 @@
+/*
+ * halotools_b200 — C ABI of the B200-native pair-counting engine.
+ *
+ * The reference (astropy/halotools) has no C ABI: its native boundary is the
+ * Cython engine call
+ *     engine(double_mesh, x1, y1, z1, x2, y2, z2, bins..., (first_cell1, last_cell1)) -> counts
+ * (/root/reference/halotools/mock_observables/pair_counters/cpairs/npairs_3d_engine.pyx:17).
+ * Every htb_*_engine entry point below replaces exactly one such engine and takes
+ * the same information as plain pointers and sizes:
+ *     double_mesh  -> htb_mesh_geom   (the scalars the engines read from the mesh object,
+ *                                      npairs_3d_engine.pyx:47-96; the per-point cell
+ *                                      assignment / sort is done on the GPU)
+ *     x1in..z2in   -> base pointers + element stride + count (UNSORTED, as the engine gets them)
+ *     cell1_tuple  -> first_cell1, last_cell1 (reference mesh1 cell ids, half-open)
+ *     return value -> caller-allocated output array.
+ * Pointers are HOST pointers unless HTB_FLAG_DEVICE_INPUT is set, in which case the
+ * coordinate / weight arrays are device pointers on the current CUDA device (outputs
+ * and bins are always host).  All functions return 0 on success, non-zero on error
+ * (htb_last_error() gives the message).  No torch types appear here.
+ */
+#ifndef HALOTOOLS_B200_H
+#define HALOTOOLS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HTB_ABI_VERSION 1
+
+/* flags */
+#define HTB_FLAG_DEVICE_INPUT 1u   /* coordinate/weight pointers are device pointers          */
+#define HTB_FLAG_NO_CULL      2u   /* visit exactly the reference's cell windows (no pruning) */
+#define HTB_FLAG_GENERIC      4u   /* force the generic (literal top-down scan) kernels       */
+#define HTB_FLAG_NO_TMA       8u   /* stage sample2 tiles with ld.global/st.shared instead of cp.async.bulk */
+
+/* Scalars of RectangularDoubleMesh / RectangularDoubleMesh2D
+ * (/root/reference/halotools/mock_observables/pair_counters/rectangular_mesh.py:228-374,
+ *  rectangular_mesh_2d.py:147-250).  For ndim == 2 only entries [0], [1] are read.  */
+typedef struct htb_mesh_geom {
+    int32_t ndim;            /* 3, or 2 for the surface-density mesh                        */
+    int32_t pbc;             /* double_mesh._PBCs                                            */
+    int32_t ndivs1[3];       /* mesh1.num_{x,y,z}divs                                        */
+    int32_t ndivs2[3];       /* mesh2.num_{x,y,z}divs  (a multiple of ndivs1)                */
+    int32_t cover[3];        /* ceil(search_length / mesh2 cell size), engine.pyx:74-79      */
+    int32_t reserved;
+    double  period[3];       /* {x,y,z}period                                                */
+    double  cell1_size[3];   /* mesh1.{x,y,z}cell_size                                       */
+    double  cell2_size[3];   /* mesh2.{x,y,z}cell_size                                       */
+    double  search[3];       /* search_{x,y,z}length                                         */
+} htb_mesh_geom;
+
+/* Work / timing counters filled by every engine call (all optional: pass NULL). */
+typedef struct htb_stats {
+    double   pairs_evaluated;   /* W_gpu: (i, j) pairs whose separation the kernel computed  */
+    double   pairs_reference;   /* W_ref: pairs the reference loop nest would visit          */
+    float    ms_h2d;            /* host->device copies                                       */
+    float    ms_mesh;           /* cell assignment + counting sort of both samples           */
+    float    ms_count;          /* the pair-counting kernel(s)                               */
+    float    ms_total;          /* whole call, CUDA-event timed on the engine's stream       */
+    int32_t  kernel_launches;   /* kernels launched by this call                             */
+    int32_t  tiles;             /* sample1 tiles processed                                   */
+    int32_t  tiles_redone;      /* tiles re-evaluated by the exact path (edge-ambiguous key) */
+    int32_t  refine1[3];        /* sub-divisions of each reference mesh1 cell                */
+    int32_t  refine2[3];        /* sub-divisions of each reference mesh2 cell                */
+    int32_t  path;              /* 1 = fast queue kernel, 0 = generic kernel                 */
+} htb_stats;
+
+const char *htb_last_error(void);
+int  htb_abi_version(void);
+/* number of visible CUDA devices (0 if none / driver missing) */
+int  htb_device_count(void);
+/* select the CUDA device used by subsequent calls from this thread */
+int  htb_set_device(int device);
+/* use an existing CUDA stream (cudaStream_t as void*) for subsequent calls; NULL = library stream */
+int  htb_set_stream(void *cuda_stream);
+
+/* npairs_3d_engine.pyx:17 — counts[k] = #{(i,j): dx^2+dy^2+dz^2 <= rbins[k]^2}, int64[nb]. */
+int htb_npairs_3d_engine(const htb_mesh_geom *mesh,
+                         const double *x1, const double *y1, const double *z1, int64_t stride1, int64_t n1,
+                         const double *x2, const double *y2, const double *z2, int64_t stride2, int64_t n2,
+                         const double *rbins, int32_t nb,
+                         int64_t first_cell1, int64_t last_cell1,
+                         int64_t *counts_out, uint32_t flags, htb_stats *stats);
+
+/* npairs_xy_z_engine.pyx:17 — counts[k,g] = #{dx^2+dy^2 <= rp[k]^2 and dz^2 <= pi[g]^2}, int64[nrp*npi]. */
+int htb_npairs_xy_z_engine(const htb_mesh_geom *mesh,
+                           const double *x1, const double *y1, const double *z1, int64_t stride1, int64_t n1,
+                           const double *x2, const double *y2, const double *z2, int64_t stride2, int64_t n2,
+                           const double *rp_bins, int32_t nrp, const double *pi_bins, int32_t npi,
+                           int64_t first_cell1, int64_t last_cell1,
+                           int64_t *counts_out, uint32_t flags, htb_stats *stats);
+
+/* npairs_s_mu_engine.pyx:18 — mu_bins are the sin(theta_los) edges the reference front-end
+ * passes down (npairs_s_mu.py:174-175); output int64[ns*nmu], 2-D cumulative.               */
+int htb_npairs_s_mu_engine(const htb_mesh_geom *mesh,
+                           const double *x1, const double *y1, const double *z1, int64_t stride1, int64_t n1,
+                           const double *x2, const double *y2, const double *z2, int64_t stride2, int64_t n2,
+                           const double *s_bins, int32_t ns, const double *mu_bins, int32_t nmu,
+                           int64_t first_cell1, int64_t last_cell1,
+                           int64_t *counts_out, uint32_t flags, htb_stats *stats);
+
+/* marked_npairs_3d_engine.pyx:22 — counts[k] = sum f_id(w1_i, w2_j) over dsq <= rbins[k]^2, f64[nb].
+ * w1, w2: row-major (n, nw) weights in the SAME (unsorted) order as the coordinates.          */
+int htb_marked_npairs_3d_engine(const htb_mesh_geom *mesh,
+                                const double *x1, const double *y1, const double *z1, int64_t stride1, int64_t n1,
+                                const double *x2, const double *y2, const double *z2, int64_t stride2, int64_t n2,
+                                const double *w1, const double *w2, int32_t nw, int32_t weight_func_id,
+                                const double *rbins, int32_t nb,
+                                int64_t first_cell1, int64_t last_cell1,
+                                double *counts_out, uint32_t flags, htb_stats *stats);
+
+/* mean_delta_sigma_engine.pyx:19 — per-object excess surface density, f64[n1*(nrp-1)], rows in
+ * the INPUT order of sample1 (the engine un-sorts at exit, :184-185); rows of galaxies whose
+ * mesh1 cell is outside [first_cell1, last_cell1) are zero, as in each reference worker.      */
+int htb_mean_delta_sigma_engine(const htb_mesh_geom *mesh,
+                                const double *x1, const double *y1, int64_t stride1, int64_t n1,
+                                const double *x2, const double *y2, int64_t stride2, const double *m2, int64_t n2,
+                                const double *rp_bins, int32_t nrp,
+                                int64_t first_cell1, int64_t last_cell1,
+                                double *delta_sigma_out, uint32_t flags, htb_stats *stats);
+
+/* RectangularMesh cell assignment alone (rectangular_mesh.py:19-22,211-225): writes the
+ * reference cell id of every point (int64[n]) — used by the mesh parity tests.               */
+int htb_mesh_cell_ids(int32_t ndim, const double *x, const double *y, const double *z, int64_t stride, int64_t n,
+                      const double *cell_size, const int32_t *ndivs, int64_t *cell_ids_out, uint32_t flags);
+
+/* RectangularMesh.cell_id_indices of a sample (int64[ncells+1]) computed by the GPU counting sort. */
+int htb_mesh_cell_id_indices(int32_t ndim, const double *x, const double *y, const double *z, int64_t stride, int64_t n,
+                             const double *cell_size, const int32_t *ndivs, int64_t *cell_id_indices_out, uint32_t flags);
+
+/* Predicted work (pairs the reference would visit) per reference mesh1 cell, f64[ncells1]:
+ * the partitioner input for sharding mesh1 cells over ranks (mesh_helpers.py:183-221).        */
+int htb_cell1_work(const htb_mesh_geom *mesh,
+                   const double *x1, const double *y1, const double *z1, int64_t stride1, int64_t n1,
+                   const double *x2, const double *y2, const double *z2, int64_t stride2, int64_t n2,
+                   double *work_out, uint32_t flags);
+
+/* Measured FP64 non-FMA issue rate (DADD/DMUL instr-lanes per second) of the current device. */
+int htb_measure_fp64_rate(double *ops_per_second_out, double *sm_clock_mhz_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HALOTOOLS_B200_H */

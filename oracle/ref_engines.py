@@ -1,0 +1,153 @@
+"""TEST INFRASTRUCTURE — drives the UNMODIFIED reference Cython engines in oracle/_ref.
+
+oracle/_ref holds only shared objects compiled by oracle/build_ref.py from the
+sources where they lie under /root/reference (nothing of the reference is in the
+repo).  On the GPU box the reference python front-ends are not available, so the
+engines are called the way the reference front-ends call them
+(/root/reference/halotools/mock_observables/pair_counters/npairs_3d.py:135-148):
+a double-mesh object, the unsorted coordinate arrays, the bins and a
+``(first_cell1, last_cell1)`` tuple; work is fanned out over a
+``multiprocessing.Pool`` and partial results are summed.  The double-mesh handed
+to the engine is oracle/mesh.py's restatement wearing the attribute names the
+engines read (npairs_3d_engine.pyx:47-96).
+
+Used as (1) an extra check of the C oracle, (2) ``cpu_baseline.kind ==
+"reference"`` / ``bench.py --impl reference``.
+"""
+import importlib
+import multiprocessing
+import os
+import sys
+from functools import partial
+
+import numpy as np
+
+from . import oracle as _o
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_REF = os.path.join(_HERE, "_ref")
+
+_ENGINE_MODULES = {
+    "npairs_3d_engine": "halotools.mock_observables.pair_counters.cpairs.npairs_3d_engine",
+    "npairs_xy_z_engine": "halotools.mock_observables.pair_counters.cpairs.npairs_xy_z_engine",
+    "npairs_s_mu_engine": "halotools.mock_observables.pair_counters.cpairs.npairs_s_mu_engine",
+    "marked_npairs_3d_engine": "halotools.mock_observables.pair_counters.marked_cpairs.marked_npairs_3d_engine",
+    "mean_delta_sigma_engine": "halotools.mock_observables.surface_density.engines.mean_delta_sigma_engine",
+}
+
+
+def available():
+    return os.path.isdir(os.path.join(_REF, "halotools"))
+
+
+def engine(name):
+    if not available():
+        raise RuntimeError("oracle/_ref is not built (run python oracle/build_ref.py where /root/reference exists)")
+    if "halotools" in sys.modules and not any(
+            os.path.abspath(p) == _REF for p in getattr(sys.modules["halotools"], "__path__", [])):
+        # a full reference tree is already imported (golden generation); use its engines
+        return getattr(importlib.import_module(_ENGINE_MODULES[name]), name)
+    if _REF not in sys.path:
+        sys.path.insert(0, _REF)
+    return getattr(importlib.import_module(_ENGINE_MODULES[name]), name)
+
+
+class _MeshView(object):
+    def __init__(self, m):
+        self.npts = m.npts
+        self.ncells = m.ncells
+        self.idx_sorted = m.idx_sorted
+        self.cell_id_indices = m.cell_id_indices
+        names = "xyz"
+        for d in range(m.ndim):
+            setattr(self, "num_%sdivs" % names[d], m.num_divs[d])
+            setattr(self, "%scell_size" % names[d], m.cell_size[d])
+            setattr(self, "%speriod" % names[d], m.period[d])
+
+
+class _DoubleMeshView(object):
+    def __init__(self, dm):
+        self.mesh1 = _MeshView(dm.mesh1)
+        self.mesh2 = _MeshView(dm.mesh2)
+        self._PBCs = dm.PBCs
+        names = "xyz"
+        for d in range(dm.ndim):
+            setattr(self, "%speriod" % names[d], dm.period[d])
+            setattr(self, "search_%slength" % names[d], dm.search[d])
+            setattr(self, "num_%scell2_per_%scell1" % (names[d], names[d]), dm.per[d])
+
+
+def _cell1_tuples(ncells, num_threads):
+    # pair_counters/mesh_helpers.py:183-221
+    if num_threads == 1:
+        return 1, [(0, ncells)]
+    if num_threads > ncells:
+        return ncells, [(a, a + 1) for a in range(ncells)]
+    parts = [a for a in np.array_split(np.arange(ncells), num_threads) if len(a) > 0]
+    return num_threads, [(int(a[0]), int(a[0]) + len(a)) for a in parts]
+
+
+def _run(eng, ncells, num_threads, cell1_range=None):
+    if cell1_range is not None:
+        first, last = int(cell1_range[0]), int(cell1_range[1])
+        if num_threads == 1:
+            return eng((first, last))
+        nt, tuples = _cell1_tuples(last - first, num_threads)
+        tuples = [(a + first, b + first) for a, b in tuples]
+    else:
+        nt, tuples = _cell1_tuples(ncells, num_threads)
+    if nt > 1:
+        pool = multiprocessing.Pool(nt)
+        try:
+            result = pool.map(eng, tuples)
+        finally:
+            pool.close()
+            pool.join()
+        return np.sum(np.array(result), axis=0)
+    return eng(tuples[0])
+
+
+def npairs_3d(sample1, sample2, rbins, period=None, approx_cell1_size=None, approx_cell2_size=None,
+              num_threads=1, cell1_range=None):
+    rbins = np.atleast_1d(rbins).astype("f8")
+    rmax = float(np.max(rbins))
+    dm, c1, c2 = _o.build_double_mesh_3d(sample1, sample2, [rmax] * 3, period, approx_cell1_size, approx_cell2_size)
+    eng = partial(engine("npairs_3d_engine"), _DoubleMeshView(dm), c1[0], c1[1], c1[2], c2[0], c2[1], c2[2], rbins)
+    return np.array(_run(eng, dm.mesh1.ncells, num_threads, cell1_range))
+
+
+def npairs_xy_z(sample1, sample2, rp_bins, pi_bins, period=None, approx_cell1_size=None,
+                approx_cell2_size=None, num_threads=1, cell1_range=None):
+    rp_bins = np.atleast_1d(rp_bins).astype("f8")
+    pi_bins = np.atleast_1d(pi_bins).astype("f8")
+    rp_max, pi_max = float(np.max(rp_bins)), float(np.max(pi_bins))
+    dm, c1, c2 = _o.build_double_mesh_3d(sample1, sample2, [rp_max, rp_max, pi_max], period,
+                                         approx_cell1_size, approx_cell2_size)
+    eng = partial(engine("npairs_xy_z_engine"), _DoubleMeshView(dm), c1[0], c1[1], c1[2], c2[0], c2[1], c2[2],
+                  rp_bins, pi_bins)
+    return np.array(_run(eng, dm.mesh1.ncells, num_threads, cell1_range))
+
+
+def npairs_s_mu(sample1, sample2, s_bins, mu_bins, period=None, approx_cell1_size=None,
+                approx_cell2_size=None, num_threads=1):
+    s_bins = np.atleast_1d(s_bins).astype("f8")
+    rmax = float(np.max(s_bins))
+    mu_prime = np.sort(np.sin(np.arccos(np.atleast_1d(mu_bins))))
+    dm, c1, c2 = _o.build_double_mesh_3d(sample1, sample2, [rmax] * 3, period, approx_cell1_size, approx_cell2_size)
+    eng = partial(engine("npairs_s_mu_engine"), _DoubleMeshView(dm), c1[0], c1[1], c1[2], c2[0], c2[1], c2[2],
+                  s_bins, mu_prime)
+    return np.array(_run(eng, dm.mesh1.ncells, num_threads))
+
+
+def marked_npairs_3d(sample1, sample2, rbins, weight_func_id, period=None, weights1=None, weights2=None,
+                     approx_cell1_size=None, approx_cell2_size=None, num_threads=1, cell1_range=None):
+    rbins = np.atleast_1d(rbins).astype("f8")
+    rmax = float(np.max(rbins))
+    nw = _o.NUM_WEIGHTS[int(weight_func_id)]
+    n1, n2 = np.shape(sample1)[0], np.shape(sample2)[0]
+    w1 = np.ones((n1, nw)) if weights1 is None else np.asarray(weights1, dtype=np.float64).reshape(n1, nw)
+    w2 = np.ones((n2, nw)) if weights2 is None else np.asarray(weights2, dtype=np.float64).reshape(n2, nw)
+    dm, c1, c2 = _o.build_double_mesh_3d(sample1, sample2, [rmax] * 3, period, approx_cell1_size, approx_cell2_size)
+    eng = partial(engine("marked_npairs_3d_engine"), _DoubleMeshView(dm), c1[0], c1[1], c1[2], c2[0], c2[1], c2[2],
+                  w1, w2, int(weight_func_id), rbins)
+    return np.array(_run(eng, dm.mesh1.ncells, num_threads, cell1_range))
