@@ -107,6 +107,21 @@ class Columns(object):
     """
 
     def __init__(self, cols):
+        self.device = all(getattr(c, "is_cuda", False) for c in cols)
+        if self.device:
+            # torch CUDA tensors (column views of an (N, ndim) float64 tensor): pass device pointers
+            import torch
+            n = int(cols[0].shape[0])
+            if not all(c.dtype == torch.float64 and c.dim() == 1 and int(c.shape[0]) == n for c in cols):
+                raise TypeError("device samples must be float64 CUDA tensors of shape (Npts, ndim)")
+            strides = set(int(c.stride(0)) for c in cols) if n > 0 else {1}
+            if len(strides) != 1:
+                raise TypeError("device sample columns must share one stride")
+            self.cols = cols
+            self.n = n
+            self.stride = list(strides)[0]
+            self.ptrs = [ctypes.cast(ctypes.c_void_p(int(c.data_ptr())), ctypes.POINTER(ctypes.c_double)) for c in cols]
+            return
         cols = [np.asarray(c) for c in cols]
         n = cols[0].shape[0]
         ok = all(c.dtype == np.float64 and c.ndim == 1 and c.shape[0] == n for c in cols)
@@ -125,12 +140,13 @@ class Columns(object):
         self.ptrs = [_dp(c) for c in cols]
 
 
-def run_engine(func_name, *args):
+def run_engine(func_name, *args, **kw):
     """Call an engine entry point, appending (flags, stats) and recording the stats."""
     global last_stats
     lib = require_gpu()
     st = Stats()
-    rc = getattr(lib, func_name)(*args, ctypes.c_uint32(default_flags),
+    flags = default_flags | (FLAG_DEVICE_INPUT if kw.get("device") else 0)
+    rc = getattr(lib, func_name)(*args, ctypes.c_uint32(flags),
                                  ctypes.byref(st) if collect_stats else None)
     check(rc)
     last_stats = st.as_dict() if collect_stats else None

@@ -48,7 +48,7 @@ def npairs_3d(sample1, sample2, rbins, period=None, num_threads=1,
         c1.ptrs[0], c1.ptrs[1], c1.ptrs[2], ctypes.c_int64(c1.stride), ctypes.c_int64(c1.n),
         c2.ptrs[0], c2.ptrs[1], c2.ptrs[2], ctypes.c_int64(c2.stride), ctypes.c_int64(c2.n),
         _lib._dp(rb), ctypes.c_int32(len(rb)), ctypes.c_int64(first), ctypes.c_int64(last),
-        counts.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)))
+        counts.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), device=c1.device)
     return np.array(_dist.allreduce_sum(counts))
 
 
@@ -80,6 +80,8 @@ def _npairs_3d_process_args(sample1, sample2, rbins, period,
         raise ValueError(msg)
 
     if period is None:
+        if getattr(sample1, "is_cuda", False) or getattr(sample2, "is_cuda", False):
+            raise ValueError("device-resident samples need an explicit ``period``")
         PBCs = False
         x1, y1, z1, x2, y2, z2, period = (
             _enclose_in_box(x1, y1, z1, x2, y2, z2,

@@ -1,0 +1,211 @@
+"""GPU parity tests (pytest -m gpu): the CUDA path, called through the public functions and hence
+through the C ABI of libhalotools_b200.so, against (1) the golden vectors of the unmodified
+reference, (2) the CPU oracle on the same seeded inputs, (3) size-independent properties at larger
+sizes.  Integer counts must be IDENTICAL; float sums within the tolerance written in each test."""
+import numpy as np
+import pytest
+
+import halotools_b200 as hb
+from halotools_b200 import _lib
+from oracle import oracle
+from tests.golden import cases
+
+pytestmark = pytest.mark.gpu
+
+INT_FUNCS = ("npairs_3d", "npairs_xy_z", "npairs_s_mu")
+ALL = cases.names()
+
+
+def run_gpu(name, flags=0):
+    fn, args, kwargs = cases.get(name)
+    old = _lib.default_flags
+    _lib.default_flags = flags
+    try:
+        return cases.flatten(getattr(hb, fn)(*args, **kwargs))
+    finally:
+        _lib.default_flags = old
+
+
+def compare(fn, got, want):
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert g.shape == w.shape, (g.shape, w.shape)
+        if fn in INT_FUNCS:
+            assert g.dtype == np.int64
+            assert np.array_equal(g, w), (g, w)
+        elif fn == "marked_npairs_3d":
+            # float sums, order differs from the reference's serial loop: 1e-12 relative (north_star)
+            assert np.allclose(g, w, rtol=1e-12, atol=0), (g, w)
+        elif fn == "mean_delta_sigma":
+            # cancelling difference of large sums: abs + rel tolerance (SURVEY.md 8d parity gates)
+            scale = np.max(np.abs(w))
+            assert np.allclose(g, w, rtol=1e-10, atol=1e-12 * scale), np.max(np.abs(g - w))
+        else:
+            # estimators over identical counts
+            assert np.allclose(g, w, rtol=1e-10, atol=1e-12, equal_nan=True), (g, w)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_matches_reference_golden(name, golden):
+    fn = cases._cases()[name][0]
+    compare(fn, run_gpu(name), golden(name))
+
+
+ENGINE_INT = [n for n in ALL if cases._cases()[n][0] in INT_FUNCS and n != "n3d_c1_full"]
+
+
+@pytest.mark.parametrize("name", ENGINE_INT)
+@pytest.mark.parametrize("flags", [_lib.FLAG_GENERIC, _lib.FLAG_NO_CULL, _lib.FLAG_GENERIC | _lib.FLAG_NO_CULL])
+def test_kernel_variants_agree(name, flags, golden):
+    fn = cases._cases()[name][0]
+    compare(fn, run_gpu(name, flags), golden(name))
+
+
+def test_fast_path_taken_and_culling_reduces_work():
+    fn, args, kwargs = cases.get("n3d_c1_small")
+    hb.npairs_3d(*args, **kwargs)
+    st = dict(_lib.last_stats)
+    assert st["path"] == 1
+    assert st["pairs_evaluated"] > 0
+    assert st["pairs_evaluated"] <= st["pairs_reference"]
+    _, dm = oracle.npairs_3d(*args, return_mesh=True, **kwargs)
+    assert st["pairs_reference"] == dm.visited_pairs()
+    old = _lib.default_flags
+    _lib.default_flags = _lib.FLAG_NO_CULL
+    try:
+        hb.npairs_3d(*args, **kwargs)
+    finally:
+        _lib.default_flags = old
+    assert _lib.last_stats["pairs_evaluated"] == st["pairs_reference"]
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_geometries_vs_oracle(seed):
+    rng = np.random.RandomState(seed)
+    n1, n2 = rng.randint(1, 3000), rng.randint(1, 3000)
+    L = float(rng.uniform(0.5, 300.0))
+    period = [L, L * rng.uniform(1.0, 2.0), L * rng.uniform(1.0, 3.0)] if seed != 2 else None
+    ext = np.array(period) if period is not None else np.array([L, L, L])
+    s1 = rng.uniform(0, 1, (n1, 3)) * ext
+    s2 = rng.uniform(0, 1, (n2, 3)) * ext
+    rmax = L / rng.uniform(3.0, 12.0)
+    rbins = np.sort(rng.uniform(0.0, rmax, rng.randint(2, 16)))
+    rbins[-1] = rmax
+    want = oracle.npairs_3d(s1, s2, rbins, period=period)
+    got = hb.npairs_3d(s1, s2, rbins, period=period)
+    assert np.array_equal(got, want)
+    rp, pi = rbins, np.sort(rng.uniform(0.0, rmax, 3))
+    assert np.array_equal(hb.npairs_xy_z(s1, s2, rp, pi, period=period), oracle.npairs_xy_z(s1, s2, rp, pi, period=period))
+
+
+def test_dense_sample_many_tiles_vs_oracle():
+    # dense enough that the refined grids (m > 1) and multi-tile columns are exercised
+    s1 = cases.pts(5, 60000, 100.0)
+    s2 = cases.pts(6, 80000, 100.0)
+    rbins = np.logspace(-1, np.log10(10.0), 15)
+    got = hb.npairs_3d(s1, s2, rbins, period=100.0)
+    st = dict(_lib.last_stats)
+    want = oracle.npairs_3d(s1, s2, rbins, period=100.0, num_threads=8)
+    assert np.array_equal(got, want)
+    assert max(st["refine2"]) > 1 and st["pairs_evaluated"] < st["pairs_reference"]
+
+
+def test_empty_and_tiny_inputs():
+    rbins = np.array([0.1, 0.2, 0.3])
+    one = np.array([[0.5, 0.5, 0.5]])
+    assert np.array_equal(hb.npairs_3d(one, one, rbins, period=1.0), [1, 1, 1])
+    two = np.array([[0.05, 0.5, 0.5], [0.95, 0.5, 0.5]])
+    assert np.array_equal(hb.npairs_3d(two, two, rbins, period=1.0), [2, 4, 4])
+    assert np.array_equal(hb.npairs_3d(two, two, rbins, period=None), oracle.npairs_3d(two, two, rbins, period=None))
+    empty = np.zeros((0, 3))
+    assert np.array_equal(hb.npairs_3d(empty, one, rbins, period=1.0), [0, 0, 0])
+    assert np.array_equal(hb.npairs_3d(one, empty, rbins, period=1.0), [0, 0, 0])
+
+
+def test_float32_and_strided_inputs():
+    s1, s2 = cases.pts(43, 500).astype(np.float32), cases.pts(44, 500)[::2]
+    rbins = np.array([0.05, 0.1, 0.2])
+    want = oracle.npairs_3d(s1.astype(np.float64), s2, rbins, period=1.0)
+    assert np.array_equal(hb.npairs_3d(s1, s2, rbins, period=1.0), want)
+    fortran = np.asfortranarray(cases.pts(45, 400))
+    assert np.array_equal(hb.npairs_3d(fortran, fortran, rbins, period=1.0),
+                          oracle.npairs_3d(fortran, fortran, rbins, period=1.0))
+
+
+def test_cell1_ranges_are_additive():
+    """The reference's parallelisation unit (cell1_tuple) is the multi-GPU shard: partial counts add up."""
+    import ctypes
+    from halotools_b200.pair_counters.mesh_helpers import double_mesh_geometry
+    s1, s2 = cases.pts(43, 3000, 100.0), cases.pts(44, 3000, 100.0)
+    rbins = np.logspace(-1, 1, 10)
+    geom = double_mesh_geometry(3, [10.0] * 3, [10.0] * 3, [10.0] * 3, [100.0] * 3, True)
+    g = geom.as_struct()
+    c1, c2 = _lib.Columns([s1[:, 0], s1[:, 1], s1[:, 2]]), _lib.Columns([s2[:, 0], s2[:, 1], s2[:, 2]])
+    total = np.zeros(len(rbins), dtype=np.int64)
+    nc = geom.ncells1
+    for a, b in ((0, nc // 4), (nc // 4, nc // 4), (nc // 4, nc - 7), (nc - 7, nc)):
+        part = np.zeros(len(rbins), dtype=np.int64)
+        _lib.run_engine("htb_npairs_3d_engine", ctypes.byref(g),
+                        c1.ptrs[0], c1.ptrs[1], c1.ptrs[2], ctypes.c_int64(c1.stride), ctypes.c_int64(c1.n),
+                        c2.ptrs[0], c2.ptrs[1], c2.ptrs[2], ctypes.c_int64(c2.stride), ctypes.c_int64(c2.n),
+                        _lib._dp(rbins), ctypes.c_int32(len(rbins)), ctypes.c_int64(a), ctypes.c_int64(b),
+                        part.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)))
+        total += part
+    assert np.array_equal(total, oracle.npairs_3d(s1, s2, rbins, period=100.0))
+
+
+def test_mesh_cell_ids_and_offsets_match_numpy_semantics():
+    import ctypes
+    from oracle.mesh import Mesh
+    L, nd = 250.0, 12
+    cs = L / nd
+    edge = np.array([cs * k for k in range(nd + 1)])          # exact multiples: floor-division quirk
+    rng = np.random.RandomState(3)
+    x = np.concatenate([edge, rng.uniform(0, L, 5000), np.nextafter(edge, 0), np.nextafter(edge, L)])
+    x = np.clip(x, 0, L)
+    y = rng.permutation(x)
+    z = rng.permutation(x)
+    m = Mesh([x, y, z], [L, L, L], [cs, cs, cs])
+    ids = np.zeros(len(x), dtype=np.int64)
+    cell = (ctypes.c_double * 3)(cs, cs, cs)
+    ndv = (ctypes.c_int32 * 3)(nd, nd, nd)
+    lib = _lib.require_gpu()
+    cols = _lib.Columns([x, y, z])
+    _lib.check(lib.htb_mesh_cell_ids(3, cols.ptrs[0], cols.ptrs[1], cols.ptrs[2], ctypes.c_int64(1),
+                                     ctypes.c_int64(len(x)), cell, ndv,
+                                     ids.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), ctypes.c_uint32(0)))
+    assert np.array_equal(ids, m.cell_ids)
+    cii = np.zeros(m.ncells + 1, dtype=np.int64)
+    _lib.check(lib.htb_mesh_cell_id_indices(3, cols.ptrs[0], cols.ptrs[1], cols.ptrs[2], ctypes.c_int64(1),
+                                            ctypes.c_int64(len(x)), cell, ndv,
+                                            cii.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), ctypes.c_uint32(0)))
+    assert np.array_equal(cii, m.cell_id_indices)
+
+
+def test_linearity_and_symmetry_properties_large():
+    """Size-independent properties at a size the oracle would take long for: counts are additive over
+    a split of sample2 and symmetric under swapping the samples."""
+    s1, s2 = cases.pts(11, 200000, 500.0), cases.pts(12, 300000, 500.0)
+    rbins = np.logspace(-1, np.log10(25.0), 15)
+    full = hb.npairs_3d(s1, s2, rbins, period=500.0)
+    a = hb.npairs_3d(s1, s2[:100000], rbins, period=500.0)
+    b = hb.npairs_3d(s1, s2[100000:], rbins, period=500.0)
+    assert np.array_equal(a + b, full)
+    assert np.array_equal(hb.npairs_3d(s2, s1, rbins, period=500.0), full)
+    auto = hb.npairs_3d(s1, s1, rbins, period=500.0)
+    assert auto[0] >= len(s1) and np.all(np.diff(auto) >= 0) and np.all((auto - len(s1)) % 2 == 0)
+
+
+def test_marked_integer_weights_exact(golden):
+    got = run_gpu("marked_grid_integer")[0]
+    assert np.array_equal(got, golden("marked_grid_integer")[0])
+
+
+def test_delta_sigma_rows_follow_input_order():
+    gal, ptcl = cases.pts(43, 300, 1.0), cases.pts(44, 20000, 1.0)
+    rpb = np.logspace(np.log10(0.02), np.log10(0.25), 8)
+    base = hb.mean_delta_sigma(gal, ptcl, 1.0, rpb, period=1.0, per_object=True)
+    perm = np.random.RandomState(0).permutation(len(gal))
+    shuffled = hb.mean_delta_sigma(gal[perm], ptcl, 1.0, rpb, period=1.0, per_object=True)
+    scale = np.max(np.abs(base))
+    assert np.allclose(shuffled, base[perm], rtol=1e-10, atol=1e-12 * scale)

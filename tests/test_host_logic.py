@@ -1,0 +1,223 @@
+"""CPU tests (no GPU) of the host layer: argument validation with the reference's error types and
+message fragments (the strings the reference's own tests assert on), mesh geometry against the
+oracle's restatement, estimators, the C-ABI library (loads, exports every declared symbol, no compute
+call), and the multi-rank sharding logic over gloo with world_size 2."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import halotools_b200 as hb
+from halotools_b200 import _lib, distributed
+from halotools_b200.custom_exceptions import HalotoolsError
+from halotools_b200.pair_counters.mesh_helpers import double_mesh_geometry, _cell1_parallelization_indices
+from halotools_b200.pair_counters.npairs_3d import _npairs_3d_process_args
+from halotools_b200.pair_counters.marked_npairs_3d import _marked_npairs_process_weights, _func_signature_int_from_wfunc
+from halotools_b200.two_point_clustering.tpcf_estimators import _TP_estimator, _TP_estimator_crossx
+from oracle import oracle
+from oracle.mesh import DoubleMesh
+from tests.golden import cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+S = cases.pts(43, 100)
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _lib.load()
+    assert lib.htb_abi_version() == 1
+    header = open(os.path.join(ROOT, "include", "halotools_b200.h")).read()
+    declared = set(re.findall(r"^(?:const char \*|int\s+)(htb_[a-z0-9_]+)\s*\(", header, flags=re.M))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name)
+    assert ctypes.sizeof(_lib.MeshGeom) == 2 * 4 + 3 * 3 * 4 + 4 + 4 * 3 * 8
+    assert isinstance(lib.htb_device_count(), int)
+
+
+def test_no_cpu_fallback_without_gpu():
+    if _lib.load().htb_device_count() > 0:
+        pytest.skip("a GPU is visible")
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        hb.npairs_3d(S, S, [0.1, 0.2], period=1.0)
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        hb.mean_delta_sigma(S, S, 1.0, [0.1, 0.2], period=1.0)
+
+
+def test_product_does_not_import_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "halotools_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("# oracle", ""), os.path.join(dirpath, f)
+
+
+@pytest.mark.parametrize("bad", [2.5, "Cuba Gooding Jr.", np.int64(2)])
+def test_num_threads_validation(bad):
+    with pytest.raises(ValueError, match="Input ``num_threads`` argument must be an integer or the string 'max'"):
+        hb.npairs_3d(S, S, [0.1, 0.2], period=1.0, num_threads=bad)
+    with pytest.raises(ValueError, match="num_threads"):
+        hb.npairs_xy_z(S, S, [0.1, 0.2], [0.1, 0.2], period=1.0, num_threads=bad)
+
+
+def test_rbins_and_period_validation():
+    with pytest.raises(ValueError, match="Input ``rbins`` must be a monotonically increasing 1D array with at least two entries"):
+        hb.npairs_3d(S, S, [0.1], period=1.0)
+    with pytest.raises(ValueError, match="rbins"):
+        hb.npairs_3d(S, S, [0.1, 0.3, 0.2], period=1.0)
+    with pytest.raises(ValueError, match="Input ``period`` must be a bounded positive number in all dimensions"):
+        hb.npairs_3d(S, S, [0.1, 0.2], period=[1.0, 1.0, np.inf])
+    with pytest.raises(ValueError, match="period"):
+        hb.npairs_3d(S, S, [0.1, 0.2], period=-1.0)
+    with pytest.raises(ValueError, match="The maximum length over which you search for pairs of points"):
+        hb.npairs_3d(S, S, [0.1, 0.4], period=1.0)
+    with pytest.raises(ValueError, match="rp_bins"):
+        hb.npairs_xy_z(S, S, [0.1], [0.1, 0.2], period=1.0)
+    with pytest.raises(ValueError, match="pi_bins"):
+        hb.npairs_xy_z(S, S, [0.1, 0.2], [0.2, 0.1, 0.3], period=1.0)
+    with pytest.raises(ValueError, match="mu_bins"):
+        hb.npairs_s_mu(S, S, [0.1, 0.2], [0.5], period=1.0)
+    with pytest.raises(ValueError, match="must be a length-3 sequence"):
+        hb.npairs_3d(S, S, [0.1, 0.2], period=1.0, approx_cell1_size=[0.1, 0.1])
+
+
+def test_process_args_defaults():
+    r = _npairs_3d_process_args(S, S, [0.1, 0.25], None, 1, None, None)
+    period, pbcs = r[7], r[9]
+    assert pbcs is False and np.allclose(period, max(np.ptp(S), 0.75))
+    assert r[10] == [0.25, 0.25, 0.25] and r[11] == [0.25, 0.25, 0.25]
+    assert min(np.min(c) for c in r[:6]) == 0.0
+    r = _npairs_3d_process_args(S, S, [0.1, 0.25], 2.0, "max", 0.3, [0.1, 0.2, 0.3])
+    assert np.array_equal(r[7], [2.0, 2.0, 2.0]) and r[9] is True and r[10] == [0.3, 0.3, 0.3]
+
+
+def test_weights_validation():
+    for wid, nw in cases.NUM_WEIGHTS.items():
+        assert _func_signature_int_from_wfunc(wid) == nw
+        w1, w2 = _marked_npairs_process_weights(S, S, np.ones((100, nw)), None, wid)
+        assert w1.shape == (100, nw) and w2.shape == (100, nw) and np.all(w2 == 1)
+        with pytest.raises(HalotoolsError):
+            _marked_npairs_process_weights(S, S, np.ones((100, nw + 1)), None, wid)
+    with pytest.raises(HalotoolsError, match="does not have the correct length"):
+        _marked_npairs_process_weights(S, S, np.ones(99), None, 1)
+    with pytest.raises(HalotoolsError, match="is not recognized"):
+        _func_signature_int_from_wfunc(18)
+    with pytest.raises(ValueError, match="must be an integer ID"):
+        _func_signature_int_from_wfunc(1.0)
+    with pytest.raises(HalotoolsError, match="1-D or 2-D array"):
+        _marked_npairs_process_weights(S, S, np.ones((100, 1, 1)), None, 1)
+
+
+def test_clustering_level_validation():
+    rb = np.logspace(-2, -1, 5)
+    with pytest.raises(TypeError, match="Input sample of points must be a Numpy ndarray of shape"):
+        hb.tpcf(np.ones((10, 2)), rb, period=1.0)
+    with pytest.raises(TypeError, match="strictly positive"):
+        hb.tpcf(S, [0.0, 0.1, 0.2], period=1.0)
+    with pytest.raises(ValueError, match="If no PBCs are specified, randoms must be provided"):
+        hb.tpcf(S, rb, period=None)
+    with pytest.raises(ValueError, match="is not in the list of available estimators"):
+        hb.tpcf(S, rb, period=1.0, estimator="Jose Canseco")
+    with pytest.raises(ValueError, match="does not permit you to look for pairs"):
+        hb.tpcf(S, [0.1, 0.4], period=1.0)
+    with pytest.raises(HalotoolsError, match="You must either provide both"):
+        hb.tpcf(S, rb, period=1.0, RR_precomputed=np.ones(4))
+    with pytest.raises(HalotoolsError, match="must match length"):
+        hb.tpcf(S, rb, period=1.0, randoms=S, RR_precomputed=np.ones(3), NR_precomputed=100)
+    with pytest.raises(ValueError, match="`normalize_by` parameter not recognized"):
+        hb.marked_tpcf(S, rb, period=1.0, normalize_by="Arnold Schwarzenegger")
+    with pytest.raises(HalotoolsError, match="`marks1` must have same length as `sample1`"):
+        hb.marked_tpcf(S, rb, period=1.0, marks1=np.ones(7))
+    with pytest.raises(ValueError, match="there are values in the x-dimension"):
+        hb.mean_delta_sigma(S + np.array([1.0, 0, 0]), S, 1.0, rb, period=1.0)
+    with pytest.raises(ValueError, match="your input data has negative values"):
+        hb.mean_delta_sigma(S - 0.5, S, 1.0, rb, period=1.0)
+
+
+@pytest.mark.parametrize("n1", [1, 7, 60])
+@pytest.mark.parametrize("L,search", [(1.0, 0.3), (250.0, 20.0), (1000.0, 30.0), (3.0, 1.0)])
+@pytest.mark.parametrize("a1,a2", [(None, None), (0.07, 0.013), (0.5, 0.25)])
+def test_mesh_geometry_matches_oracle_mesh(n1, L, search, a1, a2):
+    pts1 = cases.pts(1, n1, L)
+    ac1 = [search] * 3 if a1 is None else [a1 * L] * 3
+    ac2 = [search] * 3 if a2 is None else [a2 * L] * 3
+    geom = double_mesh_geometry(3, ac1, ac2, [search] * 3, [L] * 3, True)
+    dm = DoubleMesh([pts1[:, d] for d in range(3)], [pts1[:, d] for d in range(3)], ac1, ac2, [search] * 3, [L] * 3, True)
+    assert geom.ndivs1 == dm.mesh1.num_divs and geom.ndivs2 == dm.mesh2.num_divs
+    assert geom.cell1_size == dm.mesh1.cell_size and geom.cell2_size == dm.mesh2.cell_size
+    assert geom.cover == dm.cover
+    for d in range(3):
+        assert geom.ndivs2[d] % geom.ndivs1[d] == 0 and geom.ndivs1[d] >= 3 and geom.ndivs2[d] <= 50
+        assert geom.cell1_size[d] >= search * (1 - 1e-12)
+
+
+def test_reference_mesh_configs():
+    # SURVEY.md 8a row a2
+    assert double_mesh_geometry(3, [20.0] * 3, [20.0] * 3, [20.0] * 3, [250.0] * 3, True).ndivs1 == [12, 12, 12]
+    assert double_mesh_geometry(3, [30.0, 30.0, 60.0], [30.0, 30.0, 60.0], [30.0, 30.0, 60.0], [1000.0] * 3, True).ndivs1 == [33, 33, 16]
+    assert double_mesh_geometry(3, [20.0] * 3, [20.0] * 3, [20.0] * 3, [1000.0] * 3, True).ndivs1 == [50, 50, 50]
+    assert double_mesh_geometry(2, [30.0] * 2, [30.0] * 2, [30.0] * 2, [1000.0] * 2, True).ndivs1 == [33, 33]
+
+
+def test_cell1_parallelization_indices():
+    assert _cell1_parallelization_indices(10, 1) == (1, [(0, 10)])
+    n, t = _cell1_parallelization_indices(3, 5)
+    assert n == 3 and t == [(0, 1), (1, 2), (2, 3)]
+    n, t = _cell1_parallelization_indices(10, 3)
+    assert t == [(0, 4), (4, 7), (7, 10)]
+    assert distributed.split_cells(10, 3) == [(0, 4), (4, 7), (7, 10)]
+    work = np.array([0, 0, 10, 0, 0, 10, 0, 0, 10, 10.0])
+    parts = distributed.split_cells(10, 2, work)
+    assert parts[0][0] == 0 and parts[-1][1] == 10 and parts[0][1] == parts[1][0]
+    assert abs(work[parts[0][0]:parts[0][1]].sum() - 20.0) <= 10.0
+
+
+def test_estimators():
+    DD, DR, RR = np.array([10.0, 20.0]), np.array([5.0, 8.0]), np.array([4.0, 2.0])
+    assert np.allclose(_TP_estimator(DD, DR, RR, 10, 10, 20, 20, "Natural"), DD / RR * 4 - 1)
+    assert np.allclose(_TP_estimator(DD, DR, RR, 10, 10, 20, 20, "Landy-Szalay"), DD / RR * 4 - 2 * DR / RR * 2 + 1)
+    assert np.allclose(_TP_estimator(DD, DR, RR, 10, 10, 20, 20, "Hamilton"), DD * RR / DR ** 2 - 1)
+    assert np.allclose(_TP_estimator_crossx(DD, DR, DR, RR, 10, 10, 20, 20, "Hamilton"), DD * RR / DR ** 2 - 1)
+    with pytest.raises(ValueError, match="zero RR pairs"):
+        _TP_estimator(DD, DR, np.array([0.0, 1.0]), 10, 10, 20, 20, "Natural")
+    with pytest.raises(ValueError, match="zero DR pairs"):
+        _TP_estimator(DD, np.array([0.0, 1.0]), RR, 10, 10, 20, 20, "Hamilton")
+    with pytest.raises(ValueError, match="not supported for cross-correlations"):
+        _TP_estimator_crossx(DD, DR, DR, RR, 10, 10, 20, 20, "Hewett")
+
+
+GLOO_WORKER = r'''
+import os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, %(root)r)
+from halotools_b200 import distributed
+from oracle import oracle
+from tests.golden import cases
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=int(sys.argv[1]), world_size=2)
+distributed.enable()
+fn, args, kwargs = cases.get("n3d_periodic")
+_, dm = oracle.npairs_3d(*args, return_mesh=True, **kwargs)
+first, last = distributed.cell1_range(dm.mesh1.ncells)
+part = oracle.npairs_3d(*args, cell1_range=(first, last), **kwargs)     # stands in for this rank's GPU
+total = distributed.allreduce_sum(part)
+assert np.array_equal(total, oracle.npairs_3d(*args, **kwargs)), (total, part)
+assert first < last and (first == 0 or last == dm.mesh1.ncells)
+dist.destroy_process_group()
+print("rank", sys.argv[1], "ok", first, last)
+'''
+
+
+def test_two_rank_sharding_over_gloo(tmp_path):
+    port = 29500 + (os.getpid() % 2000)
+    script = tmp_path / "worker.py"
+    script.write_text(GLOO_WORKER % {"root": ROOT, "port": port})
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(2)]
+    outs = [p.communicate(timeout=240)[0].decode() for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert "ok" in o
