@@ -162,6 +162,8 @@ k_count(const __grid_constant__ WalkGeom G, const __grid_constant__ WalkArrays A
 }
 
 // ------------------------------------------------------------------ Fast3
+// Queue capacity per lane.  Between two capacity checks a lane pushes at most 10 keys (one odd
+// leading j = 2, one group of 4 j = 8; the tail of <= 3 j = 6), so the flush threshold is QCAP - 10.
 #define QCAP 32
 struct Fast3 {
     static constexpr int DIM = 3, NPAY = 0, WARPS = 8, MINBLOCKS = 2;
@@ -266,14 +268,14 @@ struct Fast3 {
                     pair_fast(xs0, ys0, zs0, xb, yb, zb);
                     pair_fast(xs1, ys1, zs1, xb, yb, zb);
                 }
-                if (__any_sync(HTB_FULL, qptr > qbase + 128u * (QCAP - 8))) flush();
+                if (__any_sync(HTB_FULL, qptr > qbase + 128u * (QCAP - 10))) flush();
             }
             for (; j < hi; ++j) {
                 const double xj = lds_f64(bx + 8 * j), yj = lds_f64(by + 8 * j), zj = lds_f64(bz + 8 * j);
                 pair_fast(xs0, ys0, zs0, xj, yj, zj);
                 pair_fast(xs1, ys1, zs1, xj, yj, zj);
             }
-            if (__any_sync(HTB_FULL, qptr > qbase + 128u * (QCAP - 8))) flush();
+            if (__any_sync(HTB_FULL, qptr > qbase + 128u * (QCAP - 10))) flush();
         } else {
             for (int j = lo; j < hi; ++j) {
                 const double xj = lds_f64(bx + 8 * j), yj = lds_f64(by + 8 * j), zj = lds_f64(bz + 8 * j);
