@@ -205,6 +205,8 @@ def run_gpu(args):
             acc["launches"] += st["kernel_launches"]
             acc["count_evaluated"].append(st["pairs_evaluated"])
             acc["count_ms"].append(st["ms_count"])
+            acc.setdefault("calls", []).append({k: st[k] for k in ("ms_h2d", "ms_mesh", "ms_count", "ms_total", "tiles",
+                                                                   "tiles_redone", "refine1", "refine2")})
         xi = landy_szalay(out[0], out[1], out[2], N, NR)
         stats_acc.update(acc)
         return xi
@@ -221,7 +223,10 @@ def run_gpu(args):
             e0.record(stream)
             res = None
             for _ in range(steps):
+                t0 = time.perf_counter()
                 res = fn()
+                if os.environ.get("HTB_BENCH_VERBOSE"):
+                    sys.stderr.write("step wall %.1f ms %s\n" % ((time.perf_counter() - t0) * 1e3, json.dumps(stats_acc.get("calls"))))
             e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
@@ -284,7 +289,8 @@ def run_gpu(args):
                         "ms_per_step": ms_e2e},
                 "gpu_launches": int(acc["launches"] * args.steps),
                 "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-                "breakdown_ms": {"mesh_sort": acc["ms_mesh"], "count_kernels": acc["ms_count"]}}
+                "breakdown_ms": {"mesh_sort": acc["ms_mesh"], "count_kernels": acc["ms_count"]},
+                "calls": acc.get("calls")}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

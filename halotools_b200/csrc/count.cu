@@ -164,7 +164,7 @@ k_count(const __grid_constant__ WalkGeom G, const __grid_constant__ WalkArrays A
 // ------------------------------------------------------------------ Fast3
 // Queue capacity per lane.  Between two capacity checks a lane pushes at most 10 keys (one odd
 // leading j = 2, one group of 4 j = 8; the tail of <= 3 j = 6), so the flush threshold is QCAP - 10.
-#define QCAP 32
+#define QCAP 64
 struct Fast3 {
     static constexpr int DIM = 3, NPAY = 0, WARPS = 8, MINBLOCKS = 2;
     static constexpr bool TMA = true;
@@ -176,7 +176,8 @@ struct Fast3 {
     double x0, y0, z0, x1, y1, z1;
     unsigned c[HTB_NBF];
     unsigned clow;
-    bool dirty, exact;
+    unsigned eqmin;             // min over keys/edges of key ^ edge_key: 0 <=> some key equals an edge key
+    bool exact;
     unsigned long long tot;
 
     static size_t scratch_bytes(const Params &) { return sizeof(uint32_t) * QCAP * 32; }
@@ -185,7 +186,7 @@ struct Fast3 {
     {
         qbase = smem_u32(scratch) + 4u * (uint32_t)ln;
         qptr = qbase;
-        tot = 0; dirty = false; exact = false; clow = 0;
+        tot = 0; eqmin = 0xffffffffu; exact = false; clow = 0;
 #pragma unroll
         for (int s = 0; s < HTB_NBF; ++s) c[s] = 0;
     }
@@ -194,32 +195,43 @@ struct Fast3 {
     {
         x0 = p0[0]; y0 = p0[1]; z0 = p0[2];
         x1 = p1[0]; y1 = p1[1]; z1 = p1[2];
-        exact = false; dirty = false;
+        exact = false; eqmin = 0xffffffffu;
     }
-    // top-down cumulative scan of one key over slots S, S-1, then recurse while any lane is still inside
+    // Deferred binning = a compaction cascade over this lane's queue column.  Pass 1 applies the two
+    // top thresholds (68% + 22% of the in-range pairs of log-spaced bins die there); every further
+    // pass applies one threshold to the survivors, compacting them in place.  The cumulative count
+    // of a level is simply the number of survivors.  A key EQUAL to an edge key cannot be decided
+    // from 32 bits -> the tile is flagged dirty and redone with exact 64-bit compares.
     template <int S>
-    __device__ __forceinline__ void levels(int key)
+    __device__ __forceinline__ void cascade(uint32_t qend)
     {
-        const bool in_a = key <= P.F[S];
-        dirty |= (key == P.F[S]);
-        c[S] += in_a ? 1u : 0u;
-        if (S >= 1) {
-            const bool in_b = key <= P.F[S >= 1 ? S - 1 : 0];
-            dirty |= (key == P.F[S >= 1 ? S - 1 : 0]);
-            c[S >= 1 ? S - 1 : 0] += in_b ? 1u : 0u;
-            if (S >= 2) {
-                if (__any_sync(HTB_FULL, in_b)) levels<(S >= 2 ? S - 2 : 0)>(key);
-            }
+        if (!__any_sync(HTB_FULL, qend != qbase)) return;
+        const int F = P.F[S];
+        uint32_t w = qbase;
+#pragma unroll 2
+        for (uint32_t r = qbase; r != qend; r += 128u) {
+            const int key = (int)lds_u32(r);
+            eqmin = min(eqmin, (unsigned)(key ^ F));
+            if (key <= F) { sts_u32(w, (uint32_t)key); w += 128u; }
         }
+        c[S] += (w - qbase) >> 7;
+        if (S > 0) cascade<(S > 0 ? S - 1 : 0)>(w);
     }
     __device__ __forceinline__ void flush()
     {
-        const int qn = (int)((qptr - qbase) >> 7);
-        const int maxn = __reduce_max_sync(HTB_FULL, qn);
-        for (int e = 0; e < maxn; ++e) {
-            const int key = (e < qn) ? (int)lds_u32(qbase + 128u * (uint32_t)e) : 0x7fffffff;
-            levels<HTB_NBF - 1>(key);
+        const int Ft = P.F[HTB_NBF - 1], Fs = P.F[HTB_NBF - 2];
+        unsigned nin = 0;
+        uint32_t w = qbase;
+#pragma unroll 2
+        for (uint32_t r = qbase; r != qptr; r += 128u) {
+            const int key = (int)lds_u32(r);
+            nin += (unsigned)(key - Ft - 1) >> 31;            // key <= Ft
+            eqmin = min(eqmin, min((unsigned)(key ^ Ft), (unsigned)(key ^ Fs)));
+            if (key <= Fs) { sts_u32(w, (uint32_t)key); w += 128u; }
         }
+        c[HTB_NBF - 1] += nin;
+        c[HTB_NBF - 2] += (w - qbase) >> 7;
+        cascade<HTB_NBF - 3>(w);
         qptr = qbase;
     }
     __device__ __forceinline__ void pair_fast(double xs, double ys, double zs, double xj, double yj, double zj)
@@ -288,11 +300,11 @@ struct Fast3 {
     {
         if (!exact) {
             flush();
-            if (__any_sync(HTB_FULL, dirty) && pass == 0) {
+            if (__any_sync(HTB_FULL, eqmin == 0u) && pass == 0) {
                 // a key collided with an edge key: throw the tile's counts away and redo it exactly
 #pragma unroll
                 for (int s = 0; s < HTB_NBF; ++s) c[s] = 0;
-                clow = 0; dirty = false; exact = true;
+                clow = 0; eqmin = 0xffffffffu; exact = true;
                 return true;
             }
         }
