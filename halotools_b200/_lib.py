@@ -11,12 +11,13 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhalotools_b200.so")
+LIB_PATH = os.environ.get("HTB_LIB_PATH") or os.path.join(_HERE, "libhalotools_b200.so")   # override: kernel-variant sweeps
 
 FLAG_DEVICE_INPUT = 1
 FLAG_NO_CULL = 2
 FLAG_GENERIC = 4
 FLAG_NO_TMA = 8
+FLAG_NO_SYM = 16
 
 EXPORTS = (
     "htb_last_error", "htb_abi_version", "htb_device_count", "htb_set_device", "htb_set_stream",

@@ -239,7 +239,7 @@ struct Call {
         return 0;
     }
     // full set-up: upload, sort both samples, tile list, walker geometry
-    int setup(const htb_mesh_geom *g, int sphere,
+    int setup(const htb_mesh_geom *g, int sphere, bool allow_sym,
               const double *const *c1, int64_t stride1, int64_t n1, const double *w1,
               const double *const *c2, int64_t stride2, int64_t n2, const double *w2, int nw,
               bool perm1, int64_t first_cell1, int64_t last_cell1, uint32_t fl)
@@ -270,9 +270,20 @@ struct Call {
         HTB_CUDA(cudaEventRecord(ev[1], st));
         // ---- K1
         choose_refinement(g, n1, n2, m1, m2);
+        // Symmetric auto-correlation (count each zero-shift unordered pair once, weight 2) needs the two
+        // samples to be the SAME sorted arrays and the reference window to be symmetric (mesh1 == mesh2).
+        bool sym = allow_sym && same && !(fl & HTB_FLAG_NO_SYM) && !getenv("HTB_NO_SYM");
+        for (int d = 0; d < dim && sym; ++d) sym = (g->ndivs1[d] == g->ndivs2[d]);
+        if (sym) for (int d = 0; d < dim; ++d) m1[d] = m2[d];
         const FineGrid g1 = make_grid(g, 0, m1), g2 = make_grid(g, 1, m2);
-        if (htb_sort_sample(st, ws, g1, d1, ds1, n1, dw1, nw, perm1, s1, &launches)) return 1;
-        if (htb_sort_sample(st, ws, g2, d2, ds2, n2, dw2, nw, false, s2, &launches)) return 1;
+        if (sym) {
+            if (htb_sort_sample(st, ws, g2, d2, ds2, n2, dw2, nw, perm1, s2, &launches)) return 1;
+            s1 = s2;
+        } else {
+            if (htb_sort_sample(st, ws, g1, d1, ds1, n1, dw1, nw, perm1, s1, &launches)) return 1;
+            if (htb_sort_sample(st, ws, g2, d2, ds2, n2, dw2, nw, false, s2, &launches)) return 1;
+        }
+        G.sym = sym ? 1 : 0;
         // ---- walker geometry
         G.dim = dim;
         G.pbc = g->pbc ? 1 : 0;
@@ -390,7 +401,7 @@ extern "C" int htb_npairs_3d_engine(const htb_mesh_geom *mesh,
     Call c;
     if (c.begin()) return 1;
     const double *c1[3] = {x1, y1, z1}, *c2[3] = {x2, y2, z2};
-    if (c.setup(mesh, 1, c1, stride1, n1, nullptr, c2, stride2, n2, nullptr, 0, false, first_cell1, last_cell1, flags)) return 1;
+    if (c.setup(mesh, 1, true, c1, stride1, n1, nullptr, c2, stride2, n2, nullptr, 0, false, first_cell1, last_cell1, flags)) return 1;
     std::vector<double> rsq((size_t)nb);
     for (int k = 0; k < nb; ++k) rsq[k] = rbins[k] * rbins[k];
     // eligibility of the fast kernel: sane monotone edges whose 32-bit keys stay below 2^31
@@ -449,7 +460,7 @@ extern "C" int htb_npairs_xy_z_engine(const htb_mesh_geom *mesh,
     Call c;
     if (c.begin()) return 1;
     const double *c1[3] = {x1, y1, z1}, *c2[3] = {x2, y2, z2};
-    if (c.setup(mesh, 0, c1, stride1, n1, nullptr, c2, stride2, n2, nullptr, 0, false, first_cell1, last_cell1, flags)) return 1;
+    if (c.setup(mesh, 0, true, c1, stride1, n1, nullptr, c2, stride2, n2, nullptr, 0, false, first_cell1, last_cell1, flags)) return 1;
     std::vector<double> e((size_t)nrp + npi);
     for (int k = 0; k < nrp; ++k) e[k] = rp_bins[k] * rp_bins[k];
     for (int k = 0; k < npi; ++k) e[nrp + k] = pi_bins[k] * pi_bins[k];
@@ -483,7 +494,7 @@ extern "C" int htb_npairs_s_mu_engine(const htb_mesh_geom *mesh,
     Call c;
     if (c.begin()) return 1;
     const double *c1[3] = {x1, y1, z1}, *c2[3] = {x2, y2, z2};
-    if (c.setup(mesh, 1, c1, stride1, n1, nullptr, c2, stride2, n2, nullptr, 0, false, first_cell1, last_cell1, flags)) return 1;
+    if (c.setup(mesh, 1, true, c1, stride1, n1, nullptr, c2, stride2, n2, nullptr, 0, false, first_cell1, last_cell1, flags)) return 1;
     std::vector<double> e((size_t)ns + nmu);
     double m0 = -INFINITY, m1 = -INFINITY;
     for (int k = 0; k < ns; ++k) { e[k] = s_bins[k] * s_bins[k]; if (e[k] > m0) m0 = e[k]; }
@@ -532,7 +543,7 @@ extern "C" int htb_marked_npairs_3d_engine(const htb_mesh_geom *mesh,
     Call c;
     if (c.begin()) return 1;
     const double *c1[3] = {x1, y1, z1}, *c2[3] = {x2, y2, z2};
-    if (c.setup(mesh, 1, c1, stride1, n1, w1, c2, stride2, n2, w2, nw, false, first_cell1, last_cell1, flags)) return 1;
+    if (c.setup(mesh, 1, false, c1, stride1, n1, w1, c2, stride2, n2, w2, nw, false, first_cell1, last_cell1, flags)) return 1;
     std::vector<double> rsq((size_t)nb);
     for (int k = 0; k < nb; ++k) rsq[k] = rbins[k] * rbins[k];
     void *edev = nullptr;
@@ -563,7 +574,7 @@ extern "C" int htb_mean_delta_sigma_engine(const htb_mesh_geom *mesh,
     Call c;
     if (c.begin()) return 1;
     const double *c1[3] = {x1, y1, nullptr}, *c2[3] = {x2, y2, nullptr};
-    if (c.setup(mesh, 1, c1, stride1, n1, nullptr, c2, stride2, n2, m2, 1, true, first_cell1, last_cell1, flags)) return 1;
+    if (c.setup(mesh, 1, false, c1, stride1, n1, nullptr, c2, stride2, n2, m2, 1, true, first_cell1, last_cell1, flags)) return 1;
     const int nbin = nrp - 1;
     std::vector<double> e((size_t)nrp + nbin);
     for (int k = 0; k < nrp; ++k) e[k] = rp_bins[k] * rp_bins[k];
@@ -649,7 +660,7 @@ extern "C" int htb_cell1_work(const htb_mesh_geom *mesh,
     Call c;
     if (c.begin()) return 1;
     const double *c1[3] = {x1, y1, z1}, *c2[3] = {x2, y2, z2};
-    if (c.setup(mesh, 1, c1, stride1, n1, nullptr, c2, stride2, n2, nullptr, 0, false, 0, 0, flags)) return 1;
+    if (c.setup(mesh, 1, false, c1, stride1, n1, nullptr, c2, stride2, n2, nullptr, 0, false, 0, 0, flags)) return 1;
     double *work_dev = nullptr;
     int64_t nc1 = 0;
     if (htb_reference_work(c.st, c.ws, c.G, c.s1, c.s2, &work_dev, &nc1, &c.launches)) return 1;

@@ -145,13 +145,15 @@ k_count(const __grid_constant__ WalkGeom G, const __grid_constant__ WalkArrays A
         }
         if (!v0) p0[0] = 1.0e150;
         if (!v1) p1[0] = 1.0e150;
-        v.tile_begin(p0, p1, v0, v1, i0, i1, A);
-        bool redo = false;
-        for (int pass = 0; pass < 2; ++pass) {
-            walk_tile<V>(v, G, A, S, gchunk, blo, bhi, fs, pairs, cnt);
-            redo = v.tile_end(A, i0, i1, pass);
-            if (!redo) break;
-            ++redone;
+        const int nsub = G.sym ? 2 : 1;
+        for (int sub = 0; sub < nsub; ++sub) {
+            v.tile_begin(p0, p1, v0, v1, i0, i1, A);
+            for (int pass = 0; pass < 2; ++pass) {
+                walk_tile<V>(v, G, A, S, gchunk, blo, bhi, fs, pairs, cnt, G.sym ? sub + 1 : 0, start, start + (uint32_t)cnt);
+                const bool redo = v.tile_end(A, i0, i1, pass, sub == 1 ? 2u : 1u);
+                if (!redo) break;
+                ++redone;
+            }
         }
     }
     v.kernel_end();
@@ -164,9 +166,15 @@ k_count(const __grid_constant__ WalkGeom G, const __grid_constant__ WalkArrays A
 // ------------------------------------------------------------------ Fast3
 // Queue capacity per lane.  Between two capacity checks a lane pushes at most 10 keys (one odd
 // leading j = 2, one group of 4 j = 8; the tail of <= 3 j = 6), so the flush threshold is QCAP - 10.
+#ifndef QCAP
 #define QCAP 64
+#endif
+#ifndef FAST3_WARPS
+#define FAST3_WARPS 8
+#define FAST3_MINBLOCKS 2
+#endif
 struct Fast3 {
-    static constexpr int DIM = 3, NPAY = 0, WARPS = 8, MINBLOCKS = 2;
+    static constexpr int DIM = 3, NPAY = 0, WARPS = FAST3_WARPS, MINBLOCKS = FAST3_MINBLOCKS;
     static constexpr bool TMA = true;
     typedef Fast3Params Params;
     const Params &P;
@@ -296,7 +304,7 @@ struct Fast3 {
             }
         }
     }
-    __device__ __forceinline__ bool tile_end(const WalkArrays &, uint32_t, uint32_t, int pass)
+    __device__ __forceinline__ bool tile_end(const WalkArrays &, uint32_t, uint32_t, int pass, unsigned wt)
     {
         if (!exact) {
             flush();
@@ -312,7 +320,7 @@ struct Fast3 {
 #pragma unroll
         for (int s = 0; s < HTB_NBF; ++s) {
             const unsigned r = __reduce_add_sync(HTB_FULL, c[s]);
-            if (lane == s) tot += (unsigned long long)r + low;
+            if (lane == s) tot += (unsigned long long)wt * ((unsigned long long)r + low);
             c[s] = 0;
         }
         clow = 0;
@@ -407,12 +415,12 @@ struct GenCount {
             pair(v1, xs1, ys1, zs1, xj, yj, zj);
         }
     }
-    __device__ __forceinline__ bool tile_end(const WalkArrays &, uint32_t, uint32_t, int)
+    __device__ __forceinline__ bool tile_end(const WalkArrays &, uint32_t, uint32_t, int, unsigned wt)
     {
         __syncwarp();
         for (int k = lane; k < P.nhist; k += 32) {
             const uint32_t h = hist[k];
-            if (h) { atomicAdd(P.counts + k, (unsigned long long)h); hist[k] = 0; }
+            if (h) { atomicAdd(P.counts + k, (unsigned long long)wt * h); hist[k] = 0; }
         }
         __syncwarp();
         return false;
@@ -515,7 +523,7 @@ struct Marked3 {
             pair(v1, wb, xs1, ys1, zs1, xj, yj, zj, bw + 8 * j * P.nw);
         }
     }
-    __device__ __forceinline__ bool tile_end(const WalkArrays &, uint32_t, uint32_t, int)
+    __device__ __forceinline__ bool tile_end(const WalkArrays &, uint32_t, uint32_t, int, unsigned)
     {
         __syncwarp();
         for (int k = lane; k < P.nhist; k += 32) {
@@ -589,7 +597,7 @@ struct DSigma {
             inside += acc[(k + 1) * 64 + col];
         }
     }
-    __device__ __forceinline__ bool tile_end(const WalkArrays &A, uint32_t i0, uint32_t i1, int)
+    __device__ __forceinline__ bool tile_end(const WalkArrays &A, uint32_t i0, uint32_t i1, int, unsigned)
     {
         __syncwarp();
         finish(v0, lane, i0, A);

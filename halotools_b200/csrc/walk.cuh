@@ -27,6 +27,7 @@ struct WalkGeom {
     int pbc;
     int sphere;                     // 1: fast-dim reach shrinks with slow-dim distance (3-D r / 2-D rp); 0: cylinder (rp, pi)
     int nocull;
+    int sym;                        // sample1 IS sample2 (same sorted arrays): count each zero-shift unordered pair once, weight 2
     int nd1[3], nd2[3], per[3], cover[3];
     int m1[3], m2[3], nf1[3], nf2[3];
     double period[3], h2[3], slop[3], reach[3];
@@ -150,7 +151,9 @@ __device__ __forceinline__ void walk_tile(V &v, const WalkGeom &G, const WalkArr
                                           WarpSmem<V::DIM, V::NPAY> &S, uint32_t &gchunk,
                                           const double (&blo)[3], const double (&bhi)[3],
                                           const int (&fs)[3] /* tile's fine/ref indices: slow dims fine idx, fast dim ref cell */,
-                                          unsigned long long &pairs, int tile_cnt)
+                                          unsigned long long &pairs, int tile_cnt,
+                                          int wt_pass /* 0: every span; 1: symmetric mode, weight-1 spans; 2: weight-2 spans */,
+                                          uint32_t ts, uint32_t te /* the tile's own sorted index range */)
 {
     constexpr int DIM = V::DIM;
     constexpr int F = DIM - 1;                 // fast dimension
@@ -282,6 +285,21 @@ __device__ __forceinline__ void walk_tile(V &v, const WalkGeom &G, const WalkArr
                     const int64_t cbase = slowlin * G.nf2[F] - (int64_t)k * G.nf2[F];
                     jb = A.off2[cbase + plo];
                     je = A.off2[cbase + phi + 1];
+                    if (wt_pass != 0) {
+                        // Symmetric auto-correlation: a pair evaluated with zero shift in every dimension
+                        // has bit-identical dsq in both directions (IEEE subtraction is antisymmetric), so
+                        // it is evaluated once, from the point with the smaller sorted index, and counted
+                        // twice.  The tile's own index range is evaluated in full with weight 1 (it holds
+                        // the self pairs); wrapped spans are evaluated from both sides as the reference does.
+                        const uint32_t fullcode = code | ((uint32_t)(kc + 1) << (2 * F));
+                        const bool zero = fullcode == (DIM == 3 ? 21u : 5u);
+                        if (zero) {
+                            if (wt_pass == 1) { jb = max(jb, ts); je = min(je, te); }
+                            else { jb = max(jb, te); }
+                        } else if (wt_pass == 2) {
+                            je = jb;
+                        }
+                    }
                     has = je > jb;
                 }
                 const uint32_t bal = __ballot_sync(HTB_FULL, has);

@@ -34,6 +34,7 @@ extern "C" {
 #define HTB_FLAG_NO_CULL      2u   /* visit exactly the reference's cell windows (no pruning) */
 #define HTB_FLAG_GENERIC      4u   /* force the generic (literal top-down scan) kernels       */
 #define HTB_FLAG_NO_TMA       8u   /* stage sample2 tiles with ld.global/st.shared instead of cp.async.bulk */
+#define HTB_FLAG_NO_SYM       16u  /* auto-correlations: evaluate (i,j) and (j,i) separately, as the reference does */
 
 /* Scalars of RectangularDoubleMesh / RectangularDoubleMesh2D
  * (/root/reference/halotools/mock_observables/pair_counters/rectangular_mesh.py:228-374,

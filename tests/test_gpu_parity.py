@@ -55,7 +55,8 @@ ENGINE_INT = [n for n in ALL if cases._cases()[n][0] in INT_FUNCS and n != "n3d_
 
 
 @pytest.mark.parametrize("name", ENGINE_INT)
-@pytest.mark.parametrize("flags", [_lib.FLAG_GENERIC, _lib.FLAG_NO_CULL, _lib.FLAG_GENERIC | _lib.FLAG_NO_CULL])
+@pytest.mark.parametrize("flags", [_lib.FLAG_GENERIC, _lib.FLAG_NO_CULL, _lib.FLAG_GENERIC | _lib.FLAG_NO_CULL,
+                                   _lib.FLAG_NO_SYM, _lib.FLAG_NO_SYM | _lib.FLAG_NO_CULL])
 def test_kernel_variants_agree(name, flags, golden):
     fn = cases._cases()[name][0]
     compare(fn, run_gpu(name, flags), golden(name))
@@ -71,12 +72,17 @@ def test_fast_path_taken_and_culling_reduces_work():
     _, dm = oracle.npairs_3d(*args, return_mesh=True, **kwargs)
     assert st["pairs_reference"] == dm.visited_pairs()
     old = _lib.default_flags
-    _lib.default_flags = _lib.FLAG_NO_CULL
+    _lib.default_flags = _lib.FLAG_NO_CULL | _lib.FLAG_NO_SYM
     try:
         hb.npairs_3d(*args, **kwargs)
+        assert _lib.last_stats["pairs_evaluated"] == st["pairs_reference"]
+        # symmetric auto-correlation evaluates roughly half of the pairs of the two-sided count
+        _lib.default_flags = _lib.FLAG_NO_SYM
+        hb.npairs_3d(*args, **kwargs)
+        two_sided = _lib.last_stats["pairs_evaluated"]
     finally:
         _lib.default_flags = old
-    assert _lib.last_stats["pairs_evaluated"] == st["pairs_reference"]
+    assert st["pairs_evaluated"] < 0.62 * two_sided
 
 
 @pytest.mark.parametrize("seed", [1, 2, 3])
