@@ -18,6 +18,7 @@ FLAG_NO_CULL = 2
 FLAG_GENERIC = 4
 FLAG_NO_TMA = 8
 FLAG_NO_SYM = 16
+FLAG_UNIFORM_MASS = 32
 
 EXPORTS = (
     "htb_last_error", "htb_abi_version", "htb_device_count", "htb_set_device", "htb_set_stream",
@@ -146,7 +147,7 @@ def run_engine(func_name, *args, **kw):
     global last_stats
     lib = require_gpu()
     st = Stats()
-    flags = default_flags | (FLAG_DEVICE_INPUT if kw.get("device") else 0)
+    flags = default_flags | (FLAG_DEVICE_INPUT if kw.get("device") else 0) | int(kw.get("extra_flags", 0))
     rc = getattr(lib, func_name)(*args, ctypes.c_uint32(flags),
                                  ctypes.byref(st) if collect_stats else None)
     check(rc)

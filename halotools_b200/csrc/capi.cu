@@ -205,14 +205,22 @@ struct Call {
             return 0;
         }
         if (n <= 0) { for (int k = 0; k < cnt; ++k) dst[k] = nullptr; *dstride = 1; return 0; }
-        bool interleaved = (stride == cnt);
-        for (int k = 1; k < cnt && interleaved; ++k) interleaved = (src[k] == src[0] + k);
-        if (interleaved && cnt > 1) {
+        // columns of one row-major (n, stride) host matrix (e.g. x, y of an (N, 3) sample): ship the whole
+        // block with ONE contiguous copy and keep the stride on the device
+        bool interleaved = cnt > 1 && stride >= cnt;
+        int64_t maxoff = 0;
+        for (int k = 1; k < cnt && interleaved; ++k) {
+            const int64_t off = src[k] - src[0];
+            interleaved = off > 0 && off < stride;
+            if (off > maxoff) maxoff = off;
+        }
+        if (interleaved) {
             double *buf = nullptr;
-            if (ws.alloc((void **)&buf, sizeof(double) * (size_t)n * cnt)) return 1;
-            HTB_CUDA(cudaMemcpyAsync(buf, src[0], sizeof(double) * (size_t)n * cnt, cudaMemcpyHostToDevice, st));
-            for (int k = 0; k < cnt; ++k) dst[k] = buf + k;
-            *dstride = cnt;
+            const size_t len = (size_t)(n - 1) * (size_t)stride + (size_t)maxoff + 1;
+            if (ws.alloc((void **)&buf, sizeof(double) * len)) return 1;
+            HTB_CUDA(cudaMemcpyAsync(buf, src[0], sizeof(double) * len, cudaMemcpyHostToDevice, st));
+            for (int k = 0; k < cnt; ++k) dst[k] = buf + (src[k] - src[0]);
+            *dstride = stride;
             return 0;
         }
         for (int k = 0; k < cnt; ++k) {
@@ -574,7 +582,16 @@ extern "C" int htb_mean_delta_sigma_engine(const htb_mesh_geom *mesh,
     Call c;
     if (c.begin()) return 1;
     const double *c1[3] = {x1, y1, nullptr}, *c2[3] = {x2, y2, nullptr};
-    if (c.setup(mesh, 1, false, c1, stride1, n1, nullptr, c2, stride2, n2, m2, 1, true, first_cell1, last_cell1, flags)) return 1;
+    // HTB_FLAG_UNIFORM_MASS: every particle has the mass m2[0] (the reference's scalar
+    // ``effective_particle_masses``): the mass array is neither uploaded nor sorted.
+    const bool uniform = (flags & HTB_FLAG_UNIFORM_MASS) != 0;
+    double mass = 0.0;
+    if (uniform && n2 > 0) {
+        if (flags & HTB_FLAG_DEVICE_INPUT) HTB_CUDA(cudaMemcpy(&mass, m2, sizeof(double), cudaMemcpyDeviceToHost));
+        else mass = m2[0];
+    }
+    if (c.setup(mesh, 1, false, c1, stride1, n1, nullptr, c2, stride2, n2, uniform ? nullptr : m2, uniform ? 0 : 1, true,
+                first_cell1, last_cell1, flags)) return 1;
     const int nbin = nrp - 1;
     std::vector<double> e((size_t)nrp + nbin);
     for (int k = 0; k < nrp; ++k) e[k] = rp_bins[k] * rp_bins[k];
@@ -590,7 +607,8 @@ extern "C" int htb_mean_delta_sigma_engine(const htb_mesh_geom *mesh,
     gp.e0 = (const double *)edev; gp.e1 = (const double *)edev + nrp;
     gp.fcounts = out_dev;
     gp.perm1 = c.s1.perm;
-    if (htb_launch_gen(c.st, 4, c.G, c.A, gp, &c.launches)) return 1;
+    gp.max0 = mass;
+    if (htb_launch_gen(c.st, uniform ? 5 : 4, c.G, c.A, gp, &c.launches)) return 1;
     if (n1 > 0) HTB_CUDA(cudaMemcpyAsync(out, out_dev, sizeof(double) * (size_t)n1 * nbin, cudaMemcpyDeviceToHost, c.st));
     return c.finish(stats, 0);
     HTB_GUARD_END

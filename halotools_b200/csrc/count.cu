@@ -608,6 +608,123 @@ struct DSigma {
     __device__ __forceinline__ void kernel_end() {}
 };
 
+// ------------------------------------------------------------------ DSigmaU (uniform particle mass)
+// With one mass m for every particle the per-pair logarithm disappears:
+//   sum_j m (1 - ln(R^2 / d_j^2)) = m [ n (1 - ln R^2) + ln prod_j d_j^2 ]
+// and the product is carried as (product of mantissas in [1,2), integer sum of exponents), renormalised
+// before it can overflow.  Per in-bin pair: 5 f64 ops for d^2 + 1 DMUL, no division, no log.
+// scratch per warp: cnt[slot][64] u32 (slot 0 = inside rp[0], slot b+1 = bin b), es[bin][64] i32,
+// pm[bin][64] f64.
+struct DSigmaU {
+    static constexpr int DIM = 2, NPAY = 0, WARPS = 4, MINBLOCKS = 3;
+    static constexpr bool TMA = true;
+    typedef GenParams Params;
+    const Params &P;
+    double *pm;
+    int *es;
+    unsigned *cnt;
+    int lane, nbin;
+    double x0, y0, x1, y1;
+    bool v0, v1;
+    int since;
+
+    static size_t scratch_bytes(const Params &p)
+    {
+        const size_t nbin = (size_t)(p.n0 - 1);
+        return 64 * (8 * nbin + 4 * nbin + 4 * (nbin + 1));
+    }
+    __device__ DSigmaU(const Params &p, void *scratch, int ln) : P(p), lane(ln)
+    {
+        nbin = P.n0 - 1;
+        pm = (double *)scratch;
+        es = (int *)(pm + 64 * nbin);
+        cnt = (unsigned *)(es + 64 * nbin);
+        since = 0;
+    }
+    __device__ __forceinline__ void tile_begin(const double (&p0)[3], const double (&p1)[3], bool a, bool b, uint32_t, uint32_t,
+                                               const WalkArrays &)
+    {
+        x0 = p0[0]; y0 = p0[1]; x1 = p1[0]; y1 = p1[1];
+        v0 = a; v1 = b;
+        for (int s = 0; s < nbin; ++s) {
+            pm[s * 64 + lane] = 1.0; pm[s * 64 + 32 + lane] = 1.0;
+            es[s * 64 + lane] = 0; es[s * 64 + 32 + lane] = 0;
+        }
+        for (int s = 0; s <= nbin; ++s) { cnt[s * 64 + lane] = 0; cnt[s * 64 + 32 + lane] = 0; }
+        since = 0;
+        __syncwarp();
+    }
+    __device__ __forceinline__ void pair(bool valid, int col, double xs, double ys, double xj, double yj)
+    {
+        const double dx = xs - xj, dy = ys - yj;
+        const double dxy_sq = dx * dx + dy * dy;
+        if (valid && dxy_sq <= P.e0[nbin]) {
+            int k = nbin - 1;
+            while (k >= 0 && dxy_sq <= P.e0[k]) --k;
+            cnt[(k + 1) * 64 + col] += 1u;
+            if (k >= 0) {
+                const int hi = __double2hiint(dxy_sq);
+                es[k * 64 + col] += (hi >> 20) - 1023;
+                const double mant = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(dxy_sq));
+                pm[k * 64 + col] *= mant;
+            }
+        }
+    }
+    __device__ __forceinline__ void renorm(int col)
+    {
+        for (int b = 0; b < nbin; ++b) {
+            const double v = pm[b * 64 + col];
+            const int hi = __double2hiint(v);
+            es[b * 64 + col] += (hi >> 20) - 1023;
+            pm[b * 64 + col] = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(v));
+        }
+    }
+    __device__ __forceinline__ void chunk(uint32_t stage, int lo, int hi, uint32_t, const double (&sh)[3])
+    {
+        const uint32_t bx = stage, by = stage + 8 * HTB_CH;
+        const double xs0 = x0 - sh[0], ys0 = y0 - sh[1];
+        const double xs1 = x1 - sh[0], ys1 = y1 - sh[1];
+        // every multiply grows a product by < 2: renormalise before 2^1023 can be reached
+        if (since + (hi - lo) > 900) { renorm(lane); renorm(32 + lane); since = 0; }
+        since += hi - lo;
+        for (int j = lo; j < hi; ++j) {
+            const double xj = lds_f64(bx + 8 * j), yj = lds_f64(by + 8 * j);
+            pair(v0, lane, xs0, ys0, xj, yj);
+            pair(v1, 32 + lane, xs1, ys1, xj, yj);
+        }
+    }
+    __device__ __forceinline__ void finish(bool valid, int col, uint32_t isorted)
+    {
+        if (!valid) return;
+        const double m = P.max0;
+        const int64_t row = P.perm1 ? (int64_t)P.perm1[isorted] : (int64_t)isorted;
+        double inside = (double)cnt[col];
+        for (int k = 0; k < nbin; ++k) {
+            const double n = (double)cnt[(k + 1) * 64 + col];
+            // sum over the bin's pairs of ln(d^2 / rp[k+1]^2), exponents and mantissas kept apart
+            const double r2 = P.e0[k + 1];
+            const int rhi = __double2hiint(r2);
+            const int re = (rhi >> 20) - 1023;
+            const double rm = __hiloint2double((rhi & 0x000fffff) | 0x3ff00000, __double2loint(r2));
+            const double v = pm[k * 64 + col];
+            const double lnratio = 0.6931471805599453 * ((double)es[k * 64 + col] - n * (double)re) + (log(v) - n * log(rm));
+            const double t = m * (n + lnratio);
+            const double ds = m * inside * 2 * P.e1[k] - t;
+            P.fcounts[row * nbin + k] = ds / (3.14159265358979323846 * (P.e0[k + 1] - P.e0[k]));
+            inside += n;
+        }
+    }
+    __device__ __forceinline__ bool tile_end(const WalkArrays &, uint32_t i0, uint32_t i1, int, unsigned)
+    {
+        __syncwarp();
+        finish(v0, lane, i0);
+        finish(v1, 32 + lane, i1);
+        __syncwarp();
+        return false;
+    }
+    __device__ __forceinline__ void kernel_end() {}
+};
+
 // ------------------------------------------------------------------ host launchers
 template <class V>
 static int launch_count(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const typename V::Params &P,
@@ -642,6 +759,7 @@ int htb_launch_gen(cudaStream_t st, int kind, const WalkGeom &G, const WalkArray
     case 2: return launch_count<GenCount<2>>(st, G, A, P, l);
     case 3: return launch_count<Marked3>(st, G, A, P, l);
     case 4: return launch_count<DSigma>(st, G, A, P, l);
+    case 5: return launch_count<DSigmaU>(st, G, A, P, l);
     }
     htb_set_error("unknown kernel kind %d", kind);
     return 1;

@@ -21,6 +21,9 @@ def mean_delta_sigma(galaxies, particles, effective_particle_masses,
     z), in the bins defined by ``rp_bins``: float64 (len(rp_bins)-1,), or (Ngal, len(rp_bins)-1)
     rows in input order when ``per_object`` is True.  Semantics follow the reference engine
     (surface_density/engines/mean_delta_sigma_engine.pyx:162-185)."""
+    # one mass for every particle (the reference broadcasts the scalar, mean_delta_sigma.py:279-281):
+    # the engine then needs no per-particle mass array and no per-pair logarithm
+    uniform_mass = len(np.atleast_1d(effective_particle_masses)) == 1
     result = _mean_delta_sigma_process_args(
         galaxies, particles, effective_particle_masses, rp_bins,
         period, num_threads, approx_cell1_size, approx_cell2_size)
@@ -39,7 +42,10 @@ def mean_delta_sigma(galaxies, particles, effective_particle_masses,
     first, last = _dist.cell1_range(geom.ncells1)
     c1 = _lib.Columns([x1in, y1in])
     c2 = _lib.Columns([x2in, y2in])
-    m2 = np.ascontiguousarray(w2in, dtype=np.float64)
+    m2 = np.ascontiguousarray(w2in[:1] if (uniform_mass and len(w2in) > 0) else w2in, dtype=np.float64)
+    extra = _lib.FLAG_UNIFORM_MASS if (uniform_mass and not _lib.default_flags & _lib.FLAG_GENERIC) else 0
+    if not extra:
+        m2 = np.ascontiguousarray(w2in, dtype=np.float64)
     g = geom.as_struct()
     rb = np.ascontiguousarray(rp_bins, dtype=np.float64)
     _lib.run_engine(
@@ -47,7 +53,7 @@ def mean_delta_sigma(galaxies, particles, effective_particle_masses,
         c1.ptrs[0], c1.ptrs[1], ctypes.c_int64(c1.stride), ctypes.c_int64(c1.n),
         c2.ptrs[0], c2.ptrs[1], ctypes.c_int64(c2.stride), _lib._dp(m2), ctypes.c_int64(c2.n),
         _lib._dp(rb), ctypes.c_int32(len(rb)), ctypes.c_int64(first), ctypes.c_int64(last),
-        _lib._dp(delta_sigma))
+        _lib._dp(delta_sigma), extra_flags=extra)
     if per_object:
         return _dist.allreduce_sum(delta_sigma)
     # rows outside this rank's mesh1 cells are zero, so the mean is the all-reduced column sum / N

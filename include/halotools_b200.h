@@ -34,6 +34,7 @@ extern "C" {
 #define HTB_FLAG_NO_CULL      2u   /* visit exactly the reference's cell windows (no pruning) */
 #define HTB_FLAG_GENERIC      4u   /* force the generic (literal top-down scan) kernels       */
 #define HTB_FLAG_NO_TMA       8u   /* stage sample2 tiles with ld.global/st.shared instead of cp.async.bulk */
+#define HTB_FLAG_UNIFORM_MASS 32u  /* mean_delta_sigma: all particle masses equal m2[0] (scalar effective_particle_masses) */
 #define HTB_FLAG_NO_SYM       16u  /* auto-correlations: evaluate (i,j) and (j,i) separately, as the reference does */
 
 /* Scalars of RectangularDoubleMesh / RectangularDoubleMesh2D

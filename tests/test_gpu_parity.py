@@ -215,3 +215,9 @@ def test_delta_sigma_rows_follow_input_order():
     shuffled = hb.mean_delta_sigma(gal[perm], ptcl, 1.0, rpb, period=1.0, per_object=True)
     scale = np.max(np.abs(base))
     assert np.allclose(shuffled, base[perm], rtol=1e-10, atol=1e-12 * scale)
+
+
+@pytest.mark.parametrize("name", ["ds_periodic_per_object", "ds_nonperiodic", "ds_cellsizes"])
+def test_delta_sigma_general_mass_kernel_agrees(name, golden):
+    """FLAG_GENERIC routes scalar masses through the per-particle-mass kernel (per-pair log)."""
+    compare("mean_delta_sigma", run_gpu(name, _lib.FLAG_GENERIC), golden(name))
