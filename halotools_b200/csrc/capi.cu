@@ -181,6 +181,7 @@ struct Call {
     int m1[3] = {1, 1, 1}, m2[3] = {1, 1, 1};
     unsigned int *ctr = nullptr;          // [0] tile counter, [1] tiles redone, [2..3] pairs evaluated (u64)
     int64_t max_tiles = 0;
+    int64_t first_cell = 0, last_cell = 0;  // this call's range of reference mesh1 cells
     uint32_t flags = 0;
 
     ~Call()
@@ -253,6 +254,8 @@ struct Call {
               bool perm1, int64_t first_cell1, int64_t last_cell1, uint32_t fl)
     {
         flags = fl;
+        first_cell = first_cell1;
+        last_cell = last_cell1;
         const int dim = g->ndim;
         if (dim != 2 && dim != 3) { htb_set_error("mesh->ndim must be 2 or 3"); return 1; }
         if (n1 < 0 || n2 < 0 || n1 > 2000000000LL || n2 > 2000000000LL) { htb_set_error("sample sizes must be in [0, 2e9]"); return 1; }
@@ -356,7 +359,7 @@ struct Call {
             memcpy(&pe, &h[2], sizeof(pe));
             stats->pairs_evaluated = (double)pe;
             double wr = 0.0;
-            for (int64_t c = 0; c < nc1; ++c) wr += work[(size_t)c];
+            for (int64_t c = (first_cell > 0 ? first_cell : 0); c < nc1 && c < last_cell; ++c) wr += work[(size_t)c];
             stats->pairs_reference = wr;
             cudaEventElapsedTime(&stats->ms_h2d, ev[0], ev[1]);
             cudaEventElapsedTime(&stats->ms_mesh, ev[1], ev[2]);
