@@ -66,6 +66,10 @@ class ClockSampler(object):
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            # nvidia-smi takes a while to attach to the driver; do not let that overlap the timed region
+            t0 = time.time()
+            while not self.lines and time.time() - t0 < 10.0:
+                time.sleep(0.05)
         except Exception:
             self.proc = None
 

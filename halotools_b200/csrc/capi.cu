@@ -109,14 +109,14 @@ static int clampi(double v, int lo, int hi)
     return (int)v;
 }
 
-static void choose_refinement(const htb_mesh_geom *g, int64_t n1, int64_t n2, int *m1, int *m2)
+static void choose_refinement(const htb_mesh_geom *g, int64_t n1, int64_t n2, int tile, int *m1, int *m2)
 {
     const int dim = g->ndim, F = dim - 1, S = dim - 1;
     double vol = 1.0;
     for (int d = 0; d < dim; ++d) vol *= g->period[d];
     const double dens1 = (double)(n1 > 0 ? n1 : 1) / vol, dens2 = (double)(n2 > 0 ? n2 : 1) / vol;
-    // sample1: a tile (HTB_TILE points) should be roughly a cube / square
-    const double side = pow((double)HTB_TILE / dens1, 1.0 / dim);
+    // sample1: a tile should be roughly a cube / square
+    const double side = pow((double)tile / dens1, 1.0 / dim);
     for (int d = 0; d < dim; ++d) {
         if (d == F) m1[d] = clampi(floor(4.0 * g->cell1_size[d] / side + 0.5), 1, 16);
         else m1[d] = clampi(floor(g->cell1_size[d] / side + 0.5), 1, 8);
@@ -251,7 +251,8 @@ struct Call {
     int setup(const htb_mesh_geom *g, int sphere, bool allow_sym,
               const double *const *c1, int64_t stride1, int64_t n1, const double *w1,
               const double *const *c2, int64_t stride2, int64_t n2, const double *w2, int nw,
-              bool perm1, int64_t first_cell1, int64_t last_cell1, uint32_t fl)
+              bool perm1, int64_t first_cell1, int64_t last_cell1, uint32_t fl,
+              int tile = HTB_TILE, double sentinel = 1.0e150)
     {
         flags = fl;
         first_cell = first_cell1;
@@ -280,7 +281,7 @@ struct Call {
         else if (stage_rows(w2, n2, nw, &dw2)) return 1;
         HTB_CUDA(cudaEventRecord(ev[1], st));
         // ---- K1
-        choose_refinement(g, n1, n2, m1, m2);
+        choose_refinement(g, n1, n2, tile, m1, m2);
         // Symmetric auto-correlation (count each zero-shift unordered pair once, weight 2) needs the two
         // samples to be the SAME sorted arrays and the reference window to be symmetric (mesh1 == mesh2).
         bool sym = allow_sym && same && !(fl & HTB_FLAG_NO_SYM) && !getenv("HTB_NO_SYM");
@@ -288,13 +289,15 @@ struct Call {
         if (sym) for (int d = 0; d < dim; ++d) m1[d] = m2[d];
         const FineGrid g1 = make_grid(g, 0, m1), g2 = make_grid(g, 1, m2);
         if (sym) {
-            if (htb_sort_sample(st, ws, g2, d2, ds2, n2, dw2, nw, perm1, s2, &launches)) return 1;
+            if (htb_sort_sample(st, ws, g2, d2, ds2, n2, dw2, nw, perm1, sentinel, s2, &launches)) return 1;
             s1 = s2;
         } else {
-            if (htb_sort_sample(st, ws, g1, d1, ds1, n1, dw1, nw, perm1, s1, &launches)) return 1;
-            if (htb_sort_sample(st, ws, g2, d2, ds2, n2, dw2, nw, false, s2, &launches)) return 1;
+            if (htb_sort_sample(st, ws, g1, d1, ds1, n1, dw1, nw, perm1, sentinel, s1, &launches)) return 1;
+            if (htb_sort_sample(st, ws, g2, d2, ds2, n2, dw2, nw, false, sentinel, s2, &launches)) return 1;
         }
         G.sym = sym ? 1 : 0;
+        G.tile = tile;
+        G.sentinel = sentinel;
         // ---- walker geometry
         G.dim = dim;
         G.pbc = g->pbc ? 1 : 0;
@@ -409,34 +412,47 @@ extern "C" int htb_npairs_3d_engine(const htb_mesh_geom *mesh,
     HTB_GUARD_BEGIN
     if (!mesh || !rbins || !counts_out || nb < 1) { htb_set_error("htb_npairs_3d_engine: bad arguments"); return 1; }
     if (mesh->ndim != 3) { htb_set_error("htb_npairs_3d_engine needs a 3-d mesh"); return 1; }
-    Call c;
-    if (c.begin()) return 1;
-    const double *c1[3] = {x1, y1, z1}, *c2[3] = {x2, y2, z2};
-    if (c.setup(mesh, 1, true, c1, stride1, n1, nullptr, c2, stride2, n2, nullptr, 0, false, first_cell1, last_cell1, flags)) return 1;
     std::vector<double> rsq((size_t)nb);
     for (int k = 0; k < nb; ++k) rsq[k] = rbins[k] * rbins[k];
-    // eligibility of the fast kernel: sane monotone edges whose 32-bit keys stay below 2^31
-    bool fast = !(flags & HTB_FLAG_GENERIC) && nb <= HTB_NBF && finite_all(rbins, nb) && rsq[nb - 1] < 1e290;
+    // Eligibility of the fast kernel.  Its 32-bit keys are (bits(dsq) >> 26) relative to the top squared
+    // edge, so every separation a tile can meet and every non-zero edge must lie within 2^+-31 of it:
+    //   above: points inside the box are at most 2L apart per dimension after the periodic shift and the
+    //          sentinel of unused lanes / pad entries sits at 8L  ->  dsq < 256 Lmax^2;
+    //   below: smaller separations (and exact zeros) are caught per group by the kernel (Hwin) and
+    //          evaluated exactly; edges below the window send the call to the generic kernel.
+    bool fast = !(flags & HTB_FLAG_GENERIC) && nb <= HTB_NBF && finite_all(rbins, nb);
     for (int k = 0; k + 1 < nb && fast; ++k) fast = rbins[k] >= 0.0 && rsq[k] <= rsq[k + 1];
-    if (fast && nb == 1) fast = rbins[0] >= 0.0;
+    if (fast) fast = rbins[nb - 1] >= 0.0 && rsq[nb - 1] > 1e-290 && rsq[nb - 1] < 1e290;
+    double lmax = 0.0;
+    for (int d = 0; d < 3; ++d) if (mesh->period[d] > lmax) lmax = mesh->period[d];
+    if (fast) fast = std::isfinite(lmax) && lmax > 0.0 && lmax < 1e140;
     Fast3Params fp{};
     if (fast) {
+        const long long Kt = (long long)(dbits(rsq[nb - 1]) >> 26);
+        const long long Kmax = (long long)(dbits(256.0 * lmax * lmax) >> 26);
+        const long long lim = 31LL << 26;
+        if (Kmax - Kt >= lim) fast = false;
         fp.nb = nb;
-        fp.H_lo = (int)(dbits(rsq[0]) >> 32);
-        const unsigned long long base = (unsigned long long)(unsigned)fp.H_lo << 32;
-        fp.U_span = (unsigned)(dbits(rsq[nb - 1]) >> 32) - (unsigned)fp.H_lo;
-        const unsigned long long ktop = (dbits(rsq[nb - 1]) - base) >> 26;
-        if (ktop >= 0x7ffffff0ULL) fast = false;
+        fp.nbias = (int)(unsigned)(0ULL - (unsigned long long)Kt);
+        fp.Hwin = (int)(dbits(rsq[nb - 1]) >> 32) - (31 << 20);
         const int pad = HTB_NBF - nb;
         for (int s = 0; s < HTB_NBF; ++s) {
-            if (s < pad) { fp.F[s] = -1; fp.E[s] = 0; }
-            else {
-                fp.F[s] = (int)((dbits(rsq[s - pad]) - base) >> 26);
-                fp.E[s] = dbits(rsq[s - pad]);
-            }
+            fp.F[s] = INT32_MIN; fp.E[s] = 0;
+            if (s < pad) continue;
+            const double e = rsq[s - pad];
+            fp.E[s] = dbits(e);
+            if (e == 0.0) continue;                      // only exact zeros satisfy it: always decided exactly
+            const long long d = (long long)(dbits(e) >> 26) - Kt;
+            if (d <= -lim) { fast = false; break; }
+            fp.F[s] = (int)d;
         }
         fp.E_top = dbits(rsq[nb - 1]);
     }
+    Call c;
+    if (c.begin()) return 1;
+    const double *c1[3] = {x1, y1, z1}, *c2[3] = {x2, y2, z2};
+    if (c.setup(mesh, 1, true, c1, stride1, n1, nullptr, c2, stride2, n2, nullptr, 0, false, first_cell1, last_cell1, flags,
+                fast ? 32 * htb_fast3_ppl() : HTB_TILE, fast ? 8.0 * lmax : 1.0e150)) return 1;
     unsigned long long *counts_dev = nullptr;
     if (c.ws.alloc((void **)&counts_dev, sizeof(unsigned long long) * (size_t)nb)) return 1;
     HTB_CUDA(cudaMemsetAsync(counts_dev, 0, sizeof(unsigned long long) * (size_t)nb, c.st));
@@ -662,7 +678,7 @@ extern "C" int htb_mesh_cell_id_indices(int32_t ndim, const double *x, const dou
         f.ncells *= f.nf[d];
     }
     SortedSample s;
-    if (htb_sort_sample(c.st, c.ws, f, dev, ds, n, nullptr, 0, false, s, &c.launches)) return 1;
+    if (htb_sort_sample(c.st, c.ws, f, dev, ds, n, nullptr, 0, false, 1.0e150, s, &c.launches)) return 1;
     std::vector<uint32_t> off((size_t)f.ncells + 1);
     HTB_CUDA(cudaMemcpyAsync(off.data(), s.off, sizeof(uint32_t) * off.size(), cudaMemcpyDeviceToHost, c.st));
     HTB_CUDA(cudaStreamSynchronize(c.st));

@@ -31,7 +31,7 @@ __global__ void k_seg_tiles(const uint32_t *__restrict__ off1, WalkGeom G, int64
         if (rid >= first_cell1 && rid < last_cell1) {
             const int64_t c0 = (s / G.nd1[F]) * G.nf1[F] + (int64_t)af * G.m1[F];
             const uint32_t cnt = off1[c0 + G.m1[F]] - off1[c0];
-            nt = (cnt + HTB_TILE - 1) / HTB_TILE;
+            nt = (cnt + (uint32_t)G.tile - 1) / (uint32_t)G.tile;
         }
         ntile[s] = nt;
     }
@@ -49,7 +49,7 @@ __global__ void k_fill_tiles(const uint32_t *__restrict__ off1, WalkGeom G, int6
         const int64_t c0 = (s / G.nd1[F]) * G.nf1[F] + (int64_t)af * G.m1[F];
         const uint32_t st = off1[c0];
         const uint32_t b = tbase[s];
-        for (uint32_t t = 0; t < nt; ++t) tiles[b + t] = make_uint2(st + t * HTB_TILE, (uint32_t)s);
+        for (uint32_t t = 0; t < nt; ++t) tiles[b + t] = make_uint2(st + t * (uint32_t)G.tile, (uint32_t)s);
     }
 }
 
@@ -93,6 +93,7 @@ k_count(const __grid_constant__ WalkGeom G, const __grid_constant__ WalkArrays A
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int DIM = V::DIM;
     constexpr int F = DIM - 1;
+    constexpr int PPL = V::PPL;                 // sample1 points per lane; a tile holds 32 * PPL points
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     typedef WarpSmem<DIM, V::NPAY> WS;
     unsigned char *mine = smem_raw + (size_t)warp * (WS::bytes() + (size_t)scratch_bytes_per_warp);
@@ -110,7 +111,7 @@ k_count(const __grid_constant__ WalkGeom G, const __grid_constant__ WalkArrays A
     }
     __syncwarp();
 
-    V v(P, scratch, lane);
+    V v(P, scratch, lane, A);
     uint32_t gchunk = 0;
     unsigned long long pairs = 0;
     unsigned int redone = 0;
@@ -131,26 +132,37 @@ k_count(const __grid_constant__ WalkGeom G, const __grid_constant__ WalkArrays A
 #pragma unroll
         for (int d = F - 1; d >= 0; --d) { fs[d] = (int)(slow % G.nf1[d]); slow /= G.nf1[d]; }
         const uint32_t segend = A.off1[c0 + G.m1[F]];
-        const int cnt = (int)min((uint32_t)HTB_TILE, segend - start);
-        // this lane's two points (index clamped for the bounding box; invalid ones get a far sentinel)
-        const bool v0 = lane < cnt, v1 = lane + 32 < cnt;
-        const uint32_t i0 = start + (uint32_t)min(lane, cnt - 1), i1 = start + (uint32_t)min(lane + 32, cnt - 1);
-        double p0[3] = {0, 0, 0}, p1[3] = {0, 0, 0}, blo[3] = {0, 0, 0}, bhi[3] = {0, 0, 0};
+        const int cnt = (int)min((uint32_t)(32 * PPL), segend - start);
+        // this lane's points (index clamped for the bounding box; unused lanes get a far sentinel)
+        bool val[PPL];
+        uint32_t idx[PPL];
+        double p[PPL][3], blo[3] = {0, 0, 0}, bhi[3] = {0, 0, 0};
+#pragma unroll
+        for (int q = 0; q < PPL; ++q) {
+            val[q] = lane + 32 * q < cnt;
+            idx[q] = start + (uint32_t)min(lane + 32 * q, cnt - 1);
+            p[q][0] = p[q][1] = p[q][2] = 0.0;
+        }
 #pragma unroll
         for (int d = 0; d < DIM; ++d) {
-            p0[d] = A.c1[d][i0];
-            p1[d] = A.c1[d][i1];
-            blo[d] = warp_min(fmin(p0[d], p1[d]));
-            bhi[d] = warp_max(fmax(p0[d], p1[d]));
+            double lo = 0.0, hi = 0.0;
+#pragma unroll
+            for (int q = 0; q < PPL; ++q) {
+                p[q][d] = A.c1[d][idx[q]];
+                lo = q ? fmin(lo, p[q][d]) : p[q][d];
+                hi = q ? fmax(hi, p[q][d]) : p[q][d];
+            }
+            blo[d] = warp_min(lo);
+            bhi[d] = warp_max(hi);
         }
-        if (!v0) p0[0] = 1.0e150;
-        if (!v1) p1[0] = 1.0e150;
+#pragma unroll
+        for (int q = 0; q < PPL; ++q) if (!val[q]) p[q][0] = G.sentinel;
         const int nsub = G.sym ? 2 : 1;
         for (int sub = 0; sub < nsub; ++sub) {
-            v.tile_begin(p0, p1, v0, v1, i0, i1, A);
+            v.tile_begin(p, val, idx, A);
             for (int pass = 0; pass < 2; ++pass) {
                 walk_tile<V>(v, G, A, S, gchunk, blo, bhi, fs, pairs, cnt, G.sym ? sub + 1 : 0, start, start + (uint32_t)cnt);
-                const bool redo = v.tile_end(A, i0, i1, pass, sub == 1 ? 2u : 1u);
+                const bool redo = v.tile_end(A, idx, pass, sub == 1 ? 2u : 1u);
                 if (!redo) break;
                 ++redone;
             }
@@ -164,94 +176,168 @@ k_count(const __grid_constant__ WalkGeom G, const __grid_constant__ WalkArrays A
 }
 
 // ------------------------------------------------------------------ Fast3
-// Queue capacity per lane.  Between two capacity checks a lane pushes at most 10 keys (one odd
-// leading j = 2, one group of 4 j = 8; the tail of <= 3 j = 6), so the flush threshold is QCAP - 10.
+// npairs_3d with <= 16 monotone bins.  Per evaluated pair the hot loop spends, besides the 8 strict
+// f64 operations of the reference (npairs_3d_engine.pyx:173-176), five integer instructions:
+//   key  = (bits(dsq) >> 26) - (bits(top edge) >> 26)      one LEA.HI; 32-bit, wraps harmlessly
+//   ctop += key >> 31                                      one LEA.HI: pairs certainly inside the top edge
+//   if (key <= F[second edge from the top]) push key       ISETP + predicated STS + pointer bump
+// plus two 3-input minimum trackers per TWO pairs that catch the cases 32 bits cannot decide: a key
+// EQUAL to the top-edge key (umin == 0) and a separation so small (or exactly zero) that the key
+// would wrap (hmin < Hwin).  The trackers are tested together with the queue-full test once per
+// group of 16 pairs; when one fires the group's pushes are rolled back and the group is re-evaluated
+// with exact 64-bit compares.  Queued keys (12 % of the pairs for log-spaced bins) are binned later at
+// full lane occupancy by a compaction cascade: flush1() applies one more edge and keeps the survivors
+// at the bottom of the queue, deep() runs the remaining edges only when enough survivors have piled
+// up.  The cumulative count of an edge is the number of keys that survived it — the reference's
+// top-down scan (npairs_3d_engine.pyx:178-182).  A queued key equal to an edge key marks the tile
+// dirty: its counts are discarded and the tile is re-evaluated exactly.
 #ifndef QCAP
-#define QCAP 64
+#define QCAP 72               // queue slots per lane
+#endif
+#ifndef QSURV
+#define QSURV 24              // run the deep cascade when a lane holds more survivors than this
 #endif
 #ifndef FAST3_WARPS
 #define FAST3_WARPS 8
 #define FAST3_MINBLOCKS 2
 #endif
-struct Fast3 {
-    static constexpr int DIM = 3, NPAY = 0, WARPS = FAST3_WARPS, MINBLOCKS = FAST3_MINBLOCKS;
+#ifndef FAST3_PPL
+#define FAST3_PPL 2
+#endif
+#define QGROUP 16             // pairs per lane between two queue checks
+
+__device__ __forceinline__ void lds_f64x2_tok(uint32_t addr, uint32_t tok, double &a, double &b)
+{
+    // not volatile: the scheduler may hoist these loads over the queue stores.  `tok` changes with every
+    // staged chunk, so loads of different chunks are never merged.
+    asm("ld.shared.v2.f64 {%0, %1}, [%2]; // %3" : "=d"(a), "=d"(b) : "r"(addr), "r"(tok));
+}
+__device__ __forceinline__ void sts_u32_nc(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v));
+}
+
+template <int PPL_>
+struct Fast3T {
+    static constexpr int DIM = 3, NPAY = 0, PPL = PPL_, WARPS = FAST3_WARPS, MINBLOCKS = FAST3_MINBLOCKS;
     static constexpr bool TMA = true;
+    static constexpr int GJ = QGROUP / PPL;     // sample2 points per group
+    static constexpr int TOP = HTB_NBF - 1;
     typedef Fast3Params Params;
     const Params &P;
     uint32_t qbase;             // shared-space address of this lane's queue column
+    uint32_t qs;                // end of the survivor region = start of the keys pushed since flush1()
     uint32_t qptr;              // next free slot (qbase + 128 * entries)
+    uint32_t qsave;             // qptr at the start of the current group (roll-back point)
     int lane;
-    double x0, y0, z0, x1, y1, z1;
+    double x[PPL], y[PPL], z[PPL];
     unsigned c[HTB_NBF];
-    unsigned clow;
-    unsigned eqmin;             // min over keys/edges of key ^ edge_key: 0 <=> some key equals an edge key
-    bool exact;
+    unsigned ctop, csave;
+    unsigned umin;
+    int hmin;
+    bool exact, dirty, always_exact;
     unsigned long long tot;
 
     static size_t scratch_bytes(const Params &) { return sizeof(uint32_t) * QCAP * 32; }
 
-    __device__ __forceinline__ Fast3(const Params &p, void *scratch, int ln) : P(p), lane(ln)
+    __device__ __forceinline__ Fast3T(const Params &p, void *scratch, int ln, const WalkArrays &A) : P(p), lane(ln)
     {
         qbase = smem_u32(scratch) + 4u * (uint32_t)ln;
-        qptr = qbase;
-        tot = 0; eqmin = 0xffffffffu; exact = false; clow = 0;
+        qs = qptr = qsave = qbase;
+        tot = 0; ctop = csave = 0; umin = 0xffffffffu; hmin = 0x7fffffff;
+        exact = dirty = false;
+        // a point outside [0, period] can be arbitrarily far away: the 32-bit keys could wrap
+        always_exact = ((A.flags1[0] | A.flags2[0]) & 1u) != 0u;
 #pragma unroll
         for (int s = 0; s < HTB_NBF; ++s) c[s] = 0;
     }
-    __device__ __forceinline__ void tile_begin(const double (&p0)[3], const double (&p1)[3], bool, bool, uint32_t, uint32_t,
+    __device__ __forceinline__ void tile_begin(const double (&p)[PPL][3], const bool (&)[PPL], const uint32_t (&)[PPL],
                                                const WalkArrays &)
     {
-        x0 = p0[0]; y0 = p0[1]; z0 = p0[2];
-        x1 = p1[0]; y1 = p1[1]; z1 = p1[2];
-        exact = false; eqmin = 0xffffffffu;
+#pragma unroll
+        for (int q = 0; q < PPL; ++q) { x[q] = p[q][0]; y[q] = p[q][1]; z[q] = p[q][2]; }
+        exact = always_exact; dirty = false;
     }
-    // Deferred binning = a compaction cascade over this lane's queue column.  Pass 1 applies the two
-    // top thresholds (68% + 22% of the in-range pairs of log-spaced bins die there); every further
-    // pass applies one threshold to the survivors, compacting them in place.  The cumulative count
-    // of a level is simply the number of survivors.  A key EQUAL to an edge key cannot be decided
-    // from 32 bits -> the tile is flagged dirty and redone with exact 64-bit compares.
+    // one cascade level: the keys in [qbase, end) were admitted by F[S + 1]; keep those <= F[S]
+    // (S == -1: nothing left to apply, only look for a key equal to F[0])
     template <int S>
-    __device__ __forceinline__ void cascade(uint32_t qend)
+    __device__ __forceinline__ void cascade(uint32_t end)
     {
-        if (!__any_sync(HTB_FULL, qend != qbase)) return;
-        const int F = P.F[S];
-        uint32_t w = qbase;
+        if (!__any_sync(HTB_FULL, end != qbase)) return;
+        const int Fin = P.F[S + 1];
+        int mx = (int)0x80000000;
+        if constexpr (S >= 0) {
+            const int Fk = P.F[S];
+            uint32_t w = qbase;
 #pragma unroll 2
-        for (uint32_t r = qbase; r != qend; r += 128u) {
-            const int key = (int)lds_u32(r);
-            eqmin = min(eqmin, (unsigned)(key ^ F));
-            if (key <= F) { sts_u32(w, (uint32_t)key); w += 128u; }
+            for (uint32_t r = qbase; r != end; r += 128u) {
+                const int key = (int)lds_u32(r);
+                mx = max(mx, key);
+                if (key <= Fk) { sts_u32_nc(w, (uint32_t)key); w += 128u; }
+            }
+            c[S] += (w - qbase) >> 7;
+            dirty |= (mx == Fin);
+            cascade<S - 1>(w);
+        } else {
+            for (uint32_t r = qbase; r != end; r += 128u) mx = max(mx, (int)lds_u32(r));
+            dirty |= (mx == Fin);
         }
-        c[S] += (w - qbase) >> 7;
-        if (S > 0) cascade<(S > 0 ? S - 1 : 0)>(w);
     }
-    __device__ __forceinline__ void flush()
+    __device__ __forceinline__ void deep()
     {
-        const int Ft = P.F[HTB_NBF - 1], Fs = P.F[HTB_NBF - 2];
-        unsigned nin = 0;
-        uint32_t w = qbase;
-#pragma unroll 2
-        for (uint32_t r = qbase; r != qptr; r += 128u) {
-            const int key = (int)lds_u32(r);
-            nin += (unsigned)(key - Ft - 1) >> 31;            // key <= Ft
-            eqmin = min(eqmin, min((unsigned)(key ^ Ft), (unsigned)(key ^ Fs)));
-            if (key <= Fs) { sts_u32(w, (uint32_t)key); w += 128u; }
-        }
-        c[HTB_NBF - 1] += nin;
-        c[HTB_NBF - 2] += (w - qbase) >> 7;
-        cascade<HTB_NBF - 3>(w);
-        qptr = qbase;
+        cascade<TOP - 3>(qs);
+        qs = qptr = qsave = qbase;
     }
-    __device__ __forceinline__ void pair_fast(double xs, double ys, double zs, double xj, double yj, double zj)
+    // bin the keys pushed since the last call against one more edge; survivors stay queued
+    __device__ __forceinline__ void flush1()
+    {
+        const int Fin = P.F[TOP - 1], Fk = P.F[TOP - 2];
+        int mx = (int)0x80000000;
+        uint32_t w = qs;
+#pragma unroll 2
+        for (uint32_t r = qs; r != qptr; r += 128u) {
+            const int key = (int)lds_u32(r);
+            mx = max(mx, key);
+            if (key <= Fk) { sts_u32_nc(w, (uint32_t)key); w += 128u; }
+        }
+        dirty |= (mx == Fin);
+        c[TOP - 1] += (qptr - qs) >> 7;
+        c[TOP - 2] += (w - qs) >> 7;
+        qs = qptr = qsave = w;
+        if (__any_sync(HTB_FULL, w > qbase + 128u * QSURV)) deep();
+    }
+    __device__ __forceinline__ void key_of(double xs, double ys, double zs, double xj, double yj, double zj, int &key, int &hi)
     {
         const double dx = xs - xj, dy = ys - yj, dz = zs - zj;
         const double dsq = dx * dx + dy * dy + dz * dz;
-        const int u = __double2hiint(dsq) - P.H_lo;
-        clow += (unsigned)u >> 31;
-        if ((unsigned)u <= P.U_span) {
-            sts_u32(qptr, __funnelshift_r((unsigned)__double2loint(dsq), (unsigned)u, 26));
-            qptr += 128u;
-        }
+        hi = __double2hiint(dsq);
+        // (bits >> 26) + nbias, written as the high word of a left shift so that it maps to one LEA.HI
+        key = (int)(__funnelshift_l((unsigned)__double2loint(dsq), (unsigned)hi, 6) + (unsigned)P.nbias);
+    }
+    __device__ __forceinline__ void push(int key)
+    {
+        ctop += (unsigned)key >> 31;
+        if (key <= P.F[TOP - 1]) { sts_u32_nc(qptr, (uint32_t)key); qptr += 128u; }
+    }
+    // one point of this lane against two staged points
+    __device__ __forceinline__ void pair2(double xs, double ys, double zs, double xa, double ya, double za,
+                                          double xb, double yb, double zb)
+    {
+        int ka, kb, ha, hb;
+        key_of(xs, ys, zs, xa, ya, za, ka, ha);
+        key_of(xs, ys, zs, xb, yb, zb, kb, hb);
+        umin = min(umin, min((unsigned)ka, (unsigned)kb));
+        hmin = min(hmin, min(ha, hb));
+        push(ka);
+        push(kb);
+    }
+    __device__ __forceinline__ void pair_fast(double xs, double ys, double zs, double xj, double yj, double zj)
+    {
+        int k, h;
+        key_of(xs, ys, zs, xj, yj, zj, k, h);
+        umin = min(umin, (unsigned)k);
+        hmin = min(hmin, h);
+        push(k);
     }
     __device__ __forceinline__ void pair_exact(double xs, double ys, double zs, double xj, double yj, double zj)
     {
@@ -263,67 +349,99 @@ struct Fast3 {
             for (int s = 0; s < HTB_NBF; ++s) c[s] += (b <= P.E[s]) ? 1u : 0u;
         }
     }
-    __device__ __forceinline__ void chunk(uint32_t stage, int lo, int hi, uint32_t, const double (&sh)[3])
+    __device__ __forceinline__ void exact_range(uint32_t stage, int j0, int j1, const double (&xs)[PPL],
+                                                const double (&ys)[PPL], const double (&zs)[PPL])
     {
         const uint32_t bx = stage, by = stage + 8 * HTB_CH, bz = stage + 16 * HTB_CH;
-        const double xs0 = x0 - sh[0], ys0 = y0 - sh[1], zs0 = z0 - sh[2];
-        const double xs1 = x1 - sh[0], ys1 = y1 - sh[1], zs1 = z1 - sh[2];
-        if (!exact) {
-            int j = lo;
-            if ((j & 1) && j < hi) {
-                const double xj = lds_f64(bx + 8 * j), yj = lds_f64(by + 8 * j), zj = lds_f64(bz + 8 * j);
-                pair_fast(xs0, ys0, zs0, xj, yj, zj);
-                pair_fast(xs1, ys1, zs1, xj, yj, zj);
-                ++j;
-            }
-            for (; j + 4 <= hi; j += 4) {
+        for (int j = j0; j < j1; ++j) {
+            const double xj = lds_f64(bx + 8 * j), yj = lds_f64(by + 8 * j), zj = lds_f64(bz + 8 * j);
 #pragma unroll
-                for (int u = 0; u < 4; u += 2) {
-                    double xa, xb, ya, yb, za, zb;
-                    lds_f64x2(bx + 8 * (j + u), xa, xb);
-                    lds_f64x2(by + 8 * (j + u), ya, yb);
-                    lds_f64x2(bz + 8 * (j + u), za, zb);
-                    pair_fast(xs0, ys0, zs0, xa, ya, za);
-                    pair_fast(xs1, ys1, zs1, xa, ya, za);
-                    pair_fast(xs0, ys0, zs0, xb, yb, zb);
-                    pair_fast(xs1, ys1, zs1, xb, yb, zb);
-                }
-                if (__any_sync(HTB_FULL, qptr > qbase + 128u * (QCAP - 10))) flush();
-            }
-            for (; j < hi; ++j) {
-                const double xj = lds_f64(bx + 8 * j), yj = lds_f64(by + 8 * j), zj = lds_f64(bz + 8 * j);
-                pair_fast(xs0, ys0, zs0, xj, yj, zj);
-                pair_fast(xs1, ys1, zs1, xj, yj, zj);
-            }
-            if (__any_sync(HTB_FULL, qptr > qbase + 128u * (QCAP - 10))) flush();
-        } else {
-            for (int j = lo; j < hi; ++j) {
-                const double xj = lds_f64(bx + 8 * j), yj = lds_f64(by + 8 * j), zj = lds_f64(bz + 8 * j);
-                pair_exact(xs0, ys0, zs0, xj, yj, zj);
-                pair_exact(xs1, ys1, zs1, xj, yj, zj);
-            }
+            for (int q = 0; q < PPL; ++q) pair_exact(xs[q], ys[q], zs[q], xj, yj, zj);
         }
     }
-    __device__ __forceinline__ bool tile_end(const WalkArrays &, uint32_t, uint32_t, int pass, unsigned wt)
+    // after every group of <= QGROUP pairs per lane
+    __device__ __forceinline__ void check(uint32_t stage, int j0, int j1, const double (&xs)[PPL],
+                                          const double (&ys)[PPL], const double (&zs)[PPL])
+    {
+        const bool undecided = (umin == 0u) | (hmin < P.Hwin);
+        const bool full = qptr > qbase + 128u * (QCAP - QGROUP);
+        if (__any_sync(HTB_FULL, undecided | full)) {
+            if (__any_sync(HTB_FULL, undecided)) {
+                // some pair of this group cannot be decided from its 32-bit key: take the whole group back
+                qptr = qsave; ctop = csave;
+                exact_range(stage, j0, j1, xs, ys, zs);
+                umin = 0xffffffffu; hmin = 0x7fffffff;
+            }
+            if (__any_sync(HTB_FULL, qptr > qbase + 128u * (QCAP - QGROUP))) flush1();
+        }
+        qsave = qptr; csave = ctop;
+    }
+    __device__ __forceinline__ void chunk(uint32_t stage, int lo, int hi, uint32_t tok, const double (&sh)[3])
+    {
+        const uint32_t bx = stage, by = stage + 8 * HTB_CH, bz = stage + 16 * HTB_CH;
+        double xs[PPL], ys[PPL], zs[PPL];
+#pragma unroll
+        for (int q = 0; q < PPL; ++q) { xs[q] = x[q] - sh[0]; ys[q] = y[q] - sh[1]; zs[q] = z[q] - sh[2]; }
+        if (exact) { exact_range(stage, lo, hi, xs, ys, zs); return; }
+        int j = lo;
+        if ((j & 1) && j < hi) {
+            const double xj = lds_f64(bx + 8 * j), yj = lds_f64(by + 8 * j), zj = lds_f64(bz + 8 * j);
+#pragma unroll
+            for (int q = 0; q < PPL; ++q) pair_fast(xs[q], ys[q], zs[q], xj, yj, zj);
+            check(stage, j, j + 1, xs, ys, zs);
+            ++j;
+        }
+        if (j + GJ <= hi) {
+            // register double buffering: the loads of the next two staged points are issued before the
+            // queue stores of the current ones (the hardware keeps shared loads behind earlier stores)
+            double xa, xb, ya, yb, za, zb;
+            lds_f64x2_tok(bx + 8 * j, tok, xa, xb);
+            lds_f64x2_tok(by + 8 * j, tok, ya, yb);
+            lds_f64x2_tok(bz + 8 * j, tok, za, zb);
+            for (; j + GJ <= hi; j += GJ) {
+#pragma unroll
+                for (int u = 0; u < GJ; u += 2) {
+                    double xc, xd, yc, yd, zc, zd;
+                    lds_f64x2_tok(bx + 8 * (j + u + 2), tok, xc, xd);     // may run past hi: harmless, never used
+                    lds_f64x2_tok(by + 8 * (j + u + 2), tok, yc, yd);
+                    lds_f64x2_tok(bz + 8 * (j + u + 2), tok, zc, zd);
+#pragma unroll
+                    for (int q = 0; q < PPL; ++q) pair2(xs[q], ys[q], zs[q], xa, ya, za, xb, yb, zb);
+                    xa = xc; xb = xd; ya = yc; yb = yd; za = zc; zb = zd;
+                }
+                check(stage, j, j + GJ, xs, ys, zs);
+            }
+        }
+        if (j < hi) {
+            for (int jj = j; jj < hi; ++jj) {
+                const double xj = lds_f64(bx + 8 * jj), yj = lds_f64(by + 8 * jj), zj = lds_f64(bz + 8 * jj);
+#pragma unroll
+                for (int q = 0; q < PPL; ++q) pair_fast(xs[q], ys[q], zs[q], xj, yj, zj);
+            }
+            check(stage, j, hi, xs, ys, zs);
+        }
+    }
+    __device__ __forceinline__ bool tile_end(const WalkArrays &, const uint32_t (&)[PPL], int pass, unsigned wt)
     {
         if (!exact) {
-            flush();
-            if (__any_sync(HTB_FULL, eqmin == 0u) && pass == 0) {
-                // a key collided with an edge key: throw the tile's counts away and redo it exactly
+            flush1();
+            deep();
+            c[TOP] += ctop;
+            ctop = csave = 0;
+            if (__any_sync(HTB_FULL, dirty) && pass == 0) {
+                // a queued key collided with an edge key: throw the tile's counts away and redo it exactly
 #pragma unroll
                 for (int s = 0; s < HTB_NBF; ++s) c[s] = 0;
-                clow = 0; eqmin = 0xffffffffu; exact = true;
+                dirty = false; exact = true;
                 return true;
             }
         }
-        const unsigned low = __reduce_add_sync(HTB_FULL, clow);
 #pragma unroll
         for (int s = 0; s < HTB_NBF; ++s) {
             const unsigned r = __reduce_add_sync(HTB_FULL, c[s]);
-            if (lane == s) tot += (unsigned long long)wt * ((unsigned long long)r + low);
+            if (lane == s) tot += (unsigned long long)wt * (unsigned long long)r;
             c[s] = 0;
         }
-        clow = 0;
         return false;
     }
     __device__ __forceinline__ void kernel_end()
@@ -332,12 +450,13 @@ struct Fast3 {
         if (lane < HTB_NBF && k >= 0 && tot) atomicAdd(P.counts + k, tot);
     }
 };
+typedef Fast3T<FAST3_PPL> Fast3;
 
 // ------------------------------------------------------------------ generic integer-count variants
 // per-warp u32 histogram in shared memory (scratch), flushed to the global u64 histogram per tile
 template <int KIND>   // 0: 3-D r   1: (rp, pi)   2: (s, mu) differential
 struct GenCount {
-    static constexpr int DIM = 3, NPAY = 0, WARPS = 8, MINBLOCKS = 2;
+    static constexpr int DIM = 3, NPAY = 0, PPL = 2, WARPS = 8, MINBLOCKS = 2;
     static constexpr bool TMA = true;
     typedef GenParams Params;
     const Params &P;
@@ -348,17 +467,17 @@ struct GenCount {
 
     static size_t scratch_bytes(const Params &p) { return sizeof(uint32_t) * (size_t)((p.nhist + 3) & ~3); }
 
-    __device__ GenCount(const Params &p, void *scratch, int ln) : P(p), hist((uint32_t *)scratch), lane(ln)
+    __device__ GenCount(const Params &p, void *scratch, int ln, const WalkArrays &) : P(p), hist((uint32_t *)scratch), lane(ln)
     {
         for (int k = lane; k < P.nhist; k += 32) hist[k] = 0;
         __syncwarp();
     }
-    __device__ __forceinline__ void tile_begin(const double (&p0)[3], const double (&p1)[3], bool a, bool b, uint32_t, uint32_t,
+    __device__ __forceinline__ void tile_begin(const double (&p)[2][3], const bool (&val)[2], const uint32_t (&)[2],
                                                const WalkArrays &)
     {
-        x0 = p0[0]; y0 = p0[1]; z0 = p0[2];
-        x1 = p1[0]; y1 = p1[1]; z1 = p1[2];
-        v0 = a; v1 = b;
+        x0 = p[0][0]; y0 = p[0][1]; z0 = p[0][2];
+        x1 = p[1][0]; y1 = p[1][1]; z1 = p[1][2];
+        v0 = val[0]; v1 = val[1];
     }
     __device__ __forceinline__ void pair(bool valid, double xs, double ys, double zs, double xj, double yj, double zj)
     {
@@ -415,7 +534,7 @@ struct GenCount {
             pair(v1, xs1, ys1, zs1, xj, yj, zj);
         }
     }
-    __device__ __forceinline__ bool tile_end(const WalkArrays &, uint32_t, uint32_t, int, unsigned wt)
+    __device__ __forceinline__ bool tile_end(const WalkArrays &, const uint32_t (&)[2], int, unsigned wt)
     {
         __syncwarp();
         for (int k = lane; k < P.nhist; k += 32) {
@@ -465,7 +584,7 @@ __device__ __forceinline__ double warp_sum(double v)
 }
 
 struct Marked3 {
-    static constexpr int DIM = 3, NPAY = HTB_MAX_NW, WARPS = 8, MINBLOCKS = 2;
+    static constexpr int DIM = 3, NPAY = HTB_MAX_NW, PPL = 2, WARPS = 8, MINBLOCKS = 2;
     static constexpr bool TMA = true;
     typedef GenParams Params;
     const Params &P;
@@ -477,17 +596,18 @@ struct Marked3 {
 
     static size_t scratch_bytes(const Params &p) { return sizeof(double) * (size_t)((p.nhist + 1) & ~1); }
 
-    __device__ Marked3(const Params &p, void *scratch, int ln) : P(p), hist((double *)scratch), lane(ln)
+    __device__ Marked3(const Params &p, void *scratch, int ln, const WalkArrays &) : P(p), hist((double *)scratch), lane(ln)
     {
         for (int k = lane; k < P.nhist; k += 32) hist[k] = 0.0;
         __syncwarp();
     }
-    __device__ __forceinline__ void tile_begin(const double (&p0)[3], const double (&p1)[3], bool a, bool b,
-                                               uint32_t i0, uint32_t i1, const WalkArrays &A)
+    __device__ __forceinline__ void tile_begin(const double (&p)[2][3], const bool (&val)[2], const uint32_t (&idx)[2],
+                                               const WalkArrays &A)
     {
-        x0 = p0[0]; y0 = p0[1]; z0 = p0[2];
-        x1 = p1[0]; y1 = p1[1]; z1 = p1[2];
-        v0 = a; v1 = b;
+        x0 = p[0][0]; y0 = p[0][1]; z0 = p[0][2];
+        x1 = p[1][0]; y1 = p[1][1]; z1 = p[1][2];
+        v0 = val[0]; v1 = val[1];
+        const uint32_t i0 = idx[0], i1 = idx[1];
 #pragma unroll
         for (int k = 0; k < HTB_MAX_NW; ++k) {
             wa[k] = (k < A.nw) ? A.pay1[(size_t)i0 * A.nw + k] : 0.0;
@@ -523,7 +643,7 @@ struct Marked3 {
             pair(v1, wb, xs1, ys1, zs1, xj, yj, zj, bw + 8 * j * P.nw);
         }
     }
-    __device__ __forceinline__ bool tile_end(const WalkArrays &, uint32_t, uint32_t, int, unsigned)
+    __device__ __forceinline__ bool tile_end(const WalkArrays &, const uint32_t (&)[2], int, unsigned)
     {
         __syncwarp();
         for (int k = lane; k < P.nhist; k += 32) {
@@ -540,7 +660,7 @@ struct Marked3 {
 // scratch layout per warp: acc[slot][64], slot 0 = mass inside rp[0]; slots 1..nbin = mass in bin b
 // (differential); slots nbin+1..2*nbin = sum m*(1 - ln(rp[b+1]^2 / d^2)) over pairs in bin b.
 struct DSigma {
-    static constexpr int DIM = 2, NPAY = 1, WARPS = 4, MINBLOCKS = 2;
+    static constexpr int DIM = 2, NPAY = 1, PPL = 2, WARPS = 4, MINBLOCKS = 2;
     static constexpr bool TMA = true;
     typedef GenParams Params;
     const Params &P;
@@ -551,12 +671,12 @@ struct DSigma {
 
     static size_t scratch_bytes(const Params &p) { return sizeof(double) * 64 * (size_t)(2 * (p.n0 - 1) + 1); }
 
-    __device__ DSigma(const Params &p, void *scratch, int ln) : P(p), acc((double *)scratch), lane(ln) {}
-    __device__ __forceinline__ void tile_begin(const double (&p0)[3], const double (&p1)[3], bool a, bool b, uint32_t, uint32_t,
+    __device__ DSigma(const Params &p, void *scratch, int ln, const WalkArrays &) : P(p), acc((double *)scratch), lane(ln) {}
+    __device__ __forceinline__ void tile_begin(const double (&p)[2][3], const bool (&val)[2], const uint32_t (&)[2],
                                                const WalkArrays &)
     {
-        x0 = p0[0]; y0 = p0[1]; x1 = p1[0]; y1 = p1[1];
-        v0 = a; v1 = b;
+        x0 = p[0][0]; y0 = p[0][1]; x1 = p[1][0]; y1 = p[1][1];
+        v0 = val[0]; v1 = val[1];
         const int nslot = 2 * (P.n0 - 1) + 1;
         for (int s = 0; s < nslot; ++s) { acc[s * 64 + lane] = 0.0; acc[s * 64 + 32 + lane] = 0.0; }
         __syncwarp();
@@ -597,11 +717,11 @@ struct DSigma {
             inside += acc[(k + 1) * 64 + col];
         }
     }
-    __device__ __forceinline__ bool tile_end(const WalkArrays &A, uint32_t i0, uint32_t i1, int, unsigned)
+    __device__ __forceinline__ bool tile_end(const WalkArrays &A, const uint32_t (&idx)[2], int, unsigned)
     {
         __syncwarp();
-        finish(v0, lane, i0, A);
-        finish(v1, 32 + lane, i1, A);
+        finish(v0, lane, idx[0], A);
+        finish(v1, 32 + lane, idx[1], A);
         __syncwarp();
         return false;
     }
@@ -616,7 +736,7 @@ struct DSigma {
 // scratch per warp: cnt[slot][64] u32 (slot 0 = inside rp[0], slot b+1 = bin b), es[bin][64] i32,
 // pm[bin][64] f64.
 struct DSigmaU {
-    static constexpr int DIM = 2, NPAY = 0, WARPS = 4, MINBLOCKS = 3;
+    static constexpr int DIM = 2, NPAY = 0, PPL = 2, WARPS = 4, MINBLOCKS = 3;
     static constexpr bool TMA = true;
     typedef GenParams Params;
     const Params &P;
@@ -633,7 +753,7 @@ struct DSigmaU {
         const size_t nbin = (size_t)(p.n0 - 1);
         return 64 * (8 * nbin + 4 * nbin + 4 * (nbin + 1));
     }
-    __device__ DSigmaU(const Params &p, void *scratch, int ln) : P(p), lane(ln)
+    __device__ DSigmaU(const Params &p, void *scratch, int ln, const WalkArrays &) : P(p), lane(ln)
     {
         nbin = P.n0 - 1;
         pm = (double *)scratch;
@@ -641,11 +761,11 @@ struct DSigmaU {
         cnt = (unsigned *)(es + 64 * nbin);
         since = 0;
     }
-    __device__ __forceinline__ void tile_begin(const double (&p0)[3], const double (&p1)[3], bool a, bool b, uint32_t, uint32_t,
+    __device__ __forceinline__ void tile_begin(const double (&p)[2][3], const bool (&val)[2], const uint32_t (&)[2],
                                                const WalkArrays &)
     {
-        x0 = p0[0]; y0 = p0[1]; x1 = p1[0]; y1 = p1[1];
-        v0 = a; v1 = b;
+        x0 = p[0][0]; y0 = p[0][1]; x1 = p[1][0]; y1 = p[1][1];
+        v0 = val[0]; v1 = val[1];
         for (int s = 0; s < nbin; ++s) {
             pm[s * 64 + lane] = 1.0; pm[s * 64 + 32 + lane] = 1.0;
             es[s * 64 + lane] = 0; es[s * 64 + 32 + lane] = 0;
@@ -714,11 +834,11 @@ struct DSigmaU {
             inside += n;
         }
     }
-    __device__ __forceinline__ bool tile_end(const WalkArrays &, uint32_t i0, uint32_t i1, int, unsigned)
+    __device__ __forceinline__ bool tile_end(const WalkArrays &, const uint32_t (&idx)[2], int, unsigned)
     {
         __syncwarp();
-        finish(v0, lane, i0);
-        finish(v1, 32 + lane, i1);
+        finish(v0, lane, idx[0]);
+        finish(v1, 32 + lane, idx[1]);
         __syncwarp();
         return false;
     }
@@ -749,6 +869,7 @@ static int launch_count(cudaStream_t st, const WalkGeom &G, const WalkArrays &A,
     return 0;
 }
 
+int htb_fast3_ppl() { return FAST3_PPL; }
 int htb_launch_fast3(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const Fast3Params &P, int *l)
 { return launch_count<Fast3>(st, G, A, P, l); }
 int htb_launch_gen(cudaStream_t st, int kind, const WalkGeom &G, const WalkArrays &A, const GenParams &P, int *l)
@@ -776,7 +897,7 @@ int htb_build_tiles(cudaStream_t st, Workspace &ws, const WalkGeom &G, const Sor
     if (ws.alloc((void **)&ntile, sizeof(uint32_t) * (size_t)(nseg + 1))) return 1;
     if (ws.alloc((void **)&tbase, sizeof(uint32_t) * (size_t)(nseg + 1))) return 1;
     if (ws.alloc((void **)&total, sizeof(uint32_t) * 4)) return 1;
-    const int64_t max_tiles = s1.n / HTB_TILE + nseg + 1;
+    const int64_t max_tiles = s1.n / G.tile + nseg + 1;
     uint2 *tiles = nullptr;
     if (ws.alloc((void **)&tiles, sizeof(uint2) * (size_t)max_tiles)) return 1;
     int blocks = (int)((nseg + 255) / 256);

@@ -7,9 +7,9 @@
 
 struct Fast3Params {
     int nb;                          // number of rbins (<= HTB_NBF); slot s holds bin s - (HTB_NBF - nb)
-    int H_lo;                        // high word of the lowest squared edge
-    unsigned U_span;                 // high word of the top squared edge minus H_lo
-    int F[HTB_NBF];                  // 32-bit monotone keys of the squared edges (pads = -1)
+    int nbias;                       // -(bits(top squared edge) >> 26), low 32 bits: key = (bits(dsq) >> 26) + nbias
+    int Hwin;                        // pairs whose dsq high word is below this are re-evaluated exactly (key would wrap)
+    int F[HTB_NBF];                  // keys of the squared edges relative to the top edge (pads / zero edges = INT_MIN)
     unsigned long long E[HTB_NBF];   // raw bit patterns of the squared edges (pads = 0)
     unsigned long long E_top;
     unsigned long long *counts;      // [nb] global accumulators
@@ -26,6 +26,7 @@ struct GenParams {
     const uint32_t *perm1;           // DSigma: sorted position -> input row
 };
 
+int htb_fast3_ppl();            // sample1 points per lane of the fast kernel (its tiles hold 32x that)
 int htb_launch_fast3(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const Fast3Params &P, int *launches);
 int htb_launch_gen(cudaStream_t st, int kind, const WalkGeom &G, const WalkArrays &A, const GenParams &P, int *launches);
 int htb_build_tiles(cudaStream_t st, Workspace &ws, const WalkGeom &G, const SortedSample &s1,

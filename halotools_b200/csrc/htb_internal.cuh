@@ -10,7 +10,7 @@
 
 #include "../../include/halotools_b200.h"
 
-#define HTB_TILE 64            // sample1 points per tile (one warp, 2 points per lane)
+#define HTB_TILE 64            // default sample1 points per tile (one warp, 2 points per lane)
 #define HTB_MAX_DIM 3
 
 struct HtbError {
@@ -61,7 +61,7 @@ struct Workspace;   // stream-ordered allocations of one engine call (freed at t
 // ---- mesh.cu
 int htb_sort_sample(cudaStream_t st, Workspace &ws, const FineGrid &g,
                     const double *const *coords_dev, int64_t stride, int64_t n,
-                    const double *w_dev, int nw, bool keep_perm, SortedSample &out, int *launches);
+                    const double *w_dev, int nw, bool keep_perm, double pad_value, SortedSample &out, int *launches);
 int htb_exclusive_scan_u32(cudaStream_t st, Workspace &ws, const uint32_t *in, uint32_t *out,
                            int64_t n, uint32_t *total_dev, int *launches);
 int htb_ref_cell_ids(cudaStream_t st, int dim, const double *const *coords_dev, int64_t stride, int64_t n,

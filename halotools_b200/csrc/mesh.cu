@@ -62,13 +62,13 @@ k_scatter(const double *__restrict__ x, const double *__restrict__ y, const doub
 }
 
 // pad entries [n, npad) with a far-away sentinel so that staging reads past a span end are harmless
-__global__ void k_pad(double *a, double *b, double *c, int64_t n, int64_t npad)
+__global__ void k_pad(double *a, double *b, double *c, int64_t n, int64_t npad, double value)
 {
     int64_t i = n + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < npad) {
-        a[i] = 1.0e150;
-        b[i] = 1.0e150;
-        if (c) c[i] = 1.0e150;
+        a[i] = value;
+        b[i] = value;
+        if (c) c[i] = value;
     }
 }
 
@@ -189,7 +189,7 @@ static int grid_for(int64_t n, int threads)
 
 int htb_sort_sample(cudaStream_t st, Workspace &ws, const FineGrid &g,
                     const double *const *cd, int64_t stride, int64_t n,
-                    const double *w_dev, int nw, bool keep_perm, SortedSample &out, int *launches)
+                    const double *w_dev, int nw, bool keep_perm, double pad_value, SortedSample &out, int *launches)
 {
     out.n = n;
     out.g = g;
@@ -227,7 +227,7 @@ int htb_sort_sample(cudaStream_t st, Workspace &ws, const FineGrid &g,
                                                  out.c[0], out.c[1], nullptr, out.perm, w_dev, out.w, nw);
         if (launches) *launches += 1;
     }
-    k_pad<<<1, 32, 0, st>>>(out.c[0], out.c[1], g.dim == 3 ? out.c[2] : nullptr, n, out.npad);
+    k_pad<<<1, 32, 0, st>>>(out.c[0], out.c[1], g.dim == 3 ? out.c[2] : nullptr, n, out.npad, pad_value);
     if (launches) *launches += 1;
     HTB_CUDA(cudaGetLastError());
     return 0;

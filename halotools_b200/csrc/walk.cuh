@@ -19,7 +19,9 @@
 #define HTB_WARPS 8                 // warps per block of the counting kernels (overridable per variant)
 #define HTB_CH 64                   // sample2 points per staged chunk
 #define HTB_NSTAGE 2
-#define HTB_SPAN_CAP 128
+#ifndef HTB_SPAN_CAP
+#define HTB_SPAN_CAP 96
+#endif
 #define HTB_FULL 0xffffffffu
 
 struct WalkGeom {
@@ -32,6 +34,8 @@ struct WalkGeom {
     int m1[3], m2[3], nf1[3], nf2[3];
     double period[3], h2[3], slop[3], reach[3];
     double r2slow;                  // (max separation over the slow dims)^2, with safety margin
+    double sentinel;                // x coordinate given to the unused lanes of a partial tile (never in range)
+    int tile;                       // sample1 points per tile (32 * points per lane of the kernel variant)
 };
 
 struct WalkArrays {
@@ -65,7 +69,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+__device__ __forceinline__ uint32_t mbar_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t ok;
     do {
@@ -77,6 +81,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
             : "r"(bar), "r"(parity)
             : "memory");
     } while (!ok);
+    return ok;      // data dependence for loads that must not be scheduled above the wait
 }
 // 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
@@ -143,9 +148,10 @@ struct TileInfo {
 };
 
 // The walker.  V must provide:
-//   static constexpr int DIM, NPAY; static constexpr bool TMA;
-//   __device__ void chunk(uint32_t stage_smem_addr, int lo, int hi, uint32_t j0, const double (&sh)[3]) — evaluate
-//        pairs between the lane's points (shifted by sh) and staged sample2 entries [lo, hi).
+//   static constexpr int DIM, NPAY, PPL; static constexpr bool TMA;
+//   __device__ void chunk(uint32_t stage_smem_addr, int lo, int hi, uint32_t tok, const double (&sh)[3]) — evaluate
+//        pairs between the lane's PPL points (shifted by sh) and staged sample2 entries [lo, hi); tok is a value
+//        that depends on the stage's mbarrier wait (an input for loads that may be scheduled freely).
 template <class V>
 __device__ __forceinline__ void walk_tile(V &v, const WalkGeom &G, const WalkArrays &A,
                                           WarpSmem<V::DIM, V::NPAY> &S, uint32_t &gchunk,
@@ -212,7 +218,8 @@ __device__ __forceinline__ void walk_tile(V &v, const WalkGeom &G, const WalkArr
             // ---- current chunk
             const uint32_t jb = S.span[3 * sc], je = S.span[3 * sc + 1], code = S.span[3 * sc + 2];
             const int stg = gchunk % HTB_NSTAGE;
-            if (V::TMA) mbar_wait(S.bar[stg], (gchunk / HTB_NSTAGE) & 1u);
+            uint32_t tok = jc;
+            if (V::TMA) tok += mbar_wait(S.bar[stg], (gchunk / HTB_NSTAGE) & 1u);
             else __syncwarp();
             const int lo = (int)(max(jb, jc) - jc);
             const int hi = (int)(min(je, jc + HTB_CH) - jc);
@@ -222,7 +229,7 @@ __device__ __forceinline__ void walk_tile(V &v, const WalkGeom &G, const WalkArr
                 const int k = (int)((code >> (2 * d)) & 3u) - 1;
                 sh[d] = (double)(k * G.pbc) * G.period[d];
             }
-            v.chunk(smem_u32(S.stage[stg]), lo, hi, jc, sh);
+            v.chunk(smem_u32(S.stage[stg]), lo, hi, tok, sh);
             pairs += (unsigned long long)(hi - lo) * (unsigned)tile_cnt;
             __syncwarp();
             ++gchunk;
