@@ -98,14 +98,15 @@ k_count(const __grid_constant__ WalkGeom G, const __grid_constant__ WalkArrays A
     typedef WarpSmem<DIM, V::NPAY> WS;
     unsigned char *mine = smem_raw + (size_t)warp * (WS::bytes() + (size_t)scratch_bytes_per_warp);
     WS S;
-    for (int s = 0; s < HTB_NSTAGE; ++s) S.stage[s] = (double *)mine + s * WS::stage_doubles();
+    S.stage0 = (double *)mine;
+    S.stage0_s = smem_u32(mine);
     unsigned char *bars = mine + sizeof(double) * HTB_NSTAGE * WS::stage_doubles();
-    for (int s = 0; s < HTB_NSTAGE; ++s) S.bar[s] = smem_u32(bars + 16 * s);
+    S.bar0 = smem_u32(bars);
     S.span = (uint32_t *)(bars + 16 * HTB_NSTAGE);
     void *scratch = mine + WS::bytes();
     if (V::TMA) {
         if (lane == 0) {
-            for (int s = 0; s < HTB_NSTAGE; ++s) mbar_init(S.bar[s], 1);
+            for (int s = 0; s < HTB_NSTAGE; ++s) mbar_init(S.bar(s), 1);
             mbar_fence_init();
         }
     }
@@ -158,8 +159,10 @@ k_count(const __grid_constant__ WalkGeom G, const __grid_constant__ WalkArrays A
 #pragma unroll
         for (int q = 0; q < PPL; ++q) if (!val[q]) p[q][0] = G.sentinel;
         const int nsub = G.sym ? 2 : 1;
+#pragma unroll 1
         for (int sub = 0; sub < nsub; ++sub) {
             v.tile_begin(p, val, idx, A);
+#pragma unroll 1
             for (int pass = 0; pass < 2; ++pass) {
                 walk_tile<V>(v, G, A, S, gchunk, blo, bhi, fs, pairs, cnt, G.sym ? sub + 1 : 0, start, start + (uint32_t)cnt);
                 const bool redo = v.tile_end(A, idx, pass, sub == 1 ? 2u : 1u);
@@ -223,6 +226,7 @@ struct Fast3T {
     static constexpr bool TMA = true;
     static constexpr int GJ = QGROUP / PPL;     // sample2 points per group
     static constexpr int TOP = HTB_NBF - 1;
+    static constexpr uint32_t QFULL = 128u * (QCAP - QGROUP - PPL);   // flush when a lane's queue is longer than this
     typedef Fast3Params Params;
     const Params &P;
     uint32_t qbase;             // shared-space address of this lane's queue column
@@ -230,7 +234,10 @@ struct Fast3T {
     uint32_t qptr;              // next free slot (qbase + 128 * entries)
     uint32_t qsave;             // qptr at the start of the current group (roll-back point)
     int lane;
-    double x[PPL], y[PPL], z[PPL];
+    uint32_t idx[PPL];          // sorted positions of this lane's points (coordinates are re-read when the shift changes)
+    unsigned valmask;
+    double xs[PPL], ys[PPL], zs[PPL];   // this lane's points, periodic shift applied
+    double sentinel;
     unsigned c[HTB_NBF];
     unsigned ctop, csave;
     unsigned umin;
@@ -246,17 +253,55 @@ struct Fast3T {
         qs = qptr = qsave = qbase;
         tot = 0; ctop = csave = 0; umin = 0xffffffffu; hmin = 0x7fffffff;
         exact = dirty = false;
+        valmask = 0; sentinel = 0.0;
         // a point outside [0, period] can be arbitrarily far away: the 32-bit keys could wrap
         always_exact = ((A.flags1[0] | A.flags2[0]) & 1u) != 0u;
 #pragma unroll
         for (int s = 0; s < HTB_NBF; ++s) c[s] = 0;
+#pragma unroll
+        for (int q = 0; q < PPL; ++q) { idx[q] = 0; xs[q] = ys[q] = zs[q] = 0.0; }
     }
-    __device__ __forceinline__ void tile_begin(const double (&p)[PPL][3], const bool (&)[PPL], const uint32_t (&)[PPL],
+    __device__ __forceinline__ void tile_begin(const double (&p)[PPL][3], const bool (&val)[PPL], const uint32_t (&id)[PPL],
                                                const WalkArrays &)
     {
+        valmask = 0;
 #pragma unroll
-        for (int q = 0; q < PPL; ++q) { x[q] = p[q][0]; y[q] = p[q][1]; z[q] = p[q][2]; }
+        for (int q = 0; q < PPL; ++q) {
+            idx[q] = id[q];
+            if (val[q]) valmask |= 1u << q; else sentinel = p[q][0];
+        }
         exact = always_exact; dirty = false;
+    }
+    __device__ __forceinline__ void set_shift(const double (&sh)[3], const WalkArrays &A)
+    {
+#pragma unroll
+        for (int q = 0; q < PPL; ++q) {
+            const double bx = ((valmask >> q) & 1u) ? A.c1[0][idx[q]] : sentinel;
+            xs[q] = bx - sh[0];
+            ys[q] = A.c1[1][idx[q]] - sh[1];
+            zs[q] = A.c1[2][idx[q]] - sh[2];
+        }
+    }
+    // Compaction pass over this lane's keys in [r, end): keys <= Fk are kept (moved down to w), a key equal to Fin
+    // (the edge that admitted the keys) marks the tile dirty.  Four independent loads per trip hide the latency.
+    __device__ __forceinline__ uint32_t compact(uint32_t r, uint32_t end, uint32_t w, int Fk, int Fin)
+    {
+        bool eq = false;
+        for (; r + 512u <= end; r += 512u) {
+            const int k0 = (int)lds_u32(r), k1 = (int)lds_u32(r + 128u), k2 = (int)lds_u32(r + 256u), k3 = (int)lds_u32(r + 384u);
+            eq |= (k0 == Fin) | (k1 == Fin) | (k2 == Fin) | (k3 == Fin);
+            if (k0 <= Fk) { sts_u32_nc(w, (uint32_t)k0); w += 128u; }
+            if (k1 <= Fk) { sts_u32_nc(w, (uint32_t)k1); w += 128u; }
+            if (k2 <= Fk) { sts_u32_nc(w, (uint32_t)k2); w += 128u; }
+            if (k3 <= Fk) { sts_u32_nc(w, (uint32_t)k3); w += 128u; }
+        }
+        for (; r != end; r += 128u) {
+            const int k0 = (int)lds_u32(r);
+            eq |= (k0 == Fin);
+            if (k0 <= Fk) { sts_u32_nc(w, (uint32_t)k0); w += 128u; }
+        }
+        dirty |= eq;
+        return w;
     }
     // one cascade level: the keys in [qbase, end) were admitted by F[S + 1]; keep those <= F[S]
     // (S == -1: nothing left to apply, only look for a key equal to F[0])
@@ -264,23 +309,12 @@ struct Fast3T {
     __device__ __forceinline__ void cascade(uint32_t end)
     {
         if (!__any_sync(HTB_FULL, end != qbase)) return;
-        const int Fin = P.F[S + 1];
-        int mx = (int)0x80000000;
         if constexpr (S >= 0) {
-            const int Fk = P.F[S];
-            uint32_t w = qbase;
-#pragma unroll 2
-            for (uint32_t r = qbase; r != end; r += 128u) {
-                const int key = (int)lds_u32(r);
-                mx = max(mx, key);
-                if (key <= Fk) { sts_u32_nc(w, (uint32_t)key); w += 128u; }
-            }
+            const uint32_t w = compact(qbase, end, qbase, P.F[S], P.F[S + 1]);
             c[S] += (w - qbase) >> 7;
-            dirty |= (mx == Fin);
             cascade<S - 1>(w);
         } else {
-            for (uint32_t r = qbase; r != end; r += 128u) mx = max(mx, (int)lds_u32(r));
-            dirty |= (mx == Fin);
+            (void)compact(qbase, end, qbase, (int)0x80000000, P.F[0]);
         }
     }
     __device__ __forceinline__ void deep()
@@ -289,26 +323,17 @@ struct Fast3T {
         qs = qptr = qsave = qbase;
     }
     // bin the keys pushed since the last call against one more edge; survivors stay queued
-    __device__ __forceinline__ void flush1()
+    __device__ __forceinline__ void flush1(bool force_deep)
     {
-        const int Fin = P.F[TOP - 1], Fk = P.F[TOP - 2];
-        int mx = (int)0x80000000;
-        uint32_t w = qs;
-#pragma unroll 2
-        for (uint32_t r = qs; r != qptr; r += 128u) {
-            const int key = (int)lds_u32(r);
-            mx = max(mx, key);
-            if (key <= Fk) { sts_u32_nc(w, (uint32_t)key); w += 128u; }
-        }
-        dirty |= (mx == Fin);
+        const uint32_t w = compact(qs, qptr, qs, P.F[TOP - 2], P.F[TOP - 1]);
         c[TOP - 1] += (qptr - qs) >> 7;
         c[TOP - 2] += (w - qs) >> 7;
         qs = qptr = qsave = w;
-        if (__any_sync(HTB_FULL, w > qbase + 128u * QSURV)) deep();
+        if (force_deep || __any_sync(HTB_FULL, w > qbase + 128u * QSURV)) deep();
     }
-    __device__ __forceinline__ void key_of(double xs, double ys, double zs, double xj, double yj, double zj, int &key, int &hi)
+    __device__ __forceinline__ void key_of(double x1s, double y1s, double z1s, double xj, double yj, double zj, int &key, int &hi)
     {
-        const double dx = xs - xj, dy = ys - yj, dz = zs - zj;
+        const double dx = x1s - xj, dy = y1s - yj, dz = z1s - zj;
         const double dsq = dx * dx + dy * dy + dz * dz;
         hi = __double2hiint(dsq);
         // (bits >> 26) + nbias, written as the high word of a left shift so that it maps to one LEA.HI
@@ -320,28 +345,27 @@ struct Fast3T {
         if (key <= P.F[TOP - 1]) { sts_u32_nc(qptr, (uint32_t)key); qptr += 128u; }
     }
     // one point of this lane against two staged points
-    __device__ __forceinline__ void pair2(double xs, double ys, double zs, double xa, double ya, double za,
-                                          double xb, double yb, double zb)
+    __device__ __forceinline__ void pair2(int q, double xa, double ya, double za, double xb, double yb, double zb)
     {
         int ka, kb, ha, hb;
-        key_of(xs, ys, zs, xa, ya, za, ka, ha);
-        key_of(xs, ys, zs, xb, yb, zb, kb, hb);
+        key_of(xs[q], ys[q], zs[q], xa, ya, za, ka, ha);
+        key_of(xs[q], ys[q], zs[q], xb, yb, zb, kb, hb);
         umin = min(umin, min((unsigned)ka, (unsigned)kb));
         hmin = min(hmin, min(ha, hb));
         push(ka);
         push(kb);
     }
-    __device__ __forceinline__ void pair_fast(double xs, double ys, double zs, double xj, double yj, double zj)
+    __device__ __forceinline__ void pair_fast(int q, double xj, double yj, double zj)
     {
         int k, h;
-        key_of(xs, ys, zs, xj, yj, zj, k, h);
+        key_of(xs[q], ys[q], zs[q], xj, yj, zj, k, h);
         umin = min(umin, (unsigned)k);
         hmin = min(hmin, h);
         push(k);
     }
-    __device__ __forceinline__ void pair_exact(double xs, double ys, double zs, double xj, double yj, double zj)
+    __device__ __forceinline__ void pair_exact(int q, double xj, double yj, double zj)
     {
-        const double dx = xs - xj, dy = ys - yj, dz = zs - zj;
+        const double dx = xs[q] - xj, dy = ys[q] - yj, dz = zs[q] - zj;
         const double dsq = dx * dx + dy * dy + dz * dz;
         const unsigned long long b = (unsigned long long)__double_as_longlong(dsq);
         if (b <= P.E_top) {
@@ -349,48 +373,45 @@ struct Fast3T {
             for (int s = 0; s < HTB_NBF; ++s) c[s] += (b <= P.E[s]) ? 1u : 0u;
         }
     }
-    __device__ __forceinline__ void exact_range(uint32_t stage, int j0, int j1, const double (&xs)[PPL],
-                                                const double (&ys)[PPL], const double (&zs)[PPL])
+    __device__ __forceinline__ void exact_range(uint32_t stage, int j0, int j1)
     {
         const uint32_t bx = stage, by = stage + 8 * HTB_CH, bz = stage + 16 * HTB_CH;
+#pragma unroll 1
         for (int j = j0; j < j1; ++j) {
             const double xj = lds_f64(bx + 8 * j), yj = lds_f64(by + 8 * j), zj = lds_f64(bz + 8 * j);
 #pragma unroll
-            for (int q = 0; q < PPL; ++q) pair_exact(xs[q], ys[q], zs[q], xj, yj, zj);
+            for (int q = 0; q < PPL; ++q) pair_exact(q, xj, yj, zj);
         }
     }
-    // after every group of <= QGROUP pairs per lane
-    __device__ __forceinline__ void check(uint32_t stage, int j0, int j1, const double (&xs)[PPL],
-                                          const double (&ys)[PPL], const double (&zs)[PPL])
+    // after every group of <= QGROUP + PPL pairs per lane: staged entries [j0, j1) since the last check
+    __device__ __forceinline__ void check(uint32_t stage, int j0, int j1)
     {
         const bool undecided = (umin == 0u) | (hmin < P.Hwin);
-        const bool full = qptr > qbase + 128u * (QCAP - QGROUP);
+        const bool full = qptr > qbase + QFULL;
         if (__any_sync(HTB_FULL, undecided | full)) {
             if (__any_sync(HTB_FULL, undecided)) {
                 // some pair of this group cannot be decided from its 32-bit key: take the whole group back
                 qptr = qsave; ctop = csave;
-                exact_range(stage, j0, j1, xs, ys, zs);
+                exact_range(stage, j0, j1);
                 umin = 0xffffffffu; hmin = 0x7fffffff;
             }
-            if (__any_sync(HTB_FULL, qptr > qbase + 128u * (QCAP - QGROUP))) flush1();
+            if (__any_sync(HTB_FULL, qptr > qbase + QFULL)) flush1(false);
         }
         qsave = qptr; csave = ctop;
     }
-    __device__ __forceinline__ void chunk(uint32_t stage, int lo, int hi, uint32_t tok, const double (&sh)[3])
+    __device__ __forceinline__ void chunk(uint32_t stage, int lo, int hi, uint32_t tok)
     {
         const uint32_t bx = stage, by = stage + 8 * HTB_CH, bz = stage + 16 * HTB_CH;
-        double xs[PPL], ys[PPL], zs[PPL];
-#pragma unroll
-        for (int q = 0; q < PPL; ++q) { xs[q] = x[q] - sh[0]; ys[q] = y[q] - sh[1]; zs[q] = z[q] - sh[2]; }
-        if (exact) { exact_range(stage, lo, hi, xs, ys, zs); return; }
+        if (exact) { exact_range(stage, lo, hi); return; }
         int j = lo;
         if ((j & 1) && j < hi) {
+            // odd leading entry: evaluated alone, checked together with the group that follows
             const double xj = lds_f64(bx + 8 * j), yj = lds_f64(by + 8 * j), zj = lds_f64(bz + 8 * j);
 #pragma unroll
-            for (int q = 0; q < PPL; ++q) pair_fast(xs[q], ys[q], zs[q], xj, yj, zj);
-            check(stage, j, j + 1, xs, ys, zs);
+            for (int q = 0; q < PPL; ++q) pair_fast(q, xj, yj, zj);
             ++j;
         }
+        int j0 = lo;
         if (j + GJ <= hi) {
             // register double buffering: the loads of the next two staged points are issued before the
             // queue stores of the current ones (the hardware keeps shared loads behind earlier stores)
@@ -398,6 +419,7 @@ struct Fast3T {
             lds_f64x2_tok(bx + 8 * j, tok, xa, xb);
             lds_f64x2_tok(by + 8 * j, tok, ya, yb);
             lds_f64x2_tok(bz + 8 * j, tok, za, zb);
+#pragma unroll 1
             for (; j + GJ <= hi; j += GJ) {
 #pragma unroll
                 for (int u = 0; u < GJ; u += 2) {
@@ -406,26 +428,27 @@ struct Fast3T {
                     lds_f64x2_tok(by + 8 * (j + u + 2), tok, yc, yd);
                     lds_f64x2_tok(bz + 8 * (j + u + 2), tok, zc, zd);
 #pragma unroll
-                    for (int q = 0; q < PPL; ++q) pair2(xs[q], ys[q], zs[q], xa, ya, za, xb, yb, zb);
+                    for (int q = 0; q < PPL; ++q) pair2(q, xa, ya, za, xb, yb, zb);
                     xa = xc; xb = xd; ya = yc; yb = yd; za = zc; zb = zd;
                 }
-                check(stage, j, j + GJ, xs, ys, zs);
+                check(stage, j0, j + GJ);
+                j0 = j + GJ;
             }
         }
-        if (j < hi) {
-            for (int jj = j; jj < hi; ++jj) {
-                const double xj = lds_f64(bx + 8 * jj), yj = lds_f64(by + 8 * jj), zj = lds_f64(bz + 8 * jj);
+        if (j0 < hi) {
+#pragma unroll 1
+            for (; j < hi; ++j) {
+                const double xj = lds_f64(bx + 8 * j), yj = lds_f64(by + 8 * j), zj = lds_f64(bz + 8 * j);
 #pragma unroll
-                for (int q = 0; q < PPL; ++q) pair_fast(xs[q], ys[q], zs[q], xj, yj, zj);
+                for (int q = 0; q < PPL; ++q) pair_fast(q, xj, yj, zj);
             }
-            check(stage, j, hi, xs, ys, zs);
+            check(stage, j0, hi);
         }
     }
     __device__ __forceinline__ bool tile_end(const WalkArrays &, const uint32_t (&)[PPL], int pass, unsigned wt)
     {
         if (!exact) {
-            flush1();
-            deep();
+            flush1(true);
             c[TOP] += ctop;
             ctop = csave = 0;
             if (__any_sync(HTB_FULL, dirty) && pass == 0) {
@@ -463,9 +486,15 @@ struct GenCount {
     uint32_t *hist;
     int lane;
     double x0, y0, z0, x1, y1, z1;
+    double xs0, ys0, zs0, xs1, ys1, zs1;
     bool v0, v1;
 
     static size_t scratch_bytes(const Params &p) { return sizeof(uint32_t) * (size_t)((p.nhist + 3) & ~3); }
+    __device__ __forceinline__ void set_shift(const double (&sh)[3], const WalkArrays &)
+    {
+        xs0 = x0 - sh[0]; ys0 = y0 - sh[1]; zs0 = z0 - sh[2];
+        xs1 = x1 - sh[0]; ys1 = y1 - sh[1]; zs1 = z1 - sh[2];
+    }
 
     __device__ GenCount(const Params &p, void *scratch, int ln, const WalkArrays &) : P(p), hist((uint32_t *)scratch), lane(ln)
     {
@@ -523,11 +552,9 @@ struct GenCount {
             }
         }
     }
-    __device__ __forceinline__ void chunk(uint32_t stage, int lo, int hi, uint32_t, const double (&sh)[3])
+    __device__ __forceinline__ void chunk(uint32_t stage, int lo, int hi, uint32_t)
     {
         const uint32_t bx = stage, by = stage + 8 * HTB_CH, bz = stage + 16 * HTB_CH;
-        const double xs0 = x0 - sh[0], ys0 = y0 - sh[1], zs0 = z0 - sh[2];
-        const double xs1 = x1 - sh[0], ys1 = y1 - sh[1], zs1 = z1 - sh[2];
         for (int j = lo; j < hi; ++j) {
             const double xj = lds_f64(bx + 8 * j), yj = lds_f64(by + 8 * j), zj = lds_f64(bz + 8 * j);
             pair(v0, xs0, ys0, zs0, xj, yj, zj);
@@ -591,10 +618,16 @@ struct Marked3 {
     double *hist;
     int lane;
     double x0, y0, z0, x1, y1, z1;
+    double xs0, ys0, zs0, xs1, ys1, zs1;
     double wa[HTB_MAX_NW], wb[HTB_MAX_NW];
     bool v0, v1;
 
     static size_t scratch_bytes(const Params &p) { return sizeof(double) * (size_t)((p.nhist + 1) & ~1); }
+    __device__ __forceinline__ void set_shift(const double (&sh)[3], const WalkArrays &)
+    {
+        xs0 = x0 - sh[0]; ys0 = y0 - sh[1]; zs0 = z0 - sh[2];
+        xs1 = x1 - sh[0]; ys1 = y1 - sh[1]; zs1 = z1 - sh[2];
+    }
 
     __device__ Marked3(const Params &p, void *scratch, int ln, const WalkArrays &) : P(p), hist((double *)scratch), lane(ln)
     {
@@ -632,11 +665,9 @@ struct Marked3 {
             if (lane == 0) hist[k] += s;
         }
     }
-    __device__ __forceinline__ void chunk(uint32_t stage, int lo, int hi, uint32_t, const double (&sh)[3])
+    __device__ __forceinline__ void chunk(uint32_t stage, int lo, int hi, uint32_t)
     {
         const uint32_t bx = stage, by = stage + 8 * HTB_CH, bz = stage + 16 * HTB_CH, bw = stage + 24 * HTB_CH;
-        const double xs0 = x0 - sh[0], ys0 = y0 - sh[1], zs0 = z0 - sh[2];
-        const double xs1 = x1 - sh[0], ys1 = y1 - sh[1], zs1 = z1 - sh[2];
         for (int j = lo; j < hi; ++j) {
             const double xj = lds_f64(bx + 8 * j), yj = lds_f64(by + 8 * j), zj = lds_f64(bz + 8 * j);
             pair(v0, wa, xs0, ys0, zs0, xj, yj, zj, bw + 8 * j * P.nw);
@@ -667,9 +698,14 @@ struct DSigma {
     double *acc;
     int lane;
     double x0, y0, x1, y1;
+    double xs0, ys0, xs1, ys1;
     bool v0, v1;
 
     static size_t scratch_bytes(const Params &p) { return sizeof(double) * 64 * (size_t)(2 * (p.n0 - 1) + 1); }
+    __device__ __forceinline__ void set_shift(const double (&sh)[3], const WalkArrays &)
+    {
+        xs0 = x0 - sh[0]; ys0 = y0 - sh[1]; xs1 = x1 - sh[0]; ys1 = y1 - sh[1];
+    }
 
     __device__ DSigma(const Params &p, void *scratch, int ln, const WalkArrays &) : P(p), acc((double *)scratch), lane(ln) {}
     __device__ __forceinline__ void tile_begin(const double (&p)[2][3], const bool (&val)[2], const uint32_t (&)[2],
@@ -693,11 +729,9 @@ struct DSigma {
             if (k >= 0) acc[(nbin + 1 + k) * 64 + col] += mj * (1 - log(P.e0[k + 1] / dxy_sq));
         }
     }
-    __device__ __forceinline__ void chunk(uint32_t stage, int lo, int hi, uint32_t, const double (&sh)[3])
+    __device__ __forceinline__ void chunk(uint32_t stage, int lo, int hi, uint32_t)
     {
         const uint32_t bx = stage, by = stage + 8 * HTB_CH, bm = stage + 16 * HTB_CH;
-        const double xs0 = x0 - sh[0], ys0 = y0 - sh[1];
-        const double xs1 = x1 - sh[0], ys1 = y1 - sh[1];
         for (int j = lo; j < hi; ++j) {
             const double xj = lds_f64(bx + 8 * j), yj = lds_f64(by + 8 * j), mj = lds_f64(bm + 8 * j);
             pair(v0, lane, xs0, ys0, xj, yj, mj);
@@ -745,8 +779,13 @@ struct DSigmaU {
     unsigned *cnt;
     int lane, nbin;
     double x0, y0, x1, y1;
+    double xs0, ys0, xs1, ys1;
     bool v0, v1;
     int since;
+    __device__ __forceinline__ void set_shift(const double (&sh)[3], const WalkArrays &)
+    {
+        xs0 = x0 - sh[0]; ys0 = y0 - sh[1]; xs1 = x1 - sh[0]; ys1 = y1 - sh[1];
+    }
 
     static size_t scratch_bytes(const Params &p)
     {
@@ -799,11 +838,9 @@ struct DSigmaU {
             pm[b * 64 + col] = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(v));
         }
     }
-    __device__ __forceinline__ void chunk(uint32_t stage, int lo, int hi, uint32_t, const double (&sh)[3])
+    __device__ __forceinline__ void chunk(uint32_t stage, int lo, int hi, uint32_t)
     {
         const uint32_t bx = stage, by = stage + 8 * HTB_CH;
-        const double xs0 = x0 - sh[0], ys0 = y0 - sh[1];
-        const double xs1 = x1 - sh[0], ys1 = y1 - sh[1];
         // every multiply grows a product by < 2: renormalise before 2^1023 can be reached
         if (since + (hi - lo) > 900) { renorm(lane); renorm(32 + lane); since = 0; }
         since += hi - lo;

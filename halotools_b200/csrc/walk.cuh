@@ -127,18 +127,23 @@ __device__ __forceinline__ double warp_max(double v)
 }
 __device__ __forceinline__ int floor_div(int a, int b) { int q = a / b; return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q; }
 
-// Per-warp shared-memory context
+// Per-warp shared-memory context: HTB_NSTAGE stage buffers (DIM coordinate rows of HTB_CH doubles + payload rows of
+// HTB_CH * NPAY doubles), one mbarrier per stage, the span list.  Plain scalars only (no arrays indexed at run time,
+// which would live in local memory).
 template <int DIM, int NPAY>
 struct WarpSmem {
-    // stage buffers: DIM coordinate rows of HTB_CH doubles + payload rows (HTB_CH * NPAY doubles)
-    double *stage[HTB_NSTAGE];      // base of each stage
-    uint32_t bar[HTB_NSTAGE];       // shared-space addresses of the mbarriers
+    double *stage0;                 // generic pointer to stage 0
+    uint32_t stage0_s;              // its shared-space address
+    uint32_t bar0;                  // shared-space address of mbarrier 0 (16 bytes apart)
     uint32_t *span;                 // HTB_SPAN_CAP * 3 u32: {jb, je, code}
     static __host__ __device__ constexpr int stage_doubles() { return HTB_CH * (DIM + NPAY); }
     static __host__ __device__ constexpr size_t bytes()
     {
         return sizeof(double) * HTB_NSTAGE * stage_doubles() + 16 * HTB_NSTAGE + sizeof(uint32_t) * 3 * HTB_SPAN_CAP;
     }
+    __device__ __forceinline__ double *stage(int s) const { return stage0 + s * stage_doubles(); }
+    __device__ __forceinline__ uint32_t stage_s(int s) const { return stage0_s + (uint32_t)(s * stage_doubles() * 8); }
+    __device__ __forceinline__ uint32_t bar(int s) const { return bar0 + 16u * (uint32_t)s; }
 };
 
 struct TileInfo {
@@ -149,9 +154,11 @@ struct TileInfo {
 
 // The walker.  V must provide:
 //   static constexpr int DIM, NPAY, PPL; static constexpr bool TMA;
-//   __device__ void chunk(uint32_t stage_smem_addr, int lo, int hi, uint32_t tok, const double (&sh)[3]) — evaluate
-//        pairs between the lane's PPL points (shifted by sh) and staged sample2 entries [lo, hi); tok is a value
-//        that depends on the stage's mbarrier wait (an input for loads that may be scheduled freely).
+//   __device__ void set_shift(const double (&sh)[3], const WalkArrays &A) — the periodic shift of the following chunks
+//        (the variant keeps its points' shifted coordinates, x1 - shift first as in npairs_3d_engine.pyx:167)
+//   __device__ void chunk(uint32_t stage_smem_addr, int lo, int hi, uint32_t tok) — evaluate pairs between the lane's
+//        PPL points and staged sample2 entries [lo, hi); tok is a value that depends on the stage's mbarrier wait
+//        (an input for loads that may be scheduled freely).
 template <class V>
 __device__ __forceinline__ void walk_tile(V &v, const WalkGeom &G, const WalkArrays &A,
                                           WarpSmem<V::DIM, V::NPAY> &S, uint32_t &gchunk,
@@ -180,6 +187,7 @@ __device__ __forceinline__ void walk_tile(V &v, const WalkGeom &G, const WalkArr
 
     int nspan = 0;
 
+    uint32_t cur_code = 0xffffffffu;          // shift code the variant currently holds (none yet for this tile pass)
     auto consume = [&]() {
         // ---- stream the span list through the staging ring
         int si = 0, sc = 0;                    // issue / compute span cursors
@@ -191,19 +199,20 @@ __device__ __forceinline__ void walk_tile(V &v, const WalkGeom &G, const WalkArr
                 const uint32_t je = S.span[3 * si + 1];
                 const uint32_t jend = (je + 1u) & ~1u;
                 const uint32_t cnt = min((uint32_t)HTB_CH, jend - ji);
-                const int stg = (gchunk + inflight) % HTB_NSTAGE;
-                double *dst = S.stage[stg];
+                const int stg = (int)((gchunk + (uint32_t)inflight) % HTB_NSTAGE);
                 if (V::TMA) {
                     if (lane == 0) {
+                        const uint32_t dst = S.stage_s(stg), bar = S.bar(stg);
                         const uint32_t bytes = cnt * 8u * (DIM + A.nw * (V::NPAY > 0 ? 1 : 0));
-                        mbar_expect_tx(S.bar[stg], bytes);
+                        mbar_expect_tx(bar, bytes);
 #pragma unroll
                         for (int d = 0; d < DIM; ++d)
-                            tma_bulk_g2s(smem_u32(dst + d * HTB_CH), A.c2[d] + ji, cnt * 8u, S.bar[stg]);
+                            tma_bulk_g2s(dst + (uint32_t)(d * HTB_CH * 8), A.c2[d] + ji, cnt * 8u, bar);
                         if (V::NPAY > 0)
-                            tma_bulk_g2s(smem_u32(dst + DIM * HTB_CH), A.pay2 + (size_t)ji * A.nw, cnt * 8u * A.nw, S.bar[stg]);
+                            tma_bulk_g2s(dst + (uint32_t)(DIM * HTB_CH * 8), A.pay2 + (size_t)ji * A.nw, cnt * 8u * A.nw, bar);
                     }
                 } else {
+                    double *dst = S.stage(stg);
                     for (uint32_t q = lane; q < cnt; q += 32) {
 #pragma unroll
                         for (int d = 0; d < DIM; ++d) dst[d * HTB_CH + q] = A.c2[d][ji + q];
@@ -217,19 +226,23 @@ __device__ __forceinline__ void walk_tile(V &v, const WalkGeom &G, const WalkArr
             }
             // ---- current chunk
             const uint32_t jb = S.span[3 * sc], je = S.span[3 * sc + 1], code = S.span[3 * sc + 2];
-            const int stg = gchunk % HTB_NSTAGE;
+            const int stg = (int)(gchunk % HTB_NSTAGE);
+            if (code != cur_code) {
+                double sh[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+                for (int d = 0; d < DIM; ++d) {
+                    const int k = (int)((code >> (2 * d)) & 3u) - 1;
+                    sh[d] = (double)(k * G.pbc) * G.period[d];
+                }
+                v.set_shift(sh, A);
+                cur_code = code;
+            }
             uint32_t tok = jc;
-            if (V::TMA) tok += mbar_wait(S.bar[stg], (gchunk / HTB_NSTAGE) & 1u);
+            if (V::TMA) tok += mbar_wait(S.bar(stg), (gchunk / HTB_NSTAGE) & 1u);
             else __syncwarp();
             const int lo = (int)(max(jb, jc) - jc);
             const int hi = (int)(min(je, jc + HTB_CH) - jc);
-            double sh[3];
-#pragma unroll
-            for (int d = 0; d < DIM; ++d) {
-                const int k = (int)((code >> (2 * d)) & 3u) - 1;
-                sh[d] = (double)(k * G.pbc) * G.period[d];
-            }
-            v.chunk(smem_u32(S.stage[stg]), lo, hi, tok, sh);
+            v.chunk(S.stage_s(stg), lo, hi, tok);
             pairs += (unsigned long long)(hi - lo) * (unsigned)tile_cnt;
             __syncwarp();
             ++gchunk;
