@@ -241,7 +241,7 @@ def run_gpu(args):
         return ms / steps, res
 
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("HTB_BENCH_NO_SAMPLER"):
         sampler.start()
     ms_step, xi_res = timed(step_resident, args.steps, args.warmup)
     acc = dict(stats_acc)

@@ -46,20 +46,24 @@ extern "C" int htb_set_stream(void *s)
     return 0;
 }
 
+static bool g_pool_ready[64] = {false};
+
 static int get_stream(cudaStream_t *out)
 {
-    if (g_have_user_stream) { *out = g_user_stream; return 0; }
     int dev = 0;
     HTB_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) { htb_set_error("device index %d out of range", dev); return 1; }
-    if (!g_lib_stream[dev]) {
-        HTB_CUDA(cudaStreamCreateWithFlags(&g_lib_stream[dev], cudaStreamNonBlocking));
-        // keep freed blocks cached in the stream-ordered pool between calls
+    if (!g_pool_ready[dev]) {
+        // keep freed blocks cached in the stream-ordered pool between calls (the default is to hand them
+        // back to the driver at every synchronisation, which costs far more than the kernels)
         cudaMemPool_t pool;
         HTB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
         uint64_t thresh = UINT64_MAX;
         HTB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+        g_pool_ready[dev] = true;
     }
+    if (g_have_user_stream) { *out = g_user_stream; return 0; }
+    if (!g_lib_stream[dev]) HTB_CUDA(cudaStreamCreateWithFlags(&g_lib_stream[dev], cudaStreamNonBlocking));
     *out = g_lib_stream[dev];
     return 0;
 }

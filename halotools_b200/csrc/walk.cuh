@@ -17,8 +17,12 @@
 #include "htb_internal.cuh"
 
 #define HTB_WARPS 8                 // warps per block of the counting kernels (overridable per variant)
+#ifndef HTB_CH
 #define HTB_CH 64                   // sample2 points per staged chunk
+#endif
+#ifndef HTB_NSTAGE
 #define HTB_NSTAGE 2
+#endif
 #ifndef HTB_SPAN_CAP
 #define HTB_SPAN_CAP 96
 #endif
