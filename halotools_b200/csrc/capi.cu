@@ -302,6 +302,20 @@ struct Call {
         G.sym = sym ? 1 : 0;
         G.tile = tile;
         G.sentinel = sentinel;
+        {
+            // a tile may straddle K reference cells along the fast dimension if the union of their windows
+            // (K * per + 2 * cover mesh2 cells) cannot reach the same mesh2 cell twice
+            const int Fd = dim - 1;
+            const int per = g->ndivs2[Fd] / g->ndivs1[Fd];
+            int K = (g->ndivs2[Fd] - 2 * g->cover[Fd]) / per;
+            if (K > g->ndivs1[Fd]) K = g->ndivs1[Fd];
+            // HTB_FLAG_NO_CULL promises exactly the reference's cell windows: no union windows then
+            if (K < 1 || (fl & HTB_FLAG_NO_CULL) || getenv("HTB_NO_STRADDLE")) K = 1;
+            G.maxspan = K;
+            G.maxfine = m1[Fd];           // a tile is never longer than one reference cell
+            if (const char *e = getenv("HTB_MAXFINE")) { const int v = atoi(e); if (v >= 1) G.maxfine = v; }
+            G.cs1f = g->cell1_size[Fd];
+        }
         // ---- walker geometry
         G.dim = dim;
         G.pbc = g->pbc ? 1 : 0;

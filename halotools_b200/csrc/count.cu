@@ -14,43 +14,57 @@
 #include "count.cuh"
 
 // ------------------------------------------------------------------ tile list
-__global__ void k_seg_tiles(const uint32_t *__restrict__ off1, WalkGeom G, int64_t nseg,
-                            int64_t first_cell1, int64_t last_cell1, uint32_t *__restrict__ ntile)
+// One thread per fine COLUMN of sample1 (fixed slow-dimension fine indices; a contiguous run of the sorted arrays):
+// the part of the column that lies in reference cells [first_cell1, last_cell1) is cut greedily into tiles of up to
+// G.tile consecutive points that straddle at most G.maxspan reference cells and cover at most G.maxfine fine cells
+// along the fast dimension.
+// Tile descriptor: {first sorted index, column | (points << 24)}.
+__device__ __forceinline__ uint32_t htb_column_tiles(const uint32_t *__restrict__ off1, const WalkGeom &G, int64_t col,
+                                                     int64_t first_cell1, int64_t last_cell1, uint2 *out, uint32_t base)
 {
     const int F = G.dim - 1;
-    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < nseg; s += (int64_t)gridDim.x * blockDim.x) {
-        // seg = slowlin * nd1[F] + a_fast
-        const int af = (int)(s % G.nd1[F]);
-        int64_t slow = s / G.nd1[F];
-        int fsl[2] = {0, 0};
-        for (int d = F - 1; d >= 0; --d) { fsl[d] = (int)(slow % G.nf1[d]); slow /= G.nf1[d]; }
-        int64_t rid = 0;
-        for (int d = 0; d < F; ++d) rid = rid * G.nd1[d] + fsl[d] / G.m1[d];
-        rid = rid * G.nd1[F] + af;
-        uint32_t nt = 0;
-        if (rid >= first_cell1 && rid < last_cell1) {
-            const int64_t c0 = (s / G.nd1[F]) * G.nf1[F] + (int64_t)af * G.m1[F];
-            const uint32_t cnt = off1[c0 + G.m1[F]] - off1[c0];
-            nt = (cnt + (uint32_t)G.tile - 1) / (uint32_t)G.tile;
-        }
-        ntile[s] = nt;
+    int64_t rem = col, rid = 0, mul = 1;
+    // reference cell id of (slow dims of this column, fast index 0): last dimension fastest
+    int fsl[2] = {0, 0};
+    for (int d = F - 1; d >= 0; --d) { fsl[d] = (int)(rem % G.nf1[d]); rem /= G.nf1[d]; }
+    for (int d = 0; d < F; ++d) rid = rid * G.nd1[d] + fsl[d] / G.m1[d];
+    (void)mul;
+    rid *= G.nd1[F];
+    int64_t zlo64 = first_cell1 - rid, zhi64 = last_cell1 - rid;
+    const int zlo = (int)(zlo64 < 0 ? 0 : (zlo64 > G.nd1[F] ? G.nd1[F] : zlo64));
+    const int zhi = (int)(zhi64 < 0 ? 0 : (zhi64 > G.nd1[F] ? G.nd1[F] : zhi64));
+    if (zlo >= zhi) return 0;
+    const uint32_t *o = off1 + col * G.nf1[F];
+    const int mf = G.m1[F];
+    uint32_t pos = o[zlo * mf];
+    const uint32_t end = o[zhi * mf];
+    uint32_t n = 0;
+    int f = zlo * mf;
+    while (pos < end) {
+        while (o[f + 1] <= pos) ++f;                          // fine cell (fast dim) of the tile's first point
+        const int lim = min(min(zhi, f / mf + G.maxspan) * mf, f + G.maxfine);
+        const uint32_t e = min(pos + (uint32_t)G.tile, o[lim]);
+        if (out) out[base + n] = make_uint2(pos, (uint32_t)col | ((e - pos) << 24));
+        ++n;
+        pos = e;
     }
+    return n;
 }
 
-__global__ void k_fill_tiles(const uint32_t *__restrict__ off1, WalkGeom G, int64_t nseg,
+__global__ void k_seg_tiles(const uint32_t *__restrict__ off1, WalkGeom G, int64_t ncol,
+                            int64_t first_cell1, int64_t last_cell1, uint32_t *__restrict__ ntile)
+{
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < ncol; s += (int64_t)gridDim.x * blockDim.x)
+        ntile[s] = htb_column_tiles(off1, G, s, first_cell1, last_cell1, nullptr, 0u);
+}
+
+__global__ void k_fill_tiles(const uint32_t *__restrict__ off1, WalkGeom G, int64_t ncol,
+                             int64_t first_cell1, int64_t last_cell1,
                              const uint32_t *__restrict__ ntile, const uint32_t *__restrict__ tbase,
                              uint2 *__restrict__ tiles)
 {
-    const int F = G.dim - 1;
-    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < nseg; s += (int64_t)gridDim.x * blockDim.x) {
-        const uint32_t nt = ntile[s];
-        if (!nt) continue;
-        const int af = (int)(s % G.nd1[F]);
-        const int64_t c0 = (s / G.nd1[F]) * G.nf1[F] + (int64_t)af * G.m1[F];
-        const uint32_t st = off1[c0];
-        const uint32_t b = tbase[s];
-        for (uint32_t t = 0; t < nt; ++t) tiles[b + t] = make_uint2(st + t * (uint32_t)G.tile, (uint32_t)s);
-    }
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < ncol; s += (int64_t)gridDim.x * blockDim.x)
+        if (ntile[s]) (void)htb_column_tiles(off1, G, s, first_cell1, last_cell1, tiles, tbase[s]);
 }
 
 // pairs the reference loop nest visits, per reference cell1 (W_ref)
@@ -125,23 +139,22 @@ k_count(const __grid_constant__ WalkGeom G, const __grid_constant__ WalkArrays A
         if (t >= ntiles) break;
         const uint2 td = A.tiles[t];
         const uint32_t start = td.x;
-        const int64_t seg = td.y;
+        const int cnt = (int)(td.y >> 24);
+        int64_t slow = (int64_t)(td.y & 0xffffffu);
         int fs[3] = {0, 0, 0};
-        fs[F] = (int)(seg % G.nd1[F]);
-        int64_t slow = seg / G.nd1[F];
-        const int64_t c0 = slow * G.nf1[F] + (int64_t)fs[F] * G.m1[F];
 #pragma unroll
         for (int d = F - 1; d >= 0; --d) { fs[d] = (int)(slow % G.nf1[d]); slow /= G.nf1[d]; }
-        const uint32_t segend = A.off1[c0 + G.m1[F]];
-        const int cnt = (int)min((uint32_t)(32 * PPL), segend - start);
         // this lane's points (index clamped for the bounding box; unused lanes get a far sentinel)
         bool val[PPL];
         uint32_t idx[PPL];
         double p[PPL][3], blo[3] = {0, 0, 0}, bhi[3] = {0, 0, 0};
 #pragma unroll
         for (int q = 0; q < PPL; ++q) {
-            val[q] = lane + 32 * q < cnt;
-            idx[q] = start + (uint32_t)min(lane + 32 * q, cnt - 1);
+            // odd point slots run backwards, so a lane holds points from both ends of the tile (sorted along the
+            // fast dimension): its share of in-range pairs, hence its queue length, follows the warp average
+            const int slot = (q & 1) ? 32 * q + 31 - lane : 32 * q + lane;
+            val[q] = slot < cnt;
+            idx[q] = start + (uint32_t)min(slot, cnt - 1);
             p[q][0] = p[q][1] = p[q][2] = 0.0;
         }
 #pragma unroll
@@ -158,13 +171,16 @@ k_count(const __grid_constant__ WalkGeom G, const __grid_constant__ WalkArrays A
         }
 #pragma unroll
         for (int q = 0; q < PPL; ++q) if (!val[q]) p[q][0] = G.sentinel;
+        // reference cells (fast dimension) of the tile's first and last point: the digitisation of the mesh sort
+        fs[F] = htb_ref_digitize(__shfl_sync(HTB_FULL, p[0][F], 0), G.cs1f, G.nd1[F]);
+        const int nref = htb_ref_digitize(__shfl_sync(HTB_FULL, p[PPL - 1][F], (PPL & 1) ? 31 : 0), G.cs1f, G.nd1[F]) - fs[F] + 1;
         const int nsub = G.sym ? 2 : 1;
 #pragma unroll 1
         for (int sub = 0; sub < nsub; ++sub) {
             v.tile_begin(p, val, idx, A);
 #pragma unroll 1
             for (int pass = 0; pass < 2; ++pass) {
-                walk_tile<V>(v, G, A, S, gchunk, blo, bhi, fs, pairs, cnt, G.sym ? sub + 1 : 0, start, start + (uint32_t)cnt);
+                walk_tile<V>(v, G, A, S, gchunk, blo, bhi, fs, nref, pairs, cnt, G.sym ? sub + 1 : 0, start, start + (uint32_t)cnt);
                 const bool redo = v.tile_end(A, idx, pass, sub == 1 ? 2u : 1u);
                 if (!redo) break;
                 ++redone;
@@ -928,21 +944,23 @@ int htb_build_tiles(cudaStream_t st, Workspace &ws, const WalkGeom &G, const Sor
                     int64_t *max_tiles_out, int *launches)
 {
     const int F = G.dim - 1;
-    int64_t nseg = G.nd1[F];
+    int64_t nseg = 1;                                   // fine columns of sample1
     for (int d = 0; d < F; ++d) nseg *= G.nf1[d];
+    if (nseg >= (1 << 24)) { htb_set_error("too many fine columns in the sample1 mesh (%lld)", (long long)nseg); return 1; }
     uint32_t *ntile = nullptr, *tbase = nullptr, *total = nullptr;
     if (ws.alloc((void **)&ntile, sizeof(uint32_t) * (size_t)(nseg + 1))) return 1;
     if (ws.alloc((void **)&tbase, sizeof(uint32_t) * (size_t)(nseg + 1))) return 1;
     if (ws.alloc((void **)&total, sizeof(uint32_t) * 4)) return 1;
-    const int64_t max_tiles = s1.n / G.tile + nseg + 1;
+    // every tile is either full or ends at a reference-cell boundary of its column
+    const int64_t max_tiles = s1.n / G.tile + nseg * G.nd1[F] + 1;
     uint2 *tiles = nullptr;
     if (ws.alloc((void **)&tiles, sizeof(uint2) * (size_t)max_tiles)) return 1;
-    int blocks = (int)((nseg + 255) / 256);
+    int blocks = (int)((nseg + 127) / 128);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    k_seg_tiles<<<blocks, 256, 0, st>>>(s1.off, G, nseg, first_cell1, last_cell1, ntile);
+    k_seg_tiles<<<blocks, 128, 0, st>>>(s1.off, G, nseg, first_cell1, last_cell1, ntile);
     if (launches) *launches += 1;
     if (htb_exclusive_scan_u32(st, ws, ntile, tbase, nseg, total, launches)) return 1;
-    k_fill_tiles<<<blocks, 256, 0, st>>>(s1.off, G, nseg, ntile, tbase, tiles);
+    k_fill_tiles<<<blocks, 128, 0, st>>>(s1.off, G, nseg, first_cell1, last_cell1, ntile, tbase, tiles);
     if (launches) *launches += 1;
     HTB_CUDA(cudaGetLastError());
     *tiles_out = tiles;

@@ -39,7 +39,10 @@ struct WalkGeom {
     double period[3], h2[3], slop[3], reach[3];
     double r2slow;                  // (max separation over the slow dims)^2, with safety margin
     double sentinel;                // x coordinate given to the unused lanes of a partial tile (never in range)
+    double cs1f;                    // reference mesh1 cell size along the fast dimension (as handed to the mesh sort)
     int tile;                       // sample1 points per tile (32 * points per lane of the kernel variant)
+    int maxspan;                    // reference mesh1 cells along the fast dimension one tile may straddle (>= 1)
+    int maxfine;                    // fine mesh1 cells along the fast dimension one tile may cover (bounds its extent)
 };
 
 struct WalkArrays {
@@ -167,7 +170,8 @@ template <class V>
 __device__ __forceinline__ void walk_tile(V &v, const WalkGeom &G, const WalkArrays &A,
                                           WarpSmem<V::DIM, V::NPAY> &S, uint32_t &gchunk,
                                           const double (&blo)[3], const double (&bhi)[3],
-                                          const int (&fs)[3] /* tile's fine/ref indices: slow dims fine idx, fast dim ref cell */,
+                                          const int (&fs)[3] /* tile's fine/ref indices: slow dims fine idx, fast dim FIRST ref cell */,
+                                          const int nref /* reference cells along the fast dimension the tile straddles */,
                                           unsigned long long &pairs, int tile_cnt,
                                           int wt_pass /* 0: every span; 1: symmetric mode, weight-1 spans; 2: weight-2 spans */,
                                           uint32_t ts, uint32_t te /* the tile's own sorted index range */)
@@ -183,7 +187,11 @@ __device__ __forceinline__ void walk_tile(V &v, const WalkGeom &G, const WalkArr
     for (int d = 0; d < DIM; ++d) {
         a[d] = (d == F) ? fs[d] : fs[d] / G.m1[d];
         wlo[d] = (a[d] * G.per[d] - G.cover[d]) * G.m2[d];
-        wn[d] = (G.per[d] + 2 * G.cover[d]) * G.m2[d];
+        // A tile that straddles nref reference cells along the fast dimension walks the union of their windows:
+        // every cell of the union keeps the shift of its own unwrapped index, the cells a point would not have
+        // visited in the reference are farther than the search length from it (cover cells away), and the host
+        // only allows nref > 1 when the union cannot reach the same cell twice (maxspan).
+        wn[d] = (G.per[d] * (d == F ? nref : 1) + 2 * G.cover[d]) * G.m2[d];
     }
     const int ncol = (DIM == 3) ? wn[0] * wn[1] : wn[0];
     const int kfmin = floor_div(wlo[F], G.nf2[F]);
