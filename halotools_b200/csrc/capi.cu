@@ -627,8 +627,36 @@ extern "C" int htb_mean_delta_sigma_engine(const htb_mesh_geom *mesh,
         if (flags & HTB_FLAG_DEVICE_INPUT) HTB_CUDA(cudaMemcpy(&mass, m2, sizeof(double), cudaMemcpyDeviceToHost));
         else mass = m2[0];
     }
+    // fast path (DSigmaQ): uniform mass, <= HTB_NBF monotone edges whose 32-bit relative keys cannot wrap
+    // (same window argument as htb_npairs_3d_engine)
+    std::vector<double> rsq((size_t)nrp);
+    for (int k = 0; k < nrp; ++k) rsq[k] = rp_bins[k] * rp_bins[k];
+    bool fast = uniform && !(flags & HTB_FLAG_GENERIC) && nrp <= HTB_NBF && finite_all(rp_bins, nrp) && std::isfinite(mass);
+    for (int k = 0; k + 1 < nrp && fast; ++k) fast = rp_bins[k] >= 0.0 && rsq[k] <= rsq[k + 1];
+    if (fast) fast = rsq[nrp - 1] > 1e-290 && rsq[nrp - 1] < 1e290;
+    double lmax = mesh->period[0] > mesh->period[1] ? mesh->period[0] : mesh->period[1];
+    if (fast) fast = std::isfinite(lmax) && lmax > 0.0 && lmax < 1e140;
+    DSQParams qp{};
+    if (fast) {
+        const long long Kt = (long long)(dbits(rsq[nrp - 1]) >> 26);
+        const long long Kmax = (long long)(dbits(256.0 * lmax * lmax) >> 26);
+        const long long lim = 31LL << 26;
+        if (Kmax - Kt >= lim) fast = false;
+        qp.nrp = nrp;
+        qp.nbias = (int)(unsigned)(0ULL - (unsigned long long)Kt);
+        qp.Hwin = (int)(dbits(rsq[nrp - 1]) >> 32) - (31 << 20);
+        const int pad = HTB_NBF - nrp;
+        for (int s = 0; s < HTB_NBF; ++s) qp.E[s] = s < pad ? 0ULL : dbits(rsq[s - pad]);
+        // lower edge of the top annulus; an edge below the key window (or zero) makes every in-range pair
+        // take the queue (Tspan = 0 keeps the in-register top annulus off only when F1 == 0)
+        long long d = (long long)(dbits(rsq[nrp - 2]) >> 26) - Kt;
+        if (rsq[nrp - 2] == 0.0 || d <= -lim) d = -lim + 1;
+        qp.F1 = (int)d;
+        qp.Tspan = d < 0 ? (unsigned)(-d - 1) : 0u;
+        qp.mass = mass;
+    }
     if (c.setup(mesh, 1, false, c1, stride1, n1, nullptr, c2, stride2, n2, uniform ? nullptr : m2, uniform ? 0 : 1, true,
-                first_cell1, last_cell1, flags)) return 1;
+                first_cell1, last_cell1, flags, fast ? 32 : HTB_TILE, fast ? 8.0 * lmax : 1.0e150)) return 1;
     const int nbin = nrp - 1;
     std::vector<double> e((size_t)nrp + nbin);
     for (int k = 0; k < nrp; ++k) e[k] = rp_bins[k] * rp_bins[k];
@@ -639,15 +667,22 @@ extern "C" int htb_mean_delta_sigma_engine(const htb_mesh_geom *mesh,
     const size_t nout = (size_t)(n1 > 0 ? n1 : 1) * nbin;
     if (c.ws.alloc((void **)&out_dev, sizeof(double) * nout)) return 1;
     HTB_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(double) * nout, c.st));
-    GenParams gp{};
-    gp.n0 = nrp; gp.n1 = nbin; gp.nhist = 0; gp.nw = 1;
-    gp.e0 = (const double *)edev; gp.e1 = (const double *)edev + nrp;
-    gp.fcounts = out_dev;
-    gp.perm1 = c.s1.perm;
-    gp.max0 = mass;
-    if (htb_launch_gen(c.st, uniform ? 5 : 4, c.G, c.A, gp, &c.launches)) return 1;
+    if (fast) {
+        qp.e0 = (const double *)edev; qp.e1 = (const double *)edev + nrp;
+        qp.out = out_dev;
+        qp.perm1 = c.s1.perm;
+        if (htb_launch_dsq(c.st, c.G, c.A, qp, &c.launches)) return 1;
+    } else {
+        GenParams gp{};
+        gp.n0 = nrp; gp.n1 = nbin; gp.nhist = 0; gp.nw = 1;
+        gp.e0 = (const double *)edev; gp.e1 = (const double *)edev + nrp;
+        gp.fcounts = out_dev;
+        gp.perm1 = c.s1.perm;
+        gp.max0 = mass;
+        if (htb_launch_gen(c.st, uniform ? 5 : 4, c.G, c.A, gp, &c.launches)) return 1;
+    }
     if (n1 > 0) HTB_CUDA(cudaMemcpyAsync(out, out_dev, sizeof(double) * (size_t)n1 * nbin, cudaMemcpyDeviceToHost, c.st));
-    return c.finish(stats, 0);
+    return c.finish(stats, fast ? 1 : 0);
     HTB_GUARD_END
 }
 

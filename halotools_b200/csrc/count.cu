@@ -898,6 +898,294 @@ struct DSigmaU {
     __device__ __forceinline__ void kernel_end() {}
 };
 
+// ------------------------------------------------------------------ DSigmaQ (uniform particle mass, fast path)
+// mean_delta_sigma_engine.pyx:162-180 for one particle mass m.  Per galaxy and annulus the engine needs the number of
+// particles n and sum ln d^2 (see DSigmaU); here every lane owns ONE galaxy and
+//   * a pair certainly inside the TOP annulus (F1 < key < 0, the same 32-bit relative keys as Fast3) is folded
+//     immediately into register accumulators: mantissa product (one predicated DMUL), exponent sum, count;
+//   * every other pair that may be in range (key <= F1) pushes its full 64-bit d^2 to the lane's queue; the queue
+//     is drained at full lane occupancy by a top-down compaction cascade with exact 64-bit compares, each pass
+//     folding the keys of one annulus into that annulus' accumulators (mantissa products in registers, exponent
+//     sums and counts in shared memory);
+//   * a key equal to the top-edge key, or a separation too small for the 32-bit key, rolls the group back and
+//     pushes the group's in-range pairs after exact compares (the cascade decides everything exactly).
+// Integer decisions are therefore exact; the float sums differ from the reference by summation order only.
+#ifndef DSQ_QCAP
+#define DSQ_QCAP 44           // queue slots (64-bit) per lane
+#endif
+#ifndef DSQ_QSURV
+#define DSQ_QSURV 10          // run the deep cascade when a lane holds more survivors than this
+#endif
+#ifndef DSQ_WARPS
+#define DSQ_WARPS 4
+#define DSQ_MINBLOCKS 3
+#endif
+#ifndef DSQ_GROUP
+#define DSQ_GROUP 16          // pairs per lane between two queue checks
+#endif
+
+__device__ __forceinline__ void sts_u64_nc(uint32_t addr, unsigned long long v)
+{
+    asm volatile("st.shared.u64 [%0], %1;" ::"r"(addr), "l"(v));
+}
+__device__ __forceinline__ unsigned long long lds_u64(uint32_t addr)
+{
+    unsigned long long v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr));
+    return v;
+}
+
+struct DSigmaQ {
+    static constexpr int DIM = 2, NPAY = 0, PPL = 1, WARPS = DSQ_WARPS, MINBLOCKS = DSQ_MINBLOCKS;
+    static constexpr bool TMA = true;
+    static constexpr int TOP = HTB_NBF - 1;
+    static constexpr uint32_t QFULL = 256u * (DSQ_QCAP - DSQ_GROUP - 1);
+    typedef DSQParams Params;
+    const Params &P;
+    int lane, pad;
+    uint32_t qbase, qs, qptr, qsave;
+    int *ex;                    // [HTB_NBF][32] exponent sums (unbiased) per annulus slot
+    unsigned *nn;               // [HTB_NBF][32] counts per slot (slot pad = inside rp[0])
+    double M[HTB_NBF];          // mantissa products per slot, kept in [1, 2)
+    double x, y, xs, ys;
+    double Mtop, Msave;         // top annulus: running mantissa product since the last fold
+    int Etop, Esave;            // ... sum of raw exponent fields
+    unsigned Ntop, Nsave;       // ... count
+    unsigned umin;
+    int hmin;
+    int groups;
+    bool valid, always_exact;
+
+    static size_t scratch_bytes(const Params &) { return 8 * 32 * DSQ_QCAP + 2 * 4 * 32 * HTB_NBF; }
+
+    __device__ __forceinline__ DSigmaQ(const Params &p, void *scratch, int ln, const WalkArrays &A) : P(p), lane(ln)
+    {
+        pad = HTB_NBF - P.nrp;
+        qbase = smem_u32(scratch) + 8u * (uint32_t)ln;
+        qs = qptr = qsave = qbase;
+        ex = (int *)((unsigned char *)scratch + 8 * 32 * DSQ_QCAP) + ln;
+        nn = (unsigned *)((unsigned char *)scratch + 8 * 32 * DSQ_QCAP + 4 * 32 * HTB_NBF) + ln;
+        x = y = xs = ys = 0.0;
+        Mtop = Msave = 1.0; Etop = Esave = 0; Ntop = Nsave = 0;
+        umin = 0xffffffffu; hmin = 0x7fffffff; groups = 0; valid = false;
+        always_exact = ((A.flags1[0] | A.flags2[0]) & 1u) != 0u;
+#pragma unroll
+        for (int s = 0; s < HTB_NBF; ++s) M[s] = 1.0;
+    }
+    __device__ __forceinline__ void tile_begin(const double (&p)[1][3], const bool (&val)[1], const uint32_t (&)[1],
+                                               const WalkArrays &)
+    {
+        x = p[0][0]; y = p[0][1]; valid = val[0];
+#pragma unroll
+        for (int s = 0; s < HTB_NBF; ++s) { M[s] = 1.0; ex[32 * s] = 0; nn[32 * s] = 0u; }
+        Mtop = Msave = 1.0; Etop = Esave = 0; Ntop = Nsave = 0;
+        groups = 0;
+    }
+    __device__ __forceinline__ void set_shift(const double (&sh)[3], const WalkArrays &)
+    {
+        xs = x - sh[0]; ys = y - sh[1];
+    }
+    static __device__ __forceinline__ double mant_of(unsigned long long b)
+    {
+        return __longlong_as_double((long long)((b & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL));
+    }
+    // fold the running top-annulus product into slot TOP (keeps every product in [1, 2): no overflow)
+    __device__ __forceinline__ void fold_top()
+    {
+        const double v = M[TOP] * Mtop;
+        const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+        ex[32 * TOP] += Etop - 1023 * (int)Ntop + (int)(b >> 52) - 1023;
+        nn[32 * TOP] += Ntop;
+        M[TOP] = mant_of(b);
+        Mtop = Msave = 1.0; Etop = Esave = 0; Ntop = Nsave = 0;
+    }
+    // One cascade pass per annulus slot S: the keys in [begin, end) satisfy d^2 <= E[S].  Those above E[S - 1] belong
+    // to slot S and are folded into its accumulators; the others are compacted down for the next pass.
+    template <int S>
+    __device__ __forceinline__ void cascade(uint32_t begin, uint32_t end)
+    {
+        if (!__any_sync(HTB_FULL, end != begin)) return;
+        if (S <= pad) {
+            // everything left lies inside the lowest edge: count only
+            nn[32 * (S < 0 ? 0 : S)] += (end - begin) >> 8;
+            return;
+        }
+        if constexpr (S > 0) {
+            const unsigned long long lower = P.E[S - 1];
+            double m = 1.0;
+            int e = 0;
+            uint32_t w = begin;
+            for (uint32_t r = begin; r != end; r += 256u) {
+                const unsigned long long b = lds_u64(r);
+                if (b > lower) { m *= mant_of(b); e += (int)(b >> 52); }
+                else { sts_u64_nc(w, b); w += 256u; }
+            }
+            const unsigned folded = (end - w) >> 8;
+            const double v = M[S] * m;
+            const unsigned long long vb = (unsigned long long)__double_as_longlong(v);
+            ex[32 * S] += e - 1023 * (int)folded + (int)(vb >> 52) - 1023;
+            nn[32 * S] += folded;
+            M[S] = mant_of(vb);
+            cascade<S - 1>(begin, w);
+        }
+    }
+    __device__ __forceinline__ void deep()
+    {
+        cascade<TOP - 2>(qbase, qs);
+        qs = qptr = qsave = qbase;
+    }
+    // Drain the keys pushed since the last call through the passes of the two outermost annuli (the top one only
+    // receives the rare keys the 32-bit test could not place); the rest stays queued for deep().
+    __device__ __forceinline__ void flush1(bool force_deep)
+    {
+        const unsigned long long lower = P.E[TOP - 1], lower2 = P.E[TOP - 2];
+        const bool two = pad < TOP - 1;             // slot TOP - 1 is an annulus (not the inside bucket)
+        double m1 = 1.0;
+        int e1 = 0;
+        unsigned n1 = 0;
+        uint32_t w = qs;
+        for (uint32_t r = qs; r != qptr; r += 256u) {
+            const unsigned long long b = lds_u64(r);
+            if (b > lower) { Mtop *= mant_of(b); Etop += (int)(b >> 52); Ntop += 1u; }
+            else if (two && b > lower2) { m1 *= mant_of(b); e1 += (int)(b >> 52); n1 += 1u; }
+            else { sts_u64_nc(w, b); w += 256u; }
+        }
+        fold_top();
+        if (two) {
+            const double v = M[TOP - 1] * m1;
+            const unsigned long long vb = (unsigned long long)__double_as_longlong(v);
+            ex[32 * (TOP - 1)] += e1 - 1023 * (int)n1 + (int)(vb >> 52) - 1023;
+            nn[32 * (TOP - 1)] += n1;
+            M[TOP - 1] = mant_of(vb);
+        }
+        qs = qptr = qsave = w;
+        if (force_deep || __any_sync(HTB_FULL, w > qbase + 256u * DSQ_QSURV)) {
+            if (two) deep();
+            else { nn[32 * (TOP - 1)] += (qs - qbase) >> 8; qs = qptr = qsave = qbase; }   // one annulus: the rest is inside rp[0]
+        }
+    }
+    __device__ __forceinline__ void pair2(double xa, double ya, double xb, double yb)
+    {
+        const double dxa = xs - xa, dya = ys - ya, dxb = xs - xb, dyb = ys - yb;
+        const double da = dxa * dxa + dya * dya, db = dxb * dxb + dyb * dyb;
+        const int ha = __double2hiint(da), hb = __double2hiint(db);
+        const int ka = (int)(__funnelshift_l((unsigned)__double2loint(da), (unsigned)ha, 6) + (unsigned)P.nbias);
+        const int kb = (int)(__funnelshift_l((unsigned)__double2loint(db), (unsigned)hb, 6) + (unsigned)P.nbias);
+        umin = min(umin, min((unsigned)ka, (unsigned)kb));
+        hmin = min(hmin, min(ha, hb));
+        one(da, ha, ka);
+        one(db, hb, kb);
+    }
+    __device__ __forceinline__ void one(double d, int h, int k)
+    {
+        if ((unsigned)(k - P.F1 - 1) < P.Tspan) {
+            // certainly inside the top annulus
+            Mtop *= __hiloint2double((h & 0x000fffff) | 0x3ff00000, __double2loint(d));
+            Etop += (int)((unsigned)h >> 20);
+            Ntop += 1u;
+        }
+        if (k <= P.F1) { sts_u64_nc(qptr, (unsigned long long)__double_as_longlong(d)); qptr += 256u; }
+    }
+    __device__ __forceinline__ void pair_fast(double xj, double yj)
+    {
+        const double dx = xs - xj, dy = ys - yj;
+        const double d = dx * dx + dy * dy;
+        const int h = __double2hiint(d);
+        const int k = (int)(__funnelshift_l((unsigned)__double2loint(d), (unsigned)h, 6) + (unsigned)P.nbias);
+        umin = min(umin, (unsigned)k);
+        hmin = min(hmin, h);
+        one(d, h, k);
+    }
+    // exact evaluation of staged entries [j0, j1): every pair inside the top edge goes to the queue
+    __device__ __forceinline__ void exact_range(uint32_t stage, int j0, int j1)
+    {
+        const uint32_t bx = stage, by = stage + 8 * HTB_CH;
+#pragma unroll 1
+        for (int j = j0; j < j1; ++j) {
+            const double dx = xs - lds_f64(bx + 8 * j), dy = ys - lds_f64(by + 8 * j);
+            const double d = dx * dx + dy * dy;
+            const unsigned long long b = (unsigned long long)__double_as_longlong(d);
+            if (b <= P.E[TOP]) { sts_u64_nc(qptr, b); qptr += 256u; }
+            if (__any_sync(HTB_FULL, qptr > qbase + 256u * (DSQ_QCAP - 2))) flush1(false);
+        }
+    }
+    __device__ __forceinline__ void check(uint32_t stage, int j0, int j1)
+    {
+        const bool undecided = (umin == 0u) | (hmin < P.Hwin);
+        const bool full = qptr > qbase + QFULL;
+        ++groups;
+        if (__any_sync(HTB_FULL, undecided | full | ((groups & 31) == 0))) {
+            if (__any_sync(HTB_FULL, undecided)) {
+                qptr = qsave; Mtop = Msave; Etop = Esave; Ntop = Nsave;
+                exact_range(stage, j0, j1);
+                umin = 0xffffffffu; hmin = 0x7fffffff;
+            }
+            if (__any_sync(HTB_FULL, qptr > qbase + QFULL)) flush1(false);
+            else if ((groups & 31) == 0) fold_top();      // bounds the running product (< 2^512) and exponent sum
+        }
+        qsave = qptr; Msave = Mtop; Esave = Etop; Nsave = Ntop;
+    }
+    __device__ __forceinline__ void chunk(uint32_t stage, int lo, int hi, uint32_t tok)
+    {
+        const uint32_t bx = stage, by = stage + 8 * HTB_CH;
+        if (always_exact) { exact_range(stage, lo, hi); qsave = qptr; return; }
+        int j = lo;
+        if ((j & 1) && j < hi) { pair_fast(lds_f64(bx + 8 * j), lds_f64(by + 8 * j)); ++j; }
+        int j0 = lo;
+        if (j + DSQ_GROUP <= hi) {
+            double xa, xb, ya, yb;
+            lds_f64x2_tok(bx + 8 * j, tok, xa, xb);
+            lds_f64x2_tok(by + 8 * j, tok, ya, yb);
+#pragma unroll 1
+            for (; j + DSQ_GROUP <= hi; j += DSQ_GROUP) {
+#pragma unroll
+                for (int u = 0; u < DSQ_GROUP; u += 2) {
+                    double xc, xd, yc, yd;
+                    lds_f64x2_tok(bx + 8 * (j + u + 2), tok, xc, xd);     // may run past hi: harmless, never used
+                    lds_f64x2_tok(by + 8 * (j + u + 2), tok, yc, yd);
+                    pair2(xa, ya, xb, yb);
+                    xa = xc; xb = xd; ya = yc; yb = yd;
+                }
+                check(stage, j0, j + DSQ_GROUP);
+                j0 = j + DSQ_GROUP;
+            }
+        }
+        if (j0 < hi) {
+#pragma unroll 1
+            for (; j < hi; ++j) pair_fast(lds_f64(bx + 8 * j), lds_f64(by + 8 * j));
+            check(stage, j0, hi);
+        }
+    }
+    __device__ __forceinline__ bool tile_end(const WalkArrays &, const uint32_t (&idx)[1], int, unsigned)
+    {
+        flush1(true);
+        if (valid) {
+            const int nbin = P.nrp - 1;
+            const double m = P.mass;
+            const int64_t row = P.perm1 ? (int64_t)P.perm1[idx[0]] : (int64_t)idx[0];
+            double inside = (double)nn[32 * pad];
+#pragma unroll
+            for (int s = 1; s < HTB_NBF; ++s) {
+                const int k = s - 1 - pad;            // annulus between edges k and k + 1
+                if (k < 0) continue;
+                const double n = (double)nn[32 * s];
+                // sum over the annulus of ln(d^2 / rp[k+1]^2): exponents and mantissas kept apart
+                const double r2 = P.e0[k + 1];
+                const int rhi = __double2hiint(r2);
+                const int re = (rhi >> 20) - 1023;
+                const double rm = __hiloint2double((rhi & 0x000fffff) | 0x3ff00000, __double2loint(r2));
+                const double lnratio = 0.6931471805599453 * ((double)ex[32 * s] - n * (double)re) + (log(M[s]) - n * log(rm));
+                const double t = m * (n + lnratio);
+                const double ds = m * inside * 2 * P.e1[k] - t;
+                P.out[row * nbin + k] = ds / (3.14159265358979323846 * (P.e0[k + 1] - P.e0[k]));
+                inside += n;
+            }
+        }
+        return false;
+    }
+    __device__ __forceinline__ void kernel_end() {}
+};
+
 // ------------------------------------------------------------------ host launchers
 template <class V>
 static int launch_count(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const typename V::Params &P,
@@ -925,6 +1213,8 @@ static int launch_count(cudaStream_t st, const WalkGeom &G, const WalkArrays &A,
 int htb_fast3_ppl() { return FAST3_PPL; }
 int htb_launch_fast3(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const Fast3Params &P, int *l)
 { return launch_count<Fast3>(st, G, A, P, l); }
+int htb_launch_dsq(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const DSQParams &P, int *l)
+{ return launch_count<DSigmaQ>(st, G, A, P, l); }
 int htb_launch_gen(cudaStream_t st, int kind, const WalkGeom &G, const WalkArrays &A, const GenParams &P, int *l)
 {
     switch (kind) {

@@ -15,6 +15,20 @@ struct Fast3Params {
     unsigned long long *counts;      // [nb] global accumulators
 };
 
+// mean_delta_sigma fast path (one mass for all particles, <= HTB_NBF rp edges)
+struct DSQParams {
+    int nrp;                         // number of rp edges; edge k lives in slot k + (HTB_NBF - nrp)
+    int nbias;                       // key = (bits(dsq) >> 26) + nbias, relative to the top squared edge
+    int Hwin;                        // dsq high words below this: key would wrap -> decided exactly
+    int F1;                          // key of the second edge from the top (lower edge of the top bin)
+    unsigned Tspan;                  // -F1 - 1 (0 disables the in-register top bin)
+    unsigned long long E[HTB_NBF];   // raw bit patterns of the squared edges (pads = 0)
+    const double *e0, *e1;           // device: squared edges, ln(rp[k+1]/rp[k])
+    double mass;
+    double *out;                     // (n1, nrp - 1) rows in input order
+    const uint32_t *perm1;           // sorted position -> input row
+};
+
 struct GenParams {
     int n0, n1;                      // number of edges along the first / second bin axis
     int nhist;                       // histogram length
@@ -28,6 +42,7 @@ struct GenParams {
 
 int htb_fast3_ppl();            // sample1 points per lane of the fast kernel (its tiles hold 32x that)
 int htb_launch_fast3(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const Fast3Params &P, int *launches);
+int htb_launch_dsq(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const DSQParams &P, int *launches);
 int htb_launch_gen(cudaStream_t st, int kind, const WalkGeom &G, const WalkArrays &A, const GenParams &P, int *launches);
 int htb_build_tiles(cudaStream_t st, Workspace &ws, const WalkGeom &G, const SortedSample &s1,
                     int64_t first_cell1, int64_t last_cell1, uint2 **tiles_out, uint32_t **ntiles_dev_out,
