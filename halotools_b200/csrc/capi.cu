@@ -420,6 +420,49 @@ static int upload(Call &c, const void *host, size_t bytes, void **dev)
 #define HTB_GUARD_END                                                          \
     } catch (const std::exception &e) { htb_set_error("exception: %s", e.what()); return 1; }
 
+// Parameters of the fast queue kernels (Fast3 / FastXYZ) for the squared edges rsq[0..nb), or false if they are
+// not eligible.  The 32-bit keys are (bits(dsq) >> 26) relative to the top squared edge, so every separation a
+// tile can meet and every non-zero edge must lie within 2^+-31 of it:
+//   above: points inside the box are at most 2L apart per dimension after the periodic shift and the sentinel
+//          of unused lanes / pad entries sits at 8L  ->  dsq < 256 Lmax^2;
+//   below: smaller separations (and exact zeros) are caught per group by the kernel (Hwin) and evaluated
+//          exactly; edges below the window send the call to the generic kernel.
+static bool fast3_params(const htb_mesh_geom *mesh, const double *bins, const double *rsq, int nb, uint32_t flags,
+                         Fast3Params *out, double *lmax_out)
+{
+    bool fast = !(flags & HTB_FLAG_GENERIC) && nb >= 1 && nb <= HTB_NBF && finite_all(bins, nb);
+    for (int k = 0; k + 1 < nb && fast; ++k) fast = bins[k] >= 0.0 && rsq[k] <= rsq[k + 1];
+    if (fast) fast = bins[nb - 1] >= 0.0 && rsq[nb - 1] > 1e-290 && rsq[nb - 1] < 1e290;
+    double lmax = 0.0;
+    for (int d = 0; d < mesh->ndim; ++d) if (mesh->period[d] > lmax) lmax = mesh->period[d];
+    if (fast) fast = std::isfinite(lmax) && lmax > 0.0 && lmax < 1e140;
+    *lmax_out = lmax;
+    if (!fast) return false;
+    Fast3Params fp{};
+    const long long Kt = (long long)(dbits(rsq[nb - 1]) >> 26);
+    const long long Kmax = (long long)(dbits(256.0 * lmax * lmax) >> 26);
+    const long long lim = 31LL << 26;
+    if (Kmax - Kt >= lim) return false;
+    fp.nb = nb;
+    fp.nbias = (int)(unsigned)(0ULL - (unsigned long long)Kt);
+    fp.Hwin = (int)(dbits(rsq[nb - 1]) >> 32) - (31 << 20);
+    fp.Hz0 = -1;
+    const int pad = HTB_NBF - nb;
+    for (int s = 0; s < HTB_NBF; ++s) {
+        fp.F[s] = INT32_MIN; fp.E[s] = 0;
+        if (s < pad) continue;
+        const double e = rsq[s - pad];
+        fp.E[s] = dbits(e);
+        if (e == 0.0) continue;                      // only exact zeros satisfy it: always decided exactly
+        const long long d = (long long)(dbits(e) >> 26) - Kt;
+        if (d <= -lim) return false;
+        fp.F[s] = (int)d;
+    }
+    fp.E_top = dbits(rsq[nb - 1]);
+    *out = fp;
+    return true;
+}
+
 // ------------------------------------------------------------------ npairs_3d
 extern "C" int htb_npairs_3d_engine(const htb_mesh_geom *mesh,
                                     const double *x1, const double *y1, const double *z1, int64_t stride1, int64_t n1,
@@ -432,40 +475,9 @@ extern "C" int htb_npairs_3d_engine(const htb_mesh_geom *mesh,
     if (mesh->ndim != 3) { htb_set_error("htb_npairs_3d_engine needs a 3-d mesh"); return 1; }
     std::vector<double> rsq((size_t)nb);
     for (int k = 0; k < nb; ++k) rsq[k] = rbins[k] * rbins[k];
-    // Eligibility of the fast kernel.  Its 32-bit keys are (bits(dsq) >> 26) relative to the top squared
-    // edge, so every separation a tile can meet and every non-zero edge must lie within 2^+-31 of it:
-    //   above: points inside the box are at most 2L apart per dimension after the periodic shift and the
-    //          sentinel of unused lanes / pad entries sits at 8L  ->  dsq < 256 Lmax^2;
-    //   below: smaller separations (and exact zeros) are caught per group by the kernel (Hwin) and
-    //          evaluated exactly; edges below the window send the call to the generic kernel.
-    bool fast = !(flags & HTB_FLAG_GENERIC) && nb <= HTB_NBF && finite_all(rbins, nb);
-    for (int k = 0; k + 1 < nb && fast; ++k) fast = rbins[k] >= 0.0 && rsq[k] <= rsq[k + 1];
-    if (fast) fast = rbins[nb - 1] >= 0.0 && rsq[nb - 1] > 1e-290 && rsq[nb - 1] < 1e290;
     double lmax = 0.0;
-    for (int d = 0; d < 3; ++d) if (mesh->period[d] > lmax) lmax = mesh->period[d];
-    if (fast) fast = std::isfinite(lmax) && lmax > 0.0 && lmax < 1e140;
     Fast3Params fp{};
-    if (fast) {
-        const long long Kt = (long long)(dbits(rsq[nb - 1]) >> 26);
-        const long long Kmax = (long long)(dbits(256.0 * lmax * lmax) >> 26);
-        const long long lim = 31LL << 26;
-        if (Kmax - Kt >= lim) fast = false;
-        fp.nb = nb;
-        fp.nbias = (int)(unsigned)(0ULL - (unsigned long long)Kt);
-        fp.Hwin = (int)(dbits(rsq[nb - 1]) >> 32) - (31 << 20);
-        const int pad = HTB_NBF - nb;
-        for (int s = 0; s < HTB_NBF; ++s) {
-            fp.F[s] = INT32_MIN; fp.E[s] = 0;
-            if (s < pad) continue;
-            const double e = rsq[s - pad];
-            fp.E[s] = dbits(e);
-            if (e == 0.0) continue;                      // only exact zeros satisfy it: always decided exactly
-            const long long d = (long long)(dbits(e) >> 26) - Kt;
-            if (d <= -lim) { fast = false; break; }
-            fp.F[s] = (int)d;
-        }
-        fp.E_top = dbits(rsq[nb - 1]);
-    }
+    bool fast = fast3_params(mesh, rbins, rsq.data(), nb, flags, &fp, &lmax);
     Call c;
     if (c.begin()) return 1;
     const double *c1[3] = {x1, y1, z1}, *c2[3] = {x2, y2, z2};
@@ -502,19 +514,46 @@ extern "C" int htb_npairs_xy_z_engine(const htb_mesh_geom *mesh,
     HTB_GUARD_BEGIN
     if (!mesh || !rp_bins || !pi_bins || !counts_out || nrp < 1 || npi < 1) { htb_set_error("htb_npairs_xy_z_engine: bad arguments"); return 1; }
     if (mesh->ndim != 3) { htb_set_error("htb_npairs_xy_z_engine needs a 3-d mesh"); return 1; }
-    Call c;
-    if (c.begin()) return 1;
-    const double *c1[3] = {x1, y1, z1}, *c2[3] = {x2, y2, z2};
-    if (c.setup(mesh, 0, true, c1, stride1, n1, nullptr, c2, stride2, n2, nullptr, 0, false, first_cell1, last_cell1, flags)) return 1;
     std::vector<double> e((size_t)nrp + npi);
     for (int k = 0; k < nrp; ++k) e[k] = rp_bins[k] * rp_bins[k];
     for (int k = 0; k < npi; ++k) e[nrp + k] = pi_bins[k] * pi_bins[k];
-    void *edev = nullptr;
-    if (upload(c, e.data(), sizeof(double) * e.size(), &edev)) return 1;
+    // Fast path (FastXYZ): the rp edges as in npairs_3d, one pi edge, or two when the lower one is so small that
+    // pairs inside it are rare (wp's pi_bins = [0, pi_max]): those are found by the kernel and counted exactly.
+    double lmax = 0.0;
+    Fast3Params fp{};
+    bool fast = (npi == 1 || npi == 2) && finite_all(pi_bins, npi) && pi_bins[npi - 1] >= 0.0 &&
+                fast3_params(mesh, rp_bins, e.data(), nrp, flags, &fp, &lmax);
+    if (fast && npi == 2) fast = pi_bins[0] >= 0.0 && e[nrp] <= 1e-8 * e[nrp + 1];
     const int nh = nrp * npi;
+    Call c;
+    if (c.begin()) return 1;
+    const double *c1[3] = {x1, y1, z1}, *c2[3] = {x2, y2, z2};
+    if (c.setup(mesh, 0, true, c1, stride1, n1, nullptr, c2, stride2, n2, nullptr, 0, false, first_cell1, last_cell1, flags,
+                fast ? 32 * htb_fast3_ppl() : HTB_TILE, fast ? 8.0 * lmax : 1.0e150)) return 1;
     unsigned long long *counts_dev = nullptr;
     if (c.ws.alloc((void **)&counts_dev, sizeof(unsigned long long) * (size_t)nh)) return 1;
     HTB_CUDA(cudaMemsetAsync(counts_dev, 0, sizeof(unsigned long long) * (size_t)nh, c.st));
+    if (fast) {
+        // device layout: column of the top pi edge first, then the lower pi edge column; interleaved on the host
+        fp.pi_top_sq = e[nrp + npi - 1];
+        fp.counts = counts_dev;
+        if (npi == 2) {
+            fp.Epi0 = dbits(e[nrp]);
+            fp.Hz0 = (int)(dbits(e[nrp]) >> 32);
+            fp.counts0 = counts_dev + nrp;
+        }
+        if (htb_launch_fastxyz(c.st, c.G, c.A, fp, &c.launches)) return 1;
+        std::vector<long long> cols((size_t)nh);
+        HTB_CUDA(cudaMemcpyAsync(cols.data(), counts_dev, sizeof(int64_t) * (size_t)nh, cudaMemcpyDeviceToHost, c.st));
+        if (c.finish(stats, 1)) return 1;
+        for (int k = 0; k < nrp; ++k) {
+            counts_out[(size_t)k * npi + (npi - 1)] = cols[(size_t)k];
+            if (npi == 2) counts_out[(size_t)k * npi] = cols[(size_t)nrp + k];
+        }
+        return 0;
+    }
+    void *edev = nullptr;
+    if (upload(c, e.data(), sizeof(double) * e.size(), &edev)) return 1;
     GenParams gp{};
     gp.n0 = nrp; gp.n1 = npi; gp.nhist = nh;
     gp.e0 = (const double *)edev; gp.e1 = (const double *)edev + nrp;

@@ -178,6 +178,7 @@ k_count(const __grid_constant__ WalkGeom G, const __grid_constant__ WalkArrays A
 #pragma unroll 1
         for (int sub = 0; sub < nsub; ++sub) {
             v.tile_begin(p, val, idx, A);
+            v.tile_weight(sub == 1 ? 2u : 1u);
 #pragma unroll 1
             for (int pass = 0; pass < 2; ++pass) {
                 walk_tile<V>(v, G, A, S, gchunk, blo, bhi, fs, nref, pairs, cnt, G.sym ? sub + 1 : 0, start, start + (uint32_t)cnt);
@@ -236,13 +237,14 @@ __device__ __forceinline__ void sts_u32_nc(uint32_t addr, uint32_t v)
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v));
 }
 
-template <int PPL_>
+template <int PPL_, int KIND = 0>      // KIND 0: npairs_3d;  1: npairs_xy_z with one or two pi edges
 struct Fast3T {
     static constexpr int DIM = 3, NPAY = 0, PPL = PPL_, WARPS = FAST3_WARPS, MINBLOCKS = FAST3_MINBLOCKS;
     static constexpr bool TMA = true;
     static constexpr int GJ = QGROUP / PPL;     // sample2 points per group
     static constexpr int TOP = HTB_NBF - 1;
-    static constexpr uint32_t QFULL = 128u * (QCAP - QGROUP - PPL);   // flush when a lane's queue is longer than this
+    static constexpr int QC = KIND == 1 ? QCAP - 16 : QCAP;       // (rp, pi): 16 rows go to the lower-pi-edge counters
+    static constexpr uint32_t QFULL = 128u * (QC - QGROUP - PPL);     // flush when a lane's queue is longer than this
     typedef Fast3Params Params;
     const Params &P;
     uint32_t qbase;             // shared-space address of this lane's queue column
@@ -258,16 +260,24 @@ struct Fast3T {
     unsigned ctop, csave;
     unsigned umin;
     int hmin;
+    int hzmin;                  // (rp, pi): smallest dz^2 high word since the last check
+    uint32_t c0base;            // (rp, pi): shared-space address of this lane's 16 counters of pairs that also lie
+                                // inside the LOWER pi edge (rare by construction, always decided by the exact path)
+    unsigned wt_now;
+    unsigned long long tot0;
     bool exact, dirty, always_exact;
     unsigned long long tot;
 
     static size_t scratch_bytes(const Params &) { return sizeof(uint32_t) * QCAP * 32; }
+    __device__ __forceinline__ void tile_weight(unsigned wt) { wt_now = wt; }
 
     __device__ __forceinline__ Fast3T(const Params &p, void *scratch, int ln, const WalkArrays &A) : P(p), lane(ln)
     {
         qbase = smem_u32(scratch) + 4u * (uint32_t)ln;
         qs = qptr = qsave = qbase;
-        tot = 0; ctop = csave = 0; umin = 0xffffffffu; hmin = 0x7fffffff;
+        tot = 0; ctop = csave = 0; umin = 0xffffffffu; hmin = 0x7fffffff; hzmin = 0x7fffffff; wt_now = 1; tot0 = 0;
+        c0base = qbase + 128u * QC;
+        if (KIND == 1) { for (int k = 0; k < HTB_NBF; ++k) sts_u32(c0base + 128u * k, 0u); }
         exact = dirty = false;
         valmask = 0; sentinel = 0.0;
         // a point outside [0, period] can be arbitrarily far away: the 32-bit keys could wrap
@@ -350,10 +360,20 @@ struct Fast3T {
     __device__ __forceinline__ void key_of(double x1s, double y1s, double z1s, double xj, double yj, double zj, int &key, int &hi)
     {
         const double dx = x1s - xj, dy = y1s - yj, dz = z1s - zj;
-        const double dsq = dx * dx + dy * dy + dz * dz;
-        hi = __double2hiint(dsq);
-        // (bits >> 26) + nbias, written as the high word of a left shift so that it maps to one LEA.HI
-        key = (int)(__funnelshift_l((unsigned)__double2loint(dsq), (unsigned)hi, 6) + (unsigned)P.nbias);
+        if (KIND == 0) {
+            const double dsq = dx * dx + dy * dy + dz * dz;
+            hi = __double2hiint(dsq);
+            // (bits >> 26) + nbias, written as the high word of a left shift so that it maps to one LEA.HI
+            key = (int)(__funnelshift_l((unsigned)__double2loint(dsq), (unsigned)hi, 6) + (unsigned)P.nbias);
+        } else {
+            // npairs_xy_z_engine.pyx:180-183: dxy_sq = dx*dx + dy*dy, dz_sq = dz*dz
+            const double dxy_sq = dx * dx + dy * dy;
+            const double dz_sq = dz * dz;
+            hi = __double2hiint(dxy_sq);
+            hzmin = min(hzmin, __double2hiint(dz_sq));
+            const int k = (int)(__funnelshift_l((unsigned)__double2loint(dxy_sq), (unsigned)hi, 6) + (unsigned)P.nbias);
+            key = (dz_sq <= P.pi_top_sq) ? k : 0x7fffffff;       // exact f64 compare: outside the top pi edge = out of range
+        }
     }
     __device__ __forceinline__ void push(int key)
     {
@@ -382,11 +402,27 @@ struct Fast3T {
     __device__ __forceinline__ void pair_exact(int q, double xj, double yj, double zj)
     {
         const double dx = xs[q] - xj, dy = ys[q] - yj, dz = zs[q] - zj;
-        const double dsq = dx * dx + dy * dy + dz * dz;
-        const unsigned long long b = (unsigned long long)__double_as_longlong(dsq);
-        if (b <= P.E_top) {
+        if (KIND == 0) {
+            const double dsq = dx * dx + dy * dy + dz * dz;
+            const unsigned long long b = (unsigned long long)__double_as_longlong(dsq);
+            if (b <= P.E_top) {
 #pragma unroll
-            for (int s = 0; s < HTB_NBF; ++s) c[s] += (b <= P.E[s]) ? 1u : 0u;
+                for (int s = 0; s < HTB_NBF; ++s) c[s] += (b <= P.E[s]) ? 1u : 0u;
+            }
+        } else {
+            const double dxy_sq = dx * dx + dy * dy;
+            const double dz_sq = dz * dz;
+            const unsigned long long b = (unsigned long long)__double_as_longlong(dxy_sq);
+            if (b <= P.E_top && dz_sq <= P.pi_top_sq) {
+#pragma unroll
+                for (int s = 0; s < HTB_NBF; ++s) c[s] += (b <= P.E[s]) ? 1u : 0u;
+                if (P.counts0 && (unsigned long long)__double_as_longlong(dz_sq) <= P.Epi0) {
+                    // also inside the lower pi edge
+#pragma unroll 1
+                    for (int s = 0; s < HTB_NBF; ++s)
+                        if (b <= P.E[s]) sts_u32(c0base + 128u * s, lds_u32(c0base + 128u * s) + 1u);
+                }
+            }
         }
     }
     __device__ __forceinline__ void exact_range(uint32_t stage, int j0, int j1)
@@ -402,14 +438,15 @@ struct Fast3T {
     // after every group of <= QGROUP + PPL pairs per lane: staged entries [j0, j1) since the last check
     __device__ __forceinline__ void check(uint32_t stage, int j0, int j1)
     {
-        const bool undecided = (umin == 0u) | (hmin < P.Hwin);
+        const bool undecided = (umin == 0u) | (hmin < P.Hwin) | (KIND == 1 && hzmin <= P.Hz0);
         const bool full = qptr > qbase + QFULL;
         if (__any_sync(HTB_FULL, undecided | full)) {
             if (__any_sync(HTB_FULL, undecided)) {
-                // some pair of this group cannot be decided from its 32-bit key: take the whole group back
+                // some pair of this group cannot be decided from its 32-bit key (or may lie inside the lower pi
+                // edge): take the whole group back
                 qptr = qsave; ctop = csave;
                 exact_range(stage, j0, j1);
-                umin = 0xffffffffu; hmin = 0x7fffffff;
+                umin = 0xffffffffu; hmin = 0x7fffffff; hzmin = 0x7fffffff;
             }
             if (__any_sync(HTB_FULL, qptr > qbase + QFULL)) flush1(false);
         }
@@ -471,6 +508,7 @@ struct Fast3T {
                 // a queued key collided with an edge key: throw the tile's counts away and redo it exactly
 #pragma unroll
                 for (int s = 0; s < HTB_NBF; ++s) c[s] = 0;
+                if (KIND == 1) { for (int k = 0; k < HTB_NBF; ++k) sts_u32(c0base + 128u * k, 0u); }
                 dirty = false; exact = true;
                 return true;
             }
@@ -481,15 +519,25 @@ struct Fast3T {
             if (lane == s) tot += (unsigned long long)wt * (unsigned long long)r;
             c[s] = 0;
         }
+        if (KIND == 1) {
+#pragma unroll 1
+            for (int s = 0; s < HTB_NBF; ++s) {
+                const unsigned r = __reduce_add_sync(HTB_FULL, lds_u32(c0base + 128u * s));
+                if (lane == s) tot0 += (unsigned long long)wt * (unsigned long long)r;
+                sts_u32(c0base + 128u * s, 0u);
+            }
+        }
         return false;
     }
     __device__ __forceinline__ void kernel_end()
     {
         const int k = lane - (HTB_NBF - P.nb);
         if (lane < HTB_NBF && k >= 0 && tot) atomicAdd(P.counts + k, tot);
+        if (KIND == 1 && P.counts0 && lane < HTB_NBF && k >= 0 && tot0) atomicAdd(P.counts0 + k, tot0);
     }
 };
-typedef Fast3T<FAST3_PPL> Fast3;
+typedef Fast3T<FAST3_PPL, 0> Fast3;
+typedef Fast3T<FAST3_PPL, 1> FastXYZ;
 
 // ------------------------------------------------------------------ generic integer-count variants
 // per-warp u32 histogram in shared memory (scratch), flushed to the global u64 histogram per tile
@@ -512,6 +560,7 @@ struct GenCount {
         xs1 = x1 - sh[0]; ys1 = y1 - sh[1]; zs1 = z1 - sh[2];
     }
 
+    __device__ __forceinline__ void tile_weight(unsigned) {}
     __device__ GenCount(const Params &p, void *scratch, int ln, const WalkArrays &) : P(p), hist((uint32_t *)scratch), lane(ln)
     {
         for (int k = lane; k < P.nhist; k += 32) hist[k] = 0;
@@ -645,6 +694,7 @@ struct Marked3 {
         xs1 = x1 - sh[0]; ys1 = y1 - sh[1]; zs1 = z1 - sh[2];
     }
 
+    __device__ __forceinline__ void tile_weight(unsigned) {}
     __device__ Marked3(const Params &p, void *scratch, int ln, const WalkArrays &) : P(p), hist((double *)scratch), lane(ln)
     {
         for (int k = lane; k < P.nhist; k += 32) hist[k] = 0.0;
@@ -723,6 +773,7 @@ struct DSigma {
         xs0 = x0 - sh[0]; ys0 = y0 - sh[1]; xs1 = x1 - sh[0]; ys1 = y1 - sh[1];
     }
 
+    __device__ __forceinline__ void tile_weight(unsigned) {}
     __device__ DSigma(const Params &p, void *scratch, int ln, const WalkArrays &) : P(p), acc((double *)scratch), lane(ln) {}
     __device__ __forceinline__ void tile_begin(const double (&p)[2][3], const bool (&val)[2], const uint32_t (&)[2],
                                                const WalkArrays &)
@@ -808,6 +859,7 @@ struct DSigmaU {
         const size_t nbin = (size_t)(p.n0 - 1);
         return 64 * (8 * nbin + 4 * nbin + 4 * (nbin + 1));
     }
+    __device__ __forceinline__ void tile_weight(unsigned) {}
     __device__ DSigmaU(const Params &p, void *scratch, int ln, const WalkArrays &) : P(p), lane(ln)
     {
         nbin = P.n0 - 1;
@@ -958,6 +1010,7 @@ struct DSigmaQ {
 
     static size_t scratch_bytes(const Params &) { return 8 * 32 * DSQ_QCAP + 2 * 4 * 32 * HTB_NBF; }
 
+    __device__ __forceinline__ void tile_weight(unsigned) {}
     __device__ __forceinline__ DSigmaQ(const Params &p, void *scratch, int ln, const WalkArrays &A) : P(p), lane(ln)
     {
         pad = HTB_NBF - P.nrp;
@@ -1213,6 +1266,8 @@ static int launch_count(cudaStream_t st, const WalkGeom &G, const WalkArrays &A,
 int htb_fast3_ppl() { return FAST3_PPL; }
 int htb_launch_fast3(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const Fast3Params &P, int *l)
 { return launch_count<Fast3>(st, G, A, P, l); }
+int htb_launch_fastxyz(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const Fast3Params &P, int *l)
+{ return launch_count<FastXYZ>(st, G, A, P, l); }
 int htb_launch_dsq(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const DSQParams &P, int *l)
 { return launch_count<DSigmaQ>(st, G, A, P, l); }
 int htb_launch_gen(cudaStream_t st, int kind, const WalkGeom &G, const WalkArrays &A, const GenParams &P, int *l)

@@ -13,6 +13,11 @@ struct Fast3Params {
     unsigned long long E[HTB_NBF];   // raw bit patterns of the squared edges (pads = 0)
     unsigned long long E_top;
     unsigned long long *counts;      // [nb] global accumulators
+    // (rp, pi) variant only: the keys are those of dx^2 + dy^2; a pair takes part if dz^2 <= pi_top_sq
+    double pi_top_sq;                // squared top pi edge
+    unsigned long long Epi0;         // raw bits of the squared lower pi edge (two pi edges only)
+    int Hz0;                         // dz^2 high words <= this send the group to the exact path (-1: one pi edge)
+    unsigned long long *counts0;     // [nb] accumulators of the lower pi edge column, or null
 };
 
 // mean_delta_sigma fast path (one mass for all particles, <= HTB_NBF rp edges)
@@ -42,6 +47,7 @@ struct GenParams {
 
 int htb_fast3_ppl();            // sample1 points per lane of the fast kernel (its tiles hold 32x that)
 int htb_launch_fast3(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const Fast3Params &P, int *launches);
+int htb_launch_fastxyz(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const Fast3Params &P, int *launches);
 int htb_launch_dsq(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const DSQParams &P, int *launches);
 int htb_launch_gen(cudaStream_t st, int kind, const WalkGeom &G, const WalkArrays &A, const GenParams &P, int *launches);
 int htb_build_tiles(cudaStream_t st, Workspace &ws, const WalkGeom &G, const SortedSample &s1,
