@@ -624,12 +624,39 @@ extern "C" int htb_marked_npairs_3d_engine(const htb_mesh_geom *mesh,
     if (mesh->ndim != 3) { htb_set_error("htb_marked_npairs_3d_engine needs a 3-d mesh"); return 1; }
     if (nw < 1 || nw > HTB_MAX_NW) { htb_set_error("weights per point must be in [1, %d]", HTB_MAX_NW); return 1; }
     if (weight_func_id < 0 || weight_func_id > 17) { htb_set_error("marking function does not exist, id=%d", weight_func_id); return 1; }
+    std::vector<double> rsq((size_t)nb);
+    for (int k = 0; k < nb; ++k) rsq[k] = rbins[k] * rbins[k];
+    // Fast path (MarkedQ): one weight per point and the product marking function (ids 0 and 1), edges as in
+    // npairs_3d.  With the same sample AND the same weights on both sides the product is symmetric, so the
+    // symmetric auto-correlation mode applies.
+    double lmax = 0.0;
+    Fast3Params fp{};
+    const bool fast = nw == 1 && (weight_func_id == 0 || weight_func_id == 1) &&
+                      fast3_params(mesh, rbins, rsq.data(), nb, flags, &fp, &lmax);
     Call c;
     if (c.begin()) return 1;
     const double *c1[3] = {x1, y1, z1}, *c2[3] = {x2, y2, z2};
-    if (c.setup(mesh, 1, false, c1, stride1, n1, w1, c2, stride2, n2, w2, nw, false, first_cell1, last_cell1, flags)) return 1;
-    std::vector<double> rsq((size_t)nb);
-    for (int k = 0; k < nb; ++k) rsq[k] = rbins[k] * rbins[k];
+    if (c.setup(mesh, 1, fast && w1 == w2, c1, stride1, n1, w1, c2, stride2, n2, w2, nw, false, first_cell1, last_cell1, flags,
+                HTB_TILE, fast ? 8.0 * lmax : 1.0e150)) return 1;
+    if (fast) {
+        double *fs = nullptr;
+        if (c.ws.alloc((void **)&fs, sizeof(double) * (HTB_NBF + 1))) return 1;
+        HTB_CUDA(cudaMemsetAsync(fs, 0, sizeof(double) * (HTB_NBF + 1), c.st));
+        fp.fsums = fs;
+        if (htb_launch_markedq(c.st, c.G, c.A, fp, &c.launches)) return 1;
+        double h[HTB_NBF + 1];
+        HTB_CUDA(cudaMemcpyAsync(h, fs, sizeof(h), cudaMemcpyDeviceToHost, c.st));
+        if (c.finish(stats, 1)) return 1;
+        // cumulative sums (marked_npairs_3d_engine.pyx:212-216): a pair of level s counts for every edge >= s
+        const int pad = HTB_NBF - nb;
+        double run = 0.0;
+        for (int s = 0; s < HTB_NBF; ++s) {
+            run += h[s];
+            if (s >= pad && s < HTB_NBF - 1) counts_out[s - pad] = run;
+        }
+        counts_out[nb - 1] = h[HTB_NBF];
+        return 0;
+    }
     void *edev = nullptr;
     if (upload(c, rsq.data(), sizeof(double) * (size_t)nb, &edev)) return 1;
     double *counts_dev = nullptr;

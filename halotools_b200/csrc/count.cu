@@ -950,6 +950,265 @@ struct DSigmaU {
     __device__ __forceinline__ void kernel_end() {}
 };
 
+// ------------------------------------------------------------------ MarkedQ (marked_npairs_3d, weight = w1 * w2)
+// marked_npairs_3d_engine.pyx:204-216 with marking function 1 (mweights, marking_functions.pyx:14-24; id 0, the
+// custom hook, is the same product).  The distance arithmetic and the 32-bit relative keys are those of Fast3.
+// Per lane and point: the weights w2_j of all pairs certainly inside the top edge are summed in a register
+// (one predicated DADD per pair); a pair that may lie inside the second edge pushes {key, w2_j} to the point's
+// queue.  The queues are drained by the compaction cascade; a key that drops out at level S adds its weight to
+// the DIFFERENTIAL sum of level S (each weight is added once), the host forms the cumulative sums.  Ambiguous
+// keys: group roll-back / exact tile redo as in Fast3.
+#ifndef MQ_QD
+#define MQ_QD 13              // queue rows (16 bytes per lane) per point
+#endif
+#ifndef MQ_QSURV
+#define MQ_QSURV 4
+#endif
+#define MQ_GROUP 8            // pairs per lane between two queue checks (4 per point)
+
+__device__ __forceinline__ void sts_kw(uint32_t addr, int key, double w)
+{
+    asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(addr), "l"((long long)key), "d"(w));
+}
+__device__ __forceinline__ void lds_kw(uint32_t addr, int &key, double &w)
+{
+    long long k;
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(k), "=d"(w) : "r"(addr));
+    key = (int)k;
+}
+
+struct MarkedQ {
+    static constexpr int DIM = 3, NPAY = 1, PPL = 2, WARPS = 4, MINBLOCKS = 3;
+    static constexpr bool TMA = true;
+    static constexpr int GJ = MQ_GROUP / PPL;
+    static constexpr int TOP = HTB_NBF - 1;
+    static constexpr uint32_t QBYTES = 512u * MQ_QD;                       // one point's queue
+    static constexpr uint32_t QFULL = 512u * (MQ_QD - GJ - 1);
+    typedef Fast3Params Params;
+    const Params &P;
+    int lane;
+    uint32_t qbase;             // queue of point 0; point 1 follows at + QBYTES
+    uint32_t qs0, qp0, qv0, qs1, qp1, qv1;   // per point: survivor end, push pointer, roll-back point
+    double xs[PPL], ys[PPL], zs[PPL], x[PPL], y[PPL], z[PPL], w1[PPL];
+    double Wtop[PPL], Wsave[PPL];   // sum of w2 over the pairs certainly inside the top edge
+    double accD[HTB_NBF];           // differential weighted sums per level (this tile)
+    double Xall;                    // all weights added by the exact path (they are not in Wtop)
+    unsigned umin;
+    int hmin;
+    bool exact, dirty, always_exact;
+    double tot;
+
+    static size_t scratch_bytes(const Params &) { return 2 * 512 * MQ_QD; }
+    __device__ __forceinline__ void tile_weight(unsigned) {}
+
+    __device__ __forceinline__ MarkedQ(const Params &p, void *scratch, int ln, const WalkArrays &A) : P(p), lane(ln)
+    {
+        qbase = smem_u32(scratch) + 16u * (uint32_t)ln;
+        qs0 = qp0 = qv0 = qbase;
+        qs1 = qp1 = qv1 = qbase + QBYTES;
+        tot = 0.0; Xall = 0.0; umin = 0xffffffffu; hmin = 0x7fffffff;
+        exact = dirty = false;
+        always_exact = ((A.flags1[0] | A.flags2[0]) & 1u) != 0u;
+#pragma unroll
+        for (int s = 0; s < HTB_NBF; ++s) accD[s] = 0.0;
+#pragma unroll
+        for (int q = 0; q < PPL; ++q) { x[q] = y[q] = z[q] = xs[q] = ys[q] = zs[q] = w1[q] = Wtop[q] = Wsave[q] = 0.0; }
+    }
+    __device__ __forceinline__ void tile_begin(const double (&p)[PPL][3], const bool (&val)[PPL], const uint32_t (&id)[PPL],
+                                               const WalkArrays &A)
+    {
+#pragma unroll
+        for (int q = 0; q < PPL; ++q) {
+            x[q] = p[q][0]; y[q] = p[q][1]; z[q] = p[q][2];
+            w1[q] = val[q] ? A.pay1[id[q]] : 0.0;
+            Wtop[q] = Wsave[q] = 0.0;
+        }
+        exact = always_exact; dirty = false;
+    }
+    __device__ __forceinline__ void set_shift(const double (&sh)[3], const WalkArrays &)
+    {
+#pragma unroll
+        for (int q = 0; q < PPL; ++q) { xs[q] = x[q] - sh[0]; ys[q] = y[q] - sh[1]; zs[q] = z[q] - sh[2]; }
+    }
+    // compaction pass over one point's queue [r, end): keys <= Fk are kept (moved down to w); the weights of the
+    // others are summed (they drop out at this level); a key equal to Fin (the edge that admitted it) = dirty
+    __device__ __forceinline__ uint32_t compact(uint32_t r, uint32_t end, uint32_t w, int Fk, int Fin, double &dropped)
+    {
+        bool eq = false;
+        double s = 0.0;
+        for (; r != end; r += 512u) {
+            int k; double wt;
+            lds_kw(r, k, wt);
+            eq |= (k == Fin);
+            if (k <= Fk) { sts_kw(w, k, wt); w += 512u; }
+            else s += wt;
+        }
+        dirty |= eq;
+        dropped = s;
+        return w;
+    }
+    template <int S>
+    __device__ __forceinline__ void cascade(uint32_t base, uint32_t end, double wq)
+    {
+        if (!__any_sync(HTB_FULL, end != base)) return;
+        if constexpr (S >= 1) {
+            // keys in [base, end) were admitted by F[S]; those above F[S - 1] have level S
+            double d;
+            const uint32_t w = compact(base, end, base, P.F[S - 1], P.F[S], d);
+            accD[S] += wq * d;
+            cascade<S - 1>(base, w, wq);
+        } else {
+            // level 0: everything left has level 0
+            double d;
+            (void)compact(base, end, base, (int)0x80000000, P.F[0], d);
+            accD[0] += wq * d;
+        }
+    }
+    __device__ __forceinline__ void flush_point(uint32_t base, uint32_t &qs, uint32_t &qp, uint32_t &qv, double wq, bool force)
+    {
+        // new keys were admitted by F[TOP - 1]: those above F[TOP - 2] have level TOP - 1
+        double d;
+        const uint32_t w = compact(qs, qp, qs, P.F[TOP - 2], P.F[TOP - 1], d);
+        accD[TOP - 1] += wq * d;
+        qs = qp = qv = w;
+        if (force || __any_sync(HTB_FULL, w > base + 512u * MQ_QSURV)) {
+            cascade<TOP - 2>(base, qs, wq);
+            qs = qp = qv = base;
+        }
+    }
+    __device__ __forceinline__ void flush(bool force)
+    {
+        flush_point(qbase, qs0, qp0, qv0, w1[0], force);
+        flush_point(qbase + QBYTES, qs1, qp1, qv1, w1[1], force);
+    }
+    __device__ __forceinline__ void pair_fast(int q, uint32_t &qp, double xj, double yj, double zj, double wj)
+    {
+        const double dx = xs[q] - xj, dy = ys[q] - yj, dz = zs[q] - zj;
+        const double dsq = dx * dx + dy * dy + dz * dz;
+        const int hi = __double2hiint(dsq);
+        const int key = (int)(__funnelshift_l((unsigned)__double2loint(dsq), (unsigned)hi, 6) + (unsigned)P.nbias);
+        umin = min(umin, (unsigned)key);
+        hmin = min(hmin, hi);
+        if (key < 0) Wtop[q] += wj;
+        if (key <= P.F[TOP - 1]) { sts_kw(qp, key, wj); qp += 512u; }
+    }
+    __device__ __forceinline__ void pair_exact(int q, double xj, double yj, double zj, double wj)
+    {
+        const double dx = xs[q] - xj, dy = ys[q] - yj, dz = zs[q] - zj;
+        const double dsq = dx * dx + dy * dy + dz * dz;
+        const unsigned long long b = (unsigned long long)__double_as_longlong(dsq);
+        if (b <= P.E_top) {
+            const double w = w1[q] * wj;
+            Xall += w;
+            bool below = false;                     // already inside a lower edge
+#pragma unroll
+            for (int s = 0; s < HTB_NBF; ++s) {
+                const bool in = b <= P.E[s];
+                if (in && !below) accD[s] += w;
+                below = below || in;
+            }
+        }
+    }
+    __device__ __forceinline__ void exact_range(uint32_t stage, int j0, int j1)
+    {
+        const uint32_t bx = stage, by = stage + 8 * HTB_CH, bz = stage + 16 * HTB_CH, bw = stage + 24 * HTB_CH;
+#pragma unroll 1
+        for (int j = j0; j < j1; ++j) {
+            const double xj = lds_f64(bx + 8 * j), yj = lds_f64(by + 8 * j), zj = lds_f64(bz + 8 * j), wj = lds_f64(bw + 8 * j);
+#pragma unroll
+            for (int q = 0; q < PPL; ++q) pair_exact(q, xj, yj, zj, wj);
+        }
+    }
+    __device__ __forceinline__ void check(uint32_t stage, int j0, int j1)
+    {
+        const bool undecided = (umin == 0u) | (hmin < P.Hwin);
+        const bool full = (qp0 > qbase + QFULL) | (qp1 > qbase + QBYTES + QFULL);
+        if (__any_sync(HTB_FULL, undecided | full)) {
+            if (__any_sync(HTB_FULL, undecided)) {
+                qp0 = qv0; qp1 = qv1; Wtop[0] = Wsave[0]; Wtop[1] = Wsave[1];
+                exact_range(stage, j0, j1);
+                umin = 0xffffffffu; hmin = 0x7fffffff;
+            }
+            if (__any_sync(HTB_FULL, (qp0 > qbase + QFULL) | (qp1 > qbase + QBYTES + QFULL))) flush(false);
+        }
+        qv0 = qp0; qv1 = qp1; Wsave[0] = Wtop[0]; Wsave[1] = Wtop[1];
+    }
+    __device__ __forceinline__ void chunk(uint32_t stage, int lo, int hi, uint32_t tok)
+    {
+        const uint32_t bx = stage, by = stage + 8 * HTB_CH, bz = stage + 16 * HTB_CH, bw = stage + 24 * HTB_CH;
+        if (exact) { exact_range(stage, lo, hi); return; }
+        int j = lo;
+        if ((j & 1) && j < hi) {
+            const double xj = lds_f64(bx + 8 * j), yj = lds_f64(by + 8 * j), zj = lds_f64(bz + 8 * j), wj = lds_f64(bw + 8 * j);
+            pair_fast(0, qp0, xj, yj, zj, wj);
+            pair_fast(1, qp1, xj, yj, zj, wj);
+            ++j;
+        }
+        int j0 = lo;
+        if (j + GJ <= hi) {
+            double xa, xb, ya, yb, za, zb, wa, wb;
+            lds_f64x2_tok(bx + 8 * j, tok, xa, xb);
+            lds_f64x2_tok(by + 8 * j, tok, ya, yb);
+            lds_f64x2_tok(bz + 8 * j, tok, za, zb);
+            lds_f64x2_tok(bw + 8 * j, tok, wa, wb);
+#pragma unroll 1
+            for (; j + GJ <= hi; j += GJ) {
+#pragma unroll
+                for (int u = 0; u < GJ; u += 2) {
+                    double xc, xd, yc, yd, zc, zd, wc, wd;
+                    lds_f64x2_tok(bx + 8 * (j + u + 2), tok, xc, xd);     // may run past hi: harmless, never used
+                    lds_f64x2_tok(by + 8 * (j + u + 2), tok, yc, yd);
+                    lds_f64x2_tok(bz + 8 * (j + u + 2), tok, zc, zd);
+                    lds_f64x2_tok(bw + 8 * (j + u + 2), tok, wc, wd);
+                    pair_fast(0, qp0, xa, ya, za, wa);
+                    pair_fast(1, qp1, xa, ya, za, wa);
+                    pair_fast(0, qp0, xb, yb, zb, wb);
+                    pair_fast(1, qp1, xb, yb, zb, wb);
+                    xa = xc; xb = xd; ya = yc; yb = yd; za = zc; zb = zd; wa = wc; wb = wd;
+                }
+                check(stage, j0, j + GJ);
+                j0 = j + GJ;
+            }
+        }
+        if (j0 < hi) {
+#pragma unroll 1
+            for (; j < hi; ++j) {
+                const double xj = lds_f64(bx + 8 * j), yj = lds_f64(by + 8 * j), zj = lds_f64(bz + 8 * j), wj = lds_f64(bw + 8 * j);
+                pair_fast(0, qp0, xj, yj, zj, wj);
+                pair_fast(1, qp1, xj, yj, zj, wj);
+            }
+            check(stage, j0, hi);
+        }
+    }
+    __device__ __forceinline__ bool tile_end(const WalkArrays &, const uint32_t (&)[PPL], int pass, unsigned wt)
+    {
+        if (!exact) {
+            flush(true);
+            if (__any_sync(HTB_FULL, dirty) && pass == 0) {
+#pragma unroll
+                for (int s = 0; s < HTB_NBF; ++s) accD[s] = 0.0;
+                Wtop[0] = Wtop[1] = Wsave[0] = Wsave[1] = 0.0; Xall = 0.0;
+                dirty = false; exact = true;
+                return true;
+            }
+        }
+        const double all_in = warp_sum(w1[0] * Wtop[0] + w1[1] * Wtop[1] + Xall);
+        if (lane == HTB_NBF) tot += (double)wt * all_in;
+#pragma unroll
+        for (int s = 0; s < HTB_NBF; ++s) {
+            const double r = warp_sum(accD[s]);
+            if (lane == s) tot += (double)wt * r;
+            accD[s] = 0.0;
+        }
+        Wtop[0] = Wtop[1] = Wsave[0] = Wsave[1] = 0.0; Xall = 0.0;
+        return false;
+    }
+    __device__ __forceinline__ void kernel_end()
+    {
+        if (lane <= HTB_NBF && tot != 0.0) atomicAdd(P.fsums + lane, tot);
+    }
+};
+
 // ------------------------------------------------------------------ DSigmaQ (uniform particle mass, fast path)
 // mean_delta_sigma_engine.pyx:162-180 for one particle mass m.  Per galaxy and annulus the engine needs the number of
 // particles n and sum ln d^2 (see DSigmaU); here every lane owns ONE galaxy and
@@ -1266,6 +1525,8 @@ static int launch_count(cudaStream_t st, const WalkGeom &G, const WalkArrays &A,
 int htb_fast3_ppl() { return FAST3_PPL; }
 int htb_launch_fast3(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const Fast3Params &P, int *l)
 { return launch_count<Fast3>(st, G, A, P, l); }
+int htb_launch_markedq(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const Fast3Params &P, int *l)
+{ return launch_count<MarkedQ>(st, G, A, P, l); }
 int htb_launch_fastxyz(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const Fast3Params &P, int *l)
 { return launch_count<FastXYZ>(st, G, A, P, l); }
 int htb_launch_dsq(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const DSQParams &P, int *l)

@@ -18,6 +18,9 @@ struct Fast3Params {
     unsigned long long Epi0;         // raw bits of the squared lower pi edge (two pi edges only)
     int Hz0;                         // dz^2 high words <= this send the group to the exact path (-1: one pi edge)
     unsigned long long *counts0;     // [nb] accumulators of the lower pi edge column, or null
+    // marked variant (MarkedQ, weight function w1 * w2): [HTB_NBF + 1] float sums: slot s = pairs whose lowest
+    // satisfied edge is slot s (differential), slot HTB_NBF = all pairs inside the top edge
+    double *fsums;
 };
 
 // mean_delta_sigma fast path (one mass for all particles, <= HTB_NBF rp edges)
@@ -47,6 +50,7 @@ struct GenParams {
 
 int htb_fast3_ppl();            // sample1 points per lane of the fast kernel (its tiles hold 32x that)
 int htb_launch_fast3(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const Fast3Params &P, int *launches);
+int htb_launch_markedq(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const Fast3Params &P, int *launches);
 int htb_launch_fastxyz(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const Fast3Params &P, int *launches);
 int htb_launch_dsq(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const DSQParams &P, int *launches);
 int htb_launch_gen(cudaStream_t st, int kind, const WalkGeom &G, const WalkArrays &A, const GenParams &P, int *launches);
