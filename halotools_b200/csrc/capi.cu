@@ -7,6 +7,9 @@
 #include <cstring>
 #include <cmath>
 #include <vector>
+#include <thread>
+#include <atomic>
+#include <algorithm>
 
 #include "count.cuh"
 
@@ -86,6 +89,10 @@ void Workspace::release()
     for (int i = nptrs - 1; i >= 0; --i) cudaFreeAsync(ptrs[i], st);
     nptrs = 0;
 }
+
+#define HTB_GUARD_BEGIN try {
+#define HTB_GUARD_END                                                          \
+    } catch (const std::exception &e) { htb_set_error("exception: %s", e.what()); return 1; }
 
 // ------------------------------------------------------------------ refinement heuristics
 static void env_triplet(const char *name, int *m, int dim)
@@ -173,6 +180,138 @@ static FineGrid make_grid(const htb_mesh_geom *g, int which, const int *m)
     return f;
 }
 
+// ------------------------------------------------------------------ host -> device staging of pageable arrays
+// cudaMemcpyAsync from pageable memory goes through the driver's single bounce buffer (about 2 GB/s measured on
+// the B200 boxes).  Large pageable inputs are therefore packed by a few host threads into a ring of pinned
+// chunks (de-interleaving strided columns on the way) and copied chunk by chunk on per-thread streams.
+#define HTB_STAGE_THREADS 8
+#define HTB_STAGE_CHUNK (256 * 1024)          // elements per column and chunk
+struct StagePool {
+    double *pinned[HTB_STAGE_THREADS][2] = {{nullptr}};
+    cudaEvent_t ev[HTB_STAGE_THREADS][2] = {{nullptr}};
+    cudaEvent_t done[HTB_STAGE_THREADS] = {nullptr};
+    cudaStream_t st[HTB_STAGE_THREADS] = {nullptr};
+    int cols = 0;
+    bool ready = false;
+};
+static StagePool g_stage[64];
+
+static int stage_pool_init(int dev, int cols)
+{
+    StagePool &sp = g_stage[dev];
+    if (sp.ready && sp.cols >= cols) return 0;
+    for (int t = 0; t < HTB_STAGE_THREADS; ++t)
+        for (int b = 0; b < 2; ++b) {
+            if (sp.pinned[t][b]) cudaFreeHost(sp.pinned[t][b]);
+            HTB_CUDA(cudaHostAlloc((void **)&sp.pinned[t][b], sizeof(double) * (size_t)HTB_STAGE_CHUNK * cols, cudaHostAllocDefault));
+            if (!sp.ev[t][b]) HTB_CUDA(cudaEventCreateWithFlags(&sp.ev[t][b], cudaEventDisableTiming));
+        }
+    for (int t = 0; t < HTB_STAGE_THREADS; ++t) {
+        if (!sp.st[t]) HTB_CUDA(cudaStreamCreateWithFlags(&sp.st[t], cudaStreamNonBlocking));
+        if (!sp.done[t]) HTB_CUDA(cudaEventCreateWithFlags(&sp.done[t], cudaEventDisableTiming));
+    }
+    sp.cols = cols;
+    sp.ready = true;
+    return 0;
+}
+
+static bool host_pointer_is_pageable(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+// copy cnt strided host columns of n elements into cnt contiguous device arrays; `st` waits for the copies
+static int staged_upload(cudaStream_t st, const double *const *src, int cnt, int64_t stride, int64_t n, double *const *dst)
+{
+    int dev = 0;
+    HTB_CUDA(cudaGetDevice(&dev));
+    if (stage_pool_init(dev, cnt)) return 1;
+    StagePool &sp = g_stage[dev];
+    const int64_t nchunk = (n + HTB_STAGE_CHUNK - 1) / HTB_STAGE_CHUNK;
+    int nthreads = (int)std::min<int64_t>(HTB_STAGE_THREADS, nchunk);
+    const unsigned hw = std::thread::hardware_concurrency();
+    if (hw > 0 && (unsigned)nthreads > hw) nthreads = (int)hw;
+    std::atomic<int> failed(0);
+    auto work = [&](int t) {
+        if (cudaSetDevice(dev) != cudaSuccess) { failed = 1; return; }
+        int k = 0;
+        for (int64_t c = t; c < nchunk; c += nthreads, ++k) {
+            const int b = k & 1;
+            // (a never-recorded event is complete; a buffer used by an earlier upload of this call may still be in flight)
+            if (cudaEventSynchronize(sp.ev[t][b]) != cudaSuccess) { failed = 1; return; }
+            const int64_t i0 = c * HTB_STAGE_CHUNK;
+            const int64_t len = std::min<int64_t>(HTB_STAGE_CHUNK, n - i0);
+            double *buf = sp.pinned[t][b];
+            for (int col = 0; col < cnt; ++col) {
+                const double *s = src[col] + i0 * stride;
+                double *d = buf + (size_t)col * HTB_STAGE_CHUNK;
+                if (stride == 1) memcpy(d, s, sizeof(double) * (size_t)len);
+                else for (int64_t i = 0; i < len; ++i) d[i] = s[i * stride];
+            }
+            for (int col = 0; col < cnt; ++col)
+                if (cudaMemcpyAsync(dst[col] + i0, buf + (size_t)col * HTB_STAGE_CHUNK, sizeof(double) * (size_t)len,
+                                    cudaMemcpyHostToDevice, sp.st[t]) != cudaSuccess) { failed = 1; return; }
+            if (cudaEventRecord(sp.ev[t][b], sp.st[t]) != cudaSuccess) { failed = 1; return; }
+        }
+        if (cudaEventRecord(sp.done[t], sp.st[t]) != cudaSuccess) failed = 1;
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nthreads; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+    if (failed) { htb_set_error("staged host->device upload failed: %s", cudaGetErrorString(cudaGetLastError())); return 1; }
+    for (int t = 0; t < nthreads; ++t) HTB_CUDA(cudaStreamWaitEvent(st, sp.done[t], 0));
+    // the pinned chunks are reused by the next call: make sure this call's copies are done before it returns
+    // (every engine call ends with a stream synchronisation of `st`, which now depends on them)
+    return 0;
+}
+
+// column-wise minimum and maximum of `cols` strided host columns (threads; one pass over memory)
+extern "C" int htb_host_minmax(const double *base, int64_t n, int64_t stride, int32_t cols, double *min_out, double *max_out)
+{
+    HTB_GUARD_BEGIN
+    if (!base || cols < 1 || cols > 8 || !min_out || !max_out || stride < cols) { htb_set_error("htb_host_minmax: bad arguments"); return 1; }
+    for (int c = 0; c < cols; ++c) { min_out[c] = INFINITY; max_out[c] = -INFINITY; }
+    if (n <= 0) return 0;
+    unsigned hw = std::thread::hardware_concurrency();
+    int nt = (int)std::min<int64_t>(hw ? hw : 1, std::min<int64_t>(16, (n + 65535) / 65536));
+    std::vector<double> lo((size_t)nt * 8, INFINITY), hi((size_t)nt * 8, -INFINITY), nan((size_t)nt, 0.0);
+    auto work = [&](int t) {
+        const int64_t a = n * t / nt, b = n * (t + 1) / nt;
+        double l[8], h[8];
+        bool bad = false;
+        for (int c = 0; c < cols; ++c) { l[c] = INFINITY; h[c] = -INFINITY; }
+        for (int64_t i = a; i < b; ++i) {
+            const double *row = base + i * stride;
+            for (int c = 0; c < cols; ++c) {
+                const double v = row[c];
+                if (v < l[c]) l[c] = v;
+                if (v > h[c]) h[c] = v;
+                bad |= (v != v);
+            }
+        }
+        for (int c = 0; c < cols; ++c) { lo[(size_t)t * 8 + c] = l[c]; hi[(size_t)t * 8 + c] = h[c]; }
+        nan[(size_t)t] = bad ? 1.0 : 0.0;
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+    bool anynan = false;
+    for (int t = 0; t < nt; ++t) {
+        anynan |= nan[(size_t)t] != 0.0;
+        for (int c = 0; c < cols; ++c) {
+            if (lo[(size_t)t * 8 + c] < min_out[c]) min_out[c] = lo[(size_t)t * 8 + c];
+            if (hi[(size_t)t * 8 + c] > max_out[c]) max_out[c] = hi[(size_t)t * 8 + c];
+        }
+    }
+    if (anynan) for (int c = 0; c < cols; ++c) { min_out[c] = NAN; max_out[c] = NAN; }   // comparisons with NaN fail, as in numpy
+    return 0;
+    HTB_GUARD_END
+}
+
 // ------------------------------------------------------------------ one engine call
 struct Call {
     cudaStream_t st = nullptr;
@@ -210,6 +349,15 @@ struct Call {
             return 0;
         }
         if (n <= 0) { for (int k = 0; k < cnt; ++k) dst[k] = nullptr; *dstride = 1; return 0; }
+        if (n >= 4 * HTB_STAGE_CHUNK && host_pointer_is_pageable(src[0]) && !getenv("HTB_NO_STAGED_UPLOAD")) {
+            double *bufs[3] = {nullptr, nullptr, nullptr};
+            for (int k = 0; k < cnt; ++k) {
+                if (ws.alloc((void **)&bufs[k], sizeof(double) * (size_t)n)) return 1;
+                dst[k] = bufs[k];
+            }
+            *dstride = 1;
+            return staged_upload(st, src, cnt, stride, n, bufs);
+        }
         // columns of one row-major (n, stride) host matrix (e.g. x, y of an (N, 3) sample): ship the whole
         // block with ONE contiguous copy and keep the stride on the device
         bool interleaved = cnt > 1 && stride >= cnt;
@@ -247,7 +395,11 @@ struct Call {
         if (flags & HTB_FLAG_DEVICE_INPUT) { *dst = src; return 0; }
         double *buf = nullptr;
         if (ws.alloc((void **)&buf, sizeof(double) * (size_t)(n > 0 ? n : 1) * nw)) return 1;
-        if (n > 0) HTB_CUDA(cudaMemcpyAsync(buf, src, sizeof(double) * (size_t)n * nw, cudaMemcpyHostToDevice, st));
+        if (n * nw >= 4 * HTB_STAGE_CHUNK && host_pointer_is_pageable(src) && !getenv("HTB_NO_STAGED_UPLOAD")) {
+            const double *one[1] = {src};
+            double *dstp[1] = {buf};
+            if (staged_upload(st, one, 1, 1, n * nw, dstp)) return 1;
+        } else if (n > 0) HTB_CUDA(cudaMemcpyAsync(buf, src, sizeof(double) * (size_t)n * nw, cudaMemcpyHostToDevice, st));
         *dst = buf;
         return 0;
     }
@@ -416,9 +568,6 @@ static int upload(Call &c, const void *host, size_t bytes, void **dev)
     return 0;
 }
 
-#define HTB_GUARD_BEGIN try {
-#define HTB_GUARD_END                                                          \
-    } catch (const std::exception &e) { htb_set_error("exception: %s", e.what()); return 1; }
 
 // Parameters of the fast queue kernels (Fast3 / FastXYZ) for the squared edges rsq[0..nb), or false if they are
 // not eligible.  The 32-bit keys are (bits(dsq) >> 26) relative to the top squared edge, so every separation a

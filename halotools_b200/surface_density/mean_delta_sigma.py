@@ -24,9 +24,10 @@ def mean_delta_sigma(galaxies, particles, effective_particle_masses,
     # one mass for every particle (the reference broadcasts the scalar, mean_delta_sigma.py:279-281):
     # the engine then needs no per-particle mass array and no per-pair logarithm
     uniform_mass = len(np.atleast_1d(effective_particle_masses)) == 1
+    use_scalar = uniform_mass and not _lib.default_flags & _lib.FLAG_GENERIC
     result = _mean_delta_sigma_process_args(
         galaxies, particles, effective_particle_masses, rp_bins,
-        period, num_threads, approx_cell1_size, approx_cell2_size)
+        period, num_threads, approx_cell1_size, approx_cell2_size, _broadcast_scalar_mass=not use_scalar)
     x1in, y1in, x2in, y2in, w2in = result[0:5]
     rp_bins, period, num_threads, PBCs, approx_cell1_size, approx_cell2_size = result[5:]
     rp_max = np.max(rp_bins)
@@ -42,10 +43,8 @@ def mean_delta_sigma(galaxies, particles, effective_particle_masses,
     first, last = _dist.cell1_range(geom.ncells1)
     c1 = _lib.Columns([x1in, y1in])
     c2 = _lib.Columns([x2in, y2in])
-    m2 = np.ascontiguousarray(w2in[:1] if (uniform_mass and len(w2in) > 0) else w2in, dtype=np.float64)
-    extra = _lib.FLAG_UNIFORM_MASS if (uniform_mass and not _lib.default_flags & _lib.FLAG_GENERIC) else 0
-    if not extra:
-        m2 = np.ascontiguousarray(w2in, dtype=np.float64)
+    extra = _lib.FLAG_UNIFORM_MASS if use_scalar else 0
+    m2 = np.ascontiguousarray(w2in[:1] if use_scalar else w2in, dtype=np.float64)
     g = geom.as_struct()
     rb = np.ascontiguousarray(rp_bins, dtype=np.float64)
     _lib.run_engine(
@@ -63,7 +62,7 @@ def mean_delta_sigma(galaxies, particles, effective_particle_masses,
 
 def _mean_delta_sigma_process_args(
         galaxies, particles, effective_particle_masses, rp_bins,
-        period, num_threads, approx_cell1_size, approx_cell2_size):
+        period, num_threads, approx_cell1_size, approx_cell2_size, _broadcast_scalar_mass=True):
     """Same processing as mean_delta_sigma.py:258-330, including the reference's habit of writing
     the shifted coordinates back into the caller's arrays when ``period`` is None (:263-273)."""
     period, PBCs = get_period(period)
@@ -84,7 +83,12 @@ def _mean_delta_sigma_process_args(
 
     effective_particle_masses = np.atleast_1d(effective_particle_masses)
     if len(effective_particle_masses) == 1:
-        effective_particle_masses = np.zeros(particles.shape[0]) + effective_particle_masses[0]
+        # the reference broadcasts the scalar to one mass per particle (mean_delta_sigma.py:279-281); the engine
+        # takes the scalar itself (HTB_FLAG_UNIFORM_MASS), so the Npart-long array is only built on request
+        if _broadcast_scalar_mass:
+            effective_particle_masses = np.zeros(particles.shape[0]) + effective_particle_masses[0]
+        else:
+            effective_particle_masses = np.asarray(effective_particle_masses, dtype=np.float64)
     else:
         msg = "Must have same number of ``particle_masses`` as particles"
         assert effective_particle_masses.shape[0] == particles.shape[0], msg

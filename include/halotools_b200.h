@@ -139,6 +139,11 @@ int htb_cell1_work(const htb_mesh_geom *mesh,
                    const double *x2, const double *y2, const double *z2, int64_t stride2, int64_t n2,
                    double *work_out, uint32_t flags);
 
+/* Host helper for the front-ends' bounds checks (mock_observables_helpers.py:25-71 enforce_sample_respects_pbcs):
+ * minimum and maximum of `cols` adjacent strided columns of a row-major host matrix, one threaded pass.
+ * NaNs anywhere make every result NaN (so that comparisons fail as they do in numpy).            */
+int htb_host_minmax(const double *base, int64_t n, int64_t stride, int32_t cols, double *min_out, double *max_out);
+
 /* Measured FP64 non-FMA issue rate (DADD/DMUL instr-lanes per second) of the current device. */
 int htb_measure_fp64_rate(double *ops_per_second_out, double *sm_clock_mhz_out);
 
