@@ -221,3 +221,136 @@ def test_delta_sigma_rows_follow_input_order():
 def test_delta_sigma_general_mass_kernel_agrees(name, golden):
     """FLAG_GENERIC routes scalar masses through the per-particle-mass kernel (per-pair log)."""
     compare("mean_delta_sigma", run_gpu(name, _lib.FLAG_GENERIC), golden(name))
+
+
+# ---------------------------------------------------------------- fast queue kernels (round 1, second half)
+def _dup_points(rng, n, L, frac=0.05):
+    """points with exact duplicates and shared coordinates (zero and tiny separations)"""
+    s = rng.uniform(0, L, (n, 3))
+    k = int(n * frac)
+    s[:k] = s[k:2 * k]                     # exact duplicates: dsq == 0
+    s[2 * k:3 * k, 2] = s[3 * k:4 * k, 2]  # same z: dz == 0
+    s[4 * k:5 * k] = s[5 * k:6 * k] + 1e-13  # separations far below the key window
+    return np.ascontiguousarray(np.mod(s, L))
+
+
+@pytest.mark.parametrize("pi_bins", [[0.0, 25.0], [1e-7, 25.0], [0.0, 3.0]])
+def test_fast_xy_z_path_vs_oracle_with_degenerate_separations(pi_bins):
+    rng = np.random.RandomState(11)
+    L = 120.0
+    s1 = _dup_points(rng, 30000, L)
+    s2 = np.vstack([s1[:5000], _dup_points(rng, 25000, L)])
+    rp = np.logspace(-1.5, np.log10(12.0), 11)
+    for a, b in ((s1, s1), (s1, s2)):
+        got = hb.npairs_xy_z(a, b, rp, pi_bins, period=L)
+        assert _lib.last_stats["path"] == 1, "fast (rp, pi) kernel not taken"
+        want = oracle.npairs_xy_z(a, b, rp, pi_bins, period=L, num_threads=4)
+        assert got.dtype == np.int64 and np.array_equal(got, want), (got - want)
+        old = _lib.default_flags
+        _lib.default_flags = _lib.FLAG_GENERIC
+        try:
+            gen = hb.npairs_xy_z(a, b, rp, pi_bins, period=L)
+            assert _lib.last_stats["path"] == 0
+        finally:
+            _lib.default_flags = old
+        assert np.array_equal(gen, want)
+
+
+def test_fast_xy_z_not_taken_for_many_pi_edges():
+    rng = np.random.RandomState(12)
+    s = rng.uniform(0, 80.0, (5000, 3))
+    rp = np.logspace(-1, 1, 8)
+    pi = np.linspace(0, 20, 9)
+    got = hb.npairs_xy_z(s, s, rp, pi, period=80.0)
+    assert _lib.last_stats["path"] == 0
+    assert np.array_equal(got, oracle.npairs_xy_z(s, s, rp, pi, period=80.0, num_threads=4))
+
+
+@pytest.mark.parametrize("wfunc", [1])
+@pytest.mark.parametrize("shared", [True, False])
+def test_fast_marked_path_vs_oracle(wfunc, shared):
+    rng = np.random.RandomState(13)
+    L = 150.0
+    s1 = _dup_points(rng, 40000, L)
+    w1 = rng.uniform(0.5, 1.5, len(s1))
+    if shared:
+        s2, w2 = s1, w1
+    else:
+        s2 = _dup_points(rng, 30000, L)
+        w2 = rng.uniform(-1.0, 2.0, len(s2))
+    rb = np.logspace(-1.2, np.log10(14.0), 13)
+    got = hb.marked_npairs_3d(s1, s2, rb, wfunc, period=L, weights1=w1, weights2=w2)
+    assert _lib.last_stats["path"] == 1, "fast marked kernel not taken"
+    want = oracle.marked_npairs_3d(s1, s2, rb, wfunc, period=L, weights1=w1, weights2=w2, num_threads=4)
+    # float sums in a different order than the reference's serial loop; mixed-sign weights: scale by the sum of |terms|
+    scale = oracle.marked_npairs_3d(s1, s2, rb, wfunc, period=L, weights1=np.abs(w1), weights2=np.abs(w2), num_threads=4)
+    assert np.all(np.abs(got - want) <= 1e-12 * scale), (got - want) / scale
+    # integer weights: exact equality with 6 x the plain counts (reference test: test_marked_npairs_3d.py:261)
+    i1, i2 = np.full(len(s1), 2.0), np.full(len(s2), 3.0)
+    exact = hb.marked_npairs_3d(s1, s2, rb, wfunc, period=L, weights1=i1, weights2=i1 if shared else i2)
+    n = hb.npairs_3d(s1, s2, rb, period=L)
+    assert np.array_equal(exact, (4.0 if shared else 6.0) * n)
+
+
+def test_fast_marked_not_taken_for_other_marks(golden):
+    rng = np.random.RandomState(14)
+    s = rng.uniform(0, 60.0, (3000, 3))
+    w = rng.uniform(0, 1, (3000, 2))
+    rb = np.logspace(-1, 1, 7)
+    got = hb.marked_npairs_3d(s, s, rb, 5, period=60.0, weights1=w, weights2=w)
+    assert _lib.last_stats["path"] == 0
+    want = oracle.marked_npairs_3d(s, s, rb, 5, period=60.0, weights1=w, weights2=w, num_threads=4)
+    assert np.allclose(got, want, rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("nrp", [2, 3, 9, 16])
+def test_fast_delta_sigma_path_vs_oracle(nrp):
+    rng = np.random.RandomState(15)
+    L = 200.0
+    gal = _dup_points(rng, 3000, L)
+    ptcl = np.vstack([gal[:500], _dup_points(rng, 150000, L)])       # particles on top of galaxies: d == 0
+    rp = np.logspace(-1, np.log10(20.0), nrp)
+    got = hb.mean_delta_sigma(gal, ptcl, 2.5, rp, period=L, per_object=True)
+    assert _lib.last_stats["path"] == 1, "fast delta-sigma kernel not taken"
+    want = oracle.mean_delta_sigma(gal, ptcl, 2.5, rp, period=L, per_object=True, num_threads=4)
+    scale = np.max(np.abs(want))
+    assert np.allclose(got, want, rtol=1e-10, atol=1e-12 * scale), np.max(np.abs(got - want)) / scale
+    many = np.full(len(ptcl), 2.5)
+    gen = hb.mean_delta_sigma(gal, ptcl, many, rp, period=L, per_object=True)     # per-particle masses: general kernel
+    assert _lib.last_stats["path"] == 0
+    assert np.allclose(gen, want, rtol=1e-10, atol=1e-12 * scale)
+
+
+def test_fast3_tiles_straddling_reference_cells_keep_counts():
+    """column tiles may straddle reference cells (union windows): same counts as one tile per cell"""
+    import os
+    rng = np.random.RandomState(16)
+    L = 300.0
+    s1 = rng.uniform(0, L, (60000, 3))
+    s2 = rng.uniform(0, L, (90000, 3))
+    rb = np.logspace(-1, np.log10(15.0), 12)
+    a = hb.npairs_3d(s1, s2, rb, period=L)
+    os.environ["HTB_NO_STRADDLE"] = "1"
+    try:
+        b = hb.npairs_3d(s1, s2, rb, period=L)
+    finally:
+        del os.environ["HTB_NO_STRADDLE"]
+    assert np.array_equal(a, b)
+    assert np.array_equal(a, oracle.npairs_3d(s1, s2, rb, period=L, num_threads=4))
+
+
+def test_large_pageable_inputs_take_the_staged_upload():
+    """>= 1M points from ordinary (pageable) numpy memory go through the pinned staging ring"""
+    rng = np.random.RandomState(17)
+    L = 400.0
+    s = rng.uniform(0, L, (1500000, 3))
+    rb = np.logspace(-1, np.log10(8.0), 9)
+    a = hb.npairs_3d(s, s, rb, period=L)
+    import os
+    os.environ["HTB_NO_STAGED_UPLOAD"] = "1"
+    try:
+        b = hb.npairs_3d(s, s, rb, period=L)
+    finally:
+        del os.environ["HTB_NO_STAGED_UPLOAD"]
+    assert np.array_equal(a, b)
+    assert a[0] >= len(s)

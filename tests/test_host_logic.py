@@ -221,3 +221,34 @@ def test_two_rank_sharding_over_gloo(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "ok" in o
+
+
+def test_host_minmax_helper_matches_numpy():
+    """htb_host_minmax is pure host code of the library (no CUDA call): usable without a GPU"""
+    import ctypes
+    from halotools_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.RandomState(5)
+    a = rng.uniform(-3, 7, (300000, 3))
+    lo, hi = (ctypes.c_double * 3)(), (ctypes.c_double * 3)()
+    assert lib.htb_host_minmax(ctypes.c_void_p(a.ctypes.data), ctypes.c_int64(len(a)), ctypes.c_int64(3),
+                               ctypes.c_int32(3), lo, hi) == 0
+    assert list(lo) == list(a.min(axis=0)) and list(hi) == list(a.max(axis=0))
+    a[1234, 1] = np.nan
+    assert lib.htb_host_minmax(ctypes.c_void_p(a.ctypes.data), ctypes.c_int64(len(a)), ctypes.c_int64(3),
+                               ctypes.c_int32(3), lo, hi) == 0
+    assert all(np.isnan(v) for v in lo) and all(np.isnan(v) for v in hi)
+
+
+def test_pbc_check_messages_on_large_samples():
+    from halotools_b200.helpers import enforce_sample_respects_pbcs
+    s = np.random.RandomState(6).uniform(0, 10.0, (1200000, 3))
+    enforce_sample_respects_pbcs(s[:, 0], s[:, 1], s[:, 2], [10.0, 10.0, 10.0])
+    s[77, 2] = -0.5
+    with pytest.raises(ValueError) as err:
+        enforce_sample_respects_pbcs(s[:, 0], s[:, 1], s[:, 2], [10.0, 10.0, 10.0])
+    assert "negative values" in str(err.value)
+    s[77, 2] = 10.5
+    with pytest.raises(ValueError) as err:
+        enforce_sample_respects_pbcs(s[:, 0], s[:, 1], s[:, 2], [10.0, 10.0, 10.0])
+    assert "zperiod" in str(err.value)
