@@ -264,8 +264,17 @@ def run_gpu(args):
         i_rr = int(np.argmax(stats_acc["count_evaluated"]))
         ach = stats_acc["count_evaluated"][i_rr] * OPS_PER_PAIR / (stats_acc["count_ms"][i_rr] * 1e-3) / 1e12
         peak = rate / 1e12
+        traffic = None
+        try:
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel, from the committed ncu capture
+            with open(os.path.join(ROOT, "profiles", "r01_fast3_traffic.json")) as fh:
+                tj = json.load(fh)
+            traffic = int(tj["dram_bytes_read"]) + int(tj["dram_bytes_write"])
+        except Exception:
+            traffic = None
         roofline = {"bound": "fp64_issue", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                    "traffic": None, "kernel": "k_count<Fast3> (RR launch)",
+                    "traffic": traffic, "traffic_unit": "bytes per launch (ncu --set full, profiles/r01_fast3_final_ncu.txt)",
+                    "kernel": "k_count<Fast3> (RR launch)",
                     "peak_source": "htb_measure_fp64_rate: DADD/DMUL non-FMA issue rate measured live on this GPU "
                                    "(MEASURED_PEAKS.json has no FP64 entry)",
                     "pairs_evaluated_per_launch": stats_acc["count_evaluated"][i_rr],
