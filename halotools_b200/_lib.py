@@ -19,9 +19,13 @@ FLAG_GENERIC = 4
 FLAG_NO_TMA = 8
 FLAG_NO_SYM = 16
 FLAG_UNIFORM_MASS = 32
+FLAG_COLUMN_SUM = 64
+FLAG_CACHE_SAMPLE1 = 128
+FLAG_CACHE_SAMPLE2 = 256
 
 EXPORTS = (
-    "htb_last_error", "htb_abi_version", "htb_device_count", "htb_set_device", "htb_set_stream",
+    "htb_last_error", "htb_abi_version", "htb_device_count", "htb_set_device", "htb_set_stream", "htb_set_shard",
+    "htb_cache_begin", "htb_cache_end",
     "htb_npairs_3d_engine", "htb_npairs_xy_z_engine", "htb_npairs_s_mu_engine",
     "htb_marked_npairs_3d_engine", "htb_mean_delta_sigma_engine",
     "htb_mesh_cell_ids", "htb_mesh_cell_id_indices", "htb_cell1_work", "htb_measure_fp64_rate",
@@ -98,6 +102,43 @@ def set_device(index):
     check(require_gpu().htb_set_device(int(index)))
 
 
+def set_shard(rank, world):
+    """This thread's engine calls count only rank's work-balanced share of the mesh1 cells (host state only)."""
+    check(load().htb_set_shard(int(rank), int(world)))
+
+
+class upload_cache(object):
+    """Context manager: host samples uploaded by the engine calls inside stay on the device until exit
+    (htb_cache_begin / htb_cache_end).  Re-entrant (only the outermost level frees)."""
+    _depth = 0
+
+    def __enter__(self):
+        if library_present():
+            if upload_cache._depth == 0:
+                load().htb_cache_begin()
+            upload_cache._depth += 1
+            self._on = True
+        else:
+            self._on = False
+        return self
+
+    def __exit__(self, *exc):
+        if self._on:
+            upload_cache._depth -= 1
+            if upload_cache._depth == 0:
+                load().htb_cache_end()
+        return False
+
+
+def cache_flags(c1, c2, caller_owned):
+    """Engine flags that let the samples of this call take part in the upload cache: only inside an
+    ``upload_cache()`` block, and only for pointers into the caller's own arrays (``caller_owned``: the
+    front-end made no shifted / converted temporary, whose address could be recycled)."""
+    if upload_cache._depth == 0 or not caller_owned:
+        return 0
+    return (FLAG_CACHE_SAMPLE1 if c1.stable else 0) | (FLAG_CACHE_SAMPLE2 if c2.stable else 0)
+
+
 def _dp(a):
     return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
 
@@ -111,6 +152,7 @@ class Columns(object):
 
     def __init__(self, cols):
         self.device = all(getattr(c, "is_cuda", False) for c in cols)
+        self.stable = False       # True: the pointers are views of the caller's own float64 array (no temporary copy)
         if self.device:
             # torch CUDA tensors (column views of an (N, ndim) float64 tensor): pass device pointers
             import torch
@@ -134,6 +176,7 @@ class Columns(object):
             ok = len(strides) == 1 and list(strides)[0] % 8 == 0 and list(strides)[0] > 0
             if ok:
                 stride = list(strides)[0] // 8
+        self.stable = bool(ok and n > 0)
         if not ok or n == 0:
             cols = [np.ascontiguousarray(c, dtype=np.float64) for c in cols]
             stride = 1

@@ -49,6 +49,50 @@ extern "C" int htb_set_stream(void *s)
     return 0;
 }
 
+// Multi-GPU shard of the calling thread's engine calls (htb_set_shard): rank r of `world` ranks.
+static thread_local int g_shard_rank = 0, g_shard_world = 1;
+extern "C" int htb_set_shard(int rank, int world)
+{
+    if (world < 1 || rank < 0 || rank >= world) { htb_set_error("htb_set_shard: need 0 <= rank < world"); return 1; }
+    g_shard_rank = rank;
+    g_shard_world = world;
+    return 0;
+}
+
+// Upload cache (htb_cache_begin / htb_cache_end): between the two calls the coordinate arrays a thread's engine
+// calls bring to the device stay there, keyed by (host pointers, stride, count), so the DD, DR and RR counts of one
+// tpcf() call move every sample across PCIe once (the reference re-gathers every sample in every call,
+// tpcf.py:76-113,164-205).  The caller promises not to modify the arrays in between.
+struct UploadEnt {
+    const double *src[3];
+    int cnt;
+    int64_t stride, n;
+    const double *dev[3];
+    int64_t dstride;
+    void *blocks[3];
+    int nblocks;
+    cudaStream_t st;
+};
+static thread_local bool g_cache_on = false;
+static thread_local std::vector<UploadEnt> *g_cache = nullptr;
+
+extern "C" int htb_cache_begin(void)
+{
+    if (!g_cache) g_cache = new std::vector<UploadEnt>();
+    g_cache_on = true;
+    return 0;
+}
+extern "C" int htb_cache_end(void)
+{
+    g_cache_on = false;
+    if (g_cache) {
+        for (auto &e : *g_cache)
+            for (int k = 0; k < e.nblocks; ++k) cudaFreeAsync(e.blocks[k], e.st);
+        g_cache->clear();
+    }
+    return 0;
+}
+
 static bool g_pool_ready[64] = {false};
 
 static int get_stream(cudaStream_t *out)
@@ -325,6 +369,9 @@ struct Call {
     unsigned int *ctr = nullptr;          // [0] tile counter, [1] tiles redone, [2..3] pairs evaluated (u64)
     int64_t max_tiles = 0;
     int64_t first_cell = 0, last_cell = 0;  // this call's range of reference mesh1 cells
+    long long *range_dev = nullptr;         // device {first, last}: this rank's shard of that range (htb_set_shard)
+    double *work_dev = nullptr;             // predicted work per reference mesh1 cell (computed once per call)
+    int64_t nc1 = 0;
     uint32_t flags = 0;
 
     ~Call()
@@ -341,7 +388,8 @@ struct Call {
         return 0;
     }
     // bring `cnt` arrays of n elements (common element stride) to the device; returns device pointers + stride
-    int stage_coords(const double *const *src, int cnt, int64_t stride, int64_t n, const double **dst, int64_t *dstride)
+    int stage_coords(const double *const *src, int cnt, int64_t stride, int64_t n, const double **dst, int64_t *dstride,
+                     bool cacheable = false)
     {
         if (flags & HTB_FLAG_DEVICE_INPUT) {
             for (int k = 0; k < cnt; ++k) dst[k] = src[k];
@@ -349,14 +397,43 @@ struct Call {
             return 0;
         }
         if (n <= 0) { for (int k = 0; k < cnt; ++k) dst[k] = nullptr; *dstride = 1; return 0; }
+        UploadEnt ent{};
+        const bool caching = cacheable && g_cache_on && g_cache;
+        if (caching) {
+            for (auto &e : *g_cache) {
+                bool hit = e.cnt == cnt && e.stride == stride && e.n == n && e.st == st;
+                for (int k = 0; k < cnt && hit; ++k) hit = e.src[k] == src[k];
+                if (hit) { for (int k = 0; k < cnt; ++k) dst[k] = e.dev[k]; *dstride = e.dstride; return 0; }
+            }
+            ent.cnt = cnt; ent.stride = stride; ent.n = n; ent.st = st;
+            for (int k = 0; k < cnt; ++k) ent.src[k] = src[k];
+        }
+        // device blocks: owned by the call's workspace, or by the upload cache when it is on
+        auto dev_alloc = [&](void **p, size_t bytes) -> int {
+            if (!caching) return ws.alloc(p, bytes);
+            bytes = (bytes + 255) & ~(size_t)255;
+            cudaError_t e = cudaMallocAsync(p, bytes, st);
+            if (e != cudaSuccess) { htb_set_error("cudaMallocAsync(%zu bytes) failed: %s", bytes, cudaGetErrorString(e)); return 1; }
+            ent.blocks[ent.nblocks++] = *p;
+            return 0;
+        };
+        auto done = [&]() -> int {
+            if (caching) {
+                for (int k = 0; k < cnt; ++k) ent.dev[k] = dst[k];
+                ent.dstride = *dstride;
+                g_cache->push_back(ent);
+            }
+            return 0;
+        };
         if (n >= 4 * HTB_STAGE_CHUNK && host_pointer_is_pageable(src[0]) && !getenv("HTB_NO_STAGED_UPLOAD")) {
             double *bufs[3] = {nullptr, nullptr, nullptr};
             for (int k = 0; k < cnt; ++k) {
-                if (ws.alloc((void **)&bufs[k], sizeof(double) * (size_t)n)) return 1;
+                if (dev_alloc((void **)&bufs[k], sizeof(double) * (size_t)n)) return 1;
                 dst[k] = bufs[k];
             }
             *dstride = 1;
-            return staged_upload(st, src, cnt, stride, n, bufs);
+            if (staged_upload(st, src, cnt, stride, n, bufs)) return 1;
+            return done();
         }
         // columns of one row-major (n, stride) host matrix (e.g. x, y of an (N, 3) sample): ship the whole
         // block with ONE contiguous copy and keep the stride on the device
@@ -370,15 +447,15 @@ struct Call {
         if (interleaved) {
             double *buf = nullptr;
             const size_t len = (size_t)(n - 1) * (size_t)stride + (size_t)maxoff + 1;
-            if (ws.alloc((void **)&buf, sizeof(double) * len)) return 1;
+            if (dev_alloc((void **)&buf, sizeof(double) * len)) return 1;
             HTB_CUDA(cudaMemcpyAsync(buf, src[0], sizeof(double) * len, cudaMemcpyHostToDevice, st));
             for (int k = 0; k < cnt; ++k) dst[k] = buf + (src[k] - src[0]);
             *dstride = stride;
-            return 0;
+            return done();
         }
         for (int k = 0; k < cnt; ++k) {
             double *buf = nullptr;
-            if (ws.alloc((void **)&buf, sizeof(double) * (size_t)n)) return 1;
+            if (dev_alloc((void **)&buf, sizeof(double) * (size_t)n)) return 1;
             if (stride == 1)
                 HTB_CUDA(cudaMemcpyAsync(buf, src[k], sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
             else
@@ -387,7 +464,7 @@ struct Call {
             dst[k] = buf;
         }
         *dstride = 1;
-        return 0;
+        return done();
     }
     int stage_rows(const double *src, int64_t n, int nw, const double **dst)
     {
@@ -429,9 +506,9 @@ struct Call {
         const double *dw1 = nullptr, *dw2 = nullptr;
         bool same = (n1 == n2 && stride1 == stride2);
         for (int d = 0; d < dim && same; ++d) same = (c1[d] == c2[d]);
-        if (stage_coords(c1, dim, stride1, n1, d1, &ds1)) return 1;
+        if (stage_coords(c1, dim, stride1, n1, d1, &ds1, (fl & HTB_FLAG_CACHE_SAMPLE1) != 0)) return 1;
         if (same) { for (int d = 0; d < dim; ++d) d2[d] = d1[d]; ds2 = ds1; }
-        else if (stage_coords(c2, dim, stride2, n2, d2, &ds2)) return 1;
+        else if (stage_coords(c2, dim, stride2, n2, d2, &ds2, (fl & HTB_FLAG_CACHE_SAMPLE2) != 0)) return 1;
         if (stage_rows(w1, n1, nw, &dw1)) return 1;
         if (w2 == w1 && same) dw2 = dw1;
         else if (stage_rows(w2, n2, nw, &dw2)) return 1;
@@ -467,6 +544,14 @@ struct Call {
             G.maxfine = m1[Fd];           // a tile is never longer than one reference cell
             if (const char *e = getenv("HTB_MAXFINE")) { const int v = atoi(e); if (v >= 1) G.maxfine = v; }
             G.cs1f = g->cell1_size[Fd];
+            // slicing a tile only pays if a slice still holds enough pair evaluations to amortise the per-item
+            // latencies (tile fetch, point loads, first TMA): about 2e5 pairs per item
+            double est = (double)tile * (double)(n2 > 0 ? n2 : 1);
+            for (int d = 0; d < dim; ++d) est *= std::min(1.0, 2.6 * g->search[d] / g->period[d]);
+            G.maxslices = clampi(est / 2.0e5, 1, 16);
+            if (const char *e = getenv("HTB_MAXSLICES")) { const int v = atoi(e); if (v >= 1 && v <= 64) G.maxslices = v; }
+            G.items_per_warp = HTB_ITEMS_PER_WARP;
+            if (const char *e = getenv("HTB_ITEMS_PER_WARP")) { const int v = atoi(e); if (v >= 1 && v <= 1024) G.items_per_warp = v; }
         }
         // ---- walker geometry
         G.dim = dim;
@@ -495,7 +580,15 @@ struct Call {
         // ---- tiles + counters
         uint2 *tiles = nullptr;
         uint32_t *ntiles_dev = nullptr;
-        if (htb_build_tiles(st, ws, G, s1, first_cell1, last_cell1, &tiles, &ntiles_dev, &max_tiles, &launches)) return 1;
+        if (g_shard_world > 1) {
+            // this rank's share of [first_cell1, last_cell1), cut by predicted work on the device (no host sync)
+            double *balance_dev = nullptr;
+            if (htb_reference_work(st, ws, G, s1, s2, &work_dev, &balance_dev, &nc1, &launches)) return 1;
+            if (ws.alloc((void **)&range_dev, 2 * sizeof(long long))) return 1;
+            const int64_t lo = first_cell1 < 0 ? 0 : first_cell1, hi = last_cell1 > nc1 ? nc1 : last_cell1;
+            if (htb_shard_range(st, balance_dev, lo, hi, g_shard_rank, g_shard_world, range_dev, &launches)) return 1;
+        }
+        if (htb_build_tiles(st, ws, G, s1, first_cell1, last_cell1, range_dev, &tiles, &ntiles_dev, &max_tiles, &launches)) return 1;
         if (ws.alloc((void **)&ctr, 64)) return 1;
         HTB_CUDA(cudaMemsetAsync(ctr, 0, 64, st));
         for (int d = 0; d < 3; ++d) { A.c1[d] = s1.c[d]; A.c2[d] = s2.c[d]; }
@@ -506,6 +599,10 @@ struct Call {
         A.tile_counter = ctr;
         A.tiles_redone = ctr + 1;
         A.pairs_evaluated = (unsigned long long *)(ctr + 2);
+        A.redo_ctr = ctr + 4;
+        A.redo_cap = getenv("HTB_REDO_INPLACE") ? 0u : (1u << 16);
+        A.redo_ent = nullptr;
+        if (A.redo_cap && ws.alloc((void **)&A.redo_ent, sizeof(uint2) * (size_t)A.redo_cap)) return 1;
         HTB_CUDA(cudaEventRecord(ev[2], st));
         return 0;
     }
@@ -515,10 +612,10 @@ struct Call {
         unsigned int h[4] = {0, 0, 0, 0};
         uint32_t ntiles = 0;
         std::vector<double> work;
-        int64_t nc1 = 0;
+        long long range_h[2] = {(long long)first_cell, (long long)last_cell};
         if (stats) {
-            double *work_dev = nullptr;
-            if (htb_reference_work(st, ws, G, s1, s2, &work_dev, &nc1, &launches)) return 1;
+            if (!work_dev && htb_reference_work(st, ws, G, s1, s2, &work_dev, nullptr, &nc1, &launches)) return 1;
+            if (range_dev) HTB_CUDA(cudaMemcpyAsync(range_h, range_dev, sizeof(range_h), cudaMemcpyDeviceToHost, st));
             work.resize((size_t)nc1);
             HTB_CUDA(cudaMemcpyAsync(work.data(), work_dev, sizeof(double) * (size_t)nc1, cudaMemcpyDeviceToHost, st));
             HTB_CUDA(cudaMemcpyAsync(h, ctr, sizeof(h), cudaMemcpyDeviceToHost, st));
@@ -532,7 +629,7 @@ struct Call {
             memcpy(&pe, &h[2], sizeof(pe));
             stats->pairs_evaluated = (double)pe;
             double wr = 0.0;
-            for (int64_t c = (first_cell > 0 ? first_cell : 0); c < nc1 && c < last_cell; ++c) wr += work[(size_t)c];
+            for (int64_t c = (range_h[0] > 0 ? range_h[0] : 0); c < nc1 && c < range_h[1]; ++c) wr += work[(size_t)c];
             stats->pairs_reference = wr;
             cudaEventElapsedTime(&stats->ms_h2d, ev[0], ev[1]);
             cudaEventElapsedTime(&stats->ms_mesh, ev[1], ev[2]);
@@ -822,6 +919,38 @@ extern "C" int htb_marked_npairs_3d_engine(const htb_mesh_geom *mesh,
 }
 
 // ------------------------------------------------------------------ mean_delta_sigma
+// Column sums of the (n, nbin) per-object rows in a fixed order (HTB_FLAG_COLUMN_SUM): block b sums rows
+// b, b + gridDim.x, ... per column, a second launch adds the per-block partial sums.
+__global__ void __launch_bounds__(256) k_colsum_partial(const double *__restrict__ rows, long long n, int nbin,
+                                                        double *__restrict__ partial)
+{
+    __shared__ double sh[256];
+    const long long total = n * nbin;
+    // thread t of block b owns column (t % nbin) for rows b * rpb + t / nbin + i * rows_per_pass
+    const int rows_per_block = 256 / nbin;             // nbin <= 256 checked on the host
+    const int r = threadIdx.x / nbin, k = threadIdx.x % nbin;
+    double s = 0.0;
+    if (r < rows_per_block)
+        for (long long row = (long long)blockIdx.x * rows_per_block + r; row < n; row += (long long)gridDim.x * rows_per_block)
+            s += rows[row * nbin + k];
+    (void)total;
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x < nbin) {
+        double t = 0.0;
+        for (int q = 0; q < rows_per_block; ++q) t += sh[q * nbin + threadIdx.x];
+        partial[(size_t)blockIdx.x * nbin + threadIdx.x] = t;
+    }
+}
+__global__ void k_colsum_final(const double *__restrict__ partial, int nblocks, int nbin, double *__restrict__ out)
+{
+    const int k = threadIdx.x;
+    if (k >= nbin) return;
+    double t = 0.0;
+    for (int b = 0; b < nblocks; ++b) t += partial[(size_t)b * nbin + k];
+    out[k] = t;
+}
+
 extern "C" int htb_mean_delta_sigma_engine(const htb_mesh_geom *mesh,
                                            const double *x1, const double *y1, int64_t stride1, int64_t n1,
                                            const double *x2, const double *y2, int64_t stride2, const double *m2, int64_t n2,
@@ -896,7 +1025,18 @@ extern "C" int htb_mean_delta_sigma_engine(const htb_mesh_geom *mesh,
         gp.max0 = mass;
         if (htb_launch_gen(c.st, uniform ? 5 : 4, c.G, c.A, gp, &c.launches)) return 1;
     }
-    if (n1 > 0) HTB_CUDA(cudaMemcpyAsync(out, out_dev, sizeof(double) * (size_t)n1 * nbin, cudaMemcpyDeviceToHost, c.st));
+    if (flags & HTB_FLAG_COLUMN_SUM) {
+        if (nbin > 256) { htb_set_error("HTB_FLAG_COLUMN_SUM supports at most 256 bins"); return 1; }
+        const int nblocks = 592;
+        double *partial = nullptr, *sums = nullptr;
+        if (c.ws.alloc((void **)&partial, sizeof(double) * (size_t)nblocks * nbin)) return 1;
+        if (c.ws.alloc((void **)&sums, sizeof(double) * (size_t)nbin)) return 1;
+        k_colsum_partial<<<nblocks, 256, 0, c.st>>>(out_dev, (long long)(n1 > 0 ? n1 : 0), nbin, partial);
+        k_colsum_final<<<1, 256, 0, c.st>>>(partial, nblocks, nbin, sums);
+        c.launches += 2;
+        HTB_CUDA(cudaGetLastError());
+        HTB_CUDA(cudaMemcpyAsync(out, sums, sizeof(double) * (size_t)nbin, cudaMemcpyDeviceToHost, c.st));
+    } else if (n1 > 0) HTB_CUDA(cudaMemcpyAsync(out, out_dev, sizeof(double) * (size_t)n1 * nbin, cudaMemcpyDeviceToHost, c.st));
     return c.finish(stats, fast ? 1 : 0);
     HTB_GUARD_END
 }
@@ -968,7 +1108,7 @@ extern "C" int htb_cell1_work(const htb_mesh_geom *mesh,
     if (c.setup(mesh, 1, false, c1, stride1, n1, nullptr, c2, stride2, n2, nullptr, 0, false, 0, 0, flags)) return 1;
     double *work_dev = nullptr;
     int64_t nc1 = 0;
-    if (htb_reference_work(c.st, c.ws, c.G, c.s1, c.s2, &work_dev, &nc1, &c.launches)) return 1;
+    if (htb_reference_work(c.st, c.ws, c.G, c.s1, c.s2, &work_dev, nullptr, &nc1, &c.launches)) return 1;
     HTB_CUDA(cudaMemcpyAsync(work_out, work_dev, sizeof(double) * (size_t)nc1, cudaMemcpyDeviceToHost, c.st));
     HTB_CUDA(cudaStreamSynchronize(c.st));
     return 0;

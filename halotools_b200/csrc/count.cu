@@ -52,49 +52,109 @@ __device__ __forceinline__ uint32_t htb_column_tiles(const uint32_t *__restrict_
 }
 
 __global__ void k_seg_tiles(const uint32_t *__restrict__ off1, WalkGeom G, int64_t ncol,
-                            int64_t first_cell1, int64_t last_cell1, uint32_t *__restrict__ ntile)
+                            int64_t first_cell1, int64_t last_cell1, const long long *__restrict__ range,
+                            uint32_t *__restrict__ ntile)
 {
+    if (range) { first_cell1 = range[0]; last_cell1 = range[1]; }      // this rank's shard, cut on the device
     for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < ncol; s += (int64_t)gridDim.x * blockDim.x)
         ntile[s] = htb_column_tiles(off1, G, s, first_cell1, last_cell1, nullptr, 0u);
 }
 
 __global__ void k_fill_tiles(const uint32_t *__restrict__ off1, WalkGeom G, int64_t ncol,
-                             int64_t first_cell1, int64_t last_cell1,
+                             int64_t first_cell1, int64_t last_cell1, const long long *__restrict__ range,
                              const uint32_t *__restrict__ ntile, const uint32_t *__restrict__ tbase,
                              uint2 *__restrict__ tiles)
 {
+    if (range) { first_cell1 = range[0]; last_cell1 = range[1]; }
     for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < ncol; s += (int64_t)gridDim.x * blockDim.x)
         if (ntile[s]) (void)htb_column_tiles(off1, G, s, first_cell1, last_cell1, tiles, tbase[s]);
 }
 
-// pairs the reference loop nest visits, per reference cell1 (W_ref)
+// pairs the reference loop nest visits, per reference cell1 (W_ref), and - for the multi-GPU cut -
+// the pairs this engine expects to evaluate: in symmetric mode a zero-shift neighbour cell is evaluated only from
+// the cell with the smaller id (half of the own cell), wrapped neighbours from both sides.
 __global__ void k_wref(const uint32_t *__restrict__ rc1, const uint32_t *__restrict__ rc2, WalkGeom G,
-                       int64_t ncell1, double *__restrict__ work)
+                       int64_t ncell1, double *__restrict__ work, double *__restrict__ balance)
 {
     for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < ncell1; c += (int64_t)gridDim.x * blockDim.x) {
         const uint32_t n1 = rc1[c];
-        double w = 0.0;
+        double w = 0.0, wb = 0.0;
         if (n1) {
             int a[3] = {0, 0, 0};
             int64_t rem = c;
             for (int d = G.dim - 1; d >= 0; --d) { a[d] = (int)(rem % G.nd1[d]); rem /= G.nd1[d]; }
             int lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1};
             for (int d = 0; d < G.dim; ++d) { lo[d] = a[d] * G.per[d] - G.cover[d]; hi[d] = (a[d] + 1) * G.per[d] + G.cover[d]; }
-            unsigned long long s = 0;
+            unsigned long long s = 0, s2 = 0;          // s2: twice the symmetric-mode pairs
             for (int ux = lo[0]; ux < hi[0]; ++ux) {
-                const int wx = ux - floor_div(ux, G.nd2[0]) * G.nd2[0];
+                const int kx = floor_div(ux, G.nd2[0]), wx = ux - kx * G.nd2[0];
                 for (int uy = lo[1]; uy < hi[1]; ++uy) {
-                    const int wy = uy - floor_div(uy, G.nd2[1]) * G.nd2[1];
-                    if (G.dim == 2) { s += rc2[(int64_t)wx * G.nd2[1] + wy]; continue; }
+                    const int ky = floor_div(uy, G.nd2[1]), wy = uy - ky * G.nd2[1];
+                    if (G.dim == 2) {
+                        const int64_t c2 = (int64_t)wx * G.nd2[1] + wy;
+                        const unsigned long long n2 = rc2[c2];
+                        s += n2;
+                        s2 += ((kx | ky) != 0 || c2 > c) ? 2 * n2 : (c2 == c ? n2 : 0);
+                        continue;
+                    }
                     for (int uz = lo[2]; uz < hi[2]; ++uz) {
-                        const int wz = uz - floor_div(uz, G.nd2[2]) * G.nd2[2];
-                        s += rc2[((int64_t)wx * G.nd2[1] + wy) * G.nd2[2] + wz];
+                        const int kz = floor_div(uz, G.nd2[2]), wz = uz - kz * G.nd2[2];
+                        const int64_t c2 = ((int64_t)wx * G.nd2[1] + wy) * G.nd2[2] + wz;
+                        const unsigned long long n2 = rc2[c2];
+                        s += n2;
+                        s2 += ((kx | ky | kz) != 0 || c2 > c) ? 2 * n2 : (c2 == c ? n2 : 0);
                     }
                 }
             }
             w = (double)n1 * (double)s;
+            wb = G.sym ? (double)n1 * (double)s2 : 2.0 * w;
         }
         work[c] = w;
+        if (balance) balance[c] = wb;
+    }
+}
+
+// Multi-GPU shard of a call (htb_set_shard): rank r of `world` takes the contiguous run of reference mesh1 cells of
+// [first, last) whose exclusive cumulative predicted work lies in [total * r / world, total * (r + 1) / world) - the
+// reference's contiguous cell ranges (mesh_helpers.py:183-221) with the cut points moved so that every rank gets
+// the same number of pair evaluations instead of the same number of cells.  One block; range_out = {first, last}.
+__global__ void __launch_bounds__(1024) k_shard_range(const double *__restrict__ work, long long first, long long last,
+                                                       int rank, int world, long long *__restrict__ range_out)
+{
+    __shared__ double part[1024];
+    __shared__ long long below[2];
+    const int t = threadIdx.x;
+    const long long n = last > first ? last - first : 0;
+    const long long per = (n + 1023) / 1024;
+    const long long a = first + min(n, per * t), b = first + min(n, per * (t + 1));
+    double s = 0.0;
+    for (long long c = a; c < b; ++c) s += work[c];
+    part[t] = s;
+    if (t < 2) below[t] = 0;
+    __syncthreads();
+    // exclusive scan of the 1024 partial sums (the values are integers below 2^53: the sums are exact, so
+    // the order of the additions does not matter)
+    for (int o = 1; o < 1024; o <<= 1) {
+        const double v = t >= o ? part[t - o] : 0.0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    const double total = part[1023];
+    double cum = part[t] - s;
+    const double lo = total * (double)rank / (double)world, hi = total * (double)(rank + 1) / (double)world;
+    long long nlo = 0, nhi = 0;
+    for (long long c = a; c < b; ++c) {
+        nlo += cum < lo;              // cells that belong to lower ranks
+        nhi += cum < hi;              // ... to this rank or lower ranks
+        cum += work[c];
+    }
+    if (nlo) atomicAdd((unsigned long long *)&below[0], (unsigned long long)nlo);
+    if (nhi) atomicAdd((unsigned long long *)&below[1], (unsigned long long)nhi);
+    __syncthreads();
+    if (t == 0) {
+        range_out[0] = first + below[0];
+        range_out[1] = rank + 1 >= world ? last : first + below[1];
     }
 }
 
@@ -131,12 +191,61 @@ k_count(const __grid_constant__ WalkGeom G, const __grid_constant__ WalkArrays A
     unsigned long long pairs = 0;
     unsigned int redone = 0;
     const int ntiles = A.ntiles_dev[0];
+    // Work items: when there are too few tiles to keep every resident warp busy to the end (small samples, one
+    // rank's shard of a multi-GPU count, clustered sample1), every tile is cut into K SLICES of its sample2
+    // columns; slices of one tile are independent work items (counts and per-object sums are additive).
+    int K = 1;
+    {
+        const long long target = (long long)gridDim.x * V::WARPS * G.items_per_warp;
+        if (ntiles > 0 && ntiles < target) K = (int)min((long long)(G.sym ? min(G.maxslices, 8) : G.maxslices), (target + ntiles - 1) / ntiles);
+        if (K < 1) K = 1;
+    }
+    const int nitems = ntiles * K;
 
+    // One work item: slice `slice` of `nsl` of tile t.  redo_sub < 0: the normal evaluation (both weight passes in
+    // symmetric mode).  A fast kernel that finds it cannot decide a tile from its 32-bit keys asks for an exact
+    // re-evaluation (tile_end returns true): that re-evaluation is many times slower per pair, so it is not done
+    // in place but cut into HTB_REDO_SPLIT finer slices that go to a second queue served by every warp that runs
+    // out of ordinary items - otherwise a single late redo is the tail of the whole launch.
+    // redo_sub >= 0: such an exact re-evaluation of weight pass redo_sub.
+    bool main_done = false;
     while (true) {
-        int t = 0;
-        if (lane == 0) t = (int)atomicAdd(A.tile_counter, 1u);
-        t = __shfl_sync(HTB_FULL, t, 0);
-        if (t >= ntiles) break;
+        // ---- next work item: the ordinary queue first, then the redo queue (entries published by any warp; done
+        // when every ordinary item has completed and the queue is drained: reserved == published == taken)
+        int t = 0, slice = 0, nsl = K, redo_sub = -1;
+        if (!main_done) {
+            if (lane == 0) t = (int)atomicAdd(A.tile_counter, 1u);
+            t = __shfl_sync(HTB_FULL, t, 0);
+            if (t >= nitems) main_done = true;
+            else { slice = t % K; t /= K; }
+        }
+        if (main_done) {
+            if (A.redo_cap < HTB_REDO_SPLIT) break;
+            unsigned got = 0xffffffffu;
+            int quit = 0;
+            if (lane == 0) {
+                volatile unsigned *c = A.redo_ctr;
+                while (true) {
+                    const unsigned done = c[3];               // read first: a finished item has published its entries
+                    __threadfence();
+                    const unsigned reserved = c[0], published = c[1], taken = c[2];
+                    if (taken < published) {
+                        if (atomicCAS(A.redo_ctr + 2, taken, taken + 1u) == taken) { got = taken; break; }
+                        continue;
+                    }
+                    // nothing to take: finished only if no ordinary item is still running (it could publish more)
+                    // and every reservation has been published
+                    if (done >= (unsigned)nitems && published == reserved) { quit = 1; break; }
+                    __nanosleep(500);
+                }
+            }
+            quit = __shfl_sync(HTB_FULL, quit, 0);
+            if (quit) break;
+            got = __shfl_sync(HTB_FULL, got, 0);
+            __threadfence();
+            const uint2 e = A.redo_ent[got];
+            t = (int)e.x; slice = (int)(e.y & 0xffffffu); nsl = K * HTB_REDO_SPLIT; redo_sub = (int)(e.y >> 24);
+        }
         const uint2 td = A.tiles[t];
         const uint32_t start = td.x;
         const int cnt = (int)(td.y >> 24);
@@ -176,17 +285,41 @@ k_count(const __grid_constant__ WalkGeom G, const __grid_constant__ WalkArrays A
         const int nref = htb_ref_digitize(__shfl_sync(HTB_FULL, p[PPL - 1][F], (PPL & 1) ? 31 : 0), G.cs1f, G.nd1[F]) - fs[F] + 1;
         const int nsub = G.sym ? 2 : 1;
 #pragma unroll 1
-        for (int sub = 0; sub < nsub; ++sub) {
+        for (int sub = (redo_sub < 0 ? 0 : redo_sub); sub < (redo_sub < 0 ? nsub : redo_sub + 1); ++sub) {
             v.tile_begin(p, val, idx, A);
             v.tile_weight(sub == 1 ? 2u : 1u);
+            if (redo_sub >= 0) v.force_exact();
 #pragma unroll 1
-            for (int pass = 0; pass < 2; ++pass) {
-                walk_tile<V>(v, G, A, S, gchunk, blo, bhi, fs, nref, pairs, cnt, G.sym ? sub + 1 : 0, start, start + (uint32_t)cnt);
+            for (int pass = (redo_sub < 0 ? 0 : 1); pass < 2; ++pass) {
+                walk_tile<V>(v, G, A, S, gchunk, blo, bhi, fs, nref, pairs, cnt, G.sym ? sub + 1 : 0, start, start + (uint32_t)cnt,
+                             slice, nsl);
                 const bool redo = v.tile_end(A, idx, pass, sub == 1 ? 2u : 1u);
                 if (!redo) break;
                 ++redone;
+                // hand the exact re-evaluation to the redo queue (if it has room), else do it here
+                unsigned pos = 0xffffffffu;
+                if (A.redo_cap >= HTB_REDO_SPLIT) {
+                    if (lane == 0) {
+                        unsigned old = *(volatile unsigned *)(A.redo_ctr + 0);                 // reserve (never past the end)
+                        while (old + HTB_REDO_SPLIT <= A.redo_cap) {
+                            const unsigned seen = atomicCAS(A.redo_ctr + 0, old, old + HTB_REDO_SPLIT);
+                            if (seen == old) { pos = old; break; }
+                            old = seen;
+                        }
+                    }
+                    pos = __shfl_sync(HTB_FULL, pos, 0);
+                }
+                if (pos == 0xffffffffu) continue;                                              // in place (pass 1)
+                if (lane < HTB_REDO_SPLIT)
+                    A.redo_ent[pos + lane] = make_uint2((unsigned)t, ((unsigned)sub << 24) | (unsigned)(slice * HTB_REDO_SPLIT + lane));
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) atomicAdd(A.redo_ctr + 1, (unsigned)HTB_REDO_SPLIT);            // publish
+                break;
             }
         }
+        __syncwarp();
+        if (redo_sub < 0 && lane == 0) { __threadfence(); atomicAdd(A.redo_ctr + 3, 1u); }     // ordinary items completed
     }
     v.kernel_end();
     if (lane == 0) {
@@ -270,6 +403,7 @@ struct Fast3T {
 
     static size_t scratch_bytes(const Params &) { return sizeof(uint32_t) * QCAP * 32; }
     __device__ __forceinline__ void tile_weight(unsigned wt) { wt_now = wt; }
+    __device__ __forceinline__ void force_exact() { exact = true; }
 
     __device__ __forceinline__ Fast3T(const Params &p, void *scratch, int ln, const WalkArrays &A) : P(p), lane(ln)
     {
@@ -561,6 +695,7 @@ struct GenCount {
     }
 
     __device__ __forceinline__ void tile_weight(unsigned) {}
+    __device__ __forceinline__ void force_exact() {}
     __device__ GenCount(const Params &p, void *scratch, int ln, const WalkArrays &) : P(p), hist((uint32_t *)scratch), lane(ln)
     {
         for (int k = lane; k < P.nhist; k += 32) hist[k] = 0;
@@ -695,6 +830,7 @@ struct Marked3 {
     }
 
     __device__ __forceinline__ void tile_weight(unsigned) {}
+    __device__ __forceinline__ void force_exact() {}
     __device__ Marked3(const Params &p, void *scratch, int ln, const WalkArrays &) : P(p), hist((double *)scratch), lane(ln)
     {
         for (int k = lane; k < P.nhist; k += 32) hist[k] = 0.0;
@@ -774,6 +910,7 @@ struct DSigma {
     }
 
     __device__ __forceinline__ void tile_weight(unsigned) {}
+    __device__ __forceinline__ void force_exact() {}
     __device__ DSigma(const Params &p, void *scratch, int ln, const WalkArrays &) : P(p), acc((double *)scratch), lane(ln) {}
     __device__ __forceinline__ void tile_begin(const double (&p)[2][3], const bool (&val)[2], const uint32_t (&)[2],
                                                const WalkArrays &)
@@ -814,7 +951,8 @@ struct DSigma {
         for (int k = 0; k < nbin; ++k) {
             // sum_{pairs inside rp[k]} m * 2 * dlog[k]  -  sum_{pairs in bin k} m (1 - ln(rp[k+1]^2/d^2))
             const double ds = inside * 2 * P.e1[k] - acc[(nbin + 1 + k) * 64 + col];
-            P.fcounts[row * nbin + k] = ds / (3.14159265358979323846 * (P.e0[k + 1] - P.e0[k]));
+            // (the rows start at zero; slices of one tile add their shares)
+            atomicAdd(&P.fcounts[row * nbin + k], ds / (3.14159265358979323846 * (P.e0[k + 1] - P.e0[k])));
             inside += acc[(k + 1) * 64 + col];
         }
     }
@@ -860,6 +998,7 @@ struct DSigmaU {
         return 64 * (8 * nbin + 4 * nbin + 4 * (nbin + 1));
     }
     __device__ __forceinline__ void tile_weight(unsigned) {}
+    __device__ __forceinline__ void force_exact() {}
     __device__ DSigmaU(const Params &p, void *scratch, int ln, const WalkArrays &) : P(p), lane(ln)
     {
         nbin = P.n0 - 1;
@@ -935,7 +1074,8 @@ struct DSigmaU {
             const double lnratio = 0.6931471805599453 * ((double)es[k * 64 + col] - n * (double)re) + (log(v) - n * log(rm));
             const double t = m * (n + lnratio);
             const double ds = m * inside * 2 * P.e1[k] - t;
-            P.fcounts[row * nbin + k] = ds / (3.14159265358979323846 * (P.e0[k + 1] - P.e0[k]));
+            // (the rows start at zero; slices of one tile add their shares)
+            atomicAdd(&P.fcounts[row * nbin + k], ds / (3.14159265358979323846 * (P.e0[k + 1] - P.e0[k])));
             inside += n;
         }
     }
@@ -1000,6 +1140,7 @@ struct MarkedQ {
 
     static size_t scratch_bytes(const Params &) { return 2 * 512 * MQ_QD; }
     __device__ __forceinline__ void tile_weight(unsigned) {}
+    __device__ __forceinline__ void force_exact() { exact = true; }
 
     __device__ __forceinline__ MarkedQ(const Params &p, void *scratch, int ln, const WalkArrays &A) : P(p), lane(ln)
     {
@@ -1270,6 +1411,7 @@ struct DSigmaQ {
     static size_t scratch_bytes(const Params &) { return 8 * 32 * DSQ_QCAP + 2 * 4 * 32 * HTB_NBF; }
 
     __device__ __forceinline__ void tile_weight(unsigned) {}
+    __device__ __forceinline__ void force_exact() {}
     __device__ __forceinline__ DSigmaQ(const Params &p, void *scratch, int ln, const WalkArrays &A) : P(p), lane(ln)
     {
         pad = HTB_NBF - P.nrp;
@@ -1489,7 +1631,7 @@ struct DSigmaQ {
                 const double lnratio = 0.6931471805599453 * ((double)ex[32 * s] - n * (double)re) + (log(M[s]) - n * log(rm));
                 const double t = m * (n + lnratio);
                 const double ds = m * inside * 2 * P.e1[k] - t;
-                P.out[row * nbin + k] = ds / (3.14159265358979323846 * (P.e0[k + 1] - P.e0[k]));
+                atomicAdd(&P.out[row * nbin + k], ds / (3.14159265358979323846 * (P.e0[k + 1] - P.e0[k])));
                 inside += n;
             }
         }
@@ -1545,8 +1687,18 @@ int htb_launch_gen(cudaStream_t st, int kind, const WalkGeom &G, const WalkArray
     return 1;
 }
 
+int htb_shard_range(cudaStream_t st, const double *work_dev, int64_t first_cell1, int64_t last_cell1,
+                    int rank, int world, long long *range_dev, int *launches)
+{
+    k_shard_range<<<1, 1024, 0, st>>>(work_dev, (long long)first_cell1, (long long)last_cell1, rank, world, range_dev);
+    if (launches) *launches += 1;
+    HTB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int htb_build_tiles(cudaStream_t st, Workspace &ws, const WalkGeom &G, const SortedSample &s1,
-                    int64_t first_cell1, int64_t last_cell1, uint2 **tiles_out, uint32_t **ntiles_dev_out,
+                    int64_t first_cell1, int64_t last_cell1, const long long *range_dev,
+                    uint2 **tiles_out, uint32_t **ntiles_dev_out,
                     int64_t *max_tiles_out, int *launches)
 {
     const int F = G.dim - 1;
@@ -1563,10 +1715,10 @@ int htb_build_tiles(cudaStream_t st, Workspace &ws, const WalkGeom &G, const Sor
     if (ws.alloc((void **)&tiles, sizeof(uint2) * (size_t)max_tiles)) return 1;
     int blocks = (int)((nseg + 127) / 128);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    k_seg_tiles<<<blocks, 128, 0, st>>>(s1.off, G, nseg, first_cell1, last_cell1, ntile);
+    k_seg_tiles<<<blocks, 128, 0, st>>>(s1.off, G, nseg, first_cell1, last_cell1, range_dev, ntile);
     if (launches) *launches += 1;
     if (htb_exclusive_scan_u32(st, ws, ntile, tbase, nseg, total, launches)) return 1;
-    k_fill_tiles<<<blocks, 128, 0, st>>>(s1.off, G, nseg, first_cell1, last_cell1, ntile, tbase, tiles);
+    k_fill_tiles<<<blocks, 128, 0, st>>>(s1.off, G, nseg, first_cell1, last_cell1, range_dev, ntile, tbase, tiles);
     if (launches) *launches += 1;
     HTB_CUDA(cudaGetLastError());
     *tiles_out = tiles;
@@ -1576,12 +1728,14 @@ int htb_build_tiles(cudaStream_t st, Workspace &ws, const WalkGeom &G, const Sor
 }
 
 int htb_reference_work(cudaStream_t st, Workspace &ws, const WalkGeom &G, const SortedSample &s1,
-                       const SortedSample &s2, double **work_dev_out, int64_t *ncell1_out, int *launches)
+                       const SortedSample &s2, double **work_dev_out, double **balance_dev_out, int64_t *ncell1_out,
+                       int *launches)
 {
     int64_t nc1 = 1, nc2 = 1;
     for (int d = 0; d < G.dim; ++d) { nc1 *= G.nd1[d]; nc2 *= G.nd2[d]; }
     uint32_t *rc1 = nullptr, *rc2 = nullptr;
-    double *work = nullptr;
+    double *work = nullptr, *balance = nullptr;
+    if (balance_dev_out && ws.alloc((void **)&balance, sizeof(double) * (size_t)nc1)) return 1;
     if (ws.alloc((void **)&rc1, sizeof(uint32_t) * (size_t)nc1)) return 1;
     if (ws.alloc((void **)&rc2, sizeof(uint32_t) * (size_t)nc2)) return 1;
     if (ws.alloc((void **)&work, sizeof(double) * (size_t)nc1)) return 1;
@@ -1591,10 +1745,11 @@ int htb_reference_work(cudaStream_t st, Workspace &ws, const WalkGeom &G, const 
     if (htb_ref_cell_counts(st, s2, rc2, launches)) return 1;
     int blocks = (int)((nc1 + 127) / 128);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    k_wref<<<blocks, 128, 0, st>>>(rc1, rc2, G, nc1, work);
+    k_wref<<<blocks, 128, 0, st>>>(rc1, rc2, G, nc1, work, balance);
     if (launches) *launches += 1;
     HTB_CUDA(cudaGetLastError());
     *work_dev_out = work;
+    if (balance_dev_out) *balance_dev_out = balance;
     *ncell1_out = nc1;
     return 0;
 }

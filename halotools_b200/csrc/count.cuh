@@ -55,7 +55,11 @@ int htb_launch_fastxyz(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, 
 int htb_launch_dsq(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const DSQParams &P, int *launches);
 int htb_launch_gen(cudaStream_t st, int kind, const WalkGeom &G, const WalkArrays &A, const GenParams &P, int *launches);
 int htb_build_tiles(cudaStream_t st, Workspace &ws, const WalkGeom &G, const SortedSample &s1,
-                    int64_t first_cell1, int64_t last_cell1, uint2 **tiles_out, uint32_t **ntiles_dev_out,
+                    int64_t first_cell1, int64_t last_cell1, const long long *range_dev /* device {first, last} or null */,
+                    uint2 **tiles_out, uint32_t **ntiles_dev_out,
                     int64_t *max_tiles_out, int *launches);
+int htb_shard_range(cudaStream_t st, const double *work_dev, int64_t first_cell1, int64_t last_cell1,
+                    int rank, int world, long long *range_dev, int *launches);
 int htb_reference_work(cudaStream_t st, Workspace &ws, const WalkGeom &G, const SortedSample &s1,
-                       const SortedSample &s2, double **work_dev_out, int64_t *ncell1_out, int *launches);
+                       const SortedSample &s2, double **work_dev_out, double **balance_dev_out /* may be null */,
+                       int64_t *ncell1_out, int *launches);

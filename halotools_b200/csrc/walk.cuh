@@ -27,6 +27,10 @@
 #define HTB_SPAN_CAP 96
 #endif
 #define HTB_FULL 0xffffffffu
+#define HTB_REDO_SPLIT 16           // an exact re-evaluation of a tile slice is cut into this many finer slices (<= 32)
+#ifndef HTB_ITEMS_PER_WARP
+#define HTB_ITEMS_PER_WARP 32       // tiles are sliced until every resident warp has about this many work items
+#endif
 
 struct WalkGeom {
     int dim;
@@ -43,6 +47,8 @@ struct WalkGeom {
     int tile;                       // sample1 points per tile (32 * points per lane of the kernel variant)
     int maxspan;                    // reference mesh1 cells along the fast dimension one tile may straddle (>= 1)
     int maxfine;                    // fine mesh1 cells along the fast dimension one tile may cover (bounds its extent)
+    int maxslices;                  // a tile's sample2 columns may be cut into up to this many independent work items
+    int items_per_warp;             // ... until every resident warp has about this many work items
 };
 
 struct WalkArrays {
@@ -59,6 +65,9 @@ struct WalkArrays {
     unsigned int *tile_counter;
     unsigned long long *pairs_evaluated;
     unsigned int *tiles_redone;
+    uint2 *redo_ent;                // exact re-evaluations waiting for a warp: {tile, weight pass << 24 | fine slice}
+    unsigned int *redo_ctr;         // [0] reserved, [1] published, [2] taken, [3] ordinary items completed
+    unsigned int redo_cap;          // entries redo_ent can hold (0: re-evaluate in place)
 };
 
 // ------------------------------------------------------------------ PTX helpers
@@ -174,7 +183,8 @@ __device__ __forceinline__ void walk_tile(V &v, const WalkGeom &G, const WalkArr
                                           const int nref /* reference cells along the fast dimension the tile straddles */,
                                           unsigned long long &pairs, int tile_cnt,
                                           int wt_pass /* 0: every span; 1: symmetric mode, weight-1 spans; 2: weight-2 spans */,
-                                          uint32_t ts, uint32_t te /* the tile's own sorted index range */)
+                                          uint32_t ts, uint32_t te /* the tile's own sorted index range */,
+                                          const int slice, const int nslices /* this work item's share of the columns */)
 {
     constexpr int DIM = V::DIM;
     constexpr int F = DIM - 1;                 // fast dimension
@@ -193,7 +203,9 @@ __device__ __forceinline__ void walk_tile(V &v, const WalkGeom &G, const WalkArr
         // only allows nref > 1 when the union cannot reach the same cell twice (maxspan).
         wn[d] = (G.per[d] * (d == F ? nref : 1) + 2 * G.cover[d]) * G.m2[d];
     }
-    const int ncol = (DIM == 3) ? wn[0] * wn[1] : wn[0];
+    const int ncol_all = (DIM == 3) ? wn[0] * wn[1] : wn[0];
+    const int col0 = (int)((long long)ncol_all * slice / nslices);          // this slice: columns [col0, ncol)
+    const int ncol = (int)((long long)ncol_all * (slice + 1) / nslices);
     const int kfmin = floor_div(wlo[F], G.nf2[F]);
     const int kfmax = floor_div(wlo[F] + wn[F] - 1, G.nf2[F]);
 
@@ -266,8 +278,8 @@ __device__ __forceinline__ void walk_tile(V &v, const WalkGeom &G, const WalkArr
     };
 
     // generate spans (lane-parallel over columns) until the list is nearly full, then stream them
-    int base = 0, kf = kfmin;
-    bool more = ncol > 0;
+    int base = col0, kf = kfmin;
+    bool more = ncol > col0;
     while (more) {
         while (true) {
             if (base >= ncol) { more = false; break; }

@@ -12,21 +12,36 @@ every call counts all cells (N independent replicas).
 """
 import numpy as np
 
-_state = {"enabled": False, "group": None, "weights": None}
+_state = {"enabled": False, "group": None, "balanced": False}
 
 
-def enable(group=None):
-    """Shard subsequent pair-counter calls over the ranks of ``group`` (default: world)."""
+def enable(group=None, balanced=None):
+    """Shard subsequent pair-counter calls over the ranks of ``group`` (default: world).
+
+    ``balanced`` (default: True on NCCL, i.e. when the GPUs are there): the engine cuts the mesh1
+    cell range on the device so that every rank gets the same predicted work (htb_set_shard); the
+    front-ends then pass the full cell range.  Otherwise the reference's equal-cell-count rule
+    (``cell1_range``) is applied on the host."""
     import torch.distributed as dist
     if not dist.is_initialized():
         raise RuntimeError("torch.distributed is not initialised")
     _state["enabled"] = True
     _state["group"] = group
+    if balanced is None:
+        balanced = dist.get_backend(group) == "nccl"
+    _state["balanced"] = bool(balanced)
+    if _state["balanced"]:
+        from . import _lib
+        _lib.set_shard(dist.get_rank(group), dist.get_world_size(group))
 
 
 def disable():
+    if _state["balanced"]:
+        from . import _lib
+        _lib.set_shard(0, 1)
     _state["enabled"] = False
     _state["group"] = None
+    _state["balanced"] = False
 
 
 def is_enabled():
@@ -65,7 +80,9 @@ def split_cells(ncells, world, work=None):
 
 
 def cell1_range(ncells, work=None):
-    """This rank's (first_cell1, last_cell1)."""
+    """This rank's (first_cell1, last_cell1); the full range when the engine does the (balanced) cut."""
+    if _state["balanced"]:
+        return 0, ncells
     rank, world = _rank_world()
     return split_cells(ncells, world, work)[rank]
 

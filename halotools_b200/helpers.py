@@ -92,6 +92,9 @@ def get_period(period):
 def _column_extrema(x, y, z):
     """(min, max) per coordinate.  Large float64 samples whose three coordinates are adjacent columns of one
     matrix are scanned once by the library's threaded host helper; anything else goes through numpy."""
+    if all(getattr(a, "is_cuda", False) for a in (x, y, z)):
+        # device-resident columns (torch CUDA tensors): the extrema are found where the data lives
+        return [(float(a.min()), float(a.max())) if a.numel() else (0.0, 0.0) for a in (x, y, z)]
     try:
         n = len(x)
         if (n >= 1000000 and all(isinstance(a, np.ndarray) and a.dtype == np.float64 and a.ndim == 1 for a in (x, y, z))
@@ -131,8 +134,9 @@ def enforce_sample_respects_pbcs(x, y, z, period):
 
 def enforce_sample_has_correct_shape(sample, ndim=3):
     """(Npts, ndim) or TypeError (mock_observables_helpers.py:135)."""
-    sample = np.atleast_1d(sample)
-    shape = np.shape(sample)
+    if not getattr(sample, "is_cuda", False):
+        sample = np.atleast_1d(sample)
+    shape = tuple(sample.shape)
     if not (len(shape) == 2 and shape[1] == ndim):
         msg = ("Input sample of points must be a Numpy ndarray of shape (Npts, {0}).\n"
                "To convert a sequence of 1d arrays x, y, z into correct shape expected \n"

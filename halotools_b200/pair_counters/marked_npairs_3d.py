@@ -52,7 +52,7 @@ def marked_npairs_3d(sample1, sample2, rbins, weight_func_id, period=None,
         c2.ptrs[0], c2.ptrs[1], c2.ptrs[2], ctypes.c_int64(c2.stride), ctypes.c_int64(c2.n),
         _lib._dp(w1), _lib._dp(w2), ctypes.c_int32(w1.shape[1]), ctypes.c_int32(int(weight_func_id)),
         _lib._dp(rb), ctypes.c_int32(len(rb)), ctypes.c_int64(first), ctypes.c_int64(last),
-        _lib._dp(counts))
+        _lib._dp(counts), extra_flags=_lib.cache_flags(c1, c2, PBCs))
     return np.array(_dist.allreduce_sum(counts))
 
 

@@ -48,7 +48,8 @@ def npairs_3d(sample1, sample2, rbins, period=None, num_threads=1,
         c1.ptrs[0], c1.ptrs[1], c1.ptrs[2], ctypes.c_int64(c1.stride), ctypes.c_int64(c1.n),
         c2.ptrs[0], c2.ptrs[1], c2.ptrs[2], ctypes.c_int64(c2.stride), ctypes.c_int64(c2.n),
         _lib._dp(rb), ctypes.c_int32(len(rb)), ctypes.c_int64(first), ctypes.c_int64(last),
-        counts.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), device=c1.device)
+        counts.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), device=c1.device,
+        extra_flags=_lib.cache_flags(c1, c2, PBCs))
     return np.array(_dist.allreduce_sum(counts))
 
 

@@ -39,25 +39,39 @@ def mean_delta_sigma(galaxies, particles, effective_particle_masses,
 
     n1 = len(x1in)
     nbin = len(rp_bins) - 1
-    delta_sigma = np.zeros((n1, nbin), dtype=np.float64)
+    # per_object=False only needs the column sums: they are formed on the device (HTB_FLAG_COLUMN_SUM) and the
+    # (Ngal, nbin) rows never cross PCIe
+    delta_sigma = np.zeros((n1, nbin) if per_object else (nbin,), dtype=np.float64)
     first, last = _dist.cell1_range(geom.ncells1)
     c1 = _lib.Columns([x1in, y1in])
     c2 = _lib.Columns([x2in, y2in])
-    extra = _lib.FLAG_UNIFORM_MASS if use_scalar else 0
+    if c1.device != c2.device:
+        raise TypeError("galaxies and particles must both be host arrays or both be CUDA tensors")
+    extra = (_lib.FLAG_UNIFORM_MASS if use_scalar else 0) | (0 if per_object else _lib.FLAG_COLUMN_SUM)
+    if c1.device and not use_scalar:
+        raise TypeError("device-resident samples need a scalar ``effective_particle_masses``")
     m2 = np.ascontiguousarray(w2in[:1] if use_scalar else w2in, dtype=np.float64)
+    if c1.device:
+        # HTB_FLAG_DEVICE_INPUT covers every sample pointer, the mass included
+        import torch
+        m2_dev = torch.from_numpy(m2).to(x2in.device)
+        m2_ptr = ctypes.cast(ctypes.c_void_p(int(m2_dev.data_ptr())), ctypes.POINTER(ctypes.c_double))
+    else:
+        m2_ptr = _lib._dp(m2)
     g = geom.as_struct()
     rb = np.ascontiguousarray(rp_bins, dtype=np.float64)
     _lib.run_engine(
         "htb_mean_delta_sigma_engine", ctypes.byref(g),
         c1.ptrs[0], c1.ptrs[1], ctypes.c_int64(c1.stride), ctypes.c_int64(c1.n),
-        c2.ptrs[0], c2.ptrs[1], ctypes.c_int64(c2.stride), _lib._dp(m2), ctypes.c_int64(c2.n),
+        c2.ptrs[0], c2.ptrs[1], ctypes.c_int64(c2.stride), m2_ptr, ctypes.c_int64(c2.n),
         _lib._dp(rb), ctypes.c_int32(len(rb)), ctypes.c_int64(first), ctypes.c_int64(last),
-        _lib._dp(delta_sigma), extra_flags=extra)
+        _lib._dp(delta_sigma), extra_flags=extra, device=c1.device)
     if per_object:
         return _dist.allreduce_sum(delta_sigma)
     # rows outside this rank's mesh1 cells are zero, so the mean is the all-reduced column sum / N
-    colsum = _dist.allreduce_sum(np.sum(delta_sigma, axis=0))
-    return colsum / float(n1) if _dist.is_enabled() else np.mean(delta_sigma, axis=0)
+    # (np.mean(axis=0) of the reference, mean_delta_sigma.py:252-255)
+    colsum = _dist.allreduce_sum(delta_sigma)
+    return colsum / float(n1) if n1 > 0 else colsum * np.nan
 
 
 def _mean_delta_sigma_process_args(
@@ -66,6 +80,8 @@ def _mean_delta_sigma_process_args(
     """Same processing as mean_delta_sigma.py:258-330, including the reference's habit of writing
     the shifted coordinates back into the caller's arrays when ``period`` is None (:263-273)."""
     period, PBCs = get_period(period)
+    if PBCs is False and (getattr(galaxies, "is_cuda", False) or getattr(particles, "is_cuda", False)):
+        raise ValueError("device-resident samples need an explicit ``period``")
 
     if PBCs is False:
         _x1, _y1, _z1, _x2, _y2, _z2, period = _enclose_in_box(

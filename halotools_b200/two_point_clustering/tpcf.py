@@ -10,6 +10,7 @@ from ..helpers import (enforce_sample_has_correct_shape, get_num_threads, get_pe
                        get_separation_bins_array)
 from ..pair_counters import npairs_3d
 from ..pair_counters.mesh_helpers import _enforce_maximum_search_length
+from .. import _lib
 from . import _driver
 from .clustering_helpers import (process_optional_input_sample2, tpcf_estimator_dd_dr_rr_requirements,
                                  verify_tpcf_estimator)
@@ -54,10 +55,12 @@ def tpcf(sample1, rbins, sample2=None, randoms=None, period=None,
         D2R = nr * (dv * (np.shape(sample2)[0] / volume))
         return D1R, D2R, dv * ((nr ** 2) / volume)
 
-    D1D1, D1D2, D2D2 = _driver.data_counts(count, sample1, sample2, same, do_auto, do_cross,
-                                           approx_cell1_size, approx_cell2_size)
-    D1R, D2R, RR = _driver.random_counts(count, analytic, sample1, sample2, randoms, same, do_RR, do_DR,
-                                         approx_cell1_size, approx_cell2_size, approx_cellran_size)
+    # the engine's upload cache: every sample crosses PCIe once for all the counts of this call
+    with _lib.upload_cache():
+        D1D1, D1D2, D2D2 = _driver.data_counts(count, sample1, sample2, same, do_auto, do_cross,
+                                               approx_cell1_size, approx_cell2_size)
+        D1R, D2R, RR = _driver.random_counts(count, analytic, sample1, sample2, randoms, same, do_RR, do_DR,
+                                             approx_cell1_size, approx_cell2_size, approx_cellran_size)
     if RR_precomputed is not None:
         RR = RR_precomputed
     return _driver.combine(same, do_auto, do_cross, D1D1, D1D2, D2D2, D1R, D2R, RR, N1, N2, NR, estimator)

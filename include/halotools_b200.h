@@ -35,6 +35,9 @@ extern "C" {
 #define HTB_FLAG_GENERIC      4u   /* force the generic (literal top-down scan) kernels       */
 #define HTB_FLAG_NO_TMA       8u   /* stage sample2 tiles with ld.global/st.shared instead of cp.async.bulk */
 #define HTB_FLAG_UNIFORM_MASS 32u  /* mean_delta_sigma: all particle masses equal m2[0] (scalar effective_particle_masses) */
+#define HTB_FLAG_COLUMN_SUM   64u  /* mean_delta_sigma: delta_sigma_out is f64[nrp-1], the sums of the per-object rows over this call's galaxies (per_object=False needs nothing else) */
+#define HTB_FLAG_CACHE_SAMPLE1 128u /* sample1's host coordinate arrays take part in the upload cache (htb_cache_begin) */
+#define HTB_FLAG_CACHE_SAMPLE2 256u /* ... sample2's */
 #define HTB_FLAG_NO_SYM       16u  /* auto-correlations: evaluate (i,j) and (j,i) separately, as the reference does */
 
 /* Scalars of RectangularDoubleMesh / RectangularDoubleMesh2D
@@ -77,6 +80,21 @@ int  htb_device_count(void);
 int  htb_set_device(int device);
 /* use an existing CUDA stream (cudaStream_t as void*) for subsequent calls; NULL = library stream */
 int  htb_set_stream(void *cuda_stream);
+
+/* Upload cache: between htb_cache_begin() and htb_cache_end() the host coordinate arrays this thread's engine calls
+ * bring to the device stay resident, keyed by (pointers, stride, count): the DD, DR and RR counts of one tpcf() move
+ * every sample across PCIe once (the reference re-gathers every sample in every engine call, tpcf.py:76-113,164-205).
+ * Only samples flagged HTB_FLAG_CACHE_SAMPLE1/2 take part; the caller must not modify or free those arrays in
+ * between.  htb_cache_end() frees the device copies.                                                          */
+int  htb_cache_begin(void);
+int  htb_cache_end(void);
+
+/* Multi-GPU sharding (one process per GPU): after htb_set_shard(rank, world) every engine call of this thread
+ * processes only rank's share of the reference mesh1 cells in [first_cell1, last_cell1) - contiguous cell ranges as
+ * in the reference's _cell1_parallelization_indices (mesh_helpers.py:183-221), with the cut points placed on the
+ * device so that every rank gets the same predicted work (pairs the reference would visit) instead of the same
+ * number of cells.  The caller sums the outputs of the ranks (npairs_3d.py:145).  world = 1 switches it off.  */
+int  htb_set_shard(int rank, int world);
 
 /* npairs_3d_engine.pyx:17 — counts[k] = #{(i,j): dx^2+dy^2+dz^2 <= rbins[k]^2}, int64[nb]. */
 int htb_npairs_3d_engine(const htb_mesh_geom *mesh,

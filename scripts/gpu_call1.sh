@@ -1,0 +1,8 @@
+#!/bin/bash
+set -u
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+echo "== pytest gpu"; timeout 1200 python -m pytest tests -m gpu -q -x --timeout 600 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_gpu.log
+echo "== bench"; timeout 600 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -3 gpurun_out/bench.log | cut -c1-600; tail -5 gpurun_out/bench.err
+echo "== shardsim tpcf"; timeout 300 python scripts/gpu_shardsim.py tpcf > gpurun_out/shardsim_tpcf.json 2> gpurun_out/shardsim_tpcf.err; tail -5 gpurun_out/shardsim_tpcf.err
+echo "== shardsim c5"; timeout 400 python scripts/gpu_shardsim.py c5 > gpurun_out/shardsim_c5.json 2> gpurun_out/shardsim_c5.err; tail -5 gpurun_out/shardsim_c5.err

@@ -354,3 +354,123 @@ def test_large_pageable_inputs_take_the_staged_upload():
         del os.environ["HTB_NO_STAGED_UPLOAD"]
     assert np.array_equal(a, b)
     assert a[0] >= len(s)
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_device_side_balanced_shards_add_up(world):
+    """htb_set_shard: the ranks' work-balanced cell ranges partition the call (counts, sums and W_ref add up)"""
+    rng = np.random.RandomState(18)
+    L = 200.0
+    # clustered sample1: a plain cell-count split would be badly unbalanced
+    blob = np.mod(rng.normal(60.0, 6.0, (30000, 3)), L)
+    s1 = np.vstack([blob, rng.uniform(0, L, (10000, 3))])
+    s2 = rng.uniform(0, L, (50000, 3))
+    rb = np.logspace(-1, np.log10(12.0), 11)
+    w1, w2 = rng.uniform(0.5, 1.5, len(s1)), rng.uniform(0.5, 1.5, len(s2))
+    full = hb.npairs_3d(s1, s2, rb, period=L)
+    wfull = _lib.last_stats["pairs_reference"]
+    mfull = hb.marked_npairs_3d(s1, s2, rb, 1, period=L, weights1=w1, weights2=w2)
+    dfull = hb.mean_delta_sigma(s1[:5000], s2, 1.0, rb, period=L, per_object=True)
+    dmean = hb.mean_delta_sigma(s1[:5000], s2, 1.0, rb, period=L)
+    tot, wtot, mtot, dtot, dmtot, shares = 0, 0.0, 0.0, 0.0, 0.0, []
+    try:
+        for r in range(world):
+            _lib.set_shard(r, world)
+            tot = tot + hb.npairs_3d(s1, s2, rb, period=L)
+            shares.append(_lib.last_stats["pairs_reference"])
+            wtot += shares[-1]
+            mtot = mtot + hb.marked_npairs_3d(s1, s2, rb, 1, period=L, weights1=w1, weights2=w2)
+            dtot = dtot + hb.mean_delta_sigma(s1[:5000], s2, 1.0, rb, period=L, per_object=True)
+            dmtot = dmtot + hb.mean_delta_sigma(s1[:5000], s2, 1.0, rb, period=L) * 5000.0
+    finally:
+        _lib.set_shard(0, 1)
+    assert np.array_equal(tot, full)
+    assert wtot == wfull
+    # balanced: no rank has more than its share plus one (heavy) cell's worth of work
+    assert max(shares) <= wfull / world * 1.5, shares
+    assert np.allclose(mtot, mfull, rtol=1e-12, atol=0)
+    scale = np.max(np.abs(dfull))
+    assert np.allclose(dtot, dfull, rtol=1e-10, atol=1e-12 * scale)
+    assert np.allclose(dmtot / 5000.0, dmean, rtol=1e-10, atol=1e-12 * scale)
+
+
+@pytest.mark.parametrize("maxslices", ["1", "3", "8"])
+def test_tile_slices_keep_results(maxslices):
+    """few tiles -> every tile is cut into column slices (independent work items): identical counts, same sums"""
+    import os
+    rng = np.random.RandomState(19)
+    L = 150.0
+    s1 = rng.uniform(0, L, (2000, 3))          # a handful of tiles only
+    s2 = rng.uniform(0, L, (200000, 3))
+    rb = np.logspace(-1, np.log10(14.0), 13)
+    w1, w2 = rng.uniform(0.5, 1.5, len(s1)), rng.uniform(0.5, 1.5, len(s2))
+    os.environ["HTB_MAXSLICES"] = maxslices
+    try:
+        a = hb.npairs_3d(s1, s2, rb, period=L)
+        x = hb.npairs_xy_z(s1, s2, rb, [0.0, 20.0], period=L)
+        sm = hb.npairs_s_mu(s1, s2, rb, np.linspace(0, 1, 6), period=L)
+        m = hb.marked_npairs_3d(s1, s2, rb, 1, period=L, weights1=w1, weights2=w2)
+        d = hb.mean_delta_sigma(s1, s2, 1.0, rb, period=L, per_object=True)
+        dg = hb.mean_delta_sigma(s1[:300], s2, np.full(len(s2), 1.0), rb, period=L, per_object=True)
+        auto = hb.npairs_3d(s1, s1, rb, period=L)
+    finally:
+        del os.environ["HTB_MAXSLICES"]
+    assert np.array_equal(a, oracle.npairs_3d(s1, s2, rb, period=L, num_threads=4))
+    assert np.array_equal(x, oracle.npairs_xy_z(s1, s2, rb, [0.0, 20.0], period=L, num_threads=4))
+    assert np.array_equal(sm, oracle.npairs_s_mu(s1, s2, rb, np.linspace(0, 1, 6), period=L, num_threads=4))
+    assert np.array_equal(auto, oracle.npairs_3d(s1, s1, rb, period=L, num_threads=4))
+    assert np.allclose(m, oracle.marked_npairs_3d(s1, s2, rb, 1, period=L, weights1=w1, weights2=w2, num_threads=4),
+                       rtol=1e-12, atol=0)
+    want = oracle.mean_delta_sigma(s1, s2, 1.0, rb, period=L, per_object=True, num_threads=4)
+    scale = np.max(np.abs(want))
+    assert np.allclose(d, want, rtol=1e-10, atol=1e-12 * scale)
+    assert np.allclose(dg, want[:300], rtol=1e-10, atol=1e-12 * scale)
+
+
+def test_delta_sigma_device_resident_inputs_and_column_sums():
+    """CUDA tensors in (no host copy of the samples); per_object=False returns the device-side column sums / N"""
+    import torch
+    rng = np.random.RandomState(20)
+    L = 120.0
+    gal, ptcl = rng.uniform(0, L, (4000, 3)), rng.uniform(0, L, (120000, 3))
+    rp = np.logspace(-1, 1, 9)
+    want = oracle.mean_delta_sigma(gal, ptcl, 1.5, rp, period=L, per_object=True, num_threads=4)
+    scale = np.max(np.abs(want))
+    gd, pd = torch.from_numpy(gal).cuda(), torch.from_numpy(ptcl).cuda()
+    rows = hb.mean_delta_sigma(gd, pd, 1.5, rp, period=L, per_object=True)
+    assert np.allclose(rows, want, rtol=1e-10, atol=1e-12 * scale)
+    mean_dev = hb.mean_delta_sigma(gd, pd, 1.5, rp, period=L)
+    mean_host = hb.mean_delta_sigma(gal, ptcl, 1.5, rp, period=L)
+    assert mean_dev.shape == (len(rp) - 1,)
+    assert np.allclose(mean_dev, np.mean(want, axis=0), rtol=1e-10, atol=1e-12 * scale)
+    assert np.allclose(mean_host, mean_dev, rtol=1e-12, atol=1e-14 * scale)
+    many = hb.mean_delta_sigma(gal, ptcl, np.full(len(ptcl), 1.5), rp, period=L)     # general-mass kernel, column sums
+    assert np.allclose(many, np.mean(want, axis=0), rtol=1e-10, atol=1e-12 * scale)
+
+
+def test_upload_cache_reuses_only_caller_owned_arrays():
+    """inside upload_cache() a sample is uploaded once; temporaries (float32 conversions, non-periodic shifts)
+    never take part, so recycled host addresses cannot alias stale device copies"""
+    rng = np.random.RandomState(21)
+    L = 90.0
+    a, b = rng.uniform(0, L, (40000, 3)), rng.uniform(0, L, (50000, 3))
+    rb = np.logspace(-1, 1, 8)
+    want_ab = oracle.npairs_3d(a, b, rb, period=L, num_threads=4)
+    want_bb = oracle.npairs_3d(b, b, rb, period=L, num_threads=4)
+    with _lib.upload_cache():
+        assert np.array_equal(hb.npairs_3d(a, b, rb, period=L), want_ab)
+        first = _lib.last_stats["ms_h2d"]
+        assert np.array_equal(hb.npairs_3d(b, b, rb, period=L), want_bb)      # b is already there
+        assert np.array_equal(hb.npairs_3d(a, b, rb, period=L), want_ab)
+        # temporaries: float32 input (converted copy) and the non-periodic path (shifted copies), several times
+        for seed in range(3):
+            c = np.random.RandomState(seed).uniform(0, L, (40000, 3))
+            assert np.array_equal(hb.npairs_3d(c.astype(np.float32), b, rb, period=L),
+                                  oracle.npairs_3d(c.astype(np.float32).astype(np.float64), b, rb, period=L, num_threads=4))
+            assert np.array_equal(hb.npairs_3d(c, b, rb), oracle.npairs_3d(c, b, rb, num_threads=4))
+    assert first >= 0.0
+    # the estimator drivers use it
+    xi = hb.tpcf(a, rb, randoms=b, period=L, estimator="Landy-Szalay")
+    DD, DR, RR = (np.diff(oracle.npairs_3d(x, y, rb, period=L, num_threads=4)) for x, y in ((a, a), (a, b), (b, b)))
+    from halotools_b200.two_point_clustering.tpcf_estimators import _TP_estimator
+    assert np.allclose(xi, _TP_estimator(DD, DR, RR, len(a), len(a), len(b), len(b), "Landy-Szalay"), rtol=1e-12)
