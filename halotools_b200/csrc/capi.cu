@@ -164,7 +164,7 @@ static int clampi(double v, int lo, int hi)
     return (int)v;
 }
 
-static void choose_refinement(const htb_mesh_geom *g, int64_t n1, int64_t n2, int tile, int *m1, int *m2)
+static void choose_refinement(const htb_mesh_geom *g, int64_t n1, int64_t n2, int tile, int *m1, int *m2, int mode = 0)
 {
     const int dim = g->ndim, F = dim - 1, S = dim - 1;
     double vol = 1.0;
@@ -186,6 +186,15 @@ static void choose_refinement(const htb_mesh_geom *g, int64_t n1, int64_t n2, in
         m2[d] = clampi(floor(scale), 1, cap);
     }
     m2[F] = clampi(floor(8.0 * g->cell2_size[F] / g->search[F] + 0.5), 1, 16);
+    if (mode == 1) {
+        // cell-resolved kernels (DSigmaR) decide per fine cell of sample2: cells small against the bins (a
+        // sixteenth of the search length) but holding >= ~256 points, so the per-cell work is amortised
+        const double side_n = pow(256.0 / dens2, 1.0 / dim);
+        for (int d = 0; d < dim; ++d) {
+            const double side = std::max(g->search[d] / 16.0, side_n);
+            m2[d] = clampi(floor(g->cell2_size[d] / side + 0.5), 1, 16);
+        }
+    }
     // respect the cell budgets
     for (int which = 0; which < 2; ++which) {
         int *m = which ? m2 : m1;
@@ -485,7 +494,7 @@ struct Call {
               const double *const *c1, int64_t stride1, int64_t n1, const double *w1,
               const double *const *c2, int64_t stride2, int64_t n2, const double *w2, int nw,
               bool perm1, int64_t first_cell1, int64_t last_cell1, uint32_t fl,
-              int tile = HTB_TILE, double sentinel = 1.0e150)
+              int tile = HTB_TILE, double sentinel = 1.0e150, int refine_mode = 0)
     {
         flags = fl;
         first_cell = first_cell1;
@@ -514,7 +523,7 @@ struct Call {
         else if (stage_rows(w2, n2, nw, &dw2)) return 1;
         HTB_CUDA(cudaEventRecord(ev[1], st));
         // ---- K1
-        choose_refinement(g, n1, n2, tile, m1, m2);
+        choose_refinement(g, n1, n2, tile, m1, m2, refine_mode);
         // Symmetric auto-correlation (count each zero-shift unordered pair once, weight 2) needs the two
         // samples to be the SAME sorted arrays and the reference window to be symmetric (mesh1 == mesh2).
         bool sym = allow_sym && same && !(fl & HTB_FLAG_NO_SYM) && !getenv("HTB_NO_SYM");
@@ -999,8 +1008,16 @@ extern "C" int htb_mean_delta_sigma_engine(const htb_mesh_geom *mesh,
         qp.Tspan = d < 0 ? (unsigned)(-d - 1) : 0u;
         qp.mass = mass;
     }
+    // cell-resolved fast path (DSigmaR): additionally needs a positive lowest edge and squared separations / edges
+    // within the exponent window its running products are renormalised for
+    bool ring = fast && nrp >= 2 && rsq[0] >= 1e-290 && !getenv("HTB_NO_DSR");
+    if (ring) {
+        const double et = rsq[nrp - 1];
+        ring = et >= ldexp(1.0, -38) && et <= ldexp(1.0, 58) && 8.0 * lmax * lmax <= ldexp(et, 40);
+        for (int d = 0; d < 2 && ring; ++d) ring = (int64_t)mesh->ndivs2[d] * 16 < 65536;
+    }
     if (c.setup(mesh, 1, false, c1, stride1, n1, nullptr, c2, stride2, n2, uniform ? nullptr : m2, uniform ? 0 : 1, true,
-                first_cell1, last_cell1, flags, fast ? 32 : HTB_TILE, fast ? 8.0 * lmax : 1.0e150)) return 1;
+                first_cell1, last_cell1, flags, fast ? 32 : HTB_TILE, fast ? 8.0 * lmax : 1.0e150, ring ? 1 : 0)) return 1;
     const int nbin = nrp - 1;
     std::vector<double> e((size_t)nrp + nbin);
     for (int k = 0; k < nrp; ++k) e[k] = rp_bins[k] * rp_bins[k];
@@ -1011,7 +1028,17 @@ extern "C" int htb_mean_delta_sigma_engine(const htb_mesh_geom *mesh,
     const size_t nout = (size_t)(n1 > 0 ? n1 : 1) * nbin;
     if (c.ws.alloc((void **)&out_dev, sizeof(double) * nout)) return 1;
     HTB_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(double) * nout, c.st));
-    if (fast) {
+    if (ring) {
+        DSRParams rp{};
+        rp.nrp = nrp;
+        for (int k = 0; k < HTB_NBF; ++k) rp.Ed[k] = k < nrp ? rsq[k] : INFINITY;
+        rp.tiny2 = ldexp(rsq[nrp - 1], -24);
+        rp.mass = mass;
+        rp.e0 = (const double *)edev; rp.e1 = (const double *)edev + nrp;
+        rp.out = out_dev;
+        rp.perm1 = c.s1.perm;
+        if (htb_launch_dsr(c.st, c.G, c.A, rp, &c.launches)) return 1;
+    } else if (fast) {
         qp.e0 = (const double *)edev; qp.e1 = (const double *)edev + nrp;
         qp.out = out_dev;
         qp.perm1 = c.s1.perm;
@@ -1037,7 +1064,7 @@ extern "C" int htb_mean_delta_sigma_engine(const htb_mesh_geom *mesh,
         HTB_CUDA(cudaGetLastError());
         HTB_CUDA(cudaMemcpyAsync(out, sums, sizeof(double) * (size_t)nbin, cudaMemcpyDeviceToHost, c.st));
     } else if (n1 > 0) HTB_CUDA(cudaMemcpyAsync(out, out_dev, sizeof(double) * (size_t)n1 * nbin, cudaMemcpyDeviceToHost, c.st));
-    return c.finish(stats, fast ? 1 : 0);
+    return c.finish(stats, ring ? 2 : (fast ? 1 : 0));
     HTB_GUARD_END
 }
 

@@ -10,6 +10,7 @@
 //   GenSMU   npairs_s_mu (differential histogram)                npairs_s_mu_engine.pyx:196-229
 //   Marked3  marked_npairs_3d, 17 weight functions               marked_npairs_3d_engine.pyx:204-216
 //   DSigma   mean_delta_sigma per-object accumulators (2-D)      mean_delta_sigma_engine.pyx:162-180
+#include <type_traits>
 #include "walk.cuh"
 #include "count.cuh"
 
@@ -159,6 +160,9 @@ __global__ void __launch_bounds__(1024) k_shard_range(const double *__restrict__
 }
 
 // ------------------------------------------------------------------ kernel skeleton
+template <class V, class = void> struct HtbPerCell { static constexpr bool value = false; };
+template <class V> struct HtbPerCell<V, std::void_t<decltype(V::PER_CELL)>> { static constexpr bool value = V::PER_CELL; };
+
 template <class V>
 __global__ void __launch_bounds__(V::WARPS * 32, V::MINBLOCKS)
 k_count(const __grid_constant__ WalkGeom G, const __grid_constant__ WalkArrays A,
@@ -291,8 +295,11 @@ k_count(const __grid_constant__ WalkGeom G, const __grid_constant__ WalkArrays A
             if (redo_sub >= 0) v.force_exact();
 #pragma unroll 1
             for (int pass = (redo_sub < 0 ? 0 : 1); pass < 2; ++pass) {
-                walk_tile<V>(v, G, A, S, gchunk, blo, bhi, fs, nref, pairs, cnt, G.sym ? sub + 1 : 0, start, start + (uint32_t)cnt,
-                             slice, nsl);
+                if constexpr (HtbPerCell<V>::value)
+                    walk_tile_cells<V>(v, G, A, S, gchunk, blo, bhi, fs, nref, pairs, cnt, slice, nsl);
+                else
+                    walk_tile<V>(v, G, A, S, gchunk, blo, bhi, fs, nref, pairs, cnt, G.sym ? sub + 1 : 0, start, start + (uint32_t)cnt,
+                                 slice, nsl);
                 const bool redo = v.tile_end(A, idx, pass, sub == 1 ? 2u : 1u);
                 if (!redo) break;
                 ++redone;
@@ -1640,6 +1647,252 @@ struct DSigmaQ {
     __device__ __forceinline__ void kernel_end() {}
 };
 
+// ------------------------------------------------------------------ DSigmaR (uniform particle mass, cell-resolved)
+// mean_delta_sigma_engine.pyx:162-180 for one particle mass.  As in DSigmaQ every lane owns one galaxy and needs,
+// per annulus, the number of particles and sum ln d^2 (carried as a product).  Most particles of config-5-like
+// inputs lie in range (65 % of the evaluated pairs) and the annuli are wide compared with a fine cell of the
+// particle mesh, so the annulus of a pair is decided PER (galaxy, CELL) instead of per pair: from the galaxy's
+// distance range to the cell's box the lane knows the slots (annuli) its pairs with that cell can fall into;
+//   * at most NE = 1, 2 or 3 edges inside the range (the warp takes the largest NE of its lanes): per pair 5 f64
+//     ops for d^2, one unconditional DMUL into the cell product and, per edge, one exact 64-bit integer compare, a
+//     select, a DMUL into the CUMULATIVE product of the pairs below that edge and a predicated count - no queue, no
+//     key, no cascade.  At the end of the cell the lane banks the cumulative products: slot s + i gets
+//     C_i as numerator and C_(i-1) as denominator, and the product of an annulus is recovered at the end of the
+//     tile as numerator / denominator (in logarithms);
+//   * more edges inside some lane's range, or a pair that may be (nearly) coincident: the whole warp takes the
+//     exact per-pair scan for that cell (slot search bounded by the lane's range).
+// Slots: s = number of edges e with e < d^2 (0: inside rp[0], 1..nrp-1: annulus s-1, nrp: outside); every decision
+// is the reference's exact `dxy_sq <= rp^2` on the same f64 value, so only the summation order differs.
+struct DSigmaR {
+    static constexpr int DIM = 2, NPAY = 0, PPL = 1, WARPS = 4, MINBLOCKS = 2;
+    static constexpr bool TMA = true, PER_CELL = true;
+    static constexpr int NS = HTB_NBF + 4;
+    typedef DSRParams Params;
+    const Params &P;
+    int lane;
+    uint32_t *extra;
+    double *Num, *Den;          // [NS][32] mantissas in [1, 2) of the numerator / denominator products per slot
+    int *eNum, *eDen;           // ... their binary exponents
+    unsigned *cnt;              // [NS][32] pair counts per slot
+    uint32_t es;                // shared-space address of the warp's copy of the squared edges (+inf padded)
+    double x, y, xs, ys;
+    bool valid, always_exact;
+    int mode;                   // warp-uniform: 1..3 = edges per lane handled in registers, 0 = exact scan
+    int slo, shi;
+    unsigned long long eb0, eb1, eb2;
+    double Pall, C0, C1, C2;
+    int Eall, E0, E1, E2;
+    unsigned n0, n1, n2, npart;
+
+    static size_t scratch_bytes(const Params &) { return 8 * HTB_SPAN_CAP + 8 * (HTB_NBF + 4) + (size_t)NS * 32 * (8 + 8 + 4 + 4 + 4); }
+    __device__ __forceinline__ uint32_t *span_extra() { return extra; }
+    __device__ __forceinline__ void tile_weight(unsigned) {}
+    __device__ __forceinline__ void force_exact() {}
+    __device__ __forceinline__ DSigmaR(const Params &p, void *scratch, int ln, const WalkArrays &A) : P(p), lane(ln)
+    {
+        unsigned char *b = (unsigned char *)scratch;
+        extra = (uint32_t *)b; b += 8 * HTB_SPAN_CAP;
+        double *ed = (double *)b; b += 8 * (HTB_NBF + 4);
+        es = smem_u32(ed);
+        if (ln < HTB_NBF + 4) ed[ln] = ln < HTB_NBF ? P.Ed[ln] : __longlong_as_double(0x7ff0000000000000LL);
+        Num = (double *)b + ln; b += 8 * 32 * NS;
+        Den = (double *)b + ln; b += 8 * 32 * NS;
+        eNum = (int *)b + ln; b += 4 * 32 * NS;
+        eDen = (int *)b + ln; b += 4 * 32 * NS;
+        cnt = (unsigned *)b + ln;
+        x = y = xs = ys = 0.0; valid = false; mode = 1; slo = shi = 0; eb0 = eb1 = eb2 = 0;
+        Pall = C0 = C1 = C2 = 1.0; Eall = E0 = E1 = E2 = 0; n0 = n1 = n2 = npart = 0;
+        always_exact = ((A.flags1[0] | A.flags2[0]) & 1u) != 0u;
+        __syncwarp();
+    }
+    __device__ __forceinline__ void tile_begin(const double (&p)[1][3], const bool (&val)[1], const uint32_t (&)[1],
+                                               const WalkArrays &)
+    {
+        // unused lanes of a partial tile shadow lane 0 (always valid): nothing they meet is out of the ordinary
+        const double x0 = __shfl_sync(HTB_FULL, p[0][0], 0), y0 = __shfl_sync(HTB_FULL, p[0][1], 0);
+        valid = val[0];
+        x = valid ? p[0][0] : x0;
+        y = valid ? p[0][1] : y0;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) { Num[32 * s] = 1.0; Den[32 * s] = 1.0; eNum[32 * s] = 0; eDen[32 * s] = 0; cnt[32 * s] = 0u; }
+    }
+    __device__ __forceinline__ void set_shift(const double (&sh)[3], const WalkArrays &)
+    {
+        xs = x - sh[0]; ys = y - sh[1];
+    }
+    static __device__ __forceinline__ void renorm(double &m, int &e)
+    {
+        const int h = __double2hiint(m);
+        e += (h >> 20) - 1023;
+        m = __hiloint2double((h & 0x000fffff) | 0x3ff00000, __double2loint(m));
+    }
+    __device__ __forceinline__ void cell_begin(double bx0, double bx1, double by0, double by1)
+    {
+        npart = 0;
+        if (always_exact) { slo = 0; shi = P.nrp; mode = 0; return; }
+        const double gx = fmax(0.0, fmax(bx0 - xs, xs - bx1)), gy = fmax(0.0, fmax(by0 - ys, ys - by1));
+        const double fx = fmax(xs - bx0, bx1 - xs), fy = fmax(ys - by0, by1 - ys);
+        const double dmin2 = (gx * gx + gy * gy) * (1.0 - 1e-12), dmax2 = (fx * fx + fy * fy) * (1.0 + 1e-12);
+        int a = 0, b = 0;
+#pragma unroll
+        for (int k = 0; k < HTB_NBF; ++k) {
+            const double e = P.Ed[k];
+            a += (e < dmin2) ? 1 : 0;
+            b += (e < dmax2) ? 1 : 0;
+        }
+        slo = a; shi = b;
+        const int u = (dmin2 < P.tiny2) ? 99 : b - a;           // edges inside this lane's range
+        const int umax = __reduce_max_sync(HTB_FULL, u);
+        mode = umax <= 1 ? 1 : (umax <= 3 ? umax : 0);
+        if (mode == 0) return;
+        // this lane's edges: pairs with bits(d^2) <= eb_i are inside edge slo + i; edges at or beyond the range's
+        // upper end hold every pair of the cell (+inf: the compare is always true)
+        const unsigned long long inf = 0x7ff0000000000000ULL;
+        eb0 = u >= 1 ? lds_u64(es + 8u * (uint32_t)a) : inf;
+        eb1 = u >= 2 ? lds_u64(es + 8u * (uint32_t)(a + 1)) : inf;
+        eb2 = u >= 3 ? lds_u64(es + 8u * (uint32_t)(a + 2)) : inf;
+        Pall = C0 = C1 = C2 = 1.0; Eall = E0 = E1 = E2 = 0; n0 = n1 = n2 = 0;
+    }
+    template <int NE>
+    __device__ __forceinline__ void pair_fast(double xj, double yj)
+    {
+        const double dx = xs - xj, dy = ys - yj;
+        const double d = dx * dx + dy * dy;
+        const unsigned long long b = (unsigned long long)__double_as_longlong(d);
+        Pall *= d;
+        const bool c0 = b <= eb0;
+        C0 *= c0 ? d : 1.0;
+        n0 += c0 ? 1u : 0u;
+        if (NE >= 2) {
+            const bool c1 = b <= eb1;
+            C1 *= c1 ? d : 1.0;
+            n1 += c1 ? 1u : 0u;
+        }
+        if (NE >= 3) {
+            const bool c2 = b <= eb2;
+            C2 *= c2 ? d : 1.0;
+            n2 += c2 ? 1u : 0u;
+        }
+    }
+    template <int NE>
+    __device__ __forceinline__ void renorm_all()
+    {
+        renorm(Pall, Eall);
+        renorm(C0, E0);
+        if (NE >= 2) renorm(C1, E1);
+        if (NE >= 3) renorm(C2, E2);
+    }
+    template <int NE>
+    __device__ __forceinline__ void chunk_fast(uint32_t bx, uint32_t by, int lo, int hi, uint32_t tok)
+    {
+        int j = lo;
+        if ((j & 1) && j < hi) { pair_fast<NE>(lds_f64(bx + 8 * j), lds_f64(by + 8 * j)); ++j; }
+#pragma unroll 1
+        for (; j + 8 <= hi; j += 8) {
+            double xa[8], ya[8];
+#pragma unroll
+            for (int u = 0; u < 8; u += 2) {
+                lds_f64x2_tok(bx + 8 * (j + u), tok, xa[u], xa[u + 1]);
+                lds_f64x2_tok(by + 8 * (j + u), tok, ya[u], ya[u + 1]);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) pair_fast<NE>(xa[u], ya[u]);
+            renorm_all<NE>();
+        }
+#pragma unroll 1
+        for (; j < hi; ++j) pair_fast<NE>(lds_f64(bx + 8 * j), lds_f64(by + 8 * j));
+        renorm_all<NE>();
+    }
+    __device__ __forceinline__ void pair_exact(double xj, double yj)
+    {
+        const double dx = xs - xj, dy = ys - yj;
+        const double d = dx * dx + dy * dy;
+        const unsigned long long b = (unsigned long long)__double_as_longlong(d);
+        int s = shi;
+        while (s > slo && b <= lds_u64(es + 8u * (uint32_t)(s - 1))) --s;
+        if (s < P.nrp) {
+            cnt[32 * s] += 1u;
+            if (s >= 1) {
+                Num[32 * s] *= __longlong_as_double((long long)((b & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL));
+                eNum[32 * s] += (int)(b >> 52) - 1023;
+            }
+        }
+    }
+    __device__ __forceinline__ void chunk(uint32_t stage, int lo, int hi, uint32_t tok)
+    {
+        const uint32_t bx = stage, by = stage + 8 * HTB_CH;
+        npart += (unsigned)(hi - lo);
+        if (mode == 1) chunk_fast<1>(bx, by, lo, hi, tok);
+        else if (mode == 2) chunk_fast<2>(bx, by, lo, hi, tok);
+        else if (mode == 3) chunk_fast<3>(bx, by, lo, hi, tok);
+        else {
+#pragma unroll 1
+            for (int j = lo; j < hi; ++j) pair_exact(lds_f64(bx + 8 * j), lds_f64(by + 8 * j));
+            // the exact pairs multiplied mantissas in [1, 2) into Num (<= HTB_CH of them): pull the exponents out
+#pragma unroll 1
+            for (int s = max(slo, 1); s <= min(shi, P.nrp - 1); ++s) renorm(Num[32 * s], eNum[32 * s]);
+        }
+    }
+    __device__ __forceinline__ void bank(double *arr, int *earr, int s, double m, int e)
+    {
+        double v = arr[32 * s] * m;
+        int ee = earr[32 * s] + e;
+        renorm(v, ee);
+        arr[32 * s] = v; earr[32 * s] = ee;
+    }
+    __device__ __forceinline__ void cell_end()
+    {
+        if (mode == 0) return;
+        // cumulative products C_0 <= C_1 <= C_2 <= Pall (as sets of pairs): slot slo + i holds C_i / C_(i-1)
+        cnt[32 * slo] += n0;
+        bank(Num, eNum, slo, C0, E0);
+        double pm = C0; int pe = E0; unsigned pn = n0;
+        if (mode >= 2) {
+            cnt[32 * (slo + 1)] += n1 - pn;
+            bank(Num, eNum, slo + 1, C1, E1);
+            bank(Den, eDen, slo + 1, pm, pe);
+            pm = C1; pe = E1; pn = n1;
+        }
+        if (mode >= 3) {
+            cnt[32 * (slo + 2)] += n2 - pn;
+            bank(Num, eNum, slo + 2, C2, E2);
+            bank(Den, eDen, slo + 2, pm, pe);
+            pm = C2; pe = E2; pn = n2;
+        }
+        cnt[32 * (slo + mode)] += npart - pn;
+        bank(Num, eNum, slo + mode, Pall, Eall);
+        bank(Den, eDen, slo + mode, pm, pe);
+    }
+    __device__ __forceinline__ bool tile_end(const WalkArrays &, const uint32_t (&idx)[1], int, unsigned)
+    {
+        if (valid) {
+            const int nbin = P.nrp - 1;
+            const double m = P.mass;
+            const int64_t row = P.perm1 ? (int64_t)P.perm1[idx[0]] : (int64_t)idx[0];
+            double inside = (double)cnt[0];
+#pragma unroll 1
+            for (int k = 0; k < nbin; ++k) {
+                const int s = k + 1;
+                const double n = (double)cnt[32 * s];
+                // sum over the annulus of ln(d^2 / rp[k+1]^2): exponents and mantissas kept apart
+                const double r2 = P.e0[k + 1];
+                const int rhi = __double2hiint(r2);
+                const int re = (rhi >> 20) - 1023;
+                const double rm = __hiloint2double((rhi & 0x000fffff) | 0x3ff00000, __double2loint(r2));
+                const double ex = (double)(eNum[32 * s] - eDen[32 * s]);
+                const double lm = log(Num[32 * s]) - log(Den[32 * s]);
+                const double lnratio = 0.6931471805599453 * (ex - n * (double)re) + (lm - n * log(rm));
+                const double t = m * (n + lnratio);
+                const double ds = m * inside * 2 * P.e1[k] - t;
+                atomicAdd(&P.out[row * nbin + k], ds / (3.14159265358979323846 * (P.e0[k + 1] - P.e0[k])));
+                inside += n;
+            }
+        }
+        return false;
+    }
+    __device__ __forceinline__ void kernel_end() {}
+};
+
 // ------------------------------------------------------------------ host launchers
 template <class V>
 static int launch_count(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const typename V::Params &P,
@@ -1673,6 +1926,8 @@ int htb_launch_fastxyz(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, 
 { return launch_count<FastXYZ>(st, G, A, P, l); }
 int htb_launch_dsq(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const DSQParams &P, int *l)
 { return launch_count<DSigmaQ>(st, G, A, P, l); }
+int htb_launch_dsr(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const DSRParams &P, int *l)
+{ return launch_count<DSigmaR>(st, G, A, P, l); }
 int htb_launch_gen(cudaStream_t st, int kind, const WalkGeom &G, const WalkArrays &A, const GenParams &P, int *l)
 {
     switch (kind) {

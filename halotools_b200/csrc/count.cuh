@@ -37,6 +37,17 @@ struct DSQParams {
     const uint32_t *perm1;           // sorted position -> input row
 };
 
+// mean_delta_sigma, cell-resolved fast path (DSigmaR): one mass for all particles, 2 <= nrp <= HTB_NBF edges
+struct DSRParams {
+    int nrp;                         // number of rp edges
+    double Ed[HTB_NBF];              // squared edges, ascending; entries >= nrp hold +inf
+    double tiny2;                    // a cell that may hold a pair closer than this (squared) takes the exact path
+    double mass;
+    const double *e0, *e1;           // device: squared edges, ln(rp[k+1]/rp[k])
+    double *out;                     // (n1, nrp - 1) rows in input order
+    const uint32_t *perm1;           // sorted position -> input row
+};
+
 struct GenParams {
     int n0, n1;                      // number of edges along the first / second bin axis
     int nhist;                       // histogram length
@@ -53,6 +64,7 @@ int htb_launch_fast3(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, co
 int htb_launch_markedq(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const Fast3Params &P, int *launches);
 int htb_launch_fastxyz(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const Fast3Params &P, int *launches);
 int htb_launch_dsq(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const DSQParams &P, int *launches);
+int htb_launch_dsr(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const DSRParams &P, int *launches);
 int htb_launch_gen(cudaStream_t st, int kind, const WalkGeom &G, const WalkArrays &A, const GenParams &P, int *launches);
 int htb_build_tiles(cudaStream_t st, Workspace &ws, const WalkGeom &G, const SortedSample &s1,
                     int64_t first_cell1, int64_t last_cell1, const long long *range_dev /* device {first, last} or null */,

@@ -363,3 +363,206 @@ __device__ __forceinline__ void walk_tile(V &v, const WalkGeom &G, const WalkArr
         __syncwarp();
     }
 }
+
+// ------------------------------------------------------------------ cell-resolved walker
+// walk_tile() for variants that take warp-wide decisions PER FINE CELL of sample2 (V::PER_CELL): the spans are the
+// same runs of fine cells along the fast dimension, streamed by the same TMA ring, but the compute side cuts every
+// run at the cell boundaries (one coalesced load of the run's offsets, then shuffles) and brackets the staged
+// points of each non-empty cell with
+//   v.cell_begin(xlo, xhi, ylo, yhi)    the cell's bounding box in sample2's own (unshifted) coordinates, slop included
+//   v.chunk(stage, lo, hi, tok) ...     as in walk_tile
+//   v.cell_end()
+// 2-D only (DIM == 2), no symmetric mode.  V::span_extra() gives 2 * HTB_SPAN_CAP extra u32 of per-warp scratch.
+template <class V>
+__device__ __forceinline__ void walk_tile_cells(V &v, const WalkGeom &G, const WalkArrays &A,
+                                                WarpSmem<V::DIM, V::NPAY> &S, uint32_t &gchunk,
+                                                const double (&blo)[3], const double (&bhi)[3],
+                                                const int (&fs)[3], const int nref,
+                                                unsigned long long &pairs, int tile_cnt,
+                                                const int slice, const int nslices)
+{
+    static_assert(V::DIM == 2, "cell-resolved walker: 2-D meshes only");
+    constexpr int DIM = 2;
+    constexpr int F = 1;
+    const int lane = threadIdx.x & 31;
+    const bool cull = !G.nocull && !((A.flags1[0] | A.flags2[0]) & 1u);
+    uint32_t *extra = v.span_extra();          // per span: {first fine cell of the run (unwrapped, biased), column | ncells << 16}
+
+    int a[3], wlo[3], wn[3];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+        a[d] = (d == F) ? fs[d] : fs[d] / G.m1[d];
+        wlo[d] = (a[d] * G.per[d] - G.cover[d]) * G.m2[d];
+        wn[d] = (G.per[d] * (d == F ? nref : 1) + 2 * G.cover[d]) * G.m2[d];
+    }
+    const int ncol_all = wn[0];
+    const int col0 = (int)((long long)ncol_all * slice / nslices);
+    const int ncol = (int)((long long)ncol_all * (slice + 1) / nslices);
+    const int kfmin = floor_div(wlo[F], G.nf2[F]);
+    const int kfmax = floor_div(wlo[F] + wn[F] - 1, G.nf2[F]);
+
+    int nspan = 0;
+    uint32_t cur_code = 0xffffffffu;
+    auto consume = [&]() {
+        int si = 0, sc = 0;
+        uint32_t ji = 0, jc = 0;
+        if (nspan > 0) { ji = jc = S.span[0] & ~1u; }
+        int inflight = 0;
+        // state of the run being computed
+        int run = -1;                          // span index the cell cursor belongs to
+        int cell = 0, ncell = 0;               // cell cursor inside the run, cells in the run
+        int cbatch = 0;                        // first cell of the offsets held in `bnd`
+        uint32_t bnd = 0;                      // lane l: end offset of cell cbatch + l of the run
+        uint32_t cell_end = 0;
+        int U0 = 0, ufirst = 0;
+        int64_t cbase = 0;
+        bool began = false;
+        while (sc < nspan) {
+            while (si < nspan && inflight < HTB_NSTAGE) {
+                const uint32_t je = S.span[3 * si + 1];
+                const uint32_t jend = (je + 1u) & ~1u;
+                const uint32_t cnt = min((uint32_t)HTB_CH, jend - ji);
+                const int stg = (int)((gchunk + (uint32_t)inflight) % HTB_NSTAGE);
+                if (lane == 0) {
+                    const uint32_t dst = S.stage_s(stg), bar = S.bar(stg);
+                    mbar_expect_tx(bar, cnt * 8u * DIM);
+#pragma unroll
+                    for (int d = 0; d < DIM; ++d)
+                        tma_bulk_g2s(dst + (uint32_t)(d * HTB_CH * 8), A.c2[d] + ji, cnt * 8u, bar);
+                }
+                ++inflight;
+                ji += HTB_CH;
+                if (ji >= je) { ++si; if (si < nspan) ji = S.span[3 * si] & ~1u; }
+            }
+            const uint32_t jb = S.span[3 * sc], je = S.span[3 * sc + 1], code = S.span[3 * sc + 2];
+            const int stg = (int)(gchunk % HTB_NSTAGE);
+            if (code != cur_code) {
+                double sh[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+                for (int d = 0; d < DIM; ++d) {
+                    const int k = (int)((code >> (2 * d)) & 3u) - 1;
+                    sh[d] = (double)(k * G.pbc) * G.period[d];
+                }
+                v.set_shift(sh, A);
+                cur_code = code;
+            }
+            if (run != sc) {
+                // a new run: its cells and their offsets
+                run = sc;
+                const uint32_t e0 = extra[2 * sc], e1 = extra[2 * sc + 1];
+                ufirst = (int)e0 - (1 << 30);                 // unwrapped fine index (fast dim) of the run's first cell
+                U0 = wlo[0] + (int)(e1 & 0xffffu);            // unwrapped fine column
+                ncell = (int)(e1 >> 16);
+                const int k0 = floor_div(U0, G.nf2[0]);
+                const int kf = floor_div(ufirst, G.nf2[F]);
+                cbase = (int64_t)(U0 - k0 * G.nf2[0]) * G.nf2[F] - (int64_t)kf * G.nf2[F];
+                cell = 0; cbatch = 0;
+                bnd = A.off2[cbase + ufirst + 1 + min(lane, ncell - 1)];
+                cell_end = __shfl_sync(HTB_FULL, bnd, 0);
+                began = false;
+            }
+            uint32_t tok = jc;
+            tok += mbar_wait(S.bar(stg), (gchunk / HTB_NSTAGE) & 1u);
+            uint32_t pos = max(jb, jc);
+            const uint32_t end = min(je, jc + HTB_CH);
+            pairs += (unsigned long long)(end - pos) * (unsigned)tile_cnt;
+            while (pos < end) {
+                while (cell_end <= pos) {
+                    // the cell is exhausted: close it, move to the next one of the run
+                    if (began) { v.cell_end(); began = false; }
+                    ++cell;
+                    if (cell - cbatch >= 32) {
+                        cbatch = cell;
+                        bnd = A.off2[cbase + ufirst + 1 + min(cbatch + lane, ncell - 1)];
+                    }
+                    cell_end = __shfl_sync(HTB_FULL, bnd, cell - cbatch);
+                }
+                if (!began) {
+                    const int u = ufirst + cell;
+                    const int kf = floor_div(u, G.nf2[F]), k0 = floor_div(U0, G.nf2[0]);
+                    const double x0 = (double)(U0 - k0 * G.nf2[0]) * G.h2[0], y0 = (double)(u - kf * G.nf2[F]) * G.h2[F];
+                    v.cell_begin(x0 - G.slop[0], x0 + G.h2[0] + G.slop[0], y0 - G.slop[F], y0 + G.h2[F] + G.slop[F]);
+                    began = true;
+                }
+                const uint32_t seg = min(end, cell_end);
+                v.chunk(S.stage_s(stg), (int)(pos - jc), (int)(seg - jc), tok);
+                pos = seg;
+            }
+            __syncwarp();
+            ++gchunk;
+            --inflight;
+            jc += HTB_CH;
+            if (jc >= je) {
+                if (began) { v.cell_end(); began = false; }
+                ++sc;
+                if (sc < nspan) jc = S.span[3 * sc] & ~1u;
+            }
+        }
+        nspan = 0;
+    };
+
+    int base = col0, kf = kfmin;
+    bool more = ncol > col0;
+    while (more) {
+        while (true) {
+            if (base >= ncol) { more = false; break; }
+            const int col = base + lane;
+            const bool valid = col < ncol;
+            const int U = wlo[0] + col;
+            double d2 = 0.0;
+            uint32_t code = 0;
+            int64_t slowlin = 0;
+            {
+                const int k = floor_div(U, G.nf2[0]);
+                const int w = U - k * G.nf2[0];
+                const int kc = k < -1 ? -1 : (k > 1 ? 1 : k);
+                const double elo = (double)w * G.h2[0] + (double)(kc * G.pbc) * G.period[0] - G.slop[0];
+                const double ehi = elo + G.h2[0] + 2.0 * G.slop[0];
+                const double gap = fmax(0.0, fmax(elo - bhi[0], blo[0] - ehi));
+                d2 = gap * gap;
+                code = (uint32_t)(kc + 1);
+                slowlin = w;
+            }
+            const bool keep = valid && (!cull || d2 <= G.r2slow);
+            double reach = 0.0;
+            if (cull) reach = sqrt(fmax(G.r2slow - d2, 0.0)) + G.slop[F];
+            {
+                const int k = kf;
+                const int kc = k < -1 ? -1 : (k > 1 ? 1 : k);
+                int plo = max(wlo[F], k * G.nf2[F]);
+                int phi = min(wlo[F] + wn[F], (k + 1) * G.nf2[F]) - 1;
+                bool has = keep && plo <= phi;
+                if (has && cull) {
+                    const double offc = -(double)k * G.period[F] + (double)(kc * G.pbc) * G.period[F];
+                    const double qlo = (blo[F] - reach - offc) / G.h2[F];
+                    const double qhi = (bhi[F] + reach - offc) / G.h2[F];
+                    plo = (int)fmax(floor(qlo), (double)plo);
+                    phi = (int)fmin(floor(qhi), (double)phi);
+                    has = plo <= phi;
+                }
+                uint32_t jb = 0, je = 0;
+                if (has) {
+                    const int64_t cb = slowlin * G.nf2[F] - (int64_t)k * G.nf2[F];
+                    jb = A.off2[cb + plo];
+                    je = A.off2[cb + phi + 1];
+                    has = je > jb;
+                }
+                const uint32_t bal = __ballot_sync(HTB_FULL, has);
+                if (has) {
+                    const int pos = nspan + __popc(bal & ((1u << lane) - 1u));
+                    S.span[3 * pos] = jb;
+                    S.span[3 * pos + 1] = je;
+                    S.span[3 * pos + 2] = code | ((uint32_t)(kc + 1) << (2 * F));
+                    extra[2 * pos] = (uint32_t)(plo + (1 << 30));
+                    extra[2 * pos + 1] = (uint32_t)col | ((uint32_t)(phi - plo + 1) << 16);
+                }
+                nspan += __popc(bal);
+            }
+            if (++kf > kfmax) { kf = kfmin; base += 32; }
+            if (nspan + 32 > HTB_SPAN_CAP) break;
+        }
+        __syncwarp();
+        consume();
+        __syncwarp();
+    }
+}

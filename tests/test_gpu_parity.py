@@ -303,15 +303,23 @@ def test_fast_marked_not_taken_for_other_marks(golden):
     assert np.allclose(got, want, rtol=1e-12, atol=0)
 
 
+@pytest.mark.parametrize("kernel", ["cells", "queue"])
 @pytest.mark.parametrize("nrp", [2, 3, 9, 16])
-def test_fast_delta_sigma_path_vs_oracle(nrp):
+def test_fast_delta_sigma_path_vs_oracle(nrp, kernel):
+    """the two uniform-mass kernels: cell-resolved (DSigmaR, path 2) and per-pair queue (DSigmaQ, path 1)"""
+    import os
     rng = np.random.RandomState(15)
     L = 200.0
     gal = _dup_points(rng, 3000, L)
     ptcl = np.vstack([gal[:500], _dup_points(rng, 150000, L)])       # particles on top of galaxies: d == 0
     rp = np.logspace(-1, np.log10(20.0), nrp)
-    got = hb.mean_delta_sigma(gal, ptcl, 2.5, rp, period=L, per_object=True)
-    assert _lib.last_stats["path"] == 1, "fast delta-sigma kernel not taken"
+    if kernel == "queue":
+        os.environ["HTB_NO_DSR"] = "1"
+    try:
+        got = hb.mean_delta_sigma(gal, ptcl, 2.5, rp, period=L, per_object=True)
+    finally:
+        os.environ.pop("HTB_NO_DSR", None)
+    assert _lib.last_stats["path"] == (2 if kernel == "cells" else 1), "fast delta-sigma kernel not taken"
     want = oracle.mean_delta_sigma(gal, ptcl, 2.5, rp, period=L, per_object=True, num_threads=4)
     scale = np.max(np.abs(want))
     assert np.allclose(got, want, rtol=1e-10, atol=1e-12 * scale), np.max(np.abs(got - want)) / scale
@@ -474,3 +482,31 @@ def test_upload_cache_reuses_only_caller_owned_arrays():
     DD, DR, RR = (np.diff(oracle.npairs_3d(x, y, rb, period=L, num_threads=4)) for x, y in ((a, a), (a, b), (b, b)))
     from halotools_b200.two_point_clustering.tpcf_estimators import _TP_estimator
     assert np.allclose(xi, _TP_estimator(DD, DR, RR, len(a), len(a), len(b), len(b), "Landy-Szalay"), rtol=1e-12)
+
+
+@pytest.mark.parametrize("case", ["dense", "sparse", "wide_bins", "nonperiodic", "rect"])
+def test_cell_resolved_delta_sigma_vs_oracle(case):
+    """DSigmaR decides the annulus per (galaxy, particle cell): dense / sparse cells, two wide bins (cells that hold a
+    galaxy cross one edge), non-periodic enclosing box, non-square box"""
+    rng = np.random.RandomState(22)
+    L, period = 300.0, 300.0
+    ngal, nptcl, rp = 4000, 600000, np.logspace(-1, np.log10(25.0), 13)
+    if case == "sparse":
+        nptcl = 20000
+    elif case == "wide_bins":
+        rp = np.array([2.0, 30.0])
+    elif case == "rect":
+        period = [300.0, 200.0, 100.0]
+    gal = rng.uniform(0, 1, (ngal, 3)) * (period if case == "rect" else L)
+    ptcl = rng.uniform(0, 1, (nptcl, 3)) * (period if case == "rect" else L)
+    # a clump of particles right on top of / very close to some galaxies
+    ptcl[:200] = gal[:200]
+    ptcl[200:400, :2] = gal[200:400, :2] + 1e-9
+    kw = {} if case == "nonperiodic" else {"period": period}
+    g1, p1 = (gal.copy(), ptcl.copy()) if case == "nonperiodic" else (gal, ptcl)      # the non-periodic path shifts in place
+    got = hb.mean_delta_sigma(g1, p1, 0.7, rp, per_object=True, **kw)
+    assert _lib.last_stats["path"] == 2, "cell-resolved kernel not taken"
+    g2, p2 = (gal.copy(), ptcl.copy()) if case == "nonperiodic" else (gal, ptcl)
+    want = oracle.mean_delta_sigma(g2, p2, 0.7, rp, per_object=True, num_threads=8, **kw)
+    scale = np.max(np.abs(want))
+    assert np.allclose(got, want, rtol=1e-10, atol=1e-12 * scale), np.max(np.abs(got - want)) / scale
