@@ -530,13 +530,6 @@ struct Call {
         for (int d = 0; d < dim && sym; ++d) sym = (g->ndivs1[d] == g->ndivs2[d]);
         if (sym) for (int d = 0; d < dim; ++d) m1[d] = m2[d];
         const FineGrid g1 = make_grid(g, 0, m1), g2 = make_grid(g, 1, m2);
-        if (sym) {
-            if (htb_sort_sample(st, ws, g2, d2, ds2, n2, dw2, nw, perm1, sentinel, s2, &launches)) return 1;
-            s1 = s2;
-        } else {
-            if (htb_sort_sample(st, ws, g1, d1, ds1, n1, dw1, nw, perm1, sentinel, s1, &launches)) return 1;
-            if (htb_sort_sample(st, ws, g2, d2, ds2, n2, dw2, nw, false, sentinel, s2, &launches)) return 1;
-        }
         G.sym = sym ? 1 : 0;
         G.tile = tile;
         G.sentinel = sentinel;
@@ -586,17 +579,35 @@ struct Call {
         }
         if (sphere && g->search[dim - 1] > rslow) rslow = g->search[dim - 1];
         G.r2slow = rslow * rslow * (1.0 + 1e-9);
-        // ---- tiles + counters
-        uint2 *tiles = nullptr;
-        uint32_t *ntiles_dev = nullptr;
+        // ---- K1: counting sort of both samples
         if (g_shard_world > 1) {
-            // this rank's share of [first_cell1, last_cell1), cut by predicted work on the device (no host sync)
+            // One rank of a sharded call: cell ids and per-cell counts of BOTH samples first; from them this rank's
+            // share of [first_cell1, last_cell1), cut by predicted work on the device (no host sync); then only the
+            // points inside the x-layers that share can touch are put in order (the rest is never moved).
+            if (!sym && htb_sort_begin(st, ws, g1, d1, ds1, n1, dw1, nw, perm1, s1, &launches)) return 1;
+            if (htb_sort_begin(st, ws, g2, d2, ds2, n2, dw2, nw, sym ? perm1 : false, s2, &launches)) return 1;
             double *balance_dev = nullptr;
-            if (htb_reference_work(st, ws, G, s1, s2, &work_dev, &balance_dev, &nc1, &launches)) return 1;
+            if (htb_reference_work(st, ws, G, sym ? s2 : s1, s2, &work_dev, &balance_dev, &nc1, &launches, true)) return 1;
             if (ws.alloc((void **)&range_dev, 2 * sizeof(long long))) return 1;
             const int64_t lo = first_cell1 < 0 ? 0 : first_cell1, hi = last_cell1 > nc1 ? nc1 : last_cell1;
             if (htb_shard_range(st, balance_dev, lo, hi, g_shard_rank, g_shard_world, range_dev, &launches)) return 1;
+            int *xwin = nullptr;
+            if (ws.alloc((void **)&xwin, 4 * sizeof(int))) return 1;
+            if (htb_shard_windows(st, range_dev, G, xwin, &launches)) return 1;
+            const bool window = !getenv("HTB_NO_WINDOW_SORT");
+            if (!sym && htb_sort_finish(st, ws, d1, ds1, dw1, nw, sentinel, window ? xwin : nullptr, s1, &launches)) return 1;
+            if (htb_sort_finish(st, ws, d2, ds2, dw2, nw, sentinel, window ? xwin + 2 : nullptr, s2, &launches)) return 1;
+            if (sym) s1 = s2;
+        } else if (sym) {
+            if (htb_sort_sample(st, ws, g2, d2, ds2, n2, dw2, nw, perm1, sentinel, s2, &launches)) return 1;
+            s1 = s2;
+        } else {
+            if (htb_sort_sample(st, ws, g1, d1, ds1, n1, dw1, nw, perm1, sentinel, s1, &launches)) return 1;
+            if (htb_sort_sample(st, ws, g2, d2, ds2, n2, dw2, nw, false, sentinel, s2, &launches)) return 1;
         }
+        // ---- tiles + counters
+        uint2 *tiles = nullptr;
+        uint32_t *ntiles_dev = nullptr;
         if (htb_build_tiles(st, ws, G, s1, first_cell1, last_cell1, range_dev, &tiles, &ntiles_dev, &max_tiles, &launches)) return 1;
         if (ws.alloc((void **)&ctr, 64)) return 1;
         HTB_CUDA(cudaMemsetAsync(ctr, 0, 64, st));

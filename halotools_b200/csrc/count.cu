@@ -173,7 +173,7 @@ k_count(const __grid_constant__ WalkGeom G, const __grid_constant__ WalkArrays A
     constexpr int F = DIM - 1;
     constexpr int PPL = V::PPL;                 // sample1 points per lane; a tile holds 32 * PPL points
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    typedef WarpSmem<DIM, V::NPAY> WS;
+    typedef WarpSmem<DIM, V::NPAY, HtbChunk<V>::value> WS;
     unsigned char *mine = smem_raw + (size_t)warp * (WS::bytes() + (size_t)scratch_bytes_per_warp);
     WS S;
     S.stage0 = (double *)mine;
@@ -1663,28 +1663,40 @@ struct DSigmaQ {
 //     exact per-pair scan for that cell (slot search bounded by the lane's range).
 // Slots: s = number of edges e with e < d^2 (0: inside rp[0], 1..nrp-1: annulus s-1, nrp: outside); every decision
 // is the reference's exact `dxy_sq <= rp^2` on the same f64 value, so only the summation order differs.
+#ifndef DSR_WARPS
+#define DSR_WARPS 4
+#define DSR_MINBLOCKS 4
+#endif
+#ifndef DSR_CH
+#define DSR_CH 128          // particles per staged chunk
+#endif
 struct DSigmaR {
-    static constexpr int DIM = 2, NPAY = 0, PPL = 1, WARPS = 4, MINBLOCKS = 2;
+    static constexpr int DIM = 2, NPAY = 0, PPL = 1, WARPS = DSR_WARPS, MINBLOCKS = DSR_MINBLOCKS;
     static constexpr bool TMA = true, PER_CELL = true;
+    static constexpr int CH = DSR_CH;
     static constexpr int NS = HTB_NBF + 4;
     typedef DSRParams Params;
     const Params &P;
     int lane;
     uint32_t *extra;
-    double *Num, *Den;          // [NS][32] mantissas in [1, 2) of the numerator / denominator products per slot
-    int *eNum, *eDen;           // ... their binary exponents
-    unsigned *cnt;              // [NS][32] pair counts per slot
+    // per-lane accumulators per slot, indexed with the lane's own slot numbers: they live in LOCAL memory (L1
+    // resident, touched only at cell boundaries and by the exact path), which keeps shared memory for the staging
+    // ring and lets 12-16 warps per SM hide the f64 latencies
+    double Num[NS], Den[NS];    // mantissas in [1, 2) of the numerator / denominator products
+    int eNum[NS], eDen[NS];     // ... their binary exponents
+    unsigned cnt[NS];           // pair counts
     uint32_t es;                // shared-space address of the warp's copy of the squared edges (+inf padded)
     double x, y, xs, ys;
     bool valid, always_exact;
     int mode;                   // warp-uniform: 1..3 = edges per lane handled in registers, 0 = exact scan
+    int uex;                    // warp-uniform: edges the exact scan has to test per pair (the widest lane range)
     int slo, shi;
     unsigned long long eb0, eb1, eb2;
     double Pall, C0, C1, C2;
     int Eall, E0, E1, E2;
     unsigned n0, n1, n2, npart;
 
-    static size_t scratch_bytes(const Params &) { return 8 * HTB_SPAN_CAP + 8 * (HTB_NBF + 4) + (size_t)NS * 32 * (8 + 8 + 4 + 4 + 4); }
+    static size_t scratch_bytes(const Params &) { return 8 * HTB_SPAN_CAP + 8 * (2 * HTB_NBF + 4); }
     __device__ __forceinline__ uint32_t *span_extra() { return extra; }
     __device__ __forceinline__ void tile_weight(unsigned) {}
     __device__ __forceinline__ void force_exact() {}
@@ -1692,15 +1704,10 @@ struct DSigmaR {
     {
         unsigned char *b = (unsigned char *)scratch;
         extra = (uint32_t *)b; b += 8 * HTB_SPAN_CAP;
-        double *ed = (double *)b; b += 8 * (HTB_NBF + 4);
+        double *ed = (double *)b; b += 8 * (2 * HTB_NBF + 4);
         es = smem_u32(ed);
-        if (ln < HTB_NBF + 4) ed[ln] = ln < HTB_NBF ? P.Ed[ln] : __longlong_as_double(0x7ff0000000000000LL);
-        Num = (double *)b + ln; b += 8 * 32 * NS;
-        Den = (double *)b + ln; b += 8 * 32 * NS;
-        eNum = (int *)b + ln; b += 4 * 32 * NS;
-        eDen = (int *)b + ln; b += 4 * 32 * NS;
-        cnt = (unsigned *)b + ln;
-        x = y = xs = ys = 0.0; valid = false; mode = 1; slo = shi = 0; eb0 = eb1 = eb2 = 0;
+        for (int k = ln; k < 2 * HTB_NBF + 4; k += 32) ed[k] = k < HTB_NBF ? P.Ed[k] : __longlong_as_double(0x7ff0000000000000LL);
+        x = y = xs = ys = 0.0; valid = false; mode = 1; uex = 0; slo = shi = 0; eb0 = eb1 = eb2 = 0;
         Pall = C0 = C1 = C2 = 1.0; Eall = E0 = E1 = E2 = 0; n0 = n1 = n2 = npart = 0;
         always_exact = ((A.flags1[0] | A.flags2[0]) & 1u) != 0u;
         __syncwarp();
@@ -1714,7 +1721,7 @@ struct DSigmaR {
         x = valid ? p[0][0] : x0;
         y = valid ? p[0][1] : y0;
 #pragma unroll
-        for (int s = 0; s < NS; ++s) { Num[32 * s] = 1.0; Den[32 * s] = 1.0; eNum[32 * s] = 0; eDen[32 * s] = 0; cnt[32 * s] = 0u; }
+        for (int s = 0; s < NS; ++s) { Num[s] = 1.0; Den[s] = 1.0; eNum[s] = 0; eDen[s] = 0; cnt[s] = 0u; }
     }
     __device__ __forceinline__ void set_shift(const double (&sh)[3], const WalkArrays &)
     {
@@ -1729,7 +1736,7 @@ struct DSigmaR {
     __device__ __forceinline__ void cell_begin(double bx0, double bx1, double by0, double by1)
     {
         npart = 0;
-        if (always_exact) { slo = 0; shi = P.nrp; mode = 0; return; }
+        if (always_exact) { slo = 0; shi = P.nrp; mode = 0; uex = P.nrp; return; }
         const double gx = fmax(0.0, fmax(bx0 - xs, xs - bx1)), gy = fmax(0.0, fmax(by0 - ys, ys - by1));
         const double fx = fmax(xs - bx0, bx1 - xs), fy = fmax(ys - by0, by1 - ys);
         const double dmin2 = (gx * gx + gy * gy) * (1.0 - 1e-12), dmax2 = (fx * fx + fy * fy) * (1.0 + 1e-12);
@@ -1744,7 +1751,7 @@ struct DSigmaR {
         const int u = (dmin2 < P.tiny2) ? 99 : b - a;           // edges inside this lane's range
         const int umax = __reduce_max_sync(HTB_FULL, u);
         mode = umax <= 1 ? 1 : (umax <= 3 ? umax : 0);
-        if (mode == 0) return;
+        if (mode == 0) { uex = __reduce_max_sync(HTB_FULL, b - a); return; }
         // this lane's edges: pairs with bits(d^2) <= eb_i are inside edge slo + i; edges at or beyond the range's
         // upper end hold every pair of the cell (+inf: the compare is always true)
         const unsigned long long inf = 0x7ff0000000000000ULL;
@@ -1753,6 +1760,13 @@ struct DSigmaR {
         eb2 = u >= 3 ? lds_u64(es + 8u * (uint32_t)(a + 2)) : inf;
         Pall = C0 = C1 = C2 = 1.0; Eall = E0 = E1 = E2 = 0; n0 = n1 = n2 = 0;
     }
+    // if (bits(d) <= edge) { C *= d; n += 1; } as one 64-bit compare, a predicated DMUL and a predicated IADD
+    // (left to the compiler this becomes an unconditional DMUL, two selects and two integer instructions)
+    static __device__ __forceinline__ void below(double &C, unsigned &n, double d, unsigned long long b, unsigned long long edge)
+    {
+        asm("{\n\t.reg .pred p;\n\tsetp.le.u64 p, %3, %4;\n\t@p mul.rn.f64 %0, %0, %2;\n\t@p add.u32 %1, %1, 1;\n\t}"
+            : "+d"(C), "+r"(n) : "d"(d), "l"(b), "l"(edge));
+    }
     template <int NE>
     __device__ __forceinline__ void pair_fast(double xj, double yj)
     {
@@ -1760,19 +1774,9 @@ struct DSigmaR {
         const double d = dx * dx + dy * dy;
         const unsigned long long b = (unsigned long long)__double_as_longlong(d);
         Pall *= d;
-        const bool c0 = b <= eb0;
-        C0 *= c0 ? d : 1.0;
-        n0 += c0 ? 1u : 0u;
-        if (NE >= 2) {
-            const bool c1 = b <= eb1;
-            C1 *= c1 ? d : 1.0;
-            n1 += c1 ? 1u : 0u;
-        }
-        if (NE >= 3) {
-            const bool c2 = b <= eb2;
-            C2 *= c2 ? d : 1.0;
-            n2 += c2 ? 1u : 0u;
-        }
+        below(C0, n0, d, b, eb0);
+        if (NE >= 2) below(C1, n1, d, b, eb1);
+        if (NE >= 3) below(C2, n2, d, b, eb2);
     }
     template <int NE>
     __device__ __forceinline__ void renorm_all()
@@ -1803,24 +1807,29 @@ struct DSigmaR {
         for (; j < hi; ++j) pair_fast<NE>(lds_f64(bx + 8 * j), lds_f64(by + 8 * j));
         renorm_all<NE>();
     }
+    // exact path: the slot of a pair is slo + the number of this lane's edges below d^2; every lane tests the same
+    // number of edges (uex, the widest range of the warp - edges beyond a lane's own range cannot be below d^2, and
+    // the table is padded with +inf), so the loop is uniform and its loads are independent
     __device__ __forceinline__ void pair_exact(double xj, double yj)
     {
         const double dx = xs - xj, dy = ys - yj;
         const double d = dx * dx + dy * dy;
         const unsigned long long b = (unsigned long long)__double_as_longlong(d);
-        int s = shi;
-        while (s > slo && b <= lds_u64(es + 8u * (uint32_t)(s - 1))) --s;
+        int s = slo;
+        const uint32_t e0 = es + 8u * (uint32_t)slo;
+#pragma unroll 4
+        for (int k = 0; k < uex; ++k) s += (b > lds_u64(e0 + 8u * (uint32_t)k)) ? 1 : 0;
         if (s < P.nrp) {
-            cnt[32 * s] += 1u;
+            cnt[s] += 1u;
             if (s >= 1) {
-                Num[32 * s] *= __longlong_as_double((long long)((b & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL));
-                eNum[32 * s] += (int)(b >> 52) - 1023;
+                Num[s] *= __longlong_as_double((long long)((b & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL));
+                eNum[s] += (int)(b >> 52) - 1023;
             }
         }
     }
     __device__ __forceinline__ void chunk(uint32_t stage, int lo, int hi, uint32_t tok)
     {
-        const uint32_t bx = stage, by = stage + 8 * HTB_CH;
+        const uint32_t bx = stage, by = stage + 8 * CH;
         npart += (unsigned)(hi - lo);
         if (mode == 1) chunk_fast<1>(bx, by, lo, hi, tok);
         else if (mode == 2) chunk_fast<2>(bx, by, lo, hi, tok);
@@ -1828,38 +1837,38 @@ struct DSigmaR {
         else {
 #pragma unroll 1
             for (int j = lo; j < hi; ++j) pair_exact(lds_f64(bx + 8 * j), lds_f64(by + 8 * j));
-            // the exact pairs multiplied mantissas in [1, 2) into Num (<= HTB_CH of them): pull the exponents out
+            // the exact pairs multiplied mantissas in [1, 2) into Num (<= CH of them): pull the exponents out
 #pragma unroll 1
-            for (int s = max(slo, 1); s <= min(shi, P.nrp - 1); ++s) renorm(Num[32 * s], eNum[32 * s]);
+            for (int s = max(slo, 1); s <= min(shi, P.nrp - 1); ++s) renorm(Num[s], eNum[s]);
         }
     }
     __device__ __forceinline__ void bank(double *arr, int *earr, int s, double m, int e)
     {
-        double v = arr[32 * s] * m;
-        int ee = earr[32 * s] + e;
+        double v = arr[s] * m;
+        int ee = earr[s] + e;
         renorm(v, ee);
-        arr[32 * s] = v; earr[32 * s] = ee;
+        arr[s] = v; earr[s] = ee;
     }
     __device__ __forceinline__ void cell_end()
     {
         if (mode == 0) return;
         // cumulative products C_0 <= C_1 <= C_2 <= Pall (as sets of pairs): slot slo + i holds C_i / C_(i-1)
-        cnt[32 * slo] += n0;
+        cnt[slo] += n0;
         bank(Num, eNum, slo, C0, E0);
         double pm = C0; int pe = E0; unsigned pn = n0;
         if (mode >= 2) {
-            cnt[32 * (slo + 1)] += n1 - pn;
+            cnt[slo + 1] += n1 - pn;
             bank(Num, eNum, slo + 1, C1, E1);
             bank(Den, eDen, slo + 1, pm, pe);
             pm = C1; pe = E1; pn = n1;
         }
         if (mode >= 3) {
-            cnt[32 * (slo + 2)] += n2 - pn;
+            cnt[slo + 2] += n2 - pn;
             bank(Num, eNum, slo + 2, C2, E2);
             bank(Den, eDen, slo + 2, pm, pe);
             pm = C2; pe = E2; pn = n2;
         }
-        cnt[32 * (slo + mode)] += npart - pn;
+        cnt[slo + mode] += npart - pn;
         bank(Num, eNum, slo + mode, Pall, Eall);
         bank(Den, eDen, slo + mode, pm, pe);
     }
@@ -1873,14 +1882,14 @@ struct DSigmaR {
 #pragma unroll 1
             for (int k = 0; k < nbin; ++k) {
                 const int s = k + 1;
-                const double n = (double)cnt[32 * s];
+                const double n = (double)cnt[s];
                 // sum over the annulus of ln(d^2 / rp[k+1]^2): exponents and mantissas kept apart
                 const double r2 = P.e0[k + 1];
                 const int rhi = __double2hiint(r2);
                 const int re = (rhi >> 20) - 1023;
                 const double rm = __hiloint2double((rhi & 0x000fffff) | 0x3ff00000, __double2loint(r2));
-                const double ex = (double)(eNum[32 * s] - eDen[32 * s]);
-                const double lm = log(Num[32 * s]) - log(Den[32 * s]);
+                const double ex = (double)(eNum[s] - eDen[s]);
+                const double lm = log(Num[s]) - log(Den[s]);
                 const double lnratio = 0.6931471805599453 * (ex - n * (double)re) + (lm - n * log(rm));
                 const double t = m * (n + lnratio);
                 const double ds = m * inside * 2 * P.e1[k] - t;
@@ -1898,7 +1907,7 @@ template <class V>
 static int launch_count(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const typename V::Params &P,
                         int *launches)
 {
-    typedef WarpSmem<V::DIM, V::NPAY> WS;
+    typedef WarpSmem<V::DIM, V::NPAY, HtbChunk<V>::value> WS;
     const size_t scratch = (V::scratch_bytes(P) + 15) & ~(size_t)15;
     const size_t smem = V::WARPS * (WS::bytes() + scratch);
     if (smem > 200 * 1024) {
@@ -1940,6 +1949,29 @@ int htb_launch_gen(cudaStream_t st, int kind, const WalkGeom &G, const WalkArray
     }
     htb_set_error("unknown kernel kind %d", kind);
     return 1;
+}
+
+// x-layer windows of a rank's cell range: mesh1 layers [first / (ny nz), (last - 1) / (ny nz)] and the mesh2 layers
+// their neighbour windows reach (npairs_3d_engine.pyx:117-123); xwin = {first layer, layers} (mesh1), {..} (mesh2)
+__global__ void k_shard_windows(const long long *__restrict__ range, WalkGeom G, int *__restrict__ xwin)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    long long per0 = 1;
+    for (int d = 1; d < G.dim; ++d) per0 *= G.nd1[d];
+    const long long first = range[0], last = range[1];
+    if (last <= first) { xwin[0] = 0; xwin[1] = 0; xwin[2] = 0; xwin[3] = 0; return; }
+    const int lo = (int)(first / per0), hi = (int)((last - 1) / per0);
+    xwin[0] = lo; xwin[1] = hi - lo + 1;
+    xwin[2] = lo * G.per[0] - G.cover[0];
+    xwin[3] = (hi - lo + 1) * G.per[0] + 2 * G.cover[0];
+}
+
+int htb_shard_windows(cudaStream_t st, const long long *range_dev, const WalkGeom &G, int *xwin_dev, int *launches)
+{
+    k_shard_windows<<<1, 32, 0, st>>>(range_dev, G, xwin_dev);
+    if (launches) *launches += 1;
+    HTB_CUDA(cudaGetLastError());
+    return 0;
 }
 
 int htb_shard_range(cudaStream_t st, const double *work_dev, int64_t first_cell1, int64_t last_cell1,
@@ -1984,7 +2016,7 @@ int htb_build_tiles(cudaStream_t st, Workspace &ws, const WalkGeom &G, const Sor
 
 int htb_reference_work(cudaStream_t st, Workspace &ws, const WalkGeom &G, const SortedSample &s1,
                        const SortedSample &s2, double **work_dev_out, double **balance_dev_out, int64_t *ncell1_out,
-                       int *launches)
+                       int *launches, bool presort)
 {
     int64_t nc1 = 1, nc2 = 1;
     for (int d = 0; d < G.dim; ++d) { nc1 *= G.nd1[d]; nc2 *= G.nd2[d]; }
@@ -1996,8 +2028,13 @@ int htb_reference_work(cudaStream_t st, Workspace &ws, const WalkGeom &G, const 
     if (ws.alloc((void **)&work, sizeof(double) * (size_t)nc1)) return 1;
     HTB_CUDA(cudaMemsetAsync(rc1, 0, sizeof(uint32_t) * (size_t)nc1, st));
     HTB_CUDA(cudaMemsetAsync(rc2, 0, sizeof(uint32_t) * (size_t)nc2, st));
-    if (htb_ref_cell_counts(st, s1, rc1, launches)) return 1;
-    if (htb_ref_cell_counts(st, s2, rc2, launches)) return 1;
+    if (presort) {
+        if (htb_ref_cell_counts_pre(st, s1, rc1, launches)) return 1;
+        if (htb_ref_cell_counts_pre(st, s2, rc2, launches)) return 1;
+    } else {
+        if (htb_ref_cell_counts(st, s1, rc1, launches)) return 1;
+        if (htb_ref_cell_counts(st, s2, rc2, launches)) return 1;
+    }
     int blocks = (int)((nc1 + 127) / 128);
     if (blocks > 148 * 8) blocks = 148 * 8;
     k_wref<<<blocks, 128, 0, st>>>(rc1, rc2, G, nc1, work, balance);

@@ -74,4 +74,5 @@ int htb_shard_range(cudaStream_t st, const double *work_dev, int64_t first_cell1
                     int rank, int world, long long *range_dev, int *launches);
 int htb_reference_work(cudaStream_t st, Workspace &ws, const WalkGeom &G, const SortedSample &s1,
                        const SortedSample &s2, double **work_dev_out, double **balance_dev_out /* may be null */,
-                       int64_t *ncell1_out, int *launches);
+                       int64_t *ncell1_out, int *launches, bool presort = false /* samples only went through htb_sort_begin */);
+int htb_shard_windows(cudaStream_t st, const long long *range_dev, const WalkGeom &G, int *xwin_dev /* [4] */, int *launches);

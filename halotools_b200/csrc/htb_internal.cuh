@@ -54,6 +54,7 @@ struct SortedSample {
     uint32_t *flags = nullptr;  // [1] bit0: some point lies outside [0, period] in some dimension
     uint32_t *cell = nullptr;   // scratch [n]: fine cell id per input point
     uint32_t *rank = nullptr;   // scratch [n]: arrival rank inside the cell
+    uint32_t *count = nullptr;  // scratch [ncells + 2]: points per fine cell
 };
 
 struct Workspace;   // stream-ordered allocations of one engine call (freed at the end)
@@ -62,6 +63,14 @@ struct Workspace;   // stream-ordered allocations of one engine call (freed at t
 int htb_sort_sample(cudaStream_t st, Workspace &ws, const FineGrid &g,
                     const double *const *coords_dev, int64_t stride, int64_t n,
                     const double *w_dev, int nw, bool keep_perm, double pad_value, SortedSample &out, int *launches);
+// the same sort in two halves, so that a rank of a sharded call can look at the cell counts of both samples,
+// settle its cell range and drop the points outside its window (xwin_dev: device {first reference x-layer, layers})
+int htb_sort_begin(cudaStream_t st, Workspace &ws, const FineGrid &g,
+                   const double *const *coords_dev, int64_t stride, int64_t n,
+                   const double *w_dev, int nw, bool keep_perm, SortedSample &out, int *launches);
+int htb_sort_finish(cudaStream_t st, Workspace &ws, const double *const *coords_dev, int64_t stride,
+                    const double *w_dev, int nw, double pad_value, const int *xwin_dev, SortedSample &out, int *launches);
+int htb_ref_cell_counts_pre(cudaStream_t st, const SortedSample &s, uint32_t *counts_dev /* [prod nd] zeroed */, int *launches);
 int htb_exclusive_scan_u32(cudaStream_t st, Workspace &ws, const uint32_t *in, uint32_t *out,
                            int64_t n, uint32_t *total_dev, int *launches);
 int htb_ref_cell_ids(cudaStream_t st, int dim, const double *const *coords_dev, int64_t stride, int64_t n,

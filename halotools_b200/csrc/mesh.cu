@@ -50,7 +50,9 @@ k_scatter(const double *__restrict__ x, const double *__restrict__ y, const doub
           const double *__restrict__ w, double *__restrict__ ow, int nw)
 {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const uint32_t pos = off[cell[i]] + rank[i];
+        const uint32_t cid = cell[i];
+        const uint32_t pos = off[cid] + rank[i];
+        if (off[cid + 1] == off[cid]) continue;       // the cell was emptied: outside this rank's window (htb_sort_finish)
         ox[pos] = x[i * stride];
         oy[pos] = y[i * stride];
         if (DIM == 3) oz[pos] = z[i * stride];
@@ -187,9 +189,26 @@ static int grid_for(int64_t n, int threads)
     return (int)b;
 }
 
-int htb_sort_sample(cudaStream_t st, Workspace &ws, const FineGrid &g,
-                    const double *const *cd, int64_t stride, int64_t n,
-                    const double *w_dev, int nw, bool keep_perm, double pad_value, SortedSample &out, int *launches)
+// fine cells whose reference index along dimension 0 is outside the window {first layer (may be negative), layers}
+// lose their points: a rank that counts only some x-layers of mesh1 cells needs the points of its own window only
+__global__ void k_mask_counts(uint32_t *__restrict__ count, FineGrid g, const int *__restrict__ xwin)
+{
+    const int lo = xwin[0], cnt = xwin[1];
+    if (cnt >= g.nd[0]) return;
+    int64_t per0 = 1;
+    for (int d = 1; d < g.dim; ++d) per0 *= g.nf[d];
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < g.ncells; c += (int64_t)gridDim.x * blockDim.x) {
+        const int r0 = (int)(c / per0) / g.m[0];
+        int rel = (r0 - lo) % g.nd[0];
+        if (rel < 0) rel += g.nd[0];
+        if (rel >= cnt) count[c] = 0u;
+    }
+}
+
+// first half of the sort: allocations, fine cell id and arrival rank of every point, points per fine cell
+int htb_sort_begin(cudaStream_t st, Workspace &ws, const FineGrid &g,
+                   const double *const *cd, int64_t stride, int64_t n,
+                   const double *w_dev, int nw, bool keep_perm, SortedSample &out, int *launches)
 {
     out.n = n;
     out.g = g;
@@ -203,20 +222,33 @@ int htb_sort_sample(cudaStream_t st, Workspace &ws, const FineGrid &g,
     if (w_dev && ws.alloc((void **)&out.w, sizeof(double) * (size_t)((n > 0 ? n : 1) * nw + 2))) return 1;
     if (ws.alloc((void **)&out.cell, sizeof(uint32_t) * (size_t)(n > 0 ? n : 1))) return 1;
     if (ws.alloc((void **)&out.rank, sizeof(uint32_t) * (size_t)(n > 0 ? n : 1))) return 1;
-    uint32_t *count = nullptr;
-    if (ws.alloc((void **)&count, sizeof(uint32_t) * (size_t)(g.ncells + 2))) return 1;
-    HTB_CUDA(cudaMemsetAsync(count, 0, sizeof(uint32_t) * (size_t)(g.ncells + 2), st));
+    if (ws.alloc((void **)&out.count, sizeof(uint32_t) * (size_t)(g.ncells + 2))) return 1;
+    HTB_CUDA(cudaMemsetAsync(out.count, 0, sizeof(uint32_t) * (size_t)(g.ncells + 2), st));
     HTB_CUDA(cudaMemsetAsync(out.flags, 0, sizeof(uint32_t) * 4, st));
     if (n > 0) {
         const int blocks = grid_for(n, 256);
         if (g.dim == 3)
-            k_assign<3><<<blocks, 256, 0, st>>>(cd[0], cd[1], cd[2], stride, n, g, out.cell, out.rank, count, out.flags);
+            k_assign<3><<<blocks, 256, 0, st>>>(cd[0], cd[1], cd[2], stride, n, g, out.cell, out.rank, out.count, out.flags);
         else
-            k_assign<2><<<blocks, 256, 0, st>>>(cd[0], cd[1], nullptr, stride, n, g, out.cell, out.rank, count, out.flags);
+            k_assign<2><<<blocks, 256, 0, st>>>(cd[0], cd[1], nullptr, stride, n, g, out.cell, out.rank, out.count, out.flags);
         if (launches) *launches += 1;
     }
-    // off[0..ncells] : exclusive scan over ncells+1 entries (the extra entry is zero) gives off[ncells] = n
-    if (htb_exclusive_scan_u32(st, ws, count, out.off, g.ncells + 1, nullptr, launches)) return 1;
+    HTB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// second half: (optional window) -> offsets -> scatter into SoA order
+int htb_sort_finish(cudaStream_t st, Workspace &ws, const double *const *cd, int64_t stride,
+                    const double *w_dev, int nw, double pad_value, const int *xwin_dev, SortedSample &out, int *launches)
+{
+    const FineGrid &g = out.g;
+    const int64_t n = out.n;
+    if (xwin_dev) {
+        k_mask_counts<<<grid_for(g.ncells, 256), 256, 0, st>>>(out.count, g, xwin_dev);
+        if (launches) *launches += 1;
+    }
+    // off[0..ncells] : exclusive scan over ncells+1 entries (the extra entry is zero) gives off[ncells] = points kept
+    if (htb_exclusive_scan_u32(st, ws, out.count, out.off, g.ncells + 1, nullptr, launches)) return 1;
     if (n > 0) {
         const int blocks = grid_for(n, 256);
         if (g.dim == 3)
@@ -231,6 +263,14 @@ int htb_sort_sample(cudaStream_t st, Workspace &ws, const FineGrid &g,
     if (launches) *launches += 1;
     HTB_CUDA(cudaGetLastError());
     return 0;
+}
+
+int htb_sort_sample(cudaStream_t st, Workspace &ws, const FineGrid &g,
+                    const double *const *cd, int64_t stride, int64_t n,
+                    const double *w_dev, int nw, bool keep_perm, double pad_value, SortedSample &out, int *launches)
+{
+    if (htb_sort_begin(st, ws, g, cd, stride, n, w_dev, nw, keep_perm, out, launches)) return 1;
+    return htb_sort_finish(st, ws, cd, stride, w_dev, nw, pad_value, nullptr, out, launches);
 }
 
 // ------------------------------------------------------------------ reference cell ids only
@@ -279,6 +319,30 @@ __global__ void k_ref_counts(const uint32_t *__restrict__ off, FineGrid g, uint3
         for (int d = 0; d < g.dim; ++d) rid = rid * g.nd[d] + f[d] / g.m[d];
         atomicAdd(&counts[rid], k);
     }
+}
+
+// ... from the per-fine-cell point counts (before the offsets exist)
+__global__ void k_ref_counts_c(const uint32_t *__restrict__ count, FineGrid g, uint32_t *__restrict__ counts)
+{
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < g.ncells; c += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t k = count[c];
+        if (!k) continue;
+        int64_t rem = c;
+        int f[3] = {0, 0, 0};
+        for (int d = g.dim - 1; d >= 0; --d) { f[d] = (int)(rem % g.nf[d]); rem /= g.nf[d]; }
+        int64_t rid = 0;
+        for (int d = 0; d < g.dim; ++d) rid = rid * g.nd[d] + f[d] / g.m[d];
+        atomicAdd(&counts[rid], k);
+    }
+}
+
+int htb_ref_cell_counts_pre(cudaStream_t st, const SortedSample &s, uint32_t *counts_dev, int *launches)
+{
+    const int blocks = grid_for(s.g.ncells, 256);
+    k_ref_counts_c<<<blocks, 256, 0, st>>>(s.count, s.g, counts_dev);
+    if (launches) *launches += 1;
+    HTB_CUDA(cudaGetLastError());
+    return 0;
 }
 
 int htb_ref_cell_counts(cudaStream_t st, const SortedSample &s, uint32_t *counts_dev, int *launches)

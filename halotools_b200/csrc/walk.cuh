@@ -146,13 +146,13 @@ __device__ __forceinline__ int floor_div(int a, int b) { int q = a / b; return (
 // Per-warp shared-memory context: HTB_NSTAGE stage buffers (DIM coordinate rows of HTB_CH doubles + payload rows of
 // HTB_CH * NPAY doubles), one mbarrier per stage, the span list.  Plain scalars only (no arrays indexed at run time,
 // which would live in local memory).
-template <int DIM, int NPAY>
+template <int DIM, int NPAY, int CH = HTB_CH>
 struct WarpSmem {
     double *stage0;                 // generic pointer to stage 0
     uint32_t stage0_s;              // its shared-space address
     uint32_t bar0;                  // shared-space address of mbarrier 0 (16 bytes apart)
     uint32_t *span;                 // HTB_SPAN_CAP * 3 u32: {jb, je, code}
-    static __host__ __device__ constexpr int stage_doubles() { return HTB_CH * (DIM + NPAY); }
+    static __host__ __device__ constexpr int stage_doubles() { return CH * (DIM + NPAY); }
     static __host__ __device__ constexpr size_t bytes()
     {
         return sizeof(double) * HTB_NSTAGE * stage_doubles() + 16 * HTB_NSTAGE + sizeof(uint32_t) * 3 * HTB_SPAN_CAP;
@@ -161,6 +161,10 @@ struct WarpSmem {
     __device__ __forceinline__ uint32_t stage_s(int s) const { return stage0_s + (uint32_t)(s * stage_doubles() * 8); }
     __device__ __forceinline__ uint32_t bar(int s) const { return bar0 + 16u * (uint32_t)s; }
 };
+
+// sample2 points per staged chunk of a variant: V::CH if it declares one, else HTB_CH
+template <class V, class = void> struct HtbChunk { static constexpr int value = HTB_CH; };
+template <class V> struct HtbChunk<V, decltype((void)V::CH)> { static constexpr int value = V::CH; };
 
 struct TileInfo {
     int cnt;                // valid points in the tile
@@ -375,7 +379,7 @@ __device__ __forceinline__ void walk_tile(V &v, const WalkGeom &G, const WalkArr
 // 2-D only (DIM == 2), no symmetric mode.  V::span_extra() gives 2 * HTB_SPAN_CAP extra u32 of per-warp scratch.
 template <class V>
 __device__ __forceinline__ void walk_tile_cells(V &v, const WalkGeom &G, const WalkArrays &A,
-                                                WarpSmem<V::DIM, V::NPAY> &S, uint32_t &gchunk,
+                                                WarpSmem<V::DIM, V::NPAY, HtbChunk<V>::value> &S, uint32_t &gchunk,
                                                 const double (&blo)[3], const double (&bhi)[3],
                                                 const int (&fs)[3], const int nref,
                                                 unsigned long long &pairs, int tile_cnt,
@@ -384,6 +388,7 @@ __device__ __forceinline__ void walk_tile_cells(V &v, const WalkGeom &G, const W
     static_assert(V::DIM == 2, "cell-resolved walker: 2-D meshes only");
     constexpr int DIM = 2;
     constexpr int F = 1;
+    constexpr int CH = HtbChunk<V>::value;
     const int lane = threadIdx.x & 31;
     const bool cull = !G.nocull && !((A.flags1[0] | A.flags2[0]) & 1u);
     uint32_t *extra = v.span_extra();          // per span: {first fine cell of the run (unwrapped, biased), column | ncells << 16}
@@ -421,17 +426,17 @@ __device__ __forceinline__ void walk_tile_cells(V &v, const WalkGeom &G, const W
             while (si < nspan && inflight < HTB_NSTAGE) {
                 const uint32_t je = S.span[3 * si + 1];
                 const uint32_t jend = (je + 1u) & ~1u;
-                const uint32_t cnt = min((uint32_t)HTB_CH, jend - ji);
+                const uint32_t cnt = min((uint32_t)CH, jend - ji);
                 const int stg = (int)((gchunk + (uint32_t)inflight) % HTB_NSTAGE);
                 if (lane == 0) {
                     const uint32_t dst = S.stage_s(stg), bar = S.bar(stg);
                     mbar_expect_tx(bar, cnt * 8u * DIM);
 #pragma unroll
                     for (int d = 0; d < DIM; ++d)
-                        tma_bulk_g2s(dst + (uint32_t)(d * HTB_CH * 8), A.c2[d] + ji, cnt * 8u, bar);
+                        tma_bulk_g2s(dst + (uint32_t)(d * CH * 8), A.c2[d] + ji, cnt * 8u, bar);
                 }
                 ++inflight;
-                ji += HTB_CH;
+                ji += CH;
                 if (ji >= je) { ++si; if (si < nspan) ji = S.span[3 * si] & ~1u; }
             }
             const uint32_t jb = S.span[3 * sc], je = S.span[3 * sc + 1], code = S.span[3 * sc + 2];
@@ -464,7 +469,7 @@ __device__ __forceinline__ void walk_tile_cells(V &v, const WalkGeom &G, const W
             uint32_t tok = jc;
             tok += mbar_wait(S.bar(stg), (gchunk / HTB_NSTAGE) & 1u);
             uint32_t pos = max(jb, jc);
-            const uint32_t end = min(je, jc + HTB_CH);
+            const uint32_t end = min(je, jc + CH);
             pairs += (unsigned long long)(end - pos) * (unsigned)tile_cnt;
             while (pos < end) {
                 while (cell_end <= pos) {
@@ -491,7 +496,7 @@ __device__ __forceinline__ void walk_tile_cells(V &v, const WalkGeom &G, const W
             __syncwarp();
             ++gchunk;
             --inflight;
-            jc += HTB_CH;
+            jc += CH;
             if (jc >= je) {
                 if (began) { v.cell_end(); began = false; }
                 ++sc;
