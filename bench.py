@@ -311,6 +311,115 @@ def run_gpu(args):
     return 0
 
 
+# ------------------------------------------------------------------ config-5 workload (scaling runs; not the driver's line)
+def run_gpu_c5(args):
+    """BASELINE.json configs[4]: mean_delta_sigma, 1e6 galaxies x 1e8 particles, Lbox 1000, 15 log rp bins 0.1-30,
+    one particle mass.  Same JSON contract; W_ref = pairs the reference's 2-d mesh loop visits."""
+    import torch
+    import torch.distributed as dist
+    import halotools_b200 as hb
+    from halotools_b200 import _lib, distributed, synthetic
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    _lib.require_gpu()
+    torch.cuda.set_device(local)
+    _lib.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        distributed.enable()
+    stream = torch.cuda.Stream()
+    import ctypes
+    _lib.check(_lib.load().htb_set_stream(ctypes.c_void_p(stream.cuda_stream)))
+    ngal, nptcl, L = args.c5_galaxies, args.c5_particles, 1000.0
+    gal = synthetic.uniform_points(43, ngal, L)
+    ptcl = synthetic.uniform_points(44, nptcl, L)
+    rp = np.logspace(-1, np.log10(30.0), 15)
+    gal_h, ptcl_h = torch.from_numpy(gal).pin_memory(), torch.from_numpy(ptcl).pin_memory()
+    del gal, ptcl
+    gal_np, ptcl_np = gal_h.numpy(), ptcl_h.numpy()
+    gal_d, ptcl_d = gal_h.cuda(), ptcl_h.cuda()
+    torch.cuda.synchronize()
+    acc = {}
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        r = hb.mean_delta_sigma(gal_d, ptcl_d, 1.0, rp, period=L)
+        acc.update(_lib.last_stats)
+        return r
+
+    def step_e2e():
+        return hb.mean_delta_sigma(gal_np, ptcl_np, 1.0, rp, period=L)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            res = None
+            for _ in range(steps):
+                res = fn()
+            e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps, res
+
+    sampler = ClockSampler(local)
+    if rank == 0 and not os.environ.get("HTB_BENCH_NO_SAMPLER"):
+        sampler.start()
+    ms_step, res = timed(step_resident, args.steps, args.warmup)
+    st = dict(acc)
+    tot = torch.tensor([st["pairs_reference"], st["pairs_evaluated"], st["ms_count"]], device="cuda", dtype=torch.float64)
+    if world > 1:
+        mx = tot.clone()
+        dist.all_reduce(tot)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        st["ms_count"] = float(mx[2])
+    W, Wgpu = float(tot[0]), float(tot[1])
+    ms_e2e, res2 = timed(step_e2e, max(1, args.steps // 2), 1)
+    clocks = sampler.stop() if rank == 0 else None
+    scale = float(np.max(np.abs(res)))
+    assert np.allclose(res, res2, rtol=1e-9, atol=1e-12 * scale), "resident and end-to-end paths disagree"
+    if rank == 0:
+        rate, _ = _lib.measure_fp64_rate()
+        ach = Wgpu / world * 5.0 / (st["ms_count"] * 1e-3) / 1e12
+        line = {"metric": "pair evals/sec", "value": W / (ms_step * 1e-3) / 1e9, "unit": "GPairs/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "configs[4]: mean_delta_sigma, %d galaxies x %d particles, Lbox 1000, 15 log rp bins "
+                                       "0.1-30, one particle mass" % (ngal, nptcl),
+                           "pairs_unit": "W_ref = pairs visited by the reference mesh loop for the same call",
+                           "pairs_reference_per_step": W, "pairs_evaluated_per_step": Wgpu,
+                           "l2": "inputs (%.1f GB of coordinates) are larger than L2" % ((ngal + nptcl) * 24 / 1e9),
+                           "parallelism": "work-balanced mesh1 cell ranges over %d rank(s), one all-reduce of the column sums" % world},
+                "e2e": {"value": W / (ms_e2e * 1e-3) / 1e9, "unit": "GPairs/s", "h2d_bytes_per_step": int((ngal + nptcl) * 24),
+                        "d2h_bytes_per_step": int(14 * 8), "ms_per_step": ms_e2e},
+                "gpu_launches": int(st["kernel_launches"] * args.steps),
+                "roofline": {"bound": "fp64_issue", "achieved": ach, "peak": rate / 1e12, "unit": "TFLOP/s", "frac": ach / (rate / 1e12),
+                             "traffic": None, "kernel": "k_count<DSigmaR> (5 f64 ops per evaluated pair; slowest rank)",
+                             "kernel_ms": st["ms_count"]},
+                "cpu_baseline": None, "clocks": clocks,
+                "breakdown_ms": {"mesh_sort": st["ms_mesh"], "count_kernel": st["ms_count"], "path": st["path"]},
+                "delta_sigma": [float(v) for v in res]}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -319,9 +428,15 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--randoms", type=int, default=N_RANDOMS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="tpcf", choices=["tpcf", "c5"],
+                    help="tpcf = BASELINE configs[1] (the driver's line); c5 = configs[4], the delta-sigma scaling config")
+    ap.add_argument("--c5-galaxies", type=int, default=1_000_000)
+    ap.add_argument("--c5-particles", type=int, default=100_000_000)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "c5":
+        return run_gpu_c5(args)
     return run_gpu(args)
 
 

@@ -93,8 +93,19 @@ def _column_extrema(x, y, z):
     """(min, max) per coordinate.  Large float64 samples whose three coordinates are adjacent columns of one
     matrix are scanned once by the library's threaded host helper; anything else goes through numpy."""
     if all(getattr(a, "is_cuda", False) for a in (x, y, z)):
-        # device-resident columns (torch CUDA tensors): the extrema are found where the data lives
-        return [(float(a.min()), float(a.max())) if a.numel() else (0.0, 0.0) for a in (x, y, z)]
+        # device-resident columns (torch CUDA tensors): the extrema are found where the data lives - in ONE pass
+        # when the three columns are views of one (N, 3) tensor (the usual case), with one small copy to the host
+        import torch
+        if x.numel() == 0:
+            return [(0.0, 0.0)] * 3
+        base = getattr(x, "_base", None)
+        if (base is not None and base.dim() == 2 and base.shape[1] == 3 and y._base is base and z._base is base
+                and x.data_ptr() == base.data_ptr() and y.data_ptr() == base[:, 1].data_ptr()
+                and z.data_ptr() == base[:, 2].data_ptr()):
+            lo, hi = torch.aminmax(base, dim=0)
+            ext = torch.stack([lo, hi]).cpu().numpy()
+            return [(float(ext[0, k]), float(ext[1, k])) for k in range(3)]
+        return [(float(a.min()), float(a.max())) for a in (x, y, z)]
     try:
         n = len(x)
         if (n >= 1000000 and all(isinstance(a, np.ndarray) and a.dtype == np.float64 and a.ndim == 1 for a in (x, y, z))
