@@ -1,0 +1,215 @@
+// K2e — BinQ: integer pair counts on ANY monotone set of edges (no limit of 16, two bin axes).
+//   KIND 0  npairs_3d with more than 16 rbins                         npairs_3d_engine.pyx:171-182
+//   KIND 1  npairs_xy_z with any number of pi edges (rp_pi_tpcf)      npairs_xy_z_engine.pyx:178-194
+//   KIND 2  npairs_s_mu                                               npairs_s_mu_engine.pyx:196-229
+// The hot loop only DECIDES whether a pair can be inside the top edge(s): the reference's strict f64 separation
+// (7-8 operations), one integer compare of its high word per bin axis against the high word of the top squared
+// edge (a conservative superset: the high word of a non-negative double is monotone), and one predicated integer
+// instruction that records the pair as a BIT of a per-lane 64-bit mask (one bit per staged sample2 point and lane
+// point) - no shared-memory queue, no stores.  At the end of every staged chunk the set bits are replayed: the
+// separation is recomputed with the same arithmetic, located among the edges by a table lookup on its exponent and
+// leading mantissa bits (first edge that can be >= the value) followed by exact 64-bit compares of the raw bit
+// patterns (order preserving for non-negative doubles), and the
+// pair is added to the DIFFERENTIAL histogram cell (lowest satisfied edge per axis) of the warp's shared-memory
+// histogram.  The host turns the differential histogram into the reference's cumulative counts (for monotone
+// edges the reference's top-down scans stop exactly at the lowest satisfied edge).
+#include "kernel.cuh"
+
+__device__ __forceinline__ void bq_lds_f64x2_tok(uint32_t addr, uint32_t tok, double &a, double &b)
+{
+    // not volatile: free to be scheduled early; `tok` changes with every staged chunk (no merging across chunks)
+    asm("ld.shared.v2.f64 {%0, %1}, [%2]; // %3" : "=d"(a), "=d"(b) : "r"(addr), "r"(tok));
+}
+__device__ __forceinline__ unsigned long long bq_lds_u64(uint32_t addr)
+{
+    unsigned long long v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr));
+    return v;
+}
+
+template <int KIND>
+struct BinQ {
+    static constexpr int DIM = 3, NPAY = 0, PPL = 2, WARPS = 8, MINBLOCKS = 2;
+    static constexpr bool TMA = true;
+    typedef BinQParams Params;
+    const Params &P;
+    uint32_t *hist;             // per-warp differential histogram (n0 * n1 u32)
+    uint32_t e_s;               // shared-space address: raw bits of the squared edges (n0 then n1), u64
+    uint32_t lut_s[2];          // shared-space addresses of the two lookup tables (u8)
+    int lane;
+    double x0, y0, z0, x1, y1, z1;
+    double xs0, ys0, zs0, xs1, ys1, zs1;
+
+    static size_t scratch_bytes(const Params &p)
+    {
+        const size_t ne = (size_t)p.n0 + p.n1;
+        return 8 * ne + (((size_t)p.T[0] + 7) & ~(size_t)7) + (((size_t)p.T[1] + 7) & ~(size_t)7) +
+               4 * (((size_t)p.n0 * p.n1 + 3) & ~(size_t)3);
+    }
+    __device__ BinQ(const Params &p, void *scratch, int ln, const WalkArrays &) : P(p), lane(ln)
+    {
+        const int ne = P.n0 + P.n1;
+        // edges and lookup tables are one contiguous block of 8-byte words on the device
+        const int nl = (((P.T[0] + 7) & ~7) + ((P.T[1] + 7) & ~7)) >> 3;
+        unsigned long long *e = (unsigned long long *)scratch;
+        hist = (uint32_t *)(e + ne + nl);
+        e_s = smem_u32(e);
+        lut_s[0] = e_s + 8u * (uint32_t)ne;
+        lut_s[1] = lut_s[0] + (uint32_t)((P.T[0] + 7) & ~7);
+        for (int k = lane; k < ne + nl; k += 32) e[k] = P.edges[k];
+        for (int k = lane; k < P.n0 * P.n1; k += 32) hist[k] = 0;
+        x0 = y0 = z0 = x1 = y1 = z1 = 0.0;
+        xs0 = ys0 = zs0 = xs1 = ys1 = zs1 = 0.0;
+        __syncwarp();
+    }
+    __device__ __forceinline__ void tile_weight(unsigned) {}
+    __device__ __forceinline__ void force_exact() {}
+    __device__ __forceinline__ void tile_begin(const double (&p)[2][3], const bool (&)[2], const uint32_t (&)[2], const WalkArrays &)
+    {
+        // unused lanes of a partial tile carry the far sentinel in x: never inside the top edge
+        x0 = p[0][0]; y0 = p[0][1]; z0 = p[0][2];
+        x1 = p[1][0]; y1 = p[1][1]; z1 = p[1][2];
+    }
+    __device__ __forceinline__ void set_shift(const double (&sh)[3], const WalkArrays &)
+    {
+        // npairs_3d_engine.pyx:167: the periodic shift is applied to the sample1 coordinate first
+        xs0 = x0 - sh[0]; ys0 = y0 - sh[1]; zs0 = z0 - sh[2];
+        xs1 = x1 - sh[0]; ys1 = y1 - sh[1]; zs1 = z1 - sh[2];
+    }
+    // the two separations the bins are defined on, in the reference's evaluation order
+    __device__ __forceinline__ void seps(double xs, double ys, double zs, double xj, double yj, double zj, double &a, double &b)
+    {
+        const double dx = xs - xj, dy = ys - yj, dz = zs - zj;
+        if (KIND == 0) {
+            a = dx * dx + dy * dy + dz * dz;            // npairs_3d_engine.pyx:176
+            b = 0.0;
+        } else if (KIND == 1) {
+            a = dx * dx + dy * dy;                      // npairs_xy_z_engine.pyx:180-183
+            b = dz * dz;
+        } else {
+            b = dx * dx + dy * dy;                      // npairs_s_mu_engine.pyx:196-200: dxy_sq, then sqr_s = dz_sq + dxy_sq
+            const double dz_sq = dz * dz;
+            a = dz_sq + b;
+        }
+    }
+    __device__ __forceinline__ unsigned maybe(double xs, double ys, double zs, double xj, double yj, double zj)
+    {
+        double a, b;
+        seps(xs, ys, zs, xj, yj, zj, a, b);
+        if (KIND == 1) return (__double2hiint(a) <= P.H0 && __double2hiint(b) <= P.H1) ? 1u : 0u;
+        return (__double2hiint(a) <= P.H0) ? 1u : 0u;
+    }
+    // first index i in [0, n] whose edge is >= the value with raw bits `bits` (n: above every edge).  Straight-line
+    // code (so that the two chains of a replay trip interleave): table lookup, two exact compares; more than one
+    // edge inside the value's table cell is finished by a loop (rare).
+    __device__ __forceinline__ int locate(int axis, int first, int n, unsigned long long bits)
+    {
+        const long long t = (long long)(bits >> P.S[axis]) - (long long)P.kmin[axis];
+        const int tt = (int)max(0ll, min(t, (long long)P.T[axis] - 1ll));
+        unsigned v;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(lut_s[axis] + (uint32_t)tt));
+        int i = t < 0 ? 0 : (int)v;
+        const uint32_t eb = e_s + 8u * (uint32_t)first;
+        const bool c1 = i < n && bq_lds_u64(eb + 8u * (uint32_t)min(i, n - 1)) < bits;
+        i += c1 ? 1 : 0;
+        if (c1 && i < n && bq_lds_u64(eb + 8u * (uint32_t)min(i, n - 1)) < bits) {
+            ++i;
+            while (i < n && bq_lds_u64(eb + 8u * (uint32_t)i) < bits) ++i;
+        }
+        return t >= (long long)P.T[axis] ? n : i;
+    }
+    // one replayed pair: recompute, locate; returns the histogram cell or -1
+    __device__ __forceinline__ int replay_one(bool act, double xs, double ys, double zs, double xj, double yj, double zj)
+    {
+        double a, b;
+        seps(xs, ys, zs, xj, yj, zj, a, b);
+        const int i0 = locate(0, 0, P.n0, (unsigned long long)__double_as_longlong(a));
+        int i1 = 0;
+        if (KIND == 1) {
+            i1 = locate(1, P.n0, P.n1, (unsigned long long)__double_as_longlong(b));
+        } else if (KIND == 2) {
+            // npairs_s_mu_engine.pyx:205-211
+            const double sqr_mu = (a > 0.0) ? b / a : 0.0;
+            i1 = locate(1, P.n0, P.n1, (unsigned long long)__double_as_longlong(sqr_mu));
+        }
+        return (act && i0 < P.n0 && i1 < P.n1) ? i0 * P.n1 + i1 : -1;
+    }
+    // every trip takes the lowest recorded pair of BOTH lane points (two independent dependency chains)
+    __device__ __forceinline__ void replay(uint32_t stage, unsigned long long M0, unsigned long long M1)
+    {
+        const uint32_t bx = stage, by = stage + 8 * HTB_CH, bz = stage + 16 * HTB_CH;
+        while (__any_sync(HTB_FULL, (M0 | M1) != 0ull)) {
+            const bool act0 = M0 != 0ull, act1 = M1 != 0ull;
+            const int j0 = max(__ffsll((long long)M0) - 1, 0), j1 = max(__ffsll((long long)M1) - 1, 0);
+            M0 &= M0 - 1ull;
+            M1 &= M1 - 1ull;
+            const double xa = lds_f64(bx + 8 * j0), ya = lds_f64(by + 8 * j0), za = lds_f64(bz + 8 * j0);
+            const double xb = lds_f64(bx + 8 * j1), yb = lds_f64(by + 8 * j1), zb = lds_f64(bz + 8 * j1);
+            const int h0 = replay_one(act0, xs0, ys0, zs0, xa, ya, za);
+            const int h1 = replay_one(act1, xs1, ys1, zs1, xb, yb, zb);
+            if (h0 >= 0) atomicAdd(hist + h0, 1u);
+            if (h1 >= 0) atomicAdd(hist + h1, 1u);
+        }
+    }
+    __device__ __forceinline__ void chunk(uint32_t stage, int lo, int hi, uint32_t tok)
+    {
+        const uint32_t bx = stage, by = stage + 8 * HTB_CH, bz = stage + 16 * HTB_CH;
+        // groups of 4 staged points, aligned; entries outside [lo, hi) are evaluated on whatever the stage holds
+        // and masked out afterwards
+        const int jb = lo & ~3, je = (hi + 3) & ~3;
+        uint32_t m[2][2] = {{0u, 0u}, {0u, 0u}};
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+            const int b0 = max(jb, 32 * w), b1 = min(je, 32 * w + 32);
+            uint32_t a0 = 0u, a1 = 0u;
+#pragma unroll 2
+            for (int j = b0; j < b1; j += 4) {
+                double xa, xb, xc, xd, ya, yb, yc, yd, za, zb, zc, zd;
+                bq_lds_f64x2_tok(bx + 8 * j, tok, xa, xb);
+                bq_lds_f64x2_tok(by + 8 * j, tok, ya, yb);
+                bq_lds_f64x2_tok(bz + 8 * j, tok, za, zb);
+                bq_lds_f64x2_tok(bx + 8 * j + 16, tok, xc, xd);
+                bq_lds_f64x2_tok(by + 8 * j + 16, tok, yc, yd);
+                bq_lds_f64x2_tok(bz + 8 * j + 16, tok, zc, zd);
+                unsigned n0 = maybe(xs0, ys0, zs0, xa, ya, za);
+                unsigned n1 = maybe(xs1, ys1, zs1, xa, ya, za);
+                n0 |= maybe(xs0, ys0, zs0, xb, yb, zb) << 1;
+                n1 |= maybe(xs1, ys1, zs1, xb, yb, zb) << 1;
+                n0 |= maybe(xs0, ys0, zs0, xc, yc, zc) << 2;
+                n1 |= maybe(xs1, ys1, zs1, xc, yc, zc) << 2;
+                n0 |= maybe(xs0, ys0, zs0, xd, yd, zd) << 3;
+                n1 |= maybe(xs1, ys1, zs1, xd, yd, zd) << 3;
+                a0 |= n0 << (j & 31);
+                a1 |= n1 << (j & 31);
+            }
+            m[0][w] = a0; m[1][w] = a1;
+        }
+        const unsigned long long range = (hi >= 64 ? ~0ull : ((1ull << hi) - 1ull)) & ~((1ull << lo) - 1ull);
+        const unsigned long long M0 = ((unsigned long long)m[0][0] | ((unsigned long long)m[0][1] << 32)) & range;
+        const unsigned long long M1 = ((unsigned long long)m[1][0] | ((unsigned long long)m[1][1] << 32)) & range;
+        replay(stage, M0, M1);
+    }
+    __device__ __forceinline__ bool tile_end(const WalkArrays &, const uint32_t (&)[2], int, unsigned wt)
+    {
+        __syncwarp();
+        const int nh = P.n0 * P.n1;
+        for (int k = lane; k < nh; k += 32) {
+            const uint32_t h = hist[k];
+            if (h) { atomicAdd(P.counts + k, (unsigned long long)wt * h); hist[k] = 0; }
+        }
+        __syncwarp();
+        return false;
+    }
+    __device__ __forceinline__ void kernel_end() {}
+};
+
+int htb_launch_binq(cudaStream_t st, int kind, const WalkGeom &G, const WalkArrays &A, const BinQParams &P, int *l)
+{
+    switch (kind) {
+    case 0: return launch_count<BinQ<0>>(st, G, A, P, l);
+    case 1: return launch_count<BinQ<1>>(st, G, A, P, l);
+    case 2: return launch_count<BinQ<2>>(st, G, A, P, l);
+    }
+    htb_set_error("unknown BinQ kind %d", kind);
+    return 1;
+}

@@ -729,6 +729,78 @@ static bool fast3_params(const htb_mesh_geom *mesh, const double *bins, const do
     return true;
 }
 
+// BinQ (binq.cu) serves any set of finite, non-decreasing squared edges on one or two bin axes: the differential
+// histogram it returns (lowest satisfied edge per axis) becomes the reference's cumulative counts by inclusive
+// prefix sums (for monotone edges the reference's top-down scans stop exactly at the lowest satisfied edge,
+// npairs_3d_engine.pyx:178-182, npairs_xy_z_engine.pyx:186-194, npairs_s_mu_engine.pyx:218-234).
+static bool binq_ok(const double *e0, int n0, const double *e1, int n1, uint32_t flags)
+{
+    if ((flags & HTB_FLAG_GENERIC) || getenv("HTB_NO_BINQ")) return false;
+    if (n0 < 1 || n1 < 1 || n0 > 255 || n1 > 255 || (long long)n0 * n1 > 4096) return false;
+    if (!finite_all(e0, n0) || (e1 && !finite_all(e1, n1))) return false;
+    for (int k = 0; k + 1 < n0; ++k) if (!(e0[k] <= e0[k + 1])) return false;
+    for (int k = 0; e1 && k + 1 < n1; ++k) if (!(e1[k] <= e1[k + 1])) return false;
+    return e0[0] >= 0.0 && (!e1 || e1[0] >= 0.0);
+}
+
+static int run_binq(Call &c, int kind, const double *e0, int n0, const double *e1, int n1, int64_t *counts_out, htb_stats *stats)
+{
+    std::vector<unsigned long long> eb((size_t)n0 + n1, 0ULL);
+    for (int k = 0; k < n0; ++k) eb[k] = dbits(e0[k] + 0.0);
+    for (int k = 0; e1 && k < n1; ++k) eb[(size_t)n0 + k] = dbits(e1[k] + 0.0);
+    // Lookup tables: key = bits >> S keeps the exponent and up to 8 mantissa bits; lut[key - kmin] is the first edge
+    // whose key is >= key (every earlier edge is certainly below the value); the kernel finishes with exact compares.
+    // kmin is the key of the smallest non-zero edge (values below it start at edge 0); S grows until the table is
+    // at most 1024 entries.
+    BinQParams bp{};
+    std::vector<unsigned char> lut[2];
+    for (int a = 0; a < 2; ++a) {
+        const int n = a ? n1 : n0;
+        const unsigned long long *b = eb.data() + (a ? n0 : 0);
+        int z = 0;
+        while (z < n - 1 && b[z] == 0ULL) ++z;
+        int S = 44;
+        while (((b[n - 1] >> S) - (b[z] >> S) + 1ULL) > 1024ULL) ++S;
+        const unsigned long long kmin = b[z] >> S;
+        const int T = (int)((b[n - 1] >> S) - kmin + 1ULL);
+        lut[a].assign(((size_t)T + 7) & ~(size_t)7, (unsigned char)n);
+        int i = 0;
+        for (int t = 0; t < T; ++t) {
+            while (i < n && (b[i] >> S) < kmin + (unsigned long long)t) ++i;
+            lut[a][(size_t)t] = (unsigned char)i;
+        }
+        bp.S[a] = S; bp.T[a] = T; bp.kmin[a] = (unsigned)kmin;
+    }
+    const size_t ne = eb.size();
+    eb.resize(ne + (lut[0].size() + lut[1].size()) / 8);
+    memcpy((unsigned char *)(eb.data() + ne), lut[0].data(), lut[0].size());
+    memcpy((unsigned char *)(eb.data() + ne) + lut[0].size(), lut[1].data(), lut[1].size());
+    void *edev = nullptr;
+    if (upload(c, eb.data(), sizeof(unsigned long long) * eb.size(), &edev)) return 1;
+    const int nh = n0 * n1;
+    unsigned long long *counts_dev = nullptr;
+    if (c.ws.alloc((void **)&counts_dev, sizeof(unsigned long long) * (size_t)nh)) return 1;
+    HTB_CUDA(cudaMemsetAsync(counts_dev, 0, sizeof(unsigned long long) * (size_t)nh, c.st));
+    bp.n0 = n0; bp.n1 = n1;
+    bp.H0 = (int)(eb[(size_t)n0 - 1] >> 32);
+    bp.H1 = e1 ? (int)(eb[(size_t)n0 + n1 - 1] >> 32) : 0;
+    bp.edges = (const unsigned long long *)edev;
+    bp.counts = counts_dev;
+    if (htb_launch_binq(c.st, kind, c.G, c.A, bp, &c.launches)) return 1;
+    std::vector<long long> diff((size_t)nh);
+    HTB_CUDA(cudaMemcpyAsync(diff.data(), counts_dev, sizeof(int64_t) * (size_t)nh, cudaMemcpyDeviceToHost, c.st));
+    if (c.finish(stats, 3)) return 1;
+    for (int k = 0; k < n0; ++k)
+        for (int g = 0; g < n1; ++g) {
+            long long s = diff[(size_t)k * n1 + g];
+            if (k > 0) s += counts_out[(size_t)(k - 1) * n1 + g];
+            if (g > 0) s += counts_out[(size_t)k * n1 + g - 1];
+            if (k > 0 && g > 0) s -= counts_out[(size_t)(k - 1) * n1 + g - 1];
+            counts_out[(size_t)k * n1 + g] = s;
+        }
+    return 0;
+}
+
 // ------------------------------------------------------------------ npairs_3d
 extern "C" int htb_npairs_3d_engine(const htb_mesh_geom *mesh,
                                     const double *x1, const double *y1, const double *z1, int64_t stride1, int64_t n1,
@@ -755,6 +827,8 @@ extern "C" int htb_npairs_3d_engine(const htb_mesh_geom *mesh,
     if (fast) {
         fp.counts = counts_dev;
         if (htb_launch_fast3(c.st, c.G, c.A, fp, &c.launches)) return 1;
+    } else if (binq_ok(rsq.data(), nb, nullptr, 1, flags)) {
+        return run_binq(c, 0, rsq.data(), nb, nullptr, 1, counts_out, stats);
     } else {
         GenParams gp{};
         gp.n0 = nb; gp.n1 = 1; gp.nhist = nb;
@@ -818,6 +892,8 @@ extern "C" int htb_npairs_xy_z_engine(const htb_mesh_geom *mesh,
         }
         return 0;
     }
+    if (binq_ok(e.data(), nrp, e.data() + nrp, npi, flags))
+        return run_binq(c, 1, e.data(), nrp, e.data() + nrp, npi, counts_out, stats);
     void *edev = nullptr;
     if (upload(c, e.data(), sizeof(double) * e.size(), &edev)) return 1;
     GenParams gp{};
@@ -849,6 +925,8 @@ extern "C" int htb_npairs_s_mu_engine(const htb_mesh_geom *mesh,
     double m0 = -INFINITY, m1 = -INFINITY;
     for (int k = 0; k < ns; ++k) { e[k] = s_bins[k] * s_bins[k]; if (e[k] > m0) m0 = e[k]; }
     for (int k = 0; k < nmu; ++k) { e[ns + k] = mu_bins[k] * mu_bins[k]; if (e[ns + k] > m1) m1 = e[ns + k]; }
+    if (binq_ok(e.data(), ns, e.data() + ns, nmu, flags))
+        return run_binq(c, 2, e.data(), ns, e.data() + ns, nmu, counts_out, stats);
     void *edev = nullptr;
     if (upload(c, e.data(), sizeof(double) * e.size(), &edev)) return 1;
     const int nh = ns * nmu;

@@ -59,12 +59,25 @@ struct GenParams {
     const uint32_t *perm1;           // DSigma: sorted position -> input row
 };
 
+// BinQ (binq.cu): integer counts on any monotone edges, one or two bin axes, differential histogram
+struct BinQParams {
+    int n0, n1;                      // edges along the first (r / rp / s) and second (none: 1 / pi / mu) bin axis
+    int H0, H1;                      // high words of the top squared edges: the hot loop's conservative range test
+    const unsigned long long *edges; // device: raw bits of the squared edges, n0 of axis 0 then n1 of axis 1, ascending;
+                                     // followed by the two lookup tables (T[0], T[1] bytes, each padded to 8)
+    unsigned long long *counts;      // device: [n0 * n1] differential histogram (lowest satisfied edge per axis)
+    // per axis: lut[(bits >> S) - kmin] = first edge whose key (bits >> S) is >= that of the value; T entries
+    int S[2], T[2];
+    unsigned kmin[2];
+};
+
 int htb_fast3_ppl();            // sample1 points per lane of the fast kernel (its tiles hold 32x that)
 int htb_launch_fast3(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const Fast3Params &P, int *launches);
 int htb_launch_markedq(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const Fast3Params &P, int *launches);
 int htb_launch_fastxyz(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const Fast3Params &P, int *launches);
 int htb_launch_dsq(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const DSQParams &P, int *launches);
 int htb_launch_dsr(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const DSRParams &P, int *launches);
+int htb_launch_binq(cudaStream_t st, int kind, const WalkGeom &G, const WalkArrays &A, const BinQParams &P, int *launches);
 int htb_launch_gen(cudaStream_t st, int kind, const WalkGeom &G, const WalkArrays &A, const GenParams &P, int *launches);
 int htb_build_tiles(cudaStream_t st, Workspace &ws, const WalkGeom &G, const SortedSample &s1,
                     int64_t first_cell1, int64_t last_cell1, const long long *range_dev /* device {first, last} or null */,

@@ -69,7 +69,7 @@ typedef struct htb_stats {
     int32_t  tiles_redone;      /* tiles re-evaluated by the exact path (edge-ambiguous key) */
     int32_t  refine1[3];        /* sub-divisions of each reference mesh1 cell                */
     int32_t  refine2[3];        /* sub-divisions of each reference mesh2 cell                */
-    int32_t  path;              /* 1 = fast queue kernel, 0 = generic kernel                 */
+    int32_t  path;              /* 0 generic, 1 fast queue kernel, 2 cell-resolved, 3 BinQ   */
 } htb_stats;
 
 const char *htb_last_error(void);

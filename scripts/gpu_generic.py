@@ -21,8 +21,10 @@ rb = synthetic.config_rbins()
 s2m = synthetic.uniform_points(43, 2000000, 1000.0)
 rp = np.logspace(-1, np.log10(30), 15)
 run("c3 npairs_xy_z wp (2 pi edges, fast)", lambda: hb.npairs_xy_z(s2m, s2m, rp, [0.0, 60.0], period=1000.0))
-run("c3 npairs_xy_z 12 pi edges (generic)", lambda: hb.npairs_xy_z(s2m, s2m, rp, np.linspace(0, 60, 12), period=1000.0))
-run("c3 npairs_s_mu 15 x 11", lambda: hb.npairs_s_mu(s2m, s2m, rp, np.linspace(0, 1, 11), period=1000.0))
+run("c3 npairs_xy_z 12 pi edges (BinQ)", lambda: hb.npairs_xy_z(s2m, s2m, rp, np.linspace(0, 60, 12), period=1000.0))
+run("c3 npairs_xy_z 41 pi edges (BinQ)", lambda: hb.npairs_xy_z(s2m, s2m, rp, np.linspace(0, 40, 41), period=1000.0))
+run("c3 npairs_3d 40 rbins (BinQ)", lambda: hb.npairs_3d(s2m, s2m, np.linspace(0.1, 30, 40), period=1000.0))
+run("c3 npairs_s_mu 15 x 11 (BinQ)", lambda: hb.npairs_s_mu(s2m, s2m, rp, np.linspace(0, 1, 11), period=1000.0))
 run("c3 npairs_3d (fast)", lambda: hb.npairs_3d(s2m, s2m, rp, period=1000.0))
 rng = np.random.RandomState(43)
 s = rng.uniform(0, 1000.0, (10000000, 3)); w = rng.uniform(0.5, 1.5, 10000000)

@@ -262,8 +262,90 @@ def test_fast_xy_z_not_taken_for_many_pi_edges():
     rp = np.logspace(-1, 1, 8)
     pi = np.linspace(0, 20, 9)
     got = hb.npairs_xy_z(s, s, rp, pi, period=80.0)
-    assert _lib.last_stats["path"] == 0
+    assert _lib.last_stats["path"] == 3, "many pi edges belong to the BinQ kernel"
     assert np.array_equal(got, oracle.npairs_xy_z(s, s, rp, pi, period=80.0, num_threads=4))
+
+
+# ---------------------------------------------------------------- BinQ (binq.cu): any monotone edges, two bin axes
+def _generic(call):
+    old = _lib.default_flags
+    _lib.default_flags = _lib.FLAG_GENERIC
+    try:
+        out = call()
+        assert _lib.last_stats["path"] == 0
+        return out
+    finally:
+        _lib.default_flags = old
+
+
+@pytest.mark.parametrize("pi_bins", [np.linspace(0.0, 40.0, 41), [0.0, 1e-9, 1.0, 1.0 + 1e-12, 7.5, 30.0], [2.0, 5.0, 11.0]])
+def test_binq_rp_pi_vs_oracle_with_degenerate_separations(pi_bins):
+    """rp_pi_tpcf's counter: many pi edges, duplicate edges, zero edges, exact duplicates / shared z / 1e-13 separations"""
+    rng = np.random.RandomState(21)
+    L = 120.0
+    s1 = _dup_points(rng, 30000, L)
+    s2 = np.vstack([s1[:5000], _dup_points(rng, 25000, L)])
+    rp = np.concatenate([[0.0], np.logspace(-1.5, np.log10(12.0), 13)])
+    for a, b in ((s1, s1), (s1, s2)):
+        got = hb.npairs_xy_z(a, b, rp, pi_bins, period=L)
+        assert _lib.last_stats["path"] == 3, "BinQ kernel not taken"
+        want = oracle.npairs_xy_z(a, b, rp, pi_bins, period=L, num_threads=4)
+        assert got.dtype == np.int64 and got.shape == want.shape and np.array_equal(got, want), (got - want)
+        assert np.array_equal(_generic(lambda: hb.npairs_xy_z(a, b, rp, pi_bins, period=L)), want)
+
+
+@pytest.mark.parametrize("nmu", [2, 11, 40])
+def test_binq_s_mu_vs_oracle_with_degenerate_separations(nmu):
+    rng = np.random.RandomState(22)
+    L = 100.0
+    s1 = _dup_points(rng, 25000, L)
+    s2 = np.vstack([s1[:4000], _dup_points(rng, 20000, L)])
+    s_bins = np.logspace(-1, np.log10(15.0), 14)
+    mu_bins = np.linspace(0.0, 1.0, nmu)
+    for a, b in ((s1, s1), (s1, s2)):
+        got = hb.npairs_s_mu(a, b, s_bins, mu_bins, period=L)
+        assert _lib.last_stats["path"] == 3, "BinQ kernel not taken"
+        want = oracle.npairs_s_mu(a, b, s_bins, mu_bins, period=L, num_threads=4)
+        assert got.dtype == np.int64 and got.shape == want.shape and np.array_equal(got, want), (got - want)
+        assert np.array_equal(_generic(lambda: hb.npairs_s_mu(a, b, s_bins, mu_bins, period=L)), want)
+
+
+def test_binq_npairs_3d_more_than_16_bins_and_nonperiodic():
+    rng = np.random.RandomState(23)
+    s1 = _dup_points(rng, 20000, 90.0)
+    s2 = rng.uniform(5.0, 70.0, (15000, 3))
+    rbins = np.concatenate([[0.0, 1e-9], np.linspace(0.01, 9.0, 38)])
+    for period in (90.0, None):
+        got = hb.npairs_3d(s1, s2, rbins, period=period)
+        assert _lib.last_stats["path"] == 3
+        want = oracle.npairs_3d(s1, s2, rbins, period=period, num_threads=4)
+        assert np.array_equal(got, want), (got - want)
+    auto = hb.npairs_3d(s1, s1, rbins, period=90.0)
+    assert np.array_equal(auto, oracle.npairs_3d(s1, s1, rbins, period=90.0, num_threads=4))
+    old = _lib.default_flags
+    _lib.default_flags = _lib.FLAG_NO_SYM | _lib.FLAG_NO_CULL
+    try:
+        assert np.array_equal(hb.npairs_3d(s1, s1, rbins, period=90.0), auto)
+    finally:
+        _lib.default_flags = old
+
+
+def test_binq_dense_tiles_and_properties_large():
+    """2e5 points: additivity over a split of sample2 and the pi-marginal of the (rp, pi) counts == the one-edge fast kernel"""
+    rng = np.random.RandomState(24)
+    L = 200.0
+    s = rng.uniform(0, L, (200000, 3))
+    rp = np.logspace(-1, np.log10(15.0), 12)
+    pi = np.linspace(0.0, 30.0, 31)
+    full = hb.npairs_xy_z(s, s, rp, pi, period=L)
+    assert _lib.last_stats["path"] == 3
+    a = hb.npairs_xy_z(s, s[:70000], rp, pi, period=L)
+    b = hb.npairs_xy_z(s, s[70000:], rp, pi, period=L)
+    assert np.array_equal(full, a + b)
+    one = hb.npairs_xy_z(s, s, rp, [0.0, 30.0], period=L)
+    assert _lib.last_stats["path"] == 1
+    assert np.array_equal(full[:, [0, -1]], one)
+    assert np.all(np.diff(full, axis=0) >= 0) and np.all(np.diff(full, axis=1) >= 0)
 
 
 @pytest.mark.parametrize("wfunc", [1])
