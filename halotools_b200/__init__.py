@@ -4,10 +4,12 @@
 ``marked_tpcf``).  Host code is Python; the mesh sort and the pair loops are hand-written CUDA
 behind the C ABI of ``include/halotools_b200.h`` (``libhalotools_b200.so``).  No CPU fallback."""
 from .custom_exceptions import HalotoolsError
-from .pair_counters import npairs_3d, npairs_xy_z, npairs_s_mu, marked_npairs_3d
-from .surface_density import mean_delta_sigma
+from .pair_counters import (npairs_3d, npairs_xy_z, npairs_s_mu, marked_npairs_3d, marked_npairs_xy_z,
+                            npairs_projected, npairs_per_object_3d)
+from .surface_density import mean_delta_sigma, weighted_npairs_xy
 from .two_point_clustering import tpcf, wp, rp_pi_tpcf, marked_tpcf
 
 __version__ = "0.1.0"
 __all__ = ("HalotoolsError", "npairs_3d", "npairs_xy_z", "npairs_s_mu", "marked_npairs_3d",
-           "mean_delta_sigma", "tpcf", "wp", "rp_pi_tpcf", "marked_tpcf")
+           "marked_npairs_xy_z", "npairs_projected", "npairs_per_object_3d",
+           "mean_delta_sigma", "weighted_npairs_xy", "tpcf", "wp", "rp_pi_tpcf", "marked_tpcf")

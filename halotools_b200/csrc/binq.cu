@@ -1,18 +1,22 @@
-// K2e — BinQ: integer pair counts on ANY monotone set of edges (no limit of 16, two bin axes).
-//   KIND 0  npairs_3d with more than 16 rbins                         npairs_3d_engine.pyx:171-182
-//   KIND 1  npairs_xy_z with any number of pi edges (rp_pi_tpcf)      npairs_xy_z_engine.pyx:178-194
-//   KIND 2  npairs_s_mu                                               npairs_s_mu_engine.pyx:196-229
+// K2e — BinQ: pair counts on ANY monotone set of edges (no limit of 16), one or two bin axes.
+//   KIND 0  3-D r          npairs_3d with more than 16 rbins            npairs_3d_engine.pyx:171-182
+//   KIND 1  (rp, pi)       npairs_xy_z with any number of pi edges      npairs_xy_z_engine.pyx:178-194
+//   KIND 2  (s, mu)        npairs_s_mu                                  npairs_s_mu_engine.pyx:196-229
+//   KIND 3  2-D rp         weighted_npairs_xy                           weighted_npairs_xy_engine.pyx:150-175
+//   MODE 0  integer counts (shared-memory u32 histogram per warp)
+//   MODE 1  weighted sums  marked_npairs_xy_z / marked_npairs_3d with general marks / weighted_npairs_xy
+//                          marked_npairs_xy_z_engine.pyx:209-225, marked_npairs_3d_engine.pyx:204-216
+//   MODE 2  per-object     npairs_per_object_3d                         npairs_per_object_3d_engine.pyx:190-207
 // The hot loop only DECIDES whether a pair can be inside the top edge(s): the reference's strict f64 separation
-// (7-8 operations), one integer compare of its high word per bin axis against the high word of the top squared
+// (5-8 operations), one integer compare of its high word per bin axis against the high word of the top squared
 // edge (a conservative superset: the high word of a non-negative double is monotone), and one predicated integer
 // instruction that records the pair as a BIT of a per-lane 64-bit mask (one bit per staged sample2 point and lane
 // point) - no shared-memory queue, no stores.  At the end of every staged chunk the set bits are replayed: the
 // separation is recomputed with the same arithmetic, located among the edges by a table lookup on its exponent and
 // leading mantissa bits (first edge that can be >= the value) followed by exact 64-bit compares of the raw bit
-// patterns (order preserving for non-negative doubles), and the
-// pair is added to the DIFFERENTIAL histogram cell (lowest satisfied edge per axis) of the warp's shared-memory
-// histogram.  The host turns the differential histogram into the reference's cumulative counts (for monotone
-// edges the reference's top-down scans stop exactly at the lowest satisfied edge).
+// patterns (order preserving for non-negative doubles), and the pair (or its weight) is added to the DIFFERENTIAL
+// histogram cell (lowest satisfied edge per axis).  The host turns the differential histogram into the reference's
+// cumulative counts (for monotone edges the reference's top-down scans stop exactly at the lowest satisfied edge).
 #include "kernel.cuh"
 
 __device__ __forceinline__ void bq_lds_f64x2_tok(uint32_t addr, uint32_t tok, double &a, double &b)
@@ -27,59 +31,87 @@ __device__ __forceinline__ unsigned long long bq_lds_u64(uint32_t addr)
     return v;
 }
 
-template <int KIND>
+template <int KIND, int MODE>
 struct BinQ {
-    static constexpr int DIM = 3, NPAY = 0, PPL = 2, WARPS = 8, MINBLOCKS = 2;
+    static constexpr int DIM = KIND == 3 ? 2 : 3, NPAY = MODE == 1 ? HTB_MAX_NW : 0, PPL = 2, WARPS = 8, MINBLOCKS = 2;
     static constexpr bool TMA = true;
     typedef BinQParams Params;
     const Params &P;
-    uint32_t *hist;             // per-warp differential histogram (n0 * n1 u32)
+    uint32_t *hist;             // MODE 0: per-warp differential histogram (n0 * n1 u32); MODE 2: 64 rows of `rstride` u32
+    double *fhist;              // MODE 1: per-warp differential float sums (n0 * n1)
     uint32_t e_s;               // shared-space address: raw bits of the squared edges (n0 then n1), u64
     uint32_t lut_s[2];          // shared-space addresses of the two lookup tables (u8)
     int lane;
+    int rstride;                // MODE 2: u32 per point row (odd: no bank conflicts between lanes)
+    unsigned vmask;             // MODE 2: validity of this lane's points
     double x0, y0, z0, x1, y1, z1;
     double xs0, ys0, zs0, xs1, ys1, zs1;
+    double wa[MODE == 1 ? HTB_MAX_NW : 1], wb[MODE == 1 ? HTB_MAX_NW : 1];
 
+    static __host__ __device__ size_t lut_bytes(const Params &p) { return (((size_t)p.T[0] + 7) & ~(size_t)7) + (((size_t)p.T[1] + 7) & ~(size_t)7); }
     static size_t scratch_bytes(const Params &p)
     {
-        const size_t ne = (size_t)p.n0 + p.n1;
-        return 8 * ne + (((size_t)p.T[0] + 7) & ~(size_t)7) + (((size_t)p.T[1] + 7) & ~(size_t)7) +
-               4 * (((size_t)p.n0 * p.n1 + 3) & ~(size_t)3);
+        const size_t ne = (size_t)p.n0 + p.n1, nh = (size_t)p.n0 * p.n1;
+        size_t acc;
+        if (MODE == 0) acc = 4 * ((nh + 3) & ~(size_t)3);
+        else if (MODE == 1) acc = 8 * nh;
+        else acc = 4 * ((64 * (size_t)(p.n0 | 1) + 3) & ~(size_t)3);
+        return 8 * ne + lut_bytes(p) + acc;
     }
     __device__ BinQ(const Params &p, void *scratch, int ln, const WalkArrays &) : P(p), lane(ln)
     {
         const int ne = P.n0 + P.n1;
         // edges and lookup tables are one contiguous block of 8-byte words on the device
-        const int nl = (((P.T[0] + 7) & ~7) + ((P.T[1] + 7) & ~7)) >> 3;
+        const int nl = (int)(lut_bytes(P) >> 3);
         unsigned long long *e = (unsigned long long *)scratch;
         hist = (uint32_t *)(e + ne + nl);
+        fhist = (double *)(e + ne + nl);
         e_s = smem_u32(e);
         lut_s[0] = e_s + 8u * (uint32_t)ne;
         lut_s[1] = lut_s[0] + (uint32_t)((P.T[0] + 7) & ~7);
+        rstride = P.n0 | 1;
+        vmask = 0;
         for (int k = lane; k < ne + nl; k += 32) e[k] = P.edges[k];
-        for (int k = lane; k < P.n0 * P.n1; k += 32) hist[k] = 0;
+        if (MODE == 0) { for (int k = lane; k < P.n0 * P.n1; k += 32) hist[k] = 0; }
+        else if (MODE == 1) { for (int k = lane; k < P.n0 * P.n1; k += 32) fhist[k] = 0.0; }
+        else { for (int k = lane; k < 64 * rstride; k += 32) hist[k] = 0; }
         x0 = y0 = z0 = x1 = y1 = z1 = 0.0;
         xs0 = ys0 = zs0 = xs1 = ys1 = zs1 = 0.0;
         __syncwarp();
     }
     __device__ __forceinline__ void tile_weight(unsigned) {}
     __device__ __forceinline__ void force_exact() {}
-    __device__ __forceinline__ void tile_begin(const double (&p)[2][3], const bool (&)[2], const uint32_t (&)[2], const WalkArrays &)
+    __device__ __forceinline__ void tile_begin(const double (&p)[2][3], const bool (&val)[2], const uint32_t (&idx)[2], const WalkArrays &A)
     {
         // unused lanes of a partial tile carry the far sentinel in x: never inside the top edge
         x0 = p[0][0]; y0 = p[0][1]; z0 = p[0][2];
         x1 = p[1][0]; y1 = p[1][1]; z1 = p[1][2];
+        vmask = (val[0] ? 1u : 0u) | (val[1] ? 2u : 0u);
+        if (MODE == 1) {
+#pragma unroll
+            for (int k = 0; k < HTB_MAX_NW; ++k) {
+                wa[k] = (A.pay1 && k < A.nw) ? A.pay1[(size_t)idx[0] * A.nw + k] : 0.0;
+                wb[k] = (A.pay1 && k < A.nw) ? A.pay1[(size_t)idx[1] * A.nw + k] : 0.0;
+            }
+        }
     }
     __device__ __forceinline__ void set_shift(const double (&sh)[3], const WalkArrays &)
     {
         // npairs_3d_engine.pyx:167: the periodic shift is applied to the sample1 coordinate first
-        xs0 = x0 - sh[0]; ys0 = y0 - sh[1]; zs0 = z0 - sh[2];
-        xs1 = x1 - sh[0]; ys1 = y1 - sh[1]; zs1 = z1 - sh[2];
+        xs0 = x0 - sh[0]; ys0 = y0 - sh[1];
+        xs1 = x1 - sh[0]; ys1 = y1 - sh[1];
+        if (DIM == 3) { zs0 = z0 - sh[2]; zs1 = z1 - sh[2]; }
     }
     // the two separations the bins are defined on, in the reference's evaluation order
     __device__ __forceinline__ void seps(double xs, double ys, double zs, double xj, double yj, double zj, double &a, double &b)
     {
-        const double dx = xs - xj, dy = ys - yj, dz = zs - zj;
+        const double dx = xs - xj, dy = ys - yj;
+        if (KIND == 3) {
+            a = dx * dx + dy * dy;                      // weighted_npairs_xy_engine.pyx:163-165
+            b = 0.0;
+            return;
+        }
+        const double dz = zs - zj;
         if (KIND == 0) {
             a = dx * dx + dy * dy + dz * dz;            // npairs_3d_engine.pyx:176
             b = 0.0;
@@ -134,21 +166,38 @@ struct BinQ {
         }
         return (act && i0 < P.n0 && i1 < P.n1) ? i0 * P.n1 + i1 : -1;
     }
+    __device__ __forceinline__ double weight_of(const double *w1, uint32_t w2addr)
+    {
+        if (P.wfunc < 0) return lds_f64(w2addr);        // weighted_npairs_xy_engine.pyx:167: the weight is w2[j] alone
+        double w2l[HTB_MAX_NW];
+#pragma unroll
+        for (int k = 0; k < HTB_MAX_NW; ++k) w2l[k] = (k < P.nw) ? lds_f64(w2addr + 8 * k) : 0.0;
+        return htb_pair_weight(P.wfunc, w1, w2l);
+    }
     // every trip takes the lowest recorded pair of BOTH lane points (two independent dependency chains)
     __device__ __forceinline__ void replay(uint32_t stage, unsigned long long M0, unsigned long long M1)
     {
-        const uint32_t bx = stage, by = stage + 8 * HTB_CH, bz = stage + 16 * HTB_CH;
+        const uint32_t bx = stage, by = stage + 8 * HTB_CH, bz = stage + 16 * HTB_CH, bw = stage + 8 * DIM * HTB_CH;
         while (__any_sync(HTB_FULL, (M0 | M1) != 0ull)) {
             const bool act0 = M0 != 0ull, act1 = M1 != 0ull;
             const int j0 = max(__ffsll((long long)M0) - 1, 0), j1 = max(__ffsll((long long)M1) - 1, 0);
             M0 &= M0 - 1ull;
             M1 &= M1 - 1ull;
-            const double xa = lds_f64(bx + 8 * j0), ya = lds_f64(by + 8 * j0), za = lds_f64(bz + 8 * j0);
-            const double xb = lds_f64(bx + 8 * j1), yb = lds_f64(by + 8 * j1), zb = lds_f64(bz + 8 * j1);
+            const double xa = lds_f64(bx + 8 * j0), ya = lds_f64(by + 8 * j0), za = DIM == 3 ? lds_f64(bz + 8 * j0) : 0.0;
+            const double xb = lds_f64(bx + 8 * j1), yb = lds_f64(by + 8 * j1), zb = DIM == 3 ? lds_f64(bz + 8 * j1) : 0.0;
             const int h0 = replay_one(act0, xs0, ys0, zs0, xa, ya, za);
             const int h1 = replay_one(act1, xs1, ys1, zs1, xb, yb, zb);
-            if (h0 >= 0) atomicAdd(hist + h0, 1u);
-            if (h1 >= 0) atomicAdd(hist + h1, 1u);
+            if (MODE == 0) {
+                if (h0 >= 0) atomicAdd(hist + h0, 1u);
+                if (h1 >= 0) atomicAdd(hist + h1, 1u);
+            } else if (MODE == 1) {
+                if (h0 >= 0) atomicAdd(fhist + h0, weight_of(wa, bw + 8 * j0 * P.nw));
+                if (h1 >= 0) atomicAdd(fhist + h1, weight_of(wb, bw + 8 * j1 * P.nw));
+            } else {
+                // rows are private to the lane's points: plain read-modify-write
+                if (h0 >= 0) hist[lane * rstride + h0] += 1u;
+                if (h1 >= 0) hist[(32 + lane) * rstride + h1] += 1u;
+            }
         }
     }
     __device__ __forceinline__ void chunk(uint32_t stage, int lo, int hi, uint32_t tok)
@@ -164,13 +213,13 @@ struct BinQ {
             uint32_t a0 = 0u, a1 = 0u;
 #pragma unroll 2
             for (int j = b0; j < b1; j += 4) {
-                double xa, xb, xc, xd, ya, yb, yc, yd, za, zb, zc, zd;
+                double xa, xb, xc, xd, ya, yb, yc, yd, za = 0.0, zb = 0.0, zc = 0.0, zd = 0.0;
                 bq_lds_f64x2_tok(bx + 8 * j, tok, xa, xb);
                 bq_lds_f64x2_tok(by + 8 * j, tok, ya, yb);
-                bq_lds_f64x2_tok(bz + 8 * j, tok, za, zb);
+                if (DIM == 3) bq_lds_f64x2_tok(bz + 8 * j, tok, za, zb);
                 bq_lds_f64x2_tok(bx + 8 * j + 16, tok, xc, xd);
                 bq_lds_f64x2_tok(by + 8 * j + 16, tok, yc, yd);
-                bq_lds_f64x2_tok(bz + 8 * j + 16, tok, zc, zd);
+                if (DIM == 3) bq_lds_f64x2_tok(bz + 8 * j + 16, tok, zc, zd);
                 unsigned n0 = maybe(xs0, ys0, zs0, xa, ya, za);
                 unsigned n1 = maybe(xs1, ys1, zs1, xa, ya, za);
                 n0 |= maybe(xs0, ys0, zs0, xb, yb, zb) << 1;
@@ -189,13 +238,35 @@ struct BinQ {
         const unsigned long long M1 = ((unsigned long long)m[1][0] | ((unsigned long long)m[1][1] << 32)) & range;
         replay(stage, M0, M1);
     }
-    __device__ __forceinline__ bool tile_end(const WalkArrays &, const uint32_t (&)[2], int, unsigned wt)
+    __device__ __forceinline__ bool tile_end(const WalkArrays &, const uint32_t (&idx)[2], int, unsigned wt)
     {
         __syncwarp();
         const int nh = P.n0 * P.n1;
-        for (int k = lane; k < nh; k += 32) {
-            const uint32_t h = hist[k];
-            if (h) { atomicAdd(P.counts + k, (unsigned long long)wt * h); hist[k] = 0; }
+        if (MODE == 0) {
+            for (int k = lane; k < nh; k += 32) {
+                const uint32_t h = hist[k];
+                if (h) { atomicAdd(P.counts + k, (unsigned long long)wt * h); hist[k] = 0; }
+            }
+        } else if (MODE == 1) {
+            for (int k = lane; k < nh; k += 32) {
+                const double h = fhist[k];
+                if (h != 0.0) { atomicAdd(P.fcounts + k, wt == 2u ? h + h : h); fhist[k] = 0.0; }
+            }
+        } else {
+            // per object: cumulative over the edges (npairs_per_object_3d_engine.pyx:190-207), rows in input order;
+            // several work items (column slices) may add to the same row
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                if (!((vmask >> q) & 1u)) continue;
+                unsigned long long *row = P.rows + (size_t)P.perm1[idx[q]] * (size_t)P.n0;
+                uint32_t *r = hist + (q * 32 + lane) * rstride;
+                unsigned long long cum = 0ull;
+                for (int k = 0; k < P.n0; ++k) {
+                    cum += r[k];
+                    r[k] = 0u;
+                    if (cum) atomicAdd(row + k, cum);
+                }
+            }
         }
         __syncwarp();
         return false;
@@ -203,13 +274,17 @@ struct BinQ {
     __device__ __forceinline__ void kernel_end() {}
 };
 
-int htb_launch_binq(cudaStream_t st, int kind, const WalkGeom &G, const WalkArrays &A, const BinQParams &P, int *l)
+int htb_launch_binq(cudaStream_t st, int kind, int mode, const WalkGeom &G, const WalkArrays &A, const BinQParams &P, int *l)
 {
-    switch (kind) {
-    case 0: return launch_count<BinQ<0>>(st, G, A, P, l);
-    case 1: return launch_count<BinQ<1>>(st, G, A, P, l);
-    case 2: return launch_count<BinQ<2>>(st, G, A, P, l);
+    switch (mode * 4 + kind) {
+    case 0: return launch_count<BinQ<0, 0>>(st, G, A, P, l);
+    case 1: return launch_count<BinQ<1, 0>>(st, G, A, P, l);
+    case 2: return launch_count<BinQ<2, 0>>(st, G, A, P, l);
+    case 4: return launch_count<BinQ<0, 1>>(st, G, A, P, l);
+    case 5: return launch_count<BinQ<1, 1>>(st, G, A, P, l);
+    case 7: return launch_count<BinQ<3, 1>>(st, G, A, P, l);
+    case 8: return launch_count<BinQ<0, 2>>(st, G, A, P, l);
     }
-    htb_set_error("unknown BinQ kind %d", kind);
+    htb_set_error("unknown BinQ kind %d / mode %d", kind, mode);
     return 1;
 }

@@ -743,7 +743,16 @@ static bool binq_ok(const double *e0, int n0, const double *e1, int n1, uint32_t
     return e0[0] >= 0.0 && (!e1 || e1[0] >= 0.0);
 }
 
-static int run_binq(Call &c, int kind, const double *e0, int n0, const double *e1, int n1, int64_t *counts_out, htb_stats *stats)
+// The reference's top-down scans stop at the first failing edge (npairs_3d_engine.pyx:178-182), so edge k admits a
+// pair iff the pair satisfies edges k..n-1: the counts are those of the suffix minima of the squared edges, which are
+// non-decreasing by construction.
+static void suffix_min(std::vector<double> &e, int first, int n)
+{
+    for (int k = n - 2; k >= 0; --k) if (e[(size_t)first + k + 1] < e[(size_t)first + k]) e[(size_t)first + k] = e[(size_t)first + k + 1];
+}
+
+// edges + lookup tables of a BinQ launch (uploaded with the call's workspace)
+static int binq_prepare(Call &c, const double *e0, int n0, const double *e1, int n1, BinQParams *out)
 {
     std::vector<unsigned long long> eb((size_t)n0 + n1, 0ULL);
     for (int k = 0; k < n0; ++k) eb[k] = dbits(e0[k] + 0.0);
@@ -777,27 +786,64 @@ static int run_binq(Call &c, int kind, const double *e0, int n0, const double *e
     memcpy((unsigned char *)(eb.data() + ne) + lut[0].size(), lut[1].data(), lut[1].size());
     void *edev = nullptr;
     if (upload(c, eb.data(), sizeof(unsigned long long) * eb.size(), &edev)) return 1;
-    const int nh = n0 * n1;
-    unsigned long long *counts_dev = nullptr;
-    if (c.ws.alloc((void **)&counts_dev, sizeof(unsigned long long) * (size_t)nh)) return 1;
-    HTB_CUDA(cudaMemsetAsync(counts_dev, 0, sizeof(unsigned long long) * (size_t)nh, c.st));
     bp.n0 = n0; bp.n1 = n1;
     bp.H0 = (int)(eb[(size_t)n0 - 1] >> 32);
     bp.H1 = e1 ? (int)(eb[(size_t)n0 + n1 - 1] >> 32) : 0;
     bp.edges = (const unsigned long long *)edev;
+    *out = bp;
+    return 0;
+}
+
+// inclusive 2-D prefix sums: differential histogram -> the reference's cumulative counts
+template <class T>
+static void prefix2d(const T *diff, int n0, int n1, T *out)
+{
+    for (int k = 0; k < n0; ++k)
+        for (int g = 0; g < n1; ++g) {
+            T s = diff[(size_t)k * n1 + g];
+            if (k > 0) s += out[(size_t)(k - 1) * n1 + g];
+            if (g > 0) s += out[(size_t)k * n1 + g - 1];
+            if (k > 0 && g > 0) s -= out[(size_t)(k - 1) * n1 + g - 1];
+            out[(size_t)k * n1 + g] = s;
+        }
+}
+
+static int run_binq(Call &c, int kind, const double *e0, int n0, const double *e1, int n1, int64_t *counts_out, htb_stats *stats)
+{
+    BinQParams bp{};
+    if (binq_prepare(c, e0, n0, e1, n1, &bp)) return 1;
+    const int nh = n0 * n1;
+    unsigned long long *counts_dev = nullptr;
+    if (c.ws.alloc((void **)&counts_dev, sizeof(unsigned long long) * (size_t)nh)) return 1;
+    HTB_CUDA(cudaMemsetAsync(counts_dev, 0, sizeof(unsigned long long) * (size_t)nh, c.st));
     bp.counts = counts_dev;
-    if (htb_launch_binq(c.st, kind, c.G, c.A, bp, &c.launches)) return 1;
+    if (htb_launch_binq(c.st, kind, 0, c.G, c.A, bp, &c.launches)) return 1;
     std::vector<long long> diff((size_t)nh);
     HTB_CUDA(cudaMemcpyAsync(diff.data(), counts_dev, sizeof(int64_t) * (size_t)nh, cudaMemcpyDeviceToHost, c.st));
     if (c.finish(stats, 3)) return 1;
-    for (int k = 0; k < n0; ++k)
-        for (int g = 0; g < n1; ++g) {
-            long long s = diff[(size_t)k * n1 + g];
-            if (k > 0) s += counts_out[(size_t)(k - 1) * n1 + g];
-            if (g > 0) s += counts_out[(size_t)k * n1 + g - 1];
-            if (k > 0 && g > 0) s -= counts_out[(size_t)(k - 1) * n1 + g - 1];
-            counts_out[(size_t)k * n1 + g] = s;
-        }
+    prefix2d<long long>(diff.data(), n0, n1, (long long *)counts_out);
+    return 0;
+}
+
+// weighted sums (MODE 1): differential float histogram -> cumulative sums.  The differential cells are summed in
+// double precision; the reference adds every pair's weight to each of its cumulative cells in turn
+// (marked_npairs_xy_z_engine.pyx:217-225), so the two agree to rounding (1e-16 relative per term).
+static int run_binq_weighted(Call &c, int kind, int nw, int wfunc, const double *e0, int n0, const double *e1, int n1,
+                             double *counts_out, htb_stats *stats)
+{
+    BinQParams bp{};
+    if (binq_prepare(c, e0, n0, e1, n1, &bp)) return 1;
+    const int nh = n0 * n1;
+    double *sums_dev = nullptr;
+    if (c.ws.alloc((void **)&sums_dev, sizeof(double) * (size_t)nh)) return 1;
+    HTB_CUDA(cudaMemsetAsync(sums_dev, 0, sizeof(double) * (size_t)nh, c.st));
+    bp.fcounts = sums_dev;
+    bp.nw = nw; bp.wfunc = wfunc;
+    if (htb_launch_binq(c.st, kind, 1, c.G, c.A, bp, &c.launches)) return 1;
+    std::vector<double> diff((size_t)nh);
+    HTB_CUDA(cudaMemcpyAsync(diff.data(), sums_dev, sizeof(double) * (size_t)nh, cudaMemcpyDeviceToHost, c.st));
+    if (c.finish(stats, 3)) return 1;
+    prefix2d<double>(diff.data(), n0, n1, counts_out);
     return 0;
 }
 
@@ -827,9 +873,10 @@ extern "C" int htb_npairs_3d_engine(const htb_mesh_geom *mesh,
     if (fast) {
         fp.counts = counts_dev;
         if (htb_launch_fast3(c.st, c.G, c.A, fp, &c.launches)) return 1;
-    } else if (binq_ok(rsq.data(), nb, nullptr, 1, flags)) {
+    } else if (suffix_min(rsq, 0, nb), binq_ok(rsq.data(), nb, nullptr, 1, flags)) {
         return run_binq(c, 0, rsq.data(), nb, nullptr, 1, counts_out, stats);
     } else {
+        for (int k = 0; k < nb; ++k) rsq[k] = rbins[k] * rbins[k];
         GenParams gp{};
         gp.n0 = nb; gp.n1 = 1; gp.nhist = nb;
         void *e0 = nullptr;
@@ -892,8 +939,13 @@ extern "C" int htb_npairs_xy_z_engine(const htb_mesh_geom *mesh,
         }
         return 0;
     }
-    if (binq_ok(e.data(), nrp, e.data() + nrp, npi, flags))
-        return run_binq(c, 1, e.data(), nrp, e.data() + nrp, npi, counts_out, stats);
+    {
+        std::vector<double> em(e);
+        suffix_min(em, 0, nrp);
+        suffix_min(em, nrp, npi);
+        if (binq_ok(em.data(), nrp, em.data() + nrp, npi, flags))
+            return run_binq(c, 1, em.data(), nrp, em.data() + nrp, npi, counts_out, stats);
+    }
     void *edev = nullptr;
     if (upload(c, e.data(), sizeof(double) * e.size(), &edev)) return 1;
     GenParams gp{};
@@ -1001,6 +1053,12 @@ extern "C" int htb_marked_npairs_3d_engine(const htb_mesh_geom *mesh,
         counts_out[nb - 1] = h[HTB_NBF];
         return 0;
     }
+    {
+        std::vector<double> em(rsq);
+        suffix_min(em, 0, nb);
+        if (binq_ok(em.data(), nb, nullptr, 1, flags))
+            return run_binq_weighted(c, 0, nw, weight_func_id, em.data(), nb, nullptr, 1, counts_out, stats);
+    }
     void *edev = nullptr;
     if (upload(c, rsq.data(), sizeof(double) * (size_t)nb, &edev)) return 1;
     double *counts_dev = nullptr;
@@ -1017,6 +1075,96 @@ extern "C" int htb_marked_npairs_3d_engine(const htb_mesh_geom *mesh,
 }
 
 // ------------------------------------------------------------------ mean_delta_sigma
+// ------------------------------------------------------------------ marked_npairs_xy_z
+extern "C" int htb_marked_npairs_xy_z_engine(const htb_mesh_geom *mesh,
+                                             const double *x1, const double *y1, const double *z1, int64_t stride1, int64_t n1,
+                                             const double *x2, const double *y2, const double *z2, int64_t stride2, int64_t n2,
+                                             const double *w1, const double *w2, int32_t nw, int32_t weight_func_id,
+                                             const double *rp_bins, int32_t nrp, const double *pi_bins, int32_t npi,
+                                             int64_t first_cell1, int64_t last_cell1,
+                                             double *counts_out, uint32_t flags, htb_stats *stats)
+{
+    HTB_GUARD_BEGIN
+    if (!mesh || !rp_bins || !pi_bins || !counts_out || nrp < 1 || npi < 1 || !w1 || !w2) { htb_set_error("htb_marked_npairs_xy_z_engine: bad arguments"); return 1; }
+    if (mesh->ndim != 3) { htb_set_error("htb_marked_npairs_xy_z_engine needs a 3-d mesh"); return 1; }
+    if (nw < 1 || nw > HTB_MAX_NW) { htb_set_error("weights per point must be in [1, %d]", HTB_MAX_NW); return 1; }
+    if (weight_func_id < 0 || weight_func_id > 17) { htb_set_error("marking function does not exist, id=%d", weight_func_id); return 1; }
+    std::vector<double> e((size_t)nrp + npi);
+    for (int k = 0; k < nrp; ++k) e[k] = rp_bins[k] * rp_bins[k];
+    for (int k = 0; k < npi; ++k) e[nrp + k] = pi_bins[k] * pi_bins[k];
+    suffix_min(e, 0, nrp);
+    suffix_min(e, nrp, npi);
+    if (!binq_ok(e.data(), nrp, e.data() + nrp, npi, flags & ~HTB_FLAG_GENERIC)) {
+        htb_set_error("htb_marked_npairs_xy_z_engine: bins must be finite, at most 255 per axis and 4096 cells");
+        return 1;
+    }
+    Call c;
+    if (c.begin()) return 1;
+    const double *c1[3] = {x1, y1, z1}, *c2[3] = {x2, y2, z2};
+    if (c.setup(mesh, 0, false, c1, stride1, n1, w1, c2, stride2, n2, w2, nw, false, first_cell1, last_cell1, flags)) return 1;
+    return run_binq_weighted(c, 1, nw, weight_func_id, e.data(), nrp, e.data() + nrp, npi, counts_out, stats);
+    HTB_GUARD_END
+}
+
+// ------------------------------------------------------------------ weighted_npairs_xy (2-D mesh)
+extern "C" int htb_weighted_npairs_xy_engine(const htb_mesh_geom *mesh,
+                                             const double *x1, const double *y1, int64_t stride1, int64_t n1,
+                                             const double *x2, const double *y2, int64_t stride2, int64_t n2,
+                                             const double *w2, const double *rp_bins, int32_t nrp,
+                                             int64_t first_cell1, int64_t last_cell1,
+                                             double *counts_out, uint32_t flags, htb_stats *stats)
+{
+    HTB_GUARD_BEGIN
+    if (!mesh || !rp_bins || !counts_out || nrp < 1 || !w2) { htb_set_error("htb_weighted_npairs_xy_engine: bad arguments"); return 1; }
+    if (mesh->ndim != 2) { htb_set_error("htb_weighted_npairs_xy_engine needs a 2-d mesh"); return 1; }
+    std::vector<double> e((size_t)nrp);
+    for (int k = 0; k < nrp; ++k) e[k] = rp_bins[k] * rp_bins[k];
+    suffix_min(e, 0, nrp);
+    if (!binq_ok(e.data(), nrp, nullptr, 1, flags & ~HTB_FLAG_GENERIC)) {
+        htb_set_error("htb_weighted_npairs_xy_engine: bins must be finite and at most 255");
+        return 1;
+    }
+    Call c;
+    if (c.begin()) return 1;
+    const double *c1[3] = {x1, y1, nullptr}, *c2[3] = {x2, y2, nullptr};
+    if (c.setup(mesh, 1, false, c1, stride1, n1, nullptr, c2, stride2, n2, w2, 1, false, first_cell1, last_cell1, flags)) return 1;
+    return run_binq_weighted(c, 3, 1, -1, e.data(), nrp, nullptr, 1, counts_out, stats);
+    HTB_GUARD_END
+}
+
+// ------------------------------------------------------------------ npairs_per_object_3d
+extern "C" int htb_npairs_per_object_3d_engine(const htb_mesh_geom *mesh,
+                                               const double *x1, const double *y1, const double *z1, int64_t stride1, int64_t n1,
+                                               const double *x2, const double *y2, const double *z2, int64_t stride2, int64_t n2,
+                                               const double *rbins, int32_t nb, int64_t first_cell1, int64_t last_cell1,
+                                               int64_t *counts_out, uint32_t flags, htb_stats *stats)
+{
+    HTB_GUARD_BEGIN
+    if (!mesh || !rbins || !counts_out || nb < 1) { htb_set_error("htb_npairs_per_object_3d_engine: bad arguments"); return 1; }
+    if (mesh->ndim != 3) { htb_set_error("htb_npairs_per_object_3d_engine needs a 3-d mesh"); return 1; }
+    if (nb > 64) { htb_set_error("htb_npairs_per_object_3d_engine: at most 64 rbins (per-point shared-memory rows)"); return 1; }
+    std::vector<double> e((size_t)nb);
+    for (int k = 0; k < nb; ++k) e[k] = rbins[k] * rbins[k];
+    suffix_min(e, 0, nb);
+    if (!binq_ok(e.data(), nb, nullptr, 1, flags & ~HTB_FLAG_GENERIC)) { htb_set_error("htb_npairs_per_object_3d_engine: rbins must be finite"); return 1; }
+    Call c;
+    if (c.begin()) return 1;
+    const double *c1[3] = {x1, y1, z1}, *c2[3] = {x2, y2, z2};
+    if (c.setup(mesh, 1, false, c1, stride1, n1, nullptr, c2, stride2, n2, nullptr, 0, true, first_cell1, last_cell1, flags)) return 1;
+    BinQParams bp{};
+    if (binq_prepare(c, e.data(), nb, nullptr, 1, &bp)) return 1;
+    const size_t nout = (size_t)(n1 > 0 ? n1 : 1) * (size_t)nb;
+    unsigned long long *rows = nullptr;
+    if (c.ws.alloc((void **)&rows, sizeof(unsigned long long) * nout)) return 1;
+    HTB_CUDA(cudaMemsetAsync(rows, 0, sizeof(unsigned long long) * nout, c.st));
+    bp.rows = rows;
+    bp.perm1 = c.s1.perm;
+    if (htb_launch_binq(c.st, 0, 2, c.G, c.A, bp, &c.launches)) return 1;
+    if (n1 > 0) HTB_CUDA(cudaMemcpyAsync(counts_out, rows, sizeof(int64_t) * (size_t)n1 * nb, cudaMemcpyDeviceToHost, c.st));
+    return c.finish(stats, 3);
+    HTB_GUARD_END
+}
+
 // Column sums of the (n, nbin) per-object rows in a fixed order (HTB_FLAG_COLUMN_SUM): block b sums rows
 // b, b + gridDim.x, ... per column, a second launch adds the per-block partial sums.
 __global__ void __launch_bounds__(256) k_colsum_partial(const double *__restrict__ rows, long long n, int nbin,

@@ -69,6 +69,12 @@ struct BinQParams {
     // per axis: lut[(bits >> S) - kmin] = first edge whose key (bits >> S) is >= that of the value; T entries
     int S[2], T[2];
     unsigned kmin[2];
+    // weighted modes (marked_npairs_xy_z, marked_npairs_3d with general marks, weighted_npairs_xy)
+    int nw, wfunc;                   // weights per point; weight_func_id, or -1: the weight is sample2's w2[0] alone
+    double *fcounts;                 // device: [n0 * n1] differential float sums
+    // per-object mode (npairs_per_object_3d)
+    unsigned long long *rows;        // device: (n1_points, n0) cumulative counts in INPUT order
+    const uint32_t *perm1;           // sorted position -> input row
 };
 
 int htb_fast3_ppl();            // sample1 points per lane of the fast kernel (its tiles hold 32x that)
@@ -77,7 +83,7 @@ int htb_launch_markedq(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, 
 int htb_launch_fastxyz(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const Fast3Params &P, int *launches);
 int htb_launch_dsq(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const DSQParams &P, int *launches);
 int htb_launch_dsr(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const DSRParams &P, int *launches);
-int htb_launch_binq(cudaStream_t st, int kind, const WalkGeom &G, const WalkArrays &A, const BinQParams &P, int *launches);
+int htb_launch_binq(cudaStream_t st, int kind /* 0 r, 1 (rp, pi), 2 (s, mu), 3 2-D rp */, int mode /* 0 counts, 1 weighted, 2 per object */, const WalkGeom &G, const WalkArrays &A, const BinQParams &P, int *launches);
 int htb_launch_gen(cudaStream_t st, int kind, const WalkGeom &G, const WalkArrays &A, const GenParams &P, int *launches);
 int htb_build_tiles(cudaStream_t st, Workspace &ws, const WalkGeom &G, const SortedSample &s1,
                     int64_t first_cell1, int64_t last_cell1, const long long *range_dev /* device {first, last} or null */,

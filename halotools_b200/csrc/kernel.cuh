@@ -181,6 +181,35 @@ k_count(const __grid_constant__ WalkGeom G, const __grid_constant__ WalkArrays A
     }
 }
 
+// ------------------------------------------------------------------ pair weights of the marked counters
+__device__ __forceinline__ double htb_pair_weight(int id, const double *w1, const double *w2)
+{
+    // marking_functions.pyx:14-217 (id 8 keeps the reference's '+', :106), custom_marking_func.pyx:12-16
+    double d;
+    switch (id) {
+    case 0: case 1: return w1[0] * w2[0];
+    case 2:  return w1[0] + w2[0];
+    case 3:  return (w1[0] == w2[0]) ? w1[1] * w2[1] : 0.0;
+    case 4:  return (w1[0] != w2[0]) ? w1[1] * w2[1] : 0.0;
+    case 5:  return (w2[0] > w1[0]) ? w1[1] * w2[1] : 0.0;
+    case 6:  return (w2[0] < w1[0]) ? w1[1] * w2[1] : 0.0;
+    case 7:  return (w2[0] > (w1[0] + w1[1])) ? w2[1] : 0.0;
+    case 8:  return (w2[0] < (w1[0] + w1[1])) ? w2[1] : 0.0;
+    case 9:  return (fabs(w1[0] - w2[0]) < w1[1]) ? w2[1] : 0.0;
+    case 10: return (fabs(w1[0] - w2[0]) > w1[1]) ? w2[1] : 0.0;
+    case 11: return (w2[0] > w1[0] * w1[1]) ? w2[1] : 0.0;
+    case 12: return w1[0] * w2[0] * (w1[1] * w2[1] + w1[2] * w2[2] + w1[3] * w2[3]);
+    case 13: d = (w1[1] * w2[1] + w1[2] * w2[2] + w1[3] * w2[3]); return w1[0] * w2[0] * d * d;
+    case 14: return w1[0] * w2[0] * (w1[1] * w2[1] + w1[2] * w2[2]);
+    case 15: d = (w1[1] * w2[1] + w1[2] * w2[2]); return w1[0] * w2[0] * d * d;
+    case 16: d = (w1[1] * w2[1] + w1[2] * w2[2] + w1[3] * w2[3]);
+             return (w1[4] == w2[4]) ? w1[0] * w2[0] * d * d : 0.0;
+    case 17: d = (w1[1] * w2[1] + w1[2] * w2[2] + w1[3] * w2[3]);
+             return (w1[4] != w2[4]) ? w1[0] * w2[0] * d * d : 0.0;
+    default: return 0.0;
+    }
+}
+
 // ------------------------------------------------------------------ host launcher
 template <class V>
 static int launch_count(cudaStream_t st, const WalkGeom &G, const WalkArrays &A, const typename V::Params &P,

@@ -141,6 +141,37 @@ int htb_mean_delta_sigma_engine(const htb_mesh_geom *mesh,
                                 int64_t first_cell1, int64_t last_cell1,
                                 double *delta_sigma_out, uint32_t flags, htb_stats *stats);
 
+/* marked_npairs_xy_z_engine.pyx:21 (marked_cpairs/) - counts[k,g] = sum f_id(w1_i, w2_j) over pairs with
+ * dx^2+dy^2 <= rp[k]^2 and dz^2 <= pi[g]^2, f64[nrp*npi] (:209-225).  Weights as in the marked 3-D engine.  */
+int htb_marked_npairs_xy_z_engine(const htb_mesh_geom *mesh,
+                                  const double *x1, const double *y1, const double *z1, int64_t stride1, int64_t n1,
+                                  const double *x2, const double *y2, const double *z2, int64_t stride2, int64_t n2,
+                                  const double *w1, const double *w2, int32_t nw, int32_t weight_func_id,
+                                  const double *rp_bins, int32_t nrp, const double *pi_bins, int32_t npi,
+                                  int64_t first_cell1, int64_t last_cell1,
+                                  double *counts_out, uint32_t flags, htb_stats *stats);
+
+/* npairs_per_object_3d_engine.pyx:17 (cpairs/) - counts[i,k] = #{j: dsq_ij <= rbins[k]^2} for every sample1 point,
+ * int64[n1*nb], rows in the INPUT order of sample1 (the engine un-sorts at exit, :209-213); rows of points whose
+ * mesh1 cell is outside [first_cell1, last_cell1) are zero, as in each reference worker.  nb <= 64.
+ * (npairs_projected_engine.pyx:17 needs no entry point of its own: it is htb_npairs_xy_z_engine with the single
+ * pi edge pi_max, :184-189.)                                                                                       */
+int htb_npairs_per_object_3d_engine(const htb_mesh_geom *mesh,
+                                    const double *x1, const double *y1, const double *z1, int64_t stride1, int64_t n1,
+                                    const double *x2, const double *y2, const double *z2, int64_t stride2, int64_t n2,
+                                    const double *rbins, int32_t nb,
+                                    int64_t first_cell1, int64_t last_cell1,
+                                    int64_t *counts_out, uint32_t flags, htb_stats *stats);
+
+/* weighted_npairs_xy_engine.pyx:17 (surface_density/engines/) - 2-D mesh (mesh->ndim == 2):
+ * counts[k] = sum w2_j over pairs with dx^2+dy^2 <= rp[k]^2, f64[nrp] (:150-175).             */
+int htb_weighted_npairs_xy_engine(const htb_mesh_geom *mesh,
+                                  const double *x1, const double *y1, int64_t stride1, int64_t n1,
+                                  const double *x2, const double *y2, int64_t stride2, int64_t n2,
+                                  const double *w2, const double *rp_bins, int32_t nrp,
+                                  int64_t first_cell1, int64_t last_cell1,
+                                  double *counts_out, uint32_t flags, htb_stats *stats);
+
 /* RectangularMesh cell assignment alone (rectangular_mesh.py:19-22,211-225): writes the
  * reference cell id of every point (int64[n]) — used by the mesh parity tests.               */
 int htb_mesh_cell_ids(int32_t ndim, const double *x, const double *y, const double *z, int64_t stride, int64_t n,

@@ -43,6 +43,11 @@ ENGINES = [
     "halotools/mock_observables/pair_counters/marked_cpairs/custom_marking_func",
     "halotools/mock_observables/pair_counters/marked_cpairs/marked_npairs_3d_engine",
     "halotools/mock_observables/surface_density/engines/mean_delta_sigma_engine",
+    # SURVEY section 8(f) rank 2
+    "halotools/mock_observables/pair_counters/cpairs/npairs_projected_engine",
+    "halotools/mock_observables/pair_counters/cpairs/npairs_per_object_3d_engine",
+    "halotools/mock_observables/pair_counters/marked_cpairs/marked_npairs_xy_z_engine",
+    "halotools/mock_observables/surface_density/engines/weighted_npairs_xy_engine",
 ]
 
 ASTROPY_SHIM = '''"""Shim for astropy.utils.misc (astropy is absent from this image)."""
@@ -69,27 +74,35 @@ TRIMMED_INITS = {
     "halotools/mock_observables/__init__.py":
         "from .pair_counters import *\n"
         "from .two_point_clustering import tpcf, wp, rp_pi_tpcf, marked_tpcf\n"
-        "from .surface_density import mean_delta_sigma\n",
+        "from .surface_density import mean_delta_sigma, weighted_npairs_xy\n",
     "halotools/mock_observables/pair_counters/__init__.py":
         "from .rectangular_mesh import RectangularDoubleMesh\n"
         "from .rectangular_mesh_2d import RectangularDoubleMesh2D\n"
         "from .npairs_3d import npairs_3d\n"
         "from .npairs_xy_z import npairs_xy_z\n"
         "from .marked_npairs_3d import marked_npairs_3d\n"
-        "from .npairs_s_mu import npairs_s_mu\n",
+        "from .npairs_s_mu import npairs_s_mu\n"
+        "from .npairs_projected import npairs_projected\n"
+        "from .npairs_per_object_3d import npairs_per_object_3d\n"
+        "from .marked_npairs_xy_z import marked_npairs_xy_z\n",
     "halotools/mock_observables/pair_counters/cpairs/__init__.py":
         "from .npairs_3d_engine import npairs_3d_engine\n"
         "from .npairs_xy_z_engine import npairs_xy_z_engine\n"
-        "from .npairs_s_mu_engine import npairs_s_mu_engine\n",
+        "from .npairs_s_mu_engine import npairs_s_mu_engine\n"
+        "from .npairs_projected_engine import npairs_projected_engine\n"
+        "from .npairs_per_object_3d_engine import npairs_per_object_3d_engine\n",
     "halotools/mock_observables/pair_counters/marked_cpairs/__init__.py":
-        "from .marked_npairs_3d_engine import marked_npairs_3d_engine\n",
+        "from .marked_npairs_3d_engine import marked_npairs_3d_engine\n"
+        "from .marked_npairs_xy_z_engine import marked_npairs_xy_z_engine\n",
     "halotools/mock_observables/two_point_clustering/__init__.py":
         "from .wp import wp\nfrom .rp_pi_tpcf import rp_pi_tpcf\n"
         "from .tpcf import tpcf\nfrom .marked_tpcf import marked_tpcf\n",
     "halotools/mock_observables/surface_density/__init__.py":
-        "from .mean_delta_sigma import mean_delta_sigma\n",
+        "from .mean_delta_sigma import mean_delta_sigma\n"
+        "from .weighted_npairs_xy import weighted_npairs_xy\n",
     "halotools/mock_observables/surface_density/engines/__init__.py":
-        "from .mean_delta_sigma_engine import mean_delta_sigma_engine\n",
+        "from .mean_delta_sigma_engine import mean_delta_sigma_engine\n"
+        "from .weighted_npairs_xy_engine import weighted_npairs_xy_engine\n",
 }
 
 # written into oracle/_ref so the engines import without the reference tree

@@ -17,6 +17,10 @@ Reference call sites restated:
   marked_npairs_3d  .../pair_counters/marked_npairs_3d.py:130-183
   mean_delta_sigma  /root/reference/halotools/mock_observables/surface_density/mean_delta_sigma.py:212-255,258-330
   _enclose_in_box   .../pair_counters/mesh_helpers.py:17-64 ; _enclose_in_square :67-110
+  npairs_projected      .../pair_counters/npairs_projected.py:118-157,160-227
+  npairs_per_object_3d  .../pair_counters/npairs_per_object_3d.py:106-142
+  marked_npairs_xy_z    .../pair_counters/marked_npairs_xy_z.py:141-194
+  weighted_npairs_xy    /root/reference/halotools/mock_observables/surface_density/weighted_npairs_xy.py:111-151,153-217
 """
 import ctypes
 import os
@@ -250,6 +254,103 @@ def mean_delta_sigma(galaxies, particles, effective_particle_masses, rp_bins, pe
     unsort[dm.mesh1.idx_sorted] = np.arange(n1)
     out = out[unsort, :]
     return out if per_object else np.mean(out, axis=0)
+
+
+def npairs_projected(sample1, sample2, rp_bins, pi_max, period=None, approx_cell1_size=None,
+                     approx_cell2_size=None, cell1_range=None):
+    rp_bins = _f8(np.atleast_1d(rp_bins))
+    rp_max, pi_max = float(np.max(rp_bins)), float(pi_max)
+    # default cell sizes are rp_max in all three dimensions (npairs_projected.py:214-221)
+    a1 = [rp_max] * 3 if approx_cell1_size is None else approx_cell1_size
+    a2 = [rp_max] * 3 if approx_cell2_size is None else approx_cell2_size
+    dm, c1, c2 = build_double_mesh_3d(sample1, sample2, [rp_max, rp_max, pi_max], period, a1, a2)
+    x1, y1, z1 = _sorted(c1, dm.mesh1)
+    x2, y2, z2 = _sorted(c2, dm.mesh2)
+    g = _geom(dm)
+    first, last = _range(dm, cell1_range)
+    out = np.zeros(len(rp_bins), dtype=np.int64)
+    lib().oracle_npairs_projected(ctypes.byref(g), _p(x1), _p(y1), _p(z1), _p(dm.mesh1.cell_id_indices, ctypes.c_int64),
+                                  _p(x2), _p(y2), _p(z2), _p(dm.mesh2.cell_id_indices, ctypes.c_int64),
+                                  _p(rp_bins), ctypes.c_int(len(rp_bins)), ctypes.c_double(pi_max),
+                                  ctypes.c_int64(first), ctypes.c_int64(last), _p(out, ctypes.c_int64))
+    return out
+
+
+def npairs_per_object_3d(sample1, sample2, rbins, period=None, approx_cell1_size=None, approx_cell2_size=None,
+                         cell1_range=None):
+    rbins = _f8(np.atleast_1d(rbins))
+    rmax = float(np.max(rbins))
+    dm, c1, c2 = build_double_mesh_3d(sample1, sample2, [rmax] * 3, period, approx_cell1_size, approx_cell2_size)
+    x1, y1, z1 = _sorted(c1, dm.mesh1)
+    x2, y2, z2 = _sorted(c2, dm.mesh2)
+    g = _geom(dm)
+    first, last = _range(dm, cell1_range)
+    n1 = len(x1)
+    out = np.zeros((n1, len(rbins)), dtype=np.int64)
+    lib().oracle_npairs_per_object_3d(ctypes.byref(g), _p(x1), _p(y1), _p(z1), _p(dm.mesh1.cell_id_indices, ctypes.c_int64),
+                                      ctypes.c_int64(n1),
+                                      _p(x2), _p(y2), _p(z2), _p(dm.mesh2.cell_id_indices, ctypes.c_int64),
+                                      _p(rbins), ctypes.c_int(len(rbins)),
+                                      ctypes.c_int64(first), ctypes.c_int64(last), _p(out, ctypes.c_int64))
+    unsort = np.empty(n1, dtype=np.int64)
+    unsort[dm.mesh1.idx_sorted] = np.arange(n1)
+    return out[unsort, :]
+
+
+def marked_npairs_xy_z(sample1, sample2, rp_bins, pi_bins, period=None, weights1=None, weights2=None,
+                       weight_func_id=0, approx_cell1_size=None, approx_cell2_size=None, cell1_range=None):
+    rp_bins = _f8(np.atleast_1d(rp_bins))
+    pi_bins = _f8(np.atleast_1d(pi_bins))
+    rp_max, pi_max = float(np.max(rp_bins)), float(np.max(pi_bins))
+    nw = NUM_WEIGHTS[int(weight_func_id)]
+    n1, n2 = np.shape(sample1)[0], np.shape(sample2)[0]
+    w1 = np.ones((n1, nw)) if weights1 is None else np.asarray(weights1, dtype=np.float64).reshape(n1, nw)
+    w2 = np.ones((n2, nw)) if weights2 is None else np.asarray(weights2, dtype=np.float64).reshape(n2, nw)
+    dm, c1, c2 = build_double_mesh_3d(sample1, sample2, [rp_max, rp_max, pi_max], period,
+                                      approx_cell1_size, approx_cell2_size)
+    x1, y1, z1 = _sorted(c1, dm.mesh1)
+    x2, y2, z2 = _sorted(c2, dm.mesh2)
+    w1s = _f8(w1[dm.mesh1.idx_sorted, :])
+    w2s = _f8(w2[dm.mesh2.idx_sorted, :])
+    g = _geom(dm)
+    first, last = _range(dm, cell1_range)
+    out = np.zeros((len(rp_bins), len(pi_bins)), dtype=np.float64)
+    lib().oracle_marked_npairs_xy_z(ctypes.byref(g), _p(x1), _p(y1), _p(z1), _p(dm.mesh1.cell_id_indices, ctypes.c_int64),
+                                    _p(x2), _p(y2), _p(z2), _p(dm.mesh2.cell_id_indices, ctypes.c_int64),
+                                    _p(w1s), _p(w2s), ctypes.c_int(nw), ctypes.c_int(int(weight_func_id)),
+                                    _p(rp_bins), ctypes.c_int(len(rp_bins)), _p(pi_bins), ctypes.c_int(len(pi_bins)),
+                                    ctypes.c_int64(first), ctypes.c_int64(last), _p(out))
+    return out
+
+
+def weighted_npairs_xy(sample1, sample2, sample2_mass, rp_bins, period=None, approx_cell1_size=None,
+                       approx_cell2_size=None, cell1_range=None):
+    sample1 = np.asarray(sample1, dtype=np.float64)
+    sample2 = np.asarray(sample2, dtype=np.float64)
+    rp_bins = _f8(np.atleast_1d(rp_bins))
+    rp_max = float(np.max(rp_bins))
+    c1 = [sample1[:, 0], sample1[:, 1]]
+    c2 = [sample2[:, 0], sample2[:, 1]]
+    if period is None:
+        c1, c2, per2 = _enclose(c1, c2, [3.0 * rp_max] * 2)       # weighted_npairs_xy.py:186-191
+        pbc = False
+    else:
+        per2 = _triple(period, 2)[:2]
+        pbc = True
+    a1 = [rp_max] * 2 if approx_cell1_size is None else _triple(approx_cell1_size, 2)
+    a2 = [rp_max] * 2 if approx_cell2_size is None else _triple(approx_cell2_size, 2)
+    dm = DoubleMesh(c1, c2, a1, a2, [rp_max] * 2, per2, pbc)
+    x1, y1 = _sorted(c1, dm.mesh1)
+    x2, y2 = _sorted(c2, dm.mesh2)
+    w2 = _f8(np.asarray(sample2_mass, dtype=np.float64)[dm.mesh2.idx_sorted])
+    g = _geom(dm)
+    first, last = _range(dm, cell1_range)
+    out = np.zeros(len(rp_bins), dtype=np.float64)
+    lib().oracle_weighted_npairs_xy(ctypes.byref(g), _p(x1), _p(y1), _p(dm.mesh1.cell_id_indices, ctypes.c_int64),
+                                    _p(x2), _p(y2), _p(w2), _p(dm.mesh2.cell_id_indices, ctypes.c_int64),
+                                    _p(rp_bins), ctypes.c_int(len(rp_bins)), ctypes.c_int64(first), ctypes.c_int64(last),
+                                    _p(out))
+    return out
 
 
 def brute_npairs_3d(sample1, sample2, rbins, period=None):

@@ -422,6 +422,178 @@ void oracle_mean_delta_sigma(const oracle_geom_t *g,
     free(rpsq);
 }
 
+/* ------------------------------------------------------------ the section-8(f) counters
+ *   npairs_projected      .../cpairs/npairs_projected_engine.pyx:113-189
+ *   npairs_per_object_3d  .../cpairs/npairs_per_object_3d_engine.pyx:118-213
+ *   marked_npairs_xy_z    .../marked_cpairs/marked_npairs_xy_z_engine.pyx:126-225
+ *   weighted_npairs_xy    /root/reference/halotools/mock_observables/surface_density/engines/weighted_npairs_xy_engine.pyx:95-175
+ * One 3-D loop nest serves the first three (the reference repeats it verbatim in each engine); `mode` picks the
+ * innermost statement.                                                                                        */
+typedef struct {
+    int mode;                 /* 0 projected, 1 per object, 2 marked (rp, pi) */
+    const double *e0; int n0; /* squared rbins / rp_bins */
+    const double *e1; int n1; /* squared pi_bins (mode 2) */
+    double pi_max_sq;         /* mode 0 */
+    const double *w1, *w2; int nw, wfunc;   /* mode 2: SORTED row-major weights */
+} f_inner_t;
+
+static void f_loop3(const oracle_geom_t *g,
+                    const double *x1, const double *y1, const double *z1, const int64_t *off1,
+                    const double *x2, const double *y2, const double *z2, const int64_t *off2,
+                    int64_t first_cell1, int64_t last_cell1, const f_inner_t *in,
+                    int64_t *icnt /* mode 0: [n0]; mode 1: (N1, n0) in sorted order */, double *fcnt /* mode 2: [n0*n1] */)
+{
+    const int ny1 = g->ndivs1[1], nz1 = g->ndivs1[2];
+    const int ny2 = g->ndivs2[1], nz2 = g->ndivs2[2];
+    const int perx = g->ndivs2[0] / g->ndivs1[0], pery = ny2 / ny1, perz = nz2 / nz1;
+    const int mw = max_window(g);
+    nbr_t *wx = (nbr_t *)malloc(sizeof(nbr_t) * mw * 3), *wy = wx + mw, *wz = wy + mw;
+    for (int64_t c1 = first_cell1; c1 < last_cell1; ++c1) {
+        const int64_t a = off1[c1], b = off1[c1 + 1];
+        if (b <= a) continue;
+        const int ix1 = (int)(c1 / ((int64_t)ny1 * nz1));
+        const int iy1 = (int)((c1 - (int64_t)ix1 * ny1 * nz1) / nz1);
+        const int iz1 = (int)(c1 - (int64_t)ix1 * ny1 * nz1 - (int64_t)iy1 * nz1);
+        const int nx = fill_window(ix1, perx, g->cover[0], g->ndivs2[0], g->period[0], g->pbc, wx);
+        const int ny = fill_window(iy1, pery, g->cover[1], ny2, g->period[1], g->pbc, wy);
+        const int nz = fill_window(iz1, perz, g->cover[2], nz2, g->period[2], g->pbc, wz);
+        for (int ax = 0; ax < nx; ++ax)
+        for (int ay = 0; ay < ny; ++ay)
+        for (int az = 0; az < nz; ++az) {
+            const int64_t c2 = (int64_t)wx[ax].idx * ny2 * nz2 + (int64_t)wy[ay].idx * nz2 + wz[az].idx;
+            const int64_t p = off2[c2], q = off2[c2 + 1];
+            if (q <= p) continue;
+            const double sx = wx[ax].shift, sy = wy[ay].shift, sz = wz[az].shift;
+            for (int64_t i = a; i < b; ++i) {
+                const double xt = x1[i] - sx, yt = y1[i] - sy, zt = z1[i] - sz;
+                for (int64_t j = p; j < q; ++j) {
+                    const double dx = xt - x2[j], dy = yt - y2[j], dz = zt - z2[j];
+                    if (in->mode == 0) {
+                        /* npairs_projected_engine.pyx:180-189 */
+                        const double dxy_sq = dx * dx + dy * dy;
+                        const double dz_sq = dz * dz;
+                        int k = in->n0 - 1;
+                        while (dxy_sq <= in->e0[k]) {
+                            if (dz_sq <= in->pi_max_sq) icnt[k] += 1;
+                            if (--k < 0) break;
+                        }
+                    } else if (in->mode == 1) {
+                        /* npairs_per_object_3d_engine.pyx:193-207 (inner counts folded into the row at once) */
+                        const double dsq = dx * dx + dy * dy + dz * dz;
+                        int k = in->n0 - 1;
+                        while (dsq <= in->e0[k]) { icnt[i * in->n0 + k] += 1; if (--k < 0) break; }
+                    } else {
+                        /* marked_npairs_xy_z_engine.pyx:211-225 */
+                        const double dxy_sq = dx * dx + dy * dy;
+                        const double dz_sq = dz * dz;
+                        const double w = pair_weight(in->wfunc, in->w1 + i * in->nw, in->w2 + j * in->nw);
+                        int k = in->n0 - 1;
+                        while (dxy_sq <= in->e0[k]) {
+                            int gq = in->n1 - 1;
+                            while (dz_sq <= in->e1[gq]) { fcnt[k * in->n1 + gq] += w; if (--gq < 0) break; }
+                            if (--k < 0) break;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    free(wx);
+}
+
+static double *squares(const double *v, int n)
+{
+    double *s = (double *)malloc(sizeof(double) * (n > 0 ? n : 1));
+    for (int k = 0; k < n; ++k) s[k] = v[k] * v[k];
+    return s;
+}
+
+void oracle_npairs_projected(const oracle_geom_t *g,
+                             const double *x1, const double *y1, const double *z1, const int64_t *off1,
+                             const double *x2, const double *y2, const double *z2, const int64_t *off2,
+                             const double *rp_bins, int nrp, double pi_max,
+                             int64_t first_cell1, int64_t last_cell1, int64_t *counts_out)
+{
+    f_inner_t in; memset(&in, 0, sizeof(in));
+    double *e0 = squares(rp_bins, nrp);
+    in.mode = 0; in.e0 = e0; in.n0 = nrp; in.pi_max_sq = pi_max * pi_max;
+    memset(counts_out, 0, sizeof(int64_t) * nrp);
+    f_loop3(g, x1, y1, z1, off1, x2, y2, z2, off2, first_cell1, last_cell1, &in, counts_out, NULL);
+    free(e0);
+}
+
+/* counts_out: (n1, nb) row-major in SORTED sample1 order (the wrapper un-sorts, engine :209-213) */
+void oracle_npairs_per_object_3d(const oracle_geom_t *g,
+                                 const double *x1, const double *y1, const double *z1, const int64_t *off1, int64_t n1,
+                                 const double *x2, const double *y2, const double *z2, const int64_t *off2,
+                                 const double *rbins, int nb,
+                                 int64_t first_cell1, int64_t last_cell1, int64_t *counts_out)
+{
+    f_inner_t in; memset(&in, 0, sizeof(in));
+    double *e0 = squares(rbins, nb);
+    in.mode = 1; in.e0 = e0; in.n0 = nb;
+    memset(counts_out, 0, sizeof(int64_t) * (size_t)n1 * nb);
+    f_loop3(g, x1, y1, z1, off1, x2, y2, z2, off2, first_cell1, last_cell1, &in, counts_out, NULL);
+    free(e0);
+}
+
+void oracle_marked_npairs_xy_z(const oracle_geom_t *g,
+                               const double *x1, const double *y1, const double *z1, const int64_t *off1,
+                               const double *x2, const double *y2, const double *z2, const int64_t *off2,
+                               const double *w1, const double *w2, int nw, int wfunc_id,
+                               const double *rp_bins, int nrp, const double *pi_bins, int npi,
+                               int64_t first_cell1, int64_t last_cell1, double *counts_out)
+{
+    f_inner_t in; memset(&in, 0, sizeof(in));
+    double *e0 = squares(rp_bins, nrp), *e1 = squares(pi_bins, npi);
+    in.mode = 2; in.e0 = e0; in.n0 = nrp; in.e1 = e1; in.n1 = npi;
+    in.w1 = w1; in.w2 = w2; in.nw = nw; in.wfunc = wfunc_id;
+    for (int k = 0; k < nrp * npi; ++k) counts_out[k] = 0.0;
+    f_loop3(g, x1, y1, z1, off1, x2, y2, z2, off2, first_cell1, last_cell1, &in, NULL, counts_out);
+    free(e0); free(e1);
+}
+
+/* 2-D mesh (cell id = ix*ny + iy), weighted_npairs_xy_engine.pyx:95-175 */
+void oracle_weighted_npairs_xy(const oracle_geom_t *g,
+                               const double *x1, const double *y1, const int64_t *off1,
+                               const double *x2, const double *y2, const double *w2, const int64_t *off2,
+                               const double *rp_bins, int nrp, int64_t first_cell1, int64_t last_cell1,
+                               double *counts_out)
+{
+    double *rpsq = squares(rp_bins, nrp);
+    const int ny1 = g->ndivs1[1], ny2 = g->ndivs2[1];
+    const int perx = g->ndivs2[0] / g->ndivs1[0], pery = ny2 / ny1;
+    const int mw = max_window(g);
+    nbr_t *wx = (nbr_t *)malloc(sizeof(nbr_t) * mw * 2), *wy = wx + mw;
+    for (int k = 0; k < nrp; ++k) counts_out[k] = 0.0;
+    for (int64_t c1 = first_cell1; c1 < last_cell1; ++c1) {
+        const int64_t a = off1[c1], b = off1[c1 + 1];
+        if (b <= a) continue;
+        const int ix1 = (int)(c1 / ny1);
+        const int iy1 = (int)(c1 - (int64_t)ix1 * ny1);
+        const int nx = fill_window(ix1, perx, g->cover[0], g->ndivs2[0], g->period[0], g->pbc, wx);
+        const int ny = fill_window(iy1, pery, g->cover[1], ny2, g->period[1], g->pbc, wy);
+        for (int ax = 0; ax < nx; ++ax)
+        for (int ay = 0; ay < ny; ++ay) {
+            const int64_t c2 = (int64_t)wx[ax].idx * ny2 + wy[ay].idx;
+            const int64_t p = off2[c2], q = off2[c2 + 1];
+            if (q <= p) continue;
+            const double sx = wx[ax].shift, sy = wy[ay].shift;
+            for (int64_t i = a; i < b; ++i) {
+                const double xt = x1[i] - sx, yt = y1[i] - sy;
+                for (int64_t j = p; j < q; ++j) {
+                    const double dx = xt - x2[j], dy = yt - y2[j];
+                    const double dxy_sq = dx * dx + dy * dy;
+                    const double w2tmp = w2[j];
+                    int k = nrp - 1;
+                    while (dxy_sq <= rpsq[k]) { counts_out[k] += w2tmp; if (--k < 0) break; }
+                }
+            }
+        }
+    }
+    free(wx); free(rpsq);
+}
+
 /* ------------------------------------------------------------ brute force O(N^2)
  * restating pair_counters/pairs.py:17-84 (npairs): per-pair minimum-image distance,
  * used by the reference's own tests as ground truth on small inputs.            */

@@ -157,6 +157,41 @@ def _cases():
                                       dict(marks1=m1, period=1.0, normalize_by="number_counts"))
     C["marked_tpcf_cross"] = ("marked_tpcf", (s1, rb2),
                               dict(sample2=s2, marks1=m1, marks2=m2, period=1.0, seed=43, iterations=2))
+    # ---- npairs_projected, npairs_per_object_3d, marked_npairs_xy_z, weighted_npairs_xy
+    # (fixture shapes: test_pair_counters/test_npairs_projected.py, test_npairs_per_object_3d.py,
+    # test_marked_npairs_xy_z.py, surface_density/tests/test_weighted_npairs_xy.py)
+    C["proj_periodic"] = ("npairs_projected", (s1, s2, rp, 0.2), dict(period=1.0))
+    C["proj_nonperiodic"] = ("npairs_projected", (s1, s2, rp, 0.2), dict(period=None))
+    C["proj_auto_logbins"] = ("npairs_projected", (s5, "same", np.logspace(-1, np.log10(20), 15), 40.0),
+                              dict(period=250.0))
+    C["proj_noncubic"] = ("npairs_projected", (s1 * scale, s2 * scale, rp, 0.25), dict(period=[1.0, 2.0, 3.0]))
+    C["proj_cellsizes"] = ("npairs_projected", (s1, s2, rp, 0.1),
+                           dict(period=1.0, approx_cell1_size=[0.2, 0.2, 0.2], approx_cell2_size=[0.15, 0.15, 0.15]))
+    C["perobj_periodic"] = ("npairs_per_object_3d", (s1, s2, rb), dict(period=1.0))
+    C["perobj_nonperiodic"] = ("npairs_per_object_3d", (s1, s2, rb), dict(period=None))
+    C["perobj_auto_logbins"] = ("npairs_per_object_3d", (s5, "same", np.logspace(-1, np.log10(20), 15)),
+                                dict(period=250.0))
+    C["perobj_clustered"] = ("npairs_per_object_3d", (cl, pts(47, 6000, 250.0), np.logspace(-1, np.log10(20), 15)),
+                             dict(period=250.0))
+    C["perobj_cellsizes"] = ("npairs_per_object_3d", (s1, s2, np.array([0.01, 0.05, 0.1])),
+                             dict(period=1.0, approx_cell1_size=0.1, approx_cell2_size=[0.05, 0.1, 0.3]))
+    for wid in range(1, 16):
+        C["mxyz_id%02d" % wid] = ("marked_npairs_xy_z", (s1, s2, rp, pi),
+                                  dict(period=1.0, weights1=weights(50 + wid, 1000, wid),
+                                       weights2=weights(80 + wid, 1000, wid), weight_func_id=wid))
+    C["mxyz_nonperiodic"] = ("marked_npairs_xy_z", (s1, s2, rp, pi),
+                             dict(period=None, weights1=weights(51, 1000, 1), weights2=weights(81, 1000, 1),
+                                  weight_func_id=1))
+    C["mxyz_auto_many_pi"] = ("marked_npairs_xy_z", (s5, "same", np.logspace(-1, np.log10(20), 10),
+                                                     np.linspace(0.0, 40.0, 21)),
+                              dict(period=250.0, weights1=weights(90, 5000, 1), weights2="same", weight_func_id=1))
+    C["mxyz_default_weights"] = ("marked_npairs_xy_z", (s1, s2, rp, pi), dict(period=1.0, weight_func_id=2))
+    g2a, g2b = pts(43, 1500, 450.0, 2), pts(44, 20000, 450.0, 2)
+    mass2 = np.random.RandomState(48).uniform(0.0, 1.0, 20000)
+    C["wxy_periodic"] = ("weighted_npairs_xy", (g2a, g2b, mass2, np.logspace(-1, 1.5, 15)), dict(period=[450.0, 450.0]))
+    C["wxy_nonperiodic"] = ("weighted_npairs_xy", (g2a, g2b, mass2, np.logspace(-1, 1.5, 15)), dict(period=None))
+    C["wxy_scalar_period_cellsizes"] = ("weighted_npairs_xy", (g2a, g2b, mass2, np.logspace(-0.5, 1.3, 9)),
+                                        dict(period=450.0, approx_cell1_size=30.0, approx_cell2_size=[15.0, 10.0]))
     return C
 
 

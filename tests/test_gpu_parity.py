@@ -12,7 +12,7 @@ from tests.golden import cases
 
 pytestmark = pytest.mark.gpu
 
-INT_FUNCS = ("npairs_3d", "npairs_xy_z", "npairs_s_mu")
+INT_FUNCS = ("npairs_3d", "npairs_xy_z", "npairs_s_mu", "npairs_projected", "npairs_per_object_3d")
 ALL = cases.names()
 
 
@@ -33,7 +33,7 @@ def compare(fn, got, want):
         if fn in INT_FUNCS:
             assert g.dtype == np.int64
             assert np.array_equal(g, w), (g, w)
-        elif fn == "marked_npairs_3d":
+        elif fn in ("marked_npairs_3d", "marked_npairs_xy_z", "weighted_npairs_xy"):
             # float sums, order differs from the reference's serial loop: 1e-12 relative (north_star)
             assert np.allclose(g, w, rtol=1e-12, atol=0), (g, w)
         elif fn == "mean_delta_sigma":
@@ -380,7 +380,7 @@ def test_fast_marked_not_taken_for_other_marks(golden):
     w = rng.uniform(0, 1, (3000, 2))
     rb = np.logspace(-1, 1, 7)
     got = hb.marked_npairs_3d(s, s, rb, 5, period=60.0, weights1=w, weights2=w)
-    assert _lib.last_stats["path"] == 0
+    assert _lib.last_stats["path"] == 3, "general marks belong to the weighted BinQ kernel"
     want = oracle.marked_npairs_3d(s, s, rb, 5, period=60.0, weights1=w, weights2=w, num_threads=4)
     assert np.allclose(got, want, rtol=1e-12, atol=0)
 
@@ -592,3 +592,94 @@ def test_cell_resolved_delta_sigma_vs_oracle(case):
     want = oracle.mean_delta_sigma(g2, p2, 0.7, rp, per_object=True, num_threads=8, **kw)
     scale = np.max(np.abs(want))
     assert np.allclose(got, want, rtol=1e-10, atol=1e-12 * scale), np.max(np.abs(got - want)) / scale
+
+
+# ---------------------------------------------------------------- SURVEY 8(f) rank 2 counters (BinQ modes 1 and 2)
+def test_npairs_projected_vs_oracle_and_xy_z_column():
+    rng = np.random.RandomState(31)
+    L = 150.0
+    s1 = _dup_points(rng, 40000, L)
+    s2 = np.vstack([s1[:6000], _dup_points(rng, 30000, L)])
+    rp = np.logspace(-1.5, np.log10(14.0), 12)
+    for a, b in ((s1, s1), (s1, s2)):
+        got = hb.npairs_projected(a, b, rp, 35.0, period=L)
+        assert _lib.last_stats["path"] == 1, "one pi edge: the fast (rp, pi) kernel"
+        want = oracle.npairs_projected(a, b, rp, 35.0, period=L)
+        assert got.dtype == np.int64 and np.array_equal(got, want), (got - want)
+    with pytest.raises(ValueError, match="pi_max"):
+        hb.npairs_projected(s1, s1, rp, 60.0, period=L)
+
+
+def test_npairs_per_object_3d_vs_oracle_rows_in_input_order():
+    rng = np.random.RandomState(32)
+    L = 100.0
+    s1 = _dup_points(rng, 30000, L)
+    s2 = np.vstack([s1[:4000], _dup_points(rng, 26000, L)])
+    rbins = np.concatenate([[0.0], np.logspace(-2, np.log10(9.0), 17)])
+    for a, b in ((s1, s1), (s1, s2)):
+        got = hb.npairs_per_object_3d(a, b, rbins, period=L)
+        want = oracle.npairs_per_object_3d(a, b, rbins, period=L)
+        assert got.dtype == np.int64 and got.shape == (len(a), len(rbins)) and np.array_equal(got, want)
+        # column sums are npairs_3d
+        assert np.array_equal(got.sum(axis=0), hb.npairs_3d(a, b, rbins, period=L))
+    sub = rng.permutation(len(s1))[:500]
+    assert np.array_equal(hb.npairs_per_object_3d(s1[sub], s2, rbins, period=L),
+                          hb.npairs_per_object_3d(s1, s2, rbins, period=L)[sub])
+    nonper = hb.npairs_per_object_3d(s1[:3000], s2[:5000], rbins, period=None)
+    assert np.array_equal(nonper, oracle.npairs_per_object_3d(s1[:3000], s2[:5000], rbins, period=None))
+
+
+@pytest.mark.parametrize("wid", [1, 5, 9, 13])
+def test_marked_npairs_xy_z_vs_oracle(wid):
+    rng = np.random.RandomState(33)
+    L = 120.0
+    s1 = _dup_points(rng, 25000, L)
+    s2 = np.vstack([s1[:3000], _dup_points(rng, 20000, L)])
+    w1, w2 = cases.weights(1, len(s1), wid), cases.weights(2, len(s2), wid)
+    rp = np.logspace(-1, np.log10(10.0), 9)
+    pi = np.linspace(0.0, 24.0, 13)
+    for a, b, wa, wb in ((s1, s1, w1, w1), (s1, s2, w1, w2)):
+        got = hb.marked_npairs_xy_z(a, b, rp, pi, period=L, weights1=wa, weights2=wb, weight_func_id=wid)
+        want = oracle.marked_npairs_xy_z(a, b, rp, pi, period=L, weights1=wa, weights2=wb, weight_func_id=wid)
+        assert got.shape == want.shape and np.allclose(got, want, rtol=1e-12, atol=0), np.max(np.abs(got / want - 1))
+    # unit weights, product marks: the sums are the integer counts
+    ones = np.ones(len(s1))
+    unit = hb.marked_npairs_xy_z(s1, s1, rp, pi, period=L, weights1=ones, weights2=ones, weight_func_id=1)
+    assert np.array_equal(unit, hb.npairs_xy_z(s1, s1, rp, pi, period=L).astype(float))
+    with pytest.raises(hb.HalotoolsError):
+        hb.marked_npairs_xy_z(s1, s1, rp, pi, period=L)            # the reference's default id 0 is not recognised
+
+
+def test_marked_npairs_3d_general_marks_take_binq_and_match_oracle():
+    rng = np.random.RandomState(34)
+    L = 100.0
+    s1 = _dup_points(rng, 25000, L)
+    s2 = _dup_points(rng, 20000, L)
+    rb = np.logspace(-1, 1, 12)
+    for wid in (2, 6, 12, 16):
+        w1, w2 = cases.weights(3, len(s1), wid), cases.weights(4, len(s2), wid)
+        got = hb.marked_npairs_3d(s1, s2, rb, wid, period=L, weights1=w1, weights2=w2)
+        assert _lib.last_stats["path"] == 3
+        want = oracle.marked_npairs_3d(s1, s2, rb, wid, period=L, weights1=w1, weights2=w2, num_threads=4)
+        assert np.allclose(got, want, rtol=1e-12, atol=0), (wid, np.max(np.abs(got / want - 1)))
+        gen = _generic(lambda: hb.marked_npairs_3d(s1, s2, rb, wid, period=L, weights1=w1, weights2=w2))
+        assert np.allclose(gen, want, rtol=1e-12, atol=0)
+
+
+def test_weighted_npairs_xy_vs_oracle():
+    rng = np.random.RandomState(35)
+    L = 300.0
+    g = rng.uniform(0, L, (20000, 2))
+    p = np.vstack([g[:2000], rng.uniform(0, L, (150000, 2))])
+    m = rng.uniform(0.0, 2.0, len(p))
+    rp = np.logspace(-1, np.log10(25.0), 14)
+    # float masses at a size where the REFERENCE's serial running sum (sqrt(n) eps for n terms) stays below 1e-12;
+    # at the full size only integer masses (every partial sum exact in f64) are compared, and exactly
+    got = hb.weighted_npairs_xy(g[:5000], p[:40000], m[:40000], rp, period=L)
+    assert _lib.last_stats["path"] == 3
+    want = oracle.weighted_npairs_xy(g[:5000], p[:40000], m[:40000], rp, period=L)
+    assert np.allclose(got, want, rtol=1e-12, atol=0), np.max(np.abs(got / want - 1))
+    ints = rng.randint(1, 5, len(p)).astype(float)                  # integer masses: exact
+    assert np.array_equal(hb.weighted_npairs_xy(g, p, ints, rp, period=L), oracle.weighted_npairs_xy(g, p, ints, rp, period=L))
+    nonper = hb.weighted_npairs_xy(g[:3000], p[:30000], m[:30000], rp, period=None)
+    assert np.allclose(nonper, oracle.weighted_npairs_xy(g[:3000], p[:30000], m[:30000], rp, period=None), rtol=1e-12)

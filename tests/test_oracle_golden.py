@@ -7,7 +7,8 @@ import pytest
 from oracle import oracle, ref_engines
 from tests.golden import cases
 
-ENGINE_FUNCS = ("npairs_3d", "npairs_xy_z", "npairs_s_mu", "marked_npairs_3d", "mean_delta_sigma")
+ENGINE_FUNCS = ("npairs_3d", "npairs_xy_z", "npairs_s_mu", "marked_npairs_3d", "mean_delta_sigma",
+                "npairs_projected", "npairs_per_object_3d", "marked_npairs_xy_z", "weighted_npairs_xy")
 ENGINE_CASES = [n for n in cases.names() if cases._cases()[n][0] in ENGINE_FUNCS and n != "n3d_c1_full"]
 
 
@@ -25,10 +26,10 @@ def test_oracle_matches_reference_golden(name, golden):
     assert len(got) == len(want)
     for g, w in zip(got, want):
         assert g.shape == w.shape
-        if fn in ("npairs_3d", "npairs_xy_z", "npairs_s_mu"):
+        if fn in ("npairs_3d", "npairs_xy_z", "npairs_s_mu", "npairs_projected", "npairs_per_object_3d"):
             assert g.dtype == np.int64
             assert np.array_equal(g, w)
-        elif fn == "marked_npairs_3d":
+        elif fn in ("marked_npairs_3d", "marked_npairs_xy_z", "weighted_npairs_xy"):
             assert np.allclose(g, w, rtol=1e-12, atol=0)
         else:
             # Delta Sigma is a cancelling difference: abs + rel tolerance
