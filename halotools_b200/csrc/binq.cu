@@ -136,19 +136,22 @@ struct BinQ {
     // edge inside the value's table cell is finished by a loop (rare).
     __device__ __forceinline__ int locate(int axis, int first, int n, unsigned long long bits)
     {
-        const long long t = (long long)(bits >> P.S[axis]) - (long long)P.kmin[axis];
-        const int tt = (int)max(0ll, min(t, (long long)P.T[axis] - 1ll));
+        // key = bits >> S with S >= 44: a 32-bit shift of the high word
+        const int t = (int)((unsigned)(bits >> 32) >> (P.S[axis] - 32)) - (int)P.kmin[axis];
+        const int T = P.T[axis];
         unsigned v;
-        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(lut_s[axis] + (uint32_t)tt));
-        int i = t < 0 ? 0 : (int)v;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(lut_s[axis] + (uint32_t)min(max(t, 0), T - 1)));
+        int i = t < 0 ? 0 : (t >= T ? n : (int)v);        // a negative value (NaN with the sign bit) has a huge key: n
         const uint32_t eb = e_s + 8u * (uint32_t)first;
-        const bool c1 = i < n && bq_lds_u64(eb + 8u * (uint32_t)min(i, n - 1)) < bits;
+        const bool c1 = (i < n) & (bq_lds_u64(eb + 8u * (uint32_t)min(i, n - 1)) < bits);
         i += c1 ? 1 : 0;
-        if (c1 && i < n && bq_lds_u64(eb + 8u * (uint32_t)min(i, n - 1)) < bits) {
-            ++i;
-            while (i < n && bq_lds_u64(eb + 8u * (uint32_t)i) < bits) ++i;
+        if (c1) {
+            if (i < n && bq_lds_u64(eb + 8u * (uint32_t)i) < bits) {
+                ++i;
+                while (i < n && bq_lds_u64(eb + 8u * (uint32_t)i) < bits) ++i;
+            }
         }
-        return t >= (long long)P.T[axis] ? n : i;
+        return i;
     }
     // one replayed pair: recompute, locate; returns the histogram cell or -1
     __device__ __forceinline__ int replay_one(bool act, double xs, double ys, double zs, double xj, double yj, double zj)

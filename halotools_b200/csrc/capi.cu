@@ -365,6 +365,39 @@ extern "C" int htb_host_minmax(const double *base, int64_t n, int64_t stride, in
     HTB_GUARD_END
 }
 
+// the same for a DEVICE-resident matrix (torch CUDA tensors handed to the front-ends): one HBM-bound pass on the GPU
+extern "C" int htb_device_minmax(const double *base_dev, int64_t n, int64_t stride, int32_t cols, double *min_out, double *max_out)
+{
+    HTB_GUARD_BEGIN
+    if (!base_dev || cols < 1 || cols > 3 || !min_out || !max_out || stride < cols) { htb_set_error("htb_device_minmax: bad arguments"); return 1; }
+    for (int c = 0; c < cols; ++c) { min_out[c] = INFINITY; max_out[c] = -INFINITY; }
+    if (n <= 0) return 0;
+    cudaStream_t st;
+    if (get_stream(&st)) return 1;
+    int dev = 0, sms = 0;
+    HTB_CUDA(cudaGetDevice(&dev));
+    HTB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int blocks = (int)std::min<int64_t>((int64_t)sms * 8, (n + 1023) / 1024);
+    double *part = nullptr;
+    HTB_CUDA(cudaMallocAsync((void **)&part, sizeof(double) * 7 * (size_t)blocks, st));
+    if (htb_device_minmax_launch(st, base_dev, n, stride, cols, part, blocks)) return 1;
+    std::vector<double> h((size_t)blocks * 7);
+    HTB_CUDA(cudaMemcpyAsync(h.data(), part, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, st));
+    HTB_CUDA(cudaFreeAsync(part, st));
+    HTB_CUDA(cudaStreamSynchronize(st));
+    bool anynan = false;
+    for (int b = 0; b < blocks; ++b) {
+        anynan |= h[(size_t)b * 7 + 6] != 0.0;
+        for (int c = 0; c < cols; ++c) {
+            if (h[(size_t)b * 7 + c] < min_out[c]) min_out[c] = h[(size_t)b * 7 + c];
+            if (h[(size_t)b * 7 + 3 + c] > max_out[c]) max_out[c] = h[(size_t)b * 7 + 3 + c];
+        }
+    }
+    if (anynan) for (int c = 0; c < cols; ++c) { min_out[c] = NAN; max_out[c] = NAN; }
+    return 0;
+    HTB_GUARD_END
+}
+
 // ------------------------------------------------------------------ one engine call
 struct Call {
     cudaStream_t st = nullptr;
@@ -760,7 +793,7 @@ static int binq_prepare(Call &c, const double *e0, int n0, const double *e1, int
     // Lookup tables: key = bits >> S keeps the exponent and up to 8 mantissa bits; lut[key - kmin] is the first edge
     // whose key is >= key (every earlier edge is certainly below the value); the kernel finishes with exact compares.
     // kmin is the key of the smallest non-zero edge (values below it start at edge 0); S grows until the table is
-    // at most 1024 entries.
+    // at most 2048 entries.
     BinQParams bp{};
     std::vector<unsigned char> lut[2];
     for (int a = 0; a < 2; ++a) {
@@ -769,7 +802,7 @@ static int binq_prepare(Call &c, const double *e0, int n0, const double *e1, int
         int z = 0;
         while (z < n - 1 && b[z] == 0ULL) ++z;
         int S = 44;
-        while (((b[n - 1] >> S) - (b[z] >> S) + 1ULL) > 1024ULL) ++S;
+        while (((b[n - 1] >> S) - (b[z] >> S) + 1ULL) > 2048ULL) ++S;
         const unsigned long long kmin = b[z] >> S;
         const int T = (int)((b[n - 1] >> S) - kmin + 1ULL);
         lut[a].assign(((size_t)T + 7) & ~(size_t)7, (unsigned char)n);

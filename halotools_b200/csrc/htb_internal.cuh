@@ -78,6 +78,9 @@ int htb_ref_cell_ids(cudaStream_t st, int dim, const double *const *coords_dev, 
 int htb_ref_cell_counts(cudaStream_t st, const SortedSample &s, uint32_t *counts_dev /* [prod nd] zeroed */,
                         int *launches);
 
+int htb_device_minmax_launch(cudaStream_t st, const double *base_dev, int64_t n, int64_t stride, int cols,
+                             double *part_dev /* [blocks][7] */, int blocks);
+
 // ---- workspace (capi.cu)
 struct Workspace {
     cudaStream_t st = nullptr;

@@ -353,3 +353,69 @@ int htb_ref_cell_counts(cudaStream_t st, const SortedSample &s, uint32_t *counts
     HTB_CUDA(cudaGetLastError());
     return 0;
 }
+
+// ------------------------------------------------------------------ column extrema of a device-resident sample
+// The front-ends' bounds check (mock_observables_helpers.py:25-71) for samples that already live on the GPU: one
+// streaming pass over the (n, cols) rows - HBM bound, 8 * cols bytes per point.  part[b] = {min[3], max[3], nan}.
+#define HTB_MM_BLOCK 256
+__global__ void __launch_bounds__(HTB_MM_BLOCK)
+k_minmax(const double *__restrict__ base, int64_t n, int64_t stride, int cols, double *__restrict__ part)
+{
+    double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    bool bad = false;
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += 4 * step) {
+        double v[4][3];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t rr = r + u * step;
+            ok[u] = rr < n;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[u][c] = (ok[u] && c < cols) ? base[rr * stride + c] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                if (ok[u] && c < cols) {
+                    lo[c] = fmin(lo[c], v[u][c]);
+                    hi[c] = fmax(hi[c], v[u][c]);
+                    bad |= (v[u][c] != v[u][c]);
+                }
+            }
+    }
+    __shared__ double s[HTB_MM_BLOCK / 32][7];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[c] = fmin(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+            hi[c] = fmax(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+        }
+    }
+    const bool anybad = __any_sync(0xffffffffu, bad);
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+        for (int c = 0; c < 3; ++c) { s[w][c] = lo[c]; s[w][3 + c] = hi[c]; }
+        s[w][6] = anybad ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double out[7];
+        for (int k = 0; k < 7; ++k) out[k] = s[0][k];
+        for (int i = 1; i < HTB_MM_BLOCK / 32; ++i) {
+            for (int c = 0; c < 3; ++c) { out[c] = fmin(out[c], s[i][c]); out[3 + c] = fmax(out[3 + c], s[i][3 + c]); }
+            out[6] = fmax(out[6], s[i][6]);
+        }
+        for (int k = 0; k < 7; ++k) part[(size_t)blockIdx.x * 7 + k] = out[k];
+    }
+}
+
+int htb_device_minmax_launch(cudaStream_t st, const double *base_dev, int64_t n, int64_t stride, int cols,
+                             double *part_dev, int blocks)
+{
+    k_minmax<<<blocks, HTB_MM_BLOCK, 0, st>>>(base_dev, n, stride, cols, part_dev);
+    HTB_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -12,7 +12,7 @@ every call counts all cells (N independent replicas).
 """
 import numpy as np
 
-_state = {"enabled": False, "group": None, "balanced": False}
+_state = {"enabled": False, "group": None, "balanced": False, "local": 0}
 
 
 def enable(group=None, balanced=None):
@@ -87,15 +87,50 @@ def cell1_range(ncells, work=None):
     return split_cells(ncells, world, work)[rank]
 
 
+class local_counts(object):
+    """Context manager for statistics that make several engine calls (tpcf: DD, DR, RR): inside it the pair counters
+    return this rank's partial counts (no all-reduce per call); on exit the arrays registered with ``add`` are summed
+    over the ranks IN PLACE with one all-reduce.  Sums commute with the np.diff the callers apply, and integer sums
+    are exact, so the results are those of one all-reduce per call."""
+
+    def __init__(self):
+        self.pending = []
+
+    def add(self, array):
+        self.pending.append(array)
+        return array
+
+    def __enter__(self):
+        _state["local"] += 1
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        _state["local"] -= 1
+        if exc_type is None and self.pending and _state["local"] == 0:
+            arrays, seen = [], set()
+            for a in self.pending:
+                if id(a) not in seen:
+                    seen.add(id(a))
+                    arrays.append(a)
+            for dtype in sorted(set(a.dtype for a in arrays), key=str):      # the same order on every rank
+                group = [a for a in arrays if a.dtype == dtype]
+                flat = allreduce_sum(np.concatenate([a.ravel() for a in group]))
+                pos = 0
+                for a in group:
+                    a[...] = flat[pos:pos + a.size].reshape(a.shape)
+                    pos += a.size
+        return False
+
+
 def allreduce_sum(array):
     """Sum a small numpy array over the ranks (NCCL when the GPUs are there, gloo otherwise)."""
     rank, world = _rank_world()
-    if world <= 1:
+    if world <= 1 or _state["local"] > 0:
         return array
     import torch
     import torch.distributed as dist
     backend = dist.get_backend(_state["group"])
-    t = torch.from_numpy(np.ascontiguousarray(array))
+    t = torch.from_numpy(np.array(array, copy=True, order="C"))       # never reduce into the caller's array
     if backend == "nccl":
         t = t.cuda()
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=_state["group"])

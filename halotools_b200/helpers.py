@@ -102,6 +102,15 @@ def _column_extrema(x, y, z):
         if (base is not None and base.dim() == 2 and base.shape[1] == 3 and y._base is base and z._base is base
                 and x.data_ptr() == base.data_ptr() and y.data_ptr() == base[:, 1].data_ptr()
                 and z.data_ptr() == base[:, 2].data_ptr()):
+            if base.dtype == torch.float64 and base.is_contiguous():
+                # one streaming pass of the library's own kernel (HBM bound; torch's strided reductions are not)
+                import ctypes
+                from . import _lib
+                lo = (ctypes.c_double * 3)()
+                hi = (ctypes.c_double * 3)()
+                _lib.check(_lib.require_gpu().htb_device_minmax(ctypes.c_void_p(int(base.data_ptr())), ctypes.c_int64(int(base.shape[0])),
+                                                                ctypes.c_int64(3), ctypes.c_int32(3), lo, hi))
+                return [(lo[k], hi[k]) for k in range(3)]
             lo, hi = torch.aminmax(base, dim=0)
             ext = torch.stack([lo, hi]).cpu().numpy()
             return [(float(ext[0, k]), float(ext[1, k])) for k in range(3)]

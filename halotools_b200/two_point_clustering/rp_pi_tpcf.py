@@ -9,6 +9,7 @@ from ..helpers import (enforce_sample_has_correct_shape, get_line_of_sight_bins_
 from ..pair_counters import npairs_xy_z
 from ..pair_counters.mesh_helpers import _enforce_maximum_search_length
 from .. import _lib
+from .. import distributed as _dist
 from . import _driver
 from .clustering_helpers import process_optional_input_sample2, verify_tpcf_estimator
 from .tpcf_estimators import _TP_estimator_requirements
@@ -33,7 +34,7 @@ def rp_pi_tpcf(sample1, rp_bins, pi_bins, sample2=None, randoms=None, period=Non
     def count(a, b, cell_a, cell_b):
         c = npairs_xy_z(a, b, rp_bins, pi_bins, period=period, num_threads=num_threads,
                         approx_cell1_size=cell_a, approx_cell2_size=cell_b)
-        return np.diff(np.diff(c, axis=0), axis=1)
+        return partial.add(np.diff(np.diff(c, axis=0), axis=1))
 
     def analytic():
         # annular cylinders of a periodic box at the mean density (rp_pi_tpcf.py:443-467)
@@ -46,8 +47,10 @@ def rp_pi_tpcf(sample1, rp_bins, pi_bins, sample2=None, randoms=None, period=Non
         D2R = n2 * (dv * (n2 / volume))
         return D1R, D2R, dv * (nr ** 2 / volume)
 
-    # the engine's upload cache: every sample crosses PCIe once for all the counts of this call
-    with _lib.upload_cache():
+    # the engine's upload cache: every sample crosses PCIe once for all the counts of this call; multi-GPU: the
+    # ranks' partial counts of ALL these calls are combined by one all-reduce at the end of the block
+    partial = _dist.local_counts()
+    with _lib.upload_cache(), partial:
         D1D1, D1D2, D2D2 = _driver.data_counts(count, sample1, sample2, same, do_auto, do_cross,
                                                approx_cell1_size, approx_cell2_size, always_auto1=True)
         D1R, D2R, RR = _driver.random_counts(count, analytic, sample1, sample2, randoms, same, do_RR, do_DR,

@@ -11,6 +11,7 @@ from ..helpers import (enforce_sample_has_correct_shape, get_num_threads, get_pe
 from ..pair_counters import npairs_3d
 from ..pair_counters.mesh_helpers import _enforce_maximum_search_length
 from .. import _lib
+from .. import distributed as _dist
 from . import _driver
 from .clustering_helpers import (process_optional_input_sample2, tpcf_estimator_dd_dr_rr_requirements,
                                  verify_tpcf_estimator)
@@ -43,8 +44,8 @@ def tpcf(sample1, rbins, sample2=None, randoms=None, period=None,
         NR = NR_precomputed if NR_precomputed is not None else N1
 
     def count(a, b, cell_a, cell_b):
-        return np.diff(npairs_3d(a, b, rbins, period=period, num_threads=num_threads,
-                                 approx_cell1_size=cell_a, approx_cell2_size=cell_b))
+        return partial.add(np.diff(npairs_3d(a, b, rbins, period=period, num_threads=num_threads,
+                                             approx_cell1_size=cell_a, approx_cell2_size=cell_b)))
 
     def analytic():
         # shells of a periodic box populated at the mean density (tpcf.py:121-145)
@@ -55,8 +56,10 @@ def tpcf(sample1, rbins, sample2=None, randoms=None, period=None,
         D2R = nr * (dv * (np.shape(sample2)[0] / volume))
         return D1R, D2R, dv * ((nr ** 2) / volume)
 
-    # the engine's upload cache: every sample crosses PCIe once for all the counts of this call
-    with _lib.upload_cache():
+    # the engine's upload cache: every sample crosses PCIe once for all the counts of this call; multi-GPU: the
+    # ranks' partial counts of ALL these calls are combined by one all-reduce at the end of the block
+    partial = _dist.local_counts()
+    with _lib.upload_cache(), partial:
         D1D1, D1D2, D2D2 = _driver.data_counts(count, sample1, sample2, same, do_auto, do_cross,
                                                approx_cell1_size, approx_cell2_size)
         D1R, D2R, RR = _driver.random_counts(count, analytic, sample1, sample2, randoms, same, do_RR, do_DR,

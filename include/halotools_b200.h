@@ -193,6 +193,10 @@ int htb_cell1_work(const htb_mesh_geom *mesh,
  * NaNs anywhere make every result NaN (so that comparisons fail as they do in numpy).            */
 int htb_host_minmax(const double *base, int64_t n, int64_t stride, int32_t cols, double *min_out, double *max_out);
 
+/* The same extrema for a DEVICE-resident row-major matrix (cols <= 3; `base_dev` is a device pointer): one HBM-bound
+ * pass on the GPU, on the library's current stream; results land in host memory.                  */
+int htb_device_minmax(const double *base_dev, int64_t n, int64_t stride, int32_t cols, double *min_out, double *max_out);
+
 /* Measured FP64 non-FMA issue rate (DADD/DMUL instr-lanes per second) of the current device. */
 int htb_measure_fp64_rate(double *ops_per_second_out, double *sm_clock_mhz_out);
 

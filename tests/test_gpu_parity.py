@@ -683,3 +683,30 @@ def test_weighted_npairs_xy_vs_oracle():
     assert np.array_equal(hb.weighted_npairs_xy(g, p, ints, rp, period=L), oracle.weighted_npairs_xy(g, p, ints, rp, period=L))
     nonper = hb.weighted_npairs_xy(g[:3000], p[:30000], m[:30000], rp, period=None)
     assert np.allclose(nonper, oracle.weighted_npairs_xy(g[:3000], p[:30000], m[:30000], rp, period=None), rtol=1e-12)
+
+
+def test_device_minmax_matches_numpy():
+    import ctypes
+    import torch
+    rng = np.random.RandomState(36)
+    for n in (1, 31, 1000, 300001):
+        a = rng.uniform(-5.0, 7.0, (n, 3))
+        t = torch.from_numpy(a).cuda()
+        lo, hi = (ctypes.c_double * 3)(), (ctypes.c_double * 3)()
+        _lib.check(_lib.load().htb_device_minmax(ctypes.c_void_p(int(t.data_ptr())), ctypes.c_int64(n), ctypes.c_int64(3),
+                                                 ctypes.c_int32(3), lo, hi))
+        assert np.array_equal(np.array(lo[:]), a.min(axis=0)) and np.array_equal(np.array(hi[:]), a.max(axis=0))
+        # two of the three columns (the 2-D engines), NaN anywhere poisons every extremum
+        _lib.check(_lib.load().htb_device_minmax(ctypes.c_void_p(int(t.data_ptr())), ctypes.c_int64(n), ctypes.c_int64(3),
+                                                 ctypes.c_int32(2), lo, hi))
+        assert np.array_equal(np.array(lo[:2]), a.min(axis=0)[:2]) and np.array_equal(np.array(hi[:2]), a.max(axis=0)[:2])
+        a[n // 2, 1] = np.nan
+        t = torch.from_numpy(a).cuda()
+        _lib.check(_lib.load().htb_device_minmax(ctypes.c_void_p(int(t.data_ptr())), ctypes.c_int64(n), ctypes.c_int64(3),
+                                                 ctypes.c_int32(3), lo, hi))
+        assert all(np.isnan(v) for v in lo[:]) and all(np.isnan(v) for v in hi[:])
+    # the front-end check on device tensors raises the reference's messages
+    s = torch.from_numpy(rng.uniform(0, 10.0, (5000, 3))).cuda()
+    s[17, 2] = 11.0
+    with pytest.raises(ValueError, match="zperiod"):
+        hb.mean_delta_sigma(s, s, 1.0, np.logspace(-1, 0, 4), period=10.0)

@@ -206,6 +206,15 @@ part = oracle.npairs_3d(*args, cell1_range=(first, last), **kwargs)     # stands
 total = distributed.allreduce_sum(part)
 assert np.array_equal(total, oracle.npairs_3d(*args, **kwargs)), (total, part)
 assert first < last and (first == 0 or last == dm.mesh1.ncells)
+# several calls of one statistic: partial counts inside local_counts(), ONE all-reduce (per dtype) on exit, in place
+full = oracle.npairs_3d(*args, **kwargs)
+with distributed.local_counts() as partial:
+    a = partial.add(np.diff(distributed.allreduce_sum(part)))           # no reduction inside the block
+    b = partial.add(distributed.allreduce_sum(part.astype(np.float64)) * 0.5)
+    assert np.array_equal(a, np.diff(part))
+    same = partial.add(a)                                               # registered twice, reduced once
+assert np.array_equal(a, np.diff(full)) and same is a and np.array_equal(b, 0.5 * full)
+assert np.array_equal(distributed.allreduce_sum(part), full)            # back to one all-reduce per call
 dist.destroy_process_group()
 print("rank", sys.argv[1], "ok", first, last)
 '''
