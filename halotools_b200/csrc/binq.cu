@@ -7,6 +7,8 @@
 //   MODE 1  weighted sums  marked_npairs_xy_z / marked_npairs_3d with general marks / weighted_npairs_xy
 //                          marked_npairs_xy_z_engine.pyx:209-225, marked_npairs_3d_engine.pyx:204-216
 //   MODE 2  per-object     npairs_per_object_3d                         npairs_per_object_3d_engine.pyx:190-207
+//   MODE 3  per-object weighted sums folded by the point's jackknife tag (payload rows {weight, tag})
+//                          npairs_jackknife_3d_engine.pyx:213-233, npairs_jackknife_xy_z_engine.pyx:222-246
 // The hot loop only DECIDES whether a pair can be inside the top edge(s): the reference's strict f64 separation
 // (5-8 operations), one integer compare of its high word per bin axis against the high word of the top squared
 // edge (a conservative superset: the high word of a non-negative double is monotone), and one predicated integer
@@ -33,12 +35,13 @@ __device__ __forceinline__ unsigned long long bq_lds_u64(uint32_t addr)
 
 template <int KIND, int MODE>
 struct BinQ {
-    static constexpr int DIM = KIND == 3 ? 2 : 3, NPAY = MODE == 1 ? HTB_MAX_NW : 0, PPL = 2, WARPS = 8, MINBLOCKS = 2;
+    static constexpr int DIM = KIND == 3 ? 2 : 3, NPAY = MODE == 1 ? HTB_MAX_NW : (MODE == 3 ? 2 : 0), PPL = 2, WARPS = 8,
+                         MINBLOCKS = MODE == 3 ? 1 : 2;
     static constexpr bool TMA = true;
     typedef BinQParams Params;
     const Params &P;
     uint32_t *hist;             // MODE 0: per-warp differential histogram (n0 * n1 u32); MODE 2: 64 rows of `rstride` u32
-    double *fhist;              // MODE 1: per-warp differential float sums (n0 * n1)
+    double *fhist;              // MODE 1: per-warp differential float sums (n0 * n1); MODE 3: 64 rows of `rstride` f64
     uint32_t e_s;               // shared-space address: raw bits of the squared edges (n0 then n1), u64
     uint32_t lut_s[2];          // shared-space addresses of the two lookup tables (u8)
     int lane;
@@ -47,6 +50,7 @@ struct BinQ {
     double x0, y0, z0, x1, y1, z1;
     double xs0, ys0, zs0, xs1, ys1, zs1;
     double wa[MODE == 1 ? HTB_MAX_NW : 1], wb[MODE == 1 ? HTB_MAX_NW : 1];
+    int tag[2];                 // MODE 3: jackknife tags of this lane's points
 
     static __host__ __device__ size_t lut_bytes(const Params &p) { return (((size_t)p.T[0] + 7) & ~(size_t)7) + (((size_t)p.T[1] + 7) & ~(size_t)7); }
     static size_t scratch_bytes(const Params &p)
@@ -55,7 +59,8 @@ struct BinQ {
         size_t acc;
         if (MODE == 0) acc = 4 * ((nh + 3) & ~(size_t)3);
         else if (MODE == 1) acc = 8 * nh;
-        else acc = 4 * ((64 * (size_t)(p.n0 | 1) + 3) & ~(size_t)3);
+        else if (MODE == 2) acc = 4 * ((64 * (size_t)(p.n0 | 1) + 3) & ~(size_t)3);
+        else acc = 8 * 64 * (nh | 1);
         return 8 * ne + lut_bytes(p) + acc;
     }
     __device__ BinQ(const Params &p, void *scratch, int ln, const WalkArrays &) : P(p), lane(ln)
@@ -69,12 +74,13 @@ struct BinQ {
         e_s = smem_u32(e);
         lut_s[0] = e_s + 8u * (uint32_t)ne;
         lut_s[1] = lut_s[0] + (uint32_t)((P.T[0] + 7) & ~7);
-        rstride = P.n0 | 1;
+        rstride = MODE == 3 ? ((P.n0 * P.n1) | 1) : (P.n0 | 1);
         vmask = 0;
         for (int k = lane; k < ne + nl; k += 32) e[k] = P.edges[k];
         if (MODE == 0) { for (int k = lane; k < P.n0 * P.n1; k += 32) hist[k] = 0; }
         else if (MODE == 1) { for (int k = lane; k < P.n0 * P.n1; k += 32) fhist[k] = 0.0; }
-        else { for (int k = lane; k < 64 * rstride; k += 32) hist[k] = 0; }
+        else if (MODE == 2) { for (int k = lane; k < 64 * rstride; k += 32) hist[k] = 0; }
+        else { for (int k = lane; k < 64 * rstride; k += 32) fhist[k] = 0.0; }
         x0 = y0 = z0 = x1 = y1 = z1 = 0.0;
         xs0 = ys0 = zs0 = xs1 = ys1 = zs1 = 0.0;
         __syncwarp();
@@ -93,6 +99,10 @@ struct BinQ {
                 wa[k] = (A.pay1 && k < A.nw) ? A.pay1[(size_t)idx[0] * A.nw + k] : 0.0;
                 wb[k] = (A.pay1 && k < A.nw) ? A.pay1[(size_t)idx[1] * A.nw + k] : 0.0;
             }
+        }
+        if (MODE == 3) {
+            wa[0] = A.pay1[(size_t)idx[0] * 2]; wb[0] = A.pay1[(size_t)idx[1] * 2];
+            tag[0] = (int)A.pay1[(size_t)idx[0] * 2 + 1]; tag[1] = (int)A.pay1[(size_t)idx[1] * 2 + 1];
         }
     }
     __device__ __forceinline__ void set_shift(const double (&sh)[3], const WalkArrays &)
@@ -196,10 +206,14 @@ struct BinQ {
             } else if (MODE == 1) {
                 if (h0 >= 0) atomicAdd(fhist + h0, weight_of(wa, bw + 8 * j0 * P.nw));
                 if (h1 >= 0) atomicAdd(fhist + h1, weight_of(wb, bw + 8 * j1 * P.nw));
-            } else {
+            } else if (MODE == 2) {
                 // rows are private to the lane's points: plain read-modify-write
                 if (h0 >= 0) hist[lane * rstride + h0] += 1u;
                 if (h1 >= 0) hist[(32 + lane) * rstride + h1] += 1u;
+            } else {
+                // jweight's w1 * w2 (npairs_jackknife_3d_engine.pyx:283-289), summed per lane point and differential cell
+                if (h0 >= 0) fhist[lane * rstride + h0] += wa[0] * lds_f64(bw + 16 * j0);
+                if (h1 >= 0) fhist[(32 + lane) * rstride + h1] += wb[0] * lds_f64(bw + 16 * j1);
             }
         }
     }
@@ -255,6 +269,18 @@ struct BinQ {
                 const double h = fhist[k];
                 if (h != 0.0) { atomicAdd(P.fcounts + k, wt == 2u ? h + h : h); fhist[k] = 0.0; }
             }
+        } else if (MODE == 3) {
+            // fold the rows of this lane's points into the table row of their jackknife tag (differential cells)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                if (!((vmask >> q) & 1u)) continue;
+                double *dst = P.fcounts + (size_t)tag[q] * (size_t)nh;
+                double *r = fhist + (q * 32 + lane) * rstride;
+                for (int k = 0; k < nh; ++k) {
+                    const double v = r[k];
+                    if (v != 0.0) { atomicAdd(dst + k, v); r[k] = 0.0; }
+                }
+            }
         } else {
             // per object: cumulative over the edges (npairs_per_object_3d_engine.pyx:190-207), rows in input order;
             // several work items (column slices) may add to the same row
@@ -287,6 +313,8 @@ int htb_launch_binq(cudaStream_t st, int kind, int mode, const WalkGeom &G, cons
     case 5: return launch_count<BinQ<1, 1>>(st, G, A, P, l);
     case 7: return launch_count<BinQ<3, 1>>(st, G, A, P, l);
     case 8: return launch_count<BinQ<0, 2>>(st, G, A, P, l);
+    case 12: return launch_count<BinQ<0, 3>>(st, G, A, P, l);
+    case 13: return launch_count<BinQ<1, 3>>(st, G, A, P, l);
     }
     htb_set_error("unknown BinQ kind %d / mode %d", kind, mode);
     return 1;

@@ -1198,6 +1198,146 @@ extern "C" int htb_npairs_per_object_3d_engine(const htb_mesh_geom *mesh,
     HTB_GUARD_END
 }
 
+// ------------------------------------------------------------------ npairs_jackknife_3d / npairs_jackknife_xy_z
+// The reference adds jweight(s, j1, j2, w1, w2) to counts[s] for EVERY sample s and every pair
+// (npairs_jackknife_3d_engine.pyx:227-233): w1*w2 if neither point carries tag s, half of it if exactly one does, 0 if
+// both do, and w1*w2 for s = 0 (:283-289).  With A[s] = the weighted pair sums of the sample1 points tagged s and B[s]
+// the same for the sample2 points, counts[0] = T = sum_s A[s] and counts[s] = T - (A[s] + B[s]) / 2 - O(1) work per
+// pair instead of O(N_samples).  A comes from one pass of the per-object BinQ kernel (rows folded by tag); B from a
+// second pass with the roles of the samples exchanged, on mesh1's grid for both samples (cells >= the search length,
+// cover 1: every pair within the search length is visited once, with the image the reference uses).  A pair whose
+// squared separation lies within one ulp of an edge may fall on different sides in the two passes when it is a WRAPPED
+// pair (x1 - L - x2 and x2 + L - x1 round independently); un-wrapped pairs are bit-identical in both directions.
+static int jackknife_pass(const htb_mesh_geom *mesh, int kind, bool swapped,
+                          const double *const *ca, int64_t sa, int64_t na, const double *pa,
+                          const double *const *cb, int64_t sb, int64_t nb_, const double *pb,
+                          const double *e0, int n0, const double *e1, int n1, int32_t nsamples,
+                          int64_t first, int64_t last, std::vector<double> &table, uint32_t flags, htb_stats *stats)
+{
+    Call c;
+    if (c.begin()) return 1;
+    if (c.setup(mesh, kind == 0 ? 1 : 0, false, ca, sa, na, pa, cb, sb, nb_, pb, 2, false, first, last, flags)) return 1;
+    BinQParams bp{};
+    if (binq_prepare(c, e0, n0, e1, n1, &bp)) return 1;
+    const size_t nh = (size_t)n0 * n1, nt = (size_t)(nsamples + 1) * nh;
+    double *tab = nullptr;
+    if (c.ws.alloc((void **)&tab, sizeof(double) * nt)) return 1;
+    HTB_CUDA(cudaMemsetAsync(tab, 0, sizeof(double) * nt, c.st));
+    bp.fcounts = tab;
+    bp.nw = 2; bp.wfunc = 1;
+    if (htb_launch_binq(c.st, kind, 3, c.G, c.A, bp, &c.launches)) return 1;
+    table.assign(nt, 0.0);
+    HTB_CUDA(cudaMemcpyAsync(table.data(), tab, sizeof(double) * nt, cudaMemcpyDeviceToHost, c.st));
+    (void)swapped;
+    return c.finish(stats, 3);
+}
+
+static int run_jackknife(const htb_mesh_geom *mesh, int kind,
+                         const double *x1, const double *y1, const double *z1, int64_t stride1, int64_t n1,
+                         const double *x2, const double *y2, const double *z2, int64_t stride2, int64_t n2,
+                         const double *w1, const double *w2, const int64_t *jtags1, const int64_t *jtags2, int32_t nsamples,
+                         const double *e0in, int n0, const double *e1in, int n1e,
+                         int64_t first_cell1, int64_t last_cell1, double *counts_out, uint32_t flags, htb_stats *stats)
+{
+    if (flags & HTB_FLAG_DEVICE_INPUT) { htb_set_error("jackknife engines take host arrays"); return 1; }
+    if (nsamples < 1 || nsamples > 100000) { htb_set_error("N_samples must be in [1, 100000]"); return 1; }
+    std::vector<double> e((size_t)n0 + n1e);
+    for (int k = 0; k < n0; ++k) e[k] = e0in[k] * e0in[k];
+    for (int k = 0; k < n1e; ++k) e[(size_t)n0 + k] = e1in[k] * e1in[k];
+    suffix_min(e, 0, n0);
+    if (n1e > 1 || kind == 1) suffix_min(e, n0, n1e);
+    const double *e1 = kind == 1 ? e.data() + n0 : nullptr;
+    const int nn1 = kind == 1 ? n1e : 1;
+    if (!binq_ok(e.data(), n0, e1, nn1, flags & ~HTB_FLAG_GENERIC) || (long long)n0 * nn1 > 48) {
+        htb_set_error("jackknife engines: bins must be finite and n_bins (x n_pi_bins) <= 48 (per-point shared-memory rows)");
+        return 1;
+    }
+    // payload rows {weight, tag}
+    std::vector<double> p1((size_t)(n1 > 0 ? n1 : 1) * 2), p2((size_t)(n2 > 0 ? n2 : 1) * 2);
+    for (int64_t i = 0; i < n1; ++i) {
+        if (jtags1[i] < 0 || jtags1[i] > nsamples) { htb_set_error("jtags1 out of [0, N_samples]"); return 1; }
+        p1[(size_t)i * 2] = w1[i]; p1[(size_t)i * 2 + 1] = (double)jtags1[i];
+    }
+    for (int64_t i = 0; i < n2; ++i) {
+        if (jtags2[i] < 0 || jtags2[i] > nsamples) { htb_set_error("jtags2 out of [0, N_samples]"); return 1; }
+        p2[(size_t)i * 2] = w2[i]; p2[(size_t)i * 2 + 1] = (double)jtags2[i];
+    }
+    const double *c1[3] = {x1, y1, z1}, *c2[3] = {x2, y2, z2};
+    std::vector<double> A, B;
+    // pass A: the reference's own geometry and cell range
+    if (jackknife_pass(mesh, kind, false, c1, stride1, n1, p1.data(), c2, stride2, n2, p2.data(),
+                       e.data(), n0, e1, nn1, nsamples, first_cell1, last_cell1, A, flags, stats)) return 1;
+    // pass B: roles exchanged, both samples on mesh1's grid.  A caller-chosen cell range selects sample1 points
+    // (the reference's worker split): the sample1 points outside it get weight 0 here.
+    htb_mesh_geom gb = *mesh;
+    int64_t nc1 = 1;
+    for (int d = 0; d < 3; ++d) {
+        gb.ndivs2[d] = gb.ndivs1[d];
+        gb.cell2_size[d] = gb.cell1_size[d];
+        gb.cover[d] = (int)ceil(gb.search[d] / gb.cell1_size[d]);
+        if (gb.cover[d] < 1) gb.cover[d] = 1;
+        nc1 *= mesh->ndivs1[d];
+    }
+    if (first_cell1 > 0 || last_cell1 < nc1) {
+        std::vector<int64_t> ids((size_t)(n1 > 0 ? n1 : 1));
+        if (n1 > 0 && htb_mesh_cell_ids(3, x1, y1, z1, stride1, n1, mesh->cell1_size, mesh->ndivs1, ids.data(), 0)) return 1;
+        for (int64_t i = 0; i < n1; ++i) if (ids[(size_t)i] < first_cell1 || ids[(size_t)i] >= last_cell1) p1[(size_t)i * 2] = 0.0;
+    }
+    htb_stats sb;
+    if (jackknife_pass(&gb, kind, true, c2, stride2, n2, p2.data(), c1, stride1, n1, p1.data(),
+                       e.data(), n0, e1, nn1, nsamples, 0, nc1, B, flags, stats ? &sb : nullptr)) return 1;
+    if (stats) {
+        stats->pairs_evaluated += sb.pairs_evaluated;
+        stats->ms_h2d += sb.ms_h2d; stats->ms_mesh += sb.ms_mesh; stats->ms_count += sb.ms_count; stats->ms_total += sb.ms_total;
+        stats->kernel_launches += sb.kernel_launches;
+    }
+    // differential -> cumulative per sample, then counts[s] = T - (A[s] + B[s]) / 2
+    const size_t nh = (size_t)n0 * nn1;
+    std::vector<double> T(nh, 0.0), cum(nh), row(nh);
+    for (int s = 0; s <= nsamples; ++s) for (size_t k = 0; k < nh; ++k) T[k] += A[(size_t)s * nh + k];
+    prefix2d<double>(T.data(), n0, nn1, cum.data());
+    for (size_t k = 0; k < nh; ++k) counts_out[k] = cum[k];
+    for (int s = 1; s <= nsamples; ++s) {
+        for (size_t k = 0; k < nh; ++k) row[k] = A[(size_t)s * nh + k] + B[(size_t)s * nh + k];
+        std::vector<double> rc(nh);
+        prefix2d<double>(row.data(), n0, nn1, rc.data());
+        for (size_t k = 0; k < nh; ++k) counts_out[(size_t)s * nh + k] = cum[k] - 0.5 * rc[k];
+    }
+    return 0;
+}
+
+extern "C" int htb_npairs_jackknife_3d_engine(const htb_mesh_geom *mesh,
+                                              const double *x1, const double *y1, const double *z1, int64_t stride1, int64_t n1,
+                                              const double *x2, const double *y2, const double *z2, int64_t stride2, int64_t n2,
+                                              const double *w1, const double *w2, const int64_t *jtags1, const int64_t *jtags2,
+                                              int32_t n_samples, const double *rbins, int32_t nb,
+                                              int64_t first_cell1, int64_t last_cell1,
+                                              double *counts_out, uint32_t flags, htb_stats *stats)
+{
+    HTB_GUARD_BEGIN
+    if (!mesh || !rbins || !counts_out || nb < 1 || !w1 || !w2 || !jtags1 || !jtags2) { htb_set_error("htb_npairs_jackknife_3d_engine: bad arguments"); return 1; }
+    if (mesh->ndim != 3) { htb_set_error("htb_npairs_jackknife_3d_engine needs a 3-d mesh"); return 1; }
+    return run_jackknife(mesh, 0, x1, y1, z1, stride1, n1, x2, y2, z2, stride2, n2, w1, w2, jtags1, jtags2, n_samples,
+                         rbins, nb, nullptr, 0, first_cell1, last_cell1, counts_out, flags, stats);
+    HTB_GUARD_END
+}
+
+extern "C" int htb_npairs_jackknife_xy_z_engine(const htb_mesh_geom *mesh,
+                                                const double *x1, const double *y1, const double *z1, int64_t stride1, int64_t n1,
+                                                const double *x2, const double *y2, const double *z2, int64_t stride2, int64_t n2,
+                                                const double *w1, const double *w2, const int64_t *jtags1, const int64_t *jtags2,
+                                                int32_t n_samples, const double *rp_bins, int32_t nrp, const double *pi_bins, int32_t npi,
+                                                int64_t first_cell1, int64_t last_cell1,
+                                                double *counts_out, uint32_t flags, htb_stats *stats)
+{
+    HTB_GUARD_BEGIN
+    if (!mesh || !rp_bins || !pi_bins || !counts_out || nrp < 1 || npi < 1 || !w1 || !w2 || !jtags1 || !jtags2) { htb_set_error("htb_npairs_jackknife_xy_z_engine: bad arguments"); return 1; }
+    if (mesh->ndim != 3) { htb_set_error("htb_npairs_jackknife_xy_z_engine needs a 3-d mesh"); return 1; }
+    return run_jackknife(mesh, 1, x1, y1, z1, stride1, n1, x2, y2, z2, stride2, n2, w1, w2, jtags1, jtags2, n_samples,
+                         rp_bins, nrp, pi_bins, npi, first_cell1, last_cell1, counts_out, flags, stats);
+    HTB_GUARD_END
+}
+
 // Column sums of the (n, nbin) per-object rows in a fixed order (HTB_FLAG_COLUMN_SUM): block b sums rows
 // b, b + gridDim.x, ... per column, a second launch adds the per-block partial sums.
 __global__ void __launch_bounds__(256) k_colsum_partial(const double *__restrict__ rows, long long n, int nbin,

@@ -7,6 +7,7 @@ from .marked_npairs_3d import marked_npairs_3d
 from .marked_npairs_xy_z import marked_npairs_xy_z
 from .npairs_projected import npairs_projected
 from .npairs_per_object_3d import npairs_per_object_3d
+from .npairs_jackknife_3d import npairs_jackknife_3d, npairs_jackknife_xy_z
 
 __all__ = ("npairs_3d", "npairs_xy_z", "npairs_s_mu", "marked_npairs_3d", "marked_npairs_xy_z",
-           "npairs_projected", "npairs_per_object_3d")
+           "npairs_projected", "npairs_per_object_3d", "npairs_jackknife_3d", "npairs_jackknife_xy_z")

@@ -172,6 +172,28 @@ int htb_weighted_npairs_xy_engine(const htb_mesh_geom *mesh,
                                   int64_t first_cell1, int64_t last_cell1,
                                   double *counts_out, uint32_t flags, htb_stats *stats);
 
+/* npairs_jackknife_3d_engine.pyx:20 (cpairs/) - counts[s,k] = sum over pairs with dsq <= rbins[k]^2 of
+ * jweight(s, jtag1_i, jtag2_j, w1_i, w2_j) (:237-291): s = 0 is the full sample, s >= 1 leaves sub-volume s out.
+ * w1, w2: one weight per point; jtags1, jtags2: int64 tags in [1, N_samples]; output f64[(N_samples+1)*nb].
+ * HOST arrays only.  nb <= 48.                                                                                  */
+int htb_npairs_jackknife_3d_engine(const htb_mesh_geom *mesh,
+                                   const double *x1, const double *y1, const double *z1, int64_t stride1, int64_t n1,
+                                   const double *x2, const double *y2, const double *z2, int64_t stride2, int64_t n2,
+                                   const double *w1, const double *w2, const int64_t *jtags1, const int64_t *jtags2,
+                                   int32_t n_samples, const double *rbins, int32_t nb,
+                                   int64_t first_cell1, int64_t last_cell1,
+                                   double *counts_out, uint32_t flags, htb_stats *stats);
+
+/* npairs_jackknife_xy_z_engine.pyx:20 (cpairs/) - the same on (rp, pi) bins, f64[(N_samples+1)*nrp*npi] (:222-246);
+ * nrp * npi <= 48.                                                                                              */
+int htb_npairs_jackknife_xy_z_engine(const htb_mesh_geom *mesh,
+                                     const double *x1, const double *y1, const double *z1, int64_t stride1, int64_t n1,
+                                     const double *x2, const double *y2, const double *z2, int64_t stride2, int64_t n2,
+                                     const double *w1, const double *w2, const int64_t *jtags1, const int64_t *jtags2,
+                                     int32_t n_samples, const double *rp_bins, int32_t nrp, const double *pi_bins, int32_t npi,
+                                     int64_t first_cell1, int64_t last_cell1,
+                                     double *counts_out, uint32_t flags, htb_stats *stats);
+
 /* RectangularMesh cell assignment alone (rectangular_mesh.py:19-22,211-225): writes the
  * reference cell id of every point (int64[n]) — used by the mesh parity tests.               */
 int htb_mesh_cell_ids(int32_t ndim, const double *x, const double *y, const double *z, int64_t stride, int64_t n,

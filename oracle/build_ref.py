@@ -48,6 +48,9 @@ ENGINES = [
     "halotools/mock_observables/pair_counters/cpairs/npairs_per_object_3d_engine",
     "halotools/mock_observables/pair_counters/marked_cpairs/marked_npairs_xy_z_engine",
     "halotools/mock_observables/surface_density/engines/weighted_npairs_xy_engine",
+    # SURVEY section 8(f) rank 3
+    "halotools/mock_observables/pair_counters/cpairs/npairs_jackknife_3d_engine",
+    "halotools/mock_observables/pair_counters/cpairs/npairs_jackknife_xy_z_engine",
 ]
 
 ASTROPY_SHIM = '''"""Shim for astropy.utils.misc (astropy is absent from this image)."""
@@ -84,13 +87,17 @@ TRIMMED_INITS = {
         "from .npairs_s_mu import npairs_s_mu\n"
         "from .npairs_projected import npairs_projected\n"
         "from .npairs_per_object_3d import npairs_per_object_3d\n"
-        "from .marked_npairs_xy_z import marked_npairs_xy_z\n",
+        "from .marked_npairs_xy_z import marked_npairs_xy_z\n"
+        "from .npairs_jackknife_3d import npairs_jackknife_3d\n"
+        "from .npairs_jackknife_xy_z import npairs_jackknife_xy_z\n",
     "halotools/mock_observables/pair_counters/cpairs/__init__.py":
         "from .npairs_3d_engine import npairs_3d_engine\n"
         "from .npairs_xy_z_engine import npairs_xy_z_engine\n"
         "from .npairs_s_mu_engine import npairs_s_mu_engine\n"
         "from .npairs_projected_engine import npairs_projected_engine\n"
-        "from .npairs_per_object_3d_engine import npairs_per_object_3d_engine\n",
+        "from .npairs_per_object_3d_engine import npairs_per_object_3d_engine\n"
+        "from .npairs_jackknife_3d_engine import npairs_jackknife_3d_engine\n"
+        "from .npairs_jackknife_xy_z_engine import npairs_jackknife_xy_z_engine\n",
     "halotools/mock_observables/pair_counters/marked_cpairs/__init__.py":
         "from .marked_npairs_3d_engine import marked_npairs_3d_engine\n"
         "from .marked_npairs_xy_z_engine import marked_npairs_xy_z_engine\n",

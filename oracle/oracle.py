@@ -20,6 +20,7 @@ Reference call sites restated:
   npairs_projected      .../pair_counters/npairs_projected.py:118-157,160-227
   npairs_per_object_3d  .../pair_counters/npairs_per_object_3d.py:106-142
   marked_npairs_xy_z    .../pair_counters/marked_npairs_xy_z.py:141-194
+  npairs_jackknife_3d / _xy_z  .../pair_counters/npairs_jackknife_3d.py:160-196, npairs_jackknife_xy_z.py:152-196
   weighted_npairs_xy    /root/reference/halotools/mock_observables/surface_density/weighted_npairs_xy.py:111-151,153-217
 """
 import ctypes
@@ -351,6 +352,48 @@ def weighted_npairs_xy(sample1, sample2, sample2_mass, rp_bins, period=None, app
                                     _p(rp_bins), ctypes.c_int(len(rp_bins)), ctypes.c_int64(first), ctypes.c_int64(last),
                                     _p(out))
     return out
+
+
+def _jackknife(sample1, sample2, bins0, bins1, jtags1, jtags2, N_samples, period, weights1, weights2,
+               approx_cell1_size, approx_cell2_size, cell1_range):
+    bins0 = _f8(np.atleast_1d(bins0))
+    m0 = float(np.max(bins0))
+    if bins1 is None:
+        search, b1 = [m0] * 3, np.zeros(0)
+    else:
+        b1 = _f8(np.atleast_1d(bins1))
+        search = [m0, m0, float(np.max(b1))]
+    n1, n2 = np.shape(sample1)[0], np.shape(sample2)[0]
+    w1 = np.ones(n1) if weights1 is None else np.asarray(weights1, dtype=np.float64)
+    w2 = np.ones(n2) if weights2 is None else np.asarray(weights2, dtype=np.float64)
+    dm, c1, c2 = build_double_mesh_3d(sample1, sample2, search, period, approx_cell1_size, approx_cell2_size)
+    x1, y1, z1 = _sorted(c1, dm.mesh1)
+    x2, y2, z2 = _sorted(c2, dm.mesh2)
+    w1s, w2s = _f8(w1[dm.mesh1.idx_sorted]), _f8(w2[dm.mesh2.idx_sorted])
+    t1 = np.ascontiguousarray(np.asarray(jtags1).astype(np.int64)[dm.mesh1.idx_sorted])
+    t2 = np.ascontiguousarray(np.asarray(jtags2).astype(np.int64)[dm.mesh2.idx_sorted])
+    g = _geom(dm)
+    first, last = _range(dm, cell1_range)
+    shape = (N_samples + 1, len(bins0)) if bins1 is None else (N_samples + 1, len(bins0), len(b1))
+    out = np.zeros(shape, dtype=np.float64)
+    lib().oracle_npairs_jackknife(ctypes.byref(g), _p(x1), _p(y1), _p(z1), _p(dm.mesh1.cell_id_indices, ctypes.c_int64),
+                                  _p(x2), _p(y2), _p(z2), _p(dm.mesh2.cell_id_indices, ctypes.c_int64),
+                                  _p(w1s), _p(w2s), _p(t1, ctypes.c_int64), _p(t2, ctypes.c_int64), ctypes.c_int(int(N_samples)),
+                                  _p(bins0), ctypes.c_int(len(bins0)), _p(b1) if len(b1) else None, ctypes.c_int(len(b1)),
+                                  ctypes.c_int64(first), ctypes.c_int64(last), _p(out))
+    return out
+
+
+def npairs_jackknife_3d(sample1, sample2, rbins, jtags1, jtags2, N_samples, period=None, weights1=None,
+                        weights2=None, approx_cell1_size=None, approx_cell2_size=None, cell1_range=None):
+    return _jackknife(sample1, sample2, rbins, None, jtags1, jtags2, N_samples, period, weights1, weights2,
+                      approx_cell1_size, approx_cell2_size, cell1_range)
+
+
+def npairs_jackknife_xy_z(sample1, sample2, rp_bins, pi_bins, jtags1, jtags2, N_samples, period=None, weights1=None,
+                          weights2=None, approx_cell1_size=None, approx_cell2_size=None, cell1_range=None):
+    return _jackknife(sample1, sample2, rp_bins, pi_bins, jtags1, jtags2, N_samples, period, weights1, weights2,
+                      approx_cell1_size, approx_cell2_size, cell1_range)
 
 
 def brute_npairs_3d(sample1, sample2, rbins, period=None):

@@ -594,6 +594,83 @@ void oracle_weighted_npairs_xy(const oracle_geom_t *g,
     free(wx); free(rpsq);
 }
 
+/* ------------------------------------------------------------ jackknife counters (section 8(f) rank 3)
+ *   npairs_jackknife_3d    .../cpairs/npairs_jackknife_3d_engine.pyx:120-233, jweight :237-291
+ *   npairs_jackknife_xy_z  .../cpairs/npairs_jackknife_xy_z_engine.pyx:128-246
+ * counts_out: (n_samples + 1, nb) or (n_samples + 1, nrp, npi) row-major.  npi = 0 selects the 3-D version.     */
+static double jweight(int64_t j, int64_t j1, int64_t j2, double w1, double w2)
+{
+    if (j == 0) return w1 * w2;
+    if ((j1 == j2) && (j1 == j)) return 0.0;
+    if ((j1 != j) && (j2 != j)) return w1 * w2;
+    return 0.5 * (w1 * w2);                /* (j1 != j2) & ((j1 == j) | (j2 == j)) */
+}
+
+void oracle_npairs_jackknife(const oracle_geom_t *g,
+                             const double *x1, const double *y1, const double *z1, const int64_t *off1,
+                             const double *x2, const double *y2, const double *z2, const int64_t *off2,
+                             const double *w1, const double *w2, const int64_t *jt1, const int64_t *jt2, int n_samples,
+                             const double *bins0, int n0, const double *bins1, int npi,
+                             int64_t first_cell1, int64_t last_cell1, double *counts_out)
+{
+    double *e0 = squares(bins0, n0), *e1 = squares(bins1, npi);
+    const int n1 = npi > 0 ? npi : 1;
+    const int ny1 = g->ndivs1[1], nz1 = g->ndivs1[2];
+    const int ny2 = g->ndivs2[1], nz2 = g->ndivs2[2];
+    const int perx = g->ndivs2[0] / g->ndivs1[0], pery = ny2 / ny1, perz = nz2 / nz1;
+    const int mw = max_window(g);
+    nbr_t *wx = (nbr_t *)malloc(sizeof(nbr_t) * mw * 3), *wy = wx + mw, *wz = wy + mw;
+    const size_t nh = (size_t)n0 * n1;
+    for (size_t k = 0; k < (size_t)(n_samples + 1) * nh; ++k) counts_out[k] = 0.0;
+    for (int64_t c1 = first_cell1; c1 < last_cell1; ++c1) {
+        const int64_t a = off1[c1], b = off1[c1 + 1];
+        if (b <= a) continue;
+        const int ix1 = (int)(c1 / ((int64_t)ny1 * nz1));
+        const int iy1 = (int)((c1 - (int64_t)ix1 * ny1 * nz1) / nz1);
+        const int iz1 = (int)(c1 - (int64_t)ix1 * ny1 * nz1 - (int64_t)iy1 * nz1);
+        const int nx = fill_window(ix1, perx, g->cover[0], g->ndivs2[0], g->period[0], g->pbc, wx);
+        const int ny = fill_window(iy1, pery, g->cover[1], ny2, g->period[1], g->pbc, wy);
+        const int nz = fill_window(iz1, perz, g->cover[2], nz2, g->period[2], g->pbc, wz);
+        for (int ax = 0; ax < nx; ++ax)
+        for (int ay = 0; ay < ny; ++ay)
+        for (int az = 0; az < nz; ++az) {
+            const int64_t c2 = (int64_t)wx[ax].idx * ny2 * nz2 + (int64_t)wy[ay].idx * nz2 + wz[az].idx;
+            const int64_t p = off2[c2], q = off2[c2 + 1];
+            if (q <= p) continue;
+            const double sx = wx[ax].shift, sy = wy[ay].shift, sz = wz[az].shift;
+            for (int64_t i = a; i < b; ++i) {
+                const double xt = x1[i] - sx, yt = y1[i] - sy, zt = z1[i] - sz;
+                for (int64_t j = p; j < q; ++j) {
+                    const double dx = xt - x2[j], dy = yt - y2[j], dz = zt - z2[j];
+                    if (npi == 0) {
+                        const double dsq = dx * dx + dy * dy + dz * dz;
+                        if (!(dsq <= e0[n0 - 1])) continue;          /* nothing would be added for any s */
+                        for (int s = 0; s <= n_samples; ++s) {
+                            const double w = jweight(s, jt1[i], jt2[j], w1[i], w2[j]);
+                            int k = n0 - 1;
+                            while (dsq <= e0[k]) { counts_out[(size_t)s * nh + k] += w; if (--k < 0) break; }
+                        }
+                    } else {
+                        const double dxy_sq = dx * dx + dy * dy;
+                        const double dz_sq = dz * dz;
+                        if (!(dxy_sq <= e0[n0 - 1]) || !(dz_sq <= e1[npi - 1])) continue;
+                        for (int s = 0; s <= n_samples; ++s) {
+                            const double w = jweight(s, jt1[i], jt2[j], w1[i], w2[j]);
+                            int k = n0 - 1;
+                            while (dxy_sq <= e0[k]) {
+                                int gq = npi - 1;
+                                while (dz_sq <= e1[gq]) { counts_out[(size_t)s * nh + (size_t)k * npi + gq] += w; if (--gq < 0) break; }
+                                if (--k < 0) break;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    free(wx); free(e0); free(e1);
+}
+
 /* ------------------------------------------------------------ brute force O(N^2)
  * restating pair_counters/pairs.py:17-84 (npairs): per-pair minimum-image distance,
  * used by the reference's own tests as ground truth on small inputs.            */

@@ -192,6 +192,23 @@ def _cases():
     C["wxy_nonperiodic"] = ("weighted_npairs_xy", (g2a, g2b, mass2, np.logspace(-1, 1.5, 15)), dict(period=None))
     C["wxy_scalar_period_cellsizes"] = ("weighted_npairs_xy", (g2a, g2b, mass2, np.logspace(-0.5, 1.3, 9)),
                                         dict(period=450.0, approx_cell1_size=30.0, approx_cell2_size=[15.0, 10.0]))
+    # ---- jackknife pair counters (fixture shapes: test_pair_counters/test_npairs_jackknife_3d.py)
+    def jt(seed, n, ns):
+        return np.random.RandomState(seed).randint(1, ns + 1, n)
+    w1j, w2j = np.random.RandomState(70).uniform(0.5, 1.5, 1000), np.random.RandomState(71).uniform(0.5, 1.5, 1000)
+    C["jk3d_periodic"] = ("npairs_jackknife_3d", (s1, s2, rb, jt(72, 1000, 10), jt(73, 1000, 10), 10), dict(period=1.0))
+    C["jk3d_weights"] = ("npairs_jackknife_3d", (s1, s2, rb, jt(72, 1000, 10), jt(73, 1000, 10), 10),
+                         dict(period=1.0, weights1=w1j, weights2=w2j))
+    C["jk3d_nonperiodic"] = ("npairs_jackknife_3d", (s1, s2, rb, jt(72, 1000, 7), jt(73, 1000, 7), 7),
+                             dict(period=None, weights1=w1j, weights2=w2j))
+    C["jk3d_auto_logbins"] = ("npairs_jackknife_3d", (s5, "same", np.logspace(-1, np.log10(20), 15),
+                                                      jt(74, 5000, 27), jt(74, 5000, 27), 27), dict(period=250.0))
+    C["jk3d_one_sample"] = ("npairs_jackknife_3d", (s1, s2, rb, np.ones(1000, dtype=int), np.ones(1000, dtype=int), 1),
+                            dict(period=1.0))
+    C["jkxyz_periodic"] = ("npairs_jackknife_xy_z", (s1, s2, rp, pi, jt(72, 1000, 10), jt(73, 1000, 10), 10),
+                           dict(period=1.0, weights1=w1j, weights2=w2j))
+    C["jkxyz_wp_like"] = ("npairs_jackknife_xy_z", (s5, "same", np.logspace(-1, np.log10(20), 12), np.array([0.0, 40.0]),
+                                                    jt(74, 5000, 8), jt(74, 5000, 8), 8), dict(period=250.0))
     return C
 
 

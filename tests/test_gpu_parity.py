@@ -36,6 +36,12 @@ def compare(fn, got, want):
         elif fn in ("marked_npairs_3d", "marked_npairs_xy_z", "weighted_npairs_xy"):
             # float sums, order differs from the reference's serial loop: 1e-12 relative (north_star)
             assert np.allclose(g, w, rtol=1e-12, atol=0), (g, w)
+        elif fn in ("npairs_jackknife_3d", "npairs_jackknife_xy_z"):
+            # counts[s] = T - (A[s] + B[s]) / 2 is formed from three float sums: 1e-12 relative to the full-sample
+            # counts (row 0) of the same bin; an element the reference gets as an exact 0 (both points always in the
+            # removed sample) comes out at the 1e-16 level of that row
+            assert np.allclose(g, w, rtol=1e-12, atol=0) or np.all(np.abs(g - w) <= 1e-12 * np.abs(w[0])[None]), \
+                np.max(np.abs(g - w) / np.abs(w[0])[None])
         elif fn == "mean_delta_sigma":
             # cancelling difference of large sums: abs + rel tolerance (SURVEY.md 8d parity gates)
             scale = np.max(np.abs(w))
@@ -710,3 +716,50 @@ def test_device_minmax_matches_numpy():
     s[17, 2] = 11.0
     with pytest.raises(ValueError, match="zperiod"):
         hb.mean_delta_sigma(s, s, 1.0, np.logspace(-1, 0, 4), period=10.0)
+
+
+# ---------------------------------------------------------------- jackknife pair counters
+@pytest.mark.parametrize("auto", [True, False])
+def test_npairs_jackknife_3d_vs_oracle(auto):
+    rng = np.random.RandomState(41)
+    L, ns = 100.0, 27
+    s1 = _dup_points(rng, 12000, L)
+    s2 = s1 if auto else np.vstack([s1[:2000], _dup_points(rng, 9000, L)])
+    w1 = rng.uniform(0.5, 1.5, len(s1))
+    w2 = w1 if auto else rng.uniform(0.5, 1.5, len(s2))
+    # spatial tags (3 x 3 x 3 sub-volumes), as tpcf_jackknife makes them
+    tag = lambda s: 1 + (np.minimum((s // (L / 3)).astype(int), 2) * np.array([9, 3, 1])).sum(axis=1)
+    t1, t2 = tag(s1), tag(s2)
+    rbins = np.logspace(-1, np.log10(9.0), 12)
+    got = hb.npairs_jackknife_3d(s1, s2, rbins, t1, t2, ns, period=L, weights1=w1, weights2=w2)
+    want = oracle.npairs_jackknife_3d(s1, s2, rbins, t1, t2, ns, period=L, weights1=w1, weights2=w2)
+    assert got.shape == want.shape == (ns + 1, len(rbins))
+    assert np.all(np.abs(got - want) <= 1e-12 * np.abs(want[0])[None]), np.max(np.abs(got - want) / want[0][None])
+    # row 0 is the plain weighted count
+    full = hb.marked_npairs_3d(s1, s2, rbins, 1, period=L, weights1=w1, weights2=w2)
+    assert np.allclose(got[0], full, rtol=1e-12)
+    # unit weights: every entry is a multiple of 1/2 and exact
+    ones1, ones2 = np.ones(len(s1)), np.ones(len(s2))
+    gi = hb.npairs_jackknife_3d(s1, s2, rbins, t1, t2, ns, period=L, weights1=ones1, weights2=ones2)
+    wi = oracle.npairs_jackknife_3d(s1, s2, rbins, t1, t2, ns, period=L, weights1=ones1, weights2=ones2)
+    assert np.array_equal(gi, wi)
+    assert np.array_equal(gi[0], hb.npairs_3d(s1, s2, rbins, period=L).astype(float))
+
+
+def test_npairs_jackknife_xy_z_vs_oracle_and_errors():
+    rng = np.random.RandomState(42)
+    L, ns = 120.0, 8
+    s1 = _dup_points(rng, 10000, L)
+    s2 = _dup_points(rng, 8000, L)
+    t1, t2 = rng.randint(1, ns + 1, len(s1)), rng.randint(1, ns + 1, len(s2))
+    rp = np.logspace(-1, np.log10(10.0), 9)
+    pi = np.array([0.0, 5.0, 25.0])
+    for per in (L, None):
+        got = hb.npairs_jackknife_xy_z(s1, s2, rp, pi, t1, t2, ns, period=per)
+        want = oracle.npairs_jackknife_xy_z(s1, s2, rp, pi, t1, t2, ns, period=per)
+        assert got.shape == want.shape == (ns + 1, len(rp), len(pi))
+        assert np.array_equal(got, want)                       # unit weights: exact halves
+    with pytest.raises(hb.HalotoolsError, match="jtags1 must be <= N_samples"):
+        hb.npairs_jackknife_xy_z(s1, s2, rp, pi, t1 + 1, t2, ns, period=L)
+    with pytest.raises(hb.HalotoolsError, match="weights2 should have same len"):
+        hb.npairs_jackknife_3d(s1, s2, rp, t1, t2, ns, period=L, weights2=np.ones(5))

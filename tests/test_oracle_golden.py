@@ -8,7 +8,8 @@ from oracle import oracle, ref_engines
 from tests.golden import cases
 
 ENGINE_FUNCS = ("npairs_3d", "npairs_xy_z", "npairs_s_mu", "marked_npairs_3d", "mean_delta_sigma",
-                "npairs_projected", "npairs_per_object_3d", "marked_npairs_xy_z", "weighted_npairs_xy")
+                "npairs_projected", "npairs_per_object_3d", "marked_npairs_xy_z", "weighted_npairs_xy",
+                "npairs_jackknife_3d", "npairs_jackknife_xy_z")
 ENGINE_CASES = [n for n in cases.names() if cases._cases()[n][0] in ENGINE_FUNCS and n != "n3d_c1_full"]
 
 
@@ -29,7 +30,8 @@ def test_oracle_matches_reference_golden(name, golden):
         if fn in ("npairs_3d", "npairs_xy_z", "npairs_s_mu", "npairs_projected", "npairs_per_object_3d"):
             assert g.dtype == np.int64
             assert np.array_equal(g, w)
-        elif fn in ("marked_npairs_3d", "marked_npairs_xy_z", "weighted_npairs_xy"):
+        elif fn in ("marked_npairs_3d", "marked_npairs_xy_z", "weighted_npairs_xy", "npairs_jackknife_3d",
+                    "npairs_jackknife_xy_z"):
             assert np.allclose(g, w, rtol=1e-12, atol=0)
         else:
             # Delta Sigma is a cancelling difference: abs + rel tolerance
