@@ -2,5 +2,6 @@ from .tpcf import tpcf
 from .wp import wp
 from .rp_pi_tpcf import rp_pi_tpcf
 from .marked_tpcf import marked_tpcf
+from .tpcf_jackknife import tpcf_jackknife, wp_jackknife
 
-__all__ = ("tpcf", "wp", "rp_pi_tpcf", "marked_tpcf")
+__all__ = ("tpcf", "wp", "rp_pi_tpcf", "marked_tpcf", "tpcf_jackknife", "wp_jackknife")

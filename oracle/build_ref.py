@@ -76,7 +76,7 @@ TRIMMED_INITS = {
         "from .array_utils import *\nfrom .array_indexing_manipulations import *\n",
     "halotools/mock_observables/__init__.py":
         "from .pair_counters import *\n"
-        "from .two_point_clustering import tpcf, wp, rp_pi_tpcf, marked_tpcf\n"
+        "from .two_point_clustering import tpcf, wp, rp_pi_tpcf, marked_tpcf, tpcf_jackknife, wp_jackknife\n"
         "from .surface_density import mean_delta_sigma, weighted_npairs_xy\n",
     "halotools/mock_observables/pair_counters/__init__.py":
         "from .rectangular_mesh import RectangularDoubleMesh\n"
@@ -103,10 +103,17 @@ TRIMMED_INITS = {
         "from .marked_npairs_xy_z_engine import marked_npairs_xy_z_engine\n",
     "halotools/mock_observables/two_point_clustering/__init__.py":
         "from .wp import wp\nfrom .rp_pi_tpcf import rp_pi_tpcf\n"
-        "from .tpcf import tpcf\nfrom .marked_tpcf import marked_tpcf\n",
+        "from .tpcf import tpcf\nfrom .marked_tpcf import marked_tpcf\n"
+        "from .tpcf_jackknife import tpcf_jackknife\nfrom .wp_jackknife import wp_jackknife\n",
     "halotools/mock_observables/surface_density/__init__.py":
         "from .mean_delta_sigma import mean_delta_sigma\n"
         "from .weighted_npairs_xy import weighted_npairs_xy\n",
+    # catalog_analysis_helpers.py (cuboid_subvolume_labels, used by the jackknife statistics) imports two names from
+    # sub-packages that need astropy; neither is touched by the functions run here
+    "halotools/empirical_models/__init__.py":
+        "def enforce_periodicity_of_box(*args, **kwargs):\n    raise NotImplementedError('not part of the hot path')\n",
+    "halotools/sim_manager/__init__.py": "",
+    "halotools/sim_manager/sim_defaults.py": "default_cosmology = None\ndefault_redshift = 0.0\n",
     "halotools/mock_observables/surface_density/engines/__init__.py":
         "from .mean_delta_sigma_engine import mean_delta_sigma_engine\n"
         "from .weighted_npairs_xy_engine import weighted_npairs_xy_engine\n",
@@ -137,6 +144,7 @@ def _prepare_scratch():
     shutil.copy(os.path.join(REF_ROOT, "halotools", "custom_exceptions.py"),
                 os.path.join(SRC, "halotools", "custom_exceptions.py"))
     for rel, text in TRIMMED_INITS.items():
+        os.makedirs(os.path.dirname(os.path.join(SRC, rel)), exist_ok=True)
         with open(os.path.join(SRC, rel), "w") as f:
             f.write(text)
     os.makedirs(os.path.join(SRC, "astropy", "utils"))

@@ -209,6 +209,16 @@ def _cases():
                            dict(period=1.0, weights1=w1j, weights2=w2j))
     C["jkxyz_wp_like"] = ("npairs_jackknife_xy_z", (s5, "same", np.logspace(-1, np.log10(20), 12), np.array([0.0, 40.0]),
                                                     jt(74, 5000, 8), jt(74, 5000, 8), 8), dict(period=250.0))
+    # jackknife statistics (fixture shapes: two_point_clustering/tests/test_tpcf_jackknife.py, test_wp_jackknife.py)
+    ranj = pts(75, 4000)
+    C["tpcf_jk_auto"] = ("tpcf_jackknife", (s1, ranj, rb2), dict(Nsub=3, period=1.0))
+    C["tpcf_jk_cross_ls"] = ("tpcf_jackknife", (s1, ranj, rb2),
+                             dict(Nsub=[2, 3, 2], sample2=s2, period=1.0, estimator="Landy-Szalay"))
+    C["tpcf_jk_nonperiodic"] = ("tpcf_jackknife", (s1, ranj, rb2), dict(Nsub=2, period=None, estimator="Landy-Szalay"))
+    C["tpcf_jk_randoms_by_number"] = ("tpcf_jackknife", (s1, [3000], rb2), dict(Nsub=2, period=1.0, seed=43))
+    C["wp_jk_auto"] = ("wp_jackknife", (s1, ranj, rpw, 0.2), dict(Nsub=3, period=1.0))
+    C["wp_jk_cross"] = ("wp_jackknife", (s1, ranj, rpw, 0.15),
+                        dict(Nsub=2, sample2=s2, period=1.0, estimator="Landy-Szalay", do_auto=False))
     return C
 
 

@@ -261,3 +261,35 @@ def test_pbc_check_messages_on_large_samples():
     with pytest.raises(ValueError) as err:
         enforce_sample_respects_pbcs(s[:, 0], s[:, 1], s[:, 2], [10.0, 10.0, 10.0])
     assert "zperiod" in str(err.value)
+
+
+def test_cuboid_subvolume_labels_and_jackknife_argument_errors():
+    """catalog_analysis_helpers.py:330-421 semantics; tpcf_jackknife.py:601-634 / npairs_jackknife_3d.py:199-262 errors"""
+    from halotools_b200.catalog_analysis_helpers import cuboid_subvolume_labels
+    from halotools_b200.two_point_clustering.tpcf_jackknife import (get_subvolume_numbers, _tpcf_jackknife_process_args,
+                                                                    _enclose_in_box)
+    from halotools_b200.pair_counters.npairs_jackknife_3d import _process_weights_jtags
+    pts = np.array([[0.0, 0.0, 0.0], [0.99, 0.99, 0.99], [1.0, 1.0, 1.0], [0.5, 0.0, 0.26], [0.24, 0.6, 0.9]])
+    labels, n = cuboid_subvolume_labels(pts, [2, 2, 4], 1.0)
+    assert n == 16 and list(labels) == [1, 16, 16, 10, 8]
+    assert list(get_subvolume_numbers(labels, n)) == [1, 0, 0, 0, 0, 0, 0, 1, 0, 1, 0, 0, 0, 0, 0, 2]
+    with pytest.raises(TypeError):
+        cuboid_subvolume_labels(pts[:, :2], 2, 1.0)
+    with pytest.raises(HalotoolsError, match="true randoms"):
+        _tpcf_jackknife_process_args(S, [100], np.array([0.1, 0.2]), 2, None, None, True, True, "Natural", 1, None)
+    with pytest.raises(HalotoolsError, match="Nsub"):
+        _tpcf_jackknife_process_args(S, S, np.array([0.1, 0.2]), [0, 1, 1], None, 1.0, True, True, "Natural", 1, None)
+    out = _tpcf_jackknife_process_args(S, [50], np.array([0.1, 0.2]), 2, None, 1.0, True, True, "Natural", 1, 43)
+    assert out[4].shape == (50, 3) and np.all(out[4] <= 1.0)
+    again = _tpcf_jackknife_process_args(S, [50], np.array([0.1, 0.2]), 2, None, 1.0, True, True, "Natural", 1, 43)
+    assert np.array_equal(out[4], again[4])
+    a, b, c, L = _enclose_in_box(S + 3.0, S + 4.0, S + 2.0)
+    assert np.isclose(c.min(), 0.0) and np.all(L == L[0]) and L[0] >= b.max()
+    tags = np.random.RandomState(1).randint(1, 5, len(S))
+    with pytest.raises(HalotoolsError, match="jtags1 must be >= 1"):
+        _process_weights_jtags(S, S, None, None, tags - 1, tags, 4)
+    with pytest.raises(HalotoolsError, match="jtags2 should have same len"):
+        _process_weights_jtags(S, S, None, None, tags, tags[:5], 4)
+    with pytest.warns(UserWarning, match="every jackknife sample"):
+        w1, w2, t1, t2 = _process_weights_jtags(S, S, None, None, np.ones(len(S), dtype=int), tags, 4)
+    assert w1.dtype == np.float64 and np.all(w1 == 1.0) and t1.dtype.kind == "i"
