@@ -29,7 +29,7 @@ EXPORTS = (
     "htb_npairs_3d_engine", "htb_npairs_xy_z_engine", "htb_npairs_s_mu_engine",
     "htb_marked_npairs_3d_engine", "htb_mean_delta_sigma_engine",
     "htb_marked_npairs_xy_z_engine", "htb_npairs_per_object_3d_engine", "htb_weighted_npairs_xy_engine",
-    "htb_npairs_jackknife_3d_engine", "htb_npairs_jackknife_xy_z_engine",
+    "htb_npairs_jackknife_3d_engine", "htb_npairs_jackknife_xy_z_engine", "htb_weighted_npairs_per_object_xy_engine",
     "htb_mesh_cell_ids", "htb_mesh_cell_id_indices", "htb_cell1_work", "htb_measure_fp64_rate",
     "htb_host_minmax", "htb_device_minmax",
 )

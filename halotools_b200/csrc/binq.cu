@@ -7,6 +7,8 @@
 //   MODE 1  weighted sums  marked_npairs_xy_z / marked_npairs_3d with general marks / weighted_npairs_xy
 //                          marked_npairs_xy_z_engine.pyx:209-225, marked_npairs_3d_engine.pyx:204-216
 //   MODE 2  per-object     npairs_per_object_3d                         npairs_per_object_3d_engine.pyx:190-207
+//   MODE 4  per-object weighted rows (weight = sample2's w2[0]), input order
+//                          weighted_npairs_per_object_xy_engine.pyx:150-185
 //   MODE 3  per-object weighted sums folded by the point's jackknife tag (payload rows {weight, tag})
 //                          npairs_jackknife_3d_engine.pyx:213-233, npairs_jackknife_xy_z_engine.pyx:222-246
 // The hot loop only DECIDES whether a pair can be inside the top edge(s): the reference's strict f64 separation
@@ -35,8 +37,8 @@ __device__ __forceinline__ unsigned long long bq_lds_u64(uint32_t addr)
 
 template <int KIND, int MODE>
 struct BinQ {
-    static constexpr int DIM = KIND == 3 ? 2 : 3, NPAY = MODE == 1 ? HTB_MAX_NW : (MODE == 3 ? 2 : 0), PPL = 2, WARPS = 8,
-                         MINBLOCKS = MODE == 3 ? 1 : 2;
+    static constexpr int DIM = KIND == 3 ? 2 : 3, NPAY = MODE == 1 ? HTB_MAX_NW : (MODE == 3 ? 2 : (MODE == 4 ? 1 : 0)), PPL = 2, WARPS = 8,
+                         MINBLOCKS = MODE >= 3 ? 1 : 2;
     static constexpr bool TMA = true;
     typedef BinQParams Params;
     const Params &P;
@@ -74,13 +76,14 @@ struct BinQ {
         e_s = smem_u32(e);
         lut_s[0] = e_s + 8u * (uint32_t)ne;
         lut_s[1] = lut_s[0] + (uint32_t)((P.T[0] + 7) & ~7);
-        rstride = MODE == 3 ? ((P.n0 * P.n1) | 1) : (P.n0 | 1);
+        rstride = MODE >= 3 ? ((P.n0 * P.n1) | 1) : (P.n0 | 1);
         vmask = 0;
         for (int k = lane; k < ne + nl; k += 32) e[k] = P.edges[k];
         if (MODE == 0) { for (int k = lane; k < P.n0 * P.n1; k += 32) hist[k] = 0; }
         else if (MODE == 1) { for (int k = lane; k < P.n0 * P.n1; k += 32) fhist[k] = 0.0; }
         else if (MODE == 2) { for (int k = lane; k < 64 * rstride; k += 32) hist[k] = 0; }
         else { for (int k = lane; k < 64 * rstride; k += 32) fhist[k] = 0.0; }
+        tag[0] = tag[1] = 0;
         x0 = y0 = z0 = x1 = y1 = z1 = 0.0;
         xs0 = ys0 = zs0 = xs1 = ys1 = zs1 = 0.0;
         __syncwarp();
@@ -210,10 +213,14 @@ struct BinQ {
                 // rows are private to the lane's points: plain read-modify-write
                 if (h0 >= 0) hist[lane * rstride + h0] += 1u;
                 if (h1 >= 0) hist[(32 + lane) * rstride + h1] += 1u;
-            } else {
+            } else if (MODE == 3) {
                 // jweight's w1 * w2 (npairs_jackknife_3d_engine.pyx:283-289), summed per lane point and differential cell
                 if (h0 >= 0) fhist[lane * rstride + h0] += wa[0] * lds_f64(bw + 16 * j0);
                 if (h1 >= 0) fhist[(32 + lane) * rstride + h1] += wb[0] * lds_f64(bw + 16 * j1);
+            } else {
+                // weighted_npairs_per_object_xy_engine.pyx:167-173: the weight is w2[j]
+                if (h0 >= 0) fhist[lane * rstride + h0] += lds_f64(bw + 8 * j0);
+                if (h1 >= 0) fhist[(32 + lane) * rstride + h1] += lds_f64(bw + 8 * j1);
             }
         }
     }
@@ -269,6 +276,20 @@ struct BinQ {
                 const double h = fhist[k];
                 if (h != 0.0) { atomicAdd(P.fcounts + k, wt == 2u ? h + h : h); fhist[k] = 0.0; }
             }
+        } else if (MODE == 4) {
+            // per object: cumulative over the edges, rows in input order (weighted_npairs_per_object_xy_engine.pyx:175-185)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                if (!((vmask >> q) & 1u)) continue;
+                double *row = P.fcounts + (size_t)P.perm1[idx[q]] * (size_t)nh;
+                double *r = fhist + (q * 32 + lane) * rstride;
+                double cum = 0.0;
+                for (int k = 0; k < nh; ++k) {
+                    cum += r[k];
+                    r[k] = 0.0;
+                    if (cum != 0.0) atomicAdd(row + k, cum);
+                }
+            }
         } else if (MODE == 3) {
             // fold the rows of this lane's points into the table row of their jackknife tag (differential cells)
 #pragma unroll
@@ -315,6 +336,7 @@ int htb_launch_binq(cudaStream_t st, int kind, int mode, const WalkGeom &G, cons
     case 8: return launch_count<BinQ<0, 2>>(st, G, A, P, l);
     case 12: return launch_count<BinQ<0, 3>>(st, G, A, P, l);
     case 13: return launch_count<BinQ<1, 3>>(st, G, A, P, l);
+    case 19: return launch_count<BinQ<3, 4>>(st, G, A, P, l);
     }
     htb_set_error("unknown BinQ kind %d / mode %d", kind, mode);
     return 1;

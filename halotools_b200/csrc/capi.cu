@@ -1165,6 +1165,41 @@ extern "C" int htb_weighted_npairs_xy_engine(const htb_mesh_geom *mesh,
     HTB_GUARD_END
 }
 
+// ------------------------------------------------------------------ weighted_npairs_per_object_xy (2-D mesh)
+extern "C" int htb_weighted_npairs_per_object_xy_engine(const htb_mesh_geom *mesh,
+                                                        const double *x1, const double *y1, int64_t stride1, int64_t n1,
+                                                        const double *x2, const double *y2, int64_t stride2, int64_t n2,
+                                                        const double *w2, const double *rp_bins, int32_t nrp,
+                                                        int64_t first_cell1, int64_t last_cell1,
+                                                        double *counts_out, uint32_t flags, htb_stats *stats)
+{
+    HTB_GUARD_BEGIN
+    if (!mesh || !rp_bins || !counts_out || nrp < 1 || !w2) { htb_set_error("htb_weighted_npairs_per_object_xy_engine: bad arguments"); return 1; }
+    if (mesh->ndim != 2) { htb_set_error("htb_weighted_npairs_per_object_xy_engine needs a 2-d mesh"); return 1; }
+    if (nrp > 48) { htb_set_error("htb_weighted_npairs_per_object_xy_engine: at most 48 rp_bins (per-point shared-memory rows)"); return 1; }
+    std::vector<double> e((size_t)nrp);
+    for (int k = 0; k < nrp; ++k) e[k] = rp_bins[k] * rp_bins[k];
+    suffix_min(e, 0, nrp);
+    if (!binq_ok(e.data(), nrp, nullptr, 1, flags & ~HTB_FLAG_GENERIC)) { htb_set_error("htb_weighted_npairs_per_object_xy_engine: rp_bins must be finite"); return 1; }
+    Call c;
+    if (c.begin()) return 1;
+    const double *c1[3] = {x1, y1, nullptr}, *c2[3] = {x2, y2, nullptr};
+    if (c.setup(mesh, 1, false, c1, stride1, n1, nullptr, c2, stride2, n2, w2, 1, true, first_cell1, last_cell1, flags)) return 1;
+    BinQParams bp{};
+    if (binq_prepare(c, e.data(), nrp, nullptr, 1, &bp)) return 1;
+    const size_t nout = (size_t)(n1 > 0 ? n1 : 1) * (size_t)nrp;
+    double *rows = nullptr;
+    if (c.ws.alloc((void **)&rows, sizeof(double) * nout)) return 1;
+    HTB_CUDA(cudaMemsetAsync(rows, 0, sizeof(double) * nout, c.st));
+    bp.fcounts = rows;
+    bp.perm1 = c.s1.perm;
+    bp.nw = 1; bp.wfunc = -1;
+    if (htb_launch_binq(c.st, 3, 4, c.G, c.A, bp, &c.launches)) return 1;
+    if (n1 > 0) HTB_CUDA(cudaMemcpyAsync(counts_out, rows, sizeof(double) * (size_t)n1 * nrp, cudaMemcpyDeviceToHost, c.st));
+    return c.finish(stats, 3);
+    HTB_GUARD_END
+}
+
 // ------------------------------------------------------------------ npairs_per_object_3d
 extern "C" int htb_npairs_per_object_3d_engine(const htb_mesh_geom *mesh,
                                                const double *x1, const double *y1, const double *z1, int64_t stride1, int64_t n1,

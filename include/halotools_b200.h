@@ -172,6 +172,16 @@ int htb_weighted_npairs_xy_engine(const htb_mesh_geom *mesh,
                                   int64_t first_cell1, int64_t last_cell1,
                                   double *counts_out, uint32_t flags, htb_stats *stats);
 
+/* weighted_npairs_per_object_xy_engine.pyx:17 (surface_density/engines/) - 2-D mesh: counts[i,k] = sum w2_j over the
+ * sample2 points with dx^2+dy^2 <= rp[k]^2 of sample1 point i, f64[n1*nrp], rows in the INPUT order of sample1
+ * (:150-190; the counter under total_mass_enclosed_per_cylinder, mass_in_cylinders.py:222).  nrp <= 48.            */
+int htb_weighted_npairs_per_object_xy_engine(const htb_mesh_geom *mesh,
+                                             const double *x1, const double *y1, int64_t stride1, int64_t n1,
+                                             const double *x2, const double *y2, int64_t stride2, int64_t n2,
+                                             const double *w2, const double *rp_bins, int32_t nrp,
+                                             int64_t first_cell1, int64_t last_cell1,
+                                             double *counts_out, uint32_t flags, htb_stats *stats);
+
 /* npairs_jackknife_3d_engine.pyx:20 (cpairs/) - counts[s,k] = sum over pairs with dsq <= rbins[k]^2 of
  * jweight(s, jtag1_i, jtag2_j, w1_i, w2_j) (:237-291): s = 0 is the full sample, s >= 1 leaves sub-volume s out.
  * w1, w2: one weight per point; jtags1, jtags2: int64 tags in [1, N_samples]; output f64[(N_samples+1)*nb].

@@ -48,6 +48,7 @@ ENGINES = [
     "halotools/mock_observables/pair_counters/cpairs/npairs_per_object_3d_engine",
     "halotools/mock_observables/pair_counters/marked_cpairs/marked_npairs_xy_z_engine",
     "halotools/mock_observables/surface_density/engines/weighted_npairs_xy_engine",
+    "halotools/mock_observables/surface_density/engines/weighted_npairs_per_object_xy_engine",
     # SURVEY section 8(f) rank 3
     "halotools/mock_observables/pair_counters/cpairs/npairs_jackknife_3d_engine",
     "halotools/mock_observables/pair_counters/cpairs/npairs_jackknife_xy_z_engine",
@@ -77,7 +78,9 @@ TRIMMED_INITS = {
     "halotools/mock_observables/__init__.py":
         "from .pair_counters import *\n"
         "from .two_point_clustering import tpcf, wp, rp_pi_tpcf, marked_tpcf, tpcf_jackknife, wp_jackknife\n"
-        "from .surface_density import mean_delta_sigma, weighted_npairs_xy\n",
+        "from .surface_density import mean_delta_sigma, weighted_npairs_xy\n"
+        "from .surface_density.weighted_npairs_per_object_xy import weighted_npairs_per_object_xy\n"
+        "from .surface_density.mass_in_cylinders import total_mass_enclosed_per_cylinder\n",
     "halotools/mock_observables/pair_counters/__init__.py":
         "from .rectangular_mesh import RectangularDoubleMesh\n"
         "from .rectangular_mesh_2d import RectangularDoubleMesh2D\n"
@@ -116,7 +119,8 @@ TRIMMED_INITS = {
     "halotools/sim_manager/sim_defaults.py": "default_cosmology = None\ndefault_redshift = 0.0\n",
     "halotools/mock_observables/surface_density/engines/__init__.py":
         "from .mean_delta_sigma_engine import mean_delta_sigma_engine\n"
-        "from .weighted_npairs_xy_engine import weighted_npairs_xy_engine\n",
+        "from .weighted_npairs_xy_engine import weighted_npairs_xy_engine\n"
+        "from .weighted_npairs_per_object_xy_engine import weighted_npairs_per_object_xy_engine\n",
 }
 
 # written into oracle/_ref so the engines import without the reference tree

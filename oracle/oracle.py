@@ -325,7 +325,7 @@ def marked_npairs_xy_z(sample1, sample2, rp_bins, pi_bins, period=None, weights1
 
 
 def weighted_npairs_xy(sample1, sample2, sample2_mass, rp_bins, period=None, approx_cell1_size=None,
-                       approx_cell2_size=None, cell1_range=None):
+                       approx_cell2_size=None, cell1_range=None, per_object=False):
     sample1 = np.asarray(sample1, dtype=np.float64)
     sample2 = np.asarray(sample2, dtype=np.float64)
     rp_bins = _f8(np.atleast_1d(rp_bins))
@@ -346,11 +346,43 @@ def weighted_npairs_xy(sample1, sample2, sample2_mass, rp_bins, period=None, app
     w2 = _f8(np.asarray(sample2_mass, dtype=np.float64)[dm.mesh2.idx_sorted])
     g = _geom(dm)
     first, last = _range(dm, cell1_range)
+    if per_object:
+        n1 = len(x1)
+        rows = np.zeros((n1, len(rp_bins)), dtype=np.float64)
+        lib().oracle_weighted_npairs_per_object_xy(
+            ctypes.byref(g), _p(x1), _p(y1), _p(dm.mesh1.cell_id_indices, ctypes.c_int64), ctypes.c_int64(n1),
+            _p(x2), _p(y2), _p(w2), _p(dm.mesh2.cell_id_indices, ctypes.c_int64),
+            _p(rp_bins), ctypes.c_int(len(rp_bins)), ctypes.c_int64(first), ctypes.c_int64(last), _p(rows))
+        unsort = np.empty(n1, dtype=np.int64)
+        unsort[dm.mesh1.idx_sorted] = np.arange(n1)
+        return rows[unsort, :]
     out = np.zeros(len(rp_bins), dtype=np.float64)
     lib().oracle_weighted_npairs_xy(ctypes.byref(g), _p(x1), _p(y1), _p(dm.mesh1.cell_id_indices, ctypes.c_int64),
                                     _p(x2), _p(y2), _p(w2), _p(dm.mesh2.cell_id_indices, ctypes.c_int64),
                                     _p(rp_bins), ctypes.c_int(len(rp_bins)), ctypes.c_int64(first), ctypes.c_int64(last),
                                     _p(out))
+    return out
+
+
+def weighted_npairs_per_object_xy(sample1, sample2, sample2_mass, rp_bins, period=None, approx_cell1_size=None,
+                                  approx_cell2_size=None, cell1_range=None):
+    """weighted_npairs_per_object_xy.py:113-152 (same front-end logic as weighted_npairs_xy)"""
+    return weighted_npairs_xy(sample1, sample2, sample2_mass, rp_bins, period=period,
+                              approx_cell1_size=approx_cell1_size, approx_cell2_size=approx_cell2_size,
+                              cell1_range=cell1_range, per_object=True)
+
+
+def total_mass_enclosed_per_cylinder(centers, particles, particle_masses, downsampling_factor, rp_bins, period,
+                                     approx_cell1_size=None, approx_cell2_size=None):
+    """mass_in_cylinders.py:211-231"""
+    particles = np.asarray(particles, dtype=np.float64)
+    m = np.atleast_1d(np.asarray(particle_masses, dtype=np.float64))
+    if len(m) == 1:
+        m = np.zeros(particles.shape[0]) + m[0]
+    mean = np.mean(m)
+    out = weighted_npairs_per_object_xy(centers, particles, m / mean, rp_bins, period=_triple(period)[:2],
+                                        approx_cell1_size=approx_cell1_size, approx_cell2_size=approx_cell2_size)
+    out *= downsampling_factor * mean
     return out
 
 

@@ -554,18 +554,44 @@ void oracle_marked_npairs_xy_z(const oracle_geom_t *g,
 }
 
 /* 2-D mesh (cell id = ix*ny + iy), weighted_npairs_xy_engine.pyx:95-175 */
+static void weighted_xy_loop(const oracle_geom_t *g,
+                             const double *x1, const double *y1, const int64_t *off1,
+                             const double *x2, const double *y2, const double *w2, const int64_t *off2,
+                             const double *rp_bins, int nrp, int64_t first_cell1, int64_t last_cell1,
+                             double *counts_out, double *rows_out);
+
 void oracle_weighted_npairs_xy(const oracle_geom_t *g,
                                const double *x1, const double *y1, const int64_t *off1,
                                const double *x2, const double *y2, const double *w2, const int64_t *off2,
                                const double *rp_bins, int nrp, int64_t first_cell1, int64_t last_cell1,
                                double *counts_out)
 {
+    for (int k = 0; k < nrp; ++k) counts_out[k] = 0.0;
+    weighted_xy_loop(g, x1, y1, off1, x2, y2, w2, off2, rp_bins, nrp, first_cell1, last_cell1, counts_out, NULL);
+}
+
+/* weighted_npairs_per_object_xy_engine.pyx:95-190: rows_out is (n1, nrp) in SORTED sample1 order (the wrapper un-sorts) */
+void oracle_weighted_npairs_per_object_xy(const oracle_geom_t *g,
+                                          const double *x1, const double *y1, const int64_t *off1, int64_t n1,
+                                          const double *x2, const double *y2, const double *w2, const int64_t *off2,
+                                          const double *rp_bins, int nrp, int64_t first_cell1, int64_t last_cell1,
+                                          double *rows_out)
+{
+    for (int64_t k = 0; k < n1 * nrp; ++k) rows_out[k] = 0.0;
+    weighted_xy_loop(g, x1, y1, off1, x2, y2, w2, off2, rp_bins, nrp, first_cell1, last_cell1, NULL, rows_out);
+}
+
+static void weighted_xy_loop(const oracle_geom_t *g,
+                             const double *x1, const double *y1, const int64_t *off1,
+                             const double *x2, const double *y2, const double *w2, const int64_t *off2,
+                             const double *rp_bins, int nrp, int64_t first_cell1, int64_t last_cell1,
+                             double *counts_out, double *rows_out)
+{
     double *rpsq = squares(rp_bins, nrp);
     const int ny1 = g->ndivs1[1], ny2 = g->ndivs2[1];
     const int perx = g->ndivs2[0] / g->ndivs1[0], pery = ny2 / ny1;
     const int mw = max_window(g);
     nbr_t *wx = (nbr_t *)malloc(sizeof(nbr_t) * mw * 2), *wy = wx + mw;
-    for (int k = 0; k < nrp; ++k) counts_out[k] = 0.0;
     for (int64_t c1 = first_cell1; c1 < last_cell1; ++c1) {
         const int64_t a = off1[c1], b = off1[c1 + 1];
         if (b <= a) continue;
@@ -586,7 +612,8 @@ void oracle_weighted_npairs_xy(const oracle_geom_t *g,
                     const double dxy_sq = dx * dx + dy * dy;
                     const double w2tmp = w2[j];
                     int k = nrp - 1;
-                    while (dxy_sq <= rpsq[k]) { counts_out[k] += w2tmp; if (--k < 0) break; }
+                    double *dst = rows_out ? rows_out + i * nrp : counts_out;
+                    while (dxy_sq <= rpsq[k]) { dst[k] += w2tmp; if (--k < 0) break; }
                 }
             }
         }

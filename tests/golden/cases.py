@@ -219,6 +219,15 @@ def _cases():
     C["wp_jk_auto"] = ("wp_jackknife", (s1, ranj, rpw, 0.2), dict(Nsub=3, period=1.0))
     C["wp_jk_cross"] = ("wp_jackknife", (s1, ranj, rpw, 0.15),
                         dict(Nsub=2, sample2=s2, period=1.0, estimator="Landy-Szalay", do_auto=False))
+    C["wpoxy_periodic"] = ("weighted_npairs_per_object_xy", (g2a, g2b, mass2, np.logspace(-1, 1.5, 15)),
+                           dict(period=[450.0, 450.0]))
+    C["wpoxy_nonperiodic"] = ("weighted_npairs_per_object_xy", (g2a, g2b, mass2, np.logspace(-0.5, 1.3, 9)), dict(period=None))
+    cen3, ptc3 = pts(43, 800, 250.0), pts(44, 30000, 250.0)
+    C["mass_per_cylinder"] = ("total_mass_enclosed_per_cylinder",
+                              (cen3, ptc3, np.random.RandomState(48).uniform(0.5, 2.0, 30000), 2.5,
+                               np.logspace(-1, 1.2, 10), 250.0), dict())
+    C["mass_per_cylinder_scalar"] = ("total_mass_enclosed_per_cylinder",
+                                     (cen3, ptc3, 3.0e9, 1.0, np.logspace(-1, 1.2, 10), [250.0, 250.0, 250.0]), dict())
     return C
 
 

@@ -33,7 +33,8 @@ def compare(fn, got, want):
         if fn in INT_FUNCS:
             assert g.dtype == np.int64
             assert np.array_equal(g, w), (g, w)
-        elif fn in ("marked_npairs_3d", "marked_npairs_xy_z", "weighted_npairs_xy"):
+        elif fn in ("marked_npairs_3d", "marked_npairs_xy_z", "weighted_npairs_xy", "weighted_npairs_per_object_xy",
+                    "total_mass_enclosed_per_cylinder"):
             # float sums, order differs from the reference's serial loop: 1e-12 relative (north_star)
             assert np.allclose(g, w, rtol=1e-12, atol=0), (g, w)
         elif fn in ("npairs_jackknife_3d", "npairs_jackknife_xy_z"):
@@ -767,3 +768,25 @@ def test_npairs_jackknife_xy_z_vs_oracle_and_errors():
         hb.npairs_jackknife_xy_z(s1, s2, rp, pi, t1 + 1, t2, ns, period=L)
     with pytest.raises(hb.HalotoolsError, match="weights2 should have same len"):
         hb.npairs_jackknife_3d(s1, s2, rp, t1, t2, ns, period=L, weights2=np.ones(5))
+
+
+def test_weighted_npairs_per_object_xy_vs_oracle():
+    rng = np.random.RandomState(37)
+    L = 300.0
+    g = rng.uniform(0, L, (6000, 2))
+    p = np.vstack([g[:1000], rng.uniform(0, L, (60000, 2))])
+    m = rng.uniform(0.0, 2.0, len(p))
+    rp = np.logspace(-1, np.log10(25.0), 14)
+    got = hb.weighted_npairs_per_object_xy(g, p, m, rp, period=L)
+    assert _lib.last_stats["path"] == 3
+    want = oracle.weighted_npairs_per_object_xy(g, p, m, rp, period=L)
+    assert got.shape == want.shape == (len(g), len(rp))
+    # each row sums <= a few thousand terms: 1e-12 relative, exact zeros stay zero
+    assert np.allclose(got, want, rtol=1e-12, atol=0), np.nanmax(np.abs(got / want - 1))
+    assert np.allclose(got.sum(axis=0), hb.weighted_npairs_xy(g, p, m, rp, period=L), rtol=1e-11)
+    ints = rng.randint(1, 5, len(p)).astype(float)
+    assert np.array_equal(hb.weighted_npairs_per_object_xy(g, p, ints, rp, period=L),
+                          oracle.weighted_npairs_per_object_xy(g, p, ints, rp, period=L))
+    sub = rng.permutation(len(g))[:300]
+    assert np.array_equal(hb.weighted_npairs_per_object_xy(g[sub], p, ints, rp, period=L),
+                          hb.weighted_npairs_per_object_xy(g, p, ints, rp, period=L)[sub])

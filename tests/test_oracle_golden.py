@@ -9,6 +9,7 @@ from tests.golden import cases
 
 ENGINE_FUNCS = ("npairs_3d", "npairs_xy_z", "npairs_s_mu", "marked_npairs_3d", "mean_delta_sigma",
                 "npairs_projected", "npairs_per_object_3d", "marked_npairs_xy_z", "weighted_npairs_xy",
+                "weighted_npairs_per_object_xy", "total_mass_enclosed_per_cylinder",
                 "npairs_jackknife_3d", "npairs_jackknife_xy_z")
 ENGINE_CASES = [n for n in cases.names() if cases._cases()[n][0] in ENGINE_FUNCS and n != "n3d_c1_full"]
 
@@ -30,7 +31,7 @@ def test_oracle_matches_reference_golden(name, golden):
         if fn in ("npairs_3d", "npairs_xy_z", "npairs_s_mu", "npairs_projected", "npairs_per_object_3d"):
             assert g.dtype == np.int64
             assert np.array_equal(g, w)
-        elif fn in ("marked_npairs_3d", "marked_npairs_xy_z", "weighted_npairs_xy", "npairs_jackknife_3d",
+        elif fn in ("marked_npairs_3d", "marked_npairs_xy_z", "weighted_npairs_xy", "weighted_npairs_per_object_xy", "total_mass_enclosed_per_cylinder", "npairs_jackknife_3d",
                     "npairs_jackknife_xy_z"):
             assert np.allclose(g, w, rtol=1e-12, atol=0)
         else:
