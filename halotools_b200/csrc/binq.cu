@@ -9,6 +9,8 @@
 //   MODE 2  per-object     npairs_per_object_3d                         npairs_per_object_3d_engine.pyx:190-207
 //   MODE 4  per-object weighted rows (weight = sample2's w2[0]), input order
 //                          weighted_npairs_per_object_xy_engine.pyx:150-185
+//   MODE 5  MODE 4's lane-private rows, reduced over the warp at the end of the tile into ONE row (few bins: no
+//           shared-memory atomics in the replay)   weighted_npairs_xy_engine.pyx:150-175
 //   MODE 3  per-object weighted sums folded by the point's jackknife tag (payload rows {weight, tag})
 //                          npairs_jackknife_3d_engine.pyx:213-233, npairs_jackknife_xy_z_engine.pyx:222-246
 // The hot loop only DECIDES whether a pair can be inside the top edge(s): the reference's strict f64 separation
@@ -37,7 +39,7 @@ __device__ __forceinline__ unsigned long long bq_lds_u64(uint32_t addr)
 
 template <int KIND, int MODE>
 struct BinQ {
-    static constexpr int DIM = KIND == 3 ? 2 : 3, NPAY = MODE == 1 ? HTB_MAX_NW : (MODE == 3 ? 2 : (MODE == 4 ? 1 : 0)), PPL = 2, WARPS = 8,
+    static constexpr int DIM = KIND == 3 ? 2 : 3, NPAY = MODE == 1 ? HTB_MAX_NW : (MODE == 3 ? 2 : (MODE >= 4 ? 1 : 0)), PPL = 2, WARPS = 8,
                          MINBLOCKS = MODE >= 3 ? 1 : 2;
     static constexpr bool TMA = true;
     typedef BinQParams Params;
@@ -276,6 +278,20 @@ struct BinQ {
                 const double h = fhist[k];
                 if (h != 0.0) { atomicAdd(P.fcounts + k, wt == 2u ? h + h : h); fhist[k] = 0.0; }
             }
+        } else if (MODE == 5) {
+            // one row for the whole call: sum the lanes' rows (differential cells), one atomic per cell and tile
+            for (int k = 0; k < nh; ++k) {
+                double v = 0.0;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    double *r = fhist + (q * 32 + lane) * rstride;
+                    if ((vmask >> q) & 1u) v += r[k];
+                    r[k] = 0.0;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(HTB_FULL, v, o);
+                if (lane == 0 && v != 0.0) atomicAdd(P.fcounts + k, v);
+            }
         } else if (MODE == 4) {
             // per object: cumulative over the edges, rows in input order (weighted_npairs_per_object_xy_engine.pyx:175-185)
 #pragma unroll
@@ -292,14 +308,29 @@ struct BinQ {
             }
         } else if (MODE == 3) {
             // fold the rows of this lane's points into the table row of their jackknife tag (differential cells)
+            // (sub-volumes are spatial: the points of a tile nearly always share one tag - then the rows are summed
+            // over the warp first and one lane adds them)
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-                if (!((vmask >> q) & 1u)) continue;
-                double *dst = P.fcounts + (size_t)tag[q] * (size_t)nh;
+                const bool v = ((vmask >> q) & 1u) != 0u;
+                const int tref = __shfl_sync(HTB_FULL, tag[q], q ? 31 : 0);      // slot 32 q lives in lane 0 (q = 0) / 31 (q = 1)
                 double *r = fhist + (q * 32 + lane) * rstride;
-                for (int k = 0; k < nh; ++k) {
-                    const double v = r[k];
-                    if (v != 0.0) { atomicAdd(dst + k, v); r[k] = 0.0; }
+                if (__all_sync(HTB_FULL, !v || tag[q] == tref)) {
+                    if (!__any_sync(HTB_FULL, v)) continue;
+                    double *dst = P.fcounts + (size_t)tref * (size_t)nh;
+                    for (int k = 0; k < nh; ++k) {
+                        double x = v ? r[k] : 0.0;
+                        r[k] = 0.0;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(HTB_FULL, x, o);
+                        if (lane == 0 && x != 0.0) atomicAdd(dst + k, x);
+                    }
+                } else if (v) {
+                    double *dst = P.fcounts + (size_t)tag[q] * (size_t)nh;
+                    for (int k = 0; k < nh; ++k) {
+                        const double x = r[k];
+                        if (x != 0.0) { atomicAdd(dst + k, x); r[k] = 0.0; }
+                    }
                 }
             }
         } else {
@@ -337,6 +368,7 @@ int htb_launch_binq(cudaStream_t st, int kind, int mode, const WalkGeom &G, cons
     case 12: return launch_count<BinQ<0, 3>>(st, G, A, P, l);
     case 13: return launch_count<BinQ<1, 3>>(st, G, A, P, l);
     case 19: return launch_count<BinQ<3, 4>>(st, G, A, P, l);
+    case 23: return launch_count<BinQ<3, 5>>(st, G, A, P, l);
     }
     htb_set_error("unknown BinQ kind %d / mode %d", kind, mode);
     return 1;

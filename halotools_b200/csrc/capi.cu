@@ -862,7 +862,7 @@ static int run_binq(Call &c, int kind, const double *e0, int n0, const double *e
 // double precision; the reference adds every pair's weight to each of its cumulative cells in turn
 // (marked_npairs_xy_z_engine.pyx:217-225), so the two agree to rounding (1e-16 relative per term).
 static int run_binq_weighted(Call &c, int kind, int nw, int wfunc, const double *e0, int n0, const double *e1, int n1,
-                             double *counts_out, htb_stats *stats)
+                             double *counts_out, htb_stats *stats, int mode = 1)
 {
     BinQParams bp{};
     if (binq_prepare(c, e0, n0, e1, n1, &bp)) return 1;
@@ -872,7 +872,7 @@ static int run_binq_weighted(Call &c, int kind, int nw, int wfunc, const double 
     HTB_CUDA(cudaMemsetAsync(sums_dev, 0, sizeof(double) * (size_t)nh, c.st));
     bp.fcounts = sums_dev;
     bp.nw = nw; bp.wfunc = wfunc;
-    if (htb_launch_binq(c.st, kind, 1, c.G, c.A, bp, &c.launches)) return 1;
+    if (htb_launch_binq(c.st, kind, mode, c.G, c.A, bp, &c.launches)) return 1;
     std::vector<double> diff((size_t)nh);
     HTB_CUDA(cudaMemcpyAsync(diff.data(), sums_dev, sizeof(double) * (size_t)nh, cudaMemcpyDeviceToHost, c.st));
     if (c.finish(stats, 3)) return 1;
@@ -1161,7 +1161,8 @@ extern "C" int htb_weighted_npairs_xy_engine(const htb_mesh_geom *mesh,
     if (c.begin()) return 1;
     const double *c1[3] = {x1, y1, nullptr}, *c2[3] = {x2, y2, nullptr};
     if (c.setup(mesh, 1, false, c1, stride1, n1, nullptr, c2, stride2, n2, w2, 1, false, first_cell1, last_cell1, flags)) return 1;
-    return run_binq_weighted(c, 3, 1, -1, e.data(), nrp, nullptr, 1, counts_out, stats);
+    // few bins: lane-private rows + a warp reduction per tile (MODE 5) instead of shared-memory atomics on a handful of cells
+    return run_binq_weighted(c, 3, 1, -1, e.data(), nrp, nullptr, 1, counts_out, stats, nrp <= 48 ? 5 : 1);
     HTB_GUARD_END
 }
 
@@ -1194,6 +1195,7 @@ extern "C" int htb_weighted_npairs_per_object_xy_engine(const htb_mesh_geom *mes
     bp.fcounts = rows;
     bp.perm1 = c.s1.perm;
     bp.nw = 1; bp.wfunc = -1;
+    c.G.maxslices = 1;
     if (htb_launch_binq(c.st, 3, 4, c.G, c.A, bp, &c.launches)) return 1;
     if (n1 > 0) HTB_CUDA(cudaMemcpyAsync(counts_out, rows, sizeof(double) * (size_t)n1 * nrp, cudaMemcpyDeviceToHost, c.st));
     return c.finish(stats, 3);
@@ -1227,6 +1229,7 @@ extern "C" int htb_npairs_per_object_3d_engine(const htb_mesh_geom *mesh,
     HTB_CUDA(cudaMemsetAsync(rows, 0, sizeof(unsigned long long) * nout, c.st));
     bp.rows = rows;
     bp.perm1 = c.s1.perm;
+    c.G.maxslices = 1;             // every row is written by one work item (no column slices: they would each add 64 x nb atomics)
     if (htb_launch_binq(c.st, 0, 2, c.G, c.A, bp, &c.launches)) return 1;
     if (n1 > 0) HTB_CUDA(cudaMemcpyAsync(counts_out, rows, sizeof(int64_t) * (size_t)n1 * nb, cudaMemcpyDeviceToHost, c.st));
     return c.finish(stats, 3);

@@ -94,13 +94,13 @@ def _run(entry, geom, cols1, cols2, weights1, weights2, jtags1, jtags2, N_sample
 def _process_weights_jtags(sample1, sample2, weights1, weights2, jtags1, jtags2, N_samples):
     """Same checks, defaults, errors and warnings as npairs_jackknife_3d.py:199-262."""
     if weights1 is None:
-        weights1 = np.array([1.0]*np.shape(sample1)[0], dtype=np.float64)
+        weights1 = np.ones(np.shape(sample1)[0], dtype=np.float64)
     else:
         weights1 = np.asarray(weights1).astype("float64")
         if np.shape(weights1)[0] != np.shape(sample1)[0]:
             raise HalotoolsError("weights1 should have same len as sample1")
     if weights2 is None:
-        weights2 = np.array([1.0]*np.shape(sample2)[0], dtype=np.float64)
+        weights2 = np.ones(np.shape(sample2)[0], dtype=np.float64)
     else:
         weights2 = np.asarray(weights2).astype("float64")
         if np.shape(weights2)[0] != np.shape(sample2)[0]:
@@ -122,10 +122,10 @@ def _process_weights_jtags(sample1, sample2, weights1, weights2, jtags1, jtags2,
     if np.max(jtags2) > N_samples:
         raise HalotoolsError("jtags2 must be <= N_samples")
 
-    # the reference tests jtags1 twice (npairs_jackknife_3d.py:256-259); the second message names sample2
-    if not np.array_equal(np.unique(jtags1), np.arange(1, N_samples+1)):
+    # the reference tests np.unique(jtags1) against 1..N_samples twice (npairs_jackknife_3d.py:256-259; the second
+    # message names sample2); with the bounds checked above that is "every tag occurs", decided here by a bincount
+    if not np.all(np.bincount(jtags1, minlength=N_samples + 1)[1:] > 0):
         warn("Warning: sample1 does not contain points in every jackknife sample.")
-    if not np.array_equal(np.unique(jtags1), np.arange(1, N_samples+1)):
         warn("Warning: sample2 does not contain points in every jackknife sample.")
 
     return weights1, weights2, jtags1, jtags2
