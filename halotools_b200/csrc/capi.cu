@@ -321,6 +321,66 @@ static int staged_upload(cudaStream_t st, const double *const *src, int cnt, int
     return 0;
 }
 
+// device -> host for large outputs into pageable memory (per-object tables): the same ring of pinned chunks, filled by
+// per-thread streams that wait for `st`, emptied by the host threads; returns when `dst` is complete
+static int staged_download(cudaStream_t st, const double *src_dev, double *dst, int64_t n)
+{
+    int dev = 0;
+    HTB_CUDA(cudaGetDevice(&dev));
+    if (stage_pool_init(dev, 1)) return 1;
+    StagePool &sp = g_stage[dev];
+    cudaEvent_t ready;
+    HTB_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    HTB_CUDA(cudaEventRecord(ready, st));
+    const int64_t nchunk = (n + HTB_STAGE_CHUNK - 1) / HTB_STAGE_CHUNK;
+    int nthreads = (int)std::min<int64_t>(HTB_STAGE_THREADS, nchunk);
+    const unsigned hw = std::thread::hardware_concurrency();
+    if (hw > 0 && (unsigned)nthreads > hw) nthreads = (int)hw;
+    std::atomic<int> failed(0);
+    auto work = [&](int t) {
+        if (cudaSetDevice(dev) != cudaSuccess) { failed = 1; return; }
+        if (cudaStreamWaitEvent(sp.st[t], ready, 0) != cudaSuccess) { failed = 1; return; }
+        int64_t prev = -1;
+        int k = 0;
+        auto drain = [&](int64_t c, int b) {
+            if (cudaEventSynchronize(sp.ev[t][b]) != cudaSuccess) { failed = 1; return; }
+            const int64_t i0 = c * HTB_STAGE_CHUNK;
+            const int64_t len = std::min<int64_t>(HTB_STAGE_CHUNK, n - i0);
+            memcpy(dst + i0, sp.pinned[t][b], sizeof(double) * (size_t)len);
+        };
+        for (int64_t c = t; c < nchunk; c += nthreads, ++k) {
+            const int b = k & 1;
+            const int64_t i0 = c * HTB_STAGE_CHUNK;
+            const int64_t len = std::min<int64_t>(HTB_STAGE_CHUNK, n - i0);
+            // buffer b was drained two chunks ago (or never used by this call); any earlier use has been synchronised
+            if (cudaMemcpyAsync(sp.pinned[t][b], src_dev + i0, sizeof(double) * (size_t)len, cudaMemcpyDeviceToHost, sp.st[t]) != cudaSuccess ||
+                cudaEventRecord(sp.ev[t][b], sp.st[t]) != cudaSuccess) { failed = 1; return; }
+            if (prev >= 0) drain(prev, b ^ 1);
+            if (failed) return;
+            prev = c;
+        }
+        if (prev >= 0) drain(prev, (k - 1) & 1);
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nthreads; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+    cudaEventDestroy(ready);
+    if (failed) { htb_set_error("staged device->host download failed: %s", cudaGetErrorString(cudaGetLastError())); return 1; }
+    return 0;
+}
+
+// copy an output table to the caller: large pageable destinations go through the pinned ring
+static int download(cudaStream_t st, const double *src_dev, double *dst, int64_t n, uint32_t flags)
+{
+    (void)flags;
+    if (n <= 0) return 0;
+    if (n >= 8 * (int64_t)HTB_STAGE_CHUNK && host_pointer_is_pageable(dst) && !getenv("HTB_NO_STAGED_UPLOAD"))
+        return staged_download(st, src_dev, dst, n);
+    HTB_CUDA(cudaMemcpyAsync(dst, src_dev, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+
 // column-wise minimum and maximum of `cols` strided host columns (threads; one pass over memory)
 extern "C" int htb_host_minmax(const double *base, int64_t n, int64_t stride, int32_t cols, double *min_out, double *max_out)
 {
@@ -659,9 +719,16 @@ struct Call {
         HTB_CUDA(cudaEventRecord(ev[2], st));
         return 0;
     }
+    bool count_marked = false;
+    // end of the counting kernels (output copies that follow are not part of ms_count)
+    int mark_count_end()
+    {
+        if (!count_marked) { HTB_CUDA(cudaEventRecord(ev[3], st)); count_marked = true; }
+        return 0;
+    }
     int finish(htb_stats *stats, int path)
     {
-        HTB_CUDA(cudaEventRecord(ev[3], st));
+        if (mark_count_end()) return 1;
         unsigned int h[4] = {0, 0, 0, 0};
         uint32_t ntiles = 0;
         std::vector<double> work;
@@ -1197,7 +1264,8 @@ extern "C" int htb_weighted_npairs_per_object_xy_engine(const htb_mesh_geom *mes
     bp.nw = 1; bp.wfunc = -1;
     c.G.maxslices = 1;
     if (htb_launch_binq(c.st, 3, 4, c.G, c.A, bp, &c.launches)) return 1;
-    if (n1 > 0) HTB_CUDA(cudaMemcpyAsync(counts_out, rows, sizeof(double) * (size_t)n1 * nrp, cudaMemcpyDeviceToHost, c.st));
+    if (c.mark_count_end()) return 1;
+    if (download(c.st, rows, counts_out, n1 * (int64_t)nrp, flags)) return 1;
     return c.finish(stats, 3);
     HTB_GUARD_END
 }
@@ -1231,7 +1299,8 @@ extern "C" int htb_npairs_per_object_3d_engine(const htb_mesh_geom *mesh,
     bp.perm1 = c.s1.perm;
     c.G.maxslices = 1;             // every row is written by one work item (no column slices: they would each add 64 x nb atomics)
     if (htb_launch_binq(c.st, 0, 2, c.G, c.A, bp, &c.launches)) return 1;
-    if (n1 > 0) HTB_CUDA(cudaMemcpyAsync(counts_out, rows, sizeof(int64_t) * (size_t)n1 * nb, cudaMemcpyDeviceToHost, c.st));
+    if (c.mark_count_end()) return 1;
+    if (download(c.st, (const double *)rows, (double *)counts_out, n1 * (int64_t)nb, flags)) return 1;      // 8-byte words
     return c.finish(stats, 3);
     HTB_GUARD_END
 }
@@ -1511,7 +1580,10 @@ extern "C" int htb_mean_delta_sigma_engine(const htb_mesh_geom *mesh,
         c.launches += 2;
         HTB_CUDA(cudaGetLastError());
         HTB_CUDA(cudaMemcpyAsync(out, sums, sizeof(double) * (size_t)nbin, cudaMemcpyDeviceToHost, c.st));
-    } else if (n1 > 0) HTB_CUDA(cudaMemcpyAsync(out, out_dev, sizeof(double) * (size_t)n1 * nbin, cudaMemcpyDeviceToHost, c.st));
+    } else if (n1 > 0) {
+        if (c.mark_count_end()) return 1;
+        if (download(c.st, out_dev, out, n1 * (int64_t)nbin, flags)) return 1;
+    }
     return c.finish(stats, ring ? 2 : (fast ? 1 : 0));
     HTB_GUARD_END
 }

@@ -42,4 +42,4 @@ def npairs_per_object_3d(sample1, sample2, rbins, period=None,
         counts.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), extra_flags=_lib.cache_flags(c1, c2, PBCs))
     # rows of points outside this rank's mesh1 cells are zero: the sum over ranks is the full table
     # (npairs_per_object_3d.py:135-137)
-    return np.array(_dist.allreduce_sum(counts))
+    return _dist.allreduce_sum(counts)           # a fresh array already (no second copy of a large table)

@@ -47,7 +47,7 @@ def weighted_npairs_per_object_xy(sample1, sample2, sample2_mass, rp_bins,
         c2.ptrs[0], c2.ptrs[1], ctypes.c_int64(c2.stride), ctypes.c_int64(c2.n),
         _lib._dp(w2), _lib._dp(rb), ctypes.c_int32(len(rb)), ctypes.c_int64(first), ctypes.c_int64(last),
         _lib._dp(counts))
-    return np.array(_dist.allreduce_sum(counts))
+    return _dist.allreduce_sum(counts)           # a fresh array already (no second copy of a large table)
 
 
 def total_mass_enclosed_per_cylinder(centers, particles,

@@ -790,3 +790,28 @@ def test_weighted_npairs_per_object_xy_vs_oracle():
     sub = rng.permutation(len(g))[:300]
     assert np.array_equal(hb.weighted_npairs_per_object_xy(g[sub], p, ints, rp, period=L),
                           hb.weighted_npairs_per_object_xy(g, p, ints, rp, period=L)[sub])
+
+
+def test_large_per_object_outputs_take_the_staged_download():
+    """per-object tables >= 2M values go to pageable memory through the pinned ring: same rows as the direct copy"""
+    import os
+    rng = np.random.RandomState(38)
+    L = 200.0
+    s = rng.uniform(0, L, (150000, 3))
+    rbins = np.logspace(-1, 1, 15)
+    staged = hb.npairs_per_object_3d(s, s, rbins, period=L)
+    assert staged.shape == (150000, 15) and staged.size >= 8 * 256 * 1024
+    os.environ["HTB_NO_STAGED_UPLOAD"] = "1"
+    try:
+        direct = hb.npairs_per_object_3d(s, s, rbins, period=L)
+    finally:
+        del os.environ["HTB_NO_STAGED_UPLOAD"]
+    assert np.array_equal(staged, direct)
+    assert np.array_equal(staged.sum(axis=0), hb.npairs_3d(s, s, rbins, period=L))
+    sub = rng.permutation(len(s))[:2000]
+    assert np.array_equal(staged[sub], oracle.npairs_per_object_3d(s[sub], s, rbins, period=L))
+    ptcl = rng.uniform(0, L, (400000, 3))
+    rp = np.logspace(-1, 1, 15)
+    rows = hb.mean_delta_sigma(s, ptcl, 1.0, rp, period=L, per_object=True)
+    assert rows.shape == (150000, 14)
+    assert np.allclose(rows.mean(axis=0), hb.mean_delta_sigma(s, ptcl, 1.0, rp, period=L), rtol=1e-9, atol=1e-12 * np.max(np.abs(rows)))
