@@ -19,8 +19,8 @@
 // instruction that records the pair as a BIT of a per-lane 64-bit mask (one bit per staged sample2 point and lane
 // point) - no shared-memory queue, no stores.  At the end of every staged chunk the set bits are replayed: the
 // separation is recomputed with the same arithmetic, located among the edges by a table lookup on its exponent and
-// leading mantissa bits (first edge that can be >= the value) followed by exact 64-bit compares of the raw bit
-// patterns (order preserving for non-negative doubles), and the pair (or its weight) is added to the DIFFERENTIAL
+// leading mantissa bits (first edge that can be >= the value; exact 64-bit compares of the raw bit patterns - order
+// preserving for non-negative doubles - only where an edge shares the value's table cell), and the pair (or its weight) is added to the DIFFERENTIAL
 // histogram cell (lowest satisfied edge per axis).  The host turns the differential histogram into the reference's
 // cumulative counts (for monotone edges the reference's top-down scans stop exactly at the lowest satisfied edge).
 #include "kernel.cuh"
@@ -146,25 +146,20 @@ struct BinQ {
         if (KIND == 1) return (__double2hiint(a) <= P.H0 && __double2hiint(b) <= P.H1) ? 1u : 0u;
         return (__double2hiint(a) <= P.H0) ? 1u : 0u;
     }
-    // first index i in [0, n] whose edge is >= the value with raw bits `bits` (n: above every edge).  Straight-line
-    // code (so that the two chains of a replay trip interleave): table lookup, two exact compares; more than one
-    // edge inside the value's table cell is finished by a loop (rare).
+    // first index i in [0, n] whose edge is >= the value with raw bits `bits` (n: above every edge): one table lookup on
+    // the value's key; exact 64-bit compares only when an edge shares the value's table cell (the entry's low bit)
     __device__ __forceinline__ int locate(int axis, int first, int n, unsigned long long bits)
     {
-        // key = bits >> S with S >= 44: a 32-bit shift of the high word
-        const int t = (int)((unsigned)(bits >> 32) >> (P.S[axis] - 32)) - (int)P.kmin[axis];
-        const int T = P.T[axis];
+        // key = bits >> S with S >= 44: a 32-bit shift of the high word.  Table entry 0 serves every key below the
+        // smallest non-zero edge's, entry T - 1 every key above the top edge's (or a negative NaN: a huge unsigned key)
+        const unsigned key = (unsigned)(bits >> 32) >> (P.S[axis] - 32);
+        const int t = min((int)key - (int)P.kmin[axis] + 1, P.T[axis] - 1);            // keys are below 2^20
         unsigned v;
-        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(lut_s[axis] + (uint32_t)min(max(t, 0), T - 1)));
-        int i = t < 0 ? 0 : (t >= T ? n : (int)v);        // a negative value (NaN with the sign bit) has a huge key: n
-        const uint32_t eb = e_s + 8u * (uint32_t)first;
-        const bool c1 = (i < n) & (bq_lds_u64(eb + 8u * (uint32_t)min(i, n - 1)) < bits);
-        i += c1 ? 1 : 0;
-        if (c1) {
-            if (i < n && bq_lds_u64(eb + 8u * (uint32_t)i) < bits) {
-                ++i;
-                while (i < n && bq_lds_u64(eb + 8u * (uint32_t)i) < bits) ++i;
-            }
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(lut_s[axis] + (uint32_t)max(t, 0)));
+        int i = (int)(v >> 1);
+        if (v & 1u) {
+            const uint32_t eb = e_s + 8u * (uint32_t)first;
+            while (i < n && bq_lds_u64(eb + 8u * (uint32_t)i) < bits) ++i;
         }
         return i;
     }
@@ -193,14 +188,16 @@ struct BinQ {
         return htb_pair_weight(P.wfunc, w1, w2l);
     }
     // every trip takes the lowest recorded pair of BOTH lane points (two independent dependency chains)
-    __device__ __forceinline__ void replay(uint32_t stage, unsigned long long M0, unsigned long long M1)
+    typedef unsigned mask_t;
+    static __device__ __forceinline__ int lowest(mask_t m) { return __ffs((int)m) - 1; }
+    __device__ __forceinline__ void replay(uint32_t stage, mask_t M0, mask_t M1, int jbase)
     {
         const uint32_t bx = stage, by = stage + 8 * HTB_CH, bz = stage + 16 * HTB_CH, bw = stage + 8 * DIM * HTB_CH;
-        while (__any_sync(HTB_FULL, (M0 | M1) != 0ull)) {
-            const bool act0 = M0 != 0ull, act1 = M1 != 0ull;
-            const int j0 = max(__ffsll((long long)M0) - 1, 0), j1 = max(__ffsll((long long)M1) - 1, 0);
-            M0 &= M0 - 1ull;
-            M1 &= M1 - 1ull;
+        while (__any_sync(HTB_FULL, (M0 | M1) != 0)) {
+            const bool act0 = M0 != 0, act1 = M1 != 0;
+            const int j0 = jbase + (act0 ? lowest(M0) : 0), j1 = jbase + (act1 ? lowest(M1) : 0);
+            M0 &= M0 - 1;
+            M1 &= M1 - 1;
             const double xa = lds_f64(bx + 8 * j0), ya = lds_f64(by + 8 * j0), za = DIM == 3 ? lds_f64(bz + 8 * j0) : 0.0;
             const double xb = lds_f64(bx + 8 * j1), yb = lds_f64(by + 8 * j1), zb = DIM == 3 ? lds_f64(bz + 8 * j1) : 0.0;
             const int h0 = replay_one(act0, xs0, ys0, zs0, xa, ya, za);
@@ -259,10 +256,11 @@ struct BinQ {
             }
             m[0][w] = a0; m[1][w] = a1;
         }
+        // the two 32-point halves of the chunk are replayed one after the other (32-bit masks)
         const unsigned long long range = (hi >= 64 ? ~0ull : ((1ull << hi) - 1ull)) & ~((1ull << lo) - 1ull);
-        const unsigned long long M0 = ((unsigned long long)m[0][0] | ((unsigned long long)m[0][1] << 32)) & range;
-        const unsigned long long M1 = ((unsigned long long)m[1][0] | ((unsigned long long)m[1][1] << 32)) & range;
-        replay(stage, M0, M1);
+        const unsigned rlo = (unsigned)range, rhi = (unsigned)(range >> 32);
+        if (__any_sync(HTB_FULL, ((m[0][0] | m[1][0]) & rlo) != 0u)) replay(stage, m[0][0] & rlo, m[1][0] & rlo, 0);
+        if (__any_sync(HTB_FULL, ((m[0][1] | m[1][1]) & rhi) != 0u)) replay(stage, m[0][1] & rhi, m[1][1] & rhi, 32);
     }
     __device__ __forceinline__ bool tile_end(const WalkArrays &, const uint32_t (&idx)[2], int, unsigned wt)
     {

@@ -836,7 +836,7 @@ static bool fast3_params(const htb_mesh_geom *mesh, const double *bins, const do
 static bool binq_ok(const double *e0, int n0, const double *e1, int n1, uint32_t flags)
 {
     if ((flags & HTB_FLAG_GENERIC) || getenv("HTB_NO_BINQ")) return false;
-    if (n0 < 1 || n1 < 1 || n0 > 255 || n1 > 255 || (long long)n0 * n1 > 4096) return false;
+    if (n0 < 1 || n1 < 1 || n0 > 127 || n1 > 127 || (long long)n0 * n1 > 4096) return false;
     if (!finite_all(e0, n0) || (e1 && !finite_all(e1, n1))) return false;
     for (int k = 0; k + 1 < n0; ++k) if (!(e0[k] <= e0[k + 1])) return false;
     for (int k = 0; e1 && k + 1 < n1; ++k) if (!(e1[k] <= e1[k + 1])) return false;
@@ -857,10 +857,11 @@ static int binq_prepare(Call &c, const double *e0, int n0, const double *e1, int
     std::vector<unsigned long long> eb((size_t)n0 + n1, 0ULL);
     for (int k = 0; k < n0; ++k) eb[k] = dbits(e0[k] + 0.0);
     for (int k = 0; e1 && k < n1; ++k) eb[(size_t)n0 + k] = dbits(e1[k] + 0.0);
-    // Lookup tables: key = bits >> S keeps the exponent and up to 8 mantissa bits; lut[key - kmin] is the first edge
-    // whose key is >= key (every earlier edge is certainly below the value); the kernel finishes with exact compares.
-    // kmin is the key of the smallest non-zero edge (values below it start at edge 0); S grows until the table is
-    // at most 2048 entries.
+    // Lookup tables: key = bits >> S keeps the exponent and up to 8 mantissa bits.  lut[key - kmin] = (i << 1) | a with i
+    // the first edge whose key is >= key (every earlier edge is certainly below the value) and a = 1 if some edge has
+    // exactly this key (only then the kernel needs exact compares: the value and that edge share a table cell).
+    // kmin is the key of the smallest non-zero edge; values with a smaller key lie below every non-zero edge (index =
+    // number of zero edges, or 0 for an exact zero).  S grows until the table has at most 2048 entries.
     BinQParams bp{};
     std::vector<unsigned char> lut[2];
     for (int a = 0; a < 2; ++a) {
@@ -869,16 +870,23 @@ static int binq_prepare(Call &c, const double *e0, int n0, const double *e1, int
         int z = 0;
         while (z < n - 1 && b[z] == 0ULL) ++z;
         int S = 44;
-        while (((b[n - 1] >> S) - (b[z] >> S) + 1ULL) > 2048ULL) ++S;
+        while (((b[n - 1] >> S) - (b[z] >> S) + 1ULL) > 2040ULL) ++S;
         const unsigned long long kmin = b[z] >> S;
-        const int T = (int)((b[n - 1] >> S) - kmin + 1ULL);
-        lut[a].assign(((size_t)T + 7) & ~(size_t)7, (unsigned char)n);
+        const int Tin = (int)((b[n - 1] >> S) - kmin + 1ULL);
+        // two guard cells: entry 0 = every key below kmin (the value lies below every non-zero edge: edge `z`, or - if
+        // there are zero edges - possibly edge 0: compare), entry Tin + 1 = every key above the top edge's (index n)
+        const int T = Tin + 2;
+        lut[a].assign(((size_t)T + 7) & ~(size_t)7, (unsigned char)(n << 1));
+        lut[a][0] = (b[z] == 0ULL) ? (unsigned char)((n << 1)) : (unsigned char)(z > 0 ? 1 : 0);   // z > 0: start at 0, compare
         int i = 0;
-        for (int t = 0; t < T; ++t) {
+        for (int t = 0; t < Tin; ++t) {
             while (i < n && (b[i] >> S) < kmin + (unsigned long long)t) ++i;
-            lut[a][(size_t)t] = (unsigned char)i;
+            const bool amb = i < n && (b[i] >> S) == kmin + (unsigned long long)t;
+            lut[a][(size_t)t + 1] = (unsigned char)((i << 1) | (amb ? 1 : 0));
         }
-        bp.S[a] = S; bp.T[a] = T; bp.kmin[a] = (unsigned)kmin;
+        lut[a][(size_t)Tin + 1] = (unsigned char)(n << 1);
+        if (b[z] == 0ULL) lut[a][1] = 1;               // all edges zero: key 0 holds them all (start at 0, compare)
+        bp.S[a] = S; bp.T[a] = T; bp.kmin[a] = (unsigned)kmin; bp.nzero[a] = z;
     }
     const size_t ne = eb.size();
     eb.resize(ne + (lut[0].size() + lut[1].size()) / 8);

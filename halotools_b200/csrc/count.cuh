@@ -66,9 +66,11 @@ struct BinQParams {
     const unsigned long long *edges; // device: raw bits of the squared edges, n0 of axis 0 then n1 of axis 1, ascending;
                                      // followed by the two lookup tables (T[0], T[1] bytes, each padded to 8)
     unsigned long long *counts;      // device: [n0 * n1] differential histogram (lowest satisfied edge per axis)
-    // per axis: lut[(bits >> S) - kmin] = first edge whose key (bits >> S) is >= that of the value; T entries
+    // per axis: lut[(bits >> S) - kmin] = (first edge whose key (bits >> S) is >= that of the value) << 1 | (an edge
+    // has exactly this key: exact compares needed); T entries
     int S[2], T[2];
     unsigned kmin[2];
+    int nzero[2];                    // per axis: number of leading zero edges (index of a positive value below the table)
     // weighted modes (marked_npairs_xy_z, marked_npairs_3d with general marks, weighted_npairs_xy)
     int nw, wfunc;                   // weights per point; weight_func_id, or -1: the weight is sample2's w2[0] alone
     double *fcounts;                 // device: [n0 * n1] differential float sums
