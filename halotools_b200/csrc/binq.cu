@@ -39,8 +39,9 @@ __device__ __forceinline__ unsigned long long bq_lds_u64(uint32_t addr)
 
 template <int KIND, int MODE>
 struct BinQ {
-    static constexpr int DIM = KIND == 3 ? 2 : 3, NPAY = MODE == 1 ? HTB_MAX_NW : (MODE == 3 ? 2 : (MODE >= 4 ? 1 : 0)), PPL = 2, WARPS = 8,
-                         MINBLOCKS = MODE >= 3 ? 1 : 2;
+    static constexpr int DIM = KIND == 3 ? 2 : 3, NPAY = MODE == 1 ? HTB_MAX_NW : (MODE == 3 ? 2 : (MODE >= 4 ? 1 : 0)), PPL = 2,
+                         WARPS = MODE >= 3 ? 4 : 8,            // per-point f64 rows: smaller blocks, so that wide rows still fit
+                         MINBLOCKS = 2;
     static constexpr bool TMA = true;
     typedef BinQParams Params;
     const Params &P;
@@ -55,6 +56,11 @@ struct BinQ {
     double xs0, ys0, zs0, xs1, ys1, zs1;
     double wa[MODE == 1 ? HTB_MAX_NW : 1], wb[MODE == 1 ? HTB_MAX_NW : 1];
     int tag[2];                 // MODE 3: jackknife tags of this lane's points
+    // balanced replay (every mode but 1): the tile's 64 points {x - shift, y - shift, z - shift, weight} and the list of
+    // the recorded pairs of a 16-point quarter chunk live in shared memory, so that ANY lane can replay ANY pair
+    static constexpr bool BAL = MODE != 1;
+    static constexpr int BAL_BYTES = BAL ? 64 * 32 + 2 * 1024 : 0;
+    uint32_t pts_s, list_s;
 
     static __host__ __device__ size_t lut_bytes(const Params &p) { return (((size_t)p.T[0] + 7) & ~(size_t)7) + (((size_t)p.T[1] + 7) & ~(size_t)7); }
     static size_t scratch_bytes(const Params &p)
@@ -65,14 +71,16 @@ struct BinQ {
         else if (MODE == 1) acc = 8 * nh;
         else if (MODE == 2) acc = 4 * ((64 * (size_t)(p.n0 | 1) + 3) & ~(size_t)3);
         else acc = 8 * 64 * (nh | 1);
-        return 8 * ne + lut_bytes(p) + acc;
+        return BAL_BYTES + 8 * ne + lut_bytes(p) + acc;
     }
     __device__ BinQ(const Params &p, void *scratch, int ln, const WalkArrays &) : P(p), lane(ln)
     {
         const int ne = P.n0 + P.n1;
         // edges and lookup tables are one contiguous block of 8-byte words on the device
         const int nl = (int)(lut_bytes(P) >> 3);
-        unsigned long long *e = (unsigned long long *)scratch;
+        pts_s = smem_u32(scratch);                  // 16-byte aligned (LDS.128)
+        list_s = pts_s + 64 * 32;
+        unsigned long long *e = (unsigned long long *)((unsigned char *)scratch + BAL_BYTES);
         hist = (uint32_t *)(e + ne + nl);
         fhist = (double *)(e + ne + nl);
         e_s = smem_u32(e);
@@ -86,6 +94,7 @@ struct BinQ {
         else if (MODE == 2) { for (int k = lane; k < 64 * rstride; k += 32) hist[k] = 0; }
         else { for (int k = lane; k < 64 * rstride; k += 32) fhist[k] = 0.0; }
         tag[0] = tag[1] = 0;
+        wa[0] = wb[0] = 0.0;
         x0 = y0 = z0 = x1 = y1 = z1 = 0.0;
         xs0 = ys0 = zs0 = xs1 = ys1 = zs1 = 0.0;
         __syncwarp();
@@ -116,6 +125,15 @@ struct BinQ {
         xs0 = x0 - sh[0]; ys0 = y0 - sh[1];
         xs1 = x1 - sh[0]; ys1 = y1 - sh[1];
         if (DIM == 3) { zs0 = z0 - sh[2]; zs1 = z1 - sh[2]; }
+        if (BAL) {
+            __syncwarp();
+            const uint32_t a = pts_s + 32u * (uint32_t)lane, b = pts_s + 32u * (uint32_t)(32 + lane);
+            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(xs0), "d"(ys0) : "memory");
+            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a + 16u), "d"(zs0), "d"(wa[0]) : "memory");
+            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(b), "d"(xs1), "d"(ys1) : "memory");
+            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(b + 16u), "d"(zs1), "d"(wb[0]) : "memory");
+            __syncwarp();
+        }
     }
     // the two separations the bins are defined on, in the reference's evaluation order
     __device__ __forceinline__ void seps(double xs, double ys, double zs, double xj, double yj, double zj, double &a, double &b)
@@ -187,41 +205,101 @@ struct BinQ {
         for (int k = 0; k < HTB_MAX_NW; ++k) w2l[k] = (k < P.nw) ? lds_f64(w2addr + 8 * k) : 0.0;
         return htb_pair_weight(P.wfunc, w1, w2l);
     }
-    // every trip takes the lowest recorded pair of BOTH lane points (two independent dependency chains)
+    // one recorded pair of lane point q (0 / 1): recompute, locate, accumulate
     typedef unsigned mask_t;
     static __device__ __forceinline__ int lowest(mask_t m) { return __ffs((int)m) - 1; }
-    __device__ __forceinline__ void replay(uint32_t stage, mask_t M0, mask_t M1, int jbase)
+    __device__ __forceinline__ void entry(const int q, const bool act, const int j, const uint32_t stage)
     {
         const uint32_t bx = stage, by = stage + 8 * HTB_CH, bz = stage + 16 * HTB_CH, bw = stage + 8 * DIM * HTB_CH;
+        const double xj = lds_f64(bx + 8 * j), yj = lds_f64(by + 8 * j), zj = DIM == 3 ? lds_f64(bz + 8 * j) : 0.0;
+        const int h = q ? replay_one(act, xs1, ys1, zs1, xj, yj, zj) : replay_one(act, xs0, ys0, zs0, xj, yj, zj);
+        if (h < 0) return;
+        if (MODE == 0) atomicAdd(hist + h, 1u);
+        else if (MODE == 1) atomicAdd(fhist + h, weight_of(q ? wb : wa, bw + 8 * j * P.nw));
+        else if (MODE == 2) hist[(32 * q + lane) * rstride + h] += 1u;      // rows are private to the lane's points
+        else if (MODE == 3)                                                // jweight's w1 * w2 (npairs_jackknife_3d_engine.pyx:283-289)
+            fhist[(32 * q + lane) * rstride + h] += (q ? wb[0] : wa[0]) * lds_f64(bw + 16 * j);
+        else fhist[(32 * q + lane) * rstride + h] += lds_f64(bw + 8 * j);   // weighted_npairs_per_object_xy_engine.pyx:167-173
+    }
+    // every trip takes the BQ_ILP lowest recorded pairs of BOTH lane points (independent dependency chains: the replay
+    // is bound by the latency of load -> f64 chain -> table -> accumulate, not by issue slots)
+#ifndef BQ_ILP
+#define BQ_ILP 1
+#endif
+    __device__ __forceinline__ void replay(uint32_t stage, mask_t M0, mask_t M1, int jbase)
+    {
+#ifdef BQ_STATS
+        if (MODE == 0) {
+            const unsigned e = __reduce_add_sync(HTB_FULL, (unsigned)(__popc(M0) + __popc(M1)));
+            const unsigned mx = __reduce_max_sync(HTB_FULL, (unsigned)max(__popc(M0), __popc(M1)));
+            if (lane == 0) { atomicAdd(P.counts + P.n0 * P.n1, (unsigned long long)e); atomicAdd(P.counts + P.n0 * P.n1 + 1, (unsigned long long)mx * 64ull); }
+        }
+#endif
         while (__any_sync(HTB_FULL, (M0 | M1) != 0)) {
-            const bool act0 = M0 != 0, act1 = M1 != 0;
-            const int j0 = jbase + (act0 ? lowest(M0) : 0), j1 = jbase + (act1 ? lowest(M1) : 0);
-            M0 &= M0 - 1;
-            M1 &= M1 - 1;
-            const double xa = lds_f64(bx + 8 * j0), ya = lds_f64(by + 8 * j0), za = DIM == 3 ? lds_f64(bz + 8 * j0) : 0.0;
-            const double xb = lds_f64(bx + 8 * j1), yb = lds_f64(by + 8 * j1), zb = DIM == 3 ? lds_f64(bz + 8 * j1) : 0.0;
-            const int h0 = replay_one(act0, xs0, ys0, zs0, xa, ya, za);
-            const int h1 = replay_one(act1, xs1, ys1, zs1, xb, yb, zb);
-            if (MODE == 0) {
-                if (h0 >= 0) atomicAdd(hist + h0, 1u);
-                if (h1 >= 0) atomicAdd(hist + h1, 1u);
-            } else if (MODE == 1) {
-                if (h0 >= 0) atomicAdd(fhist + h0, weight_of(wa, bw + 8 * j0 * P.nw));
-                if (h1 >= 0) atomicAdd(fhist + h1, weight_of(wb, bw + 8 * j1 * P.nw));
-            } else if (MODE == 2) {
-                // rows are private to the lane's points: plain read-modify-write
-                if (h0 >= 0) hist[lane * rstride + h0] += 1u;
-                if (h1 >= 0) hist[(32 + lane) * rstride + h1] += 1u;
-            } else if (MODE == 3) {
-                // jweight's w1 * w2 (npairs_jackknife_3d_engine.pyx:283-289), summed per lane point and differential cell
-                if (h0 >= 0) fhist[lane * rstride + h0] += wa[0] * lds_f64(bw + 16 * j0);
-                if (h1 >= 0) fhist[(32 + lane) * rstride + h1] += wb[0] * lds_f64(bw + 16 * j1);
-            } else {
-                // weighted_npairs_per_object_xy_engine.pyx:167-173: the weight is w2[j]
-                if (h0 >= 0) fhist[lane * rstride + h0] += lds_f64(bw + 8 * j0);
-                if (h1 >= 0) fhist[(32 + lane) * rstride + h1] += lds_f64(bw + 8 * j1);
+            bool act[2][BQ_ILP];
+            int j[2][BQ_ILP];
+#pragma unroll
+            for (int u = 0; u < BQ_ILP; ++u) {
+                act[0][u] = M0 != 0; act[1][u] = M1 != 0;
+                j[0][u] = jbase + (act[0][u] ? lowest(M0) : 0);
+                j[1][u] = jbase + (act[1][u] ? lowest(M1) : 0);
+                M0 &= M0 - 1;
+                M1 &= M1 - 1;
+            }
+#pragma unroll
+            for (int u = 0; u < BQ_ILP; ++u) {
+                entry(0, act[0][u], j[0][u], stage);
+                entry(1, act[1][u], j[1][u], stage);
             }
         }
+    }
+    // Balanced replay of one quarter chunk (16 staged points): the lanes' recorded pairs (a0 / a1: 16-bit masks of this
+    // lane's two points) are laid out as ONE list in shared memory (warp prefix sum of the counts, entry = tile slot
+    // << 4 | staged point), then every lane replays an equal share of the list - whatever lanes the pairs came from.
+    // (A lane's pairs are all in range or all out of range of a staged run far more often than not: replaying them
+    // in place keeps about 30 % of the lanes busy.)
+    __device__ __forceinline__ void replay_quarter(uint32_t stage, unsigned a0, unsigned a1, int jbase)
+    {
+        const uint32_t bx = stage, by = stage + 8 * HTB_CH, bz = stage + 16 * HTB_CH, bw = stage + 8 * DIM * HTB_CH;
+        const int c = __popc(a0) + __popc(a1);
+        int inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(HTB_FULL, inc, o);
+            if (lane >= o) inc += t;
+        }
+        const int total = __shfl_sync(HTB_FULL, inc, 31);
+        uint32_t w = list_s + 2u * (uint32_t)(inc - c);
+        for (unsigned m = a0; m; m &= m - 1u) {
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(w), "h"((unsigned short)((lane << 4) | (__ffs((int)m) - 1))) : "memory");
+            w += 2u;
+        }
+        for (unsigned m = a1; m; m &= m - 1u) {
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(w), "h"((unsigned short)(((32 + lane) << 4) | (__ffs((int)m) - 1))) : "memory");
+            w += 2u;
+        }
+        __syncwarp();
+        const int per = (total + 31) >> 5;                       // every lane replays `per` consecutive entries
+#pragma unroll 1
+        for (int k = 0; k < per; ++k) {
+            const int g = lane * per + k;
+            const bool act = g < total;
+            unsigned short e;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(e) : "r"(list_s + 2u * (uint32_t)min(g, total - 1)));
+            const int slot = (int)(e >> 4), j = jbase + (int)(e & 15u);
+            double px, py, pz, pw;
+            lds_f64x2(pts_s + 32u * (uint32_t)slot, px, py);
+            lds_f64x2(pts_s + 32u * (uint32_t)slot + 16u, pz, pw);
+            const double xj = lds_f64(bx + 8 * j), yj = lds_f64(by + 8 * j), zj = DIM == 3 ? lds_f64(bz + 8 * j) : 0.0;
+            const int h = replay_one(act, px, py, pz, xj, yj, zj);
+            if (h >= 0) {
+                if (MODE == 0) atomicAdd(hist + h, 1u);
+                else if (MODE == 2) atomicAdd(hist + slot * rstride + h, 1u);
+                else if (MODE == 3) atomicAdd(fhist + slot * rstride + h, pw * lds_f64(bw + 16 * j));     // jweight's w1 * w2
+                else atomicAdd(fhist + slot * rstride + h, lds_f64(bw + 8 * j));                          // the weight is w2[j]
+            }
+        }
+        __syncwarp();                                            // the list is rewritten by the next quarter
     }
     __device__ __forceinline__ void chunk(uint32_t stage, int lo, int hi, uint32_t tok)
     {
@@ -258,6 +336,19 @@ struct BinQ {
         }
         // the two 32-point halves of the chunk are replayed one after the other (32-bit masks)
         const unsigned long long range = (hi >= 64 ? ~0ull : ((1ull << hi) - 1ull)) & ~((1ull << lo) - 1ull);
+        if (BAL) {
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+                const unsigned rw = (unsigned)(range >> (32 * w));
+                const unsigned f0 = m[0][w] & rw, f1 = m[1][w] & rw;
+#pragma unroll
+                for (int hq = 0; hq < 2; ++hq) {
+                    const unsigned a0 = (f0 >> (16 * hq)) & 0xffffu, a1 = (f1 >> (16 * hq)) & 0xffffu;
+                    if (__any_sync(HTB_FULL, (a0 | a1) != 0u)) replay_quarter(stage, a0, a1, 32 * w + 16 * hq);
+                }
+            }
+            return;
+        }
         const unsigned rlo = (unsigned)range, rhi = (unsigned)(range >> 32);
         if (__any_sync(HTB_FULL, ((m[0][0] | m[1][0]) & rlo) != 0u)) replay(stage, m[0][0] & rlo, m[1][0] & rlo, 0);
         if (__any_sync(HTB_FULL, ((m[0][1] | m[1][1]) & rhi) != 0u)) replay(stage, m[0][1] & rhi, m[1][1] & rhi, 32);
