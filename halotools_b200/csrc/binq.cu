@@ -17,7 +17,8 @@
 // (5-8 operations), one integer compare of its high word per bin axis against the high word of the top squared
 // edge (a conservative superset: the high word of a non-negative double is monotone), and one predicated integer
 // instruction that records the pair as a BIT of a per-lane 64-bit mask (one bit per staged sample2 point and lane
-// point) - no shared-memory queue, no stores.  At the end of every staged chunk the set bits are replayed: the
+// point) - no shared-memory queue, no stores.  At the end of every staged chunk the set bits are replayed - by ALL
+// lanes in equal shares (the set bits of a quarter chunk are first laid out as one list in shared memory): the
 // separation is recomputed with the same arithmetic, located among the edges by a table lookup on its exponent and
 // leading mantissa bits (first edge that can be >= the value; exact 64-bit compares of the raw bit patterns - order
 // preserving for non-negative doubles - only where an edge shares the value's table cell), and the pair (or its weight) is added to the DIFFERENTIAL
@@ -56,11 +57,15 @@ struct BinQ {
     double xs0, ys0, zs0, xs1, ys1, zs1;
     double wa[MODE == 1 ? HTB_MAX_NW : 1], wb[MODE == 1 ? HTB_MAX_NW : 1];
     int tag[2];                 // MODE 3: jackknife tags of this lane's points
-    // balanced replay (every mode but 1): the tile's 64 points {x - shift, y - shift, z - shift, weight} and the list of
-    // the recorded pairs of a 16-point quarter chunk live in shared memory, so that ANY lane can replay ANY pair
-    static constexpr bool BAL = MODE != 1;
-    static constexpr int BAL_BYTES = BAL ? 64 * 32 + 2 * 1024 : 0;
+    // balanced replay: the tile's 64 points {x - shift, y - shift, z - shift, weight(s)} and the list of the recorded
+    // pairs of a 16-point quarter chunk live in shared memory, so that ANY lane can replay ANY pair
+    static constexpr int PT_BYTES = MODE == 1 ? 64 : 32;         // MODE 1 keeps the point's (up to) 5 marks next to it
+    static constexpr int BAL_BYTES = 64 * PT_BYTES + 2 * 1024;
     uint32_t pts_s, list_s;
+    // MODE 1 with few cells and MODE 5: every lane sums the pairs IT replays into its own row (no shared-memory f64
+    // atomics: all lanes hitting a handful of cells serialise), the rows are reduced over the warp at the end of the tile
+    static constexpr int PRIV_MAX = 48;
+    bool priv;
 
     static __host__ __device__ size_t lut_bytes(const Params &p) { return (((size_t)p.T[0] + 7) & ~(size_t)7) + (((size_t)p.T[1] + 7) & ~(size_t)7); }
     static size_t scratch_bytes(const Params &p)
@@ -68,8 +73,9 @@ struct BinQ {
         const size_t ne = (size_t)p.n0 + p.n1, nh = (size_t)p.n0 * p.n1;
         size_t acc;
         if (MODE == 0) acc = 4 * ((nh + 3) & ~(size_t)3);
-        else if (MODE == 1) acc = 8 * nh;
+        else if (MODE == 1) acc = nh <= PRIV_MAX ? 8 * 32 * (nh | 1) : 8 * nh;
         else if (MODE == 2) acc = 4 * ((64 * (size_t)(p.n0 | 1) + 3) & ~(size_t)3);
+        else if (MODE == 5) acc = 8 * 32 * (nh | 1);
         else acc = 8 * 64 * (nh | 1);
         return BAL_BYTES + 8 * ne + lut_bytes(p) + acc;
     }
@@ -79,20 +85,21 @@ struct BinQ {
         // edges and lookup tables are one contiguous block of 8-byte words on the device
         const int nl = (int)(lut_bytes(P) >> 3);
         pts_s = smem_u32(scratch);                  // 16-byte aligned (LDS.128)
-        list_s = pts_s + 64 * 32;
+        list_s = pts_s + 64 * PT_BYTES;
         unsigned long long *e = (unsigned long long *)((unsigned char *)scratch + BAL_BYTES);
         hist = (uint32_t *)(e + ne + nl);
         fhist = (double *)(e + ne + nl);
         e_s = smem_u32(e);
         lut_s[0] = e_s + 8u * (uint32_t)ne;
         lut_s[1] = lut_s[0] + (uint32_t)((P.T[0] + 7) & ~7);
-        rstride = MODE >= 3 ? ((P.n0 * P.n1) | 1) : (P.n0 | 1);
+        rstride = (MODE >= 3 || MODE == 1) ? ((P.n0 * P.n1) | 1) : (P.n0 | 1);
+        priv = MODE == 5 || (MODE == 1 && P.n0 * P.n1 <= PRIV_MAX);
         vmask = 0;
         for (int k = lane; k < ne + nl; k += 32) e[k] = P.edges[k];
         if (MODE == 0) { for (int k = lane; k < P.n0 * P.n1; k += 32) hist[k] = 0; }
-        else if (MODE == 1) { for (int k = lane; k < P.n0 * P.n1; k += 32) fhist[k] = 0.0; }
+        else if (MODE == 1) { for (int k = lane; k < (priv ? 32 * rstride : P.n0 * P.n1); k += 32) fhist[k] = 0.0; }
         else if (MODE == 2) { for (int k = lane; k < 64 * rstride; k += 32) hist[k] = 0; }
-        else { for (int k = lane; k < 64 * rstride; k += 32) fhist[k] = 0.0; }
+        else { for (int k = lane; k < (MODE == 5 ? 32 : 64) * rstride; k += 32) fhist[k] = 0.0; }
         tag[0] = tag[1] = 0;
         wa[0] = wb[0] = 0.0;
         x0 = y0 = z0 = x1 = y1 = z1 = 0.0;
@@ -125,13 +132,20 @@ struct BinQ {
         xs0 = x0 - sh[0]; ys0 = y0 - sh[1];
         xs1 = x1 - sh[0]; ys1 = y1 - sh[1];
         if (DIM == 3) { zs0 = z0 - sh[2]; zs1 = z1 - sh[2]; }
-        if (BAL) {
+        {
             __syncwarp();
-            const uint32_t a = pts_s + 32u * (uint32_t)lane, b = pts_s + 32u * (uint32_t)(32 + lane);
+            const uint32_t a = pts_s + (uint32_t)PT_BYTES * (uint32_t)lane, b = pts_s + (uint32_t)PT_BYTES * (uint32_t)(32 + lane);
             asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(xs0), "d"(ys0) : "memory");
             asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a + 16u), "d"(zs0), "d"(wa[0]) : "memory");
             asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(b), "d"(xs1), "d"(ys1) : "memory");
             asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(b + 16u), "d"(zs1), "d"(wb[0]) : "memory");
+            if (MODE == 1) {
+#pragma unroll
+                for (int k = 1; k < HTB_MAX_NW; ++k) {
+                    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a + 24u + 8u * (uint32_t)k), "d"(wa[MODE == 1 ? k : 0]) : "memory");
+                    asm volatile("st.shared.f64 [%0], %1;" ::"r"(b + 24u + 8u * (uint32_t)k), "d"(wb[MODE == 1 ? k : 0]) : "memory");
+                }
+            }
             __syncwarp();
         }
     }
@@ -205,54 +219,6 @@ struct BinQ {
         for (int k = 0; k < HTB_MAX_NW; ++k) w2l[k] = (k < P.nw) ? lds_f64(w2addr + 8 * k) : 0.0;
         return htb_pair_weight(P.wfunc, w1, w2l);
     }
-    // one recorded pair of lane point q (0 / 1): recompute, locate, accumulate
-    typedef unsigned mask_t;
-    static __device__ __forceinline__ int lowest(mask_t m) { return __ffs((int)m) - 1; }
-    __device__ __forceinline__ void entry(const int q, const bool act, const int j, const uint32_t stage)
-    {
-        const uint32_t bx = stage, by = stage + 8 * HTB_CH, bz = stage + 16 * HTB_CH, bw = stage + 8 * DIM * HTB_CH;
-        const double xj = lds_f64(bx + 8 * j), yj = lds_f64(by + 8 * j), zj = DIM == 3 ? lds_f64(bz + 8 * j) : 0.0;
-        const int h = q ? replay_one(act, xs1, ys1, zs1, xj, yj, zj) : replay_one(act, xs0, ys0, zs0, xj, yj, zj);
-        if (h < 0) return;
-        if (MODE == 0) atomicAdd(hist + h, 1u);
-        else if (MODE == 1) atomicAdd(fhist + h, weight_of(q ? wb : wa, bw + 8 * j * P.nw));
-        else if (MODE == 2) hist[(32 * q + lane) * rstride + h] += 1u;      // rows are private to the lane's points
-        else if (MODE == 3)                                                // jweight's w1 * w2 (npairs_jackknife_3d_engine.pyx:283-289)
-            fhist[(32 * q + lane) * rstride + h] += (q ? wb[0] : wa[0]) * lds_f64(bw + 16 * j);
-        else fhist[(32 * q + lane) * rstride + h] += lds_f64(bw + 8 * j);   // weighted_npairs_per_object_xy_engine.pyx:167-173
-    }
-    // every trip takes the BQ_ILP lowest recorded pairs of BOTH lane points (independent dependency chains: the replay
-    // is bound by the latency of load -> f64 chain -> table -> accumulate, not by issue slots)
-#ifndef BQ_ILP
-#define BQ_ILP 1
-#endif
-    __device__ __forceinline__ void replay(uint32_t stage, mask_t M0, mask_t M1, int jbase)
-    {
-#ifdef BQ_STATS
-        if (MODE == 0) {
-            const unsigned e = __reduce_add_sync(HTB_FULL, (unsigned)(__popc(M0) + __popc(M1)));
-            const unsigned mx = __reduce_max_sync(HTB_FULL, (unsigned)max(__popc(M0), __popc(M1)));
-            if (lane == 0) { atomicAdd(P.counts + P.n0 * P.n1, (unsigned long long)e); atomicAdd(P.counts + P.n0 * P.n1 + 1, (unsigned long long)mx * 64ull); }
-        }
-#endif
-        while (__any_sync(HTB_FULL, (M0 | M1) != 0)) {
-            bool act[2][BQ_ILP];
-            int j[2][BQ_ILP];
-#pragma unroll
-            for (int u = 0; u < BQ_ILP; ++u) {
-                act[0][u] = M0 != 0; act[1][u] = M1 != 0;
-                j[0][u] = jbase + (act[0][u] ? lowest(M0) : 0);
-                j[1][u] = jbase + (act[1][u] ? lowest(M1) : 0);
-                M0 &= M0 - 1;
-                M1 &= M1 - 1;
-            }
-#pragma unroll
-            for (int u = 0; u < BQ_ILP; ++u) {
-                entry(0, act[0][u], j[0][u], stage);
-                entry(1, act[1][u], j[1][u], stage);
-            }
-        }
-    }
     // Balanced replay of one quarter chunk (16 staged points): the lanes' recorded pairs (a0 / a1: 16-bit masks of this
     // lane's two points) are laid out as ONE list in shared memory (warp prefix sum of the counts, entry = tile slot
     // << 4 | staged point), then every lane replays an equal share of the list - whatever lanes the pairs came from.
@@ -288,15 +254,25 @@ struct BinQ {
             asm volatile("ld.shared.u16 %0, [%1];" : "=h"(e) : "r"(list_s + 2u * (uint32_t)min(g, total - 1)));
             const int slot = (int)(e >> 4), j = jbase + (int)(e & 15u);
             double px, py, pz, pw;
-            lds_f64x2(pts_s + 32u * (uint32_t)slot, px, py);
-            lds_f64x2(pts_s + 32u * (uint32_t)slot + 16u, pz, pw);
+            lds_f64x2(pts_s + (uint32_t)PT_BYTES * (uint32_t)slot, px, py);
+            lds_f64x2(pts_s + (uint32_t)PT_BYTES * (uint32_t)slot + 16u, pz, pw);
             const double xj = lds_f64(bx + 8 * j), yj = lds_f64(by + 8 * j), zj = DIM == 3 ? lds_f64(bz + 8 * j) : 0.0;
             const int h = replay_one(act, px, py, pz, xj, yj, zj);
             if (h >= 0) {
                 if (MODE == 0) atomicAdd(hist + h, 1u);
+                else if (MODE == 1) {
+                    double w1l[HTB_MAX_NW];
+                    w1l[0] = pw;
+#pragma unroll
+                    for (int q = 1; q < HTB_MAX_NW; ++q) w1l[q] = (q < P.nw) ? lds_f64(pts_s + (uint32_t)PT_BYTES * (uint32_t)slot + 24u + 8u * (uint32_t)q) : 0.0;
+                    const double w = weight_of(w1l, bw + 8 * j * P.nw);
+                    if (priv) fhist[lane * rstride + h] += w;
+                    else atomicAdd(fhist + h, w);
+                }
                 else if (MODE == 2) atomicAdd(hist + slot * rstride + h, 1u);
                 else if (MODE == 3) atomicAdd(fhist + slot * rstride + h, pw * lds_f64(bw + 16 * j));     // jweight's w1 * w2
-                else atomicAdd(fhist + slot * rstride + h, lds_f64(bw + 8 * j));                          // the weight is w2[j]
+                else if (MODE == 5) fhist[lane * rstride + h] += lds_f64(bw + 8 * j);                     // the weight is w2[j]
+                else atomicAdd(fhist + slot * rstride + h, lds_f64(bw + 8 * j));
             }
         }
         __syncwarp();                                            // the list is rewritten by the next quarter
@@ -336,7 +312,7 @@ struct BinQ {
         }
         // the two 32-point halves of the chunk are replayed one after the other (32-bit masks)
         const unsigned long long range = (hi >= 64 ? ~0ull : ((1ull << hi) - 1ull)) & ~((1ull << lo) - 1ull);
-        if (BAL) {
+        {
 #pragma unroll
             for (int w = 0; w < 2; ++w) {
                 const unsigned rw = (unsigned)(range >> (32 * w));
@@ -347,11 +323,7 @@ struct BinQ {
                     if (__any_sync(HTB_FULL, (a0 | a1) != 0u)) replay_quarter(stage, a0, a1, 32 * w + 16 * hq);
                 }
             }
-            return;
         }
-        const unsigned rlo = (unsigned)range, rhi = (unsigned)(range >> 32);
-        if (__any_sync(HTB_FULL, ((m[0][0] | m[1][0]) & rlo) != 0u)) replay(stage, m[0][0] & rlo, m[1][0] & rlo, 0);
-        if (__any_sync(HTB_FULL, ((m[0][1] | m[1][1]) & rhi) != 0u)) replay(stage, m[0][1] & rhi, m[1][1] & rhi, 32);
     }
     __device__ __forceinline__ bool tile_end(const WalkArrays &, const uint32_t (&idx)[2], int, unsigned wt)
     {
@@ -362,24 +334,20 @@ struct BinQ {
                 const uint32_t h = hist[k];
                 if (h) { atomicAdd(P.counts + k, (unsigned long long)wt * h); hist[k] = 0; }
             }
-        } else if (MODE == 1) {
+        } else if (MODE == 1 && !priv) {
             for (int k = lane; k < nh; k += 32) {
                 const double h = fhist[k];
                 if (h != 0.0) { atomicAdd(P.fcounts + k, wt == 2u ? h + h : h); fhist[k] = 0.0; }
             }
-        } else if (MODE == 5) {
+        } else if (MODE == 1 || MODE == 5) {
             // one row for the whole call: sum the lanes' rows (differential cells), one atomic per cell and tile
             for (int k = 0; k < nh; ++k) {
-                double v = 0.0;
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    double *r = fhist + (q * 32 + lane) * rstride;
-                    if ((vmask >> q) & 1u) v += r[k];
-                    r[k] = 0.0;
-                }
+                double *r = fhist + lane * rstride;
+                double v = r[k];
+                r[k] = 0.0;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(HTB_FULL, v, o);
-                if (lane == 0 && v != 0.0) atomicAdd(P.fcounts + k, v);
+                if (lane == 0 && v != 0.0) atomicAdd(P.fcounts + k, wt == 2u ? v + v : v);
             }
         } else if (MODE == 4) {
             // per object: cumulative over the edges, rows in input order (weighted_npairs_per_object_xy_engine.pyx:175-185)
