@@ -199,8 +199,12 @@ def run_gpu(args):
         acc = {"pairs_reference": 0.0, "pairs_evaluated": 0.0, "ms_count": 0.0, "launches": 0, "ms_mesh": 0.0,
                "count_evaluated": [], "count_ms": []}
         out = []
+        # the three counts of the statistic keep the ranks' partial sums; ONE all-reduce at the end of the block (what
+        # hb.tpcf does internally)
+        part = distributed.local_counts()
+        part.__enter__()
         for a, b in ((gal_d, gal_d), (gal_d, ran_d), (ran_d, ran_d)):
-            out.append(hb.npairs_3d(a, b, rbins, period=LBOX))
+            out.append(part.add(hb.npairs_3d(a, b, rbins, period=LBOX)))
             st = _lib.last_stats
             acc["pairs_reference"] += st["pairs_reference"]
             acc["pairs_evaluated"] += st["pairs_evaluated"]
@@ -211,6 +215,7 @@ def run_gpu(args):
             acc["count_ms"].append(st["ms_count"])
             acc.setdefault("calls", []).append({k: st[k] for k in ("ms_h2d", "ms_mesh", "ms_count", "ms_total", "tiles",
                                                                    "tiles_redone", "refine1", "refine2")})
+        part.__exit__(None, None, None)
         xi = landy_szalay(out[0], out[1], out[2], N, NR)
         stats_acc.update(acc)
         return xi
@@ -284,7 +289,7 @@ def run_gpu(args):
             cores = os.cpu_count() or 1
             v, dt, kind, sample, _ = cpu_sample(gal, ran, rbins, cores)
             cpu = {"value": v, "unit": "GPairs/s", "cores": cores, "kind": kind, "sample": sample, "seconds": dt}
-        h2d = int((N * 24) + (N * 24 + NR * 24) + (NR * 24))
+        h2d = int((N + NR) * 24)          # inside hb.tpcf the upload cache sends every sample across PCIe once per step
         d2h = int(3 * len(rbins) * 8)
         line = {"metric": "pair evals/sec", "value": value, "unit": "GPairs/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
@@ -297,7 +302,7 @@ def run_gpu(args):
                            "l2": "inputs (%.0f MB of sorted coordinates) exceed nothing that matters: the kernel is "
                                  "FP64-issue bound; every step re-sorts both samples and re-streams them from HBM"
                                  % ((N + NR) * 24 / 1e6),
-                           "parallelism": "mesh1 cell ranges over %d rank(s), one NCCL all-reduce per count" % world},
+                           "parallelism": "work-balanced mesh1 cell ranges over %d rank(s), one NCCL all-reduce per step" % world},
                 "e2e": {"value": e2e_value, "unit": "GPairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e},
                 "gpu_launches": int(acc["launches"] * args.steps),
@@ -404,7 +409,7 @@ def run_gpu_c5(args):
                            "pairs_reference_per_step": W, "pairs_evaluated_per_step": Wgpu,
                            "l2": "inputs (%.1f GB of coordinates) are larger than L2" % ((ngal + nptcl) * 24 / 1e9),
                            "parallelism": "work-balanced mesh1 cell ranges over %d rank(s), one all-reduce of the column sums" % world},
-                "e2e": {"value": W / (ms_e2e * 1e-3) / 1e9, "unit": "GPairs/s", "h2d_bytes_per_step": int((ngal + nptcl) * 24),
+                "e2e": {"value": W / (ms_e2e * 1e-3) / 1e9, "unit": "GPairs/s", "h2d_bytes_per_step": int((ngal + nptcl) * 16),    # the x and y columns (the engine never reads z)
                         "d2h_bytes_per_step": int(14 * 8), "ms_per_step": ms_e2e},
                 "gpu_launches": int(st["kernel_launches"] * args.steps),
                 "roofline": {"bound": "fp64_issue", "achieved": ach, "peak": rate / 1e12, "unit": "TFLOP/s", "frac": ach / (rate / 1e12),
