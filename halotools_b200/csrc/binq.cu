@@ -186,11 +186,18 @@ struct BinQ {
         // smallest non-zero edge's, entry T - 1 every key above the top edge's (or a negative NaN: a huge unsigned key)
         const unsigned key = (unsigned)(bits >> 32) >> (P.S[axis] - 32);
         const int t = min((int)key - (int)P.kmin[axis] + 1, P.T[axis] - 1);            // keys are below 2^20
-        unsigned v;
-        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(lut_s[axis] + (uint32_t)max(t, 0)));
+        const uint32_t la = lut_s[axis] + (uint32_t)max(t, 0);
+        unsigned v, v2;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(la));
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v2) : "r"(la + (t < P.T[axis] - 1 ? 1u : 0u)));
         int i = (int)(v >> 1);
-        if (v & 1u) {
-            const uint32_t eb = e_s + 8u * (uint32_t)first;
+        // edges inside the value's table cell: the next entry's index minus this one (0 unless the entry is flagged).
+        // One edge (the usual case of a flagged cell) is settled by one unconditional compare; more take the loop.
+        const int cnt = (v & 1u) ? (int)(v2 >> 1) - i : 0;
+        const uint32_t eb = e_s + 8u * (uint32_t)first;
+        const bool adv = (cnt >= 1) & (i < n) & (bq_lds_u64(eb + 8u * (uint32_t)min(i, n - 1)) < bits);
+        i += adv ? 1 : 0;
+        if (cnt >= 2 && adv) {
             while (i < n && bq_lds_u64(eb + 8u * (uint32_t)i) < bits) ++i;
         }
         return i;

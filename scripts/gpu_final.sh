@@ -18,3 +18,5 @@ echo "== ncu full capture (Fast3 RR launch)"
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_count -s 2 -c 1 -f -o gpurun_out/prof_fast3 \
     python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/prof_bench.log 2>&1
 echo "full capture rc=$?"; ls -la gpurun_out/prof_fast3.ncu-rep
+echo "== 8f counters"; timeout 600 python scripts/gpu_8f.py > gpurun_out/8f.log 2>&1; echo "rc=$?"
+echo "== ncu full capture (BinQ rp_pi)"; bash scripts/gpu_ncu_binq.sh | tail -2
