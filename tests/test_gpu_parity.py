@@ -473,10 +473,15 @@ def test_device_side_balanced_shards_add_up(world):
     mfull = hb.marked_npairs_3d(s1, s2, rb, 1, period=L, weights1=w1, weights2=w2)
     dfull = hb.mean_delta_sigma(s1[:5000], s2, 1.0, rb, period=L, per_object=True)
     dmean = hb.mean_delta_sigma(s1[:5000], s2, 1.0, rb, period=L)
-    tot, wtot, mtot, dtot, dmtot, shares = 0, 0.0, 0.0, 0.0, 0.0, []
+    pfull = hb.npairs_per_object_3d(s1[:8000], s2, rb, period=L)
+    tags1, tags2 = rng.randint(1, 6, len(s1)), rng.randint(1, 6, len(s2))
+    jfull = hb.npairs_jackknife_3d(s1, s2, rb, tags1, tags2, 5, period=L, weights1=w1, weights2=w2)
+    tot, wtot, mtot, dtot, dmtot, shares, ptot, jtot = 0, 0.0, 0.0, 0.0, 0.0, [], 0, 0.0
     try:
         for r in range(world):
             _lib.set_shard(r, world)
+            ptot = ptot + hb.npairs_per_object_3d(s1[:8000], s2, rb, period=L)
+            jtot = jtot + hb.npairs_jackknife_3d(s1, s2, rb, tags1, tags2, 5, period=L, weights1=w1, weights2=w2)
             tot = tot + hb.npairs_3d(s1, s2, rb, period=L)
             shares.append(_lib.last_stats["pairs_reference"])
             wtot += shares[-1]
@@ -486,6 +491,8 @@ def test_device_side_balanced_shards_add_up(world):
     finally:
         _lib.set_shard(0, 1)
     assert np.array_equal(tot, full)
+    assert np.array_equal(ptot, pfull)
+    assert np.all(np.abs(jtot - jfull) <= 1e-12 * np.abs(jfull[0])[None])
     assert wtot == wfull
     # balanced: no rank has more than its share plus one (heavy) cell's worth of work
     assert max(shares) <= wfull / world * 1.5, shares
