@@ -822,3 +822,24 @@ def test_large_per_object_outputs_take_the_staged_download():
     rows = hb.mean_delta_sigma(s, ptcl, 1.0, rp, period=L, per_object=True)
     assert rows.shape == (150000, 14)
     assert np.allclose(rows.mean(axis=0), hb.mean_delta_sigma(s, ptcl, 1.0, rp, period=L), rtol=1e-9, atol=1e-12 * np.max(np.abs(rows)))
+
+
+def test_odd_bin_arrays_keep_the_reference_scan_semantics():
+    """len-2 bins need not increase (npairs_3d.py:175-182): the reference's top-down scan stops at the first failing
+    edge, i.e. it counts against the suffix minima; very many bins leave BinQ for the literal-scan kernel"""
+    rng = np.random.RandomState(39)
+    L = 60.0
+    s1, s2 = _dup_points(rng, 6000, L), _dup_points(rng, 5000, L)
+    for rbins in ([3.0, 1.0], [2.0, 2.0], [0.0, 2.5]):
+        got = hb.npairs_3d(s1, s2, rbins, period=L)
+        assert np.array_equal(got, oracle.npairs_3d(s1, s2, rbins, period=L)), rbins
+    got = hb.npairs_xy_z(s1, s2, [2.0, 1.0], [5.0, 0.5], period=L)
+    assert np.array_equal(got, oracle.npairs_xy_z(s1, s2, [2.0, 1.0], [5.0, 0.5], period=L))
+    many = np.linspace(0.05, 5.0, 200)
+    got = hb.npairs_3d(s1, s2, many, period=L)
+    assert _lib.last_stats["path"] == 0, "more than 127 edges: the literal-scan kernel"
+    assert np.array_equal(got, oracle.npairs_3d(s1, s2, many, period=L, num_threads=4))
+    wide = np.linspace(0.05, 5.0, 120)
+    got = hb.npairs_3d(s1, s2, wide, period=L)
+    assert _lib.last_stats["path"] == 3
+    assert np.array_equal(got, oracle.npairs_3d(s1, s2, wide, period=L, num_threads=4))
