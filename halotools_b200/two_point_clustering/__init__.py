@@ -3,5 +3,6 @@ from .wp import wp
 from .rp_pi_tpcf import rp_pi_tpcf
 from .marked_tpcf import marked_tpcf
 from .tpcf_jackknife import tpcf_jackknife, wp_jackknife
+from .s_mu_tpcf import s_mu_tpcf, tpcf_multipole
 
-__all__ = ("tpcf", "wp", "rp_pi_tpcf", "marked_tpcf", "tpcf_jackknife", "wp_jackknife")
+__all__ = ("tpcf", "wp", "rp_pi_tpcf", "marked_tpcf", "tpcf_jackknife", "wp_jackknife", "s_mu_tpcf", "tpcf_multipole")

@@ -228,6 +228,12 @@ def _cases():
                                np.logspace(-1, 1.2, 10), 250.0), dict())
     C["mass_per_cylinder_scalar"] = ("total_mass_enclosed_per_cylinder",
                                      (cen3, ptc3, 3.0e9, 1.0, np.logspace(-1, 1.2, 10), [250.0, 250.0, 250.0]), dict())
+    # xi(s, mu) (fixture shapes: two_point_clustering/tests/test_s_mu_tpcf.py)
+    sbj, mbj = np.linspace(0.01, 0.25, 7), np.linspace(0.0, 1.0, 6)
+    C["smu_tpcf_auto_analytic"] = ("s_mu_tpcf", (s1, sbj, mbj), dict(period=1.0))
+    C["smu_tpcf_randoms_ls"] = ("s_mu_tpcf", (s1, sbj, mbj), dict(randoms=ran, period=1.0, estimator="Landy-Szalay"))
+    C["smu_tpcf_cross"] = ("s_mu_tpcf", (s1, sbj, mbj), dict(sample2=s2, period=1.0))
+    C["smu_tpcf_nonperiodic"] = ("s_mu_tpcf", (s1, sbj, mbj), dict(randoms=ran, period=None, estimator="Landy-Szalay"))
     return C
 
 

@@ -293,3 +293,17 @@ def test_cuboid_subvolume_labels_and_jackknife_argument_errors():
     with pytest.warns(UserWarning, match="every jackknife sample"):
         w1, w2, t1, t2 = _process_weights_jtags(S, S, None, None, np.ones(len(S), dtype=int), tags, 4)
     assert w1.dtype == np.float64 and np.all(w1 == 1.0) and t1.dtype.kind == "i"
+
+
+def test_tpcf_multipole_and_s_mu_argument_errors():
+    """tpcf_multipole.py:72-88 (pure host algebra) and the s_mu_tpcf validation messages (s_mu_tpcf.py:549-566)"""
+    from halotools_b200.two_point_clustering.s_mu_tpcf import tpcf_multipole, _s_mu_tpcf_process_args
+    mu_bins = np.linspace(0, 1, 41)
+    mu_c = 0.5 * (mu_bins[:-1] + mu_bins[1:])
+    xi = np.vstack([np.ones_like(mu_c), 0.5 * (3 * mu_c ** 2 - 1)])       # a pure monopole and a pure quadrupole
+    assert np.allclose(tpcf_multipole(xi, mu_bins, order=0), [1.0, 0.0], atol=2e-4)
+    assert np.allclose(tpcf_multipole(xi, mu_bins, order=2), [0.0, 1.0], atol=2e-3)
+    with pytest.raises(ValueError, match="range"):
+        _s_mu_tpcf_process_args(S, np.array([0.1, 0.2]), np.array([0.0, 1.5]), None, None, 1.0, True, True, "Natural", 1)
+    with pytest.raises(ValueError, match="randoms must be provided"):
+        _s_mu_tpcf_process_args(S, np.array([0.1, 0.2]), np.array([0.0, 1.0]), None, None, None, True, True, "Natural", 1)
