@@ -234,6 +234,14 @@ def _cases():
     C["smu_tpcf_randoms_ls"] = ("s_mu_tpcf", (s1, sbj, mbj), dict(randoms=ran, period=1.0, estimator="Landy-Szalay"))
     C["smu_tpcf_cross"] = ("s_mu_tpcf", (s1, sbj, mbj), dict(sample2=s2, period=1.0))
     C["smu_tpcf_nonperiodic"] = ("s_mu_tpcf", (s1, sbj, mbj), dict(randoms=ran, period=None, estimator="Landy-Szalay"))
+    # one- / two-halo decomposition (fixture shapes: two_point_clustering/tests/test_tpcf_one_two_halo.py)
+    hid1 = np.random.RandomState(76).randint(0, 60, 1000)
+    hid2 = np.random.RandomState(77).randint(0, 60, 1000)
+    C["tpcf_12h_auto"] = ("tpcf_one_two_halo_decomp", (s1, hid1, rb2), dict(period=1.0))
+    C["tpcf_12h_cross_ls"] = ("tpcf_one_two_halo_decomp", (s1, hid1, rb2),
+                              dict(sample2=s2, sample2_host_halo_id=hid2, randoms=ran, period=1.0, estimator="Landy-Szalay"))
+    C["tpcf_12h_cross_only"] = ("tpcf_one_two_halo_decomp", (s1, hid1, rb2),
+                                dict(sample2=s2, sample2_host_halo_id=hid2, period=1.0, do_auto=False))
     return C
 
 
