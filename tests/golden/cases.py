@@ -242,6 +242,14 @@ def _cases():
                               dict(sample2=s2, sample2_host_halo_id=hid2, randoms=ran, period=1.0, estimator="Landy-Szalay"))
     C["tpcf_12h_cross_only"] = ("tpcf_one_two_halo_decomp", (s1, hid1, rb2),
                                 dict(sample2=s2, sample2_host_halo_id=hid2, period=1.0, do_auto=False))
+    # w(theta) (fixture shapes: two_point_clustering/tests/test_angular_tpcf.py)
+    def sky(seed, n):
+        r = np.random.RandomState(seed)
+        return np.vstack([r.uniform(0, 360.0, n), np.degrees(np.arcsin(r.uniform(-1, 1, n)))]).T
+    tb = np.logspace(-1, 1.2, 9)
+    C["ang_auto_analytic"] = ("angular_tpcf", (sky(78, 2000), tb), dict())
+    C["ang_cross_randoms_ls"] = ("angular_tpcf", (sky(78, 2000), tb),
+                                 dict(sample2=sky(79, 1500), randoms=sky(80, 4000), estimator="Landy-Szalay"))
     return C
 
 
