@@ -11,9 +11,10 @@ from .. import distributed as _dist
 from ..helpers import (enforce_sample_has_correct_shape, enforce_sample_respects_pbcs, get_num_threads,
                        get_period, get_separation_bins_array)
 from ..pair_counters.mesh_helpers import _set_approximate_2d_cell_sizes, double_mesh_geometry
-from .weighted_npairs_xy import _weighted_npairs_xy_process_args
+from .weighted_npairs_xy import _weighted_npairs_xy_process_args, weighted_npairs_xy
 
-__all__ = ("weighted_npairs_per_object_xy", "total_mass_enclosed_per_cylinder")
+__all__ = ("weighted_npairs_per_object_xy", "total_mass_enclosed_per_cylinder",
+           "total_mass_enclosed_in_stack_of_cylinders", "surface_density_in_annulus", "surface_density_in_cylinder")
 
 
 def weighted_npairs_per_object_xy(sample1, sample2, sample2_mass, rp_bins,
@@ -69,6 +70,53 @@ def total_mass_enclosed_per_cylinder(centers, particles,
 
     total_mass_per_cylinder *= downsampling_factor*mean_particle_mass
     return total_mass_per_cylinder
+
+
+def total_mass_enclosed_in_stack_of_cylinders(centers, particles,
+                                              particle_masses, downsampling_factor, rp_bins, period,
+                                              num_threads=1, approx_cell1_size=None, approx_cell2_size=None):
+    """Total mass enclosed by the STACK of cylinders around all centres: float64 (len(rp_bins),)
+    (mass_in_cylinders.py:21-123)."""
+    (centers, particles, particle_masses, downsampling_factor,
+     rp_bins, period, num_threads, PBCs) = _enclosed_mass_process_args(
+        centers, particles, particle_masses, downsampling_factor, rp_bins, period, num_threads)
+
+    mean_particle_mass = np.mean(particle_masses)
+    normalized_particle_masses = particle_masses/mean_particle_mass
+
+    total_mass_in_stack_of_cylinders = weighted_npairs_xy(
+        centers, particles, normalized_particle_masses, rp_bins,
+        period=period[:2], num_threads=num_threads,
+        approx_cell1_size=approx_cell1_size, approx_cell2_size=approx_cell2_size)
+
+    total_mass_in_stack_of_cylinders *= downsampling_factor*mean_particle_mass
+    return total_mass_in_stack_of_cylinders
+
+
+def surface_density_in_annulus(centers, particles, particle_masses,
+                               downsampling_factor, rp_bins, period,
+                               num_threads=1, approx_cell1_size=None, approx_cell2_size=None):
+    """Average surface mass density in a stack of annuli (surface_density.py:17-35)."""
+    total_mass_in_stack_of_cylinders = total_mass_enclosed_in_stack_of_cylinders(
+        centers, particles, particle_masses, downsampling_factor, rp_bins, period,
+        num_threads=num_threads, approx_cell1_size=approx_cell1_size, approx_cell2_size=approx_cell2_size)
+    total_mass_in_stack_of_annuli = np.diff(total_mass_in_stack_of_cylinders)
+    rp_sq = rp_bins * rp_bins
+    area_annuli = np.pi * np.diff(rp_sq)
+    num_annuli = float(centers.shape[0])
+    return total_mass_in_stack_of_annuli / (area_annuli * num_annuli)
+
+
+def surface_density_in_cylinder(centers, particles, particle_masses,
+                                downsampling_factor, rp_bins, period,
+                                num_threads=1, approx_cell1_size=None, approx_cell2_size=None):
+    """Average surface mass density in a stack of cylinders (surface_density.py:38-53)."""
+    total_mass_in_stack_of_cylinders = total_mass_enclosed_in_stack_of_cylinders(
+        centers, particles, particle_masses, downsampling_factor, rp_bins, period,
+        num_threads=num_threads, approx_cell1_size=approx_cell1_size, approx_cell2_size=approx_cell2_size)
+    area_cylinders = np.pi * rp_bins * rp_bins
+    num_cylinders = float(centers.shape[0])
+    return total_mass_in_stack_of_cylinders / (area_cylinders * num_cylinders)
 
 
 def _enclosed_mass_process_args(centers, particles, masses, downsampling_factor, rp_bins, period, num_threads):

@@ -80,7 +80,9 @@ TRIMMED_INITS = {
         "from .two_point_clustering import tpcf, wp, rp_pi_tpcf, marked_tpcf, tpcf_jackknife, wp_jackknife, s_mu_tpcf, tpcf_multipole, tpcf_one_two_halo_decomp, angular_tpcf\n"
         "from .surface_density import mean_delta_sigma, weighted_npairs_xy\n"
         "from .surface_density.weighted_npairs_per_object_xy import weighted_npairs_per_object_xy\n"
-        "from .surface_density.mass_in_cylinders import total_mass_enclosed_per_cylinder\n",
+        "from .surface_density.mass_in_cylinders import total_mass_enclosed_per_cylinder\n"
+        "from .surface_density.mass_in_cylinders import total_mass_enclosed_in_stack_of_cylinders\n"
+        "from .surface_density.surface_density import surface_density_in_annulus, surface_density_in_cylinder\n",
     "halotools/mock_observables/pair_counters/__init__.py":
         "from .rectangular_mesh import RectangularDoubleMesh\n"
         "from .rectangular_mesh_2d import RectangularDoubleMesh2D\n"

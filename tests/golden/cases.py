@@ -250,6 +250,11 @@ def _cases():
     C["ang_auto_analytic"] = ("angular_tpcf", (sky(78, 2000), tb), dict())
     C["ang_cross_randoms_ls"] = ("angular_tpcf", (sky(78, 2000), tb),
                                  dict(sample2=sky(79, 1500), randoms=sky(80, 4000), estimator="Landy-Szalay"))
+    mcyl = np.random.RandomState(48).uniform(0.5, 2.0, 30000)
+    rpc = np.logspace(-1, 1.2, 10)
+    C["mass_stack_of_cylinders"] = ("total_mass_enclosed_in_stack_of_cylinders", (cen3, ptc3, mcyl, 2.5, rpc, 250.0), dict())
+    C["sigma_in_annulus"] = ("surface_density_in_annulus", (cen3, ptc3, mcyl, 1.0, rpc, 250.0), dict())
+    C["sigma_in_cylinder"] = ("surface_density_in_cylinder", (cen3, ptc3, 2.0e9, 3.0, rpc, [250.0, 250.0, 250.0]), dict())
     return C
 
 

@@ -34,7 +34,8 @@ def compare(fn, got, want):
             assert g.dtype == np.int64
             assert np.array_equal(g, w), (g, w)
         elif fn in ("marked_npairs_3d", "marked_npairs_xy_z", "weighted_npairs_xy", "weighted_npairs_per_object_xy",
-                    "total_mass_enclosed_per_cylinder"):
+                    "total_mass_enclosed_per_cylinder", "total_mass_enclosed_in_stack_of_cylinders",
+                    "surface_density_in_annulus", "surface_density_in_cylinder"):
             # float sums, order differs from the reference's serial loop: 1e-12 relative (north_star)
             assert np.allclose(g, w, rtol=1e-12, atol=0), (g, w)
         elif fn in ("npairs_jackknife_3d", "npairs_jackknife_xy_z"):
