@@ -11,6 +11,9 @@
 //                          weighted_npairs_per_object_xy_engine.pyx:150-185
 //   MODE 5  MODE 4's lane-private rows, reduced over the warp at the end of the tile into ONE row (few bins: no
 //           shared-memory atomics in the replay)   weighted_npairs_xy_engine.pyx:150-175
+//   MODE 6  MODE 3 with the ROLES OF THE SAMPLES EXCHANGED (the lanes hold sample2 points, sample1 is staged): the
+//           periodic shift is applied to the STAGED coordinate, so that the separation is the reference's own
+//           (x1 - shift) - x2, bit for bit (pass B of the jackknife counters)
 //   MODE 3  per-object weighted sums folded by the point's jackknife tag (payload rows {weight, tag})
 //                          npairs_jackknife_3d_engine.pyx:213-233, npairs_jackknife_xy_z_engine.pyx:222-246
 // The hot loop only DECIDES whether a pair can be inside the top edge(s): the reference's strict f64 separation
@@ -40,12 +43,14 @@ __device__ __forceinline__ unsigned long long bq_lds_u64(uint32_t addr)
 
 template <int KIND, int MODE>
 struct BinQ {
-    static constexpr int DIM = KIND == 3 ? 2 : 3, NPAY = MODE == 1 ? HTB_MAX_NW : (MODE == 3 ? 2 : (MODE >= 4 ? 1 : 0)), PPL = 2,
+    static constexpr int DIM = KIND == 3 ? 2 : 3, NPAY = MODE == 1 ? HTB_MAX_NW : ((MODE == 3 || MODE == 6) ? 2 : (MODE >= 4 ? 1 : 0)), PPL = 2,
                          WARPS = MODE >= 3 ? 4 : 8,            // per-point f64 rows: smaller blocks, so that wide rows still fit
                          MINBLOCKS = 2;
     static constexpr bool TMA = true;
+    static constexpr bool JK = MODE == 3 || MODE == 6, REV = MODE == 6;
     typedef BinQParams Params;
     const Params &P;
+    double rs0, rs1, rs2;       // REV: the (warp-uniform) periodic shift of the current span, NEGATED (x1 - shift_A = x1 + shift_B)
     uint32_t *hist;             // MODE 0: per-warp differential histogram (n0 * n1 u32); MODE 2: 64 rows of `rstride` u32
     double *fhist;              // MODE 1: per-warp differential float sums (n0 * n1); MODE 3: 64 rows of `rstride` f64
     uint32_t e_s;               // shared-space address: raw bits of the squared edges (n0 then n1), u64
@@ -121,7 +126,7 @@ struct BinQ {
                 wb[k] = (A.pay1 && k < A.nw) ? A.pay1[(size_t)idx[1] * A.nw + k] : 0.0;
             }
         }
-        if (MODE == 3) {
+        if (JK) {
             wa[0] = A.pay1[(size_t)idx[0] * 2]; wb[0] = A.pay1[(size_t)idx[1] * 2];
             tag[0] = (int)A.pay1[(size_t)idx[0] * 2 + 1]; tag[1] = (int)A.pay1[(size_t)idx[1] * 2 + 1];
         }
@@ -129,9 +134,15 @@ struct BinQ {
     __device__ __forceinline__ void set_shift(const double (&sh)[3], const WalkArrays &)
     {
         // npairs_3d_engine.pyx:167: the periodic shift is applied to the sample1 coordinate first
-        xs0 = x0 - sh[0]; ys0 = y0 - sh[1];
-        xs1 = x1 - sh[0]; ys1 = y1 - sh[1];
-        if (DIM == 3) { zs0 = z0 - sh[2]; zs1 = z1 - sh[2]; }
+        if (REV) {
+            // exchanged roles: the lanes keep their raw coordinates, the shift goes to the staged sample1 point
+            xs0 = x0; ys0 = y0; zs0 = z0; xs1 = x1; ys1 = y1; zs1 = z1;
+            rs0 = sh[0]; rs1 = sh[1]; rs2 = sh[2];
+        } else {
+            xs0 = x0 - sh[0]; ys0 = y0 - sh[1];
+            xs1 = x1 - sh[0]; ys1 = y1 - sh[1];
+            if (DIM == 3) { zs0 = z0 - sh[2]; zs1 = z1 - sh[2]; }
+        }
         {
             __syncwarp();
             const uint32_t a = pts_s + (uint32_t)PT_BYTES * (uint32_t)lane, b = pts_s + (uint32_t)PT_BYTES * (uint32_t)(32 + lane);
@@ -152,13 +163,15 @@ struct BinQ {
     // the two separations the bins are defined on, in the reference's evaluation order
     __device__ __forceinline__ void seps(double xs, double ys, double zs, double xj, double yj, double zj, double &a, double &b)
     {
-        const double dx = xs - xj, dy = ys - yj;
+        // REV: this pass's shift is minus the reference's (the window is seen from the sample2 point), so the
+        // reference's x1tmp = x1 - shift (npairs_jackknife_3d_engine.pyx:213-215) is xj + rs; dx only enters squared
+        const double dx = REV ? (xj + rs0) - xs : xs - xj, dy = REV ? (yj + rs1) - ys : ys - yj;
         if (KIND == 3) {
             a = dx * dx + dy * dy;                      // weighted_npairs_xy_engine.pyx:163-165
             b = 0.0;
             return;
         }
-        const double dz = zs - zj;
+        const double dz = REV ? (zj + rs2) - zs : zs - zj;
         if (KIND == 0) {
             a = dx * dx + dy * dy + dz * dz;            // npairs_3d_engine.pyx:176
             b = 0.0;
@@ -277,7 +290,7 @@ struct BinQ {
                     else atomicAdd(fhist + h, w);
                 }
                 else if (MODE == 2) atomicAdd(hist + slot * rstride + h, 1u);
-                else if (MODE == 3) atomicAdd(fhist + slot * rstride + h, pw * lds_f64(bw + 16 * j));     // jweight's w1 * w2
+                else if (JK) atomicAdd(fhist + slot * rstride + h, REV ? lds_f64(bw + 16 * j) * pw : pw * lds_f64(bw + 16 * j));   // jweight's w1 * w2
                 else if (MODE == 5) fhist[lane * rstride + h] += lds_f64(bw + 8 * j);                     // the weight is w2[j]
                 else atomicAdd(fhist + slot * rstride + h, lds_f64(bw + 8 * j));
             }
@@ -370,7 +383,7 @@ struct BinQ {
                     if (cum != 0.0) atomicAdd(row + k, cum);
                 }
             }
-        } else if (MODE == 3) {
+        } else if (JK) {
             // fold the rows of this lane's points into the table row of their jackknife tag (differential cells)
             // (sub-volumes are spatial: the points of a tile nearly always share one tag - then the rows are summed
             // over the warp first and one lane adds them)
@@ -431,6 +444,8 @@ int htb_launch_binq(cudaStream_t st, int kind, int mode, const WalkGeom &G, cons
     case 8: return launch_count<BinQ<0, 2>>(st, G, A, P, l);
     case 12: return launch_count<BinQ<0, 3>>(st, G, A, P, l);
     case 13: return launch_count<BinQ<1, 3>>(st, G, A, P, l);
+    case 24: return launch_count<BinQ<0, 6>>(st, G, A, P, l);
+    case 25: return launch_count<BinQ<1, 6>>(st, G, A, P, l);
     case 19: return launch_count<BinQ<3, 4>>(st, G, A, P, l);
     case 23: return launch_count<BinQ<3, 5>>(st, G, A, P, l);
     }

@@ -1322,9 +1322,9 @@ extern "C" int htb_npairs_per_object_3d_engine(const htb_mesh_geom *mesh,
 // the same for the sample2 points, counts[0] = T = sum_s A[s] and counts[s] = T - (A[s] + B[s]) / 2 - O(1) work per
 // pair instead of O(N_samples).  A comes from one pass of the per-object BinQ kernel (rows folded by tag); B from a
 // second pass with the roles of the samples exchanged, on mesh1's grid for both samples (cells >= the search length,
-// cover 1: every pair within the search length is visited once, with the image the reference uses).  A pair whose
-// squared separation lies within one ulp of an edge may fall on different sides in the two passes when it is a WRAPPED
-// pair (x1 - L - x2 and x2 + L - x1 round independently); un-wrapped pairs are bit-identical in both directions.
+// cover 1: every pair within the search length is visited once, with the image the reference uses).  In pass B the
+// periodic shift is applied to the STAGED sample1 coordinate (BinQ MODE 6): x1 + shift_B = x1 - shift_A exactly, so both
+// passes evaluate the reference's own (x1 - shift) - x2 and every pair lands in the same bin in A and in B.
 static int jackknife_pass(const htb_mesh_geom *mesh, int kind, bool swapped,
                           const double *const *ca, int64_t sa, int64_t na, const double *pa,
                           const double *const *cb, int64_t sb, int64_t nb_, const double *pb,
@@ -1342,10 +1342,9 @@ static int jackknife_pass(const htb_mesh_geom *mesh, int kind, bool swapped,
     HTB_CUDA(cudaMemsetAsync(tab, 0, sizeof(double) * nt, c.st));
     bp.fcounts = tab;
     bp.nw = 2; bp.wfunc = 1;
-    if (htb_launch_binq(c.st, kind, 3, c.G, c.A, bp, &c.launches)) return 1;
+    if (htb_launch_binq(c.st, kind, swapped ? 6 : 3, c.G, c.A, bp, &c.launches)) return 1;
     table.assign(nt, 0.0);
     HTB_CUDA(cudaMemcpyAsync(table.data(), tab, sizeof(double) * nt, cudaMemcpyDeviceToHost, c.st));
-    (void)swapped;
     return c.finish(stats, 3);
 }
 
