@@ -922,15 +922,13 @@ static int run_binq(Call &c, int kind, const double *e0, int n0, const double *e
     if (binq_prepare(c, e0, n0, e1, n1, &bp)) return 1;
     const int nh = n0 * n1;
     unsigned long long *counts_dev = nullptr;
-    if (c.ws.alloc((void **)&counts_dev, sizeof(unsigned long long) * (size_t)(nh + 2))) return 1;      // + 2 debug counters
-    HTB_CUDA(cudaMemsetAsync(counts_dev, 0, sizeof(unsigned long long) * (size_t)(nh + 2), c.st));
+    if (c.ws.alloc((void **)&counts_dev, sizeof(unsigned long long) * (size_t)nh)) return 1;
+    HTB_CUDA(cudaMemsetAsync(counts_dev, 0, sizeof(unsigned long long) * (size_t)nh, c.st));
     bp.counts = counts_dev;
     if (htb_launch_binq(c.st, kind, 0, c.G, c.A, bp, &c.launches)) return 1;
-    std::vector<long long> diff((size_t)nh + 2);
-    HTB_CUDA(cudaMemcpyAsync(diff.data(), counts_dev, sizeof(int64_t) * (size_t)(nh + 2), cudaMemcpyDeviceToHost, c.st));
+    std::vector<long long> diff((size_t)nh);
+    HTB_CUDA(cudaMemcpyAsync(diff.data(), counts_dev, sizeof(int64_t) * (size_t)nh, cudaMemcpyDeviceToHost, c.st));
     if (c.finish(stats, 3)) return 1;
-    if (getenv("HTB_BINQ_STATS")) fprintf(stderr, "BinQ replay: %lld entries, %lld lane slots (occupancy %.3f)\n", diff[nh], diff[nh + 1],
-                                          diff[nh + 1] ? (double)diff[nh] / (double)diff[nh + 1] : 0.0);
     prefix2d<long long>(diff.data(), n0, n1, (long long *)counts_out);
     return 0;
 }
