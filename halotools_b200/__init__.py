@@ -9,11 +9,11 @@ from .pair_counters import (npairs_3d, npairs_xy_z, npairs_s_mu, marked_npairs_3
 from .surface_density import (mean_delta_sigma, weighted_npairs_xy, weighted_npairs_per_object_xy,
                               total_mass_enclosed_per_cylinder, total_mass_enclosed_in_stack_of_cylinders,
                               surface_density_in_annulus, surface_density_in_cylinder)
-from .two_point_clustering import tpcf, wp, rp_pi_tpcf, marked_tpcf, tpcf_jackknife, wp_jackknife, s_mu_tpcf, tpcf_multipole, tpcf_one_two_halo_decomp, angular_tpcf
+from .two_point_clustering import tpcf, wp, rp_pi_tpcf, marked_tpcf, tpcf_jackknife, wp_jackknife, rp_pi_tpcf_jackknife, s_mu_tpcf, tpcf_multipole, tpcf_one_two_halo_decomp, angular_tpcf
 
 __version__ = "0.1.0"
 __all__ = ("HalotoolsError", "npairs_3d", "npairs_xy_z", "npairs_s_mu", "marked_npairs_3d",
            "marked_npairs_xy_z", "npairs_projected", "npairs_per_object_3d", "npairs_jackknife_3d", "npairs_jackknife_xy_z",
            "mean_delta_sigma", "weighted_npairs_xy", "weighted_npairs_per_object_xy",
            "total_mass_enclosed_per_cylinder", "total_mass_enclosed_in_stack_of_cylinders",
-           "surface_density_in_annulus", "surface_density_in_cylinder", "tpcf", "wp", "rp_pi_tpcf", "marked_tpcf", "tpcf_jackknife", "wp_jackknife", "s_mu_tpcf", "tpcf_multipole", "tpcf_one_two_halo_decomp", "angular_tpcf")
+           "surface_density_in_annulus", "surface_density_in_cylinder", "tpcf", "wp", "rp_pi_tpcf", "marked_tpcf", "tpcf_jackknife", "wp_jackknife", "rp_pi_tpcf_jackknife", "s_mu_tpcf", "tpcf_multipole", "tpcf_one_two_halo_decomp", "angular_tpcf")

@@ -81,6 +81,7 @@ struct BinQ {
         else if (MODE == 1) acc = nh <= PRIV_MAX ? 8 * 32 * (nh | 1) : 8 * nh;
         else if (MODE == 2) acc = 4 * ((64 * (size_t)(p.n0 | 1) + 3) & ~(size_t)3);
         else if (MODE == 5) acc = 8 * 32 * (nh | 1);
+        else if (JK && nh > HTB_JK_SHARED_CELLS) acc = 0;                 // rows in global memory (P.grows)
         else acc = 8 * 64 * (nh | 1);
         return BAL_BYTES + 8 * ne + lut_bytes(p) + acc;
     }
@@ -98,6 +99,11 @@ struct BinQ {
         lut_s[0] = e_s + 8u * (uint32_t)ne;
         lut_s[1] = lut_s[0] + (uint32_t)((P.T[0] + 7) & ~7);
         rstride = (MODE >= 3 || MODE == 1) ? ((P.n0 * P.n1) | 1) : (P.n0 | 1);
+        if (JK && P.n0 * P.n1 > HTB_JK_SHARED_CELLS) {
+            const unsigned gw = blockIdx.x * (unsigned)WARPS + (threadIdx.x >> 5);
+            if (gw >= P.grows_warps) __trap();
+            fhist = P.grows + (size_t)gw * 64u * (size_t)rstride;
+        }
         priv = MODE == 5 || (MODE == 1 && P.n0 * P.n1 <= PRIV_MAX);
         vmask = 0;
         for (int k = lane; k < ne + nl; k += 32) e[k] = P.edges[k];

@@ -1340,6 +1340,16 @@ static int jackknife_pass(const htb_mesh_geom *mesh, int kind, bool swapped,
     HTB_CUDA(cudaMemsetAsync(tab, 0, sizeof(double) * nt, c.st));
     bp.fcounts = tab;
     bp.nw = 2; bp.wfunc = 1;
+    if (nh > HTB_JK_SHARED_CELLS) {
+        // wide rows (rp_pi_tpcf_jackknife): the warps' 64 point rows live in global memory (L2 resident per warp)
+        int dev = 0, sms = 0;
+        HTB_CUDA(cudaGetDevice(&dev));
+        HTB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        bp.grows_warps = (unsigned)sms * 8u * 4u;              // <= 8 resident blocks of 4 warps per SM
+        const size_t gbytes = sizeof(double) * (size_t)bp.grows_warps * 64 * (nh | 1);
+        if (c.ws.alloc((void **)&bp.grows, gbytes)) return 1;
+        HTB_CUDA(cudaMemsetAsync(bp.grows, 0, gbytes, c.st));
+    }
     if (htb_launch_binq(c.st, kind, swapped ? 6 : 3, c.G, c.A, bp, &c.launches)) return 1;
     table.assign(nt, 0.0);
     HTB_CUDA(cudaMemcpyAsync(table.data(), tab, sizeof(double) * nt, cudaMemcpyDeviceToHost, c.st));
@@ -1362,8 +1372,8 @@ static int run_jackknife(const htb_mesh_geom *mesh, int kind,
     if (n1e > 1 || kind == 1) suffix_min(e, n0, n1e);
     const double *e1 = kind == 1 ? e.data() + n0 : nullptr;
     const int nn1 = kind == 1 ? n1e : 1;
-    if (!binq_ok(e.data(), n0, e1, nn1, flags & ~HTB_FLAG_GENERIC) || (long long)n0 * nn1 > 48) {
-        htb_set_error("jackknife engines: bins must be finite and n_bins (x n_pi_bins) <= 48 (per-point shared-memory rows)");
+    if (!binq_ok(e.data(), n0, e1, nn1, flags & ~HTB_FLAG_GENERIC)) {
+        htb_set_error("jackknife engines: bins must be finite, at most 127 per axis and 4096 cells");
         return 1;
     }
     // payload rows {weight, tag}

@@ -59,6 +59,7 @@ struct GenParams {
     const uint32_t *perm1;           // DSigma: sorted position -> input row
 };
 
+#define HTB_JK_SHARED_CELLS 48
 // BinQ (binq.cu): integer counts on any monotone edges, one or two bin axes, differential histogram
 struct BinQParams {
     int n0, n1;                      // edges along the first (r / rp / s) and second (none: 1 / pi / mu) bin axis
@@ -74,6 +75,10 @@ struct BinQParams {
     // weighted modes (marked_npairs_xy_z, marked_npairs_3d with general marks, weighted_npairs_xy)
     int nw, wfunc;                   // weights per point; weight_func_id, or -1: the weight is sample2's w2[0] alone
     double *fcounts;                 // device: [n0 * n1] differential float sums
+    // jackknife modes with more than HTB_JK_SHARED_CELLS cells per point row: the rows of every warp live in global
+    // memory (64 rows of (n0 * n1) | 1 doubles per warp, zero-filled by the host)
+    double *grows;
+    unsigned grows_warps;            // warps the allocation serves
     // per-object mode (npairs_per_object_3d)
     unsigned long long *rows;        // device: (n1_points, n0) cumulative counts in INPUT order
     const uint32_t *perm1;           // sorted position -> input row

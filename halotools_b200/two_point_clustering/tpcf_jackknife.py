@@ -15,7 +15,7 @@ from .clustering_helpers import process_optional_input_sample2, verify_tpcf_esti
 from .marked_tpcf import _SeededNumpyRNG
 from .tpcf_estimators import _TP_estimator, _TP_estimator_crossx, _TP_estimator_requirements
 
-__all__ = ("tpcf_jackknife", "wp_jackknife")
+__all__ = ("tpcf_jackknife", "wp_jackknife", "rp_pi_tpcf_jackknife")
 
 np.seterr(divide="ignore", invalid="ignore")  # as the reference modules do (tpcf_jackknife.py:30)
 
@@ -56,8 +56,26 @@ def wp_jackknife(sample1, randoms, rp_bins, pi_max, Nsub=[5, 5, 5], sample2=None
                                 PBCs, same, do_auto, do_cross, estimator)
 
 
+def rp_pi_tpcf_jackknife(sample1, randoms, rp_bins, pi_bins, Nsub=[5, 5, 5], sample2=None, period=None,
+                         do_auto=True, do_cross=True, estimator="Natural", num_threads=1, seed=None,
+                         approx_cell1_size=None, approx_cell2_size=None, approx_cellran_size=None):
+    """xi(rp, pi) of the full sample ((len(rp_bins)-1, len(pi_bins)-1) values) and its jackknife covariance matrix over
+    the row-major flattened bins (rp_pi_tpcf_jackknife.py:36-670)."""
+    (sample1, rp_bins, pi_bins, sample2, randoms, period, do_auto, do_cross, num_threads,
+     same, PBCs) = _wp_jackknife_tpcf_process_args(sample1, rp_bins, pi_bins, sample2, randoms, period,
+                                                   do_auto, do_cross, estimator, num_threads, seed, error=KeyError)
+
+    def count(a, b, ja, jb, nsub):
+        c = npairs_jackknife_xy_z(a, b, rp_bins, pi_bins, period=period, jtags1=ja, jtags2=jb, N_samples=nsub,
+                                  num_threads=num_threads)
+        return np.diff(np.diff(c, axis=1), axis=2)
+
+    return _jackknife_statistic(count, lambda c: c, 1.0, sample1, sample2, randoms, Nsub, period, PBCs, same,
+                                do_auto, do_cross, estimator, flatten=True)
+
+
 def _jackknife_statistic(count, squeeze, scale, sample1, sample2, randoms, Nsub, period, PBCs, same,
-                         do_auto, do_cross, estimator):
+                         do_auto, do_cross, estimator, flatten=False):
     """tpcf_jackknife.py:260-396 / wp_jackknife.py:262-420."""
     if PBCs is False:
         sample1, sample2, randoms, Lbox = _enclose_in_box(sample1, sample2, randoms)
@@ -75,6 +93,12 @@ def _jackknife_statistic(count, squeeze, scale, sample1, sample2, randoms, Nsub,
     NR_subs = NR - get_subvolume_numbers(j_index_random, N_sub_vol)
     N1_subs = N1 - get_subvolume_numbers(j_index_1, N_sub_vol)
     N2_subs = N2 - get_subvolume_numbers(j_index_2, N_sub_vol)
+
+    def cov(xi_sub):
+        # rows = jackknife samples; 2-d statistics are flattened row-major first (rp_pi_tpcf_jackknife.py:423-441)
+        if flatten:
+            xi_sub = np.reshape(xi_sub, (N_sub_vol, -1))
+        return np.array(np.cov(xi_sub.T, bias=True)) * (N_sub_vol - 1.0)
 
     def full_sub(c):
         if c is None:
@@ -110,13 +134,13 @@ def _jackknife_statistic(count, squeeze, scale, sample1, sample2, randoms, Nsub,
         xi_22_full = scale * _TP_estimator(D2D2_full, D2R_full, RR_full, N2, N2, NR, NR, estimator)
         xi_11_sub = scale * _TP_estimator(D1D1_sub, D1R_sub, RR_sub, N1_subs, N1_subs, NR_subs, NR_subs, estimator)
         xi_22_sub = scale * _TP_estimator(D2D2_sub, D2R_sub, RR_sub, N2_subs, N2_subs, NR_subs, NR_subs, estimator)
-        xi_11_cov = np.array(np.cov(xi_11_sub.T, bias=True)) * (N_sub_vol - 1.0)
-        xi_22_cov = np.array(np.cov(xi_22_sub.T, bias=True)) * (N_sub_vol - 1.0)
+        xi_11_cov = cov(xi_11_sub)
+        xi_22_cov = cov(xi_22_sub)
     if do_cross is True:
         xi_12_full = scale * _TP_estimator_crossx(D1D2_full, D1R_full, D2R_full, RR_full, N1, N2, NR, NR, estimator)
         xi_12_sub = scale * _TP_estimator_crossx(D1D2_sub, D1R_sub, D2R_sub, RR_sub,
                                                  N1_subs, N2_subs, NR_subs, NR_subs, estimator)
-        xi_12_cov = np.array(np.cov(xi_12_sub.T, bias=True)) * (N_sub_vol - 1.0)
+        xi_12_cov = cov(xi_12_sub)
 
     if same:
         return xi_11_full, xi_11_cov
@@ -193,8 +217,9 @@ def _tpcf_jackknife_process_args(sample1, randoms, rbins, Nsub, sample2, period,
 
 
 def _wp_jackknife_tpcf_process_args(sample1, rp_bins, pi_bins, sample2, randoms, period,
-                                    do_auto, do_cross, estimator, num_threads, seed):
-    """wp_jackknife.py:557-633."""
+                                    do_auto, do_cross, estimator, num_threads, seed, error=ValueError):
+    """wp_jackknife.py:557-633 (rp_pi_tpcf_jackknife.py:575-660 differs only in raising KeyError for randoms given by
+    number without a period)."""
     sample1 = enforce_sample_has_correct_shape(sample1)
     sample2, same, do_cross = process_optional_input_sample2(sample1, sample2, do_cross)
     if randoms is not None:
@@ -206,7 +231,7 @@ def _wp_jackknife_tpcf_process_args(sample1, rp_bins, pi_bins, sample2, randoms,
     pi_max = np.amax(pi_bins)
 
     period, PBCs = get_period(period)
-    randoms = _process_randoms(randoms, period, PBCs, seed, ValueError)
+    randoms = _process_randoms(randoms, period, PBCs, seed, error)
 
     _enforce_maximum_search_length([rp_max, rp_max, pi_max], period)
 

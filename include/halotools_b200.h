@@ -185,7 +185,7 @@ int htb_weighted_npairs_per_object_xy_engine(const htb_mesh_geom *mesh,
 /* npairs_jackknife_3d_engine.pyx:20 (cpairs/) - counts[s,k] = sum over pairs with dsq <= rbins[k]^2 of
  * jweight(s, jtag1_i, jtag2_j, w1_i, w2_j) (:237-291): s = 0 is the full sample, s >= 1 leaves sub-volume s out.
  * w1, w2: one weight per point; jtags1, jtags2: int64 tags in [1, N_samples]; output f64[(N_samples+1)*nb].
- * HOST arrays only.  nb <= 48.                                                                                  */
+ * HOST arrays only.                                                                                            */
 int htb_npairs_jackknife_3d_engine(const htb_mesh_geom *mesh,
                                    const double *x1, const double *y1, const double *z1, int64_t stride1, int64_t n1,
                                    const double *x2, const double *y2, const double *z2, int64_t stride2, int64_t n2,
@@ -195,7 +195,7 @@ int htb_npairs_jackknife_3d_engine(const htb_mesh_geom *mesh,
                                    double *counts_out, uint32_t flags, htb_stats *stats);
 
 /* npairs_jackknife_xy_z_engine.pyx:20 (cpairs/) - the same on (rp, pi) bins, f64[(N_samples+1)*nrp*npi] (:222-246);
- * nrp * npi <= 48.                                                                                              */
+ * more than 48 cells per point row (rp_pi_tpcf_jackknife) keep the rows in global memory.                       */
 int htb_npairs_jackknife_xy_z_engine(const htb_mesh_geom *mesh,
                                      const double *x1, const double *y1, const double *z1, int64_t stride1, int64_t n1,
                                      const double *x2, const double *y2, const double *z2, int64_t stride2, int64_t n2,

@@ -77,7 +77,7 @@ TRIMMED_INITS = {
         "from .array_utils import *\nfrom .array_indexing_manipulations import *\nfrom .spherical_geometry import *\n",
     "halotools/mock_observables/__init__.py":
         "from .pair_counters import *\n"
-        "from .two_point_clustering import tpcf, wp, rp_pi_tpcf, marked_tpcf, tpcf_jackknife, wp_jackknife, s_mu_tpcf, tpcf_multipole, tpcf_one_two_halo_decomp, angular_tpcf\n"
+        "from .two_point_clustering import tpcf, wp, rp_pi_tpcf, marked_tpcf, tpcf_jackknife, wp_jackknife, s_mu_tpcf, tpcf_multipole, tpcf_one_two_halo_decomp, angular_tpcf, rp_pi_tpcf_jackknife\n"
         "from .surface_density import mean_delta_sigma, weighted_npairs_xy\n"
         "from .surface_density.weighted_npairs_per_object_xy import weighted_npairs_per_object_xy\n"
         "from .surface_density.mass_in_cylinders import total_mass_enclosed_per_cylinder\n"
@@ -111,7 +111,8 @@ TRIMMED_INITS = {
         "from .tpcf import tpcf\nfrom .marked_tpcf import marked_tpcf\n"
         "from .tpcf_jackknife import tpcf_jackknife\nfrom .wp_jackknife import wp_jackknife\n"
         "from .s_mu_tpcf import s_mu_tpcf\nfrom .tpcf_multipole import tpcf_multipole\n"
-        "from .tpcf_one_two_halo_decomp import tpcf_one_two_halo_decomp\nfrom .angular_tpcf import angular_tpcf\n",
+        "from .tpcf_one_two_halo_decomp import tpcf_one_two_halo_decomp\nfrom .angular_tpcf import angular_tpcf\n"
+        "from .rp_pi_tpcf_jackknife import rp_pi_tpcf_jackknife\n",
     "halotools/mock_observables/surface_density/__init__.py":
         "from .mean_delta_sigma import mean_delta_sigma\n"
         "from .weighted_npairs_xy import weighted_npairs_xy\n",

@@ -38,6 +38,7 @@ if tags is None:
     tags, nsub = cuboid_subvolume_labels(s, 5, L)
 run("npairs_jackknife_3d 2e6, 125 sub-volumes", lambda: hb.npairs_jackknife_3d(s, s, rb, tags, tags, nsub, period=L, weights1=w, weights2=w))
 run("npairs_jackknife_xy_z 2e6, 125 sub-volumes, 15 x 2", lambda: hb.npairs_jackknife_xy_z(s, s, rp, [0.0, 60.0], tags, tags, nsub, period=L))
+run("npairs_jackknife_xy_z 2e6, 125 sub-volumes, 15 x 41 (rows in global memory)", lambda: hb.npairs_jackknife_xy_z(s, s, rp, np.linspace(0, 40, 41), tags, tags, nsub, period=L))
 gal = synthetic.fakesim_zheng07_mock(560, 250.0, seed=43)
 ran = synthetic.uniform_points(44, 2000000, 250.0)
 t0 = time.perf_counter(); xi, cov = hb.tpcf_jackknife(gal, ran, rb, Nsub=5, period=250.0, estimator="Landy-Szalay"); dt = time.perf_counter() - t0

@@ -255,6 +255,13 @@ def _cases():
     C["mass_stack_of_cylinders"] = ("total_mass_enclosed_in_stack_of_cylinders", (cen3, ptc3, mcyl, 2.5, rpc, 250.0), dict())
     C["sigma_in_annulus"] = ("surface_density_in_annulus", (cen3, ptc3, mcyl, 1.0, rpc, 250.0), dict())
     C["sigma_in_cylinder"] = ("surface_density_in_cylinder", (cen3, ptc3, 2.0e9, 3.0, rpc, [250.0, 250.0, 250.0]), dict())
+    # wide jackknife tables (more than 48 cells per point row) and the statistic on them
+    rpj, pij = np.logspace(-2, -0.8, 9), np.linspace(0.0, 0.28, 8)
+    C["jkxyz_wide"] = ("npairs_jackknife_xy_z", (s1, s2, rpj, pij, jt(72, 1000, 10), jt(73, 1000, 10), 10),
+                       dict(period=1.0, weights1=w1j, weights2=w2j))
+    C["rp_pi_jk_auto"] = ("rp_pi_tpcf_jackknife", (s1, ranj, rpj, pij), dict(Nsub=2, period=1.0))
+    C["rp_pi_jk_cross_ls"] = ("rp_pi_tpcf_jackknife", (s1, ranj, rpw, np.linspace(0, 0.25, 4)),
+                              dict(Nsub=[2, 2, 3], sample2=s2, period=1.0, estimator="Landy-Szalay"))
     return C
 
 

@@ -44,7 +44,7 @@ def compare(fn, got, want):
             # removed sample) comes out at the 1e-16 level of that row
             assert np.allclose(g, w, rtol=1e-12, atol=0) or np.all(np.abs(g - w) <= 1e-12 * np.abs(w[0])[None]), \
                 np.max(np.abs(g - w) / np.abs(w[0])[None])
-        elif fn in ("tpcf_jackknife", "wp_jackknife"):
+        elif fn in ("tpcf_jackknife", "wp_jackknife", "rp_pi_tpcf_jackknife"):
             # the covariance is the scatter of the sub-sample estimators (differences of nearly equal numbers):
             # 1e-8 relative to the largest element
             assert np.allclose(g, w, rtol=1e-8, atol=1e-10 * np.max(np.abs(w)), equal_nan=True), np.max(np.abs(g - w))
