@@ -50,6 +50,9 @@ struct BinQ {
     static constexpr bool JK = MODE == 3 || MODE == 6, REV = MODE == 6;
     typedef BinQParams Params;
     const Params &P;
+    double *shist;              // JK, wide rows: one shared-memory histogram for tiles whose points share a tag
+    bool wide, uni;             // JK: rows in global memory / the current tile's points share the tag `utag`
+    int utag;
     double rs0, rs1, rs2;       // REV: the (warp-uniform) periodic shift of the current span, NEGATED (x1 - shift_A = x1 + shift_B)
     uint32_t *hist;             // MODE 0: per-warp differential histogram (n0 * n1 u32); MODE 2: 64 rows of `rstride` u32
     double *fhist;              // MODE 1: per-warp differential float sums (n0 * n1); MODE 3: 64 rows of `rstride` f64
@@ -81,7 +84,7 @@ struct BinQ {
         else if (MODE == 1) acc = nh <= PRIV_MAX ? 8 * 32 * (nh | 1) : 8 * nh;
         else if (MODE == 2) acc = 4 * ((64 * (size_t)(p.n0 | 1) + 3) & ~(size_t)3);
         else if (MODE == 5) acc = 8 * 32 * (nh | 1);
-        else if (JK && nh > HTB_JK_SHARED_CELLS) acc = 0;                 // rows in global memory (P.grows)
+        else if (JK && nh > HTB_JK_SHARED_CELLS) acc = 8 * nh;            // rows in global memory (P.grows) + one histogram
         else acc = 8 * 64 * (nh | 1);
         return BAL_BYTES + 8 * ne + lut_bytes(p) + acc;
     }
@@ -99,10 +102,17 @@ struct BinQ {
         lut_s[0] = e_s + 8u * (uint32_t)ne;
         lut_s[1] = lut_s[0] + (uint32_t)((P.T[0] + 7) & ~7);
         rstride = (MODE >= 3 || MODE == 1) ? ((P.n0 * P.n1) | 1) : (P.n0 | 1);
-        if (JK && P.n0 * P.n1 > HTB_JK_SHARED_CELLS) {
+        wide = JK && P.n0 * P.n1 > HTB_JK_SHARED_CELLS;
+        uni = false; utag = 0;
+        shist = fhist;
+        if (wide) {
+            // Wide point rows (rp_pi_tpcf_jackknife): tiles whose points share one tag - nearly all of them, the
+            // sub-volumes being spatial - sum into ONE shared-memory histogram; only mixed tiles use per-point rows,
+            // which then live in this warp's slab of global memory.
             const unsigned gw = blockIdx.x * (unsigned)WARPS + (threadIdx.x >> 5);
             if (gw >= P.grows_warps) __trap();
             fhist = P.grows + (size_t)gw * 64u * (size_t)rstride;
+            for (int k = lane; k < P.n0 * P.n1; k += 32) shist[k] = 0.0;
         }
         priv = MODE == 5 || (MODE == 1 && P.n0 * P.n1 <= PRIV_MAX);
         vmask = 0;
@@ -110,7 +120,7 @@ struct BinQ {
         if (MODE == 0) { for (int k = lane; k < P.n0 * P.n1; k += 32) hist[k] = 0; }
         else if (MODE == 1) { for (int k = lane; k < (priv ? 32 * rstride : P.n0 * P.n1); k += 32) fhist[k] = 0.0; }
         else if (MODE == 2) { for (int k = lane; k < 64 * rstride; k += 32) hist[k] = 0; }
-        else { for (int k = lane; k < (MODE == 5 ? 32 : 64) * rstride; k += 32) fhist[k] = 0.0; }
+        else if (!wide) { for (int k = lane; k < (MODE == 5 ? 32 : 64) * rstride; k += 32) fhist[k] = 0.0; }
         tag[0] = tag[1] = 0;
         wa[0] = wb[0] = 0.0;
         x0 = y0 = z0 = x1 = y1 = z1 = 0.0;
@@ -135,6 +145,8 @@ struct BinQ {
         if (JK) {
             wa[0] = A.pay1[(size_t)idx[0] * 2]; wb[0] = A.pay1[(size_t)idx[1] * 2];
             tag[0] = (int)A.pay1[(size_t)idx[0] * 2 + 1]; tag[1] = (int)A.pay1[(size_t)idx[1] * 2 + 1];
+            utag = __shfl_sync(HTB_FULL, tag[0], 0);               // lane 0's first point is always valid
+            uni = wide && __all_sync(HTB_FULL, (!val[0] || tag[0] == utag) && (!val[1] || tag[1] == utag));
         }
     }
     __device__ __forceinline__ void set_shift(const double (&sh)[3], const WalkArrays &)
@@ -296,7 +308,8 @@ struct BinQ {
                     else atomicAdd(fhist + h, w);
                 }
                 else if (MODE == 2) atomicAdd(hist + slot * rstride + h, 1u);
-                else if (JK) atomicAdd(fhist + slot * rstride + h, REV ? lds_f64(bw + 16 * j) * pw : pw * lds_f64(bw + 16 * j));   // jweight's w1 * w2
+                else if (JK) atomicAdd(uni ? shist + h : fhist + slot * rstride + h,
+                                       REV ? lds_f64(bw + 16 * j) * pw : pw * lds_f64(bw + 16 * j));                  // jweight's w1 * w2
                 else if (MODE == 5) fhist[lane * rstride + h] += lds_f64(bw + 8 * j);                     // the weight is w2[j]
                 else atomicAdd(fhist + slot * rstride + h, lds_f64(bw + 8 * j));
             }
@@ -388,6 +401,12 @@ struct BinQ {
                     r[k] = 0.0;
                     if (cum != 0.0) atomicAdd(row + k, cum);
                 }
+            }
+        } else if (JK && uni) {
+            double *dst = P.fcounts + (size_t)utag * (size_t)nh;
+            for (int k = lane; k < nh; k += 32) {
+                const double x = shist[k];
+                if (x != 0.0) { atomicAdd(dst + k, x); shist[k] = 0.0; }
             }
         } else if (JK) {
             // fold the rows of this lane's points into the table row of their jackknife tag (differential cells)
