@@ -146,7 +146,7 @@ struct BinQ {
             wa[0] = A.pay1[(size_t)idx[0] * 2]; wb[0] = A.pay1[(size_t)idx[1] * 2];
             tag[0] = (int)A.pay1[(size_t)idx[0] * 2 + 1]; tag[1] = (int)A.pay1[(size_t)idx[1] * 2 + 1];
             utag = __shfl_sync(HTB_FULL, tag[0], 0);               // lane 0's first point is always valid
-            uni = wide && __all_sync(HTB_FULL, (!val[0] || tag[0] == utag) && (!val[1] || tag[1] == utag));
+            uni = __all_sync(HTB_FULL, (!val[0] || tag[0] == utag) && (!val[1] || tag[1] == utag));
         }
     }
     __device__ __forceinline__ void set_shift(const double (&sh)[3], const WalkArrays &)
@@ -308,8 +308,15 @@ struct BinQ {
                     else atomicAdd(fhist + h, w);
                 }
                 else if (MODE == 2) atomicAdd(hist + slot * rstride + h, 1u);
-                else if (JK) atomicAdd(uni ? shist + h : fhist + slot * rstride + h,
-                                       REV ? lds_f64(bw + 16 * j) * pw : pw * lds_f64(bw + 16 * j));                  // jweight's w1 * w2
+                else if (JK) {
+                    const double w = REV ? lds_f64(bw + 16 * j) * pw : pw * lds_f64(bw + 16 * j);                     // jweight's w1 * w2
+                    // one tag for the whole tile (the rule: sub-volumes are spatial): one histogram serves every point -
+                    // shared atomics for wide tables, else the replaying lane's private row (summed over the warp at the
+                    // end of the tile); mixed tiles keep a row per point
+                    if (!uni) atomicAdd(fhist + slot * rstride + h, w);
+                    else if (wide) atomicAdd(shist + h, w);
+                    else fhist[lane * rstride + h] += w;
+                }
                 else if (MODE == 5) fhist[lane * rstride + h] += lds_f64(bw + 8 * j);                     // the weight is w2[j]
                 else atomicAdd(fhist + slot * rstride + h, lds_f64(bw + 8 * j));
             }
@@ -404,9 +411,20 @@ struct BinQ {
             }
         } else if (JK && uni) {
             double *dst = P.fcounts + (size_t)utag * (size_t)nh;
-            for (int k = lane; k < nh; k += 32) {
-                const double x = shist[k];
-                if (x != 0.0) { atomicAdd(dst + k, x); shist[k] = 0.0; }
+            if (wide) {
+                for (int k = lane; k < nh; k += 32) {
+                    const double x = shist[k];
+                    if (x != 0.0) { atomicAdd(dst + k, x); shist[k] = 0.0; }
+                }
+            } else {
+                double *r = fhist + lane * rstride;
+                for (int k = 0; k < nh; ++k) {
+                    double x = r[k];
+                    r[k] = 0.0;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(HTB_FULL, x, o);
+                    if (lane == 0 && x != 0.0) atomicAdd(dst + k, x);
+                }
             }
         } else if (JK) {
             // fold the rows of this lane's points into the table row of their jackknife tag (differential cells)
