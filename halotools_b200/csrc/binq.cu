@@ -45,7 +45,7 @@ template <int KIND, int MODE>
 struct BinQ {
     static constexpr int DIM = KIND == 3 ? 2 : 3, NPAY = MODE == 1 ? HTB_MAX_NW : ((MODE == 3 || MODE == 6) ? 2 : (MODE >= 4 ? 1 : 0)), PPL = 2,
                          WARPS = MODE >= 3 ? 4 : 8,            // per-point f64 rows: smaller blocks, so that wide rows still fit
-                         MINBLOCKS = 2;
+                         MINBLOCKS = MODE >= 3 ? 4 : 2;        // 16 warps per SM either way (128 registers per thread)
     static constexpr bool TMA = true;
     static constexpr bool JK = MODE == 3 || MODE == 6, REV = MODE == 6;
     typedef BinQParams Params;
