@@ -10,7 +10,7 @@ ran = torch.from_numpy(synthetic.uniform_points(44, 5000000, 250.0)).cuda()
 rb = synthetic.config_rbins()
 for world, rank in ((1, 0), (2, 1), (4, 1), (8, 3)):
     _lib.set_shard(rank, world)
-    for ms in (None, "16"):
+    for ms in (None,):
         if ms is None: os.environ.pop("HTB_ITEMS_PER_WARP", None)
         else: os.environ["HTB_ITEMS_PER_WARP"] = ms
         row = []
