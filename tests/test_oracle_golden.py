@@ -93,3 +93,51 @@ def test_visited_pairs_config1():
     assert dm.mesh1.num_divs == [12, 12, 12] and dm.mesh2.num_divs == [12, 12, 12]
     dm2 = oracle.build_double_mesh_3d(s, s, [20.0] * 3, 250.0, None, None)[0]
     assert abs(dm2.visited_pairs() - 1.563e8) / 1.563e8 < 2e-3
+
+
+# ---------------------------------------------------------------- O(N^2) numpy cross-checks of the 8(f) restatements
+def _min_image(a, b, L):
+    d = a[:, None, :] - b[None, :, :]
+    if L is not None:
+        d = d - L * np.round(d / L)
+    return d
+
+
+@pytest.mark.parametrize("period", [1.0, None])
+def test_oracle_8f_counters_vs_brute_force(period):
+    """independent of the mesh / window logic: all-pairs numpy with the minimum image (search lengths < L/3, so the
+    mesh's image is the nearest one); integer results identical, float sums to 1e-12"""
+    rng = np.random.RandomState(3)
+    s1, s2 = rng.uniform(0, 1, (300, 3)), rng.uniform(0, 1, (400, 3))
+    w1, w2 = rng.uniform(0.5, 1.5, 300), rng.uniform(0.5, 1.5, 400)
+    t1, t2 = rng.randint(1, 5, 300), rng.randint(1, 5, 400)
+    rb = np.array([0.0, 0.05, 0.11, 0.2, 0.3])
+    pi = np.array([0.0, 0.07, 0.25])
+    d = _min_image(s1, s2, period)
+    dsq = d[..., 0] ** 2 + d[..., 1] ** 2 + d[..., 2] ** 2
+    dxy, dz = d[..., 0] ** 2 + d[..., 1] ** 2, d[..., 2] ** 2
+    in_r = dsq[..., None] <= (rb ** 2)[None, None, :]
+    in_rp = dxy[..., None] <= (rb ** 2)[None, None, :]
+    in_pi = dz[..., None] <= (pi ** 2)[None, None, :]
+    # npairs_per_object_3d, npairs_projected
+    assert np.array_equal(oracle.npairs_per_object_3d(s1, s2, rb, period=period), in_r.sum(axis=1))
+    assert np.array_equal(oracle.npairs_projected(s1, s2, rb[1:], 0.25, period=period),
+                          (in_rp[..., 1:] & in_pi[..., 2:3]).sum(axis=(0, 1)))
+    # marked_npairs_xy_z with product marks
+    ww = w1[:, None] * w2[None, :]
+    want = np.einsum("ij,ijk,ijg->kg", ww, in_rp.astype(float), in_pi.astype(float))
+    got = oracle.marked_npairs_xy_z(s1, s2, rb, pi, period=period, weights1=w1, weights2=w2, weight_func_id=1)
+    assert np.allclose(got, want, rtol=1e-12, atol=0)
+    # jackknife: jweight restated with masks (npairs_jackknife_3d_engine.pyx:283-289)
+    got = oracle.npairs_jackknife_3d(s1, s2, rb, t1, t2, 4, period=period, weights1=w1, weights2=w2)
+    for s in range(5):
+        a, b = (t1 == s)[:, None], (t2 == s)[None, :]
+        jw = ww if s == 0 else np.where(a & b, 0.0, np.where(a | b, 0.5 * ww, ww))
+        assert np.allclose(got[s], np.einsum("ij,ijk->k", jw, in_r.astype(float)), rtol=1e-12, atol=1e-12)
+    # 2-d weighted counters
+    per2 = None if period is None else [1.0, 1.0]
+    d2 = _min_image(s1[:, :2], s2[:, :2], period)
+    in2 = (d2[..., 0] ** 2 + d2[..., 1] ** 2)[..., None] <= (rb ** 2)[None, None, :]
+    rows = np.einsum("j,ijk->ik", w2, in2.astype(float))
+    assert np.allclose(oracle.weighted_npairs_per_object_xy(s1[:, :2], s2[:, :2], w2, rb, period=per2), rows, rtol=1e-12, atol=0)
+    assert np.allclose(oracle.weighted_npairs_xy(s1[:, :2], s2[:, :2], w2, rb, period=per2), rows.sum(axis=0), rtol=1e-12)
