@@ -17,6 +17,12 @@
  * coordinate / weight arrays are device pointers on the current CUDA device (outputs
  * and bins are always host).  All functions return 0 on success, non-zero on error
  * (htb_last_error() gives the message).  No torch types appear here.
+ *
+ * Threading: device, stream, shard and upload-cache settings are per calling thread; every engine call is
+ * synchronous (it returns when its outputs are in host memory).  Calls from several threads are fine on DIFFERENT
+ * devices; on one device they must be serialised by the caller (the pinned staging ring for pageable inputs and
+ * large outputs is shared per device) - the reference's own parallelism (multiprocessing over cell ranges) maps
+ * to one process per GPU (htb_set_shard) instead.
  */
 #ifndef HALOTOOLS_B200_H
 #define HALOTOOLS_B200_H
