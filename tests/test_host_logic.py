@@ -215,6 +215,24 @@ with distributed.local_counts() as partial:
     same = partial.add(a)                                               # registered twice, reduced once
 assert np.array_equal(a, np.diff(full)) and same is a and np.array_equal(b, 0.5 * full)
 assert np.array_equal(distributed.allreduce_sum(part), full)            # back to one all-reduce per call
+# a whole statistic over the two ranks: hb.tpcf with its pair counter served by the oracle on THIS rank's cell range
+# (what the GPU engine does per rank); the counts of DD, DR and RR are all-reduced once, at the end of tpcf's block
+import importlib
+import halotools_b200 as hb
+tp = importlib.import_module("halotools_b200.two_point_clustering.tpcf")
+calls = []
+def sharded_npairs_3d(a, b, rbins, period=None, num_threads=1, approx_cell1_size=None, approx_cell2_size=None):
+    kw = dict(period=period, approx_cell1_size=approx_cell1_size, approx_cell2_size=approx_cell2_size)
+    _, mesh = oracle.npairs_3d(a[:1], b[:1], rbins, return_mesh=True, **kw) if period is not None else oracle.npairs_3d(a, b, rbins, return_mesh=True, **kw)
+    rng = distributed.cell1_range(mesh.mesh1.ncells)
+    calls.append(rng)
+    return distributed.allreduce_sum(oracle.npairs_3d(a, b, rbins, cell1_range=rng, **kw))
+tp.npairs_3d = sharded_npairs_3d
+fn, targs, tkw = cases.get("tpcf_randoms_Landy-Szalay")
+xi = hb.tpcf(*targs, **tkw)
+want = np.load(%(root)r + "/tests/golden/golden.npz")["tpcf_randoms_Landy-Szalay/0"]
+assert np.allclose(xi, want, rtol=1e-10, atol=1e-12), (xi, want)
+assert len(calls) == 3 and all(c[0] < c[1] for c in calls)
 dist.destroy_process_group()
 print("rank", sys.argv[1], "ok", first, last)
 '''
