@@ -77,6 +77,7 @@ TRIMMED_INITS = {
         "from .array_utils import *\nfrom .array_indexing_manipulations import *\nfrom .spherical_geometry import *\n",
     "halotools/mock_observables/__init__.py":
         "from .pair_counters import *\n"
+        "from .catalog_analysis_helpers import return_xyz_formatted_array, apply_zspace_distortion, cuboid_subvolume_labels\n"
         "from .two_point_clustering import tpcf, wp, rp_pi_tpcf, marked_tpcf, tpcf_jackknife, wp_jackknife, s_mu_tpcf, tpcf_multipole, tpcf_one_two_halo_decomp, angular_tpcf, rp_pi_tpcf_jackknife\n"
         "from .surface_density import mean_delta_sigma, weighted_npairs_xy\n"
         "from .surface_density.weighted_npairs_per_object_xy import weighted_npairs_per_object_xy\n"
@@ -116,10 +117,13 @@ TRIMMED_INITS = {
     "halotools/mock_observables/surface_density/__init__.py":
         "from .mean_delta_sigma import mean_delta_sigma\n"
         "from .weighted_npairs_xy import weighted_npairs_xy\n",
-    # catalog_analysis_helpers.py (cuboid_subvolume_labels, used by the jackknife statistics) imports two names from
-    # sub-packages that need astropy; neither is touched by the functions run here
+    # catalog_analysis_helpers.py (cuboid_subvolume_labels, return_xyz_formatted_array) imports two names from
+    # sub-packages that need astropy: the cosmology defaults are not used (the golden cases pass their own object),
+    # enforce_periodicity_of_box is the one-line stand-in below
     "halotools/empirical_models/__init__.py":
-        "def enforce_periodicity_of_box(*args, **kwargs):\n    raise NotImplementedError('not part of the hot path')\n",
+        "def enforce_periodicity_of_box(coords, box_length, **kwargs):\n"
+        "    # stand-in for empirical_models/model_helpers.py:164-169 (that package needs astropy): the same one line\n"
+        "    return coords % box_length\n",
     "halotools/sim_manager/__init__.py": "",
     "halotools/sim_manager/sim_defaults.py": "default_cosmology = None\ndefault_redshift = 0.0\n",
     "halotools/mock_observables/surface_density/engines/__init__.py":

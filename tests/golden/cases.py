@@ -15,6 +15,13 @@ NUM_WEIGHTS = {1: 1, 2: 1, 3: 2, 4: 2, 5: 2, 6: 2, 7: 2, 8: 2, 9: 2, 10: 2, 11: 
                12: 4, 13: 4, 14: 3, 15: 3, 16: 5, 17: 5}
 
 
+class FlatLCDM(object):
+    """minimal cosmology object for the redshift-space-distortion cases (only ``efunc`` is used)"""
+
+    def efunc(self, z):
+        return np.sqrt(0.3 * (1.0 + z) ** 3 + 0.7)
+
+
 def pts(seed, n, L=1.0, dim=3):
     return np.random.RandomState(seed).uniform(0, L, (n, dim))
 
@@ -262,6 +269,17 @@ def _cases():
     C["rp_pi_jk_auto"] = ("rp_pi_tpcf_jackknife", (s1, ranj, rpj, pij), dict(Nsub=2, period=1.0))
     C["rp_pi_jk_cross_ls"] = ("rp_pi_tpcf_jackknife", (s1, ranj, rpw, np.linspace(0, 0.25, 4)),
                               dict(Nsub=[2, 2, 3], sample2=s2, period=1.0, estimator="Landy-Szalay"))
+    # input formatting step: positions + redshift-space distortions
+    rngx = np.random.RandomState(81)
+    xx, yy, zz = rngx.uniform(-50, 300, (3, 1000))
+    vv = rngx.normal(0, 300, 1000)
+    C["xyz_plain"] = ("return_xyz_formatted_array", (xx, yy, zz), dict(period=250.0))
+    C["xyz_rsd_z0"] = ("return_xyz_formatted_array", (xx, yy, zz),
+                       dict(period=[250.0, 200.0, 100.0], velocity=vv, velocity_distortion_dimension="z", cosmology=FlatLCDM()))
+    C["xyz_rsd_z07_mask"] = ("return_xyz_formatted_array", (xx, yy, zz),
+                             dict(period=250.0, velocity=vv, velocity_distortion_dimension="x", redshift=0.7,
+                                  cosmology=FlatLCDM(), mask=rngx.rand(1000) > 0.5))
+    C["zspace_distortion"] = ("apply_zspace_distortion", (zz, vv, 0.5, FlatLCDM(), 250.0), dict())
     return C
 
 

@@ -24,7 +24,8 @@ from tests.golden import cases
 
 STAT_FUNCS = ("tpcf", "wp", "rp_pi_tpcf", "marked_tpcf", "tpcf_jackknife", "wp_jackknife", "rp_pi_tpcf_jackknife",
               "s_mu_tpcf", "tpcf_one_two_halo_decomp", "angular_tpcf", "total_mass_enclosed_in_stack_of_cylinders",
-              "surface_density_in_annulus", "surface_density_in_cylinder", "total_mass_enclosed_per_cylinder")
+              "surface_density_in_annulus", "surface_density_in_cylinder", "total_mass_enclosed_per_cylinder",
+              "return_xyz_formatted_array", "apply_zspace_distortion")
 STAT_CASES = [n for n in cases.names() if cases._cases()[n][0] in STAT_FUNCS]
 
 
