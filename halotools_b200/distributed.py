@@ -12,7 +12,7 @@ every call counts all cells (N independent replicas).
 """
 import numpy as np
 
-_state = {"enabled": False, "group": None, "balanced": False, "local": 0}
+_state = {"enabled": False, "group": None, "balanced": False, "local": 0, "cells": None}
 
 
 def enable(group=None, balanced=None):
@@ -79,8 +79,28 @@ def split_cells(ncells, world, work=None):
     return [(int(cuts[r]), int(cuts[r + 1])) for r in range(world)]
 
 
+class cell_range(object):
+    """Context manager: the pair counters inside count only the reference mesh1 cells [first, last) - the
+    ``cell1_tuple`` every reference engine takes (npairs_3d_engine.pyx:17,103), which the reference front-ends
+    never expose.  Used to compare full-size counts with the reference on a sample of its cells."""
+
+    def __init__(self, first, last):
+        self.range = (int(first), int(last))
+
+    def __enter__(self):
+        self.saved = _state["cells"]
+        _state["cells"] = self.range
+        return self
+
+    def __exit__(self, *exc):
+        _state["cells"] = self.saved
+        return False
+
+
 def cell1_range(ncells, work=None):
     """This rank's (first_cell1, last_cell1); the full range when the engine does the (balanced) cut."""
+    if _state["cells"] is not None:
+        return max(0, _state["cells"][0]), min(ncells, _state["cells"][1])
     if _state["balanced"]:
         return 0, ncells
     rank, world = _rank_world()

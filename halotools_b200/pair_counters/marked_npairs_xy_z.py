@@ -9,6 +9,7 @@ from .. import distributed as _dist
 from ..custom_exceptions import HalotoolsError
 from .marked_npairs_3d import _process_one_weights
 from .mesh_helpers import _set_approximate_cell_sizes, double_mesh_geometry
+from ._args import sample_columns
 from .npairs_xy_z import _npairs_xy_z_process_args
 
 __all__ = ("marked_npairs_xy_z",)
@@ -44,8 +45,7 @@ def marked_npairs_xy_z(sample1, sample2, rp_bins, pi_bins,
 
     counts = np.zeros((len(rp_bins), len(pi_bins)), dtype=np.float64)
     first, last = _dist.cell1_range(geom.ncells1)
-    c1 = _lib.Columns([x1in, y1in, z1in])
-    c2 = c1 if (x2in is x1in and y2in is y1in and z2in is z1in) else _lib.Columns([x2in, y2in, z2in])
+    c1, c2 = sample_columns([x1in, y1in, z1in], [x2in, y2in, z2in], host_only="marked_npairs_xy_z")
     w1 = np.ascontiguousarray(weights1, dtype=np.float64)
     w2 = w1 if weights2 is weights1 else np.ascontiguousarray(weights2, dtype=np.float64)
     g = geom.as_struct()

@@ -3,14 +3,13 @@
 signature, same argument processing and errors; the mesh build and the pair loop run on the GPU
 (csrc/mesh.cu + csrc/count.cu through htb_npairs_3d_engine)."""
 import ctypes
-import multiprocessing
 
 import numpy as np
 
 from .. import _lib
 from .. import distributed as _dist
-from ..helpers import array_is_monotonic, custom_len, check_num_threads_arg
-from .mesh_helpers import _enclose_in_box, _set_approximate_cell_sizes, double_mesh_geometry
+from ._args import process_counter_args, sample_columns
+from .mesh_helpers import _set_approximate_cell_sizes, double_mesh_geometry
 
 __all__ = ("npairs_3d",)
 
@@ -39,8 +38,7 @@ def npairs_3d(sample1, sample2, rbins, period=None, num_threads=1,
 
     counts = np.zeros(len(rbins), dtype=np.int64)
     first, last = _dist.cell1_range(geom.ncells1)
-    c1 = _lib.Columns([x1in, y1in, z1in])
-    c2 = c1 if (x2in is x1in and y2in is y1in and z2in is z1in) else _lib.Columns([x2in, y2in, z2in])
+    c1, c2 = sample_columns([x1in, y1in, z1in], [x2in, y2in, z2in])
     g = geom.as_struct()
     rb = np.ascontiguousarray(rbins, dtype=np.float64)
     _lib.run_engine(
@@ -55,59 +53,11 @@ def npairs_3d(sample1, sample2, rbins, period=None, num_threads=1,
 
 def _npairs_3d_process_args(sample1, sample2, rbins, period,
                             num_threads, approx_cell1_size, approx_cell2_size):
-    """Same checks, defaults and error strings as npairs_3d.py:153-213."""
-    num_threads = check_num_threads_arg(num_threads)
-
-    same = sample2 is sample1
-    x1 = sample1[:, 0]
-    y1 = sample1[:, 1]
-    z1 = sample1[:, 2]
-    if same:
-        x2, y2, z2 = x1, y1, z1
-    else:
-        x2 = sample2[:, 0]
-        y2 = sample2[:, 1]
-        z2 = sample2[:, 2]
-    rbins = np.atleast_1d(rbins).astype('f8')
-    rmax = np.max(rbins)
-
-    try:
-        assert rbins.ndim == 1
-        assert len(rbins) > 1
-        if len(rbins) > 2:
-            assert array_is_monotonic(rbins, strict=True) == 1
-    except AssertionError:
-        msg = "Input ``rbins`` must be a monotonically increasing 1D array with at least two entries"
-        raise ValueError(msg)
-
-    if period is None:
-        if getattr(sample1, "is_cuda", False) or getattr(sample2, "is_cuda", False):
-            raise ValueError("device-resident samples need an explicit ``period``")
-        PBCs = False
-        x1, y1, z1, x2, y2, z2, period = (
-            _enclose_in_box(x1, y1, z1, x2, y2, z2,
-                            min_size=[rmax*3.0, rmax*3.0, rmax*3.0]))
-    else:
-        PBCs = True
-        period = np.atleast_1d(period).astype(float)
-        if len(period) == 1:
-            period = np.array([period[0]]*3)
-        try:
-            assert np.all(period < np.inf)
-            assert np.all(period > 0)
-        except AssertionError:
-            msg = "Input ``period`` must be a bounded positive number in all dimensions"
-            raise ValueError(msg)
-
-    if approx_cell1_size is None:
-        approx_cell1_size = [rmax, rmax, rmax]
-    elif custom_len(approx_cell1_size) == 1:
-        approx_cell1_size = [approx_cell1_size, approx_cell1_size, approx_cell1_size]
-    if approx_cell2_size is None:
-        approx_cell2_size = [rmax, rmax, rmax]
-    elif custom_len(approx_cell2_size) == 1:
-        approx_cell2_size = [approx_cell2_size, approx_cell2_size, approx_cell2_size]
-
-    return (x1, y1, z1, x2, y2, z2,
+    """The checks, defaults and error strings of npairs_3d.py:153-213 (shared processor: ``_args.py``)."""
+    (c1, c2, (rbins,), period, num_threads, PBCs,
+     approx_cell1_size, approx_cell2_size) = process_counter_args(
+        3, sample1, sample2, [(rbins, "rbins")], lambda b: [np.max(b[0])] * 3,
+        period, num_threads, approx_cell1_size, approx_cell2_size)
+    return (c1[0], c1[1], c1[2], c2[0], c2[1], c2[2],
             rbins, period, num_threads, PBCs,
             approx_cell1_size, approx_cell2_size)

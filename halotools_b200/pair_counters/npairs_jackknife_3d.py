@@ -10,6 +10,7 @@ from .. import _lib
 from .. import distributed as _dist
 from ..custom_exceptions import HalotoolsError
 from .mesh_helpers import _set_approximate_cell_sizes, double_mesh_geometry
+from ._args import sample_columns
 from .npairs_3d import _npairs_3d_process_args
 from .npairs_xy_z import _npairs_xy_z_process_args
 
@@ -72,8 +73,7 @@ def npairs_jackknife_xy_z(sample1, sample2, rp_bins, pi_bins,
 def _run(entry, geom, cols1, cols2, weights1, weights2, jtags1, jtags2, N_samples, bins, counts, keep):
     first, last = _dist.cell1_range(geom.ncells1)
     same = all(a is b for a, b in zip(cols1, cols2))
-    c1 = _lib.Columns(list(cols1))
-    c2 = c1 if same else _lib.Columns(list(cols2))
+    c1, c2 = sample_columns(cols1, cols1 if same else cols2, host_only="the jackknife pair counters")
     w1 = np.ascontiguousarray(weights1, dtype=np.float64)
     w2 = np.ascontiguousarray(weights2, dtype=np.float64)
     t1 = np.ascontiguousarray(jtags1, dtype=np.int64)

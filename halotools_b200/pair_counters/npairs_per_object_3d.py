@@ -7,6 +7,7 @@ import numpy as np
 from .. import _lib
 from .. import distributed as _dist
 from .mesh_helpers import _set_approximate_cell_sizes, double_mesh_geometry
+from ._args import sample_columns
 from .npairs_3d import _npairs_3d_process_args
 
 __all__ = ("npairs_per_object_3d",)
@@ -28,8 +29,7 @@ def npairs_per_object_3d(sample1, sample2, rbins, period=None,
         approx_cell1_size, approx_cell2_size, period)
     geom = double_mesh_geometry(3, approx_cell1_size, approx_cell2_size, search, period, PBCs)
 
-    c1 = _lib.Columns([x1in, y1in, z1in])
-    c2 = c1 if (x2in is x1in and y2in is y1in and z2in is z1in) else _lib.Columns([x2in, y2in, z2in])
+    c1, c2 = sample_columns([x1in, y1in, z1in], [x2in, y2in, z2in], host_only="npairs_per_object_3d")
     counts = np.zeros((c1.n, len(rbins)), dtype=np.int64)
     first, last = _dist.cell1_range(geom.ncells1)
     g = geom.as_struct()

@@ -8,6 +8,7 @@ from .. import _lib
 from .. import distributed as _dist
 from ..helpers import array_is_monotonic
 from .mesh_helpers import _set_approximate_cell_sizes, double_mesh_geometry
+from ._args import sample_columns
 from .npairs_3d import _npairs_3d_process_args
 
 __all__ = ("npairs_s_mu",)
@@ -46,8 +47,7 @@ def npairs_s_mu(sample1, sample2, s_bins, mu_bins, period=None, num_threads=1,
     # linear, so the all-reduce of the per-rank results equals the single-GPU answer.
     counts = np.zeros((len(s_bins), len(mu_bins_prime)), dtype=np.int64)
     first, last = _dist.cell1_range(geom.ncells1)
-    c1 = _lib.Columns([x1in, y1in, z1in])
-    c2 = c1 if (x2in is x1in and y2in is y1in and z2in is z1in) else _lib.Columns([x2in, y2in, z2in])
+    c1, c2 = sample_columns([x1in, y1in, z1in], [x2in, y2in, z2in])
     g = geom.as_struct()
     sb = np.ascontiguousarray(s_bins, dtype=np.float64)
     mb = np.ascontiguousarray(mu_bins_prime, dtype=np.float64)
@@ -57,5 +57,5 @@ def npairs_s_mu(sample1, sample2, s_bins, mu_bins, period=None, num_threads=1,
         c2.ptrs[0], c2.ptrs[1], c2.ptrs[2], ctypes.c_int64(c2.stride), ctypes.c_int64(c2.n),
         _lib._dp(sb), ctypes.c_int32(len(sb)), _lib._dp(mb), ctypes.c_int32(len(mb)),
         ctypes.c_int64(first), ctypes.c_int64(last),
-        counts.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)))
+        counts.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), device=c1.device)
     return np.array(_dist.allreduce_sum(counts))

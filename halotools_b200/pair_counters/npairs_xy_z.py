@@ -6,8 +6,8 @@ import numpy as np
 
 from .. import _lib
 from .. import distributed as _dist
-from ..helpers import array_is_monotonic, custom_len, check_num_threads_arg
-from .mesh_helpers import _enclose_in_box, _set_approximate_cell_sizes, double_mesh_geometry
+from ._args import process_counter_args, sample_columns
+from .mesh_helpers import _set_approximate_cell_sizes, double_mesh_geometry
 
 __all__ = ("npairs_xy_z",)
 
@@ -30,8 +30,7 @@ def npairs_xy_z(sample1, sample2, rp_bins, pi_bins, period=None, num_threads=1,
 
     counts = np.zeros((len(rp_bins), len(pi_bins)), dtype=np.int64)
     first, last = _dist.cell1_range(geom.ncells1)
-    c1 = _lib.Columns([x1in, y1in, z1in])
-    c2 = c1 if (x2in is x1in and y2in is y1in and z2in is z1in) else _lib.Columns([x2in, y2in, z2in])
+    c1, c2 = sample_columns([x1in, y1in, z1in], [x2in, y2in, z2in])
     g = geom.as_struct()
     rp = np.ascontiguousarray(rp_bins, dtype=np.float64)
     pi = np.ascontiguousarray(pi_bins, dtype=np.float64)
@@ -41,71 +40,19 @@ def npairs_xy_z(sample1, sample2, rp_bins, pi_bins, period=None, num_threads=1,
         c2.ptrs[0], c2.ptrs[1], c2.ptrs[2], ctypes.c_int64(c2.stride), ctypes.c_int64(c2.n),
         _lib._dp(rp), ctypes.c_int32(len(rp)), _lib._dp(pi), ctypes.c_int32(len(pi)),
         ctypes.c_int64(first), ctypes.c_int64(last),
-        counts.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), extra_flags=_lib.cache_flags(c1, c2, PBCs))
+        counts.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), device=c1.device,
+        extra_flags=_lib.cache_flags(c1, c2, PBCs))
     return np.array(_dist.allreduce_sum(counts))
-
-
-def _check_bins(bins, name):
-    bins = np.atleast_1d(bins).astype('f8')
-    try:
-        assert bins.ndim == 1
-        assert len(bins) > 1
-        if len(bins) > 2:
-            assert array_is_monotonic(bins, strict=True) == 1
-    except AssertionError:
-        msg = ("Input ``%s`` must be a monotonically increasing 1D array "
-               "with at least two entries" % name)
-        raise ValueError(msg)
-    return bins
 
 
 def _npairs_xy_z_process_args(sample1, sample2, rp_bins, pi_bins, period,
                               num_threads, approx_cell1_size, approx_cell2_size):
-    """Same checks, defaults and error strings as npairs_xy_z.py:166-237."""
-    num_threads = check_num_threads_arg(num_threads)
-
-    same = sample2 is sample1
-    x1 = sample1[:, 0]
-    y1 = sample1[:, 1]
-    z1 = sample1[:, 2]
-    if same:
-        x2, y2, z2 = x1, y1, z1
-    else:
-        x2 = sample2[:, 0]
-        y2 = sample2[:, 1]
-        z2 = sample2[:, 2]
-
-    rp_bins = _check_bins(rp_bins, "rp_bins")
-    rp_max = np.max(rp_bins)
-    pi_bins = _check_bins(pi_bins, "pi_bins")
-    pi_max = np.max(pi_bins)
-
-    if period is None:
-        PBCs = False
-        x1, y1, z1, x2, y2, z2, period = (
-            _enclose_in_box(x1, y1, z1, x2, y2, z2,
-                            min_size=[rp_max*3.0, rp_max*3.0, pi_max*3.0]))
-    else:
-        PBCs = True
-        period = np.atleast_1d(period).astype(float)
-        if len(period) == 1:
-            period = np.array([period[0]]*3)
-        try:
-            assert np.all(period < np.inf)
-            assert np.all(period > 0)
-        except AssertionError:
-            msg = "Input ``period`` must be a bounded positive number in all dimensions"
-            raise ValueError(msg)
-
-    if approx_cell1_size is None:
-        approx_cell1_size = [rp_max, rp_max, pi_max]
-    elif custom_len(approx_cell1_size) == 1:
-        approx_cell1_size = [approx_cell1_size, approx_cell1_size, approx_cell1_size]
-    if approx_cell2_size is None:
-        approx_cell2_size = [rp_max, rp_max, pi_max]
-    elif custom_len(approx_cell2_size) == 1:
-        approx_cell2_size = [approx_cell2_size, approx_cell2_size, approx_cell2_size]
-
-    return (x1, y1, z1, x2, y2, z2,
+    """The checks, defaults and error strings of npairs_xy_z.py:166-237 (shared processor: ``_args.py``)."""
+    (c1, c2, (rp_bins, pi_bins), period, num_threads, PBCs,
+     approx_cell1_size, approx_cell2_size) = process_counter_args(
+        3, sample1, sample2, [(rp_bins, "rp_bins"), (pi_bins, "pi_bins")],
+        lambda b: [np.max(b[0]), np.max(b[0]), np.max(b[1])],
+        period, num_threads, approx_cell1_size, approx_cell2_size)
+    return (c1[0], c1[1], c1[2], c2[0], c2[1], c2[2],
             rp_bins, pi_bins, period, num_threads, PBCs,
             approx_cell1_size, approx_cell2_size)

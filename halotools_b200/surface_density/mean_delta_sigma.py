@@ -8,6 +8,7 @@ from .. import _lib
 from .. import distributed as _dist
 from ..helpers import (custom_len, enforce_sample_has_correct_shape, enforce_sample_respects_pbcs,
                        get_num_threads, get_period, get_separation_bins_array)
+from ..pair_counters._args import sample_columns
 from ..pair_counters.mesh_helpers import (_enclose_in_box, _enclose_in_square,
                                           _set_approximate_2d_cell_sizes, double_mesh_geometry)
 
@@ -43,10 +44,7 @@ def mean_delta_sigma(galaxies, particles, effective_particle_masses,
     # (Ngal, nbin) rows never cross PCIe
     delta_sigma = np.zeros((n1, nbin) if per_object else (nbin,), dtype=np.float64)
     first, last = _dist.cell1_range(geom.ncells1)
-    c1 = _lib.Columns([x1in, y1in])
-    c2 = _lib.Columns([x2in, y2in])
-    if c1.device != c2.device:
-        raise TypeError("galaxies and particles must both be host arrays or both be CUDA tensors")
+    c1, c2 = sample_columns([x1in, y1in], [x2in, y2in])
     extra = (_lib.FLAG_UNIFORM_MASS if use_scalar else 0) | (0 if per_object else _lib.FLAG_COLUMN_SUM)
     if c1.device and not use_scalar:
         raise TypeError("device-resident samples need a scalar ``effective_particle_masses``")

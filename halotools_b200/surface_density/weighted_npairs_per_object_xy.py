@@ -11,6 +11,7 @@ from .. import distributed as _dist
 from ..helpers import (enforce_sample_has_correct_shape, enforce_sample_respects_pbcs, get_num_threads,
                        get_period, get_separation_bins_array)
 from ..pair_counters.mesh_helpers import _set_approximate_2d_cell_sizes, double_mesh_geometry
+from ..pair_counters._args import sample_columns
 from .weighted_npairs_xy import _weighted_npairs_xy_process_args, weighted_npairs_xy
 
 __all__ = ("weighted_npairs_per_object_xy", "total_mass_enclosed_per_cylinder",
@@ -35,8 +36,7 @@ def weighted_npairs_per_object_xy(sample1, sample2, sample2_mass, rp_bins,
         approx_cell1_size, approx_cell2_size, period)
     geom = double_mesh_geometry(2, approx_cell1_size, approx_cell2_size, search, period[:2], PBCs)
 
-    c1 = _lib.Columns([x1in, y1in])
-    c2 = _lib.Columns([x2in, y2in])
+    c1, c2 = sample_columns([x1in, y1in], [x2in, y2in], host_only="weighted_npairs_per_object_xy")
     counts = np.zeros((c1.n, len(rp_bins)), dtype=np.float64)
     first, last = _dist.cell1_range(geom.ncells1)
     w2 = np.ascontiguousarray(w2in, dtype=np.float64)

@@ -6,9 +6,8 @@ import numpy as np
 
 from .. import _lib
 from .. import distributed as _dist
-from ..helpers import array_is_monotonic, custom_len, check_num_threads_arg
-from ..pair_counters.mesh_helpers import (_enclose_in_square, _set_approximate_2d_cell_sizes,
-                                          double_mesh_geometry)
+from ..pair_counters._args import process_counter_args, sample_columns
+from ..pair_counters.mesh_helpers import _set_approximate_2d_cell_sizes, double_mesh_geometry
 
 __all__ = ("weighted_npairs_xy",)
 
@@ -32,8 +31,7 @@ def weighted_npairs_xy(sample1, sample2, sample2_mass, rp_bins,
 
     counts = np.zeros(len(rp_bins), dtype=np.float64)
     first, last = _dist.cell1_range(geom.ncells1)
-    c1 = _lib.Columns([x1in, y1in])
-    c2 = _lib.Columns([x2in, y2in])
+    c1, c2 = sample_columns([x1in, y1in], [x2in, y2in], host_only="weighted_npairs_xy")
     w2 = np.ascontiguousarray(w2in, dtype=np.float64)
     g = geom.as_struct()
     rb = np.ascontiguousarray(rp_bins, dtype=np.float64)
@@ -48,53 +46,12 @@ def weighted_npairs_xy(sample1, sample2, sample2_mass, rp_bins,
 
 def _weighted_npairs_xy_process_args(sample1, sample2, w2, rp_bins, period,
                                      num_threads, approx_cell1_size, approx_cell2_size):
-    """Same checks, defaults and error strings as weighted_npairs_xy.py:153-217."""
-    num_threads = check_num_threads_arg(num_threads)
-
-    x1 = sample1[:, 0]
-    y1 = sample1[:, 1]
-    x2 = sample2[:, 0]
-    y2 = sample2[:, 1]
-
+    """The checks, defaults and error strings of weighted_npairs_xy.py:153-217 (shared processor:
+    ``pair_counters/_args.py``, two mesh dimensions)."""
     assert w2.shape[0] == sample2.shape[0]
-
-    rp_bins = np.atleast_1d(rp_bins).astype('f8')
-    try:
-        assert rp_bins.ndim == 1
-        assert len(rp_bins) > 1
-        if len(rp_bins) > 2:
-            assert array_is_monotonic(rp_bins, strict=True) == 1
-    except AssertionError:
-        msg = ("Input ``rp_bins`` must be a monotonically increasing 1D array "
-               "with at least two entries")
-        raise ValueError(msg)
-    rp_max = np.max(rp_bins)
-
-    if period is None:
-        PBCs = False
-        x1, y1, x2, y2, period = (
-            _enclose_in_square(x1, y1, x2, y2,
-                               min_size=[rp_max*3.0, rp_max*3.0]))
-    else:
-        PBCs = True
-        period = np.atleast_1d(period).astype(float)
-        if len(period) == 1:
-            period = np.array([period[0]]*2)
-        try:
-            assert np.all(period < np.inf)
-            assert np.all(period > 0)
-        except AssertionError:
-            msg = "Input ``period`` must be a bounded positive number in all dimensions"
-            raise ValueError(msg)
-
-    if approx_cell1_size is None:
-        approx_cell1_size = [rp_max, rp_max]
-    elif custom_len(approx_cell1_size) == 1:
-        approx_cell1_size = [approx_cell1_size, approx_cell1_size]
-    if approx_cell2_size is None:
-        approx_cell2_size = [rp_max, rp_max]
-    elif custom_len(approx_cell2_size) == 1:
-        approx_cell2_size = [approx_cell2_size, approx_cell2_size]
-
-    return (x1, y1, x2, y2, w2, rp_bins, period, num_threads, PBCs,
+    (c1, c2, (rp_bins,), period, num_threads, PBCs,
+     approx_cell1_size, approx_cell2_size) = process_counter_args(
+        2, sample1, sample2, [(rp_bins, "rp_bins")], lambda b: [np.max(b[0])] * 2,
+        period, num_threads, approx_cell1_size, approx_cell2_size)
+    return (c1[0], c1[1], c2[0], c2[1], w2, rp_bins, period, num_threads, PBCs,
             approx_cell1_size, approx_cell2_size)

@@ -216,7 +216,9 @@ def marked_npairs_3d(sample1, sample2, rbins, weight_func_id, period=None, weigh
 
 def mean_delta_sigma(galaxies, particles, effective_particle_masses, rp_bins, period=None,
                      approx_cell1_size=None, approx_cell2_size=None, num_threads=1, per_object=False,
-                     cell1_range=None):
+                     cell1_range=None, return_abs=False):
+    """``return_abs``: also return A_ik, the sum of the absolute values of the terms accumulated into element
+    (i, k) - the error scale of the SURVEY 8d per-object parity gate (per_object rows, input order)."""
     galaxies = np.asarray(galaxies, dtype=np.float64)
     particles = np.asarray(particles, dtype=np.float64)
     rp_bins = _f8(np.atleast_1d(rp_bins))
@@ -246,14 +248,19 @@ def mean_delta_sigma(galaxies, particles, effective_particle_masses, rp_bins, pe
     first, last = _range(dm, cell1_range)
     n1 = galaxies.shape[0]
     out = np.zeros((n1, len(rp_bins) - 1), dtype=np.float64)
+    absout = np.zeros_like(out) if return_abs else None
     lib().oracle_mean_delta_sigma(ctypes.byref(g), _p(x1), _p(y1), _p(dm.mesh1.cell_id_indices, ctypes.c_int64),
                                   ctypes.c_int64(n1), _p(x2), _p(y2), _p(m2),
                                   _p(dm.mesh2.cell_id_indices, ctypes.c_int64),
                                   _p(rp_bins), ctypes.c_int(len(rp_bins)), ctypes.c_int64(first), ctypes.c_int64(last),
-                                  ctypes.c_int(int(num_threads)), _p(out))
+                                  ctypes.c_int(int(num_threads)), _p(out),
+                                  _p(absout) if return_abs else ctypes.POINTER(ctypes.c_double)())
     unsort = np.empty(n1, dtype=np.int64)
     unsort[dm.mesh1.idx_sorted] = np.arange(n1)
     out = out[unsort, :]
+    if return_abs:
+        absout = absout[unsort, :]
+        return (out, absout) if per_object else (np.mean(out, axis=0), np.mean(absout, axis=0))
     return out if per_object else np.mean(out, axis=0)
 
 

@@ -368,8 +368,11 @@ void oracle_mean_delta_sigma(const oracle_geom_t *g,
                              const double *x1, const double *y1, const int64_t *off1, int64_t n1,
                              const double *x2, const double *y2, const double *m2, const int64_t *off2,
                              const double *rp_bins, int nrp, int64_t first_cell1, int64_t last_cell1,
-                             int nthreads, double *out)
+                             int nthreads, double *out, double *absout)
 {
+    /* absout (optional, same shape as out): A_ik = the sum of the ABSOLUTE values of the terms accumulated into
+     * out[i][k], normalised like out - the scale of the rounding error of the cancelling difference (SURVEY 8d
+     * per-object parity gate).                                                                              */
     const int nbin = nrp - 1;
     double *rpsq = (double *)malloc(sizeof(double) * (nrp + nbin)), *dlog = rpsq + nrp;
     for (int k = 0; k < nrp; ++k) rpsq[k] = rp_bins[k] * rp_bins[k];
@@ -378,6 +381,7 @@ void oracle_mean_delta_sigma(const oracle_geom_t *g,
     const int perx = g->ndivs2[0] / g->ndivs1[0], pery = ny2 / ny1;
     const int mw = max_window(g);
     memset(out, 0, sizeof(double) * (size_t)n1 * nbin);
+    if (absout) memset(absout, 0, sizeof(double) * (size_t)n1 * nbin);
     if (nthreads < 1) nthreads = 1;
 #pragma omp parallel num_threads(nthreads)
     {
@@ -399,14 +403,17 @@ void oracle_mean_delta_sigma(const oracle_geom_t *g,
                 for (int64_t i = a; i < b; ++i) {
                     const double xt = x1[i] - sx, yt = y1[i] - sy;
                     double *row = out + (size_t)i * nbin;
+                    double *arow = absout ? absout + (size_t)i * nbin : NULL;
                     for (int64_t j = p; j < q; ++j) {
                         const double dx = xt - x2[j], dy = yt - y2[j];
                         const double dxy_sq = dx * dx + dy * dy;
                         const double m = m2[j];
                         int k = nbin - 1;
                         while (k >= 0 && dxy_sq <= rpsq[k + 1]) {
-                            if (dxy_sq > rpsq[k]) row[k] -= m * (1 - log(rpsq[k + 1] / dxy_sq));
-                            else                  row[k] += m * 2 * dlog[k];
+                            double t;
+                            if (dxy_sq > rpsq[k]) { t = m * (1 - log(rpsq[k + 1] / dxy_sq)); row[k] -= t; }
+                            else                  { t = m * 2 * dlog[k]; row[k] += t; }
+                            if (arow) arow[k] += fabs(t);
                             --k;
                         }
                     }
@@ -418,6 +425,7 @@ void oracle_mean_delta_sigma(const oracle_geom_t *g,
     for (int k = 0; k < nbin; ++k) {
         const double norm = M_PI * (rpsq[k + 1] - rpsq[k]);
         for (int64_t i = 0; i < n1; ++i) out[(size_t)i * nbin + k] /= norm;
+        if (absout) for (int64_t i = 0; i < n1; ++i) absout[(size_t)i * nbin + k] /= norm;
     }
     free(rpsq);
 }

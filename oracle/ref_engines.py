@@ -151,3 +151,26 @@ def marked_npairs_3d(sample1, sample2, rbins, weight_func_id, period=None, weigh
     eng = partial(engine("marked_npairs_3d_engine"), _DoubleMeshView(dm), c1[0], c1[1], c1[2], c2[0], c2[1], c2[2],
                   w1, w2, int(weight_func_id), rbins)
     return np.array(_run(eng, dm.mesh1.ncells, num_threads, cell1_range))
+
+
+def mean_delta_sigma(galaxies, particles, effective_particle_masses, rp_bins, period, approx_cell1_size=None,
+                     approx_cell2_size=None, num_threads=1, per_object=False, cell1_range=None):
+    """The reference's own mean_delta_sigma_engine, driven as surface_density/mean_delta_sigma.py:214-255 drives
+    it (periodic case): rows of galaxies outside ``cell1_range`` stay zero, as in each reference worker."""
+    from .mesh import DoubleMesh
+    galaxies = np.asarray(galaxies, dtype=np.float64)
+    particles = np.asarray(particles, dtype=np.float64)
+    rp_bins = np.atleast_1d(rp_bins).astype("f8")
+    rp_max = float(np.max(rp_bins))
+    m = np.atleast_1d(np.asarray(effective_particle_masses, dtype=np.float64))
+    if len(m) == 1:
+        m = np.zeros(particles.shape[0]) + m[0]
+    per2 = [float(p) for p in (np.atleast_1d(period).tolist() * 2)[:2]]
+    a1 = [rp_max] * 2 if approx_cell1_size is None else list(np.atleast_1d(approx_cell1_size).astype(float))[:2] * (2 if np.size(approx_cell1_size) == 1 else 1)
+    a2 = [rp_max] * 2 if approx_cell2_size is None else list(np.atleast_1d(approx_cell2_size).astype(float))[:2] * (2 if np.size(approx_cell2_size) == 1 else 1)
+    x1, y1 = np.ascontiguousarray(galaxies[:, 0]), np.ascontiguousarray(galaxies[:, 1])
+    x2, y2 = np.ascontiguousarray(particles[:, 0]), np.ascontiguousarray(particles[:, 1])
+    dm = DoubleMesh([x1, y1], [x2, y2], a1, a2, [rp_max] * 2, per2, True)
+    eng = partial(engine("mean_delta_sigma_engine"), _DoubleMeshView(dm), x1, y1, x2, y2, m, rp_bins)
+    out = np.array(_run(eng, dm.mesh1.ncells, num_threads, cell1_range))
+    return out if per_object else np.mean(out, axis=0)

@@ -325,3 +325,52 @@ def test_tpcf_multipole_and_s_mu_argument_errors():
         _s_mu_tpcf_process_args(S, np.array([0.1, 0.2]), np.array([0.0, 1.5]), None, None, 1.0, True, True, "Natural", 1)
     with pytest.raises(ValueError, match="randoms must be provided"):
         _s_mu_tpcf_process_args(S, np.array([0.1, 0.2]), np.array([0.0, 1.0]), None, None, None, True, True, "Natural", 1)
+
+
+class _FakeCudaColumn(object):
+    """Stands in for a column view of a float64 CUDA tensor (no GPU here): enough surface for ``_lib.Columns``."""
+    is_cuda = True
+
+    def __init__(self, n):
+        import torch
+        self.shape = (n,)
+        self.dtype = torch.float64
+
+    def dim(self):
+        return 1
+
+    def stride(self, _):
+        return 3
+
+    def data_ptr(self):
+        return 4096
+
+
+class _FakeCudaSample(object):
+    is_cuda = True
+
+    def __init__(self, n):
+        self.n = n
+        self.shape = (n, 3)
+
+    def __getitem__(self, key):
+        return _FakeCudaColumn(self.n)
+
+
+def test_samples_must_live_on_the_same_side_of_pcie():
+    """a CUDA-tensor sample next to a numpy sample must raise before any pointer reaches the engine, and
+    counters whose weights are host arrays refuse device samples."""
+    dev = _FakeCudaSample(10)
+    host = np.random.RandomState(0).uniform(0, 1, (10, 3))
+    rb = np.array([0.01, 0.1])
+    for fn, args in [(hb.npairs_3d, (rb,)), (hb.npairs_xy_z, (rb, rb)), (hb.npairs_s_mu, (rb, np.linspace(0, 1, 3))),
+                     (hb.npairs_projected, (rb, 0.2))]:
+        for s1, s2 in [(dev, host), (host, dev)]:
+            with pytest.raises(TypeError, match="both be host arrays or both be CUDA tensors"):
+                fn(s1, s2, *args, period=1.0)
+    with pytest.raises(TypeError, match="takes host"):
+        hb.marked_npairs_3d(dev, dev, rb, 1, period=1.0, weights1=np.ones(10), weights2=np.ones(10))
+    with pytest.raises(TypeError, match="takes host"):
+        hb.npairs_per_object_3d(dev, dev, rb, period=1.0)
+    with pytest.raises(ValueError, match="explicit ``period``"):
+        hb.npairs_3d(dev, dev, rb)
