@@ -15,9 +15,14 @@ same unit of work.
   roofline  FP64 non-FMA issue roofline of the dominant kernel (k_count<Fast3>): 8 f64 ops per
             evaluated pair (3 sub, 3 mul, 2 add) x pairs evaluated / kernel time, against the FP64
             DADD/DMUL issue rate measured live on the same GPU (MEASURED_PEAKS.json has no FP64 entry)
+  e2e_pageable   the same from ordinary (pageable) numpy arrays - what a drop-in caller passes
   cpu_baseline / --impl reference   the reference's own compiled Cython engine (oracle/_ref) — or the
             C oracle port when it is absent — on all host cores, on a bounded sample (a range of
-            mesh1 cells of the RR count).
+            mesh1 cells of the RR count); engine time only, the mesh build is reported beside it.
+  parity    (N = 1) the step's counts against the reference's engine AT FULL SIZE: DD in full, DR and RR
+            on the mesh1 cell range the CPU sample covers; the bench fails if any count differs
+  c5        sub-record: BASELINE configs[4] (mean_delta_sigma, 1e6 x 1e8), the north-star scaling config,
+            measured in the same run at the same N (same keys as the main line)
 
 Multi-GPU (torchrun, one rank per GPU): every rank holds both samples, counts ITS contiguous range
 of reference mesh1 cells, one NCCL all-reduce per count; total work is fixed -> "strong" scaling.
@@ -110,112 +115,172 @@ def landy_szalay(DD, DR, RR, N, NR):
 
 
 # ------------------------------------------------------------------ reference / CPU arm
-def cpu_sample(gal, ran, rbins, cores, target_cells_per_core=2):
-    """Time the reference's compiled engine (or the oracle port) on a bounded sample of the RR count:
-    a contiguous range of mesh1 cells, all host cores."""
-    from oracle import oracle, ref_engines
-    dm = oracle.build_double_mesh_3d(ran[:1000], ran[:1000], [float(rbins.max())] * 3, LBOX, None, None)[0]
-    ncells = dm.mesh1.ncells
-    ncell = int(min(ncells, max(cores * target_cells_per_core, 8)))
-    rng = (0, ncell)
-    kind = "reference" if ref_engines.available() else "port"
-    t0 = time.perf_counter()
-    if kind == "reference":
-        counts = ref_engines.npairs_3d(ran, ran, rbins, period=LBOX, num_threads=cores, cell1_range=rng)
-    else:
-        counts = oracle.npairs_3d(ran, ran, rbins, period=LBOX, num_threads=cores, cell1_range=rng)
-    dt = time.perf_counter() - t0
-    full = oracle.build_double_mesh_3d(ran, ran, [float(rbins.max())] * 3, LBOX, None, None)[0]
-    pairs = full.visited_pairs(rng[0], rng[1])
-    sample = ("RR count of the %d randoms restricted to mesh1 cells [%d, %d) of %d (%.3g visited pairs), "
-              "num_threads=%d" % (len(ran), rng[0], rng[1], ncells, pairs, cores))
-    return pairs / dt / 1e9, dt, kind, sample, counts
+class CpuArm(object):
+    """The reference's compiled npairs_3d engine (oracle/_ref; the C oracle port when it did not travel) on all host
+    cores, on a bounded sample of the step: the RR count restricted to a contiguous range of mesh1 cells.  The double
+    mesh and the worker pool are built ONCE, outside the timed region (a per-call set-up spread over 2 % of
+    the cells understates the engine); their cost is reported separately (``seconds_mesh``)."""
+
+    def __init__(self, ran, rbins, cores, target_cells_per_core=2):
+        from oracle import oracle, ref_engines
+        self.ran, self.rbins, self.cores = ran, rbins, cores
+        self.kind = "reference" if ref_engines.available() else "port"
+        if self.kind == "reference":
+            self.prep = ref_engines.PreparedCount(ran, ran, rbins, LBOX, cores)
+            self.dm = self.prep.dm
+            self.seconds_mesh = self.prep.seconds_mesh
+        else:
+            t0 = time.perf_counter()
+            self.dm = oracle.build_double_mesh_3d(ran, ran, [float(rbins.max())] * 3, LBOX, None, None)[0]
+            self.seconds_mesh = time.perf_counter() - t0
+            self.prep = None
+        ncells = self.dm.mesh1.ncells
+        self.cells = (0, int(min(ncells, max(cores * target_cells_per_core, 8))))
+        self.pairs = float(self.dm.visited_pairs(*self.cells))
+        self.sample = ("RR count of the %d randoms restricted to mesh1 cells [%d, %d) of %d (%.3g visited pairs), num_threads=%d; "
+                       "engine time only - the double mesh (%.2f s, serial numpy argsort as in the reference) and the worker "
+                       "pool are built once outside the timed region"
+                       % (len(ran), self.cells[0], self.cells[1], ncells, self.pairs, cores, self.seconds_mesh))
+
+    def run(self):
+        """-> (GPairs/s, seconds, counts) of one pass over the sample."""
+        from oracle import oracle
+        t0 = time.perf_counter()
+        if self.prep is not None:
+            counts = self.prep.run(self.cells)
+        else:
+            counts = oracle.npairs_3d(self.ran, self.ran, self.rbins, period=LBOX, num_threads=self.cores, cell1_range=self.cells)
+        dt = time.perf_counter() - t0
+        return self.pairs / dt / 1e9, dt, np.asarray(counts)
+
+    def close(self):
+        if self.prep is not None:
+            self.prep.close()
+
+
+WORKLOAD = ("configs[1]: tpcf Landy-Szalay (DD+DR+RR via npairs_3d), zheng07-on-FakeSim mock + 5e6 randoms, Lbox 250, "
+            "15 log rbins 0.1-20")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    gal, ran, rbins = make_inputs()
+    gal, ran, rbins = make_inputs(args.randoms)
     cores = os.cpu_count() or 1
+    arm = CpuArm(ran, rbins, cores)
     vals, times = [], []
-    kind = sample = None
     for i in range(args.warmup + args.steps):
-        v, dt, kind, sample, _ = cpu_sample(gal, ran, rbins, cores)
+        v, dt, _ = arm.run()
         if i >= args.warmup:
             vals.append(v)
             times.append(dt)
+    arm.close()
     value = float(np.mean(vals))
     line = {"impl": "reference", "metric": "pair evals/sec", "value": value, "unit": "GPairs/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": float(np.mean(times) * 1e3), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "configs[1]: tpcf Landy-Szalay, zheng07-on-FakeSim mock + 5e6 randoms, Lbox 250, "
-                                   "15 log rbins 0.1-20 (bounded sample of the RR count)"},
-            "cpu_baseline": {"value": value, "unit": "GPairs/s", "cores": cores, "kind": kind, "sample": sample},
+            "config": {"workload": WORKLOAD + " (each step = a bounded sample of the RR count, rate in the same W_ref pair unit)",
+                       "same_config": False,
+                       "method": "rate of the reference engine on a cell range of the dominant (RR) count; the GPU arm's "
+                                 "value is W_ref of the whole step / its time"},
+            "cpu_baseline": {"value": value, "unit": "GPairs/s", "cores": cores, "kind": arm.kind, "sample": arm.sample,
+                             "seconds_mesh": arm.seconds_mesh},
             "e2e": {"value": value, "unit": "GPairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
 
 
-# ------------------------------------------------------------------ GPU arm
-def run_gpu(args):
-    import torch
-    import torch.distributed as dist
+# ------------------------------------------------------------------ GPU arm: shared plumbing
+class Env(object):
+    def __init__(self):
+        import ctypes
+        import torch
+        import torch.distributed as dist
+        from halotools_b200 import _lib, distributed
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        _lib.require_gpu()
+        torch.cuda.set_device(self.local)
+        _lib.set_device(self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            distributed.enable()
+        self.stream = torch.cuda.Stream()
+        _lib.check(_lib.load().htb_set_stream(ctypes.c_void_p(self.stream.cuda_stream)))
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, fn, steps, warmup):
+        """W untimed calls, then EXACTLY `steps` calls between two CUDA events on the engine's stream, bracketed by a
+        barrier + synchronize on both sides; max over ranks."""
+        torch = self.torch
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(self.stream):
+            e0.record(self.stream)
+            res = None
+            for _ in range(steps):
+                res = fn()
+            e1.record(self.stream)
+        self.barrier()
+        ms = e0.elapsed_time(e1)
+        if self.world > 1:
+            t = torch.tensor([ms], device="cuda")
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps, res
+
+    def close(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------ configs[1]: the tpcf step
+def measure_tpcf(env, args, sampler):
     import halotools_b200 as hb
     from halotools_b200 import _lib, distributed
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    _lib.require_gpu()
-    torch.cuda.set_device(local)
-    _lib.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        distributed.enable()
-    stream = torch.cuda.Stream()
-    import ctypes
-    _lib.check(_lib.load().htb_set_stream(ctypes.c_void_p(stream.cuda_stream)))
+    torch, dist, world, rank = env.torch, env.dist, env.world, env.rank
 
     gal, ran, rbins = make_inputs(args.randoms)
     N, NR = len(gal), len(ran)
-    # pinned host copies for the end-to-end arm
+    # pinned host copies for the end-to-end arm; the ordinary (pageable) numpy arrays for e2e_pageable
     gal_h = torch.from_numpy(gal).pin_memory()
     ran_h = torch.from_numpy(ran).pin_memory()
     gal_np, ran_np = gal_h.numpy(), ran_h.numpy()
     gal_d, ran_d = gal_h.cuda(non_blocking=False), ran_h.cuda(non_blocking=False)
     torch.cuda.synchronize()
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     stats_acc = {}
 
     def step_resident():
         acc = {"pairs_reference": 0.0, "pairs_evaluated": 0.0, "ms_count": 0.0, "launches": 0, "ms_mesh": 0.0,
-               "count_evaluated": [], "count_ms": []}
+               "count_evaluated": [], "count_ms": [], "calls": []}
         out = []
         # the three counts of the statistic keep the ranks' partial sums; ONE all-reduce at the end of the block (what
         # hb.tpcf does internally)
-        part = distributed.local_counts()
-        part.__enter__()
-        for a, b in ((gal_d, gal_d), (gal_d, ran_d), (ran_d, ran_d)):
-            out.append(part.add(hb.npairs_3d(a, b, rbins, period=LBOX)))
-            st = _lib.last_stats
-            acc["pairs_reference"] += st["pairs_reference"]
-            acc["pairs_evaluated"] += st["pairs_evaluated"]
-            acc["ms_count"] += st["ms_count"]
-            acc["ms_mesh"] += st["ms_mesh"]
-            acc["launches"] += st["kernel_launches"]
-            acc["count_evaluated"].append(st["pairs_evaluated"])
-            acc["count_ms"].append(st["ms_count"])
-            acc.setdefault("calls", []).append({k: st[k] for k in ("ms_h2d", "ms_mesh", "ms_count", "ms_total", "tiles",
-                                                                   "tiles_redone", "refine1", "refine2")})
-        part.__exit__(None, None, None)
+        with distributed.local_counts() as part:
+            for a, b in ((gal_d, gal_d), (gal_d, ran_d), (ran_d, ran_d)):
+                out.append(part.add(hb.npairs_3d(a, b, rbins, period=LBOX)))
+                st = _lib.last_stats
+                acc["pairs_reference"] += st["pairs_reference"]
+                acc["pairs_evaluated"] += st["pairs_evaluated"]
+                acc["ms_count"] += st["ms_count"]
+                acc["ms_mesh"] += st["ms_mesh"]
+                acc["launches"] += st["kernel_launches"]
+                acc["count_evaluated"].append(st["pairs_evaluated"])
+                acc["count_ms"].append(st["ms_count"])
+                acc["calls"].append({k: st[k] for k in ("ms_h2d", "ms_mesh", "ms_count", "ms_total", "tiles",
+                                                        "tiles_redone", "refine1", "refine2")})
         xi = landy_szalay(out[0], out[1], out[2], N, NR)
         stats_acc.update(acc)
         return xi
@@ -223,120 +288,129 @@ def run_gpu(args):
     def step_e2e():
         return hb.tpcf(gal_np, rbins, randoms=ran_np, period=LBOX, estimator="Landy-Szalay")
 
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with torch.cuda.stream(stream):
-            e0.record(stream)
-            res = None
-            for _ in range(steps):
-                t0 = time.perf_counter()
-                res = fn()
-                if os.environ.get("HTB_BENCH_VERBOSE"):
-                    sys.stderr.write("step wall %.1f ms %s\n" % ((time.perf_counter() - t0) * 1e3, json.dumps(stats_acc.get("calls"))))
-            e1.record(stream)
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms / steps, res
+    def step_e2e_pageable():
+        return hb.tpcf(gal, rbins, randoms=ran, period=LBOX, estimator="Landy-Szalay")
 
-    sampler = ClockSampler(local)
-    if rank == 0 and not os.environ.get("HTB_BENCH_NO_SAMPLER"):
+    if sampler is not None:
         sampler.start()
-    ms_step, xi_res = timed(step_resident, args.steps, args.warmup)
+    ms_step, xi_res = env.timed(step_resident, args.steps, args.warmup)
     acc = dict(stats_acc)
     if world > 1:
         # per-rank stats describe this rank's shard; totals over ranks
         t = torch.tensor([acc["pairs_reference"], acc["pairs_evaluated"]], device="cuda", dtype=torch.float64)
         dist.all_reduce(t)
         acc["pairs_reference"], acc["pairs_evaluated"] = float(t[0]), float(t[1])
-    ms_e2e, xi_e2e = timed(step_e2e, max(1, args.steps // 2), 1)
-    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, xi_e2e = env.timed(step_e2e, max(1, args.steps // 2), 1)
+    ms_pg, xi_pg = env.timed(step_e2e_pageable, max(1, args.steps // 2), 1)
+    clocks = sampler.stop() if sampler is not None else None
     assert np.allclose(xi_res, xi_e2e, rtol=1e-12, atol=0), "resident and end-to-end paths disagree"
+    assert np.allclose(xi_res, xi_pg, rtol=1e-12, atol=0), "resident and pageable end-to-end paths disagree"
 
     W = acc["pairs_reference"]
-    value = W / (ms_step * 1e-3) / 1e9
-    e2e_value = W / (ms_e2e * 1e-3) / 1e9
+    out = {"ms_step": ms_step, "W": W, "N": N, "NR": NR, "acc": acc, "clocks": clocks, "stats": stats_acc,
+           "ms_e2e": ms_e2e, "ms_e2e_pageable": ms_pg, "rbins": rbins}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # ---- reference arm beside the GPU arm, and REFERENCE PARITY AT FULL SIZE: the reference's own
+        # engine on the same inputs - DD in full, DR and RR on the cell range the CPU sample times
+        from oracle import oracle, ref_engines
+        cores = os.cpu_count() or 1
+        arm = CpuArm(ran, rbins, cores)
+        v, dt, rr_ref = arm.run()
+        arm.close()
+        out["cpu"] = {"value": v, "unit": "GPairs/s", "cores": cores, "kind": arm.kind, "sample": arm.sample,
+                      "seconds": dt, "seconds_mesh": arm.seconds_mesh}
+        REF = ref_engines if ref_engines.available() else oracle
+        cells = arm.cells
+        with distributed.cell_range(*cells):
+            rr_gpu = hb.npairs_3d(ran_d, ran_d, rbins, period=LBOX)
+            dr_gpu = hb.npairs_3d(gal_d, ran_d, rbins, period=LBOX)
+        dr_ref = REF.npairs_3d(gal, ran, rbins, period=LBOX, num_threads=cores, cell1_range=cells)
+        dd_ref = REF.npairs_3d(gal, gal, rbins, period=LBOX, num_threads=cores)
+        dd_gpu = hb.npairs_3d(gal_d, gal_d, rbins, period=LBOX)
+        ok = {"DD_full": bool(np.array_equal(dd_gpu, dd_ref)), "DR_cells": bool(np.array_equal(dr_gpu, dr_ref)),
+              "RR_cells": bool(np.array_equal(rr_gpu, rr_ref))}
+        out["parity"] = {"against": arm.kind, "mesh1_cells": list(cells), "bit_exact": ok,
+                         "DD_top": int(dd_gpu[-1]), "DR_top_cells": int(dr_gpu[-1]), "RR_top_cells": int(rr_gpu[-1])}
+        assert all(ok.values()), "full-size counts differ from the reference: %r" % (out["parity"],)
+    return out
 
-    if rank == 0:
-        # FP64 issue-rate roofline of the dominant kernel (the RR launch of k_count<Fast3>) on this rank
-        rate, clk = _lib.measure_fp64_rate()
-        i_rr = int(np.argmax(stats_acc["count_evaluated"]))
-        ach = stats_acc["count_evaluated"][i_rr] * OPS_PER_PAIR / (stats_acc["count_ms"][i_rr] * 1e-3) / 1e12
-        peak = rate / 1e12
-        traffic = None
+
+def tpcf_line(env, args, m):
+    from halotools_b200 import _lib
+    world = env.world
+    acc, stats_acc, W, N, NR = m["acc"], m["stats"], m["W"], m["N"], m["NR"]
+    # FP64 issue-rate roofline of the dominant kernel (the RR launch of k_count<Fast3>) on this rank
+    rate, clk = _lib.measure_fp64_rate()
+    i_rr = int(np.argmax(stats_acc["count_evaluated"]))
+    ach = stats_acc["count_evaluated"][i_rr] * OPS_PER_PAIR / (stats_acc["count_ms"][i_rr] * 1e-3) / 1e12
+    peak = rate / 1e12
+    traffic = None
+    for name in ("r02_fast3_traffic.json", "r01_fast3_traffic.json"):
         try:
             # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel, from the committed ncu capture
-            with open(os.path.join(ROOT, "profiles", "r01_fast3_traffic.json")) as fh:
+            with open(os.path.join(ROOT, "profiles", name)) as fh:
                 tj = json.load(fh)
             traffic = int(tj["dram_bytes_read"]) + int(tj["dram_bytes_write"])
+            break
         except Exception:
             traffic = None
-        roofline = {"bound": "fp64_issue", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                    "traffic": traffic, "traffic_unit": "bytes per launch (ncu --set full, profiles/r01_fast3_final_ncu.txt)",
-                    "kernel": "k_count<Fast3> (RR launch)",
-                    "peak_source": "htb_measure_fp64_rate: DADD/DMUL non-FMA issue rate measured live on this GPU "
-                                   "(MEASURED_PEAKS.json has no FP64 entry)",
-                    "pairs_evaluated_per_launch": stats_acc["count_evaluated"][i_rr],
-                    "kernel_ms": stats_acc["count_ms"][i_rr]}
-        cpu = None
-        if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            v, dt, kind, sample, _ = cpu_sample(gal, ran, rbins, cores)
-            cpu = {"value": v, "unit": "GPairs/s", "cores": cores, "kind": kind, "sample": sample, "seconds": dt}
-        h2d = int((N + NR) * 24)          # inside hb.tpcf the upload cache sends every sample across PCIe once per step
-        d2h = int(3 * len(rbins) * 8)
-        line = {"metric": "pair evals/sec", "value": value, "unit": "GPairs/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic",
-                "config": {"workload": "configs[1]: tpcf Landy-Szalay (DD+DR+RR via npairs_3d), zheng07-on-FakeSim "
-                                       "mock (%d galaxies) + %d randoms, Lbox 250, 15 log rbins 0.1-20" % (N, NR),
-                           "pairs_unit": "W_ref = pairs visited by the reference mesh loop for the same calls",
-                           "pairs_reference_per_step": W, "pairs_evaluated_per_step": acc["pairs_evaluated"],
-                           "l2": "inputs (%.0f MB of sorted coordinates) exceed nothing that matters: the kernel is "
-                                 "FP64-issue bound; every step re-sorts both samples and re-streams them from HBM"
-                                 % ((N + NR) * 24 / 1e6),
-                           "parallelism": "work-balanced mesh1 cell ranges over %d rank(s), one NCCL all-reduce per step" % world},
-                "e2e": {"value": e2e_value, "unit": "GPairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": ms_e2e},
-                "gpu_launches": int(acc["launches"] * args.steps),
-                "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-                "breakdown_ms": {"mesh_sort": acc["ms_mesh"], "count_kernels": acc["ms_count"]},
-                "calls": acc.get("calls")}
+    roofline = {"bound": "fp64_issue", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "traffic": traffic, "traffic_unit": "bytes per launch (ncu --set full capture under profiles/)",
+                "kernel": "k_count<Fast3> (RR launch)",
+                "peak_source": "htb_measure_fp64_rate: DADD/DMUL non-FMA issue rate measured live on this GPU "
+                               "(MEASURED_PEAKS.json has no FP64 entry)",
+                "pairs_evaluated_per_launch": stats_acc["count_evaluated"][i_rr],
+                "kernel_ms": stats_acc["count_ms"][i_rr]}
+    h2d = int((N + NR) * 24)          # inside hb.tpcf the upload cache sends every sample across PCIe once per step
+    d2h = int(3 * len(m["rbins"]) * 8)
+    line = {"metric": "pair evals/sec", "value": W / (m["ms_step"] * 1e-3) / 1e9, "unit": "GPairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["ms_step"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD + " (%d galaxies, %d randoms)" % (N, NR),
+                       "pairs_unit": "W_ref = pairs visited by the reference mesh loop for the same calls",
+                       "pairs_reference_per_step": W, "pairs_evaluated_per_step": acc["pairs_evaluated"],
+                       "l2": "inputs (%.0f MB of sorted coordinates) exceed nothing that matters: the kernel is "
+                             "FP64-issue bound; every step re-sorts both samples and re-streams them from HBM"
+                             % ((N + NR) * 24 / 1e6),
+                       "parallelism": "work-balanced mesh1 cell ranges over %d rank(s), one NCCL all-reduce per step" % world},
+            "e2e": {"value": W / (m["ms_e2e"] * 1e-3) / 1e9, "unit": "GPairs/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": m["ms_e2e"], "host_memory": "pinned"},
+            "e2e_pageable": {"value": W / (m["ms_e2e_pageable"] * 1e-3) / 1e9, "unit": "GPairs/s", "h2d_bytes_per_step": h2d,
+                             "d2h_bytes_per_step": d2h, "ms_per_step": m["ms_e2e_pageable"],
+                             "host_memory": "pageable (ordinary numpy arrays, what a drop-in caller passes)"},
+            "gpu_launches": int(acc["launches"] * args.steps),
+            "roofline": roofline, "cpu_baseline": m.get("cpu"), "parity": m.get("parity"), "clocks": m["clocks"],
+            "breakdown_ms": {"mesh_sort": acc["ms_mesh"], "count_kernels": acc["ms_count"]},
+            "calls": acc.get("calls")}
+    return line
+
+
+def run_gpu(args):
+    env = Env()
+    sampler = ClockSampler(env.local) if (env.rank == 0 and not os.environ.get("HTB_BENCH_NO_SAMPLER")) else None
+    m = measure_tpcf(env, args, sampler)
+    c5 = None
+    if not args.no_c5:
+        # the north-star scaling config rides on the driver's line at every N
+        c5 = measure_c5(env, args, None, steps=max(2, min(args.steps, 3)), warmup=1)
+    if env.rank == 0:
+        line = tpcf_line(env, args, m)
+        line["c5"] = c5
         print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    env.close()
     return 0
 
 
-# ------------------------------------------------------------------ config-5 workload (scaling runs; not the driver's line)
-def run_gpu_c5(args):
+# ------------------------------------------------------------------ configs[4]: the delta-sigma scaling config
+def measure_c5(env, args, sampler, steps=None, warmup=None):
     """BASELINE.json configs[4]: mean_delta_sigma, 1e6 galaxies x 1e8 particles, Lbox 1000, 15 log rp bins 0.1-30,
     one particle mass.  Same JSON contract; W_ref = pairs the reference's 2-d mesh loop visits."""
-    import torch
-    import torch.distributed as dist
     import halotools_b200 as hb
-    from halotools_b200 import _lib, distributed, synthetic
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    _lib.require_gpu()
-    torch.cuda.set_device(local)
-    _lib.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        distributed.enable()
-    stream = torch.cuda.Stream()
-    import ctypes
-    _lib.check(_lib.load().htb_set_stream(ctypes.c_void_p(stream.cuda_stream)))
+    from halotools_b200 import _lib, synthetic
+    torch, dist, world, rank = env.torch, env.dist, env.world, env.rank
+    steps = args.steps if steps is None else steps
+    warmup = args.warmup if warmup is None else warmup
     ngal, nptcl, L = args.c5_galaxies, args.c5_particles, 1000.0
     gal = synthetic.uniform_points(43, ngal, L)
     ptcl = synthetic.uniform_points(44, nptcl, L)
@@ -348,12 +422,6 @@ def run_gpu_c5(args):
     torch.cuda.synchronize()
     acc = {}
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     def step_resident():
         r = hb.mean_delta_sigma(gal_d, ptcl_d, 1.0, rp, period=L)
         acc.update(_lib.last_stats)
@@ -362,29 +430,9 @@ def run_gpu_c5(args):
     def step_e2e():
         return hb.mean_delta_sigma(gal_np, ptcl_np, 1.0, rp, period=L)
 
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with torch.cuda.stream(stream):
-            e0.record(stream)
-            res = None
-            for _ in range(steps):
-                res = fn()
-            e1.record(stream)
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms / steps, res
-
-    sampler = ClockSampler(local)
-    if rank == 0 and not os.environ.get("HTB_BENCH_NO_SAMPLER"):
+    if sampler is not None:
         sampler.start()
-    ms_step, res = timed(step_resident, args.steps, args.warmup)
+    ms_step, res = env.timed(step_resident, steps, warmup)
     st = dict(acc)
     tot = torch.tensor([st["pairs_reference"], st["pairs_evaluated"], st["ms_count"]], device="cuda", dtype=torch.float64)
     if world > 1:
@@ -393,35 +441,43 @@ def run_gpu_c5(args):
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         st["ms_count"] = float(mx[2])
     W, Wgpu = float(tot[0]), float(tot[1])
-    ms_e2e, res2 = timed(step_e2e, max(1, args.steps // 2), 1)
-    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, res2 = env.timed(step_e2e, max(1, steps // 2), 1)
+    clocks = sampler.stop() if sampler is not None else None
     scale = float(np.max(np.abs(res)))
     assert np.allclose(res, res2, rtol=1e-9, atol=1e-12 * scale), "resident and end-to-end paths disagree"
-    if rank == 0:
-        rate, _ = _lib.measure_fp64_rate()
-        ach = Wgpu / world * 5.0 / (st["ms_count"] * 1e-3) / 1e12
-        line = {"metric": "pair evals/sec", "value": W / (ms_step * 1e-3) / 1e9, "unit": "GPairs/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "configs[4]: mean_delta_sigma, %d galaxies x %d particles, Lbox 1000, 15 log rp bins "
-                                       "0.1-30, one particle mass" % (ngal, nptcl),
-                           "pairs_unit": "W_ref = pairs visited by the reference mesh loop for the same call",
-                           "pairs_reference_per_step": W, "pairs_evaluated_per_step": Wgpu,
-                           "l2": "inputs (%.1f GB of coordinates) are larger than L2" % ((ngal + nptcl) * 24 / 1e9),
-                           "parallelism": "work-balanced mesh1 cell ranges over %d rank(s), one all-reduce of the column sums" % world},
-                "e2e": {"value": W / (ms_e2e * 1e-3) / 1e9, "unit": "GPairs/s", "h2d_bytes_per_step": int((ngal + nptcl) * 16),    # the x and y columns (the engine never reads z)
-                        "d2h_bytes_per_step": int(14 * 8), "ms_per_step": ms_e2e},
-                "gpu_launches": int(st["kernel_launches"] * args.steps),
-                "roofline": {"bound": "fp64_issue", "achieved": ach, "peak": rate / 1e12, "unit": "TFLOP/s", "frac": ach / (rate / 1e12),
-                             "traffic": None, "kernel": "k_count<DSigmaR> (5 f64 ops per evaluated pair; slowest rank)",
-                             "kernel_ms": st["ms_count"]},
-                "cpu_baseline": None, "clocks": clocks,
-                "breakdown_ms": {"mesh_sort": st["ms_mesh"], "count_kernel": st["ms_count"], "path": st["path"]},
-                "delta_sigma": [float(v) for v in res]}
+    del gal_d, ptcl_d, gal_h, ptcl_h
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    rate, _ = _lib.measure_fp64_rate()
+    ach = Wgpu / world * 5.0 / (st["ms_count"] * 1e-3) / 1e12
+    return {"metric": "pair evals/sec", "value": W / (ms_step * 1e-3) / 1e9, "unit": "GPairs/s", "n_gpus": world,
+            "steps": steps, "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[4]: mean_delta_sigma, %d galaxies x %d particles, Lbox 1000, 15 log rp bins "
+                                   "0.1-30, one particle mass" % (ngal, nptcl),
+                       "pairs_unit": "W_ref = pairs visited by the reference mesh loop for the same call",
+                       "pairs_reference_per_step": W, "pairs_evaluated_per_step": Wgpu,
+                       "l2": "inputs (%.1f GB of coordinates) are larger than L2" % ((ngal + nptcl) * 24 / 1e9),
+                       "parallelism": "work-balanced mesh1 cell ranges over %d rank(s), one all-reduce of the column sums" % world},
+            "e2e": {"value": W / (ms_e2e * 1e-3) / 1e9, "unit": "GPairs/s", "h2d_bytes_per_step": int((ngal + nptcl) * 16),    # the x and y columns (the engine never reads z)
+                    "d2h_bytes_per_step": int(14 * 8), "ms_per_step": ms_e2e},
+            "gpu_launches": int(st["kernel_launches"] * steps),
+            "roofline": {"bound": "fp64_issue", "achieved": ach, "peak": rate / 1e12, "unit": "TFLOP/s", "frac": ach / (rate / 1e12),
+                         "traffic": None, "kernel": "k_count<DSigmaR> (5 f64 ops per evaluated pair; slowest rank)",
+                         "kernel_ms": st["ms_count"]},
+            "cpu_baseline": None, "clocks": clocks,
+            "breakdown_ms": {"mesh_sort": st["ms_mesh"], "count_kernel": st["ms_count"], "path": st["path"]},
+            "delta_sigma": [float(v) for v in res]}
+
+
+def run_gpu_c5(args):
+    env = Env()
+    sampler = ClockSampler(env.local) if (env.rank == 0 and not os.environ.get("HTB_BENCH_NO_SAMPLER")) else None
+    line = measure_c5(env, args, sampler)
+    if env.rank == 0:
         print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    env.close()
     return 0
 
 
@@ -433,6 +489,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--randoms", type=int, default=N_RANDOMS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="skip the configs[4] sub-record of the default line")
     ap.add_argument("--workload", default="tpcf", choices=["tpcf", "c5"],
                     help="tpcf = BASELINE configs[1] (the driver's line); c5 = configs[4], the delta-sigma scaling config")
     ap.add_argument("--c5-galaxies", type=int, default=1_000_000)

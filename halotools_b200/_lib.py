@@ -22,6 +22,7 @@ FLAG_UNIFORM_MASS = 32
 FLAG_COLUMN_SUM = 64
 FLAG_CACHE_SAMPLE1 = 128
 FLAG_CACHE_SAMPLE2 = 256
+FLAG_PARTITION_SUM = 512
 
 EXPORTS = (
     "htb_last_error", "htb_abi_version", "htb_device_count", "htb_set_device", "htb_set_stream", "htb_set_shard",
@@ -193,7 +194,9 @@ def run_engine(func_name, *args, **kw):
     global last_stats
     lib = require_gpu()
     st = Stats()
-    flags = default_flags | (FLAG_DEVICE_INPUT if kw.get("device") else 0) | int(kw.get("extra_flags", 0))
+    from . import distributed
+    flags = (default_flags | (FLAG_DEVICE_INPUT if kw.get("device") else 0) | int(kw.get("extra_flags", 0))
+             | distributed.engine_flags())
     rc = getattr(lib, func_name)(*args, ctypes.c_uint32(flags),
                                  ctypes.byref(st) if collect_stats else None)
     check(rc)

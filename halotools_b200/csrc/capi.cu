@@ -621,6 +621,16 @@ struct Call {
         // samples to be the SAME sorted arrays and the reference window to be symmetric (mesh1 == mesh2).
         bool sym = allow_sym && same && !(fl & HTB_FLAG_NO_SYM) && !getenv("HTB_NO_SYM");
         for (int d = 0; d < dim && sym; ++d) sym = (g->ndivs1[d] == g->ndivs2[d]);
+        {
+            // A partial cell range must return what the reference engine returns for that cell1_tuple: pairs (i, j)
+            // with i inside the range and j anywhere.  The symmetric shortcut attributes an unordered pair to the
+            // point with the smaller sorted index, so its per-range counts are only right when the caller sums a
+            // partition of the cells (device-side shards, HTB_FLAG_PARTITION_SUM).
+            int64_t nc1all = 1;
+            for (int d = 0; d < dim; ++d) nc1all *= g->ndivs1[d];
+            const bool partial = first_cell1 > 0 || last_cell1 < nc1all;
+            if (partial && g_shard_world == 1 && !(fl & HTB_FLAG_PARTITION_SUM)) sym = false;
+        }
         if (sym) for (int d = 0; d < dim; ++d) m1[d] = m2[d];
         const FineGrid g1 = make_grid(g, 0, m1), g2 = make_grid(g, 1, m2);
         G.sym = sym ? 1 : 0;

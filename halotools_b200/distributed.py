@@ -97,6 +97,15 @@ class cell_range(object):
         return False
 
 
+def engine_flags():
+    """HTB_FLAG_PARTITION_SUM when the cell range an engine call receives is this rank's part of a partition whose
+    counts are summed over the ranks (the symmetric auto-correlation shortcut is then allowed on a partial range); an
+    explicit ``cell_range`` block asks for the reference's own per-range counts instead."""
+    if _state["enabled"] and _state["cells"] is None and _rank_world()[1] > 1:
+        return 512
+    return 0
+
+
 def cell1_range(ncells, work=None):
     """This rank's (first_cell1, last_cell1); the full range when the engine does the (balanced) cut."""
     if _state["cells"] is not None:

@@ -45,6 +45,12 @@ extern "C" {
 #define HTB_FLAG_CACHE_SAMPLE1 128u /* sample1's host coordinate arrays take part in the upload cache (htb_cache_begin) */
 #define HTB_FLAG_CACHE_SAMPLE2 256u /* ... sample2's */
 #define HTB_FLAG_NO_SYM       16u  /* auto-correlations: evaluate (i,j) and (j,i) separately, as the reference does */
+#define HTB_FLAG_PARTITION_SUM 512u /* [first_cell1, last_cell1) is one part of a partition of the mesh1 cells whose results the
+                                       caller SUMS (multi-GPU shards): auto-correlations may then keep the symmetric shortcut
+                                       (each unordered zero-shift pair evaluated once, from the point with the smaller sorted
+                                       index, and counted twice), whose per-part counts differ from the reference's per-range
+                                       counts although their sum over the partition is identical.  Without the flag a partial
+                                       range returns exactly what the reference engine returns for that cell1_tuple. */
 
 /* Scalars of RectangularDoubleMesh / RectangularDoubleMesh2D
  * (/root/reference/halotools/mock_observables/pair_counters/rectangular_mesh.py:228-374,

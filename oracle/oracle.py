@@ -126,7 +126,9 @@ def _sorted(cols, mesh):
 def _range(dm, cell1_range):
     if cell1_range is None:
         return 0, dm.mesh1.ncells
-    return int(cell1_range[0]), int(cell1_range[1])
+    first, last = int(cell1_range[0]), int(cell1_range[1])
+    assert 0 <= first <= last <= dm.mesh1.ncells, "cell1_range %r outside the %d mesh1 cells" % (cell1_range, dm.mesh1.ncells)
+    return first, last
 
 
 def npairs_3d(sample1, sample2, rbins, period=None, approx_cell1_size=None, approx_cell2_size=None,

@@ -90,6 +90,8 @@ def _cell1_tuples(ncells, num_threads):
 def _run(eng, ncells, num_threads, cell1_range=None):
     if cell1_range is not None:
         first, last = int(cell1_range[0]), int(cell1_range[1])
+        # the engines do not check their cell1_tuple: a range past the mesh reads out of bounds
+        assert 0 <= first <= last <= ncells, "cell1_range %r outside the %d mesh1 cells" % (cell1_range, ncells)
         if num_threads == 1:
             return eng((first, last))
         nt, tuples = _cell1_tuples(last - first, num_threads)
@@ -105,6 +107,53 @@ def _run(eng, ncells, num_threads, cell1_range=None):
             pool.join()
         return np.sum(np.array(result), axis=0)
     return eng(tuples[0])
+
+
+_WORKER_ENGINE = None       # set in the parent before the pool forks: the workers inherit the arrays (no pickling)
+
+
+def _worker_call(cells):
+    return _WORKER_ENGINE(cells)
+
+
+class PreparedCount(object):
+    """A reference npairs_3d call split into its phases so that a benchmark can time them apart: ``__init__`` builds
+    the double mesh (what RectangularDoubleMesh does in the parent, npairs_3d.py:119-125) and forks the worker pool
+    (:143); ``run(cell1_range)`` is the engine fan-out over the cells alone (:144-146).  The workers inherit the
+    sample arrays through fork, so - unlike the reference's pool.map of a partial holding the arrays - nothing is
+    pickled per task: the engine time is not diluted by set-up work when only a few cells are counted."""
+
+    def __init__(self, sample1, sample2, rbins, period, num_threads):
+        import time
+        global _WORKER_ENGINE
+        rbins = np.atleast_1d(rbins).astype("f8")
+        rmax = float(np.max(rbins))
+        t0 = time.perf_counter()
+        dm, c1, c2 = _o.build_double_mesh_3d(sample1, sample2, [rmax] * 3, period, None, None)
+        self.seconds_mesh = time.perf_counter() - t0
+        self.dm = dm
+        self.ncells = dm.mesh1.ncells
+        self.num_threads = int(num_threads)
+        _WORKER_ENGINE = partial(engine("npairs_3d_engine"), _DoubleMeshView(dm), c1[0], c1[1], c1[2], c2[0], c2[1], c2[2], rbins)
+        t0 = time.perf_counter()
+        self.pool = multiprocessing.Pool(self.num_threads) if self.num_threads > 1 else None
+        self.seconds_pool = time.perf_counter() - t0
+
+    def run(self, cell1_range):
+        first, last = int(cell1_range[0]), int(cell1_range[1])
+        if self.pool is None:
+            return np.array(_WORKER_ENGINE((first, last)))
+        # one contiguous range per worker, the reference's own split (mesh_helpers.py:183-221); every engine call
+        # re-gathers the sorted coordinates of both samples first (npairs_3d_engine.pyx:58-64) - part of the engine
+        nt, tuples = _cell1_tuples(last - first, self.num_threads)
+        tuples = [(a + first, b + first) for a, b in tuples]
+        return np.sum(np.array(self.pool.map(_worker_call, tuples, chunksize=1)), axis=0)
+
+    def close(self):
+        if self.pool is not None:
+            self.pool.close()
+            self.pool.join()
+            self.pool = None
 
 
 def npairs_3d(sample1, sample2, rbins, period=None, approx_cell1_size=None, approx_cell2_size=None,

@@ -126,19 +126,49 @@ def c4():
     return s, w, synthetic.config_rbins()
 
 
-# mesh1 of config 4 has 50^3 = 125000 cells: the first 1200 (x-layer 0: wraps in x), an interior block, the last 600
-@pytest.mark.parametrize("cells", [(0, 1200), (61000, 61600), (124400, 125000)])
-def test_config4_marked_and_unmarked_cells(c4, cells):
+def _ncells1_3d(rmax, period):
+    """Number of reference mesh1 cells of a default-cell-size call (oracle mesh restatement on two points)."""
+    pts = np.array([[0.1, 0.1, 0.1], [0.2, 0.2, 0.2]])
+    return oracle.build_double_mesh_3d(pts, pts, [rmax] * 3, period, None, None)[0].mesh1.ncells
+
+
+# mesh1 of config 4: rmax = 10**log10(20) is a hair above 20, so 49^3 = 117649 cells (not 50^3).  The first 1200 cells
+# (x-layer 0: wraps in x), an interior block, and the last 600 cells (wraps in x, y and z)
+@pytest.mark.parametrize("where", ["first", "interior", "last"])
+def test_config4_marked_and_unmarked_cells(c4, where):
     s, w, rbins = c4
+    nc = _ncells1_3d(float(rbins.max()), 1000.0)
+    assert nc == 49 ** 3
+    cells = {"first": (0, 1200), "interior": (nc // 2, nc // 2 + 600), "last": (nc - 600, nc)}[where]
     want = REF.marked_npairs_3d(s, s, rbins, 1, period=1000.0, weights1=w, weights2=w, num_threads=CORES, cell1_range=cells)
     wantn = REF.npairs_3d(s, s, rbins, period=1000.0, num_threads=CORES, cell1_range=cells)
+    assert np.all(np.isfinite(want)) and wantn[0] > 0
     with distributed.cell_range(*cells):
         got = hb.marked_npairs_3d(s, s, rbins, 1, period=1000.0, weights1=w, weights2=w)
         assert _lib.last_stats["path"] == 1          # MarkedQ
         gotn = hb.npairs_3d(s, s, rbins, period=1000.0)
     assert np.array_equal(gotn, wantn), (gotn, wantn)
     err = np.max(np.abs(got - want) / np.abs(want))
-    assert err <= 1e-12, err
+    assert err <= 1e-12, (err, got, want)
+
+
+def test_config4_symmetric_partition_sums_to_reference_cells(c4):
+    """HTB_FLAG_PARTITION_SUM (what the multi-GPU front-ends pass): per-part counts of the symmetric kernels differ
+    from the reference's per-range counts, their sum over a partition does not.  Checked on the unmarked counter:
+    two parts of a partition of ALL cells = the full count, whose first cells are pinned to the reference above."""
+    s, w, rbins = c4
+    nc = _ncells1_3d(float(rbins.max()), 1000.0)
+    full = hb.npairs_3d(s, s, rbins, period=1000.0)
+    old = _lib.default_flags
+    total = np.zeros_like(full)
+    try:
+        _lib.default_flags = old | _lib.FLAG_PARTITION_SUM
+        for cells in ((0, nc // 3), (nc // 3, nc)):
+            with distributed.cell_range(*cells):
+                total += hb.npairs_3d(s, s, rbins, period=1000.0)
+    finally:
+        _lib.default_flags = old
+    assert np.array_equal(total, full)
 
 
 # ------------------------------------------------------------------ config 5: delta-sigma, 1e6 x 1e8
