@@ -23,6 +23,7 @@ FLAG_COLUMN_SUM = 64
 FLAG_CACHE_SAMPLE1 = 128
 FLAG_CACHE_SAMPLE2 = 256
 FLAG_PARTITION_SUM = 512
+FLAG_DEVICE_OUTPUT = 1024
 
 EXPORTS = (
     "htb_last_error", "htb_abi_version", "htb_device_count", "htb_set_device", "htb_set_stream", "htb_set_shard",
@@ -32,7 +33,7 @@ EXPORTS = (
     "htb_marked_npairs_xy_z_engine", "htb_npairs_per_object_3d_engine", "htb_weighted_npairs_xy_engine",
     "htb_npairs_jackknife_3d_engine", "htb_npairs_jackknife_xy_z_engine", "htb_weighted_npairs_per_object_xy_engine",
     "htb_mesh_cell_ids", "htb_mesh_cell_id_indices", "htb_cell1_work", "htb_measure_fp64_rate",
-    "htb_host_minmax", "htb_device_minmax",
+    "htb_host_minmax", "htb_device_minmax", "htb_tp_estimator", "htb_get_stream", "htb_stream_synchronize", "htb_async_count_times",
 )
 
 
@@ -190,18 +191,60 @@ class Columns(object):
 
 
 def run_engine(func_name, *args, **kw):
-    """Call an engine entry point, appending (flags, stats) and recording the stats."""
+    """Call an engine entry point, appending (flags, stats) and recording the stats.  ``out_device=True``: the
+    output argument is a device pointer and the call is asynchronous (HTB_FLAG_DEVICE_OUTPUT; no stats)."""
     global last_stats
     lib = require_gpu()
     st = Stats()
     from . import distributed
+    out_device = bool(kw.get("out_device"))
     flags = (default_flags | (FLAG_DEVICE_INPUT if kw.get("device") else 0) | int(kw.get("extra_flags", 0))
-             | distributed.engine_flags())
+             | distributed.engine_flags() | (FLAG_DEVICE_OUTPUT if out_device else 0))
+    want_stats = collect_stats and not out_device
     rc = getattr(lib, func_name)(*args, ctypes.c_uint32(flags),
-                                 ctypes.byref(st) if collect_stats else None)
+                                 ctypes.byref(st) if want_stats else None)
     check(rc)
-    last_stats = st.as_dict() if collect_stats else None
+    last_stats = st.as_dict() if want_stats else None
     return last_stats
+
+
+def out_pointer(out, numpy_array, ctype):
+    """ctypes pointer of an engine's output: the numpy array, or - asynchronous call - a torch CUDA tensor."""
+    if out is None:
+        return numpy_array.ctypes.data_as(ctypes.POINTER(ctype))
+    if not (getattr(out, "is_cuda", False) and out.is_contiguous() and out.numel() == numpy_array.size
+            and out.element_size() == 8):
+        raise TypeError("device output must be a contiguous 8-byte CUDA tensor with %d elements" % numpy_array.size)
+    return ctypes.cast(ctypes.c_void_p(int(out.data_ptr())), ctypes.POINTER(ctype))
+
+
+_streams = {}
+
+
+def engine_stream():
+    """The CUDA stream this thread's engine calls are issued on, as a torch stream (plumbing: lets torch allocate the
+    count tables and run the NCCL all-reduce in stream order with the kernels)."""
+    import torch
+    lib = require_gpu()
+    ptr = ctypes.c_void_p()
+    check(lib.htb_get_stream(ctypes.byref(ptr)))
+    key = (torch.cuda.current_device(), ptr.value)
+    if key not in _streams:
+        _streams[key] = torch.cuda.ExternalStream(ptr.value or 0, device=torch.cuda.current_device())
+    return _streams[key]
+
+
+def async_count_times():
+    """CUDA-event durations (ms) of the counting kernels of the asynchronous calls since the last query."""
+    lib = require_gpu()
+    buf = (ctypes.c_float * 16)()
+    n = ctypes.c_int32(0)
+    check(lib.htb_async_count_times(buf, ctypes.c_int32(16), ctypes.byref(n)))
+    return [float(buf[i]) for i in range(n.value)]
+
+
+def stream_synchronize():
+    check(require_gpu().htb_stream_synchronize())
 
 
 def measure_fp64_rate():

@@ -243,6 +243,7 @@ struct StagePool {
     double *pinned[HTB_STAGE_THREADS][2] = {{nullptr}};
     cudaEvent_t ev[HTB_STAGE_THREADS][2] = {{nullptr}};
     cudaEvent_t done[HTB_STAGE_THREADS] = {nullptr};
+    cudaEvent_t dst_ready = nullptr;          // the destination blocks are ours in the order of the engine's stream
     cudaStream_t st[HTB_STAGE_THREADS] = {nullptr};
     int cols = 0;
     bool ready = false;
@@ -263,6 +264,7 @@ static int stage_pool_init(int dev, int cols)
         if (!sp.st[t]) HTB_CUDA(cudaStreamCreateWithFlags(&sp.st[t], cudaStreamNonBlocking));
         if (!sp.done[t]) HTB_CUDA(cudaEventCreateWithFlags(&sp.done[t], cudaEventDisableTiming));
     }
+    if (!sp.dst_ready) HTB_CUDA(cudaEventCreateWithFlags(&sp.dst_ready, cudaEventDisableTiming));
     sp.cols = cols;
     sp.ready = true;
     return 0;
@@ -286,9 +288,13 @@ static int staged_upload(cudaStream_t st, const double *const *src, int cnt, int
     int nthreads = (int)std::min<int64_t>(HTB_STAGE_THREADS, nchunk);
     const unsigned hw = std::thread::hardware_concurrency();
     if (hw > 0 && (unsigned)nthreads > hw) nthreads = (int)hw;
+    // the destination blocks come from the stream-ordered pool of `st`: they may still be in use by work enqueued
+    // earlier on `st` (asynchronous calls), so the copy streams start behind everything `st` holds now
+    HTB_CUDA(cudaEventRecord(sp.dst_ready, st));
     std::atomic<int> failed(0);
     auto work = [&](int t) {
         if (cudaSetDevice(dev) != cudaSuccess) { failed = 1; return; }
+        if (cudaStreamWaitEvent(sp.st[t], sp.dst_ready, 0) != cudaSuccess) { failed = 1; return; }
         int k = 0;
         for (int64_t c = t; c < nchunk; c += nthreads, ++k) {
             const int b = k & 1;
@@ -459,10 +465,39 @@ extern "C" int htb_device_minmax(const double *base_dev, int64_t n, int64_t stri
 }
 
 // ------------------------------------------------------------------ one engine call
+// sum of the per-cell predicted work over the cells [first, last) (or the device-side shard range): W_ref of a call
+__global__ void __launch_bounds__(256) k_sum_range(const double *__restrict__ work, long long ncells, long long first, long long last,
+                                                   const long long *__restrict__ range, double *__restrict__ out)
+{
+    __shared__ double sh[256];
+    if (range) { first = range[0]; last = range[1]; }
+    if (first < 0) first = 0;
+    if (last > ncells) last = ncells;
+    double s = 0.0;
+    for (long long c = first + threadIdx.x; c < last; c += 256) s += work[c];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = sh[0];
+}
+
+// CUDA events of the per-call timing (htb_stats): created once per thread and device, reused by every call
+// (five cudaEventCreate/Destroy per call were part of the 0.8 ms fixed cost of a small call)
+static thread_local cudaEvent_t g_call_ev[64][5] = {{nullptr}};
+// asynchronous calls (HTB_FLAG_DEVICE_OUTPUT) bracket their counting kernel with a pair of events from a small ring;
+// htb_async_count_times() reads the elapsed times once the caller has synchronised (bench: the kernel's live duration
+// inside the timed region)
+#define HTB_ASYNC_RING 16
+static thread_local cudaEvent_t g_async_ev[HTB_ASYNC_RING][2] = {{nullptr}};
+static thread_local int g_async_n = 0;
+
 struct Call {
     cudaStream_t st = nullptr;
     Workspace ws;
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t *ev = nullptr;            // this thread's five timing events on the current device (null: asynchronous call)
     int launches = 0;
     WalkGeom G{};
     WalkArrays A{};
@@ -475,18 +510,32 @@ struct Call {
     double *work_dev = nullptr;             // predicted work per reference mesh1 cell (computed once per call)
     int64_t nc1 = 0;
     uint32_t flags = 0;
+    bool async = false;                     // HTB_FLAG_DEVICE_OUTPUT: results stay on the device, no host synchronisation
 
-    ~Call()
-    {
-        ws.release();
-        for (int i = 0; i < 5; ++i) if (ev[i]) cudaEventDestroy(ev[i]);
-    }
-    int begin()
+    ~Call() { ws.release(); }
+    int begin(uint32_t fl = 0)
     {
         if (get_stream(&st)) return 1;
         ws.st = st;
-        for (int i = 0; i < 5; ++i) HTB_CUDA(cudaEventCreate(&ev[i]));
-        HTB_CUDA(cudaEventRecord(ev[0], st));
+        async = (fl & HTB_FLAG_DEVICE_OUTPUT) != 0;
+        if (!async) {
+            int dev = 0;
+            HTB_CUDA(cudaGetDevice(&dev));
+            ev = g_call_ev[dev];
+            for (int i = 0; i < 5; ++i) if (!ev[i]) HTB_CUDA(cudaEventCreate(&ev[i]));
+            HTB_CUDA(cudaEventRecord(ev[0], st));
+        }
+        return 0;
+    }
+    int mark(int i)
+    {
+        if (ev) HTB_CUDA(cudaEventRecord(ev[i], st));
+        else if (async && (i == 2 || i == 3)) {
+            cudaEvent_t *pair = g_async_ev[g_async_n % HTB_ASYNC_RING];
+            for (int k = 0; k < 2; ++k) if (!pair[k]) HTB_CUDA(cudaEventCreate(&pair[k]));
+            HTB_CUDA(cudaEventRecord(pair[i - 2], st));
+            if (i == 3) ++g_async_n;
+        }
         return 0;
     }
     // bring `cnt` arrays of n elements (common element stride) to the device; returns device pointers + stride
@@ -614,7 +663,7 @@ struct Call {
         if (stage_rows(w1, n1, nw, &dw1)) return 1;
         if (w2 == w1 && same) dw2 = dw1;
         else if (stage_rows(w2, n2, nw, &dw2)) return 1;
-        HTB_CUDA(cudaEventRecord(ev[1], st));
+        if (mark(1)) return 1;
         // ---- K1
         choose_refinement(g, n1, n2, tile, m1, m2, refine_mode);
         // Symmetric auto-correlation (count each zero-shift unordered pair once, weight 2) needs the two
@@ -726,54 +775,117 @@ struct Call {
         A.redo_cap = getenv("HTB_REDO_INPLACE") ? 0u : (1u << 16);
         A.redo_ent = nullptr;
         if (A.redo_cap && ws.alloc((void **)&A.redo_ent, sizeof(uint2) * (size_t)A.redo_cap)) return 1;
-        HTB_CUDA(cudaEventRecord(ev[2], st));
+        if (mark(2)) return 1;
         return 0;
     }
     bool count_marked = false;
     // end of the counting kernels (output copies that follow are not part of ms_count)
     int mark_count_end()
     {
-        if (!count_marked) { HTB_CUDA(cudaEventRecord(ev[3], st)); count_marked = true; }
+        if (!count_marked) { if (mark(3)) return 1; count_marked = true; }
         return 0;
     }
     int finish(htb_stats *stats, int path)
     {
-        if (mark_count_end()) return 1;
-        unsigned int h[4] = {0, 0, 0, 0};
-        uint32_t ntiles = 0;
-        std::vector<double> work;
-        long long range_h[2] = {(long long)first_cell, (long long)last_cell};
-        if (stats) {
-            if (!work_dev && htb_reference_work(st, ws, G, s1, s2, &work_dev, nullptr, &nc1, &launches)) return 1;
-            if (range_dev) HTB_CUDA(cudaMemcpyAsync(range_h, range_dev, sizeof(range_h), cudaMemcpyDeviceToHost, st));
-            work.resize((size_t)nc1);
-            HTB_CUDA(cudaMemcpyAsync(work.data(), work_dev, sizeof(double) * (size_t)nc1, cudaMemcpyDeviceToHost, st));
-            HTB_CUDA(cudaMemcpyAsync(h, ctr, sizeof(h), cudaMemcpyDeviceToHost, st));
-            HTB_CUDA(cudaMemcpyAsync(&ntiles, A.ntiles_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        if (async) {
+            // results stay on the device; the caller synchronises once for the whole statistic (no stats)
+            if (stats) memset(stats, 0, sizeof(*stats));
+            return 0;
         }
-        HTB_CUDA(cudaEventRecord(ev[4], st));
+        if (mark_count_end()) return 1;
+        struct { unsigned int h[4]; uint32_t ntiles; uint32_t pad; double wref; } rb = {{0, 0, 0, 0}, 0, 0, 0.0};
+        double *wsum = nullptr;
+        if (stats) {
+            // W_ref of this call's (this rank's) cell range, summed on the device: one 8-byte read-back instead of the
+            // per-cell work vector
+            if (!work_dev && htb_reference_work(st, ws, G, s1, s2, &work_dev, nullptr, &nc1, &launches)) return 1;
+            if (ws.alloc((void **)&wsum, sizeof(double))) return 1;
+            k_sum_range<<<1, 256, 0, st>>>(work_dev, (long long)nc1, (long long)first_cell, (long long)last_cell, range_dev, wsum);
+            launches += 1;
+            HTB_CUDA(cudaGetLastError());
+            HTB_CUDA(cudaMemcpyAsync(&rb.wref, wsum, sizeof(double), cudaMemcpyDeviceToHost, st));
+            HTB_CUDA(cudaMemcpyAsync(rb.h, ctr, sizeof(rb.h), cudaMemcpyDeviceToHost, st));
+            HTB_CUDA(cudaMemcpyAsync(&rb.ntiles, A.ntiles_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        }
+        if (mark(4)) return 1;
         HTB_CUDA(cudaStreamSynchronize(st));
         if (stats) {
             memset(stats, 0, sizeof(*stats));
             unsigned long long pe;
-            memcpy(&pe, &h[2], sizeof(pe));
+            memcpy(&pe, &rb.h[2], sizeof(pe));
             stats->pairs_evaluated = (double)pe;
-            double wr = 0.0;
-            for (int64_t c = (range_h[0] > 0 ? range_h[0] : 0); c < nc1 && c < range_h[1]; ++c) wr += work[(size_t)c];
-            stats->pairs_reference = wr;
+            stats->pairs_reference = rb.wref;
             cudaEventElapsedTime(&stats->ms_h2d, ev[0], ev[1]);
             cudaEventElapsedTime(&stats->ms_mesh, ev[1], ev[2]);
             cudaEventElapsedTime(&stats->ms_count, ev[2], ev[3]);
             cudaEventElapsedTime(&stats->ms_total, ev[0], ev[4]);
             stats->kernel_launches = launches;
-            stats->tiles = (int32_t)ntiles;
-            stats->tiles_redone = (int32_t)h[1];
+            stats->tiles = (int32_t)rb.ntiles;
+            stats->tiles_redone = (int32_t)rb.h[1];
             for (int d = 0; d < 3; ++d) { stats->refine1[d] = m1[d]; stats->refine2[d] = m2[d]; }
             stats->path = path;
         }
         return 0;
     }
+    // hand n 8-byte result words to the caller: device -> host, or device -> device for an asynchronous call
+    int deliver(void *out, const void *src_dev, size_t n)
+    {
+        if (n == 0) return 0;
+        HTB_CUDA(cudaMemcpyAsync(out, src_dev, 8 * n, async ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+        return 0;
+    }
+    // device buffer a finishing kernel writes the caller's n result words to: the caller's own (device) array for an
+    // asynchronous call, else a workspace block that out_fetch() copies to the host array
+    int out_buffer(void *user_out, size_t n, void **dev)
+    {
+        if (async) { *dev = user_out; return 0; }
+        return ws.alloc(dev, 8 * (n ? n : 1));
+    }
+    int out_fetch(void *user_out, const void *dev, size_t n)
+    {
+        if (async || n == 0) return 0;
+        HTB_CUDA(cudaMemcpyAsync(user_out, dev, 8 * n, cudaMemcpyDeviceToHost, st));
+        return 0;
+    }
 };
+
+// ------------------------------------------------------------------ finishing kernels (tiny, one block)
+// differential histogram (lowest satisfied edge per axis) -> the reference's cumulative counts: inclusive prefix sums
+// along the second axis, then along the first (npairs_s_mu_engine.pyx:232-234; additions only, so float sums lose nothing)
+template <class T>
+__global__ void __launch_bounds__(128) k_prefix2d(const T *__restrict__ diff, int n0, int n1, T *__restrict__ out)
+{
+    __shared__ T sh[4096];
+    const int n = n0 * n1, t = threadIdx.x;
+    for (int i = t; i < n; i += 128) sh[i] = diff[i];
+    __syncthreads();
+    for (int k = t; k < n0; k += 128) { T run = 0; for (int g = 0; g < n1; ++g) { run += sh[k * n1 + g]; sh[k * n1 + g] = run; } }
+    __syncthreads();
+    for (int g = t; g < n1; g += 128) { T run = 0; for (int k = 0; k < n0; ++k) { run += sh[k * n1 + g]; sh[k * n1 + g] = run; } }
+    __syncthreads();
+    for (int i = t; i < n; i += 128) out[i] = sh[i];
+}
+// FastXYZ: device layout {top pi column [nrp], lower pi column [nrp]} -> row-major (nrp, npi)
+__global__ void k_xyz_columns(const unsigned long long *__restrict__ cols, int nrp, int npi, unsigned long long *__restrict__ out)
+{
+    const int k = threadIdx.x;
+    if (k >= nrp) return;
+    out[k * npi + (npi - 1)] = cols[k];
+    if (npi == 2) out[k * npi] = cols[nrp + k];
+}
+// MarkedQ: differential level sums [HTB_NBF] + the sum over all in-range pairs [1] -> cumulative sums [nb]
+// (marked_npairs_3d_engine.pyx:212-216: a pair of level s counts for every edge >= s)
+__global__ void k_markedq_cumulate(const double *__restrict__ h, int nb, double *__restrict__ out)
+{
+    if (threadIdx.x) return;
+    const int pad = HTB_NBF - nb;
+    double run = 0.0;
+    for (int s = 0; s < HTB_NBF; ++s) {
+        run += h[s];
+        if (s >= pad && s < HTB_NBF - 1) out[s - pad] = run;
+    }
+    out[nb - 1] = h[HTB_NBF];
+}
 
 static bool finite_all(const double *v, int n)
 {
@@ -912,35 +1024,23 @@ static int binq_prepare(Call &c, const double *e0, int n0, const double *e1, int
     return 0;
 }
 
-// inclusive 2-D prefix sums: differential histogram -> the reference's cumulative counts
-template <class T>
-static void prefix2d(const T *diff, int n0, int n1, T *out)
-{
-    for (int k = 0; k < n0; ++k)
-        for (int g = 0; g < n1; ++g) {
-            T s = diff[(size_t)k * n1 + g];
-            if (k > 0) s += out[(size_t)(k - 1) * n1 + g];
-            if (g > 0) s += out[(size_t)k * n1 + g - 1];
-            if (k > 0 && g > 0) s -= out[(size_t)(k - 1) * n1 + g - 1];
-            out[(size_t)k * n1 + g] = s;
-        }
-}
-
 static int run_binq(Call &c, int kind, const double *e0, int n0, const double *e1, int n1, int64_t *counts_out, htb_stats *stats)
 {
     BinQParams bp{};
     if (binq_prepare(c, e0, n0, e1, n1, &bp)) return 1;
     const int nh = n0 * n1;
-    unsigned long long *counts_dev = nullptr;
+    unsigned long long *counts_dev = nullptr, *cum = nullptr;
     if (c.ws.alloc((void **)&counts_dev, sizeof(unsigned long long) * (size_t)nh)) return 1;
     HTB_CUDA(cudaMemsetAsync(counts_dev, 0, sizeof(unsigned long long) * (size_t)nh, c.st));
     bp.counts = counts_dev;
     if (htb_launch_binq(c.st, kind, 0, c.G, c.A, bp, &c.launches)) return 1;
-    std::vector<long long> diff((size_t)nh);
-    HTB_CUDA(cudaMemcpyAsync(diff.data(), counts_dev, sizeof(int64_t) * (size_t)nh, cudaMemcpyDeviceToHost, c.st));
-    if (c.finish(stats, 3)) return 1;
-    prefix2d<long long>(diff.data(), n0, n1, (long long *)counts_out);
-    return 0;
+    if (c.mark_count_end()) return 1;
+    if (c.out_buffer(counts_out, (size_t)nh, (void **)&cum)) return 1;
+    k_prefix2d<unsigned long long><<<1, 128, 0, c.st>>>(counts_dev, n0, n1, cum);
+    c.launches += 1;
+    HTB_CUDA(cudaGetLastError());
+    if (c.out_fetch(counts_out, cum, (size_t)nh)) return 1;
+    return c.finish(stats, 3);
 }
 
 // weighted sums (MODE 1): differential float histogram -> cumulative sums.  The differential cells are summed in
@@ -952,17 +1052,19 @@ static int run_binq_weighted(Call &c, int kind, int nw, int wfunc, const double 
     BinQParams bp{};
     if (binq_prepare(c, e0, n0, e1, n1, &bp)) return 1;
     const int nh = n0 * n1;
-    double *sums_dev = nullptr;
+    double *sums_dev = nullptr, *cum = nullptr;
     if (c.ws.alloc((void **)&sums_dev, sizeof(double) * (size_t)nh)) return 1;
     HTB_CUDA(cudaMemsetAsync(sums_dev, 0, sizeof(double) * (size_t)nh, c.st));
     bp.fcounts = sums_dev;
     bp.nw = nw; bp.wfunc = wfunc;
     if (htb_launch_binq(c.st, kind, mode, c.G, c.A, bp, &c.launches)) return 1;
-    std::vector<double> diff((size_t)nh);
-    HTB_CUDA(cudaMemcpyAsync(diff.data(), sums_dev, sizeof(double) * (size_t)nh, cudaMemcpyDeviceToHost, c.st));
-    if (c.finish(stats, 3)) return 1;
-    prefix2d<double>(diff.data(), n0, n1, counts_out);
-    return 0;
+    if (c.mark_count_end()) return 1;
+    if (c.out_buffer(counts_out, (size_t)nh, (void **)&cum)) return 1;
+    k_prefix2d<double><<<1, 128, 0, c.st>>>(sums_dev, n0, n1, cum);
+    c.launches += 1;
+    HTB_CUDA(cudaGetLastError());
+    if (c.out_fetch(counts_out, cum, (size_t)nh)) return 1;
+    return c.finish(stats, 3);
 }
 
 // ------------------------------------------------------------------ npairs_3d
@@ -981,7 +1083,7 @@ extern "C" int htb_npairs_3d_engine(const htb_mesh_geom *mesh,
     Fast3Params fp{};
     bool fast = fast3_params(mesh, rbins, rsq.data(), nb, flags, &fp, &lmax);
     Call c;
-    if (c.begin()) return 1;
+    if (c.begin(flags)) return 1;
     const double *c1[3] = {x1, y1, z1}, *c2[3] = {x2, y2, z2};
     if (c.setup(mesh, 1, true, c1, stride1, n1, nullptr, c2, stride2, n2, nullptr, 0, false, first_cell1, last_cell1, flags,
                 fast ? 32 * htb_fast3_ppl() : HTB_TILE, fast ? 8.0 * lmax : 1.0e150)) return 1;
@@ -1006,7 +1108,8 @@ extern "C" int htb_npairs_3d_engine(const htb_mesh_geom *mesh,
         gp.counts = counts_dev;
         if (htb_launch_gen(c.st, 0, c.G, c.A, gp, &c.launches)) return 1;
     }
-    HTB_CUDA(cudaMemcpyAsync(counts_out, counts_dev, sizeof(int64_t) * (size_t)nb, cudaMemcpyDeviceToHost, c.st));
+    if (c.mark_count_end()) return 1;
+    if (c.deliver(counts_out, counts_dev, (size_t)nb)) return 1;
     return c.finish(stats, fast ? 1 : 0);
     HTB_GUARD_END
 }
@@ -1034,7 +1137,7 @@ extern "C" int htb_npairs_xy_z_engine(const htb_mesh_geom *mesh,
     if (fast && npi == 2) fast = pi_bins[0] >= 0.0 && e[nrp] <= 1e-8 * e[nrp + 1];
     const int nh = nrp * npi;
     Call c;
-    if (c.begin()) return 1;
+    if (c.begin(flags)) return 1;
     const double *c1[3] = {x1, y1, z1}, *c2[3] = {x2, y2, z2};
     if (c.setup(mesh, 0, true, c1, stride1, n1, nullptr, c2, stride2, n2, nullptr, 0, false, first_cell1, last_cell1, flags,
                 fast ? 32 * htb_fast3_ppl() : HTB_TILE, fast ? 8.0 * lmax : 1.0e150)) return 1;
@@ -1051,14 +1154,14 @@ extern "C" int htb_npairs_xy_z_engine(const htb_mesh_geom *mesh,
             fp.counts0 = counts_dev + nrp;
         }
         if (htb_launch_fastxyz(c.st, c.G, c.A, fp, &c.launches)) return 1;
-        std::vector<long long> cols((size_t)nh);
-        HTB_CUDA(cudaMemcpyAsync(cols.data(), counts_dev, sizeof(int64_t) * (size_t)nh, cudaMemcpyDeviceToHost, c.st));
-        if (c.finish(stats, 1)) return 1;
-        for (int k = 0; k < nrp; ++k) {
-            counts_out[(size_t)k * npi + (npi - 1)] = cols[(size_t)k];
-            if (npi == 2) counts_out[(size_t)k * npi] = cols[(size_t)nrp + k];
-        }
-        return 0;
+        if (c.mark_count_end()) return 1;
+        unsigned long long *res = nullptr;
+        if (c.out_buffer(counts_out, (size_t)nh, (void **)&res)) return 1;
+        k_xyz_columns<<<1, 32, 0, c.st>>>(counts_dev, nrp, npi, res);        // nrp <= HTB_NBF
+        c.launches += 1;
+        HTB_CUDA(cudaGetLastError());
+        if (c.out_fetch(counts_out, res, (size_t)nh)) return 1;
+        return c.finish(stats, 1);
     }
     {
         std::vector<double> em(e);
@@ -1074,7 +1177,8 @@ extern "C" int htb_npairs_xy_z_engine(const htb_mesh_geom *mesh,
     gp.e0 = (const double *)edev; gp.e1 = (const double *)edev + nrp;
     gp.counts = counts_dev;
     if (htb_launch_gen(c.st, 1, c.G, c.A, gp, &c.launches)) return 1;
-    HTB_CUDA(cudaMemcpyAsync(counts_out, counts_dev, sizeof(int64_t) * (size_t)nh, cudaMemcpyDeviceToHost, c.st));
+    if (c.mark_count_end()) return 1;
+    if (c.deliver(counts_out, counts_dev, (size_t)nh)) return 1;
     return c.finish(stats, 0);
     HTB_GUARD_END
 }
@@ -1091,7 +1195,7 @@ extern "C" int htb_npairs_s_mu_engine(const htb_mesh_geom *mesh,
     if (!mesh || !s_bins || !mu_bins || !counts_out || ns < 1 || nmu < 1) { htb_set_error("htb_npairs_s_mu_engine: bad arguments"); return 1; }
     if (mesh->ndim != 3) { htb_set_error("htb_npairs_s_mu_engine needs a 3-d mesh"); return 1; }
     Call c;
-    if (c.begin()) return 1;
+    if (c.begin(flags)) return 1;
     const double *c1[3] = {x1, y1, z1}, *c2[3] = {x2, y2, z2};
     if (c.setup(mesh, 1, true, c1, stride1, n1, nullptr, c2, stride2, n2, nullptr, 0, false, first_cell1, last_cell1, flags)) return 1;
     std::vector<double> e((size_t)ns + nmu);
@@ -1112,19 +1216,16 @@ extern "C" int htb_npairs_s_mu_engine(const htb_mesh_geom *mesh,
     gp.max0 = m0; gp.max1 = m1;
     gp.counts = counts_dev;
     if (htb_launch_gen(c.st, 2, c.G, c.A, gp, &c.launches)) return 1;
-    std::vector<long long> diff((size_t)nh);
-    HTB_CUDA(cudaMemcpyAsync(diff.data(), counts_dev, sizeof(int64_t) * (size_t)nh, cudaMemcpyDeviceToHost, c.st));
-    if (c.finish(stats, 0)) return 1;
+    if (c.mark_count_end()) return 1;
+    if (nh > 4096) { htb_set_error("htb_npairs_s_mu_engine: at most 4096 (s, mu) cells"); return 1; }
     // 2-D inclusive prefix sums (npairs_s_mu_engine.pyx:232-234) over the tiny histogram
-    for (int k = 0; k < ns; ++k)
-        for (int g = 0; g < nmu; ++g) {
-            long long s = diff[(size_t)k * nmu + g];
-            if (k > 0) s += counts_out[(size_t)(k - 1) * nmu + g];
-            if (g > 0) s += counts_out[(size_t)k * nmu + g - 1];
-            if (k > 0 && g > 0) s -= counts_out[(size_t)(k - 1) * nmu + g - 1];
-            counts_out[(size_t)k * nmu + g] = s;
-        }
-    return 0;
+    unsigned long long *cum = nullptr;
+    if (c.out_buffer(counts_out, (size_t)nh, (void **)&cum)) return 1;
+    k_prefix2d<unsigned long long><<<1, 128, 0, c.st>>>(counts_dev, ns, nmu, cum);
+    c.launches += 1;
+    HTB_CUDA(cudaGetLastError());
+    if (c.out_fetch(counts_out, cum, (size_t)nh)) return 1;
+    return c.finish(stats, 0);
     HTB_GUARD_END
 }
 
@@ -1151,7 +1252,7 @@ extern "C" int htb_marked_npairs_3d_engine(const htb_mesh_geom *mesh,
     const bool fast = nw == 1 && (weight_func_id == 0 || weight_func_id == 1) &&
                       fast3_params(mesh, rbins, rsq.data(), nb, flags, &fp, &lmax);
     Call c;
-    if (c.begin()) return 1;
+    if (c.begin(flags)) return 1;
     const double *c1[3] = {x1, y1, z1}, *c2[3] = {x2, y2, z2};
     if (c.setup(mesh, 1, fast && w1 == w2, c1, stride1, n1, w1, c2, stride2, n2, w2, nw, false, first_cell1, last_cell1, flags,
                 HTB_TILE, fast ? 8.0 * lmax : 1.0e150)) return 1;
@@ -1161,18 +1262,14 @@ extern "C" int htb_marked_npairs_3d_engine(const htb_mesh_geom *mesh,
         HTB_CUDA(cudaMemsetAsync(fs, 0, sizeof(double) * (HTB_NBF + 1), c.st));
         fp.fsums = fs;
         if (htb_launch_markedq(c.st, c.G, c.A, fp, &c.launches)) return 1;
-        double h[HTB_NBF + 1];
-        HTB_CUDA(cudaMemcpyAsync(h, fs, sizeof(h), cudaMemcpyDeviceToHost, c.st));
-        if (c.finish(stats, 1)) return 1;
-        // cumulative sums (marked_npairs_3d_engine.pyx:212-216): a pair of level s counts for every edge >= s
-        const int pad = HTB_NBF - nb;
-        double run = 0.0;
-        for (int s = 0; s < HTB_NBF; ++s) {
-            run += h[s];
-            if (s >= pad && s < HTB_NBF - 1) counts_out[s - pad] = run;
-        }
-        counts_out[nb - 1] = h[HTB_NBF];
-        return 0;
+        if (c.mark_count_end()) return 1;
+        double *res = nullptr;
+        if (c.out_buffer(counts_out, (size_t)nb, (void **)&res)) return 1;
+        k_markedq_cumulate<<<1, 32, 0, c.st>>>(fs, nb, res);
+        c.launches += 1;
+        HTB_CUDA(cudaGetLastError());
+        if (c.out_fetch(counts_out, res, (size_t)nb)) return 1;
+        return c.finish(stats, 1);
     }
     {
         std::vector<double> em(rsq);
@@ -1190,7 +1287,8 @@ extern "C" int htb_marked_npairs_3d_engine(const htb_mesh_geom *mesh,
     gp.e0 = (const double *)edev;
     gp.fcounts = counts_dev;
     if (htb_launch_gen(c.st, 3, c.G, c.A, gp, &c.launches)) return 1;
-    HTB_CUDA(cudaMemcpyAsync(counts_out, counts_dev, sizeof(double) * (size_t)nb, cudaMemcpyDeviceToHost, c.st));
+    if (c.mark_count_end()) return 1;
+    if (c.deliver(counts_out, counts_dev, (size_t)nb)) return 1;
     return c.finish(stats, 0);
     HTB_GUARD_END
 }
@@ -1220,7 +1318,7 @@ extern "C" int htb_marked_npairs_xy_z_engine(const htb_mesh_geom *mesh,
         return 1;
     }
     Call c;
-    if (c.begin()) return 1;
+    if (c.begin(flags)) return 1;
     const double *c1[3] = {x1, y1, z1}, *c2[3] = {x2, y2, z2};
     if (c.setup(mesh, 0, false, c1, stride1, n1, w1, c2, stride2, n2, w2, nw, false, first_cell1, last_cell1, flags)) return 1;
     return run_binq_weighted(c, 1, nw, weight_func_id, e.data(), nrp, e.data() + nrp, npi, counts_out, stats);
@@ -1246,7 +1344,7 @@ extern "C" int htb_weighted_npairs_xy_engine(const htb_mesh_geom *mesh,
         return 1;
     }
     Call c;
-    if (c.begin()) return 1;
+    if (c.begin(flags)) return 1;
     const double *c1[3] = {x1, y1, nullptr}, *c2[3] = {x2, y2, nullptr};
     if (c.setup(mesh, 1, false, c1, stride1, n1, nullptr, c2, stride2, n2, w2, 1, false, first_cell1, last_cell1, flags)) return 1;
     // few bins: lane-private rows + a warp reduction per tile (MODE 5) instead of shared-memory atomics on a handful of cells
@@ -1271,6 +1369,7 @@ extern "C" int htb_weighted_npairs_per_object_xy_engine(const htb_mesh_geom *mes
     suffix_min(e, 0, nrp);
     if (!binq_ok(e.data(), nrp, nullptr, 1, flags & ~HTB_FLAG_GENERIC)) { htb_set_error("htb_weighted_npairs_per_object_xy_engine: rp_bins must be finite"); return 1; }
     Call c;
+    if (flags & HTB_FLAG_DEVICE_OUTPUT) { htb_set_error("per-object tables are returned to host memory (HTB_FLAG_DEVICE_OUTPUT is not supported here)"); return 1; }
     if (c.begin()) return 1;
     const double *c1[3] = {x1, y1, nullptr}, *c2[3] = {x2, y2, nullptr};
     if (c.setup(mesh, 1, false, c1, stride1, n1, nullptr, c2, stride2, n2, w2, 1, true, first_cell1, last_cell1, flags)) return 1;
@@ -1307,6 +1406,7 @@ extern "C" int htb_npairs_per_object_3d_engine(const htb_mesh_geom *mesh,
     suffix_min(e, 0, nb);
     if (!binq_ok(e.data(), nb, nullptr, 1, flags & ~HTB_FLAG_GENERIC)) { htb_set_error("htb_npairs_per_object_3d_engine: rbins must be finite"); return 1; }
     Call c;
+    if (flags & HTB_FLAG_DEVICE_OUTPUT) { htb_set_error("per-object tables are returned to host memory (HTB_FLAG_DEVICE_OUTPUT is not supported here)"); return 1; }
     if (c.begin()) return 1;
     const double *c1[3] = {x1, y1, z1}, *c2[3] = {x2, y2, z2};
     if (c.setup(mesh, 1, false, c1, stride1, n1, nullptr, c2, stride2, n2, nullptr, 0, true, first_cell1, last_cell1, flags)) return 1;
@@ -1336,6 +1436,14 @@ extern "C" int htb_npairs_per_object_3d_engine(const htb_mesh_geom *mesh,
 // cover 1: every pair within the search length is visited once, with the image the reference uses).  In pass B the
 // periodic shift is applied to the STAGED sample1 coordinate (BinQ MODE 6): x1 + shift_B = x1 - shift_A exactly, so both
 // passes evaluate the reference's own (x1 - shift) - x2 and every pair lands in the same bin in A and in B.
+// host twin of k_prefix2d (the jackknife tables are combined on the host)
+template <class T>
+static void prefix2d(const T *diff, int n0, int n1, T *out)
+{
+    for (int k = 0; k < n0; ++k) { T run = 0; for (int g = 0; g < n1; ++g) { run += diff[(size_t)k * n1 + g]; out[(size_t)k * n1 + g] = run; } }
+    for (int g = 0; g < n1; ++g) { T run = 0; for (int k = 0; k < n0; ++k) { run += out[(size_t)k * n1 + g]; out[(size_t)k * n1 + g] = run; } }
+}
+
 static int jackknife_pass(const htb_mesh_geom *mesh, int kind, bool swapped,
                           const double *const *ca, int64_t sa, int64_t na, const double *pa,
                           const double *const *cb, int64_t sb, int64_t nb_, const double *pb,
@@ -1376,7 +1484,7 @@ static int run_jackknife(const htb_mesh_geom *mesh, int kind,
                          const double *e0in, int n0, const double *e1in, int n1e,
                          int64_t first_cell1, int64_t last_cell1, double *counts_out, uint32_t flags, htb_stats *stats)
 {
-    if (flags & HTB_FLAG_DEVICE_INPUT) { htb_set_error("jackknife engines take host arrays"); return 1; }
+    if (flags & (HTB_FLAG_DEVICE_INPUT | HTB_FLAG_DEVICE_OUTPUT)) { htb_set_error("jackknife engines take and return host arrays"); return 1; }
     if (nsamples < 1 || nsamples > 100000) { htb_set_error("N_samples must be in [1, 100000]"); return 1; }
     std::vector<double> e((size_t)n0 + n1e);
     for (int k = 0; k < n0; ++k) e[k] = e0in[k] * e0in[k];
@@ -1517,7 +1625,7 @@ extern "C" int htb_mean_delta_sigma_engine(const htb_mesh_geom *mesh,
     if (!mesh || !rp_bins || !out || nrp < 2 || !m2) { htb_set_error("htb_mean_delta_sigma_engine: bad arguments"); return 1; }
     if (mesh->ndim != 2) { htb_set_error("htb_mean_delta_sigma_engine needs a 2-d mesh"); return 1; }
     Call c;
-    if (c.begin()) return 1;
+    if (c.begin(flags)) return 1;
     const double *c1[3] = {x1, y1, nullptr}, *c2[3] = {x2, y2, nullptr};
     // HTB_FLAG_UNIFORM_MASS: every particle has the mass m2[0] (the reference's scalar
     // ``effective_particle_masses``): the mass array is neither uploaded nor sorted.
@@ -1609,12 +1717,130 @@ extern "C" int htb_mean_delta_sigma_engine(const htb_mesh_geom *mesh,
         k_colsum_final<<<1, 256, 0, c.st>>>(partial, nblocks, nbin, sums);
         c.launches += 2;
         HTB_CUDA(cudaGetLastError());
-        HTB_CUDA(cudaMemcpyAsync(out, sums, sizeof(double) * (size_t)nbin, cudaMemcpyDeviceToHost, c.st));
+        if (c.mark_count_end()) return 1;
+        if (c.deliver(out, sums, (size_t)nbin)) return 1;
     } else if (n1 > 0) {
         if (c.mark_count_end()) return 1;
-        if (download(c.st, out_dev, out, n1 * (int64_t)nbin, flags)) return 1;
+        if (c.async) { if (c.deliver(out, out_dev, (size_t)n1 * nbin)) return 1; }
+        else if (download(c.st, out_dev, out, n1 * (int64_t)nbin, flags)) return 1;
     }
     return c.finish(stats, ring ? 2 : (fast ? 1 : 0));
+    HTB_GUARD_END
+}
+
+// ------------------------------------------------------------------ K3: two-point estimators on device-resident counts
+// tpcf_estimators.py:14-119 (_TP_estimator, _TP_estimator_crossx), the np.diff of tpcf.py:76-113 / rp_pi_tpcf.py:296-330
+// and wp's 2 * xi * pi_max (wp.py:219-221), evaluated by one block over the (tiny) cumulative count tables the
+// engines left on the device - after the ranks' tables were summed by an all-reduce on the same stream.  Every
+// expression is written as numpy evaluates the reference's (one rounding per operation, -fmad=false), so the result
+// is the host formula's bit for bit.
+struct TpOperand {
+    const long long *cum;      // cumulative int64 counts [n0 * n1], or null
+    const double *diff;        // differential float counts (analytic randoms) [nout], used when cum is null
+};
+__device__ __forceinline__ long long tp_diff(const long long *c, int k, int g, int n1)
+{
+    if (n1 == 1) return c[k + 1] - c[k];
+    return (c[(k + 1) * n1 + g + 1] - c[k * n1 + g + 1]) - (c[(k + 1) * n1 + g] - c[k * n1 + g]);
+}
+__global__ void k_tp_estimator(int n0, int n1, int estimator, int cross, TpOperand DD, TpOperand D1R, TpOperand D2R, TpOperand RR,
+                               double inv_f1, double inv_f2, double wp_pi_max, double *__restrict__ xi, int *__restrict__ flag)
+{
+    const int ng = n1 > 1 ? n1 - 1 : 1;
+    const int nout = (n0 - 1) * ng;
+    for (int i = threadIdx.x; i < nout; i += blockDim.x) {
+        const int k = i / ng, g = i % ng;
+        // operands as numpy sees them: int64 arrays become float64 in a true division; int64 * int64 stays int64 (wraps)
+        long long idd = 0, id1 = 0, id2 = 0, irr = 0;
+        double dd = 0.0, d1 = 0.0, d2 = 0.0, rr = 0.0;
+        const bool hdd = DD.cum || DD.diff, hd1 = D1R.cum || D1R.diff, hd2 = D2R.cum || D2R.diff, hrr = RR.cum || RR.diff;
+        if (DD.cum) { idd = tp_diff(DD.cum, k, g, n1); dd = (double)idd; } else if (DD.diff) dd = DD.diff[i];
+        if (D1R.cum) { id1 = tp_diff(D1R.cum, k, g, n1); d1 = (double)id1; } else if (D1R.diff) d1 = D1R.diff[i];
+        if (D2R.cum) { id2 = tp_diff(D2R.cum, k, g, n1); d2 = (double)id2; } else if (D2R.diff) d2 = D2R.diff[i];
+        if (RR.cum) { irr = tp_diff(RR.cum, k, g, n1); rr = (double)irr; } else if (RR.diff) rr = RR.diff[i];
+        (void)hdd;
+        // _test_for_zero_division (tpcf_estimators.py:165-183)
+        if (estimator != 3 && hrr && rr == 0.0) atomicOr(flag, 1);
+        if (estimator == 3 && ((hd1 && d1 == 0.0) || (cross && hd2 && d2 == 0.0))) atomicOr(flag, 2);
+        double v;
+        if (estimator == 0) v = inv_f1 * (dd / rr) - 1.0;                                   // Natural
+        else if (estimator == 1) v = inv_f1 * (dd / d1) - 1.0;                              // Davis-Peebles
+        else if (estimator == 2) v = inv_f1 * (dd / rr) - inv_f2 * (d1 / rr);               // Hewett
+        else if (estimator == 3) {                                                          // Hamilton
+            // (DD * RR) / (DR * DR): products of two int64 arrays are int64 products in numpy
+            const double num = (DD.cum && RR.cum) ? (double)(long long)((unsigned long long)idd * (unsigned long long)irr) : dd * rr;
+            double den;
+            if (cross) den = (D1R.cum && D2R.cum) ? (double)(long long)((unsigned long long)id1 * (unsigned long long)id2) : d1 * d2;
+            else den = D1R.cum ? (double)(long long)((unsigned long long)id1 * (unsigned long long)id1) : d1 * d1;
+            v = num / den - 1.0;
+        } else if (!cross) v = inv_f1 * (dd / rr) - inv_f2 * (2.0 * d1 / rr) + 1.0;        // Landy-Szalay
+        else v = inv_f1 * (dd / rr) - inv_f2 * (d1 / rr) - inv_f2 * (d2 / rr) + 1.0;
+        if (wp_pi_max > 0.0) v = 2.0 * v * wp_pi_max;
+        xi[i] = v;
+    }
+}
+
+extern "C" int htb_tp_estimator(int32_t n0, int32_t n1, int32_t estimator, int32_t cross,
+                                const int64_t *DD_cum, const int64_t *D1R_cum, const int64_t *D2R_cum, const int64_t *RR_cum,
+                                const double *D1R_diff, const double *D2R_diff, const double *RR_diff,
+                                double inv_factor1, double inv_factor2, double wp_pi_max,
+                                double *xi_out, int32_t *flag_out)
+{
+    HTB_GUARD_BEGIN
+    if (n0 < 2 || n1 < 1 || (long long)n0 * n1 > 65536 || estimator < 0 || estimator > 4 || !xi_out || !flag_out) {
+        htb_set_error("htb_tp_estimator: bad arguments");
+        return 1;
+    }
+    if (wp_pi_max > 0.0 && n1 != 2) { htb_set_error("htb_tp_estimator: the wp integration needs exactly two pi edges"); return 1; }
+    if (cross && (estimator == 1 || estimator == 2)) { htb_set_error("this estimator is not supported for cross-correlations"); return 1; }
+    cudaStream_t st;
+    if (get_stream(&st)) return 1;
+    TpOperand a{(const long long *)DD_cum, nullptr}, b{(const long long *)D1R_cum, D1R_diff}, c{(const long long *)D2R_cum, D2R_diff},
+              d{(const long long *)RR_cum, RR_diff};
+    k_tp_estimator<<<1, 256, 0, st>>>(n0, n1, estimator, cross, a, b, c, d, inv_factor1, inv_factor2, wp_pi_max, xi_out, flag_out);
+    HTB_CUDA(cudaGetLastError());
+    return 0;
+    HTB_GUARD_END
+}
+
+// the stream this thread's engine calls are issued on (cudaStream_t as void *), and a host wait for it: the one
+// synchronisation of a statistic built from asynchronous (HTB_FLAG_DEVICE_OUTPUT) engine calls
+extern "C" int htb_get_stream(void **stream_out)
+{
+    HTB_GUARD_BEGIN
+    cudaStream_t st;
+    if (!stream_out) { htb_set_error("htb_get_stream: null argument"); return 1; }
+    if (get_stream(&st)) return 1;
+    *stream_out = (void *)st;
+    return 0;
+    HTB_GUARD_END
+}
+// elapsed times (ms) of the counting kernels of this thread's asynchronous calls since the previous query, oldest
+// first (at most HTB_ASYNC_RING are kept); the caller must have synchronised the stream
+extern "C" int htb_async_count_times(float *ms_out, int32_t max_out, int32_t *n_out)
+{
+    HTB_GUARD_BEGIN
+    if (!ms_out || !n_out || max_out < 0) { htb_set_error("htb_async_count_times: bad arguments"); return 1; }
+    const int have = g_async_n < HTB_ASYNC_RING ? g_async_n : HTB_ASYNC_RING;
+    const int n = have < max_out ? have : max_out;
+    for (int k = 0; k < n; ++k) {
+        cudaEvent_t *pair = g_async_ev[(g_async_n - n + k) % HTB_ASYNC_RING];
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, pair[0], pair[1]) != cudaSuccess) { cudaGetLastError(); ms = -1.f; }
+        ms_out[k] = ms;
+    }
+    *n_out = n;
+    g_async_n = 0;
+    return 0;
+    HTB_GUARD_END
+}
+extern "C" int htb_stream_synchronize(void)
+{
+    HTB_GUARD_BEGIN
+    cudaStream_t st;
+    if (get_stream(&st)) return 1;
+    HTB_CUDA(cudaStreamSynchronize(st));
+    return 0;
     HTB_GUARD_END
 }
 

@@ -206,7 +206,7 @@ __device__ __forceinline__ void sts_u32_nc(uint32_t addr, uint32_t v)
 template <int PPL_, int KIND = 0>      // KIND 0: npairs_3d;  1: npairs_xy_z with one or two pi edges
 struct Fast3T {
     static constexpr int DIM = 3, NPAY = 0, PPL = PPL_, WARPS = FAST3_WARPS, MINBLOCKS = FAST3_MINBLOCKS;
-    static constexpr bool TMA = true;
+    static constexpr bool TMA = true, HAS_SELF = true;
     static constexpr int GJ = QGROUP / PPL;     // sample2 points per group
     static constexpr int TOP = HTB_NBF - 1;
     static constexpr int QC = KIND == 1 ? QCAP - 16 : QCAP;       // (rp, pi): 16 rows go to the lower-pi-edge counters
@@ -224,6 +224,7 @@ struct Fast3T {
     double sentinel;
     unsigned c[HTB_NBF];
     unsigned ctop, csave;
+    unsigned zself, zsave;      // exact-zero separations met in the tile's own index range (self pairs, duplicates)
     unsigned umin;
     int hmin;
     int hzmin;                  // (rp, pi): smallest dz^2 high word since the last check
@@ -242,7 +243,7 @@ struct Fast3T {
     {
         qbase = smem_u32(scratch) + 4u * (uint32_t)ln;
         qs = qptr = qsave = qbase;
-        tot = 0; ctop = csave = 0; umin = 0xffffffffu; hmin = 0x7fffffff; hzmin = 0x7fffffff; wt_now = 1; tot0 = 0;
+        tot = 0; ctop = csave = 0; zself = zsave = 0; umin = 0xffffffffu; hmin = 0x7fffffff; hzmin = 0x7fffffff; wt_now = 1; tot0 = 0;
         c0base = qbase + 128u * QC;
         if (KIND == 1) { for (int k = 0; k < HTB_NBF; ++k) sts_u32(c0base + 128u * k, 0u); }
         exact = dirty = false;
@@ -411,13 +412,63 @@ struct Fast3T {
             if (__any_sync(HTB_FULL, undecided)) {
                 // some pair of this group cannot be decided from its 32-bit key (or may lie inside the lower pi
                 // edge): take the whole group back
-                qptr = qsave; ctop = csave;
+                qptr = qsave; ctop = csave; zself = zsave;
                 exact_range(stage, j0, j1);
                 umin = 0xffffffffu; hmin = 0x7fffffff; hzmin = 0x7fffffff;
             }
             if (__any_sync(HTB_FULL, qptr > qbase + QFULL)) flush1(false);
         }
-        qsave = qptr; csave = ctop;
+        qsave = qptr; csave = ctop; zsave = zself;
+    }
+    // The tile's OWN index range (symmetric mode): the only chunk that holds the self pairs, whose separation is an exact
+    // zero - below the window of the 32-bit relative keys, so it used to send every group of this chunk (each holds the
+    // self pairs of eight lanes) to the exact path: 10-20 % of the instructions of a low-density count (configs 3, 4).
+    // An exact zero needs no key: 0 <= every squared edge (the fast path requires bins >= 0), and for (rp, pi) dz^2 = 0
+    // lies inside both pi edges.  Such pairs are counted in `zself` (added to every bin at the end of the tile) and
+    // hidden from the trackers; everything else - including tiny non-zero separations - goes the usual way.
+    __device__ __forceinline__ void pair_self(int q, double xj, double yj, double zj)
+    {
+        const double dx = xs[q] - xj, dy = ys[q] - yj, dz = zs[q] - zj;
+        int key, h;
+        bool zero;
+        if (KIND == 0) {
+            const double dsq = dx * dx + dy * dy + dz * dz;
+            h = __double2hiint(dsq);
+            zero = (h | __double2loint(dsq)) == 0;
+            key = (int)(__funnelshift_l((unsigned)__double2loint(dsq), (unsigned)h, 6) + (unsigned)P.nbias);
+        } else {
+            const double dxy_sq = dx * dx + dy * dy;
+            const double dz_sq = dz * dz;
+            h = __double2hiint(dxy_sq);
+            const int hz = __double2hiint(dz_sq);
+            zero = (h | __double2loint(dxy_sq) | hz | __double2loint(dz_sq)) == 0;
+            hzmin = min(hzmin, zero ? 0x7fffffff : hz);
+            const int k = (int)(__funnelshift_l((unsigned)__double2loint(dxy_sq), (unsigned)h, 6) + (unsigned)P.nbias);
+            key = (dz_sq <= P.pi_top_sq) ? k : 0x7fffffff;
+        }
+        key = zero ? 0x7fffffff : key;
+        zself += zero ? 1u : 0u;
+        umin = min(umin, (unsigned)key);
+        hmin = min(hmin, zero ? 0x7fffffff : h);
+        push(key);
+    }
+    __device__ __forceinline__ void chunk_self(uint32_t stage, int lo, int hi, uint32_t tok)
+    {
+        if (exact) { exact_range(stage, lo, hi); return; }
+        const uint32_t bx = stage, by = stage + 8 * HTB_CH, bz = stage + 16 * HTB_CH;
+        (void)tok;
+        int j = lo;
+#pragma unroll 1
+        while (j < hi) {
+            const int j0 = j, je = min(hi, j + GJ);
+#pragma unroll 1
+            for (; j < je; ++j) {
+                const double xj = lds_f64(bx + 8 * j), yj = lds_f64(by + 8 * j), zj = lds_f64(bz + 8 * j);
+#pragma unroll
+                for (int q = 0; q < PPL; ++q) pair_self(q, xj, yj, zj);
+            }
+            check(stage, j0, je);
+        }
     }
     __device__ __forceinline__ void chunk(uint32_t stage, int lo, int hi, uint32_t tok)
     {
@@ -477,8 +528,14 @@ struct Fast3T {
                 for (int s = 0; s < HTB_NBF; ++s) c[s] = 0;
                 if (KIND == 1) { for (int k = 0; k < HTB_NBF; ++k) sts_u32(c0base + 128u * k, 0u); }
                 dirty = false; exact = true;
+                zself = zsave = 0;
                 return true;
             }
+            // exact zeros of the own-range chunk: inside every edge (and inside the lower pi edge)
+#pragma unroll
+            for (int s = 0; s < HTB_NBF; ++s) c[s] += zself;
+            if (KIND == 1 && zself) { for (int k = 0; k < HTB_NBF; ++k) sts_u32(c0base + 128u * k, lds_u32(c0base + 128u * k) + zself); }
+            zself = zsave = 0;
         }
 #pragma unroll
         for (int s = 0; s < HTB_NBF; ++s) {
@@ -897,61 +954,73 @@ struct DSigmaU {
 
 // ------------------------------------------------------------------ MarkedQ (marked_npairs_3d, weight = w1 * w2)
 // marked_npairs_3d_engine.pyx:204-216 with marking function 1 (mweights, marking_functions.pyx:14-24; id 0, the
-// custom hook, is the same product).  The distance arithmetic and the 32-bit relative keys are those of Fast3.
-// Per lane and point: the weights w2_j of all pairs certainly inside the top edge are summed in a register
-// (one predicated DADD per pair); a pair that may lie inside the second edge pushes {key, w2_j} to the point's
-// queue.  The queues are drained by the compaction cascade; a key that drops out at level S adds its weight to
-// the DIFFERENTIAL sum of level S (each weight is added once), the host forms the cumulative sums.  Ambiguous
-// keys: group roll-back / exact tile redo as in Fast3.
-#ifndef MQ_QD
-#define MQ_QD 13              // queue rows (16 bytes per lane) per point
+// custom hook, is the same product).  The distance arithmetic, the 32-bit relative keys, the trackers and the
+// compaction cascade are those of Fast3; what differs is that every pair carries a weight:
+//   * the weights w2_j of all pairs certainly inside the top edge are summed per point in a register - one predicated
+//     DADD per pair, the reference's `counts[k] += weight` for the top bin;
+//   * a pair that may lie inside the second edge pushes an 8-byte entry {key, sorted index of j | point slot << 31}
+//     (one STS.64; round 1 queued {key, w2_j} as 16 bytes, which cost five instructions per push, 168 registers
+//     and half of the queue depth).  The weight is fetched when the entry DROPS OUT of the cascade (once per entry,
+//     12 % of the pairs, at full lane occupancy) from the sorted weight array, which the TMA stage has just pulled
+//     through L2;
+//   * a key that drops out at level S adds w1_i * w2_j to the DIFFERENTIAL sum of level S; the finishing kernel forms
+//     the cumulative sums.  Ambiguous keys: group roll-back / exact tile redo as in Fast3; exact zeros of the tile's own
+//     index range (self pairs) are summed directly (level 0) as in Fast3's chunk_self.
+#ifndef MQ_QCAP
+#define MQ_QCAP 48            // queue entries (8 bytes) per lane
 #endif
 #ifndef MQ_QSURV
-#define MQ_QSURV 4
+#define MQ_QSURV 14           // run the deep cascade when a lane holds more survivors than this
 #endif
-#define MQ_GROUP 8            // pairs per lane between two queue checks (4 per point)
+#ifndef MQ_WARPS
+#define MQ_WARPS 4
+#define MQ_MINBLOCKS 3
+#endif
+#define MQ_GROUP 16           // pairs per lane between two queue checks
 
-__device__ __forceinline__ void sts_kw(uint32_t addr, int key, double w)
+__device__ __forceinline__ void sts_kj(uint32_t addr, int key, uint32_t j)
 {
-    asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(addr), "l"((long long)key), "d"(w));
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(key), "r"(j));
 }
-__device__ __forceinline__ void lds_kw(uint32_t addr, int &key, double &w)
+__device__ __forceinline__ void lds_kj(uint32_t addr, int &key, uint32_t &j)
 {
-    long long k;
-    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(k), "=d"(w) : "r"(addr));
-    key = (int)k;
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(key), "=r"(j) : "r"(addr));
+}
+// if (key < 0) W += w: one ISETP + one predicated DADD (left to the compiler: DADD + two FSEL)
+__device__ __forceinline__ void add_if_neg(double &W, int key, double w)
+{
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %1, 0;\n\t@p add.rn.f64 %0, %0, %2;\n\t}" : "+d"(W) : "r"(key), "d"(w));
 }
 
 struct MarkedQ {
-    static constexpr int DIM = 3, NPAY = 1, PPL = 2, WARPS = 4, MINBLOCKS = 3;
-    static constexpr bool TMA = true;
+    static constexpr int DIM = 3, NPAY = 1, PPL = 2, WARPS = MQ_WARPS, MINBLOCKS = MQ_MINBLOCKS;
+    static constexpr bool TMA = true, HAS_SELF = true;
     static constexpr int GJ = MQ_GROUP / PPL;
     static constexpr int TOP = HTB_NBF - 1;
-    static constexpr uint32_t QBYTES = 512u * MQ_QD;                       // one point's queue
-    static constexpr uint32_t QFULL = 512u * (MQ_QD - GJ - 1);
+    static constexpr uint32_t QFULL = 256u * (MQ_QCAP - MQ_GROUP - PPL);
     typedef Fast3Params Params;
     const Params &P;
     int lane;
-    uint32_t qbase;             // queue of point 0; point 1 follows at + QBYTES
-    uint32_t qs0, qp0, qv0, qs1, qp1, qv1;   // per point: survivor end, push pointer, roll-back point
+    const double *w2g;          // sorted weights of sample2 (global memory)
+    uint32_t qbase, qs, qptr, qsave;
     double xs[PPL], ys[PPL], zs[PPL], x[PPL], y[PPL], z[PPL], w1[PPL];
     double Wtop[PPL], Wsave[PPL];   // sum of w2 over the pairs certainly inside the top edge
-    double accD[HTB_NBF];           // differential weighted sums per level (this tile)
-    double Xall;                    // all weights added by the exact path (they are not in Wtop)
+    double accD[HTB_NBF];           // differential weighted sums per level (this tile), w1 already applied
+    double Xall;                    // all weights added outside Wtop (exact path, exact zeros of the own range)
     unsigned umin;
     int hmin;
     bool exact, dirty, always_exact;
     double tot;
 
-    static size_t scratch_bytes(const Params &) { return 2 * 512 * MQ_QD; }
+    static size_t scratch_bytes(const Params &) { return 8 * 32 * MQ_QCAP; }
     __device__ __forceinline__ void tile_weight(unsigned) {}
     __device__ __forceinline__ void force_exact() { exact = true; }
 
     __device__ __forceinline__ MarkedQ(const Params &p, void *scratch, int ln, const WalkArrays &A) : P(p), lane(ln)
     {
-        qbase = smem_u32(scratch) + 16u * (uint32_t)ln;
-        qs0 = qp0 = qv0 = qbase;
-        qs1 = qp1 = qv1 = qbase + QBYTES;
+        w2g = A.pay2;
+        qbase = smem_u32(scratch) + 8u * (uint32_t)ln;
+        qs = qptr = qsave = qbase;
         tot = 0.0; Xall = 0.0; umin = 0xffffffffu; hmin = 0x7fffffff;
         exact = dirty = false;
         always_exact = ((A.flags1[0] | A.flags2[0]) & 1u) != 0u;
@@ -976,58 +1045,78 @@ struct MarkedQ {
 #pragma unroll
         for (int q = 0; q < PPL; ++q) { xs[q] = x[q] - sh[0]; ys[q] = y[q] - sh[1]; zs[q] = z[q] - sh[2]; }
     }
-    // compaction pass over one point's queue [r, end): keys <= Fk are kept (moved down to w); the weights of the
-    // others are summed (they drop out at this level); a key equal to Fin (the edge that admitted it) = dirty
+    // w1 of the entry's point times w2 of its sample2 point
+    __device__ __forceinline__ double weight_of(uint32_t j) const
+    {
+        const double wj = __ldg(w2g + (j & 0x7fffffffu));
+        return ((j >> 31) ? w1[1] : w1[0]) * wj;
+    }
+    // Compaction pass over this lane's entries in [r, end): keys <= Fk are kept (moved down to w), the weights of the
+    // others are summed (they drop out at this level); a key equal to Fin (the edge that admitted it) = dirty.
+    // Four independent entries per trip hide the shared- and global-memory latencies.
     __device__ __forceinline__ uint32_t compact(uint32_t r, uint32_t end, uint32_t w, int Fk, int Fin, double &dropped)
     {
         bool eq = false;
-        double s = 0.0;
-        for (; r != end; r += 512u) {
-            int k; double wt;
-            lds_kw(r, k, wt);
-            eq |= (k == Fin);
-            if (k <= Fk) { sts_kw(w, k, wt); w += 512u; }
-            else s += wt;
+        double s0 = 0.0, s1 = 0.0;
+        for (; r + 1024u <= end; r += 1024u) {
+            int k0, k1, k2, k3;
+            uint32_t j0, j1, j2, j3;
+            lds_kj(r, k0, j0); lds_kj(r + 256u, k1, j1); lds_kj(r + 512u, k2, j2); lds_kj(r + 768u, k3, j3);
+            eq |= (k0 == Fin) | (k1 == Fin) | (k2 == Fin) | (k3 == Fin);
+            const double a0 = k0 <= Fk ? 0.0 : weight_of(j0), a1 = k1 <= Fk ? 0.0 : weight_of(j1);
+            const double a2 = k2 <= Fk ? 0.0 : weight_of(j2), a3 = k3 <= Fk ? 0.0 : weight_of(j3);
+            if (k0 <= Fk) { sts_kj(w, k0, j0); w += 256u; }
+            if (k1 <= Fk) { sts_kj(w, k1, j1); w += 256u; }
+            if (k2 <= Fk) { sts_kj(w, k2, j2); w += 256u; }
+            if (k3 <= Fk) { sts_kj(w, k3, j3); w += 256u; }
+            s0 += a0 + a1;
+            s1 += a2 + a3;
+        }
+        for (; r != end; r += 256u) {
+            int k0;
+            uint32_t j0;
+            lds_kj(r, k0, j0);
+            eq |= (k0 == Fin);
+            if (k0 <= Fk) { sts_kj(w, k0, j0); w += 256u; }
+            else s0 += weight_of(j0);
         }
         dirty |= eq;
-        dropped = s;
+        dropped = s0 + s1;
         return w;
     }
     template <int S>
-    __device__ __forceinline__ void cascade(uint32_t base, uint32_t end, double wq)
+    __device__ __forceinline__ void cascade(uint32_t end)
     {
-        if (!__any_sync(HTB_FULL, end != base)) return;
+        if (!__any_sync(HTB_FULL, end != qbase)) return;
         if constexpr (S >= 1) {
-            // keys in [base, end) were admitted by F[S]; those above F[S - 1] have level S
+            // keys in [qbase, end) were admitted by F[S]; those above F[S - 1] have level S
             double d;
-            const uint32_t w = compact(base, end, base, P.F[S - 1], P.F[S], d);
-            accD[S] += wq * d;
-            cascade<S - 1>(base, w, wq);
+            const uint32_t w = compact(qbase, end, qbase, P.F[S - 1], P.F[S], d);
+            accD[S] += d;
+            cascade<S - 1>(w);
         } else {
             // level 0: everything left has level 0
             double d;
-            (void)compact(base, end, base, (int)0x80000000, P.F[0], d);
-            accD[0] += wq * d;
+            (void)compact(qbase, end, qbase, (int)0x80000000, P.F[0], d);
+            accD[0] += d;
         }
     }
-    __device__ __forceinline__ void flush_point(uint32_t base, uint32_t &qs, uint32_t &qp, uint32_t &qv, double wq, bool force)
+    __device__ __forceinline__ void deep()
     {
-        // new keys were admitted by F[TOP - 1]: those above F[TOP - 2] have level TOP - 1
+        cascade<TOP - 2>(qs);
+        qs = qptr = qsave = qbase;
+    }
+    // the entries pushed since the last call were admitted by F[TOP - 1]: those above F[TOP - 2] have level TOP - 1;
+    // the survivors stay queued
+    __device__ __forceinline__ void flush1(bool force_deep)
+    {
         double d;
-        const uint32_t w = compact(qs, qp, qs, P.F[TOP - 2], P.F[TOP - 1], d);
-        accD[TOP - 1] += wq * d;
-        qs = qp = qv = w;
-        if (force || __any_sync(HTB_FULL, w > base + 512u * MQ_QSURV)) {
-            cascade<TOP - 2>(base, qs, wq);
-            qs = qp = qv = base;
-        }
+        const uint32_t w = compact(qs, qptr, qs, P.F[TOP - 2], P.F[TOP - 1], d);
+        accD[TOP - 1] += d;
+        qs = qptr = qsave = w;
+        if (force_deep || __any_sync(HTB_FULL, w > qbase + 256u * MQ_QSURV)) deep();
     }
-    __device__ __forceinline__ void flush(bool force)
-    {
-        flush_point(qbase, qs0, qp0, qv0, w1[0], force);
-        flush_point(qbase + QBYTES, qs1, qp1, qv1, w1[1], force);
-    }
-    __device__ __forceinline__ void pair_fast(int q, uint32_t &qp, double xj, double yj, double zj, double wj)
+    __device__ __forceinline__ void pair_fast(int q, uint32_t jtag, double xj, double yj, double zj, double wj)
     {
         const double dx = xs[q] - xj, dy = ys[q] - yj, dz = zs[q] - zj;
         const double dsq = dx * dx + dy * dy + dz * dz;
@@ -1035,8 +1124,8 @@ struct MarkedQ {
         const int key = (int)(__funnelshift_l((unsigned)__double2loint(dsq), (unsigned)hi, 6) + (unsigned)P.nbias);
         umin = min(umin, (unsigned)key);
         hmin = min(hmin, hi);
-        if (key < 0) Wtop[q] += wj;
-        if (key <= P.F[TOP - 1]) { sts_kw(qp, key, wj); qp += 512u; }
+        add_if_neg(Wtop[q], key, wj);
+        if (key <= P.F[TOP - 1]) { sts_kj(qptr, key, jtag); qptr += 256u; }
     }
     __device__ __forceinline__ void pair_exact(int q, double xj, double yj, double zj, double wj)
     {
@@ -1048,7 +1137,7 @@ struct MarkedQ {
             Xall += w;
             bool below = false;                     // already inside a lower edge
 #pragma unroll
-            for (int s = 0; s < HTB_NBF; ++s) {
+            for (int s = 0; s < HTB_NBF - 1; ++s) {
                 const bool in = b <= P.E[s];
                 if (in && !below) accD[s] += w;
                 below = below || in;
@@ -1068,26 +1157,27 @@ struct MarkedQ {
     __device__ __forceinline__ void check(uint32_t stage, int j0, int j1)
     {
         const bool undecided = (umin == 0u) | (hmin < P.Hwin);
-        const bool full = (qp0 > qbase + QFULL) | (qp1 > qbase + QBYTES + QFULL);
+        const bool full = qptr > qbase + QFULL;
         if (__any_sync(HTB_FULL, undecided | full)) {
             if (__any_sync(HTB_FULL, undecided)) {
-                qp0 = qv0; qp1 = qv1; Wtop[0] = Wsave[0]; Wtop[1] = Wsave[1];
+                qptr = qsave; Wtop[0] = Wsave[0]; Wtop[1] = Wsave[1];
                 exact_range(stage, j0, j1);
                 umin = 0xffffffffu; hmin = 0x7fffffff;
             }
-            if (__any_sync(HTB_FULL, (qp0 > qbase + QFULL) | (qp1 > qbase + QBYTES + QFULL))) flush(false);
+            if (__any_sync(HTB_FULL, qptr > qbase + QFULL)) flush1(false);
         }
-        qv0 = qp0; qv1 = qp1; Wsave[0] = Wtop[0]; Wsave[1] = Wtop[1];
+        qsave = qptr; Wsave[0] = Wtop[0]; Wsave[1] = Wtop[1];
     }
     __device__ __forceinline__ void chunk(uint32_t stage, int lo, int hi, uint32_t tok)
     {
         const uint32_t bx = stage, by = stage + 8 * HTB_CH, bz = stage + 16 * HTB_CH, bw = stage + 24 * HTB_CH;
         if (exact) { exact_range(stage, lo, hi); return; }
+        const uint32_t jg = tok - 1u;              // sorted index of staged slot 0 (walk_tile)
         int j = lo;
         if ((j & 1) && j < hi) {
             const double xj = lds_f64(bx + 8 * j), yj = lds_f64(by + 8 * j), zj = lds_f64(bz + 8 * j), wj = lds_f64(bw + 8 * j);
-            pair_fast(0, qp0, xj, yj, zj, wj);
-            pair_fast(1, qp1, xj, yj, zj, wj);
+            pair_fast(0, jg + (uint32_t)j, xj, yj, zj, wj);
+            pair_fast(1, (jg + (uint32_t)j) | 0x80000000u, xj, yj, zj, wj);
             ++j;
         }
         int j0 = lo;
@@ -1106,10 +1196,11 @@ struct MarkedQ {
                     lds_f64x2_tok(by + 8 * (j + u + 2), tok, yc, yd);
                     lds_f64x2_tok(bz + 8 * (j + u + 2), tok, zc, zd);
                     lds_f64x2_tok(bw + 8 * (j + u + 2), tok, wc, wd);
-                    pair_fast(0, qp0, xa, ya, za, wa);
-                    pair_fast(1, qp1, xa, ya, za, wa);
-                    pair_fast(0, qp0, xb, yb, zb, wb);
-                    pair_fast(1, qp1, xb, yb, zb, wb);
+                    const uint32_t ja = jg + (uint32_t)(j + u);
+                    pair_fast(0, ja, xa, ya, za, wa);
+                    pair_fast(1, ja | 0x80000000u, xa, ya, za, wa);
+                    pair_fast(0, ja + 1u, xb, yb, zb, wb);
+                    pair_fast(1, (ja + 1u) | 0x80000000u, xb, yb, zb, wb);
                     xa = xc; xb = xd; ya = yc; yb = yd; za = zc; zb = zd; wa = wc; wb = wd;
                 }
                 check(stage, j0, j + GJ);
@@ -1120,16 +1211,56 @@ struct MarkedQ {
 #pragma unroll 1
             for (; j < hi; ++j) {
                 const double xj = lds_f64(bx + 8 * j), yj = lds_f64(by + 8 * j), zj = lds_f64(bz + 8 * j), wj = lds_f64(bw + 8 * j);
-                pair_fast(0, qp0, xj, yj, zj, wj);
-                pair_fast(1, qp1, xj, yj, zj, wj);
+                pair_fast(0, jg + (uint32_t)j, xj, yj, zj, wj);
+                pair_fast(1, (jg + (uint32_t)j) | 0x80000000u, xj, yj, zj, wj);
             }
             check(stage, j0, hi);
+        }
+    }
+    // the tile's own index range (symmetric mode): exact zeros (self pairs, duplicates) are inside every edge - their
+    // weight goes to level 0 and to the all-pairs sum directly, and they stay hidden from the trackers (Fast3::chunk_self)
+    __device__ __forceinline__ void chunk_self(uint32_t stage, int lo, int hi, uint32_t tok)
+    {
+        const uint32_t bx = stage, by = stage + 8 * HTB_CH, bz = stage + 16 * HTB_CH, bw = stage + 24 * HTB_CH;
+        if (exact) { exact_range(stage, lo, hi); return; }
+        const uint32_t jg = tok - 1u;
+        int j = lo;
+#pragma unroll 1
+        while (j < hi) {
+            const int j0 = j, je = min(hi, j + GJ);
+            double z0 = 0.0, z1 = 0.0;                  // weights of this group's exact zeros, per point
+#pragma unroll 1
+            for (; j < je; ++j) {
+                const double xj = lds_f64(bx + 8 * j), yj = lds_f64(by + 8 * j), zj = lds_f64(bz + 8 * j), wj = lds_f64(bw + 8 * j);
+#pragma unroll
+                for (int q = 0; q < PPL; ++q) {
+                    const double dx = xs[q] - xj, dy = ys[q] - yj, dz = zs[q] - zj;
+                    const double dsq = dx * dx + dy * dy + dz * dz;
+                    const int h = __double2hiint(dsq);
+                    const bool zero = (h | __double2loint(dsq)) == 0;
+                    int key = (int)(__funnelshift_l((unsigned)__double2loint(dsq), (unsigned)h, 6) + (unsigned)P.nbias);
+                    key = zero ? 0x7fffffff : key;
+                    if (q == 0) z0 += zero ? wj : 0.0; else z1 += zero ? wj : 0.0;
+                    umin = min(umin, (unsigned)key);
+                    hmin = min(hmin, zero ? 0x7fffffff : h);
+                    add_if_neg(Wtop[q], key, wj);
+                    if (key <= P.F[TOP - 1]) { sts_kj(qptr, key, (jg + (uint32_t)j) | (q ? 0x80000000u : 0u)); qptr += 256u; }
+                }
+            }
+            const bool undecided = (umin == 0u) | (hmin < P.Hwin);
+            const bool rolled = __any_sync(HTB_FULL, undecided);
+            check(stage, j0, je);                     // a rolled-back group is re-evaluated exactly, zeros included
+            if (!rolled) {
+                const double zw = w1[0] * z0 + w1[1] * z1;
+                accD[0] += zw;
+                Xall += zw;
+            }
         }
     }
     __device__ __forceinline__ bool tile_end(const WalkArrays &, const uint32_t (&)[PPL], int pass, unsigned wt)
     {
         if (!exact) {
-            flush(true);
+            flush1(true);
             if (__any_sync(HTB_FULL, dirty) && pass == 0) {
 #pragma unroll
                 for (int s = 0; s < HTB_NBF; ++s) accD[s] = 0.0;

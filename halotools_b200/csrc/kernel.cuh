@@ -222,12 +222,21 @@ static int launch_count(cudaStream_t st, const WalkGeom &G, const WalkArrays &A,
         htb_set_error("too many bins for the shared-memory accumulators (%zu bytes of shared memory per block needed)", smem);
         return 1;
     }
-    HTB_CUDA(cudaFuncSetAttribute(k_count<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int dev = 0, sms = 0, per_sm = 0;
+    // the function attribute and the occupancy query cost ~10 us each: done once per (variant, device, shared-memory size)
+    struct Cached { size_t smem; int sms, per_sm; };
+    static Cached cache[64] = {};
+    int dev = 0;
     HTB_CUDA(cudaGetDevice(&dev));
-    HTB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    HTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_count<V>, V::WARPS * 32, smem));
-    if (per_sm < 1) per_sm = 1;
+    Cached &cc = cache[dev & 63];
+    if (cc.per_sm == 0 || cc.smem != smem) {
+        int sms = 0, per_sm = 0;
+        HTB_CUDA(cudaFuncSetAttribute(k_count<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HTB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        HTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_count<V>, V::WARPS * 32, smem));
+        if (per_sm < 1) per_sm = 1;
+        cc.smem = smem; cc.sms = sms; cc.per_sm = per_sm;
+    }
+    const int sms = cc.sms, per_sm = cc.per_sm;
     k_count<V><<<sms * per_sm, V::WARPS * 32, smem, st>>>(G, A, P, (int)scratch);
     if (launches) *launches += 1;
     HTB_CUDA(cudaGetLastError());

@@ -166,6 +166,11 @@ struct WarpSmem {
 template <class V, class = void> struct HtbChunk { static constexpr int value = HTB_CH; };
 template <class V> struct HtbChunk<V, decltype((void)V::CH)> { static constexpr int value = V::CH; };
 
+// variants with a cheaper evaluation of the tile's OWN index range in symmetric mode (the chunk that holds the self
+// pairs, whose exact zeros a 32-bit relative key cannot represent): V::HAS_SELF and chunk_self()
+template <class V, class = void> struct HtbHasSelf { static constexpr bool value = false; };
+template <class V> struct HtbHasSelf<V, decltype((void)V::HAS_SELF)> { static constexpr bool value = V::HAS_SELF; };
+
 struct TileInfo {
     int cnt;                // valid points in the tile
     uint32_t start;         // first sorted index
@@ -253,7 +258,8 @@ __device__ __forceinline__ void walk_tile(V &v, const WalkGeom &G, const WalkArr
                 if (ji >= je) { ++si; if (si < nspan) ji = S.span[3 * si] & ~1u; }
             }
             // ---- current chunk
-            const uint32_t jb = S.span[3 * sc], je = S.span[3 * sc + 1], code = S.span[3 * sc + 2];
+            const uint32_t jb = S.span[3 * sc], je = S.span[3 * sc + 1], fullcode = S.span[3 * sc + 2];
+            const uint32_t code = fullcode & 0xffu;      // bit 8: the span is the tile's own index range (symmetric mode)
             const int stg = (int)(gchunk % HTB_NSTAGE);
             if (code != cur_code) {
                 double sh[3] = {0.0, 0.0, 0.0};
@@ -265,12 +271,18 @@ __device__ __forceinline__ void walk_tile(V &v, const WalkGeom &G, const WalkArr
                 v.set_shift(sh, A);
                 cur_code = code;
             }
+            // tok = (sorted index of staged slot 0) + 1, data dependent on the stage's barrier wait
             uint32_t tok = jc;
             if (V::TMA) tok += mbar_wait(S.bar(stg), (gchunk / HTB_NSTAGE) & 1u);
-            else __syncwarp();
+            else { __syncwarp(); tok += 1u; }
             const int lo = (int)(max(jb, jc) - jc);
             const int hi = (int)(min(je, jc + HTB_CH) - jc);
-            v.chunk(S.stage_s(stg), lo, hi, tok);
+            if constexpr (HtbHasSelf<V>::value) {
+                if (fullcode & 0x100u) v.chunk_self(S.stage_s(stg), lo, hi, tok);
+                else v.chunk(S.stage_s(stg), lo, hi, tok);
+            } else {
+                v.chunk(S.stage_s(stg), lo, hi, tok);
+            }
             pairs += (unsigned long long)(hi - lo) * (unsigned)tile_cnt;
             __syncwarp();
             ++gchunk;
@@ -329,6 +341,7 @@ __device__ __forceinline__ void walk_tile(V &v, const WalkGeom &G, const WalkArr
                     has = plo <= phi;
                 }
                 uint32_t jb = 0, je = 0;
+                bool own = false;
                 if (has) {
                     const int64_t cbase = slowlin * G.nf2[F] - (int64_t)k * G.nf2[F];
                     jb = A.off2[cbase + plo];
@@ -342,7 +355,7 @@ __device__ __forceinline__ void walk_tile(V &v, const WalkGeom &G, const WalkArr
                         const uint32_t fullcode = code | ((uint32_t)(kc + 1) << (2 * F));
                         const bool zero = fullcode == (DIM == 3 ? 21u : 5u);
                         if (zero) {
-                            if (wt_pass == 1) { jb = max(jb, ts); je = min(je, te); }
+                            if (wt_pass == 1) { jb = max(jb, ts); je = min(je, te); own = true; }
                             else { jb = max(jb, te); }
                         } else if (wt_pass == 2) {
                             je = jb;
@@ -355,7 +368,7 @@ __device__ __forceinline__ void walk_tile(V &v, const WalkGeom &G, const WalkArr
                     const int pos = nspan + __popc(bal & ((1u << lane) - 1u));
                     S.span[3 * pos] = jb;
                     S.span[3 * pos + 1] = je;
-                    S.span[3 * pos + 2] = code | ((uint32_t)(kc + 1) << (2 * F));
+                    S.span[3 * pos + 2] = code | ((uint32_t)(kc + 1) << (2 * F)) | (own ? 0x100u : 0u);
                 }
                 nspan += __popc(bal);
             }

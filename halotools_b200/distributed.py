@@ -55,6 +55,24 @@ def _rank_world():
     return dist.get_rank(_state["group"]), dist.get_world_size(_state["group"])
 
 
+def device_collective():
+    """True when the ranks' results can be summed where they are: sharding enabled over NCCL (the GPUs are there).  The
+    front-ends then leave their outputs on the device (HTB_FLAG_DEVICE_OUTPUT) and all-reduce the device buffer on the
+    engine's stream - no D2H -> numpy -> H2D hop (the analogue of the reference's sum over its worker pool,
+    pair_counters/npairs_3d.py:145)."""
+    if not _state["enabled"] or _state["local"] > 0:
+        return False
+    import torch.distributed as dist
+    return dist.get_world_size(_state["group"]) > 1 and dist.get_backend(_state["group"]) == "nccl"
+
+
+def allreduce_device(tensor):
+    """Sum a CUDA tensor over the ranks in place, on the current (the engine's) stream."""
+    import torch.distributed as dist
+    dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=_state["group"])
+    return tensor
+
+
 def split_cells(ncells, world, work=None):
     """Contiguous (first, last) mesh1-cell ranges for ``world`` ranks.
 

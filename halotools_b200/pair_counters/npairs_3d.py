@@ -25,6 +25,20 @@ def npairs_3d(sample1, sample2, rbins, period=None, num_threads=1,
     it never changes the result).  If sample1 is sample2 pairs are double counted and
     every point pairs with itself, as in the reference.
     """
+    return _count(sample1, sample2, rbins, period, num_threads, approx_cell1_size, approx_cell2_size, None)
+
+
+def _enqueue(out, sample1, sample2, rbins, period=None, num_threads=1, approx_cell1_size=None, approx_cell2_size=None):
+    """The same count left ON THE DEVICE: ``out`` is an int64 CUDA tensor of len(rbins) entries; the call only enqueues
+    work on the engine's stream (HTB_FLAG_DEVICE_OUTPUT) and returns the objects that must stay alive until the
+    caller synchronises.  Multi-GPU: ``out`` holds this rank's partial counts (the caller all-reduces the table)."""
+    return _count(sample1, sample2, rbins, period, num_threads, approx_cell1_size, approx_cell2_size, out)
+
+
+npairs_3d.enqueue = _enqueue
+
+
+def _count(sample1, sample2, rbins, period, num_threads, approx_cell1_size, approx_cell2_size, out):
     result = _npairs_3d_process_args(sample1, sample2, rbins, period,
                                      num_threads, approx_cell1_size, approx_cell2_size)
     x1in, y1in, z1in, x2in, y2in, z2in = result[0:6]
@@ -46,8 +60,10 @@ def npairs_3d(sample1, sample2, rbins, period=None, num_threads=1,
         c1.ptrs[0], c1.ptrs[1], c1.ptrs[2], ctypes.c_int64(c1.stride), ctypes.c_int64(c1.n),
         c2.ptrs[0], c2.ptrs[1], c2.ptrs[2], ctypes.c_int64(c2.stride), ctypes.c_int64(c2.n),
         _lib._dp(rb), ctypes.c_int32(len(rb)), ctypes.c_int64(first), ctypes.c_int64(last),
-        counts.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), device=c1.device,
-        extra_flags=_lib.cache_flags(c1, c2, PBCs))
+        _lib.out_pointer(out, counts, ctypes.c_int64), device=c1.device,
+        extra_flags=_lib.cache_flags(c1, c2, PBCs), out_device=out is not None)
+    if out is not None:
+        return (c1, c2)
     return np.array(_dist.allreduce_sum(counts))
 
 

@@ -16,6 +16,21 @@ def npairs_xy_z(sample1, sample2, rp_bins, pi_bins, period=None, num_threads=1,
                 approx_cell1_size=None, approx_cell2_size=None):
     """counts[k, g] = number of pairs with projected separation <= rp_bins[k] and line-of-sight
     (z) separation <= pi_bins[g]; int64 (len(rp_bins), len(pi_bins)), cumulative in both axes."""
+    return _count(sample1, sample2, rp_bins, pi_bins, period, num_threads, approx_cell1_size, approx_cell2_size, None)
+
+
+def _enqueue(out, sample1, sample2, rp_bins, pi_bins, period=None, num_threads=1,
+             approx_cell1_size=None, approx_cell2_size=None):
+    """The same count left ON THE DEVICE in ``out`` (int64 CUDA tensor, len(rp_bins) * len(pi_bins) entries): the call only
+    enqueues work on the engine's stream (HTB_FLAG_DEVICE_OUTPUT); returns the objects to keep alive until the caller
+    synchronises.  Multi-GPU: this rank's partial counts."""
+    return _count(sample1, sample2, rp_bins, pi_bins, period, num_threads, approx_cell1_size, approx_cell2_size, out)
+
+
+npairs_xy_z.enqueue = _enqueue
+
+
+def _count(sample1, sample2, rp_bins, pi_bins, period, num_threads, approx_cell1_size, approx_cell2_size, out):
     result = _npairs_xy_z_process_args(sample1, sample2, rp_bins, pi_bins, period,
                                        num_threads, approx_cell1_size, approx_cell2_size)
     x1in, y1in, z1in, x2in, y2in, z2in = result[0:6]
@@ -40,8 +55,10 @@ def npairs_xy_z(sample1, sample2, rp_bins, pi_bins, period=None, num_threads=1,
         c2.ptrs[0], c2.ptrs[1], c2.ptrs[2], ctypes.c_int64(c2.stride), ctypes.c_int64(c2.n),
         _lib._dp(rp), ctypes.c_int32(len(rp)), _lib._dp(pi), ctypes.c_int32(len(pi)),
         ctypes.c_int64(first), ctypes.c_int64(last),
-        counts.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), device=c1.device,
-        extra_flags=_lib.cache_flags(c1, c2, PBCs))
+        _lib.out_pointer(out, counts, ctypes.c_int64), device=c1.device,
+        extra_flags=_lib.cache_flags(c1, c2, PBCs), out_device=out is not None)
+    if out is not None:
+        return (c1, c2)
     return np.array(_dist.allreduce_sum(counts))
 
 

@@ -58,6 +58,19 @@ def mean_delta_sigma(galaxies, particles, effective_particle_masses,
         m2_ptr = _lib._dp(m2)
     g = geom.as_struct()
     rb = np.ascontiguousarray(rp_bins, dtype=np.float64)
+    if not per_object and _dist.device_collective():
+        # multi-GPU: the column sums stay on the device, are all-reduced there on the engine's stream, and cross PCIe once
+        import torch
+        with torch.cuda.stream(_lib.engine_stream()):
+            sums = torch.zeros(nbin, dtype=torch.float64, device="cuda")
+            _lib.run_engine(
+                "htb_mean_delta_sigma_engine", ctypes.byref(g),
+                c1.ptrs[0], c1.ptrs[1], ctypes.c_int64(c1.stride), ctypes.c_int64(c1.n),
+                c2.ptrs[0], c2.ptrs[1], ctypes.c_int64(c2.stride), m2_ptr, ctypes.c_int64(c2.n),
+                _lib._dp(rb), ctypes.c_int32(len(rb)), ctypes.c_int64(first), ctypes.c_int64(last),
+                _lib.out_pointer(sums, delta_sigma, ctypes.c_double), extra_flags=extra, device=c1.device, out_device=True)
+            colsum = _dist.allreduce_device(sums).cpu().numpy()
+        return colsum / float(n1) if n1 > 0 else colsum * np.nan
     _lib.run_engine(
         "htb_mean_delta_sigma_engine", ctypes.byref(g),
         c1.ptrs[0], c1.ptrs[1], ctypes.c_int64(c1.stride), ctypes.c_int64(c1.n),

@@ -12,7 +12,7 @@ from ..pair_counters import npairs_3d
 from ..pair_counters.mesh_helpers import _enforce_maximum_search_length
 from .. import _lib
 from .. import distributed as _dist
-from . import _driver
+from . import _device, _driver
 from .clustering_helpers import (process_optional_input_sample2, tpcf_estimator_dd_dr_rr_requirements,
                                  verify_tpcf_estimator)
 
@@ -43,18 +43,19 @@ def tpcf(sample1, rbins, sample2=None, randoms=None, period=None,
     else:
         NR = NR_precomputed if NR_precomputed is not None else N1
 
+    if _device.available(npairs_3d):
+        # K3 on the device: counts stay in HBM, one all-reduce, estimator kernel, ONE host synchronisation
+        return _tpcf_device(sample1, rbins, sample2, randoms, period, do_auto, do_cross, estimator, num_threads,
+                            approx_cell1_size, approx_cell2_size, approx_cellran_size, RR_precomputed, same,
+                            do_DR, do_RR, N1, N2, NR)
+
+    # host restatement of the same flow (the pair counter was replaced: CPU tests of the driver logic)
     def count(a, b, cell_a, cell_b):
         return partial.add(np.diff(npairs_3d(a, b, rbins, period=period, num_threads=num_threads,
                                              approx_cell1_size=cell_a, approx_cell2_size=cell_b)))
 
     def analytic():
-        # shells of a periodic box populated at the mean density (tpcf.py:121-145)
-        nr = len(sample1)
-        dv = np.diff((np.pi ** 1.5 / gamma(2.5)) * rbins ** 3)
-        volume = period.prod()
-        D1R = nr * (dv * (np.shape(sample1)[0] / volume))
-        D2R = nr * (dv * (np.shape(sample2)[0] / volume))
-        return D1R, D2R, dv * ((nr ** 2) / volume)
+        return _analytic_randoms(sample1, sample2, rbins, period)
 
     # the engine's upload cache: every sample crosses PCIe once for all the counts of this call; multi-GPU: the
     # ranks' partial counts of ALL these calls are combined by one all-reduce at the end of the block
@@ -69,6 +70,38 @@ def tpcf(sample1, rbins, sample2=None, randoms=None, period=None,
     return _driver.combine(same, do_auto, do_cross, D1D1, D1D2, D2D2, D1R, D2R, RR, N1, N2, NR, estimator)
 
 
+def _analytic_randoms(sample1, sample2, rbins, period):
+    """shells of a periodic box populated at the mean density (tpcf.py:121-145)"""
+    nr = len(sample1)
+    dv = np.diff((np.pi ** 1.5 / gamma(2.5)) * rbins ** 3)
+    volume = period.prod()
+    D1R = nr * (dv * (np.shape(sample1)[0] / volume))
+    D2R = nr * (dv * (np.shape(sample2)[0] / volume))
+    return D1R, D2R, dv * ((nr ** 2) / volume)
+
+
+def _tpcf_device(sample1, rbins, sample2, randoms, period, do_auto, do_cross, estimator, num_threads,
+                 approx_cell1_size, approx_cell2_size, approx_cellran_size, RR_precomputed, same,
+                 do_DR, do_RR, N1, N2, NR):
+    stat = _device.DeviceStatistic((len(rbins),))
+
+    def count(a, b, cell_a, cell_b):
+        return stat.count(npairs_3d.enqueue, a, b, rbins, period=period, num_threads=num_threads,
+                          approx_cell1_size=cell_a, approx_cell2_size=cell_b)
+
+    def analytic():
+        return tuple(stat.analytic(v) for v in _analytic_randoms(sample1, sample2, rbins, period))
+
+    with _lib.upload_cache():
+        D1D1, D1D2, D2D2 = _driver.data_counts(count, sample1, sample2, same, do_auto, do_cross,
+                                               approx_cell1_size, approx_cell2_size)
+        D1R, D2R, RR = _driver.random_counts(count, analytic, sample1, sample2, randoms, same, do_RR, do_DR,
+                                             approx_cell1_size, approx_cell2_size, approx_cellran_size)
+        if RR_precomputed is not None:
+            RR = stat.analytic(RR_precomputed)
+        return _device.combine(stat, same, do_auto, do_cross, D1D1, D1D2, D2D2, D1R, D2R, RR, N1, N2, NR, estimator)
+
+
 def _tpcf_process_args(sample1, rbins, sample2, randoms, period,
                        do_auto, do_cross, estimator, num_threads,
                        approx_cell1_size, approx_cell2_size, approx_cellran_size,
@@ -76,7 +109,7 @@ def _tpcf_process_args(sample1, rbins, sample2, randoms, period,
     """Validation in the reference's order with the reference's messages (tpcf.py:501-600)."""
     sample1 = enforce_sample_has_correct_shape(sample1)
     sample2, same, do_cross = process_optional_input_sample2(sample1, sample2, do_cross)
-    if randoms is not None:
+    if randoms is not None and not getattr(randoms, "is_cuda", False):
         randoms = np.atleast_1d(randoms)
 
     rbins = get_separation_bins_array(rbins)

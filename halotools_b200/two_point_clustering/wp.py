@@ -2,9 +2,15 @@
 (/root/reference/halotools/mock_observables/two_point_clustering/wp.py:20-240)."""
 import numpy as np
 
+import importlib
+
+from . import _device
 from .rp_pi_tpcf import _rp_pi_tpcf_process_args, rp_pi_tpcf
 
 __all__ = ['wp']
+
+# the MODULE (the package re-exports the function under the same name)
+_rp_pi = importlib.import_module(__package__ + ".rp_pi_tpcf")
 
 
 def wp(sample1, rp_bins, pi_max, sample2=None, randoms=None, period=None,
@@ -20,6 +26,11 @@ def wp(sample1, rp_bins, pi_max, sample2=None, randoms=None, period=None,
         approx_cell1_size, approx_cell2_size, approx_cellran_size, seed)
     if same:
         sample2 = None
+
+    if _device.available(_rp_pi.npairs_xy_z):
+        # the pi integration 2 * xi[:, 0] * pi_max (wp.py:219-221) is applied by the estimator kernel
+        return _rp_pi._rp_pi_tpcf(sample1, rp_bins, pi_bins, sample2, randoms, period, do_auto, do_cross, estimator,
+                                  num_threads, approx_cell1_size, approx_cell2_size, approx_cellran_size, None, pi_max)
 
     result = rp_pi_tpcf(sample1, rp_bins=rp_bins, pi_bins=pi_bins, sample2=sample2, randoms=randoms,
                         period=period, do_auto=do_auto, do_cross=do_cross, estimator=estimator,

@@ -15,11 +15,11 @@
  *     return value -> caller-allocated output array.
  * Pointers are HOST pointers unless HTB_FLAG_DEVICE_INPUT is set, in which case the
  * coordinate / weight arrays are device pointers on the current CUDA device (outputs
- * and bins are always host).  All functions return 0 on success, non-zero on error
+ * and bins are always host, unless HTB_FLAG_DEVICE_OUTPUT is set).  All functions return 0 on success, non-zero on error
  * (htb_last_error() gives the message).  No torch types appear here.
  *
  * Threading: device, stream, shard and upload-cache settings are per calling thread; every engine call is
- * synchronous (it returns when its outputs are in host memory).  Calls from several threads are fine on DIFFERENT
+ * synchronous (it returns when its outputs are in host memory) unless HTB_FLAG_DEVICE_OUTPUT is set.  Calls from several threads are fine on DIFFERENT
  * devices; on one device they must be serialised by the caller (the pinned staging ring for pageable inputs and
  * large outputs is shared per device) - the reference's own parallelism (multiprocessing over cell ranges) maps
  * to one process per GPU (htb_set_shard) instead.
@@ -44,6 +44,11 @@ extern "C" {
 #define HTB_FLAG_COLUMN_SUM   64u  /* mean_delta_sigma: delta_sigma_out is f64[nrp-1], the sums of the per-object rows over this call's galaxies (per_object=False needs nothing else) */
 #define HTB_FLAG_CACHE_SAMPLE1 128u /* sample1's host coordinate arrays take part in the upload cache (htb_cache_begin) */
 #define HTB_FLAG_CACHE_SAMPLE2 256u /* ... sample2's */
+#define HTB_FLAG_DEVICE_OUTPUT 1024u /* the output array is a DEVICE pointer on the current device and the call is ASYNCHRONOUS: everything is
+                                       enqueued on the thread's stream and the function returns without a host synchronisation (stats are not
+                                       filled).  Host input arrays must stay alive and unmodified until the caller synchronises
+                                       (htb_stream_synchronize).  Supported by the counters a statistic chains: npairs_3d, npairs_xy_z,
+                                       npairs_s_mu, marked_npairs_3d, marked_npairs_xy_z, weighted_npairs_xy, mean_delta_sigma.      */
 #define HTB_FLAG_NO_SYM       16u  /* auto-correlations: evaluate (i,j) and (j,i) separately, as the reference does */
 #define HTB_FLAG_PARTITION_SUM 512u /* [first_cell1, last_cell1) is one part of a partition of the mesh1 cells whose results the
                                        caller SUMS (multi-GPU shards): auto-correlations may then keep the symmetric shortcut
@@ -240,6 +245,33 @@ int htb_host_minmax(const double *base, int64_t n, int64_t stride, int32_t cols,
 /* The same extrema for a DEVICE-resident row-major matrix (cols <= 3; `base_dev` is a device pointer): one HBM-bound
  * pass on the GPU, on the library's current stream; results land in host memory.                  */
 int htb_device_minmax(const double *base_dev, int64_t n, int64_t stride, int32_t cols, double *min_out, double *max_out);
+
+/* K3 - the two-point estimators over DEVICE-resident cumulative count tables (tpcf_estimators.py:14-119 _TP_estimator /
+ * _TP_estimator_crossx, including the np.diff calls of tpcf.py:76-113 and rp_pi_tpcf.py:296-330 and wp's 2 * xi * pi_max,
+ * wp.py:219-221): one tiny kernel on the thread's stream, so DD / DR / RR counted with HTB_FLAG_DEVICE_OUTPUT, summed over
+ * the ranks on the device and combined into xi need ONE host synchronisation per statistic.
+ *   n0, n1            edges along the first / second bin axis of every table (n1 = 1: 3-d r bins)
+ *   estimator         0 Natural, 1 Davis-Peebles, 2 Hewett, 3 Hamilton, 4 Landy-Szalay;  cross: _TP_estimator_crossx
+ *   *_cum             DEVICE int64[n0 * n1] cumulative counts as the engines return them, or NULL
+ *   *_diff            DEVICE f64[(n0 - 1) * max(n1 - 1, 1)] differential counts (analytic randoms), read when *_cum is NULL
+ *   inv_factor1/2     1 / (ND1 ND2 / (NR1 NR2)), 1 / (ND1 NR2 / (NR1 NR2)) as the reference forms them (for Davis-Peebles
+ *                     inv_factor1 = 1 / (ND1 ND2 / (ND1 NR2)))
+ *   wp_pi_max         > 0: the output is 2 * xi[:, 0] * pi_max (n1 must be 2)
+ *   xi_out            DEVICE f64[(n0 - 1) * max(n1 - 1, 1)]
+ *   flag_out          DEVICE int32, OR-ed: bit 0 some RR bin is zero, bit 1 some DR bin is zero (_test_for_zero_division,
+ *                     tpcf_estimators.py:165-183; the caller raises the reference's ValueError)                           */
+int htb_tp_estimator(int32_t n0, int32_t n1, int32_t estimator, int32_t cross,
+                     const int64_t *DD_cum, const int64_t *D1R_cum, const int64_t *D2R_cum, const int64_t *RR_cum,
+                     const double *D1R_diff, const double *D2R_diff, const double *RR_diff,
+                     double inv_factor1, double inv_factor2, double wp_pi_max,
+                     double *xi_out, int32_t *flag_out);
+
+/* The CUDA stream (cudaStream_t as void*) this thread's calls are issued on, and a host wait for it. */
+int htb_get_stream(void **stream_out);
+int htb_stream_synchronize(void);
+/* CUDA-event durations (ms) of the counting kernels of this thread's HTB_FLAG_DEVICE_OUTPUT calls since the previous
+ * query, oldest first (a ring of 16); call after htb_stream_synchronize().                                    */
+int htb_async_count_times(float *ms_out, int32_t max_out, int32_t *n_out);
 
 /* Measured FP64 non-FMA issue rate (DADD/DMUL instr-lanes per second) of the current device. */
 int htb_measure_fp64_rate(double *ops_per_second_out, double *sm_clock_mhz_out);

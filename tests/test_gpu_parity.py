@@ -844,3 +844,100 @@ def test_odd_bin_arrays_keep_the_reference_scan_semantics():
     got = hb.npairs_3d(s1, s2, wide, period=L)
     assert _lib.last_stats["path"] == 3
     assert np.array_equal(got, oracle.npairs_3d(s1, s2, wide, period=L, num_threads=4))
+
+
+# ------------------------------------------------------------------ K3 on the device (statistics: one synchronisation per call)
+def _host_statistic(counter_name, module, fn, *args, **kwargs):
+    """the same statistic through its host restatement: the pair counter stripped of its ``enqueue`` entry"""
+    import importlib
+    mod = importlib.import_module("halotools_b200.two_point_clustering." + module)
+    real = getattr(mod, counter_name)
+
+    def plain(*a, **k):
+        return real(*a, **k)
+    setattr(mod, counter_name, plain)
+    try:
+        return getattr(hb, fn)(*args, **kwargs)
+    finally:
+        setattr(mod, counter_name, real)
+
+
+@pytest.mark.parametrize("estimator", ["Natural", "Davis-Peebles", "Hewett", "Hamilton", "Landy-Szalay"])
+@pytest.mark.parametrize("cross", [False, True])
+def test_device_estimator_is_the_numpy_formula_bit_for_bit(estimator, cross):
+    # tpcf_estimators.py:14-119 evaluated by htb_tp_estimator on the device tables vs numpy on the host counts
+    rng = np.random.RandomState(5)
+    s1, s2, ran = rng.uniform(0, 60.0, (3000, 3)), rng.uniform(0, 60.0, (2500, 3)), rng.uniform(0, 60.0, (9000, 3))
+    rbins = np.logspace(-0.3, 1.0, 9)
+    kw = dict(randoms=ran, period=60.0, estimator=estimator)
+    if cross:
+        if estimator in ("Davis-Peebles", "Hewett"):
+            pytest.skip("no cross-correlation form in the reference")
+        kw["sample2"] = s2
+    got = hb.tpcf(s1, rbins, **kw)
+    want = _host_statistic("npairs_3d", "tpcf", "tpcf", s1, rbins, **kw)
+    got = got if isinstance(got, tuple) else (got,)
+    want = want if isinstance(want, tuple) else (want,)
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert g.shape == w.shape and np.array_equal(g, w, equal_nan=True), (g, w)
+
+
+def test_device_statistics_analytic_randoms_wp_and_zero_division():
+    rng = np.random.RandomState(6)
+    s1, s2 = rng.uniform(0, 80.0, (4000, 3)), rng.uniform(0, 80.0, (3000, 3))
+    rp = np.logspace(-0.5, 1.0, 8)
+    # analytic randoms (float differential tables on the device), auto + cross
+    for fn, module, counter, args in (("tpcf", "tpcf", "npairs_3d", (s1, rp)),
+                                      ("rp_pi_tpcf", "rp_pi_tpcf", "npairs_xy_z", (s1, rp, np.linspace(0, 20, 6))),
+                                      ("wp", "rp_pi_tpcf", "npairs_xy_z", (s1, rp, 20.0))):
+        kw = dict(sample2=s2, period=80.0)
+        got = getattr(hb, fn)(*args, **kw)
+        want = _host_statistic(counter, module, fn, *args, **kw)
+        assert len(got) == 3
+        for g, w in zip(got, want):
+            assert g.shape == w.shape and np.array_equal(g, w, equal_nan=True), (fn, g, w)
+    # an empty RR bin raises the reference's ValueError (tpcf_estimators.py:165-183)
+    ran = rng.uniform(0, 80.0, (50, 3))
+    with pytest.raises(ValueError, match="zero RR pairs"):
+        hb.tpcf(s1, np.array([1e-4, 2e-4, 1.0]), randoms=ran, period=80.0, estimator="Landy-Szalay")
+    # device-resident samples: same numbers as host arrays
+    import torch
+    d1, dr = torch.from_numpy(s1).cuda(), torch.from_numpy(rng.uniform(0, 80.0, (20000, 3))).cuda()
+    a = hb.tpcf(d1, rp, randoms=dr, period=80.0, estimator="Landy-Szalay")
+    b = hb.tpcf(s1, rp, randoms=dr.cpu().numpy(), period=80.0, estimator="Landy-Szalay")
+    assert np.array_equal(a, b)
+
+
+def test_asynchronous_engine_calls_leave_counts_on_the_device():
+    # HTB_FLAG_DEVICE_OUTPUT through the front-ends' enqueue entries: every kernel path, no host synchronisation until the read
+    import torch
+    rng = np.random.RandomState(7)
+    s1, s2 = rng.uniform(0, 50.0, (5000, 3)), rng.uniform(0, 50.0, (7000, 3))
+    rb = np.logspace(-1, 1, 10)
+    many = np.logspace(-1, 1, 24)                      # > 16 bins: BinQ
+    pi = np.linspace(0, 12.0, 7)
+    _lib.async_count_times()                           # (empty the event ring)
+    with torch.cuda.stream(_lib.engine_stream()):
+        t1 = torch.zeros(len(rb), dtype=torch.int64, device="cuda")
+        t2 = torch.zeros(len(many), dtype=torch.int64, device="cuda")
+        t3 = torch.zeros(len(rb) * 2, dtype=torch.int64, device="cuda")
+        t4 = torch.zeros(len(rb) * len(pi), dtype=torch.int64, device="cuda")
+        keep = [hb.npairs_3d.enqueue(t1, s1, s2, rb, period=50.0), hb.npairs_3d.enqueue(t2, s1, s1, many, period=50.0),
+                hb.npairs_xy_z.enqueue(t3, s1, s2, rb, [0.0, 9.0], period=50.0),
+                hb.npairs_xy_z.enqueue(t4, s1, s2, rb, pi, period=50.0)]
+        old = _lib.default_flags
+        _lib.default_flags = _lib.FLAG_GENERIC
+        try:
+            t5 = torch.zeros(len(rb), dtype=torch.int64, device="cuda")
+            keep.append(hb.npairs_3d.enqueue(t5, s1, s2, rb, period=50.0))
+        finally:
+            _lib.default_flags = old
+        got = [t.cpu().numpy() for t in (t1, t2, t3, t4, t5)]
+    times = _lib.async_count_times()
+    assert len(times) == 5 and all(t > 0 for t in times)
+    assert np.array_equal(got[0], hb.npairs_3d(s1, s2, rb, period=50.0))
+    assert np.array_equal(got[1], hb.npairs_3d(s1, s1, many, period=50.0))
+    assert np.array_equal(got[2].reshape(len(rb), 2), hb.npairs_xy_z(s1, s2, rb, [0.0, 9.0], period=50.0))
+    assert np.array_equal(got[3].reshape(len(rb), len(pi)), hb.npairs_xy_z(s1, s2, rb, pi, period=50.0))
+    assert np.array_equal(got[4], got[0])
