@@ -34,6 +34,7 @@ EXPORTS = (
     "htb_npairs_jackknife_3d_engine", "htb_npairs_jackknife_xy_z_engine", "htb_weighted_npairs_per_object_xy_engine",
     "htb_mesh_cell_ids", "htb_mesh_cell_id_indices", "htb_cell1_work", "htb_measure_fp64_rate",
     "htb_host_minmax", "htb_device_minmax", "htb_tp_estimator", "htb_get_stream", "htb_stream_synchronize", "htb_async_count_times",
+    "htb_return_xyz_formatted_array", "htb_apply_zspace_distortion",
 )
 
 

@@ -704,6 +704,8 @@ struct Call {
             for (int d = 0; d < dim; ++d) est *= std::min(1.0, 2.6 * g->search[d] / g->period[d]);
             G.maxslices = clampi(est / 2.0e5, 1, 16);
             if (const char *e = getenv("HTB_MAXSLICES")) { const int v = atoi(e); if (v >= 1 && v <= 64) G.maxslices = v; }
+            G.tail_eighths = 4;
+            if (const char *e = getenv("HTB_TAIL_EIGHTHS")) { const int v = atoi(e); if (v >= 0 && v <= 512) G.tail_eighths = v; }
             G.items_per_warp = HTB_ITEMS_PER_WARP;
             if (const char *e = getenv("HTB_ITEMS_PER_WARP")) { const int v = atoi(e); if (v >= 1 && v <= 1024) G.items_per_warp = v; }
         }
@@ -761,17 +763,19 @@ struct Call {
         uint2 *tiles = nullptr;
         uint32_t *ntiles_dev = nullptr;
         if (htb_build_tiles(st, ws, G, s1, first_cell1, last_cell1, range_dev, &tiles, &ntiles_dev, &max_tiles, &launches)) return 1;
-        if (ws.alloc((void **)&ctr, 64)) return 1;
-        HTB_CUDA(cudaMemsetAsync(ctr, 0, 64, st));
+        // three cache lines: the work-item counter every warp bumps, the statistics, the redo-queue counters the idle warps
+        // poll at the end of the launch (on one line the pollers slowed the item fetches of the warps still working)
+        if (ws.alloc((void **)&ctr, 512)) return 1;
+        HTB_CUDA(cudaMemsetAsync(ctr, 0, 512, st));
         for (int d = 0; d < 3; ++d) { A.c1[d] = s1.c[d]; A.c2[d] = s2.c[d]; }
         A.off1 = s1.off; A.off2 = s2.off;
         A.pay1 = s1.w; A.pay2 = s2.w; A.nw = nw;
         A.flags1 = s1.flags; A.flags2 = s2.flags;
         A.tiles = tiles; A.ntiles_dev = ntiles_dev;
         A.tile_counter = ctr;
-        A.tiles_redone = ctr + 1;
-        A.pairs_evaluated = (unsigned long long *)(ctr + 2);
-        A.redo_ctr = ctr + 4;
+        A.tiles_redone = ctr + 32;
+        A.pairs_evaluated = (unsigned long long *)(ctr + 34);
+        A.redo_ctr = ctr + 64;
         A.redo_cap = getenv("HTB_REDO_INPLACE") ? 0u : (1u << 16);
         A.redo_ent = nullptr;
         if (A.redo_cap && ws.alloc((void **)&A.redo_ent, sizeof(uint2) * (size_t)A.redo_cap)) return 1;
@@ -793,7 +797,7 @@ struct Call {
             return 0;
         }
         if (mark_count_end()) return 1;
-        struct { unsigned int h[4]; uint32_t ntiles; uint32_t pad; double wref; } rb = {{0, 0, 0, 0}, 0, 0, 0.0};
+        struct { unsigned int h[4]; uint32_t ntiles; uint32_t pad; double wref; } rb = {{0, 0, 0, 0}, 0, 0, 0.0};   // h[0] tiles redone, h[2..3] pairs evaluated (u64)
         double *wsum = nullptr;
         if (stats) {
             // W_ref of this call's (this rank's) cell range, summed on the device: one 8-byte read-back instead of the
@@ -804,7 +808,7 @@ struct Call {
             launches += 1;
             HTB_CUDA(cudaGetLastError());
             HTB_CUDA(cudaMemcpyAsync(&rb.wref, wsum, sizeof(double), cudaMemcpyDeviceToHost, st));
-            HTB_CUDA(cudaMemcpyAsync(rb.h, ctr, sizeof(rb.h), cudaMemcpyDeviceToHost, st));
+            HTB_CUDA(cudaMemcpyAsync(rb.h, ctr + 32, sizeof(rb.h), cudaMemcpyDeviceToHost, st));
             HTB_CUDA(cudaMemcpyAsync(&rb.ntiles, A.ntiles_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         }
         if (mark(4)) return 1;
@@ -821,7 +825,7 @@ struct Call {
             cudaEventElapsedTime(&stats->ms_total, ev[0], ev[4]);
             stats->kernel_launches = launches;
             stats->tiles = (int32_t)rb.ntiles;
-            stats->tiles_redone = (int32_t)rb.h[1];
+            stats->tiles_redone = (int32_t)rb.h[0];
             for (int d = 0; d < 3; ++d) { stats->refine1[d] = m1[d]; stats->refine2[d] = m2[d]; }
             stats->path = path;
         }
@@ -1688,6 +1692,15 @@ extern "C" int htb_mean_delta_sigma_engine(const htb_mesh_geom *mesh,
         rp.nrp = nrp;
         for (int k = 0; k < HTB_NBF; ++k) rp.Ed[k] = k < nrp ? rsq[k] : INFINITY;
         rp.tiny2 = ldexp(rsq[nrp - 1], -24);
+        {
+            // factors lie in [tiny2, 8 L^2]: K of them move a product that started in [1, 2) by at most K * maxlog binades;
+            // keep that below 900 of the 1022 available (the banked mantissa adds one more)
+            const double maxlog = std::max(fabs(log2(8.0 * lmax * lmax)), fabs(log2(rp.tiny2))) + 1.0;
+            int K = (int)(900.0 / maxlog);
+            K = K < 8 ? 8 : (K > 64 ? 64 : K);
+            rp.renorm = K & ~7;
+            if (const char *e = getenv("HTB_DSR_RENORM")) { const int v = atoi(e); if (v >= 8 && v <= K) rp.renorm = v & ~7; }
+        }
         rp.mass = mass;
         rp.e0 = (const double *)edev; rp.e1 = (const double *)edev + nrp;
         rp.out = out_dev;
@@ -1840,6 +1853,84 @@ extern "C" int htb_stream_synchronize(void)
     cudaStream_t st;
     if (get_stream(&st)) return 1;
     HTB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+    HTB_GUARD_END
+}
+
+// ------------------------------------------------------------------ 8f-4: the input step on the device
+// catalog_analysis_helpers.py:108-265 (return_xyz_formatted_array) and :268-327 (apply_zspace_distortion) for samples that
+// already live in HBM (a mock generated or kept on the device between likelihood evaluations): one elementwise pass that
+// writes the (N, 3) row-major sample the pair counters take, so no coordinate crosses PCIe.  Every expression is
+// evaluated operation by operation as numpy does (np.mod = fmod with the sign fix of npy_divmod; the distortion
+// ((1 + z) * v) / 100 / E(z)), so the device sample is bit-identical to the host function's.
+__device__ __forceinline__ double htb_np_mod(double a, double b)
+{
+    // numpy's float remainder (npy_divmod): the result takes the sign of the divisor
+    double mod = fmod(a, b);
+    if (b == 0.0) return mod;                        // nan, as numpy
+    if (mod != 0.0) { if ((b < 0.0) != (mod < 0.0)) mod += b; }
+    else mod = copysign(0.0, b);
+    return mod;
+}
+__global__ void __launch_bounds__(256) k_xyz_formatted(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z,
+                                                       long long n, double px, double py, double pz,
+                                                       const double *__restrict__ vel, int dist_dim, double one_plus_z, double efunc,
+                                                       double *__restrict__ out)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double p[3] = {htb_np_mod(x[i], px), htb_np_mod(y[i], py), htb_np_mod(z[i], pz)};
+        if (dist_dim >= 0) {
+            const double L = dist_dim == 0 ? px : (dist_dim == 1 ? py : pz);
+            const double d = one_plus_z * vel[i] / 100.0 / efunc;      // spatial_distortion, :139
+            double v = p[dist_dim] + d;
+            if (!isinf(L)) v = htb_np_mod(v, L);                         // enforce_periodicity_of_box, model_helpers.py:164-169
+            p[dist_dim] = v;
+        }
+        out[3 * i] = p[0]; out[3 * i + 1] = p[1]; out[3 * i + 2] = p[2];
+    }
+}
+__global__ void __launch_bounds__(256) k_zspace(const double *__restrict__ pos, const double *__restrict__ vpec, long long n,
+                                                double efunc, double scale_factor, double Lbox, int wrap, double *__restrict__ out)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double err = vpec[i] / 100.0 / efunc / scale_factor;     // pos_err, :322
+        double v = pos[i] + err;
+        if (wrap) v = htb_np_mod(v, Lbox);
+        out[i] = v;
+    }
+}
+
+extern "C" int htb_return_xyz_formatted_array(const double *x, const double *y, const double *z, int64_t n, const double *period3,
+                                              const double *velocity, int32_t distortion_dim, double redshift, double efunc,
+                                              double *pos_out)
+{
+    HTB_GUARD_BEGIN
+    if (!period3 || !pos_out || n < 0 || (n > 0 && (!x || !y || !z)) || distortion_dim > 2 || (distortion_dim >= 0 && !velocity)) {
+        htb_set_error("htb_return_xyz_formatted_array: bad arguments");
+        return 1;
+    }
+    if (n == 0) return 0;
+    cudaStream_t st;
+    if (get_stream(&st)) return 1;
+    const int blocks = (int)std::min<int64_t>(148 * 8, (n + 255) / 256);
+    k_xyz_formatted<<<blocks, 256, 0, st>>>(x, y, z, (long long)n, period3[0], period3[1], period3[2], velocity,
+                                            distortion_dim < 0 ? -1 : distortion_dim, 1.0 + redshift, efunc, pos_out);
+    HTB_CUDA(cudaGetLastError());
+    return 0;
+    HTB_GUARD_END
+}
+
+extern "C" int htb_apply_zspace_distortion(const double *true_pos, const double *peculiar_velocity, int64_t n,
+                                           double redshift, double efunc, double Lbox, int32_t wrap, double *zspace_out)
+{
+    HTB_GUARD_BEGIN
+    if (!zspace_out || n < 0 || (n > 0 && (!true_pos || !peculiar_velocity))) { htb_set_error("htb_apply_zspace_distortion: bad arguments"); return 1; }
+    if (n == 0) return 0;
+    cudaStream_t st;
+    if (get_stream(&st)) return 1;
+    const int blocks = (int)std::min<int64_t>(148 * 8, (n + 255) / 256);
+    k_zspace<<<blocks, 256, 0, st>>>(true_pos, peculiar_velocity, (long long)n, efunc, 1.0 / (1.0 + redshift), Lbox, wrap ? 1 : 0, zspace_out);
+    HTB_CUDA(cudaGetLastError());
     return 0;
     HTB_GUARD_END
 }

@@ -206,7 +206,7 @@ __device__ __forceinline__ void sts_u32_nc(uint32_t addr, uint32_t v)
 template <int PPL_, int KIND = 0>      // KIND 0: npairs_3d;  1: npairs_xy_z with one or two pi edges
 struct Fast3T {
     static constexpr int DIM = 3, NPAY = 0, PPL = PPL_, WARPS = FAST3_WARPS, MINBLOCKS = FAST3_MINBLOCKS;
-    static constexpr bool TMA = true, HAS_SELF = true;
+    static constexpr bool TMA = true;
     static constexpr int GJ = QGROUP / PPL;     // sample2 points per group
     static constexpr int TOP = HTB_NBF - 1;
     static constexpr int QC = KIND == 1 ? QCAP - 16 : QCAP;       // (rp, pi): 16 rows go to the lower-pi-edge counters
@@ -224,7 +224,7 @@ struct Fast3T {
     double sentinel;
     unsigned c[HTB_NBF];
     unsigned ctop, csave;
-    unsigned zself, zsave;      // exact-zero separations met in the tile's own index range (self pairs, duplicates)
+    unsigned zself;             // (rp, pi): exact-zero separations met by the exact path (self pairs, duplicates)
     unsigned umin;
     int hmin;
     int hzmin;                  // (rp, pi): smallest dz^2 high word since the last check
@@ -243,7 +243,7 @@ struct Fast3T {
     {
         qbase = smem_u32(scratch) + 4u * (uint32_t)ln;
         qs = qptr = qsave = qbase;
-        tot = 0; ctop = csave = 0; zself = zsave = 0; umin = 0xffffffffu; hmin = 0x7fffffff; hzmin = 0x7fffffff; wt_now = 1; tot0 = 0;
+        tot = 0; ctop = csave = 0; zself = 0; umin = 0xffffffffu; hmin = 0x7fffffff; hzmin = 0x7fffffff; wt_now = 1; tot0 = 0;
         c0base = qbase + 128u * QC;
         if (KIND == 1) { for (int k = 0; k < HTB_NBF; ++k) sts_u32(c0base + 128u * k, 0u); }
         exact = dirty = false;
@@ -381,6 +381,10 @@ struct Fast3T {
             const double dxy_sq = dx * dx + dy * dy;
             const double dz_sq = dz * dz;
             const unsigned long long b = (unsigned long long)__double_as_longlong(dxy_sq);
+            // an exact zero (a self pair of the tile's own range in symmetric mode, a duplicate) lies inside every rp edge
+            // (the fast path requires bins >= 0) and inside both pi edges: counted once here, added to every counter at the
+            // end of the tile - the per-edge loops below ran with ONE active lane for each of them (5 % of config 3)
+            if ((b | (unsigned long long)__double_as_longlong(dz_sq)) == 0ULL) { zself += 1u; return; }
             if (b <= P.E_top && dz_sq <= P.pi_top_sq) {
 #pragma unroll
                 for (int s = 0; s < HTB_NBF; ++s) c[s] += (b <= P.E[s]) ? 1u : 0u;
@@ -412,63 +416,13 @@ struct Fast3T {
             if (__any_sync(HTB_FULL, undecided)) {
                 // some pair of this group cannot be decided from its 32-bit key (or may lie inside the lower pi
                 // edge): take the whole group back
-                qptr = qsave; ctop = csave; zself = zsave;
+                qptr = qsave; ctop = csave;
                 exact_range(stage, j0, j1);
                 umin = 0xffffffffu; hmin = 0x7fffffff; hzmin = 0x7fffffff;
             }
             if (__any_sync(HTB_FULL, qptr > qbase + QFULL)) flush1(false);
         }
-        qsave = qptr; csave = ctop; zsave = zself;
-    }
-    // The tile's OWN index range (symmetric mode): the only chunk that holds the self pairs, whose separation is an exact
-    // zero - below the window of the 32-bit relative keys, so it used to send every group of this chunk (each holds the
-    // self pairs of eight lanes) to the exact path: 10-20 % of the instructions of a low-density count (configs 3, 4).
-    // An exact zero needs no key: 0 <= every squared edge (the fast path requires bins >= 0), and for (rp, pi) dz^2 = 0
-    // lies inside both pi edges.  Such pairs are counted in `zself` (added to every bin at the end of the tile) and
-    // hidden from the trackers; everything else - including tiny non-zero separations - goes the usual way.
-    __device__ __forceinline__ void pair_self(int q, double xj, double yj, double zj)
-    {
-        const double dx = xs[q] - xj, dy = ys[q] - yj, dz = zs[q] - zj;
-        int key, h;
-        bool zero;
-        if (KIND == 0) {
-            const double dsq = dx * dx + dy * dy + dz * dz;
-            h = __double2hiint(dsq);
-            zero = (h | __double2loint(dsq)) == 0;
-            key = (int)(__funnelshift_l((unsigned)__double2loint(dsq), (unsigned)h, 6) + (unsigned)P.nbias);
-        } else {
-            const double dxy_sq = dx * dx + dy * dy;
-            const double dz_sq = dz * dz;
-            h = __double2hiint(dxy_sq);
-            const int hz = __double2hiint(dz_sq);
-            zero = (h | __double2loint(dxy_sq) | hz | __double2loint(dz_sq)) == 0;
-            hzmin = min(hzmin, zero ? 0x7fffffff : hz);
-            const int k = (int)(__funnelshift_l((unsigned)__double2loint(dxy_sq), (unsigned)h, 6) + (unsigned)P.nbias);
-            key = (dz_sq <= P.pi_top_sq) ? k : 0x7fffffff;
-        }
-        key = zero ? 0x7fffffff : key;
-        zself += zero ? 1u : 0u;
-        umin = min(umin, (unsigned)key);
-        hmin = min(hmin, zero ? 0x7fffffff : h);
-        push(key);
-    }
-    __device__ __forceinline__ void chunk_self(uint32_t stage, int lo, int hi, uint32_t tok)
-    {
-        if (exact) { exact_range(stage, lo, hi); return; }
-        const uint32_t bx = stage, by = stage + 8 * HTB_CH, bz = stage + 16 * HTB_CH;
-        (void)tok;
-        int j = lo;
-#pragma unroll 1
-        while (j < hi) {
-            const int j0 = j, je = min(hi, j + GJ);
-#pragma unroll 1
-            for (; j < je; ++j) {
-                const double xj = lds_f64(bx + 8 * j), yj = lds_f64(by + 8 * j), zj = lds_f64(bz + 8 * j);
-#pragma unroll
-                for (int q = 0; q < PPL; ++q) pair_self(q, xj, yj, zj);
-            }
-            check(stage, j0, je);
-        }
+        qsave = qptr; csave = ctop;
     }
     __device__ __forceinline__ void chunk(uint32_t stage, int lo, int hi, uint32_t tok)
     {
@@ -528,14 +482,16 @@ struct Fast3T {
                 for (int s = 0; s < HTB_NBF; ++s) c[s] = 0;
                 if (KIND == 1) { for (int k = 0; k < HTB_NBF; ++k) sts_u32(c0base + 128u * k, 0u); }
                 dirty = false; exact = true;
-                zself = zsave = 0;
+                zself = 0;
                 return true;
             }
-            // exact zeros of the own-range chunk: inside every edge (and inside the lower pi edge)
+        }
+        if (KIND == 1) {
+            // exact zeros met by the exact path: inside every rp edge and inside the lower pi edge
 #pragma unroll
             for (int s = 0; s < HTB_NBF; ++s) c[s] += zself;
-            if (KIND == 1 && zself) { for (int k = 0; k < HTB_NBF; ++k) sts_u32(c0base + 128u * k, lds_u32(c0base + 128u * k) + zself); }
-            zself = zsave = 0;
+            if (zself) { for (int k = 0; k < HTB_NBF; ++k) sts_u32(c0base + 128u * k, lds_u32(c0base + 128u * k) + zself); }
+            zself = 0;
         }
 #pragma unroll
         for (int s = 0; s < HTB_NBF; ++s) {
@@ -964,8 +920,7 @@ struct DSigmaU {
 //     12 % of the pairs, at full lane occupancy) from the sorted weight array, which the TMA stage has just pulled
 //     through L2;
 //   * a key that drops out at level S adds w1_i * w2_j to the DIFFERENTIAL sum of level S; the finishing kernel forms
-//     the cumulative sums.  Ambiguous keys: group roll-back / exact tile redo as in Fast3; exact zeros of the tile's own
-//     index range (self pairs) are summed directly (level 0) as in Fast3's chunk_self.
+//     the cumulative sums.  Ambiguous keys: group roll-back / exact tile redo as in Fast3.
 #ifndef MQ_QCAP
 #define MQ_QCAP 48            // queue entries (8 bytes) per lane
 #endif
@@ -986,15 +941,17 @@ __device__ __forceinline__ void lds_kj(uint32_t addr, int &key, uint32_t &j)
 {
     asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(key), "=r"(j) : "r"(addr));
 }
-// if (key < 0) W += w: one ISETP + one predicated DADD (left to the compiler: DADD + two FSEL)
+// if (key < 0) W += w, as ONE f64 instruction plus two integer ones: W = fma(w, m, W) with m = 1.0 or 0.0 built from the
+// sign of the key (w * 1.0 is exact, so the result is the correctly rounded W + w; w * 0.0 leaves W alone for finite w).
+// A predicated DADD comes back from ptxas as DADD + two FSEL.
 __device__ __forceinline__ void add_if_neg(double &W, int key, double w)
 {
-    asm("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %1, 0;\n\t@p add.rn.f64 %0, %0, %2;\n\t}" : "+d"(W) : "r"(key), "d"(w));
+    W = __fma_rn(w, __hiloint2double((key >> 31) & 0x3ff00000, 0), W);
 }
 
 struct MarkedQ {
     static constexpr int DIM = 3, NPAY = 1, PPL = 2, WARPS = MQ_WARPS, MINBLOCKS = MQ_MINBLOCKS;
-    static constexpr bool TMA = true, HAS_SELF = true;
+    static constexpr bool TMA = true, WANTS_BASE = true;
     static constexpr int GJ = MQ_GROUP / PPL;
     static constexpr int TOP = HTB_NBF - 1;
     static constexpr uint32_t QFULL = 256u * (MQ_QCAP - MQ_GROUP - PPL);
@@ -1003,6 +960,7 @@ struct MarkedQ {
     int lane;
     const double *w2g;          // sorted weights of sample2 (global memory)
     uint32_t qbase, qs, qptr, qsave;
+    uint32_t jg;                // sorted index of staged slot 0 of the current chunk
     double xs[PPL], ys[PPL], zs[PPL], x[PPL], y[PPL], z[PPL], w1[PPL];
     double Wtop[PPL], Wsave[PPL];   // sum of w2 over the pairs certainly inside the top edge
     double accD[HTB_NBF];           // differential weighted sums per level (this tile), w1 already applied
@@ -1015,10 +973,12 @@ struct MarkedQ {
     static size_t scratch_bytes(const Params &) { return 8 * 32 * MQ_QCAP; }
     __device__ __forceinline__ void tile_weight(unsigned) {}
     __device__ __forceinline__ void force_exact() { exact = true; }
+    __device__ __forceinline__ void chunk_base(uint32_t j0) { jg = j0; }
 
     __device__ __forceinline__ MarkedQ(const Params &p, void *scratch, int ln, const WalkArrays &A) : P(p), lane(ln)
     {
         w2g = A.pay2;
+        jg = 0;
         qbase = smem_u32(scratch) + 8u * (uint32_t)ln;
         qs = qptr = qsave = qbase;
         tot = 0.0; Xall = 0.0; umin = 0xffffffffu; hmin = 0x7fffffff;
@@ -1048,6 +1008,9 @@ struct MarkedQ {
     // w1 of the entry's point times w2 of its sample2 point
     __device__ __forceinline__ double weight_of(uint32_t j) const
     {
+#ifdef MQ_DEBUG
+        if ((j & 0x7fffffffu) > 200000000u) { printf("MQ bad j %08x lane %d qbase %u qs %u qptr %u qsave %u\n", j, lane, qbase, qs, qptr, qsave); return 0.0; }
+#endif
         const double wj = __ldg(w2g + (j & 0x7fffffffu));
         return ((j >> 31) ? w1[1] : w1[0]) * wj;
     }
@@ -1116,6 +1079,30 @@ struct MarkedQ {
         qs = qptr = qsave = w;
         if (force_deep || __any_sync(HTB_FULL, w > qbase + 256u * MQ_QSURV)) deep();
     }
+    __device__ __forceinline__ void key_of(int q, double xj, double yj, double zj, int &key, int &hi)
+    {
+        const double dx = xs[q] - xj, dy = ys[q] - yj, dz = zs[q] - zj;
+        const double dsq = dx * dx + dy * dy + dz * dz;
+        hi = __double2hiint(dsq);
+        key = (int)(__funnelshift_l((unsigned)__double2loint(dsq), (unsigned)hi, 6) + (unsigned)P.nbias);
+    }
+    __device__ __forceinline__ void push(int q, int key, uint32_t jtag, double wj)
+    {
+        add_if_neg(Wtop[q], key, wj);
+        if (key <= P.F[TOP - 1]) { sts_kj(qptr, key, jtag); qptr += 256u; }
+    }
+    // one point of this lane against two staged points (three-input minimum trackers: one VIMNMX3 each per two pairs)
+    __device__ __forceinline__ void pair2(int q, uint32_t tag, uint32_t ja, double xa, double ya, double za, double wa,
+                                          double xb, double yb, double zb, double wb)
+    {
+        int ka, kb, ha, hb;
+        key_of(q, xa, ya, za, ka, ha);
+        key_of(q, xb, yb, zb, kb, hb);
+        umin = min(umin, min((unsigned)ka, (unsigned)kb));
+        hmin = min(hmin, min(ha, hb));
+        push(q, ka, ja | tag, wa);
+        push(q, kb, (ja + 1u) | tag, wb);
+    }
     __device__ __forceinline__ void pair_fast(int q, uint32_t jtag, double xj, double yj, double zj, double wj)
     {
         const double dx = xs[q] - xj, dy = ys[q] - yj, dz = zs[q] - zj;
@@ -1125,6 +1112,9 @@ struct MarkedQ {
         umin = min(umin, (unsigned)key);
         hmin = min(hmin, hi);
         add_if_neg(Wtop[q], key, wj);
+#ifdef MQ_DEBUG
+        if ((jtag & 0x7fffffffu) > 200000000u && key <= P.F[TOP - 1]) printf("MQ push bad jtag %08x lane %d\n", jtag, lane);
+#endif
         if (key <= P.F[TOP - 1]) { sts_kj(qptr, key, jtag); qptr += 256u; }
     }
     __device__ __forceinline__ void pair_exact(int q, double xj, double yj, double zj, double wj)
@@ -1172,7 +1162,6 @@ struct MarkedQ {
     {
         const uint32_t bx = stage, by = stage + 8 * HTB_CH, bz = stage + 16 * HTB_CH, bw = stage + 24 * HTB_CH;
         if (exact) { exact_range(stage, lo, hi); return; }
-        const uint32_t jg = tok - 1u;              // sorted index of staged slot 0 (walk_tile)
         int j = lo;
         if ((j & 1) && j < hi) {
             const double xj = lds_f64(bx + 8 * j), yj = lds_f64(by + 8 * j), zj = lds_f64(bz + 8 * j), wj = lds_f64(bw + 8 * j);
@@ -1197,10 +1186,8 @@ struct MarkedQ {
                     lds_f64x2_tok(bz + 8 * (j + u + 2), tok, zc, zd);
                     lds_f64x2_tok(bw + 8 * (j + u + 2), tok, wc, wd);
                     const uint32_t ja = jg + (uint32_t)(j + u);
-                    pair_fast(0, ja, xa, ya, za, wa);
-                    pair_fast(1, ja | 0x80000000u, xa, ya, za, wa);
-                    pair_fast(0, ja + 1u, xb, yb, zb, wb);
-                    pair_fast(1, (ja + 1u) | 0x80000000u, xb, yb, zb, wb);
+                    pair2(0, 0u, ja, xa, ya, za, wa, xb, yb, zb, wb);
+                    pair2(1, 0x80000000u, ja, xa, ya, za, wa, xb, yb, zb, wb);
                     xa = xc; xb = xd; ya = yc; yb = yd; za = zc; zb = zd; wa = wc; wb = wd;
                 }
                 check(stage, j0, j + GJ);
@@ -1215,46 +1202,6 @@ struct MarkedQ {
                 pair_fast(1, (jg + (uint32_t)j) | 0x80000000u, xj, yj, zj, wj);
             }
             check(stage, j0, hi);
-        }
-    }
-    // the tile's own index range (symmetric mode): exact zeros (self pairs, duplicates) are inside every edge - their
-    // weight goes to level 0 and to the all-pairs sum directly, and they stay hidden from the trackers (Fast3::chunk_self)
-    __device__ __forceinline__ void chunk_self(uint32_t stage, int lo, int hi, uint32_t tok)
-    {
-        const uint32_t bx = stage, by = stage + 8 * HTB_CH, bz = stage + 16 * HTB_CH, bw = stage + 24 * HTB_CH;
-        if (exact) { exact_range(stage, lo, hi); return; }
-        const uint32_t jg = tok - 1u;
-        int j = lo;
-#pragma unroll 1
-        while (j < hi) {
-            const int j0 = j, je = min(hi, j + GJ);
-            double z0 = 0.0, z1 = 0.0;                  // weights of this group's exact zeros, per point
-#pragma unroll 1
-            for (; j < je; ++j) {
-                const double xj = lds_f64(bx + 8 * j), yj = lds_f64(by + 8 * j), zj = lds_f64(bz + 8 * j), wj = lds_f64(bw + 8 * j);
-#pragma unroll
-                for (int q = 0; q < PPL; ++q) {
-                    const double dx = xs[q] - xj, dy = ys[q] - yj, dz = zs[q] - zj;
-                    const double dsq = dx * dx + dy * dy + dz * dz;
-                    const int h = __double2hiint(dsq);
-                    const bool zero = (h | __double2loint(dsq)) == 0;
-                    int key = (int)(__funnelshift_l((unsigned)__double2loint(dsq), (unsigned)h, 6) + (unsigned)P.nbias);
-                    key = zero ? 0x7fffffff : key;
-                    if (q == 0) z0 += zero ? wj : 0.0; else z1 += zero ? wj : 0.0;
-                    umin = min(umin, (unsigned)key);
-                    hmin = min(hmin, zero ? 0x7fffffff : h);
-                    add_if_neg(Wtop[q], key, wj);
-                    if (key <= P.F[TOP - 1]) { sts_kj(qptr, key, (jg + (uint32_t)j) | (q ? 0x80000000u : 0u)); qptr += 256u; }
-                }
-            }
-            const bool undecided = (umin == 0u) | (hmin < P.Hwin);
-            const bool rolled = __any_sync(HTB_FULL, undecided);
-            check(stage, j0, je);                     // a rolled-back group is re-evaluated exactly, zeros included
-            if (!rolled) {
-                const double zw = w1[0] * z0 + w1[1] * z1;
-                accD[0] += zw;
-                Xall += zw;
-            }
         }
     }
     __device__ __forceinline__ bool tile_end(const WalkArrays &, const uint32_t (&)[PPL], int pass, unsigned wt)
@@ -1624,6 +1571,7 @@ struct DSigmaR {
     double Pall, C0, C1, C2;
     int Eall, E0, E1, E2;
     unsigned n0, n1, n2, npart;
+    int since;                  // factors multiplied into the running products since the last renormalisation
 
     static size_t scratch_bytes(const Params &) { return 8 * HTB_SPAN_CAP + 8 * (2 * HTB_NBF + 4); }
     __device__ __forceinline__ uint32_t *span_extra() { return extra; }
@@ -1637,7 +1585,7 @@ struct DSigmaR {
         es = smem_u32(ed);
         for (int k = ln; k < 2 * HTB_NBF + 4; k += 32) ed[k] = k < HTB_NBF ? P.Ed[k] : __longlong_as_double(0x7ff0000000000000LL);
         x = y = xs = ys = 0.0; valid = false; mode = 1; uex = 0; slo = shi = 0; eb0 = eb1 = eb2 = 0;
-        Pall = C0 = C1 = C2 = 1.0; Eall = E0 = E1 = E2 = 0; n0 = n1 = n2 = npart = 0;
+        Pall = C0 = C1 = C2 = 1.0; Eall = E0 = E1 = E2 = 0; n0 = n1 = n2 = npart = 0; since = 0;
         always_exact = ((A.flags1[0] | A.flags2[0]) & 1u) != 0u;
         __syncwarp();
     }
@@ -1687,7 +1635,7 @@ struct DSigmaR {
         eb0 = u >= 1 ? lds_u64(es + 8u * (uint32_t)a) : inf;
         eb1 = u >= 2 ? lds_u64(es + 8u * (uint32_t)(a + 1)) : inf;
         eb2 = u >= 3 ? lds_u64(es + 8u * (uint32_t)(a + 2)) : inf;
-        Pall = C0 = C1 = C2 = 1.0; Eall = E0 = E1 = E2 = 0; n0 = n1 = n2 = 0;
+        Pall = C0 = C1 = C2 = 1.0; Eall = E0 = E1 = E2 = 0; n0 = n1 = n2 = 0; since = 0;
     }
     // if (bits(d) <= edge) { C *= d; n += 1; } as one 64-bit compare, a predicated DMUL and a predicated IADD
     // (left to the compiler this becomes an unconditional DMUL, two selects and two integer instructions)
@@ -1718,8 +1666,11 @@ struct DSigmaR {
     template <int NE>
     __device__ __forceinline__ void chunk_fast(uint32_t bx, uint32_t by, int lo, int hi, uint32_t tok)
     {
+        // The running products are renormalised (exponent pulled out) every P.renorm pairs instead of after every group
+        // of 8: the host chose P.renorm so that that many factors of any separation the kernel can meet (between tiny2
+        // and 8 L^2) keep a product that started in [1, 2) inside the double range with room to spare.
         int j = lo;
-        if ((j & 1) && j < hi) { pair_fast<NE>(lds_f64(bx + 8 * j), lds_f64(by + 8 * j)); ++j; }
+        if ((j & 1) && j < hi) { pair_fast<NE>(lds_f64(bx + 8 * j), lds_f64(by + 8 * j)); ++j; ++since; }
 #pragma unroll 1
         for (; j + 8 <= hi; j += 8) {
             double xa[8], ya[8];
@@ -1730,11 +1681,14 @@ struct DSigmaR {
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) pair_fast<NE>(xa[u], ya[u]);
-            renorm_all<NE>();
+            since += 8;
+            if (since >= P.renorm) { renorm_all<NE>(); since = 0; }
         }
 #pragma unroll 1
-        for (; j < hi; ++j) pair_fast<NE>(lds_f64(bx + 8 * j), lds_f64(by + 8 * j));
-        renorm_all<NE>();
+        for (; j < hi; ++j) {
+            pair_fast<NE>(lds_f64(bx + 8 * j), lds_f64(by + 8 * j));
+            if (++since >= P.renorm) { renorm_all<NE>(); since = 0; }
+        }
     }
     // exact path: the slot of a pair is slo + the number of this lane's edges below d^2; every lane tests the same
     // number of edges (uex, the widest range of the warp - edges beyond a lane's own range cannot be below d^2, and
@@ -1781,6 +1735,8 @@ struct DSigmaR {
     __device__ __forceinline__ void cell_end()
     {
         if (mode == 0) return;
+        // (bank() multiplies a banked mantissa in [1, 2) by the running product and renormalises: the running product
+        // holds fewer than P.renorm factors, which the host's bound covers)
         // cumulative products C_0 <= C_1 <= C_2 <= Pall (as sets of pairs): slot slo + i holds C_i / C_(i-1)
         cnt[slo] += n0;
         bank(Num, eNum, slo, C0, E0);

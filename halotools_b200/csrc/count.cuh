@@ -42,6 +42,7 @@ struct DSRParams {
     int nrp;                         // number of rp edges
     double Ed[HTB_NBF];              // squared edges, ascending; entries >= nrp hold +inf
     double tiny2;                    // a cell that may hold a pair closer than this (squared) takes the exact path
+    int renorm;                      // running products are renormalised after this many factors (a multiple of 8)
     double mass;
     const double *e0, *e1;           // device: squared edges, ln(rp[k+1]/rp[k])
     double *out;                     // (n1, nrp - 1) rows in input order

@@ -44,13 +44,25 @@ k_count(const __grid_constant__ WalkGeom G, const __grid_constant__ WalkArrays A
     // Work items: when there are too few tiles to keep every resident warp busy to the end (small samples, one
     // rank's shard of a multi-GPU count, clustered sample1), every tile is cut into K SLICES of its sample2
     // columns; slices of one tile are independent work items (counts and per-object sums are additive).
-    int K = 1;
-    {
-        const long long target = (long long)gridDim.x * V::WARPS * G.items_per_warp;
-        if (ntiles > 0 && ntiles < target) K = (int)min((long long)(G.sym ? min(G.maxslices, 8) : G.maxslices), (target + ntiles - 1) / ntiles);
-        if (K < 1) K = 1;
+    // Two phases: the first nA tiles are whole work items, the LAST nB tiles (G.tail_eighths / 8 tiles per resident warp)
+    // are cut into Kmax slices each, so that the warps run out of work within a fraction of a tile of each other instead
+    // of up to a whole tile (one tile of the bench's RR count is 2 ms of one warp; a rank of an 8-GPU run has four tiles
+    // per warp).  With fewer than two tiles per resident warp every tile is sliced (KA) as far as it pays.
+    const int Kmax = G.sym ? min(G.maxslices, 8) : G.maxslices;
+    const long long W = (long long)gridDim.x * V::WARPS;
+    int KA = 1, KB = 1, nB = 0;
+    if (ntiles >= 2 * W && Kmax > 1 && G.tail_eighths > 0) {
+        KB = Kmax;
+        nB = (int)min((long long)ntiles, W * G.tail_eighths / 8);
+    } else {
+        const long long target = W * G.items_per_warp;
+        if (ntiles > 0 && ntiles < target) KA = (int)min((long long)Kmax, (target + ntiles - 1) / ntiles);
+        if (KA < 1) KA = 1;
+        KB = KA;
     }
-    const int nitems = ntiles * K;
+    const int nA = ntiles - nB;
+    const int itemsA = nA * KA;
+    const int nitems = itemsA + nB * KB;
 
     // One work item: slice `slice` of `nsl` of tile t.  redo_sub < 0: the normal evaluation (both weight passes in
     // symmetric mode).  A fast kernel that finds it cannot decide a tile from its 32-bit keys asks for an exact
@@ -62,12 +74,13 @@ k_count(const __grid_constant__ WalkGeom G, const __grid_constant__ WalkArrays A
     while (true) {
         // ---- next work item: the ordinary queue first, then the redo queue (entries published by any warp; done
         // when every ordinary item has completed and the queue is drained: reserved == published == taken)
-        int t = 0, slice = 0, nsl = K, redo_sub = -1;
+        int t = 0, slice = 0, nsl = KA, redo_sub = -1;
         if (!main_done) {
             if (lane == 0) t = (int)atomicAdd(A.tile_counter, 1u);
             t = __shfl_sync(HTB_FULL, t, 0);
             if (t >= nitems) main_done = true;
-            else { slice = t % K; t /= K; }
+            else if (t < itemsA) { slice = t % KA; t /= KA; }
+            else { const int u = t - itemsA; slice = u % KB; t = nA + u / KB; nsl = KB; }
         }
         if (main_done) {
             if (A.redo_cap < HTB_REDO_SPLIT) break;
@@ -75,6 +88,7 @@ k_count(const __grid_constant__ WalkGeom G, const __grid_constant__ WalkArrays A
             int quit = 0;
             if (lane == 0) {
                 volatile unsigned *c = A.redo_ctr;
+                unsigned backoff = 500;
                 while (true) {
                     const unsigned done = c[3];               // read first: a finished item has published its entries
                     __threadfence();
@@ -86,7 +100,8 @@ k_count(const __grid_constant__ WalkGeom G, const __grid_constant__ WalkArrays A
                     // nothing to take: finished only if no ordinary item is still running (it could publish more)
                     // and every reservation has been published
                     if (done >= (unsigned)nitems && published == reserved) { quit = 1; break; }
-                    __nanosleep(500);
+                    __nanosleep(backoff);
+                    if (backoff < 8000) backoff *= 2;
                 }
             }
             quit = __shfl_sync(HTB_FULL, quit, 0);
@@ -94,7 +109,7 @@ k_count(const __grid_constant__ WalkGeom G, const __grid_constant__ WalkArrays A
             got = __shfl_sync(HTB_FULL, got, 0);
             __threadfence();
             const uint2 e = A.redo_ent[got];
-            t = (int)e.x; slice = (int)(e.y & 0xffffffu); nsl = K * HTB_REDO_SPLIT; redo_sub = (int)(e.y >> 24);
+            t = (int)e.x; slice = (int)(e.y & 0xffffffu); nsl = (t < nA ? KA : KB) * HTB_REDO_SPLIT; redo_sub = (int)(e.y >> 24);
         }
         const uint2 td = A.tiles[t];
         const uint32_t start = td.x;

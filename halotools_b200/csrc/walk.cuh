@@ -49,6 +49,7 @@ struct WalkGeom {
     int maxfine;                    // fine mesh1 cells along the fast dimension one tile may cover (bounds its extent)
     int maxslices;                  // a tile's sample2 columns may be cut into up to this many independent work items
     int items_per_warp;             // ... until every resident warp has about this many work items
+    int tail_eighths;               // the last (resident warps x this / 8) tiles are cut into maxslices slices (0: off)
 };
 
 struct WalkArrays {
@@ -171,6 +172,10 @@ template <class V> struct HtbChunk<V, decltype((void)V::CH)> { static constexpr 
 template <class V, class = void> struct HtbHasSelf { static constexpr bool value = false; };
 template <class V> struct HtbHasSelf<V, decltype((void)V::HAS_SELF)> { static constexpr bool value = V::HAS_SELF; };
 
+// variants that need the sorted index of staged slot 0 (to name sample2 points in a queue): V::WANTS_BASE and chunk_base()
+template <class V, class = void> struct HtbWantsBase { static constexpr bool value = false; };
+template <class V> struct HtbWantsBase<V, decltype((void)V::WANTS_BASE)> { static constexpr bool value = V::WANTS_BASE; };
+
 struct TileInfo {
     int cnt;                // valid points in the tile
     uint32_t start;         // first sorted index
@@ -271,12 +276,12 @@ __device__ __forceinline__ void walk_tile(V &v, const WalkGeom &G, const WalkArr
                 v.set_shift(sh, A);
                 cur_code = code;
             }
-            // tok = (sorted index of staged slot 0) + 1, data dependent on the stage's barrier wait
             uint32_t tok = jc;
             if (V::TMA) tok += mbar_wait(S.bar(stg), (gchunk / HTB_NSTAGE) & 1u);
-            else { __syncwarp(); tok += 1u; }
+            else __syncwarp();
             const int lo = (int)(max(jb, jc) - jc);
             const int hi = (int)(min(je, jc + HTB_CH) - jc);
+            if constexpr (HtbWantsBase<V>::value) v.chunk_base(jc);
             if constexpr (HtbHasSelf<V>::value) {
                 if (fullcode & 0x100u) v.chunk_self(S.stage_s(stg), lo, hi, tok);
                 else v.chunk(S.stage_s(stg), lo, hi, tok);

@@ -273,6 +273,20 @@ int htb_stream_synchronize(void);
  * query, oldest first (a ring of 16); call after htb_stream_synchronize().                                    */
 int htb_async_count_times(float *ms_out, int32_t max_out, int32_t *n_out);
 
+/* The input step before the path, for samples that live in HBM: return_xyz_formatted_array
+ * (catalog_analysis_helpers.py:108-265) and apply_zspace_distortion (:268-327) as one elementwise kernel each, enqueued on
+ * the thread's stream (asynchronous).  ALL pointers except period3 are DEVICE pointers.
+ *   x, y, z         f64[n];  period3: host f64[3] (inf = no wrap)
+ *   velocity        f64[n] or NULL;  distortion_dim: 0 / 1 / 2 = the coordinate that receives (1 + z) v / 100 / E(z), -1 none
+ *   efunc           E(z) = H(z) / H0 of the caller's cosmology (host scalar)
+ *   pos_out         f64[n * 3] row-major: the (Npts, 3) sample the pair counters take                                   */
+int htb_return_xyz_formatted_array(const double *x, const double *y, const double *z, int64_t n, const double *period3,
+                                   const double *velocity, int32_t distortion_dim, double redshift, double efunc,
+                                   double *pos_out);
+/* zspace = true_pos + v_pec / 100 / E(z) / a, wrapped into [0, Lbox) when wrap != 0; f64[n] device arrays.              */
+int htb_apply_zspace_distortion(const double *true_pos, const double *peculiar_velocity, int64_t n,
+                                double redshift, double efunc, double Lbox, int32_t wrap, double *zspace_out);
+
 /* Measured FP64 non-FMA issue rate (DADD/DMUL instr-lanes per second) of the current device. */
 int htb_measure_fp64_rate(double *ops_per_second_out, double *sm_clock_mhz_out);
 

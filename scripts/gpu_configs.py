@@ -22,7 +22,7 @@ def timed(fn, reps=2):
         r = fn()
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
-    return r, best, dict(_lib.last_stats)
+    return r, best, dict(_lib.last_stats or {})
 
 
 which = sys.argv[1:] or ["1", "3", "4", "5"]

@@ -941,3 +941,50 @@ def test_asynchronous_engine_calls_leave_counts_on_the_device():
     assert np.array_equal(got[2].reshape(len(rb), 2), hb.npairs_xy_z(s1, s2, rb, [0.0, 9.0], period=50.0))
     assert np.array_equal(got[3].reshape(len(rb), len(pi)), hb.npairs_xy_z(s1, s2, rb, pi, period=50.0))
     assert np.array_equal(got[4], got[0])
+
+
+# ------------------------------------------------------------------ 8f-4: the input step on the device
+class _FlatLCDM(object):
+    """E(z) of a flat LCDM cosmology (what astropy's efunc returns up to radiation)."""
+    def __init__(self, om=0.3):
+        self.om = om
+
+    def efunc(self, z):
+        return np.sqrt(self.om * (1.0 + z) ** 3 + 1.0 - self.om)
+
+
+def test_input_step_on_the_device_is_the_host_function_bit_for_bit():
+    # catalog_analysis_helpers.py:108-327 - device tensors in, device (Npts, 3) sample out, no coordinate crosses PCIe
+    import torch
+    rng = np.random.RandomState(11)
+    n, L = 200000, 250.0
+    x, y, z = (rng.uniform(-0.3 * L, 1.3 * L, n) for _ in range(3))       # outside the box on both sides: np.mod wraps
+    x[:5] = [0.0, L, -L, 2 * L, -0.0]
+    v = rng.normal(0.0, 400.0, n)
+    dx, dy, dz, dv = (torch.from_numpy(a).cuda() for a in (x, y, z, v))
+    cosmo = _FlatLCDM()
+    for kw in (dict(period=L), dict(period=[L, 2 * L, 3 * L]), dict(),
+               dict(period=L, velocity=v, velocity_distortion_dimension="z"),
+               dict(period=L, velocity=v, velocity_distortion_dimension="x", redshift=1.5, cosmology=cosmo),
+               dict(velocity=v, velocity_distortion_dimension="y", redshift=0.7, cosmology=cosmo)):
+        want = hb.return_xyz_formatted_array(x, y, z, **kw)
+        dkw = dict(kw)
+        if "velocity" in dkw:
+            dkw["velocity"] = dv
+        got = hb.return_xyz_formatted_array(dx, dy, dz, **dkw)
+        assert got.is_cuda and tuple(got.shape) == (n, 3)
+        assert np.array_equal(got.cpu().numpy(), want, equal_nan=True), kw
+    mask = x > 10.0
+    got = hb.return_xyz_formatted_array(dx, dy, dz, period=L, mask=torch.from_numpy(mask).cuda())
+    assert np.array_equal(got.cpu().numpy(), hb.return_xyz_formatted_array(x, y, z, period=L, mask=mask))
+    for Lbox in (None, L):
+        want = hb.apply_zspace_distortion(np.mod(z, L), v, 0.8, cosmo, Lbox=Lbox)
+        got = hb.apply_zspace_distortion(torch.from_numpy(np.mod(z, L)).cuda(), dv, 0.8, cosmo, Lbox=Lbox)
+        assert np.array_equal(got.cpu().numpy(), want)
+    # the device sample feeds the statistics directly
+    pos_d = hb.return_xyz_formatted_array(dx, dy, dz, period=L, velocity=dv, velocity_distortion_dimension="z")
+    pos_h = hb.return_xyz_formatted_array(x, y, z, period=L, velocity=v, velocity_distortion_dimension="z")
+    rp = np.logspace(-0.5, 1.2, 9)
+    a = hb.wp(pos_d, rp, 40.0, period=L)
+    b = hb.wp(pos_h, rp, 40.0, period=L)
+    assert np.array_equal(a, b)
