@@ -24,6 +24,7 @@ FLAG_CACHE_SAMPLE1 = 128
 FLAG_CACHE_SAMPLE2 = 256
 FLAG_PARTITION_SUM = 512
 FLAG_DEVICE_OUTPUT = 1024
+FLAG_EARLY_EXIT = 2048
 
 EXPORTS = (
     "htb_last_error", "htb_abi_version", "htb_device_count", "htb_set_device", "htb_set_stream", "htb_set_shard",
@@ -34,7 +35,7 @@ EXPORTS = (
     "htb_npairs_jackknife_3d_engine", "htb_npairs_jackknife_xy_z_engine", "htb_weighted_npairs_per_object_xy_engine",
     "htb_mesh_cell_ids", "htb_mesh_cell_id_indices", "htb_cell1_work", "htb_measure_fp64_rate",
     "htb_host_minmax", "htb_device_minmax", "htb_tp_estimator", "htb_get_stream", "htb_stream_synchronize", "htb_async_count_times",
-    "htb_return_xyz_formatted_array", "htb_apply_zspace_distortion",
+    "htb_return_xyz_formatted_array", "htb_apply_zspace_distortion", "htb_upload_f64",
 )
 
 
@@ -67,6 +68,7 @@ class Stats(ctypes.Structure):
 _lib = None
 last_stats = None        # Stats of the most recent engine call (dict), for benchmarks / tests
 default_flags = 0        # OR-ed into every engine call (tests flip HTB_FLAG_GENERIC / NO_CULL here)
+stream_flags = 0         # OR-ed into the engine calls a multi-stream statistic issues (HTB_FLAG_EARLY_EXIT)
 collect_stats = True
 
 
@@ -200,7 +202,7 @@ def run_engine(func_name, *args, **kw):
     from . import distributed
     out_device = bool(kw.get("out_device"))
     flags = (default_flags | (FLAG_DEVICE_INPUT if kw.get("device") else 0) | int(kw.get("extra_flags", 0))
-             | distributed.engine_flags() | (FLAG_DEVICE_OUTPUT if out_device else 0))
+             | distributed.engine_flags() | (FLAG_DEVICE_OUTPUT if out_device else 0) | stream_flags)
     want_stats = collect_stats and not out_device
     rc = getattr(lib, func_name)(*args, ctypes.c_uint32(flags),
                                  ctypes.byref(st) if want_stats else None)
@@ -242,6 +244,40 @@ def async_count_times():
     n = ctypes.c_int32(0)
     check(lib.htb_async_count_times(buf, ctypes.c_int32(16), ctypes.byref(n)))
     return [float(buf[i]) for i in range(n.value)]
+
+
+class use_stream(object):
+    """Context manager: this thread's engine calls inside are issued on ``stream`` (a torch.cuda.Stream); the previous
+    stream is restored on exit."""
+
+    def __init__(self, stream):
+        self.stream = stream
+
+    def __enter__(self):
+        lib = require_gpu()
+        prev = ctypes.c_void_p()
+        check(lib.htb_get_stream(ctypes.byref(prev)))
+        self.prev = prev.value
+        check(lib.htb_set_stream(ctypes.c_void_p(self.stream.cuda_stream)))
+        return self.stream
+
+    def __exit__(self, *exc):
+        check(load().htb_set_stream(ctypes.c_void_p(self.prev)))
+        return False
+
+
+def uploadable(a):
+    """A host sample the library can bring to the device as it is: C-contiguous float64 (Npts, ndim)."""
+    return (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.ndim == 2 and a.flags.c_contiguous
+            and a.shape[0] > 0)
+
+
+def upload_rows(host, dev):
+    """Enqueue the copy of a C-contiguous float64 host array into the CUDA tensor ``dev`` (same number of elements) on
+    the engine's stream; the host array must stay alive until the stream is synchronised."""
+    assert host.size == dev.numel() and dev.is_contiguous()
+    check(require_gpu().htb_upload_f64(_dp(host), ctypes.c_int64(host.size),
+                                       ctypes.cast(ctypes.c_void_p(int(dev.data_ptr())), ctypes.POINTER(ctypes.c_double))))
 
 
 def stream_synchronize():

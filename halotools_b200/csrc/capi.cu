@@ -11,6 +11,8 @@
 #include <atomic>
 #include <algorithm>
 
+#include <nvtx3/nvToolsExt.h>          // header-only NVTX 3: ranges cost a null-pointer test when no tool is attached
+
 #include "count.cuh"
 
 // ------------------------------------------------------------------ errors / globals
@@ -71,10 +73,13 @@ struct UploadEnt {
     int64_t dstride;
     void *blocks[3];
     int nblocks;
+    int device;
     cudaStream_t st;
 };
 static thread_local bool g_cache_on = false;
 static thread_local std::vector<UploadEnt> *g_cache = nullptr;
+
+static void sort_cache_clear();
 
 extern "C" int htb_cache_begin(void)
 {
@@ -85,12 +90,53 @@ extern "C" int htb_cache_begin(void)
 extern "C" int htb_cache_end(void)
 {
     g_cache_on = false;
+    sort_cache_clear();
     if (g_cache) {
         for (auto &e : *g_cache)
             for (int k = 0; k < e.nblocks; ++k) cudaFreeAsync(e.blocks[k], e.st);
         g_cache->clear();
     }
     return 0;
+}
+
+// Sorted-sample cache (same scope as the upload cache): inside one statistic the counting sort of a sample on a given
+// fine grid is done ONCE - tpcf's randoms are sample2 of the DR count and both samples of the RR count on the same
+// grid (the reference builds a new RectangularDoubleMesh, i.e. two argsorts, in every npairs call, tpcf.py:76-113,164-205).
+// Entries own their device memory (their own Workspace on the creating stream); a hit from another stream waits for the
+// entry's `ready` event and is remembered, so that htb_cache_end() frees the blocks behind every user.
+struct SortEnt {
+    const double *src[3];
+    int64_t stride, n;
+    const double *w;
+    int nw;
+    bool perm;
+    double pad;
+    FineGrid g;
+    SortedSample s;
+    Workspace ws;
+    cudaEvent_t ready;
+    std::vector<cudaStream_t> users;
+};
+static thread_local std::vector<SortEnt *> *g_sort_cache = nullptr;
+
+static void sort_cache_clear()
+{
+    if (!g_sort_cache) return;
+    for (SortEnt *e : *g_sort_cache) {
+        for (cudaStream_t u : e->users) {
+            if (u == e->ws.st) continue;
+            cudaEvent_t ev;
+            if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess) {
+                cudaEventRecord(ev, u);
+                cudaStreamWaitEvent(e->ws.st, ev, 0);
+                cudaEventDestroy(ev);
+            }
+        }
+        e->ws.release();
+        if (e->ready) cudaEventDestroy(e->ready);
+        delete e;
+    }
+    g_sort_cache->clear();
 }
 
 static bool g_pool_ready[64] = {false};
@@ -512,9 +558,18 @@ struct Call {
     uint32_t flags = 0;
     bool async = false;                     // HTB_FLAG_DEVICE_OUTPUT: results stay on the device, no host synchronisation
 
-    ~Call() { ws.release(); }
+    // NVTX ranges of the host side of a call (enqueue order = stream order): htb:h2d / htb:mesh_sort / htb:count /
+    // htb:finalize, visible on the timeline of nsys / ncu next to the kernels they enqueue
+    int nvtx_open = 0;
+    void nvtx_next(const char *name)
+    {
+        if (nvtx_open) { nvtxRangePop(); nvtx_open = 0; }
+        if (name) { nvtxRangePushA(name); nvtx_open = 1; }
+    }
+    ~Call() { nvtx_next(nullptr); ws.release(); }
     int begin(uint32_t fl = 0)
     {
+        nvtx_next("htb:h2d");
         if (get_stream(&st)) return 1;
         ws.st = st;
         async = (fl & HTB_FLAG_DEVICE_OUTPUT) != 0;
@@ -529,6 +584,8 @@ struct Call {
     }
     int mark(int i)
     {
+        static const char *const names[5] = {"htb:h2d", "htb:mesh_sort", "htb:count", "htb:finalize", nullptr};
+        nvtx_next(names[i]);
         if (ev) HTB_CUDA(cudaEventRecord(ev[i], st));
         else if (async && (i == 2 || i == 3)) {
             cudaEvent_t *pair = g_async_ev[g_async_n % HTB_ASYNC_RING];
@@ -539,24 +596,35 @@ struct Call {
         return 0;
     }
     // bring `cnt` arrays of n elements (common element stride) to the device; returns device pointers + stride
+    // *stable (optional): the device pointers keep naming this sample until htb_cache_end() (device-resident input inside
+    // a cache scope, or a host sample held by the upload cache) - the condition for the sorted-sample cache
     int stage_coords(const double *const *src, int cnt, int64_t stride, int64_t n, const double **dst, int64_t *dstride,
-                     bool cacheable = false)
+                     bool cacheable = false, bool *stable = nullptr)
     {
+        if (stable) *stable = false;
         if (flags & HTB_FLAG_DEVICE_INPUT) {
             for (int k = 0; k < cnt; ++k) dst[k] = src[k];
             *dstride = stride;
+            if (stable) *stable = g_cache_on && n > 0;
             return 0;
         }
         if (n <= 0) { for (int k = 0; k < cnt; ++k) dst[k] = nullptr; *dstride = 1; return 0; }
         UploadEnt ent{};
         const bool caching = cacheable && g_cache_on && g_cache;
+        int dev = 0;
+        HTB_CUDA(cudaGetDevice(&dev));
+        // blocks taken for the cache belong to nobody until done() hands them over: free them on every failure path
+        struct BlockGuard {
+            UploadEnt &e; cudaStream_t st; bool armed;
+            ~BlockGuard() { if (armed) for (int k = 0; k < e.nblocks; ++k) cudaFreeAsync(e.blocks[k], st); }
+        } guard{ent, st, true};
         if (caching) {
             for (auto &e : *g_cache) {
-                bool hit = e.cnt == cnt && e.stride == stride && e.n == n && e.st == st;
+                bool hit = e.cnt == cnt && e.stride == stride && e.n == n && e.st == st && e.device == dev;
                 for (int k = 0; k < cnt && hit; ++k) hit = e.src[k] == src[k];
-                if (hit) { for (int k = 0; k < cnt; ++k) dst[k] = e.dev[k]; *dstride = e.dstride; return 0; }
+                if (hit) { for (int k = 0; k < cnt; ++k) dst[k] = e.dev[k]; *dstride = e.dstride; if (stable) *stable = true; return 0; }
             }
-            ent.cnt = cnt; ent.stride = stride; ent.n = n; ent.st = st;
+            ent.cnt = cnt; ent.stride = stride; ent.n = n; ent.st = st; ent.device = dev;
             for (int k = 0; k < cnt; ++k) ent.src[k] = src[k];
         }
         // device blocks: owned by the call's workspace, or by the upload cache when it is on
@@ -573,7 +641,9 @@ struct Call {
                 for (int k = 0; k < cnt; ++k) ent.dev[k] = dst[k];
                 ent.dstride = *dstride;
                 g_cache->push_back(ent);
+                if (stable) *stable = true;
             }
+            guard.armed = false;
             return 0;
         };
         if (n >= 4 * HTB_STAGE_CHUNK && host_pointer_is_pageable(src[0]) && !getenv("HTB_NO_STAGED_UPLOAD")) {
@@ -631,6 +701,39 @@ struct Call {
         *dst = buf;
         return 0;
     }
+    // counting sort of one sample, served from the sorted-sample cache when the sample is `stable` (see stage_coords)
+    int sorted(const FineGrid &g, const double *const *d, int64_t ds, int64_t n, const double *dw, int nw, bool perm,
+               double pad, bool stable, SortedSample &out)
+    {
+        if (!stable || !g_cache_on || (dw && !(flags & HTB_FLAG_DEVICE_INPUT)) || getenv("HTB_NO_SORT_CACHE"))
+            return htb_sort_sample(st, ws, g, d, ds, n, dw, nw, perm, pad, out, &launches);
+        if (!g_sort_cache) g_sort_cache = new std::vector<SortEnt *>();
+        for (SortEnt *e : *g_sort_cache) {
+            bool hit = e->stride == ds && e->n == n && e->w == dw && e->nw == (dw ? nw : 0) && e->perm == perm && e->pad == pad &&
+                       e->g.dim == g.dim;
+            for (int k = 0; k < g.dim && hit; ++k)
+                hit = e->src[k] == d[k] && e->g.nd[k] == g.nd[k] && e->g.m[k] == g.m[k] && e->g.cs[k] == g.cs[k] &&
+                      e->g.period[k] == g.period[k];
+            if (!hit) continue;
+            if (e->ws.st != st) {
+                HTB_CUDA(cudaStreamWaitEvent(st, e->ready, 0));
+                if (std::find(e->users.begin(), e->users.end(), st) == e->users.end()) e->users.push_back(st);
+            }
+            out = e->s;
+            return 0;
+        }
+        SortEnt *e = new SortEnt();
+        for (int k = 0; k < 3; ++k) e->src[k] = k < g.dim ? d[k] : nullptr;
+        e->stride = ds; e->n = n; e->w = dw; e->nw = dw ? nw : 0; e->perm = perm; e->pad = pad; e->g = g;
+        e->ws.st = st;
+        e->ready = nullptr;
+        g_sort_cache->push_back(e);                       // (owned by the cache from here on: freed by htb_cache_end)
+        if (htb_sort_sample(st, e->ws, g, d, ds, n, dw, nw, perm, pad, e->s, &launches)) return 1;
+        HTB_CUDA(cudaEventCreateWithFlags(&e->ready, cudaEventDisableTiming));
+        HTB_CUDA(cudaEventRecord(e->ready, st));
+        out = e->s;
+        return 0;
+    }
     // full set-up: upload, sort both samples, tile list, walker geometry
     int setup(const htb_mesh_geom *g, int sphere, bool allow_sym,
               const double *const *c1, int64_t stride1, int64_t n1, const double *w1,
@@ -657,9 +760,10 @@ struct Call {
         const double *dw1 = nullptr, *dw2 = nullptr;
         bool same = (n1 == n2 && stride1 == stride2);
         for (int d = 0; d < dim && same; ++d) same = (c1[d] == c2[d]);
-        if (stage_coords(c1, dim, stride1, n1, d1, &ds1, (fl & HTB_FLAG_CACHE_SAMPLE1) != 0)) return 1;
-        if (same) { for (int d = 0; d < dim; ++d) d2[d] = d1[d]; ds2 = ds1; }
-        else if (stage_coords(c2, dim, stride2, n2, d2, &ds2, (fl & HTB_FLAG_CACHE_SAMPLE2) != 0)) return 1;
+        bool stable1 = false, stable2 = false;
+        if (stage_coords(c1, dim, stride1, n1, d1, &ds1, (fl & HTB_FLAG_CACHE_SAMPLE1) != 0, &stable1)) return 1;
+        if (same) { for (int d = 0; d < dim; ++d) d2[d] = d1[d]; ds2 = ds1; stable2 = stable1; }
+        else if (stage_coords(c2, dim, stride2, n2, d2, &ds2, (fl & HTB_FLAG_CACHE_SAMPLE2) != 0, &stable2)) return 1;
         if (stage_rows(w1, n1, nw, &dw1)) return 1;
         if (w2 == w1 && same) dw2 = dw1;
         else if (stage_rows(w2, n2, nw, &dw2)) return 1;
@@ -704,7 +808,8 @@ struct Call {
             for (int d = 0; d < dim; ++d) est *= std::min(1.0, 2.6 * g->search[d] / g->period[d]);
             G.maxslices = clampi(est / 2.0e5, 1, 16);
             if (const char *e = getenv("HTB_MAXSLICES")) { const int v = atoi(e); if (v >= 1 && v <= 64) G.maxslices = v; }
-            G.tail_eighths = 4;
+            G.early_exit = ((fl & HTB_FLAG_EARLY_EXIT) || getenv("HTB_EARLY_EXIT")) ? 1 : 0;
+            G.tail_eighths = 0;          // measured (profiles/r02_tail_sweep.txt): slices cost more than the idle tail they remove
             if (const char *e = getenv("HTB_TAIL_EIGHTHS")) { const int v = atoi(e); if (v >= 0 && v <= 512) G.tail_eighths = v; }
             G.items_per_warp = HTB_ITEMS_PER_WARP;
             if (const char *e = getenv("HTB_ITEMS_PER_WARP")) { const int v = atoi(e); if (v >= 1 && v <= 1024) G.items_per_warp = v; }
@@ -753,11 +858,11 @@ struct Call {
             if (htb_sort_finish(st, ws, d2, ds2, dw2, nw, sentinel, window ? xwin + 2 : nullptr, s2, &launches)) return 1;
             if (sym) s1 = s2;
         } else if (sym) {
-            if (htb_sort_sample(st, ws, g2, d2, ds2, n2, dw2, nw, perm1, sentinel, s2, &launches)) return 1;
+            if (sorted(g2, d2, ds2, n2, dw2, nw, perm1, sentinel, stable2, s2)) return 1;
             s1 = s2;
         } else {
-            if (htb_sort_sample(st, ws, g1, d1, ds1, n1, dw1, nw, perm1, sentinel, s1, &launches)) return 1;
-            if (htb_sort_sample(st, ws, g2, d2, ds2, n2, dw2, nw, false, sentinel, s2, &launches)) return 1;
+            if (sorted(g1, d1, ds1, n1, dw1, nw, perm1, sentinel, stable1, s1)) return 1;
+            if (sorted(g2, d2, ds2, n2, dw2, nw, false, sentinel, stable2, s2)) return 1;
         }
         // ---- tiles + counters
         uint2 *tiles = nullptr;
@@ -1812,6 +1917,27 @@ extern "C" int htb_tp_estimator(int32_t n0, int32_t n1, int32_t estimator, int32
               d{(const long long *)RR_cum, RR_diff};
     k_tp_estimator<<<1, 256, 0, st>>>(n0, n1, estimator, cross, a, b, c, d, inv_factor1, inv_factor2, wp_pi_max, xi_out, flag_out);
     HTB_CUDA(cudaGetLastError());
+    return 0;
+    HTB_GUARD_END
+}
+
+// Host -> device copy of `count` doubles on the thread's stream (asynchronous): pinned memory goes out with one
+// cudaMemcpyAsync, large pageable arrays through the ring of pinned chunks filled by host threads (staged_upload) - the
+// same path the engines use for their inputs, exposed so that a statistic can bring every sample to the device ONCE
+// (or a rank its 1/world share, completed by an all-gather over NVLink) before it chains several engine calls.
+extern "C" int htb_upload_f64(const double *host_src, int64_t count, double *dev_dst)
+{
+    HTB_GUARD_BEGIN
+    if (count < 0 || (count > 0 && (!host_src || !dev_dst))) { htb_set_error("htb_upload_f64: bad arguments"); return 1; }
+    if (count == 0) return 0;
+    cudaStream_t st;
+    if (get_stream(&st)) return 1;
+    if (count >= 4 * (int64_t)HTB_STAGE_CHUNK && host_pointer_is_pageable(host_src) && !getenv("HTB_NO_STAGED_UPLOAD")) {
+        const double *src[1] = {host_src};
+        double *dst[1] = {dev_dst};
+        return staged_upload(st, src, 1, 1, count, dst);
+    }
+    HTB_CUDA(cudaMemcpyAsync(dev_dst, host_src, sizeof(double) * (size_t)count, cudaMemcpyHostToDevice, st));
     return 0;
     HTB_GUARD_END
 }

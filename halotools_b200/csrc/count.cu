@@ -11,6 +11,8 @@
 //   Marked3  marked_npairs_3d, 17 weight functions               marked_npairs_3d_engine.pyx:204-216
 //   DSigma   mean_delta_sigma per-object accumulators (2-D)      mean_delta_sigma_engine.pyx:162-180
 #include <type_traits>
+#include <vector>
+#include <cstring>
 #include "walk.cuh"
 #include "count.cuh"
 #include "kernel.cuh"
@@ -75,8 +77,12 @@ __global__ void k_fill_tiles(const uint32_t *__restrict__ off1, WalkGeom G, int6
 // pairs the reference loop nest visits, per reference cell1 (W_ref), and - for the multi-GPU cut -
 // the pairs this engine expects to evaluate: in symmetric mode a zero-shift neighbour cell is evaluated only from
 // the cell with the smaller id (half of the own cell), wrapped neighbours from both sides.
+// `wtab` (optional): per neighbour-cell offset inside the window, the fraction of its pairs that survives the walker's
+// pruning (pairs within the search length): the corner cells of a window cost far less than its face cells, and the
+// x-layers a rank's range touches at the periodic boundary are corner-heavy (an unweighted cut gave rank 0 of 8 7 %
+// fewer evaluated pairs than the others).
 __global__ void k_wref(const uint32_t *__restrict__ rc1, const uint32_t *__restrict__ rc2, WalkGeom G,
-                       int64_t ncell1, double *__restrict__ work, double *__restrict__ balance)
+                       int64_t ncell1, double *__restrict__ work, double *__restrict__ balance, const float *__restrict__ wtab)
 {
     for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < ncell1; c += (int64_t)gridDim.x * blockDim.x) {
         const uint32_t n1 = rc1[c];
@@ -87,7 +93,9 @@ __global__ void k_wref(const uint32_t *__restrict__ rc1, const uint32_t *__restr
             for (int d = G.dim - 1; d >= 0; --d) { a[d] = (int)(rem % G.nd1[d]); rem /= G.nd1[d]; }
             int lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1};
             for (int d = 0; d < G.dim; ++d) { lo[d] = a[d] * G.per[d] - G.cover[d]; hi[d] = (a[d] + 1) * G.per[d] + G.cover[d]; }
-            unsigned long long s = 0, s2 = 0;          // s2: twice the symmetric-mode pairs
+            unsigned long long s = 0;
+            double s2 = 0.0, sw = 0.0;                 // s2: twice the symmetric-mode pairs; both weighted by wtab
+            const int wy_n = hi[1] - lo[1], wz_n = G.dim == 3 ? hi[2] - lo[2] : 1;
             for (int ux = lo[0]; ux < hi[0]; ++ux) {
                 const int kx = floor_div(ux, G.nd2[0]), wx = ux - kx * G.nd2[0];
                 for (int uy = lo[1]; uy < hi[1]; ++uy) {
@@ -95,21 +103,25 @@ __global__ void k_wref(const uint32_t *__restrict__ rc1, const uint32_t *__restr
                     if (G.dim == 2) {
                         const int64_t c2 = (int64_t)wx * G.nd2[1] + wy;
                         const unsigned long long n2 = rc2[c2];
+                        const double f = wtab ? (double)wtab[(ux - lo[0]) * wy_n + (uy - lo[1])] : 1.0;
                         s += n2;
-                        s2 += ((kx | ky) != 0 || c2 > c) ? 2 * n2 : (c2 == c ? n2 : 0);
+                        sw += f * (double)n2;
+                        s2 += f * (double)(((kx | ky) != 0 || c2 > c) ? 2 * n2 : (c2 == c ? n2 : 0));
                         continue;
                     }
                     for (int uz = lo[2]; uz < hi[2]; ++uz) {
                         const int kz = floor_div(uz, G.nd2[2]), wz = uz - kz * G.nd2[2];
                         const int64_t c2 = ((int64_t)wx * G.nd2[1] + wy) * G.nd2[2] + wz;
                         const unsigned long long n2 = rc2[c2];
+                        const double f = wtab ? (double)wtab[((ux - lo[0]) * wy_n + (uy - lo[1])) * wz_n + (uz - lo[2])] : 1.0;
                         s += n2;
-                        s2 += ((kx | ky | kz) != 0 || c2 > c) ? 2 * n2 : (c2 == c ? n2 : 0);
+                        sw += f * (double)n2;
+                        s2 += f * (double)(((kx | ky | kz) != 0 || c2 > c) ? 2 * n2 : (c2 == c ? n2 : 0));
                     }
                 }
             }
             w = (double)n1 * (double)s;
-            wb = G.sym ? (double)n1 * (double)s2 : 2.0 * w;
+            wb = G.sym ? (double)n1 * s2 : 2.0 * (double)n1 * sw;
         }
         work[c] = w;
         if (balance) balance[c] = wb;
@@ -1898,9 +1910,57 @@ int htb_reference_work(cudaStream_t st, Workspace &ws, const WalkGeom &G, const 
         if (htb_ref_cell_counts(st, s1, rc1, launches)) return 1;
         if (htb_ref_cell_counts(st, s2, rc2, launches)) return 1;
     }
+    // pruning weights of the window's cells (only for the multi-GPU cut): Monte-Carlo fraction of the pairs between a
+    // mesh1 cell and the mesh2 cell at each window offset that lie within the search length, + a floor for the per-cell
+    // overheads; a fixed sample set, recomputed only when the geometry changes
+    float *wtab_dev = nullptr;
+    if (balance) {
+        static thread_local std::vector<float> tab;
+        static thread_local double key[16] = {0};
+        double k[16] = {(double)G.dim, (double)G.sphere, 0};
+        int wn[3] = {1, 1, 1};
+        size_t ntab = 1;
+        for (int d = 0; d < G.dim; ++d) {
+            wn[d] = G.per[d] + 2 * G.cover[d];
+            ntab *= (size_t)wn[d];
+            k[2 + 4 * d] = G.per[d]; k[3 + 4 * d] = G.cover[d]; k[4 + 4 * d] = G.period[d] / G.nd2[d]; k[5 + 4 * d] = G.reach[d];
+        }
+        if (ntab <= 4096) {
+            if (tab.size() != ntab || memcmp(k, key, sizeof(k)) != 0) {
+                tab.assign(ntab, 0.f);
+                const int NS = 2048;
+                unsigned long long rng = 0x9E3779B97F4A7C15ULL;
+                auto u01 = [&]() { rng = rng * 6364136223846793005ULL + 1442695040888963407ULL; return (double)(rng >> 11) * (1.0 / 9007199254740992.0); };
+                std::vector<double> p1((size_t)NS * 3), p2((size_t)NS * 3);
+                for (auto &v : p1) v = u01();
+                for (auto &v : p2) v = u01();
+                for (size_t t = 0; t < ntab; ++t) {
+                    int o[3] = {0, 0, 0};
+                    size_t rem = t;
+                    for (int d = G.dim - 1; d >= 0; --d) { o[d] = (int)(rem % wn[d]); rem /= wn[d]; }
+                    int hit = 0;
+                    for (int i = 0; i < NS; ++i) {
+                        double q = 0.0, qz = 0.0;
+                        for (int d = 0; d < G.dim; ++d) {
+                            const double cs2 = G.period[d] / G.nd2[d];
+                            const double a = p1[(size_t)i * 3 + d] * (G.per[d] * cs2);                  // in the mesh1 cell
+                            const double b = ((double)(o[d] - G.cover[d]) + p2[(size_t)i * 3 + d]) * cs2;  // in the mesh2 cell at this offset
+                            const double r = G.reach[d] > 0 ? (a - b) / G.reach[d] : 0.0;
+                            if (!G.sphere && d == G.dim - 1) qz = r * r; else q += r * r;
+                        }
+                        hit += (q <= 1.0 && qz <= 1.0) ? 1 : 0;
+                    }
+                    tab[t] = 0.03f + (float)hit / (float)NS;
+                }
+                memcpy(key, k, sizeof(k));
+            }
+            if (ws.alloc((void **)&wtab_dev, sizeof(float) * ntab)) return 1;
+            HTB_CUDA(cudaMemcpyAsync(wtab_dev, tab.data(), sizeof(float) * ntab, cudaMemcpyHostToDevice, st));
+        }
+    }
     int blocks = (int)((nc1 + 127) / 128);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    k_wref<<<blocks, 128, 0, st>>>(rc1, rc2, G, nc1, work, balance);
+    k_wref<<<blocks, 128, 0, st>>>(rc1, rc2, G, nc1, work, balance, wtab_dev);
     if (launches) *launches += 1;
     HTB_CUDA(cudaGetLastError());
     *work_dev_out = work;

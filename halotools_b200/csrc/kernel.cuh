@@ -100,6 +100,10 @@ k_count(const __grid_constant__ WalkGeom G, const __grid_constant__ WalkArrays A
                     // nothing to take: finished only if no ordinary item is still running (it could publish more)
                     // and every reservation has been published
                     if (done >= (unsigned)nitems && published == reserved) { quit = 1; break; }
+                    // HTB_FLAG_EARLY_EXIT: leave as soon as there is nothing to take, so that the block can retire and the
+                    // blocks of the next kernel (waiting on another stream) fill this launch's tail.  Every published entry
+                    // is still served: its publisher comes through this loop after its own items.
+                    if (G.early_exit) { quit = 1; break; }
                     __nanosleep(backoff);
                     if (backoff < 8000) backoff *= 2;
                 }

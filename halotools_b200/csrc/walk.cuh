@@ -49,6 +49,7 @@ struct WalkGeom {
     int maxfine;                    // fine mesh1 cells along the fast dimension one tile may cover (bounds its extent)
     int maxslices;                  // a tile's sample2 columns may be cut into up to this many independent work items
     int items_per_warp;             // ... until every resident warp has about this many work items
+    int early_exit;                 // idle warps do not wait for the redo queue to drain (HTB_FLAG_EARLY_EXIT)
     int tail_eighths;               // the last (resident warps x this / 8) tiles are cut into maxslices slices (0: off)
 };
 

@@ -73,6 +73,30 @@ def allreduce_device(tensor):
     return tensor
 
 
+def to_device(sample):
+    """A C-contiguous float64 host sample (N, d) as a CUDA tensor, copied on the engine's stream (asynchronous: the
+    caller keeps ``sample`` alive until it synchronises).  With sharding over NCCL every rank uploads only ITS 1/world of
+    the rows across PCIe and one all-gather over NVLink / NVSwitch completes every rank's copy (every rank holds the
+    same host array: the reference's workers all see the whole sample too, npairs_3d.py:139-146)."""
+    import torch
+    from . import _lib
+    n, d = sample.shape
+    if not device_collective():
+        dev = torch.empty((n, d), dtype=torch.float64, device="cuda")
+        _lib.upload_rows(sample, dev)
+        return dev
+    import torch.distributed as dist
+    rank, world = _rank_world()
+    per = -(-n // world)
+    full = torch.empty((per * world, d), dtype=torch.float64, device="cuda")
+    a, b = min(n, rank * per), min(n, (rank + 1) * per)
+    part = full[rank * per:(rank + 1) * per]
+    if b > a:
+        _lib.upload_rows(sample[a:b], part[:b - a])
+    dist.all_gather_into_tensor(full, part, group=_state["group"])        # in place: part is this rank's slot of full
+    return full[:n]
+
+
 def split_cells(ncells, world, work=None):
     """Contiguous (first, last) mesh1-cell ranges for ``world`` ranks.
 
@@ -153,6 +177,12 @@ class local_counts(object):
 
     def __exit__(self, exc_type, exc, tb):
         _state["local"] -= 1
+        if _state["local"] == 0 and _rank_world()[1] > 1:
+            # a rank that failed inside the block must not leave its peers waiting in the all-reduce: agree on the
+            # outcome first (one more tiny collective per statistic), then every rank raises
+            failed = int(allreduce_sum(np.array([1 if exc_type is not None else 0], dtype=np.int64))[0])
+            if failed and exc_type is None:
+                raise RuntimeError("halotools_b200.distributed: %d peer rank(s) failed inside this statistic" % failed)
         if exc_type is None and self.pending and _state["local"] == 0:
             arrays, seen = [], set()
             for a in self.pending:

@@ -52,6 +52,11 @@ def _rp_pi_tpcf(sample1, rp_bins, pi_bins, sample2, randoms, period, do_auto, do
     if _device.available(npairs_xy_z):
         # K3 on the device: counts stay in HBM, one all-reduce, estimator kernel, ONE host synchronisation
         stat = _device.DeviceStatistic((len(rp_bins), len(pi_bins)))
+        if same:
+            sample1, randoms = stat.inputs(PBCs, sample1, randoms)
+            sample2 = sample1
+        else:
+            sample1, sample2, randoms = stat.inputs(PBCs, sample1, sample2, randoms)
 
         def dcount(a, b, cell_a, cell_b):
             return stat.count(npairs_xy_z.enqueue, a, b, rp_bins, pi_bins, period=period, num_threads=num_threads,

@@ -84,6 +84,11 @@ def _tpcf_device(sample1, rbins, sample2, randoms, period, do_auto, do_cross, es
                  approx_cell1_size, approx_cell2_size, approx_cellran_size, RR_precomputed, same,
                  do_DR, do_RR, N1, N2, NR):
     stat = _device.DeviceStatistic((len(rbins),))
+    if same:
+        sample1, randoms = stat.inputs(period is not None, sample1, randoms)
+        sample2 = sample1
+    else:
+        sample1, sample2, randoms = stat.inputs(period is not None, sample1, sample2, randoms)
 
     def count(a, b, cell_a, cell_b):
         return stat.count(npairs_3d.enqueue, a, b, rbins, period=period, num_threads=num_threads,

@@ -49,6 +49,8 @@ extern "C" {
                                        filled).  Host input arrays must stay alive and unmodified until the caller synchronises
                                        (htb_stream_synchronize).  Supported by the counters a statistic chains: npairs_3d, npairs_xy_z,
                                        npairs_s_mu, marked_npairs_3d, marked_npairs_xy_z, weighted_npairs_xy, mean_delta_sigma.      */
+#define HTB_FLAG_EARLY_EXIT 2048u  /* warps of the counting kernel that run out of work retire at once instead of waiting to help with late exact
+                                       re-evaluations: lets the next kernel, enqueued on ANOTHER stream, fill this launch's tail (results unchanged) */
 #define HTB_FLAG_NO_SYM       16u  /* auto-correlations: evaluate (i,j) and (j,i) separately, as the reference does */
 #define HTB_FLAG_PARTITION_SUM 512u /* [first_cell1, last_cell1) is one part of a partition of the mesh1 cells whose results the
                                        caller SUMS (multi-GPU shards): auto-correlations may then keep the symmetric shortcut
@@ -265,6 +267,10 @@ int htb_tp_estimator(int32_t n0, int32_t n1, int32_t estimator, int32_t cross,
                      const double *D1R_diff, const double *D2R_diff, const double *RR_diff,
                      double inv_factor1, double inv_factor2, double wp_pi_max,
                      double *xi_out, int32_t *flag_out);
+
+/* Asynchronous host -> device copy of `count` doubles on the thread's stream (pinned: one copy; large pageable arrays:
+ * the threaded pinned-chunk ring the engines use).  host_src must stay alive until the stream is synchronised.     */
+int htb_upload_f64(const double *host_src, int64_t count, double *dev_dst);
 
 /* The CUDA stream (cudaStream_t as void*) this thread's calls are issued on, and a host wait for it. */
 int htb_get_stream(void **stream_out);
