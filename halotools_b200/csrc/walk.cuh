@@ -154,7 +154,10 @@ struct WarpSmem {
     uint32_t stage0_s;              // its shared-space address
     uint32_t bar0;                  // shared-space address of mbarrier 0 (16 bytes apart)
     uint32_t *span;                 // HTB_SPAN_CAP * 3 u32: {jb, je, code}
-    static __host__ __device__ constexpr int stage_doubles() { return CH * (DIM + NPAY); }
+    // (+ 2: the register double-buffering of the fast kernels reads one pair of doubles past the last row of a stage;
+    // without the pad that read lands in the next stage, which a TMA copy may be filling - harmless, the value is never
+    // used, but racecheck reports it)
+    static __host__ __device__ constexpr int stage_doubles() { return CH * (DIM + NPAY) + 2; }
     static __host__ __device__ constexpr size_t bytes()
     {
         return sizeof(double) * HTB_NSTAGE * stage_doubles() + 16 * HTB_NSTAGE + sizeof(uint32_t) * 3 * HTB_SPAN_CAP;
