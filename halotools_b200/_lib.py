@@ -25,6 +25,7 @@ FLAG_CACHE_SAMPLE2 = 256
 FLAG_PARTITION_SUM = 512
 FLAG_DEVICE_OUTPUT = 1024
 FLAG_EARLY_EXIT = 2048
+FLAG_PREPARE = 4096
 
 EXPORTS = (
     "htb_last_error", "htb_abi_version", "htb_device_count", "htb_set_device", "htb_set_stream", "htb_set_shard",

@@ -80,6 +80,7 @@ static thread_local bool g_cache_on = false;
 static thread_local std::vector<UploadEnt> *g_cache = nullptr;
 
 static void sort_cache_clear();
+static void prep_cache_clear();
 
 extern "C" int htb_cache_begin(void)
 {
@@ -91,6 +92,7 @@ extern "C" int htb_cache_end(void)
 {
     g_cache_on = false;
     sort_cache_clear();
+    prep_cache_clear();
     if (g_cache) {
         for (auto &e : *g_cache)
             for (int k = 0; k < e.nblocks; ++k) cudaFreeAsync(e.blocks[k], e.st);
@@ -119,6 +121,29 @@ struct SortEnt {
 };
 static thread_local std::vector<SortEnt *> *g_sort_cache = nullptr;
 
+// The same for one rank of a SHARDED call, where the sort of the two samples, the rank's cell range and its windows
+// belong together: keyed by everything that determines them.  It lets a statistic run the set-up of all its counts
+// first (HTB_FLAG_PREPARE) and launch the count kernels afterwards - see DeviceStatistic.
+struct PrepKey {
+    const double *d1[3], *d2[3], *dw1, *dw2;
+    int64_t ds1, ds2, n1, n2, first, last;
+    htb_mesh_geom geom;
+    int m1[3], m2[3];
+    int nw, perm1, sym, rank, world, window;
+    double pad;
+};
+struct PrepEnt {
+    PrepKey key;
+    SortedSample s1, s2;
+    long long *range_dev;
+    double *work_dev;
+    int64_t nc1;
+    Workspace ws;
+    cudaEvent_t ready;
+    std::vector<cudaStream_t> users;
+};
+static thread_local std::vector<PrepEnt *> *g_prep_cache = nullptr;
+
 static void sort_cache_clear()
 {
     if (!g_sort_cache) return;
@@ -137,6 +162,26 @@ static void sort_cache_clear()
         delete e;
     }
     g_sort_cache->clear();
+}
+
+static void prep_cache_clear()
+{
+    if (!g_prep_cache) return;
+    for (PrepEnt *e : *g_prep_cache) {
+        for (cudaStream_t u : e->users) {
+            if (u == e->ws.st) continue;
+            cudaEvent_t ev;
+            if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess) {
+                cudaEventRecord(ev, u);
+                cudaStreamWaitEvent(e->ws.st, ev, 0);
+                cudaEventDestroy(ev);
+            }
+        }
+        e->ws.release();
+        if (e->ready) cudaEventDestroy(e->ready);
+        delete e;
+    }
+    g_prep_cache->clear();
 }
 
 static bool g_pool_ready[64] = {false};
@@ -557,6 +602,7 @@ struct Call {
     int64_t nc1 = 0;
     uint32_t flags = 0;
     bool async = false;                     // HTB_FLAG_DEVICE_OUTPUT: results stay on the device, no host synchronisation
+    bool prepared = false;                  // HTB_FLAG_PREPARE: setup() stopped after the mesh sorts (now in the caches)
 
     // NVTX ranges of the host side of a call (enqueue order = stream order): htb:h2d / htb:mesh_sort / htb:count /
     // htb:finalize, visible on the timeline of nsys / ncu next to the kernels they enqueue
@@ -714,7 +760,7 @@ struct Call {
             for (int k = 0; k < g.dim && hit; ++k)
                 hit = e->src[k] == d[k] && e->g.nd[k] == g.nd[k] && e->g.m[k] == g.m[k] && e->g.cs[k] == g.cs[k] &&
                       e->g.period[k] == g.period[k];
-            if (!hit) continue;
+            if (!hit || !e->ready) continue;
             if (e->ws.st != st) {
                 HTB_CUDA(cudaStreamWaitEvent(st, e->ready, 0));
                 if (std::find(e->users.begin(), e->users.end(), st) == e->users.end()) e->users.push_back(st);
@@ -843,20 +889,54 @@ struct Call {
             // One rank of a sharded call: cell ids and per-cell counts of BOTH samples first; from them this rank's
             // share of [first_cell1, last_cell1), cut by predicted work on the device (no host sync); then only the
             // points inside the x-layers that share can touch are put in order (the rest is never moved).
-            if (!sym && htb_sort_begin(st, ws, g1, d1, ds1, n1, dw1, nw, perm1, s1, &launches)) return 1;
-            if (htb_sort_begin(st, ws, g2, d2, ds2, n2, dw2, nw, sym ? perm1 : false, s2, &launches)) return 1;
-            double *balance_dev = nullptr;
-            if (htb_reference_work(st, ws, G, sym ? s2 : s1, s2, &work_dev, &balance_dev, &nc1, &launches, true)) return 1;
-            if (ws.alloc((void **)&range_dev, 2 * sizeof(long long))) return 1;
-            const int64_t lo = first_cell1 < 0 ? 0 : first_cell1, hi = last_cell1 > nc1 ? nc1 : last_cell1;
-            if (htb_shard_range(st, balance_dev, lo, hi, g_shard_rank, g_shard_world, range_dev, &launches)) return 1;
-            int *xwin = nullptr;
-            if (ws.alloc((void **)&xwin, 4 * sizeof(int))) return 1;
-            if (htb_shard_windows(st, range_dev, G, xwin, &launches)) return 1;
             const bool window = !getenv("HTB_NO_WINDOW_SORT");
-            if (!sym && htb_sort_finish(st, ws, d1, ds1, dw1, nw, sentinel, window ? xwin : nullptr, s1, &launches)) return 1;
-            if (htb_sort_finish(st, ws, d2, ds2, dw2, nw, sentinel, window ? xwin + 2 : nullptr, s2, &launches)) return 1;
-            if (sym) s1 = s2;
+            const bool cacheable = g_cache_on && stable1 && stable2 && !getenv("HTB_NO_SORT_CACHE") &&
+                                   ((!dw1 && !dw2) || (flags & HTB_FLAG_DEVICE_INPUT));
+            PrepKey key;
+            memset(&key, 0, sizeof(key));
+            for (int d = 0; d < dim; ++d) { key.d1[d] = d1[d]; key.d2[d] = d2[d]; key.m1[d] = m1[d]; key.m2[d] = m2[d]; }
+            key.dw1 = dw1; key.dw2 = dw2; key.ds1 = ds1; key.ds2 = ds2; key.n1 = n1; key.n2 = n2;
+            key.first = first_cell1; key.last = last_cell1; key.geom = *g; key.geom.reserved = 0;
+            key.nw = nw; key.perm1 = perm1 ? 1 : 0; key.sym = sym ? 1 : 0; key.rank = g_shard_rank; key.world = g_shard_world;
+            key.window = window ? 1 : 0; key.pad = sentinel;
+            PrepEnt *pe = nullptr;
+            if (cacheable) {
+                if (!g_prep_cache) g_prep_cache = new std::vector<PrepEnt *>();
+                for (PrepEnt *e : *g_prep_cache) if (e->ready && memcmp(&e->key, &key, sizeof(key)) == 0) { pe = e; break; }
+            }
+            if (pe) {
+                if (pe->ws.st != st) {
+                    HTB_CUDA(cudaStreamWaitEvent(st, pe->ready, 0));
+                    if (std::find(pe->users.begin(), pe->users.end(), st) == pe->users.end()) pe->users.push_back(st);
+                }
+                s1 = pe->s1; s2 = pe->s2; range_dev = pe->range_dev; work_dev = pe->work_dev; nc1 = pe->nc1;
+            } else {
+                PrepEnt *ne = nullptr;
+                if (cacheable) {
+                    ne = new PrepEnt();
+                    ne->key = key; ne->ws.st = st; ne->ready = nullptr; ne->range_dev = nullptr; ne->work_dev = nullptr; ne->nc1 = 0;
+                    g_prep_cache->push_back(ne);             // (owned by the cache from here on: freed by htb_cache_end)
+                }
+                Workspace &w = ne ? ne->ws : ws;
+                if (!sym && htb_sort_begin(st, w, g1, d1, ds1, n1, dw1, nw, perm1, s1, &launches)) return 1;
+                if (htb_sort_begin(st, w, g2, d2, ds2, n2, dw2, nw, sym ? perm1 : false, s2, &launches)) return 1;
+                double *balance_dev = nullptr;
+                if (htb_reference_work(st, w, G, sym ? s2 : s1, s2, &work_dev, &balance_dev, &nc1, &launches, true)) return 1;
+                if (w.alloc((void **)&range_dev, 2 * sizeof(long long))) return 1;
+                const int64_t lo = first_cell1 < 0 ? 0 : first_cell1, hi = last_cell1 > nc1 ? nc1 : last_cell1;
+                if (htb_shard_range(st, balance_dev, lo, hi, g_shard_rank, g_shard_world, range_dev, &launches)) return 1;
+                int *xwin = nullptr;
+                if (w.alloc((void **)&xwin, 4 * sizeof(int))) return 1;
+                if (htb_shard_windows(st, range_dev, G, xwin, &launches)) return 1;
+                if (!sym && htb_sort_finish(st, w, d1, ds1, dw1, nw, sentinel, window ? xwin : nullptr, s1, &launches)) return 1;
+                if (htb_sort_finish(st, w, d2, ds2, dw2, nw, sentinel, window ? xwin + 2 : nullptr, s2, &launches)) return 1;
+                if (sym) s1 = s2;
+                if (ne) {
+                    ne->s1 = s1; ne->s2 = s2; ne->range_dev = range_dev; ne->work_dev = work_dev; ne->nc1 = nc1;
+                    HTB_CUDA(cudaEventCreateWithFlags(&ne->ready, cudaEventDisableTiming));
+                    HTB_CUDA(cudaEventRecord(ne->ready, st));
+                }
+            }
         } else if (sym) {
             if (sorted(g2, d2, ds2, n2, dw2, nw, perm1, sentinel, stable2, s2)) return 1;
             s1 = s2;
@@ -864,6 +944,7 @@ struct Call {
             if (sorted(g1, d1, ds1, n1, dw1, nw, perm1, sentinel, stable1, s1)) return 1;
             if (sorted(g2, d2, ds2, n2, dw2, nw, false, sentinel, stable2, s2)) return 1;
         }
+        if (fl & HTB_FLAG_PREPARE) { prepared = true; return 0; }
         // ---- tiles + counters
         uint2 *tiles = nullptr;
         uint32_t *ntiles_dev = nullptr;
@@ -1196,6 +1277,7 @@ extern "C" int htb_npairs_3d_engine(const htb_mesh_geom *mesh,
     const double *c1[3] = {x1, y1, z1}, *c2[3] = {x2, y2, z2};
     if (c.setup(mesh, 1, true, c1, stride1, n1, nullptr, c2, stride2, n2, nullptr, 0, false, first_cell1, last_cell1, flags,
                 fast ? 32 * htb_fast3_ppl() : HTB_TILE, fast ? 8.0 * lmax : 1.0e150)) return 1;
+    if (c.prepared) return 0;
     unsigned long long *counts_dev = nullptr;
     if (c.ws.alloc((void **)&counts_dev, sizeof(unsigned long long) * (size_t)nb)) return 1;
     HTB_CUDA(cudaMemsetAsync(counts_dev, 0, sizeof(unsigned long long) * (size_t)nb, c.st));
@@ -1250,6 +1332,7 @@ extern "C" int htb_npairs_xy_z_engine(const htb_mesh_geom *mesh,
     const double *c1[3] = {x1, y1, z1}, *c2[3] = {x2, y2, z2};
     if (c.setup(mesh, 0, true, c1, stride1, n1, nullptr, c2, stride2, n2, nullptr, 0, false, first_cell1, last_cell1, flags,
                 fast ? 32 * htb_fast3_ppl() : HTB_TILE, fast ? 8.0 * lmax : 1.0e150)) return 1;
+    if (c.prepared) return 0;
     unsigned long long *counts_dev = nullptr;
     if (c.ws.alloc((void **)&counts_dev, sizeof(unsigned long long) * (size_t)nh)) return 1;
     HTB_CUDA(cudaMemsetAsync(counts_dev, 0, sizeof(unsigned long long) * (size_t)nh, c.st));
@@ -1307,6 +1390,7 @@ extern "C" int htb_npairs_s_mu_engine(const htb_mesh_geom *mesh,
     if (c.begin(flags)) return 1;
     const double *c1[3] = {x1, y1, z1}, *c2[3] = {x2, y2, z2};
     if (c.setup(mesh, 1, true, c1, stride1, n1, nullptr, c2, stride2, n2, nullptr, 0, false, first_cell1, last_cell1, flags)) return 1;
+    if (c.prepared) return 0;
     std::vector<double> e((size_t)ns + nmu);
     double m0 = -INFINITY, m1 = -INFINITY;
     for (int k = 0; k < ns; ++k) { e[k] = s_bins[k] * s_bins[k]; if (e[k] > m0) m0 = e[k]; }
@@ -1365,6 +1449,7 @@ extern "C" int htb_marked_npairs_3d_engine(const htb_mesh_geom *mesh,
     const double *c1[3] = {x1, y1, z1}, *c2[3] = {x2, y2, z2};
     if (c.setup(mesh, 1, fast && w1 == w2, c1, stride1, n1, w1, c2, stride2, n2, w2, nw, false, first_cell1, last_cell1, flags,
                 HTB_TILE, fast ? 8.0 * lmax : 1.0e150)) return 1;
+    if (c.prepared) return 0;
     if (fast) {
         double *fs = nullptr;
         if (c.ws.alloc((void **)&fs, sizeof(double) * (HTB_NBF + 1))) return 1;
@@ -1430,6 +1515,7 @@ extern "C" int htb_marked_npairs_xy_z_engine(const htb_mesh_geom *mesh,
     if (c.begin(flags)) return 1;
     const double *c1[3] = {x1, y1, z1}, *c2[3] = {x2, y2, z2};
     if (c.setup(mesh, 0, false, c1, stride1, n1, w1, c2, stride2, n2, w2, nw, false, first_cell1, last_cell1, flags)) return 1;
+    if (c.prepared) return 0;
     return run_binq_weighted(c, 1, nw, weight_func_id, e.data(), nrp, e.data() + nrp, npi, counts_out, stats);
     HTB_GUARD_END
 }
@@ -1456,6 +1542,7 @@ extern "C" int htb_weighted_npairs_xy_engine(const htb_mesh_geom *mesh,
     if (c.begin(flags)) return 1;
     const double *c1[3] = {x1, y1, nullptr}, *c2[3] = {x2, y2, nullptr};
     if (c.setup(mesh, 1, false, c1, stride1, n1, nullptr, c2, stride2, n2, w2, 1, false, first_cell1, last_cell1, flags)) return 1;
+    if (c.prepared) return 0;
     // few bins: lane-private rows + a warp reduction per tile (MODE 5) instead of shared-memory atomics on a handful of cells
     return run_binq_weighted(c, 3, 1, -1, e.data(), nrp, nullptr, 1, counts_out, stats, nrp <= 48 ? 5 : 1);
     HTB_GUARD_END
@@ -1482,6 +1569,7 @@ extern "C" int htb_weighted_npairs_per_object_xy_engine(const htb_mesh_geom *mes
     if (c.begin()) return 1;
     const double *c1[3] = {x1, y1, nullptr}, *c2[3] = {x2, y2, nullptr};
     if (c.setup(mesh, 1, false, c1, stride1, n1, nullptr, c2, stride2, n2, w2, 1, true, first_cell1, last_cell1, flags)) return 1;
+    if (c.prepared) return 0;
     BinQParams bp{};
     if (binq_prepare(c, e.data(), nrp, nullptr, 1, &bp)) return 1;
     const size_t nout = (size_t)(n1 > 0 ? n1 : 1) * (size_t)nrp;
@@ -1519,6 +1607,7 @@ extern "C" int htb_npairs_per_object_3d_engine(const htb_mesh_geom *mesh,
     if (c.begin()) return 1;
     const double *c1[3] = {x1, y1, z1}, *c2[3] = {x2, y2, z2};
     if (c.setup(mesh, 1, false, c1, stride1, n1, nullptr, c2, stride2, n2, nullptr, 0, true, first_cell1, last_cell1, flags)) return 1;
+    if (c.prepared) return 0;
     BinQParams bp{};
     if (binq_prepare(c, e.data(), nb, nullptr, 1, &bp)) return 1;
     const size_t nout = (size_t)(n1 > 0 ? n1 : 1) * (size_t)nb;
@@ -1562,6 +1651,7 @@ static int jackknife_pass(const htb_mesh_geom *mesh, int kind, bool swapped,
     Call c;
     if (c.begin()) return 1;
     if (c.setup(mesh, kind == 0 ? 1 : 0, false, ca, sa, na, pa, cb, sb, nb_, pb, 2, false, first, last, flags)) return 1;
+    if (c.prepared) return 0;
     BinQParams bp{};
     if (binq_prepare(c, e0, n0, e1, n1, &bp)) return 1;
     const size_t nh = (size_t)n0 * n1, nt = (size_t)(nsamples + 1) * nh;
@@ -1782,6 +1872,7 @@ extern "C" int htb_mean_delta_sigma_engine(const htb_mesh_geom *mesh,
     }
     if (c.setup(mesh, 1, false, c1, stride1, n1, nullptr, c2, stride2, n2, uniform ? nullptr : m2, uniform ? 0 : 1, true,
                 first_cell1, last_cell1, flags, fast ? 32 : HTB_TILE, fast ? 8.0 * lmax : 1.0e150, ring ? 1 : 0)) return 1;
+    if (c.prepared) return 0;
     const int nbin = nrp - 1;
     std::vector<double> e((size_t)nrp + nbin);
     for (int k = 0; k < nrp; ++k) e[k] = rp_bins[k] * rp_bins[k];
@@ -2126,6 +2217,7 @@ extern "C" int htb_cell1_work(const htb_mesh_geom *mesh,
     if (c.begin()) return 1;
     const double *c1[3] = {x1, y1, z1}, *c2[3] = {x2, y2, z2};
     if (c.setup(mesh, 1, false, c1, stride1, n1, nullptr, c2, stride2, n2, nullptr, 0, false, 0, 0, flags)) return 1;
+    if (c.prepared) return 0;
     double *work_dev = nullptr;
     int64_t nc1 = 0;
     if (htb_reference_work(c.st, c.ws, c.G, c.s1, c.s2, &work_dev, nullptr, &nc1, &c.launches)) return 1;

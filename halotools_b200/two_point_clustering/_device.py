@@ -73,6 +73,7 @@ class DeviceStatistic(object):
         self.estimators = []
         self.multi = False      # engine calls on side streams (all samples device resident)
         self.forked = []
+        self.deferred = []
 
     def inputs(self, periodic, *samples):
         """Bring the statistic's samples to the device once (None entries and repeated objects keep their identity).
@@ -113,14 +114,38 @@ class DeviceStatistic(object):
         if side not in self.forked:
             side.wait_stream(self.stream)          # the samples and the zeroed tables were produced on the main stream
             self.forked.append(side)
+        if k == 0:
+            # the first count runs at once (set-up + count kernel): the set-ups of the others overlap with it
+            self._enqueue(side, _lib.FLAG_EARLY_EXIT, enqueue, out, args, kwargs)
+            return out
+        # the other counts: set-up only for now (HTB_FLAG_PREPARE: upload / mesh sorts / multi-GPU cut, kept in the
+        # library's caches until the end of this statistic's upload_cache scope); their count kernels are launched by
+        # launch() once EVERY set-up is enqueued, each behind all of them - otherwise the mesh sort of a later count can
+        # sit for the whole length of an earlier persistent count kernel that holds every SM
+        self._enqueue(side, _lib.FLAG_PREPARE, enqueue, out, args, kwargs)
+        ev = self.torch.cuda.Event()
+        ev.record(side)
+        self.deferred.append((side, ev, enqueue, out, args, kwargs))
+        return out
+
+    def _enqueue(self, side, flag, enqueue, out, args, kwargs):
         saved = _lib.stream_flags
-        _lib.stream_flags = saved | _lib.FLAG_EARLY_EXIT        # idle warps retire: the next count's blocks fill the tail
+        _lib.stream_flags = saved | flag
         try:
             with self.torch.cuda.stream(side), _lib.use_stream(side):
                 self.keep.append(enqueue(out, *args, **kwargs))
         finally:
             _lib.stream_flags = saved
-        return out
+
+    def launch(self):
+        """The count kernels of the deferred counts, each on its stream behind the set-ups of all of them
+        (HTB_FLAG_EARLY_EXIT: idle warps retire, so the blocks of the next kernel fill the tail of the running one)."""
+        deferred, self.deferred = self.deferred, []
+        for side, _, enqueue, out, args, kwargs in deferred:
+            for other, ev, _e, _o, _a, _k in deferred:
+                if other is not side:
+                    side.wait_event(ev)
+            self._enqueue(side, _lib.FLAG_EARLY_EXIT, enqueue, out, args, kwargs)
 
     def analytic(self, array):
         """Differential float counts computed on the host (analytic randoms) -> device row."""
@@ -136,6 +161,7 @@ class DeviceStatistic(object):
         if self.reduced:
             return
         self.reduced = True
+        self.launch()
         for side in self.forked:
             self.stream.wait_stream(side)
         rank, world = _dist._rank_world()

@@ -51,6 +51,10 @@ extern "C" {
                                        npairs_s_mu, marked_npairs_3d, marked_npairs_xy_z, weighted_npairs_xy, mean_delta_sigma.      */
 #define HTB_FLAG_EARLY_EXIT 2048u  /* warps of the counting kernel that run out of work retire at once instead of waiting to help with late exact
                                        re-evaluations: lets the next kernel, enqueued on ANOTHER stream, fill this launch's tail (results unchanged) */
+#define HTB_FLAG_PREPARE 4096u     /* run only the set-up of the call (upload, mesh sorts, multi-GPU cut) inside an htb_cache_begin/end scope and
+                                       return: the same call without the flag then finds its sorted samples in the caches.  A statistic prepares
+                                       all its counts first and launches the count kernels afterwards, so that no mesh sort waits behind a
+                                       persistent count kernel that holds every SM */
 #define HTB_FLAG_NO_SYM       16u  /* auto-correlations: evaluate (i,j) and (j,i) separately, as the reference does */
 #define HTB_FLAG_PARTITION_SUM 512u /* [first_cell1, last_cell1) is one part of a partition of the mesh1 cells whose results the
                                        caller SUMS (multi-GPU shards): auto-correlations may then keep the symmetric shortcut
