@@ -449,14 +449,23 @@ def measure_c5(env, args, sampler, steps=None, warmup=None):
     torch.cuda.synchronize()
     acc = {}
 
+    def stats_pass():
+        # UNTIMED: the same call with the ranks' results left un-reduced, i.e. as a synchronous engine call that fills the
+        # work counters and the CUDA-event time of the count kernel (multi-GPU steps leave their sums on the device and
+        # return no per-call statistics)
+        from halotools_b200 import distributed
+        with distributed.local_counts():
+            hb.mean_delta_sigma(gal_d, ptcl_d, 1.0, rp, period=L)
+            acc.update(_lib.last_stats)
+
     def step_resident():
-        r = hb.mean_delta_sigma(gal_d, ptcl_d, 1.0, rp, period=L)
-        acc.update(_lib.last_stats)
-        return r
+        return hb.mean_delta_sigma(gal_d, ptcl_d, 1.0, rp, period=L)
 
     def step_e2e():
         return hb.mean_delta_sigma(gal_np, ptcl_np, 1.0, rp, period=L)
 
+    stats_pass()
+    stats_pass()
     if sampler is not None:
         sampler.start()
     ms_step, res = env.timed(step_resident, steps, warmup)

@@ -328,7 +328,7 @@ static FineGrid make_grid(const htb_mesh_geom *g, int which, const int *m)
 // cudaMemcpyAsync from pageable memory goes through the driver's single bounce buffer (about 2 GB/s measured on
 // the B200 boxes).  Large pageable inputs are therefore packed by a few host threads into a ring of pinned
 // chunks (de-interleaving strided columns on the way) and copied chunk by chunk on per-thread streams.
-#define HTB_STAGE_THREADS 8
+#define HTB_STAGE_THREADS 16
 #define HTB_STAGE_CHUNK (256 * 1024)          // elements per column and chunk
 struct StagePool {
     double *pinned[HTB_STAGE_THREADS][2] = {{nullptr}};
@@ -377,7 +377,8 @@ static int staged_upload(cudaStream_t st, const double *const *src, int cnt, int
     StagePool &sp = g_stage[dev];
     const int64_t nchunk = (n + HTB_STAGE_CHUNK - 1) / HTB_STAGE_CHUNK;
     int nthreads = (int)std::min<int64_t>(HTB_STAGE_THREADS, nchunk);
-    const unsigned hw = std::thread::hardware_concurrency();
+    unsigned hw = std::thread::hardware_concurrency();
+    if (hw > 0 && g_shard_world > 1) hw = std::max(2u, hw / (unsigned)g_shard_world);     // one process per GPU shares the host's cores
     if (hw > 0 && (unsigned)nthreads > hw) nthreads = (int)hw;
     // the destination blocks come from the stream-ordered pool of `st`: they may still be in use by work enqueued
     // earlier on `st` (asynchronous calls), so the copy streams start behind everything `st` holds now
@@ -431,7 +432,8 @@ static int staged_download(cudaStream_t st, const double *src_dev, double *dst, 
     HTB_CUDA(cudaEventRecord(ready, st));
     const int64_t nchunk = (n + HTB_STAGE_CHUNK - 1) / HTB_STAGE_CHUNK;
     int nthreads = (int)std::min<int64_t>(HTB_STAGE_THREADS, nchunk);
-    const unsigned hw = std::thread::hardware_concurrency();
+    unsigned hw = std::thread::hardware_concurrency();
+    if (hw > 0 && g_shard_world > 1) hw = std::max(2u, hw / (unsigned)g_shard_world);     // one process per GPU shares the host's cores
     if (hw > 0 && (unsigned)nthreads > hw) nthreads = (int)hw;
     std::atomic<int> failed(0);
     auto work = [&](int t) {

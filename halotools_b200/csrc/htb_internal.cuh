@@ -53,8 +53,7 @@ struct SortedSample {
     uint32_t *perm = nullptr;   // [n] sorted position -> input index
     uint32_t *flags = nullptr;  // [1] bit0: some point lies outside [0, period] in some dimension
     uint32_t *cell = nullptr;   // scratch [n]: fine cell id per input point
-    uint32_t *rank = nullptr;   // scratch [n]: arrival rank inside the cell
-    uint32_t *count = nullptr;  // scratch [ncells + 2]: points per fine cell
+    uint32_t *count = nullptr;  // scratch [ncells + 2]: points per fine cell (after the sort: the cells' fill counters)
 };
 
 struct Workspace;   // stream-ordered allocations of one engine call (freed at the end)

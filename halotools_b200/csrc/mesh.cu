@@ -3,9 +3,14 @@
 //
 // Replaces RectangularMesh.__init__ (digitize -> argsort -> searchsorted,
 // /root/reference/halotools/mock_observables/pair_counters/rectangular_mesh.py:118-222)
-// by: k_assign (cell id + arrival rank through one atomicAdd per point), a 3-pass
-// exclusive scan of the per-cell counts, and k_scatter.  O(N) HBM traffic:
-// read 24 B + write 8 B per point in k_assign, read 32 B + write 28 B(+payload) in k_scatter.
+// by: k_assign (fine cell id of every point + points per cell through fire-and-forget atomics: RED, no round trip), a
+// 3-pass exclusive scan of the per-cell counts, and k_scatter (position = first position of the cell + arrival rank from
+// one returning atomic on the cell's fill counter).  O(N) HBM traffic: read 24 B + write 4 B per point in k_assign, read
+// 28 B + write 24 B (+ payload) in k_scatter.  1e8 particles (2-D): 7.6 ms (round 1, with the arrival rank taken and stored
+// in k_assign: 10.4 ms).  A two-pass variant (block-local partition into <= 256 buckets of consecutive cells, then an
+// L2-resident scatter per bucket) was measured at 10.7 ms and dropped: the returning atomics, not the scattered 8-byte
+// writes, are what the scatter waits for.
+#include <cstdlib>
 #include "htb_internal.cuh"
 
 #define SCAN_THREADS 256
@@ -15,7 +20,7 @@
 template <int DIM>
 __global__ void __launch_bounds__(256)
 k_assign(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z,
-         int64_t stride, int64_t n, FineGrid g, uint32_t *__restrict__ cell, uint32_t *__restrict__ rank,
+         int64_t stride, int64_t n, FineGrid g, uint32_t *__restrict__ cell,
          uint32_t *__restrict__ count, uint32_t *__restrict__ flags)
 {
     const double *src[3] = {x, y, z};
@@ -36,29 +41,39 @@ k_assign(const double *__restrict__ x, const double *__restrict__ y, const doubl
             cid = cid * (uint32_t)g.nf[d] + (uint32_t)f;
         }
         cell[i] = cid;
-        rank[i] = atomicAdd(&count[cid], 1u);
+        atomicAdd(&count[cid], 1u);                   // result unused: a RED, no round trip
     }
     if (bad) atomicOr(flags, 1u);
 }
 
+#define PART_THREADS 256
+#define PART_ITEMS 8
+#define PART_CHUNK (PART_THREADS * PART_ITEMS)
+
+// every point to its cell: pos = first position of the cell + arrival rank (one returning atomic on the cell's fill counter)
 template <int DIM>
-__global__ void __launch_bounds__(256)
-k_scatter(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z,
-          int64_t stride, int64_t n, const uint32_t *__restrict__ cell, const uint32_t *__restrict__ rank,
-          const uint32_t *__restrict__ off, double *__restrict__ ox, double *__restrict__ oy,
-          double *__restrict__ oz, uint32_t *__restrict__ perm,
-          const double *__restrict__ w, double *__restrict__ ow, int nw)
+__global__ void __launch_bounds__(PART_THREADS)
+k_scatter(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z, int64_t stride, int64_t n,
+          const uint32_t *__restrict__ cell, const uint32_t *__restrict__ off, uint32_t *__restrict__ fill,
+          double *__restrict__ ox, double *__restrict__ oy, double *__restrict__ oz,
+          uint32_t *__restrict__ perm, const double *__restrict__ w, double *__restrict__ ow, int nw)
 {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const uint32_t cid = cell[i];
-        const uint32_t pos = off[cid] + rank[i];
-        if (off[cid + 1] == off[cid]) continue;       // the cell was emptied: outside this rank's window (htb_sort_finish)
-        ox[pos] = x[i * stride];
-        oy[pos] = y[i * stride];
-        if (DIM == 3) oz[pos] = z[i * stride];
-        if (perm) perm[pos] = (uint32_t)i;
-        if (ow) {
-            for (int k = 0; k < nw; ++k) ow[(int64_t)pos * nw + k] = w[i * nw + k];
+    const int64_t nchunk = (n + PART_CHUNK - 1) / PART_CHUNK;
+    for (int64_t c = blockIdx.x; c < nchunk; c += gridDim.x) {
+#pragma unroll
+        for (int k = 0; k < PART_ITEMS; ++k) {
+            const int64_t i = c * PART_CHUNK + (int64_t)k * PART_THREADS + threadIdx.x;
+            if (i >= n) continue;
+            const uint32_t cid = cell[i];
+            if (off[cid + 1] == off[cid]) continue;       // the cell was emptied: outside this rank's window (htb_sort_finish)
+            const uint32_t pos = off[cid] + atomicAdd(&fill[cid], 1u);
+            ox[pos] = x[i * stride];
+            oy[pos] = y[i * stride];
+            if (DIM == 3) oz[pos] = z[i * stride];
+            if (perm) perm[pos] = (uint32_t)i;
+            if (ow) {
+                for (int q = 0; q < nw; ++q) ow[(int64_t)pos * nw + q] = w[i * nw + q];
+            }
         }
     }
 }
@@ -221,16 +236,15 @@ int htb_sort_begin(cudaStream_t st, Workspace &ws, const FineGrid &g,
     if (keep_perm && ws.alloc((void **)&out.perm, sizeof(uint32_t) * (size_t)(n > 0 ? n : 1))) return 1;
     if (w_dev && ws.alloc((void **)&out.w, sizeof(double) * (size_t)((n > 0 ? n : 1) * nw + 2))) return 1;
     if (ws.alloc((void **)&out.cell, sizeof(uint32_t) * (size_t)(n > 0 ? n : 1))) return 1;
-    if (ws.alloc((void **)&out.rank, sizeof(uint32_t) * (size_t)(n > 0 ? n : 1))) return 1;
     if (ws.alloc((void **)&out.count, sizeof(uint32_t) * (size_t)(g.ncells + 2))) return 1;
     HTB_CUDA(cudaMemsetAsync(out.count, 0, sizeof(uint32_t) * (size_t)(g.ncells + 2), st));
     HTB_CUDA(cudaMemsetAsync(out.flags, 0, sizeof(uint32_t) * 4, st));
     if (n > 0) {
         const int blocks = grid_for(n, 256);
         if (g.dim == 3)
-            k_assign<3><<<blocks, 256, 0, st>>>(cd[0], cd[1], cd[2], stride, n, g, out.cell, out.rank, out.count, out.flags);
+            k_assign<3><<<blocks, 256, 0, st>>>(cd[0], cd[1], cd[2], stride, n, g, out.cell, out.count, out.flags);
         else
-            k_assign<2><<<blocks, 256, 0, st>>>(cd[0], cd[1], nullptr, stride, n, g, out.cell, out.rank, out.count, out.flags);
+            k_assign<2><<<blocks, 256, 0, st>>>(cd[0], cd[1], nullptr, stride, n, g, out.cell, out.count, out.flags);
         if (launches) *launches += 1;
     }
     HTB_CUDA(cudaGetLastError());
@@ -250,13 +264,16 @@ int htb_sort_finish(cudaStream_t st, Workspace &ws, const double *const *cd, int
     // off[0..ncells] : exclusive scan over ncells+1 entries (the extra entry is zero) gives off[ncells] = points kept
     if (htb_exclusive_scan_u32(st, ws, out.count, out.off, g.ncells + 1, nullptr, launches)) return 1;
     if (n > 0) {
-        const int blocks = grid_for(n, 256);
+        // the per-cell counts have been scanned into `off`: the array now serves as the cells' fill counters
+        HTB_CUDA(cudaMemsetAsync(out.count, 0, sizeof(uint32_t) * (size_t)(g.ncells + 2), st));
+        const int64_t nchunk = (n + PART_CHUNK - 1) / PART_CHUNK;
+        const int blocks = (int)(nchunk < 148 * 8 ? nchunk : 148 * 8);
         if (g.dim == 3)
-            k_scatter<3><<<blocks, 256, 0, st>>>(cd[0], cd[1], cd[2], stride, n, out.cell, out.rank, out.off,
-                                                 out.c[0], out.c[1], out.c[2], out.perm, w_dev, out.w, nw);
+            k_scatter<3><<<blocks, PART_THREADS, 0, st>>>(cd[0], cd[1], cd[2], stride, n, out.cell, out.off, out.count,
+                                                          out.c[0], out.c[1], out.c[2], out.perm, w_dev, out.w, nw);
         else
-            k_scatter<2><<<blocks, 256, 0, st>>>(cd[0], cd[1], nullptr, stride, n, out.cell, out.rank, out.off,
-                                                 out.c[0], out.c[1], nullptr, out.perm, w_dev, out.w, nw);
+            k_scatter<2><<<blocks, PART_THREADS, 0, st>>>(cd[0], cd[1], nullptr, stride, n, out.cell, out.off, out.count,
+                                                          out.c[0], out.c[1], nullptr, out.perm, w_dev, out.w, nw);
         if (launches) *launches += 1;
     }
     k_pad<<<1, 32, 0, st>>>(out.c[0], out.c[1], g.dim == 3 ? out.c[2] : nullptr, n, out.npad, pad_value);

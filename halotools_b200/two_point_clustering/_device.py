@@ -24,6 +24,7 @@ from .tpcf_estimators import _ZERO_MSG, _list_estimators
 __all__ = ("DeviceStatistic", "available")
 
 MAX_TABLES = 6
+TIMELINE = None          # debugging: a list makes every enqueue append (what, stream index, torch event recorded behind it)
 SIDE_STREAMS = 3
 _side = {}
 
@@ -136,6 +137,10 @@ class DeviceStatistic(object):
                 self.keep.append(enqueue(out, *args, **kwargs))
         finally:
             _lib.stream_flags = saved
+        if TIMELINE is not None:
+            ev = self.torch.cuda.Event(enable_timing=True)
+            ev.record(side)
+            TIMELINE.append(("prepare" if flag == _lib.FLAG_PREPARE else "count", _side_streams(self.torch).index(side), ev))
 
     def launch(self):
         """The count kernels of the deferred counts, each on its stream behind the set-ups of all of them
