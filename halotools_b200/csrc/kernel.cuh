@@ -64,6 +64,20 @@ k_count(const __grid_constant__ WalkGeom G, const __grid_constant__ WalkArrays A
     const int itemsA = nA * KA;
     const int nitems = itemsA + nB * KB;
 
+    // HTB_FLAG_EARLY_EXIT (several count kernels of a statistic in flight on different streams): a launch whose items
+    // do not divide evenly over the resident warps ends with a round in which most warps idle - e.g. 4.2 tiles per warp
+    // on one rank of 8 take the time of 5.  The surplus blocks give their SM slots away AT ONCE instead: with `rounds`
+    // = ceil(items / warps), ceil(items / (rounds - 1/4)) warps finish in the same number of rounds, and the blocks beyond
+    // them retire before they start, so the next kernel's blocks (and its set-up kernels) run beside this one for its whole
+    // length rather than squeezing into its tail.
+    if (G.early_exit && nitems > 0 && V::WARPS * (long long)gridDim.x > 0) {
+        const long long Wt = (long long)gridDim.x * V::WARPS;
+        const long long rounds = (nitems + Wt - 1) / Wt;
+        const long long needed = (4LL * nitems + (4 * rounds - 1) - 1) / (4 * rounds - 1);
+        const long long blocks_needed = (needed + V::WARPS - 1) / V::WARPS;
+        if ((long long)blockIdx.x >= blocks_needed) return;
+    }
+
     // One work item: slice `slice` of `nsl` of tile t.  redo_sub < 0: the normal evaluation (both weight passes in
     // symmetric mode).  A fast kernel that finds it cannot decide a tile from its 32-bit keys asks for an exact
     // re-evaluation (tile_end returns true): that re-evaluation is many times slower per pair, so it is not done

@@ -14,6 +14,7 @@ The numpy estimators of ``tpcf_estimators.py`` remain for the jackknife statisti
 sub-volume) and as the host restatement the CPU tests of the driver logic run.
 """
 import ctypes
+import os
 
 import numpy as np
 
@@ -81,7 +82,6 @@ class DeviceStatistic(object):
         Host samples that cannot be copied as they are (other dtypes, strided views), and the samples of a NON-periodic
         call (the front-ends shift those into an enclosing box on the host, mesh_helpers.py:17-64), stay on the host: the
         engines then upload them themselves (upload cache) and the calls share one stream."""
-        import os
         if not periodic:
             return tuple(samples)
         distinct = {}
@@ -115,7 +115,7 @@ class DeviceStatistic(object):
         if side not in self.forked:
             side.wait_stream(self.stream)          # the samples and the zeroed tables were produced on the main stream
             self.forked.append(side)
-        if k == 0:
+        if k == 0 and not os.environ.get("HTB_PREPARE_ALL"):
             # the first count runs at once (set-up + count kernel): the set-ups of the others overlap with it
             self._enqueue(side, _lib.FLAG_EARLY_EXIT, enqueue, out, args, kwargs)
             return out
