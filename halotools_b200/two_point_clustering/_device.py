@@ -7,9 +7,11 @@ engine's CUDA stream (HTB_FLAG_DEVICE_OUTPUT) and writes its cumulative table in
 tables are summed by ONE all-reduce issued on the same stream (NCCL through torch.distributed: plumbing), the estimator
 kernel (htb_tp_estimator) reads the summed tables, and the host waits ONCE, for the D2H copy of xi and of the
 zero-division flags.  Host samples are brought to the device ONCE per statistic (each rank 1/world of the rows + an
-all-gather, ``distributed.to_device``), and the engine calls then run on SEPARATE streams: every count kernel is a
-persistent grid whose last tiles leave most of the GPU idle for about one tile time (0.5-1 ms); with the next count's
-blocks waiting on another stream that tail is filled instead of wasted (it is 10 % of a rank's step on 8 GPUs).
+all-gather, ``distributed.to_device``), and the engine calls then run on SEPARATE streams, the largest count first: every
+count kernel is a persistent grid whose last, partly filled round of tiles leaves SM slots idle (4.2 tiles per warp on one
+rank of 8 take the time of 5); with HTB_FLAG_EARLY_EXIT the surplus blocks retire at once and idle warps do not linger, so
+the set-up and count kernels of the smaller counts run in those slots.  Orders and set-up / count splits that were
+measured and lost (issue order, all set-ups first, the smaller counts' set-ups first) are listed in DESIGN.md section 5.
 The numpy estimators of ``tpcf_estimators.py`` remain for the jackknife statistics (rows per
 sub-volume) and as the host restatement the CPU tests of the driver logic run.
 """
@@ -111,22 +113,9 @@ class DeviceStatistic(object):
             with self.torch.cuda.stream(self.stream):
                 self.keep.append(enqueue(out, *args, **kwargs))
             return out
-        side = _side_streams(self.torch)[k % SIDE_STREAMS]
-        if side not in self.forked:
-            side.wait_stream(self.stream)          # the samples and the zeroed tables were produced on the main stream
-            self.forked.append(side)
-        if k == 0 and not os.environ.get("HTB_PREPARE_ALL"):
-            # the first count runs at once (set-up + count kernel): the set-ups of the others overlap with it
-            self._enqueue(side, _lib.FLAG_EARLY_EXIT, enqueue, out, args, kwargs)
-            return out
-        # the other counts: set-up only for now (HTB_FLAG_PREPARE: upload / mesh sorts / multi-GPU cut, kept in the
-        # library's caches until the end of this statistic's upload_cache scope); their count kernels are launched by
-        # launch() once EVERY set-up is enqueued, each behind all of them - otherwise the mesh sort of a later count can
-        # sit for the whole length of an earlier persistent count kernel that holds every SM
-        self._enqueue(side, _lib.FLAG_PREPARE, enqueue, out, args, kwargs)
-        ev = self.torch.cuda.Event()
-        ev.record(side)
-        self.deferred.append((side, ev, enqueue, out, args, kwargs))
+        # multi-stream mode: nothing is enqueued yet - launch() issues the counts largest first
+        a, b = args[0], args[1]
+        self.deferred.append((int(a.shape[0]) * int(b.shape[0]), k, enqueue, out, args, kwargs))
         return out
 
     def _enqueue(self, side, flag, enqueue, out, args, kwargs):
@@ -143,14 +132,22 @@ class DeviceStatistic(object):
             TIMELINE.append(("prepare" if flag == _lib.FLAG_PREPARE else "count", _side_streams(self.torch).index(side), ev))
 
     def launch(self):
-        """The count kernels of the deferred counts, each on its stream behind the set-ups of all of them
-        (HTB_FLAG_EARLY_EXIT: idle warps retire, so the blocks of the next kernel fill the tail of the running one)."""
+        """Multi-stream mode: every count is one engine call (set-up + persistent count kernel) on its own stream, the
+        LARGEST first (HTB_FLAG_EARLY_EXIT: the surplus blocks of a launch retire at once and idle warps do not wait, so the
+        set-up kernels and count kernels of the smaller counts run beside the big one - in the SM slots its last,
+        partly filled round of tiles would have left idle - instead of before or after it)."""
         deferred, self.deferred = self.deferred, []
-        for side, _, enqueue, out, args, kwargs in deferred:
-            for other, ev, _e, _o, _a, _k in deferred:
-                if other is not side:
-                    side.wait_event(ev)
-            self._enqueue(side, _lib.FLAG_EARLY_EXIT, enqueue, out, args, kwargs)
+        if not os.environ.get("HTB_ISSUE_ORDER"):
+            deferred.sort(key=lambda d: -d[0])
+        sides = []
+        for i in range(len(deferred)):
+            side = _side_streams(self.torch)[i % SIDE_STREAMS]
+            if side not in self.forked:
+                side.wait_stream(self.stream)      # the samples and the zeroed tables were produced on the main stream
+                self.forked.append(side)
+            sides.append(side)
+        for i, (_size, _k, enqueue, out, args, kwargs) in enumerate(deferred):
+            self._enqueue(sides[i], _lib.FLAG_EARLY_EXIT, enqueue, out, args, kwargs)
 
     def analytic(self, array):
         """Differential float counts computed on the host (analytic randoms) -> device row."""

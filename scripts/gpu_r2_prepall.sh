@@ -1,7 +1,7 @@
 #!/bin/bash
 set -u
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
-for V in "HTB_PREPARE_ALL=" "HTB_PREPARE_ALL=1"; do
+for V in "HTB_PREPARE_SMALL=1"; do
   echo "== $V"
   env $V timeout 600 python scripts/gpu_r2_timeline.py 2>&1 | tail -16
   env $V timeout 600 python scripts/gpu_shardsim_stat.py 1,8 2>/dev/null | python -c "
