@@ -233,6 +233,18 @@ xi = hb.tpcf(*targs, **tkw)
 want = np.load(%(root)r + "/tests/golden/golden.npz")["tpcf_randoms_Landy-Szalay/0"]
 assert np.allclose(xi, want, rtol=1e-10, atol=1e-12), (xi, want)
 assert len(calls) == 3 and all(c[0] < c[1] for c in calls)
+# a rank that fails inside a statistic does not leave its peer waiting in the all-reduce: both raise (ADVICE r1)
+try:
+    with distributed.local_counts() as partial:
+        partial.add(np.zeros(3))
+        if int(sys.argv[1]) == 1:
+            raise ValueError("rank 1 failed")
+    failed = None
+except ValueError as e:
+    failed = "own"
+except RuntimeError as e:
+    failed = "peer" if "peer rank" in str(e) else str(e)
+assert failed == ("own" if int(sys.argv[1]) == 1 else "peer"), failed
 dist.destroy_process_group()
 print("rank", sys.argv[1], "ok", first, last)
 '''
