@@ -988,3 +988,31 @@ def test_input_step_on_the_device_is_the_host_function_bit_for_bit():
     a = hb.wp(pos_d, rp, 40.0, period=L)
     b = hb.wp(pos_h, rp, 40.0, period=L)
     assert np.array_equal(a, b)
+
+
+def test_fast_path_keeps_counts_for_separations_within_a_few_ulp_of_round_and_generic_edges():
+    # separations within a few ulp of an edge - round edges (squares with zero low bits: the edge sits at the bottom of
+    # its 32-bit key cell) and generic ones - must be decided exactly as the reference decides them
+    rng = np.random.RandomState(21)
+    n = 40000
+    s = rng.uniform(0, 60.0, (n, 3))
+    # pairs at (nearly) exactly the edge separations: partner = point + edge * unit vector, nudged by a few ulp
+    edges = np.array([0.5, 1.0, 2.0, 3.0, 5.0])
+    base = s[:2000].copy()
+    u = rng.normal(size=(2000, 3))
+    u /= np.linalg.norm(u, axis=1)[:, None]
+    part = np.mod(base + u * edges[rng.randint(0, 5, 2000)][:, None] * (1.0 + rng.randint(-4, 5, 2000)[:, None] * 2.2e-16), 60.0)
+    s2 = np.vstack([s, part])
+    for rb in (edges, edges * 1.0000001234, np.logspace(-0.5, 0.8, 12)):
+        want = oracle.npairs_3d(s2, s2, rb, period=60.0, num_threads=8)
+        got = hb.npairs_3d(s2, s2, rb, period=60.0)
+        assert _lib.last_stats["path"] == 1
+        assert np.array_equal(got, want), (rb, got, want)
+        wx = oracle.npairs_xy_z(s2, s, rb, [0.0, 7.0], period=60.0, num_threads=8)
+        gx = hb.npairs_xy_z(s2, s, rb, [0.0, 7.0], period=60.0)
+        assert np.array_equal(gx, wx)
+    w = rng.randint(1, 4, len(s2)).astype(float)
+    for rb in (edges, edges * 1.0000001234):
+        wm = oracle.marked_npairs_3d(s2, s2, rb, 1, period=60.0, weights1=w, weights2=w, num_threads=8)
+        gm = hb.marked_npairs_3d(s2, s2, rb, 1, period=60.0, weights1=w, weights2=w)
+        assert np.array_equal(gm, wm), (gm, wm)          # integer weights: exact
