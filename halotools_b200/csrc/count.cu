@@ -223,6 +223,7 @@ struct Fast3T {
     static constexpr int TOP = HTB_NBF - 1;
     static constexpr int QC = KIND == 1 ? QCAP - 16 : QCAP;       // (rp, pi): 16 rows go to the lower-pi-edge counters
     static constexpr uint32_t QFULL = 128u * (QC - QGROUP - PPL);     // flush when a lane's queue is longer than this
+    static constexpr bool HAS_SELF = true;
     typedef Fast3Params Params;
     const Params &P;
     uint32_t qbase;             // shared-space address of this lane's queue column
@@ -379,16 +380,33 @@ struct Fast3T {
         hmin = min(hmin, h);
         push(k);
     }
+    __device__ __forceinline__ double edge(int s) const { return __longlong_as_double((long long)P.E[s]); }
+    // c_s += (d <= e_s) for four levels: one DSETP and one predicated integer add each (the C form comes back from
+    // ptxas as add / predicated move / move per level)
+    static __device__ __forceinline__ void count4(unsigned &c0, unsigned &c1, unsigned &c2, unsigned &c3, double e0, double e1,
+                                                  double e2, double e3, double d)
+    {
+        asm("{\n\t.reg .pred p;\n\t"
+            "setp.le.f64 p, %8, %4;\n\t@p add.u32 %0, %0, 1;\n\t"
+            "setp.le.f64 p, %8, %5;\n\t@p add.u32 %1, %1, 1;\n\t"
+            "setp.le.f64 p, %8, %6;\n\t@p add.u32 %2, %2, 1;\n\t"
+            "setp.le.f64 p, %8, %7;\n\t@p add.u32 %3, %3, 1;\n\t}"
+            : "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3) : "d"(e0), "d"(e1), "d"(e2), "d"(e3), "d"(d));
+    }
+    __device__ __forceinline__ void count_levels(double d)
+    {
+        static_assert(HTB_NBF == 16, "four groups of four levels");
+#pragma unroll
+        for (int s = 0; s < HTB_NBF; s += 4) count4(c[s], c[s + 1], c[s + 2], c[s + 3], edge(s), edge(s + 1), edge(s + 2), edge(s + 3), d);
+    }
     __device__ __forceinline__ void pair_exact(int q, double xj, double yj, double zj)
     {
         const double dx = xs[q] - xj, dy = ys[q] - yj, dz = zs[q] - zj;
         if (KIND == 0) {
+            // f64 compares (DSETP, FP64 pipe) order the non-negative values here exactly like 64-bit integer compares of
+            // the bit patterns (two ISETP each on the half-rate ALU pipe)
             const double dsq = dx * dx + dy * dy + dz * dz;
-            const unsigned long long b = (unsigned long long)__double_as_longlong(dsq);
-            if (b <= P.E_top) {
-#pragma unroll
-                for (int s = 0; s < HTB_NBF; ++s) c[s] += (b <= P.E[s]) ? 1u : 0u;
-            }
+            if (dsq <= edge(HTB_NBF - 1)) count_levels(dsq);
         } else {
             const double dxy_sq = dx * dx + dy * dy;
             const double dz_sq = dz * dz;
@@ -397,9 +415,8 @@ struct Fast3T {
             // (the fast path requires bins >= 0) and inside both pi edges: counted once here, added to every counter at the
             // end of the tile - the per-edge loops below ran with ONE active lane for each of them (5 % of config 3)
             if ((b | (unsigned long long)__double_as_longlong(dz_sq)) == 0ULL) { zself += 1u; return; }
-            if (b <= P.E_top && dz_sq <= P.pi_top_sq) {
-#pragma unroll
-                for (int s = 0; s < HTB_NBF; ++s) c[s] += (b <= P.E[s]) ? 1u : 0u;
+            if (dxy_sq <= edge(HTB_NBF - 1) && dz_sq <= P.pi_top_sq) {
+                count_levels(dxy_sq);
                 if (P.counts0 && (unsigned long long)__double_as_longlong(dz_sq) <= P.Epi0) {
                     // also inside the lower pi edge
 #pragma unroll 1
@@ -436,10 +453,13 @@ struct Fast3T {
         }
         qsave = qptr; csave = ctop;
     }
-    __device__ __forceinline__ void chunk(uint32_t stage, int lo, int hi, uint32_t tok)
+    // own: the tile's own index range in symmetric mode.  Every group of it holds a self pair, i.e. would be pushed, taken
+    // back and re-evaluated exactly - and its pairs are close, nearly all of them in range, where counting against the
+    // edges directly is cheaper than the queue (measured: sending them through the queue costs +14 % on config 4).
+    __device__ __forceinline__ void chunk(uint32_t stage, int lo, int hi, uint32_t tok, bool own)
     {
         const uint32_t bx = stage, by = stage + 8 * HTB_CH, bz = stage + 16 * HTB_CH;
-        if (exact) { exact_range(stage, lo, hi); return; }
+        if (exact | own) { exact_range(stage, lo, hi); return; }
         int j = lo;
         if ((j & 1) && j < hi) {
             // odd leading entry: evaluated alone, checked together with the group that follows
@@ -963,7 +983,7 @@ __device__ __forceinline__ void add_if_neg(double &W, int key, double w)
 
 struct MarkedQ {
     static constexpr int DIM = 3, NPAY = 1, PPL = 2, WARPS = MQ_WARPS, MINBLOCKS = MQ_MINBLOCKS;
-    static constexpr bool TMA = true, WANTS_BASE = true;
+    static constexpr bool TMA = true, WANTS_BASE = true, HAS_SELF = true;
     static constexpr int GJ = MQ_GROUP / PPL;
     static constexpr int TOP = HTB_NBF - 1;
     static constexpr uint32_t QFULL = 256u * (MQ_QCAP - MQ_GROUP - PPL);
@@ -1129,21 +1149,39 @@ struct MarkedQ {
 #endif
         if (key <= P.F[TOP - 1]) { sts_kj(qptr, key, jtag); qptr += 256u; }
     }
+    // Five levels of the exact scan: if (dsq <= e_s && no lower level took the pair) a_s += w.  Per level one DSETP (the
+    // f64 compare orders non-negative values exactly like the 64-bit integer compare of their bit patterns, and runs on
+    // the FP64 pipe instead of two ISETP on the half-rate ALU pipe), the predicate as a 1.0 / 0.0 multiplier (one SEL), one
+    // DFMA (w * 1.0 is exact, w * 0.0 leaves the sum alone) and one predicate OR; the C version - and a predicated
+    // add.f64 as well - comes back from ptxas as an unconditional DADD and two FSEL, with two ISETP for the compare.
+    static __device__ __forceinline__ void levels5(double &a0, double &a1, double &a2, double &a3, double &a4, double e0, double e1,
+                                                   double e2, double e3, double e4, double d, double w, unsigned &below)
+    {
+        asm("{\n\t.reg .pred ad, bel;\n\t.reg .b32 h, z;\n\t.reg .f64 m;\n\t"
+            "mov.b32 z, 0;\n\tsetp.ne.u32 bel, %5, 0;\n\t"
+            "setp.le.and.f64 ad, %11, %6, !bel;\n\tselp.b32 h, 0x3ff00000, 0, ad;\n\tmov.b64 m, {z, h};\n\tfma.rn.f64 %0, %12, m, %0;\n\tor.pred bel, bel, ad;\n\t"
+            "setp.le.and.f64 ad, %11, %7, !bel;\n\tselp.b32 h, 0x3ff00000, 0, ad;\n\tmov.b64 m, {z, h};\n\tfma.rn.f64 %1, %12, m, %1;\n\tor.pred bel, bel, ad;\n\t"
+            "setp.le.and.f64 ad, %11, %8, !bel;\n\tselp.b32 h, 0x3ff00000, 0, ad;\n\tmov.b64 m, {z, h};\n\tfma.rn.f64 %2, %12, m, %2;\n\tor.pred bel, bel, ad;\n\t"
+            "setp.le.and.f64 ad, %11, %9, !bel;\n\tselp.b32 h, 0x3ff00000, 0, ad;\n\tmov.b64 m, {z, h};\n\tfma.rn.f64 %3, %12, m, %3;\n\tor.pred bel, bel, ad;\n\t"
+            "setp.le.and.f64 ad, %11, %10, !bel;\n\tselp.b32 h, 0x3ff00000, 0, ad;\n\tmov.b64 m, {z, h};\n\tfma.rn.f64 %4, %12, m, %4;\n\tor.pred bel, bel, ad;\n\t"
+            "selp.u32 %5, 1, 0, bel;\n\t}"
+            : "+d"(a0), "+d"(a1), "+d"(a2), "+d"(a3), "+d"(a4), "+r"(below)
+            : "d"(e0), "d"(e1), "d"(e2), "d"(e3), "d"(e4), "d"(d), "d"(w));
+    }
+    __device__ __forceinline__ double edge(int s) const { return __longlong_as_double((long long)(s == HTB_NBF - 1 ? P.E_top : P.E[s])); }
     __device__ __forceinline__ void pair_exact(int q, double xj, double yj, double zj, double wj)
     {
         const double dx = xs[q] - xj, dy = ys[q] - yj, dz = zs[q] - zj;
         const double dsq = dx * dx + dy * dy + dz * dz;
-        const unsigned long long b = (unsigned long long)__double_as_longlong(dsq);
-        if (b <= P.E_top) {
+        if (dsq <= edge(HTB_NBF - 1)) {
             const double w = w1[q] * wj;
             Xall += w;
-            bool below = false;                     // already inside a lower edge
-#pragma unroll
-            for (int s = 0; s < HTB_NBF - 1; ++s) {
-                const bool in = b <= P.E[s];
-                if (in && !below) accD[s] += w;
-                below = below || in;
-            }
+            // the weight goes to the lowest level whose edge holds the pair (the edges ascend)
+            unsigned below = 0;
+            static_assert(HTB_NBF - 1 == 15, "three groups of five levels");
+            levels5(accD[0], accD[1], accD[2], accD[3], accD[4], edge(0), edge(1), edge(2), edge(3), edge(4), dsq, w, below);
+            levels5(accD[5], accD[6], accD[7], accD[8], accD[9], edge(5), edge(6), edge(7), edge(8), edge(9), dsq, w, below);
+            levels5(accD[10], accD[11], accD[12], accD[13], accD[14], edge(10), edge(11), edge(12), edge(13), edge(14), dsq, w, below);
         }
     }
     __device__ __forceinline__ void exact_range(uint32_t stage, int j0, int j1)
@@ -1170,10 +1208,10 @@ struct MarkedQ {
         }
         qsave = qptr; Wsave[0] = Wtop[0]; Wsave[1] = Wtop[1];
     }
-    __device__ __forceinline__ void chunk(uint32_t stage, int lo, int hi, uint32_t tok)
+    __device__ __forceinline__ void chunk(uint32_t stage, int lo, int hi, uint32_t tok, bool own)
     {
         const uint32_t bx = stage, by = stage + 8 * HTB_CH, bz = stage + 16 * HTB_CH, bw = stage + 24 * HTB_CH;
-        if (exact) { exact_range(stage, lo, hi); return; }
+        if (exact | own) { exact_range(stage, lo, hi); return; }    // own index range: see Fast3T::chunk
         int j = lo;
         if ((j & 1) && j < hi) {
             const double xj = lds_f64(bx + 8 * j), yj = lds_f64(by + 8 * j), zj = lds_f64(bz + 8 * j), wj = lds_f64(bw + 8 * j);
@@ -1653,8 +1691,11 @@ struct DSigmaR {
     // (left to the compiler this becomes an unconditional DMUL, two selects and two integer instructions)
     static __device__ __forceinline__ void below(double &C, unsigned &n, double d, unsigned long long b, unsigned long long edge)
     {
-        asm("{\n\t.reg .pred p;\n\tsetp.le.u64 p, %3, %4;\n\t@p mul.rn.f64 %0, %0, %2;\n\t@p add.u32 %1, %1, 1;\n\t}"
-            : "+d"(C), "+r"(n) : "d"(d), "l"(b), "l"(edge));
+        // the compare runs on the FP64 pipe (one DSETP) instead of two ISETP on the half-rate ALU pipe; for the values here
+        // (d >= +0, edges finite or +inf) it orders exactly like the 64-bit integer compare of the bit patterns
+        asm("{\n\t.reg .pred p;\n\tsetp.le.f64 p, %2, %3;\n\t@p mul.rn.f64 %0, %0, %2;\n\t@p add.u32 %1, %1, 1;\n\t}"
+            : "+d"(C), "+r"(n) : "d"(d), "d"(__longlong_as_double((long long)edge)));
+        (void)b;
     }
     template <int NE>
     __device__ __forceinline__ void pair_fast(double xj, double yj)

@@ -89,25 +89,24 @@ struct Workspace {
     void release();
 };
 
-// numpy's float64 floor-division followed by the reference's clip
-// (rectangular_mesh.py:19-22; numpy npy_divmod: fmod based, NOT floor(p / c)).
-__host__ __device__ inline int htb_ref_digitize(double p, double c, int ndivs)
+// numpy's float64 floor-division followed by the reference's clip (rectangular_mesh.py:19-22).  numpy's npy_divmod is
+// fmod based: mod = fmod(p, c) is the EXACT remainder, div = (p - mod) / c lands within an ulp of an integer and is
+// snapped to it, so for finite p and c > 0 the result is floor(p / c) of the exact quotient, never of the rounded one.
+// That integer is found here without fmod's bit-serial loop and without a division: an estimate from the rounded
+// reciprocal is at most one off, and the sign of fma(-q, c, p) - one rounding of the exact p - q c - is exact.
+// rc = 1.0 / c, hoisted by callers that bin many points with one cell size
+__host__ __device__ inline int htb_ref_digitize(double p, double c, double rc, int ndivs)
 {
-    double mod = fmod(p, c);
-    double div = (p - mod) / c;
-    if (mod != 0.0) {
-        if ((c < 0) != (mod < 0)) { mod += c; div -= 1.0; }
-    }
-    double fl;
-    if (div != 0.0) {
-        fl = floor(div);
-        if (div - fl > 0.5) fl += 1.0;
-    } else {
-        fl = 0.0;
-    }
+    if (!(fabs(p) < INFINITY)) return 0;                // nan, +-inf: rejected by the bounds check; numpy yields garbage here
+    double fl = floor(p * rc);
+    if (fl >= (double)ndivs + 1.0) return ndivs - 1;   // the exact quotient is >= ndivs as well
+    if (fma(-fl, c, p) < 0.0) fl -= 1.0;
+    else if (fma(-(fl + 1.0), c, p) >= 0.0) fl += 1.0;
     // astype(int) then np.where(ip >= num_divs, num_divs - 1, ip); negatives are undefined
     // behaviour in the reference (they index before the first cell) — clamp to cell 0.
     if (!(fl > -1.0)) return 0;
     if (fl >= (double)ndivs) return ndivs - 1;
     return (int)fl;
 }
+
+__host__ __device__ inline int htb_ref_digitize(double p, double c, int ndivs) { return htb_ref_digitize(p, c, 1.0 / c, ndivs); }

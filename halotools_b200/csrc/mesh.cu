@@ -25,15 +25,18 @@ k_assign(const double *__restrict__ x, const double *__restrict__ y, const doubl
 {
     const double *src[3] = {x, y, z};
     uint32_t bad = 0;
+    double rc[DIM], mc[DIM];                          // the two divisions per dimension, once per thread
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) { rc[d] = 1.0 / g.cs[d]; mc[d] = (double)g.m[d] / g.cs[d]; }
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         uint32_t cid = 0;
 #pragma unroll
         for (int d = 0; d < DIM; ++d) {
             const double p = src[d][i * stride];
-            const int r = htb_ref_digitize(p, g.cs[d], g.nd[d]);
+            const int r = htb_ref_digitize(p, g.cs[d], rc[d], g.nd[d]);
             int f = r;
             if (g.m[d] > 1) {
-                int sub = (int)floor((p - (double)r * g.cs[d]) * ((double)g.m[d] / g.cs[d]));
+                int sub = (int)floor((p - (double)r * g.cs[d]) * mc[d]);
                 sub = sub < 0 ? 0 : (sub >= g.m[d] ? g.m[d] - 1 : sub);
                 f = r * g.m[d] + sub;
             }
@@ -58,21 +61,42 @@ k_scatter(const double *__restrict__ x, const double *__restrict__ y, const doub
           double *__restrict__ ox, double *__restrict__ oy, double *__restrict__ oz,
           uint32_t *__restrict__ perm, const double *__restrict__ w, double *__restrict__ ow, int nw)
 {
+    // the PART_ITEMS points of a thread go through the dependent chain (cell id -> first position -> returning atomic ->
+    // stores) side by side, phase by phase, so that a thread has PART_ITEMS gathers / atomics in flight instead of one
     const int64_t nchunk = (n + PART_CHUNK - 1) / PART_CHUNK;
     for (int64_t c = blockIdx.x; c < nchunk; c += gridDim.x) {
+        const int64_t i0 = c * PART_CHUNK + threadIdx.x;
+        uint32_t cid[PART_ITEMS], pos[PART_ITEMS];
+        double px[PART_ITEMS], py[PART_ITEMS], pz[PART_ITEMS];
+        bool ok[PART_ITEMS];
 #pragma unroll
         for (int k = 0; k < PART_ITEMS; ++k) {
-            const int64_t i = c * PART_CHUNK + (int64_t)k * PART_THREADS + threadIdx.x;
-            if (i >= n) continue;
-            const uint32_t cid = cell[i];
-            if (off[cid + 1] == off[cid]) continue;       // the cell was emptied: outside this rank's window (htb_sort_finish)
-            const uint32_t pos = off[cid] + atomicAdd(&fill[cid], 1u);
-            ox[pos] = x[i * stride];
-            oy[pos] = y[i * stride];
-            if (DIM == 3) oz[pos] = z[i * stride];
-            if (perm) perm[pos] = (uint32_t)i;
+            const int64_t i = i0 + (int64_t)k * PART_THREADS;
+            ok[k] = i < n;
+            cid[k] = ok[k] ? cell[i] : 0u;
+            px[k] = ok[k] ? x[i * stride] : 0.0;
+            py[k] = ok[k] ? y[i * stride] : 0.0;
+            pz[k] = (DIM == 3 && ok[k]) ? z[i * stride] : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < PART_ITEMS; ++k) {
+            const uint32_t first = ok[k] ? off[cid[k]] : 0u, next = ok[k] ? off[cid[k] + 1] : 0u;
+            ok[k] = next != first;                        // an emptied cell: outside this rank's window (htb_sort_finish)
+            pos[k] = first;
+        }
+#pragma unroll
+        for (int k = 0; k < PART_ITEMS; ++k)
+            if (ok[k]) pos[k] += atomicAdd(&fill[cid[k]], 1u);
+#pragma unroll
+        for (int k = 0; k < PART_ITEMS; ++k) {
+            if (!ok[k]) continue;
+            ox[pos[k]] = px[k];
+            oy[pos[k]] = py[k];
+            if (DIM == 3) oz[pos[k]] = pz[k];
+            if (perm) perm[pos[k]] = (uint32_t)(i0 + (int64_t)k * PART_THREADS);
             if (ow) {
-                for (int q = 0; q < nw; ++q) ow[(int64_t)pos * nw + q] = w[i * nw + q];
+                const int64_t i = i0 + (int64_t)k * PART_THREADS;
+                for (int q = 0; q < nw; ++q) ow[(int64_t)pos[k] * nw + q] = w[i * nw + q];
             }
         }
     }

@@ -171,8 +171,8 @@ struct WarpSmem {
 template <class V, class = void> struct HtbChunk { static constexpr int value = HTB_CH; };
 template <class V> struct HtbChunk<V, decltype((void)V::CH)> { static constexpr int value = V::CH; };
 
-// variants with a cheaper evaluation of the tile's OWN index range in symmetric mode (the chunk that holds the self
-// pairs, whose exact zeros a 32-bit relative key cannot represent): V::HAS_SELF and chunk_self()
+// variants that want to know when a chunk is the tile's OWN index range in symmetric mode (it holds the self pairs,
+// whose exact zeros a 32-bit relative key cannot represent): V::HAS_SELF and chunk(stage, lo, hi, tok, own)
 template <class V, class = void> struct HtbHasSelf { static constexpr bool value = false; };
 template <class V> struct HtbHasSelf<V, decltype((void)V::HAS_SELF)> { static constexpr bool value = V::HAS_SELF; };
 
@@ -286,12 +286,8 @@ __device__ __forceinline__ void walk_tile(V &v, const WalkGeom &G, const WalkArr
             const int lo = (int)(max(jb, jc) - jc);
             const int hi = (int)(min(je, jc + HTB_CH) - jc);
             if constexpr (HtbWantsBase<V>::value) v.chunk_base(jc);
-            if constexpr (HtbHasSelf<V>::value) {
-                if (fullcode & 0x100u) v.chunk_self(S.stage_s(stg), lo, hi, tok);
-                else v.chunk(S.stage_s(stg), lo, hi, tok);
-            } else {
-                v.chunk(S.stage_s(stg), lo, hi, tok);
-            }
+            if constexpr (HtbHasSelf<V>::value) v.chunk(S.stage_s(stg), lo, hi, tok, (fullcode & 0x100u) != 0u);
+            else v.chunk(S.stage_s(stg), lo, hi, tok);
             pairs += (unsigned long long)(hi - lo) * (unsigned)tile_cnt;
             __syncwarp();
             ++gchunk;

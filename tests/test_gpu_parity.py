@@ -176,14 +176,21 @@ def test_cell1_ranges_are_additive():
     assert np.array_equal(total, oracle.npairs_3d(s1, s2, rbins, period=100.0))
 
 
-def test_mesh_cell_ids_and_offsets_match_numpy_semantics():
+@pytest.mark.parametrize("L,nd", [(250.0, 12), (1000.0, 33), (73.7, 129), (1.0, 7), (1000.0, 200)])
+def test_mesh_cell_ids_and_offsets_match_numpy_semantics(L, nd):
     import ctypes
     from oracle.mesh import Mesh
-    L, nd = 250.0, 12
     cs = L / nd
-    edge = np.array([cs * k for k in range(nd + 1)])          # exact multiples: floor-division quirk
+    edge = np.array([cs * k for k in range(nd + 1)])          # multiples of the cell size: the floor-division quirk
     rng = np.random.RandomState(3)
-    x = np.concatenate([edge, rng.uniform(0, L, 5000), np.nextafter(edge, 0), np.nextafter(edge, L)])
+    near = [edge]
+    for _ in range(3):                                        # ... and the 3 doubles either side of each
+        near.append(np.nextafter(near[-1], 0))
+    up = edge
+    for _ in range(3):
+        up = np.nextafter(up, 2 * L)
+        near.append(up)
+    x = np.concatenate(near + [rng.uniform(0, L, 5000)])
     x = np.clip(x, 0, L)
     y = rng.permutation(x)
     z = rng.permutation(x)
