@@ -70,8 +70,8 @@ int htb_sort_begin(cudaStream_t st, Workspace &ws, const FineGrid &g,
 int htb_sort_finish(cudaStream_t st, Workspace &ws, const double *const *coords_dev, int64_t stride,
                     const double *w_dev, int nw, double pad_value, const int *xwin_dev, SortedSample &out, int *launches);
 int htb_ref_cell_counts_pre(cudaStream_t st, const SortedSample &s, uint32_t *counts_dev /* [prod nd] zeroed */, int *launches);
-int htb_exclusive_scan_u32(cudaStream_t st, Workspace &ws, const uint32_t *in, uint32_t *out,
-                           int64_t n, uint32_t *total_dev, int *launches);
+int htb_exclusive_scan_u32(cudaStream_t st, Workspace &ws, uint32_t *in, uint32_t *out,
+                           int64_t n, uint32_t *total_dev, int *launches, bool zero_in = false);
 int htb_ref_cell_ids(cudaStream_t st, int dim, const double *const *coords_dev, int64_t stride, int64_t n,
                      const double *cell_size, const int *ndivs, int64_t *ids_dev, int *launches);
 int htb_ref_cell_counts(cudaStream_t st, const SortedSample &s, uint32_t *counts_dev /* [prod nd] zeroed */,

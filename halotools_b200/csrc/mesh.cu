@@ -59,8 +59,15 @@ __global__ void __launch_bounds__(PART_THREADS)
 k_scatter(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z, int64_t stride, int64_t n,
           const uint32_t *__restrict__ cell, const uint32_t *__restrict__ off, uint32_t *__restrict__ fill,
           double *__restrict__ ox, double *__restrict__ oy, double *__restrict__ oz,
-          uint32_t *__restrict__ perm, const double *__restrict__ w, double *__restrict__ ow, int nw)
+          uint32_t *__restrict__ perm, const double *__restrict__ w, double *__restrict__ ow, int nw,
+          int64_t npad, double pad_value)
 {
+    // entries [n, npad) get a far-away sentinel, so that staging reads past a span end are harmless
+    if (blockIdx.x == 0 && n + threadIdx.x < npad) {
+        ox[n + threadIdx.x] = pad_value;
+        oy[n + threadIdx.x] = pad_value;
+        if (DIM == 3) oz[n + threadIdx.x] = pad_value;
+    }
     // the PART_ITEMS points of a thread go through the dependent chain (cell id -> first position -> returning atomic ->
     // stores) side by side, phase by phase, so that a thread has PART_ITEMS gathers / atomics in flight instead of one
     const int64_t nchunk = (n + PART_CHUNK - 1) / PART_CHUNK;
@@ -165,8 +172,8 @@ k_scan_bsums(uint32_t *__restrict__ bsum, int64_t nb, uint32_t *__restrict__ tot
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS)
-k_scan_final(const uint32_t *__restrict__ in, int64_t n, const uint32_t *__restrict__ bsum,
-             uint32_t *__restrict__ out)
+k_scan_final(uint32_t *__restrict__ in, int64_t n, const uint32_t *__restrict__ bsum,
+             uint32_t *__restrict__ out, int zero_in)
 {
     // block-local exclusive scan of SCAN_BLOCK items laid out [k][thread] is awkward; use a
     // thread-contiguous layout instead: thread t owns items [t*ITEMS, (t+1)*ITEMS).
@@ -178,6 +185,10 @@ k_scan_final(const uint32_t *__restrict__ in, int64_t n, const uint32_t *__restr
     for (int k = 0; k < SCAN_ITEMS; ++k) {
         v[k] = (base + k < n) ? in[base + k] : 0u;
         s += v[k];
+    }
+    if (zero_in) {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) if (base + k < n) in[base + k] = 0u;
     }
     // warp inclusive scan of s
     uint32_t inc = s;
@@ -201,11 +212,69 @@ k_scan_final(const uint32_t *__restrict__ in, int64_t n, const uint32_t *__restr
 
 __global__ void k_set_u32(uint32_t *dst, const uint32_t *src) { *dst = *src; }
 
-int htb_exclusive_scan_u32(cudaStream_t st, Workspace &ws, const uint32_t *in, uint32_t *out,
-                           int64_t n, uint32_t *total_dev, int *launches)
+// one launch instead of three for small inputs (a 1e5-point call spends its time between kernels, not in them): one
+// block walks the array in chunks of 1024 x SCAN_SMALL_ITEMS, warp-shuffle scan inside a chunk, running carry across
+#define SCAN_SMALL_ITEMS 4
+#define SCAN_SMALL_MAX (1 << 15)
+__global__ void __launch_bounds__(1024)
+k_scan_small(uint32_t *__restrict__ in, int64_t n, uint32_t *__restrict__ out, uint32_t *__restrict__ total, int zero_in)
+{
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t carry_s;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t carry = 0;
+    for (int64_t base = 0; base < n; base += 1024 * SCAN_SMALL_ITEMS) {
+        const int64_t i0 = base + (int64_t)threadIdx.x * SCAN_SMALL_ITEMS;
+        uint32_t v[SCAN_SMALL_ITEMS], s = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_SMALL_ITEMS; ++k) { v[k] = (i0 + k < n) ? in[i0 + k] : 0u; s += v[k]; }
+        if (zero_in) {
+#pragma unroll
+            for (int k = 0; k < SCAN_SMALL_ITEMS; ++k) if (i0 + k < n) in[i0 + k] = 0u;
+        }
+        uint32_t inc = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) wsum[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t w = wsum[lane], winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += t;
+            }
+            wsum[lane] = winc - w;                       // exclusive warp bases
+            if (lane == 31) carry_s = winc;              // chunk total
+        }
+        __syncthreads();
+        uint32_t run = carry + wsum[wid] + inc - s;
+#pragma unroll
+        for (int k = 0; k < SCAN_SMALL_ITEMS; ++k) {
+            if (i0 + k < n) out[i0 + k] = run;
+            run += v[k];
+        }
+        carry += carry_s;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total) *total = carry;
+}
+
+// zero_in: the input is zeroed once it has been read (the sort reuses the scanned counters as fill counters)
+int htb_exclusive_scan_u32(cudaStream_t st, Workspace &ws, uint32_t *in, uint32_t *out,
+                           int64_t n, uint32_t *total_dev, int *launches, bool zero_in)
 {
     if (n <= 0) {
         if (total_dev) HTB_CUDA(cudaMemsetAsync(total_dev, 0, sizeof(uint32_t), st));
+        return 0;
+    }
+    if (n <= SCAN_SMALL_MAX) {
+        k_scan_small<<<1, 1024, 0, st>>>(in, n, out, total_dev, zero_in ? 1 : 0);
+        if (launches) *launches += 1;
+        HTB_CUDA(cudaGetLastError());
         return 0;
     }
     const int64_t nblk = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
@@ -213,7 +282,7 @@ int htb_exclusive_scan_u32(cudaStream_t st, Workspace &ws, const uint32_t *in, u
     if (ws.alloc((void **)&bsum, sizeof(uint32_t) * (size_t)nblk)) return 1;
     k_scan_partial<<<(unsigned)nblk, SCAN_THREADS, 0, st>>>(in, n, bsum);
     k_scan_bsums<<<1, 1024, 0, st>>>(bsum, nblk, total_dev);
-    k_scan_final<<<(unsigned)nblk, SCAN_THREADS, 0, st>>>(in, n, bsum, out);
+    k_scan_final<<<(unsigned)nblk, SCAN_THREADS, 0, st>>>(in, n, bsum, out, zero_in ? 1 : 0);
     if (launches) *launches += 3;
     HTB_CUDA(cudaGetLastError());
     return 0;
@@ -256,13 +325,13 @@ int htb_sort_begin(cudaStream_t st, Workspace &ws, const FineGrid &g,
     for (int d = 0; d < g.dim; ++d)
         if (ws.alloc((void **)&out.c[d], sizeof(double) * (size_t)out.npad)) return 1;
     if (ws.alloc((void **)&out.off, sizeof(uint32_t) * (size_t)(g.ncells + 2))) return 1;
-    if (ws.alloc((void **)&out.flags, sizeof(uint32_t) * 4)) return 1;
     if (keep_perm && ws.alloc((void **)&out.perm, sizeof(uint32_t) * (size_t)(n > 0 ? n : 1))) return 1;
     if (w_dev && ws.alloc((void **)&out.w, sizeof(double) * (size_t)((n > 0 ? n : 1) * nw + 2))) return 1;
     if (ws.alloc((void **)&out.cell, sizeof(uint32_t) * (size_t)(n > 0 ? n : 1))) return 1;
-    if (ws.alloc((void **)&out.count, sizeof(uint32_t) * (size_t)(g.ncells + 2))) return 1;
-    HTB_CUDA(cudaMemsetAsync(out.count, 0, sizeof(uint32_t) * (size_t)(g.ncells + 2), st));
-    HTB_CUDA(cudaMemsetAsync(out.flags, 0, sizeof(uint32_t) * 4, st));
+    // the flags word sits behind the counters: one memset for both
+    if (ws.alloc((void **)&out.count, sizeof(uint32_t) * (size_t)(g.ncells + 2 + 4))) return 1;
+    out.flags = out.count + g.ncells + 2;
+    HTB_CUDA(cudaMemsetAsync(out.count, 0, sizeof(uint32_t) * (size_t)(g.ncells + 2 + 4), st));
     if (n > 0) {
         const int blocks = grid_for(n, 256);
         if (g.dim == 3)
@@ -286,22 +355,23 @@ int htb_sort_finish(cudaStream_t st, Workspace &ws, const double *const *cd, int
         if (launches) *launches += 1;
     }
     // off[0..ncells] : exclusive scan over ncells+1 entries (the extra entry is zero) gives off[ncells] = points kept
-    if (htb_exclusive_scan_u32(st, ws, out.count, out.off, g.ncells + 1, nullptr, launches)) return 1;
+    // (the per-cell counts, once scanned into `off`, are zeroed by the scan: the array then serves as the cells' fill counters)
+    if (htb_exclusive_scan_u32(st, ws, out.count, out.off, g.ncells + 1, nullptr, launches, true)) return 1;
     if (n > 0) {
-        // the per-cell counts have been scanned into `off`: the array now serves as the cells' fill counters
-        HTB_CUDA(cudaMemsetAsync(out.count, 0, sizeof(uint32_t) * (size_t)(g.ncells + 2), st));
         const int64_t nchunk = (n + PART_CHUNK - 1) / PART_CHUNK;
         const int blocks = (int)(nchunk < 148 * 8 ? nchunk : 148 * 8);
         if (g.dim == 3)
             k_scatter<3><<<blocks, PART_THREADS, 0, st>>>(cd[0], cd[1], cd[2], stride, n, out.cell, out.off, out.count,
-                                                          out.c[0], out.c[1], out.c[2], out.perm, w_dev, out.w, nw);
+                                                          out.c[0], out.c[1], out.c[2], out.perm, w_dev, out.w, nw, out.npad, pad_value);
         else
             k_scatter<2><<<blocks, PART_THREADS, 0, st>>>(cd[0], cd[1], nullptr, stride, n, out.cell, out.off, out.count,
-                                                          out.c[0], out.c[1], nullptr, out.perm, w_dev, out.w, nw);
+                                                          out.c[0], out.c[1], nullptr, out.perm, w_dev, out.w, nw, out.npad, pad_value);
         if (launches) *launches += 1;
     }
-    k_pad<<<1, 32, 0, st>>>(out.c[0], out.c[1], g.dim == 3 ? out.c[2] : nullptr, n, out.npad, pad_value);
-    if (launches) *launches += 1;
+    if (n <= 0) {
+        k_pad<<<1, 32, 0, st>>>(out.c[0], out.c[1], g.dim == 3 ? out.c[2] : nullptr, n, out.npad, pad_value);
+        if (launches) *launches += 1;
+    }
     HTB_CUDA(cudaGetLastError());
     return 0;
 }
