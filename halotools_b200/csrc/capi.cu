@@ -276,7 +276,18 @@ static void choose_refinement(const htb_mesh_geom *g, int64_t n1, int64_t n2, in
         const int cap = clampi(floor(4.0 * g->cell2_size[d] / g->search[d] + 0.5), 1, 8);
         m2[d] = clampi(floor(scale), 1, cap);
     }
-    m2[F] = clampi(floor(8.0 * g->cell2_size[F] / g->search[F] + 0.5), 1, 16);
+    // along the fast dimension the spans are cut at fine-cell resolution (half a cell of wasted evaluations at either
+    // end): cells of a 32nd of the search length, as long as a cell still holds ~5 points on average - below that the
+    // sort of the larger mesh costs what the tighter spans save (configs 1, 3, 4 stay near the round-1 value of an 8th;
+    // the bench's RR launch evaluates 11 % fewer pairs, 61.0 -> 55.8 ms; profiles/r02_refine_sweep.txt).
+    {
+        double fz = 32.0;
+        if (const char *e = getenv("HTB_FZ")) { const double v = atof(e); if (v >= 1.0 && v <= 64.0) fz = v; }
+        double colfine = 1.0;
+        for (int d = 0; d < S; ++d) colfine *= g->cell2_size[d] / m2[d];
+        const int cap = clampi(floor(dens2 * colfine * g->cell2_size[F] / 5.0), 8, 64);
+        m2[F] = clampi(floor(fz * g->cell2_size[F] / g->search[F] + 0.5), 1, std::min(cap, (int)fz));
+    }
     if (mode == 1) {
         // cell-resolved kernels (DSigmaR) decide per fine cell of sample2: cells small against the bins (a
         // sixteenth of the search length) but holding >= ~256 points, so the per-cell work is amortised
