@@ -35,7 +35,7 @@ EXPORTS = (
     "htb_marked_npairs_xy_z_engine", "htb_npairs_per_object_3d_engine", "htb_weighted_npairs_xy_engine",
     "htb_npairs_jackknife_3d_engine", "htb_npairs_jackknife_xy_z_engine", "htb_weighted_npairs_per_object_xy_engine",
     "htb_mesh_cell_ids", "htb_mesh_cell_id_indices", "htb_cell1_work", "htb_measure_fp64_rate",
-    "htb_host_minmax", "htb_device_minmax", "htb_tp_estimator", "htb_get_stream", "htb_stream_synchronize", "htb_async_count_times",
+    "htb_host_minmax", "htb_device_minmax", "htb_tp_estimator", "htb_get_stream", "htb_stream_synchronize", "htb_async_count_times", "htb_async_kernel_spans", "htb_async_kernel_stamps",
     "htb_return_xyz_formatted_array", "htb_apply_zspace_distortion", "htb_upload_f64",
 )
 
@@ -245,6 +245,25 @@ def async_count_times():
     n = ctypes.c_int32(0)
     check(lib.htb_async_count_times(buf, ctypes.c_int32(16), ctypes.byref(n)))
     return [float(buf[i]) for i in range(n.value)]
+
+
+def async_kernel_spans():
+    """Device-side durations (ms; first warp in -> last warp out) of the counting kernels of the asynchronous calls since
+    the last ``async_count_times`` query (which resets the ring: ask for the spans first)."""
+    lib = require_gpu()
+    buf = (ctypes.c_float * 16)()
+    n = ctypes.c_int32(0)
+    check(lib.htb_async_kernel_spans(buf, ctypes.c_int32(16), ctypes.byref(n)))
+    return [float(buf[i]) for i in range(n.value)]
+
+
+def async_kernel_stamps():
+    """(first warp in, last warp out) in ns of the device's globaltimer for the same launches (not reset either)."""
+    lib = require_gpu()
+    buf = (ctypes.c_uint64 * 32)()
+    n = ctypes.c_int32(0)
+    check(lib.htb_async_kernel_stamps(buf, ctypes.c_int32(16), ctypes.byref(n)))
+    return [(int(buf[2 * i]), int(buf[2 * i + 1])) for i in range(n.value)]
 
 
 class use_stream(object):

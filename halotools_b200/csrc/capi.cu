@@ -597,6 +597,9 @@ static thread_local cudaEvent_t g_call_ev[64][5] = {{nullptr}};
 #define HTB_ASYNC_RING 16
 static thread_local cudaEvent_t g_async_ev[HTB_ASYNC_RING][2] = {{nullptr}};
 static thread_local int g_async_n = 0;
+// ... and the kernel's own device-side time stamps {~first warp in, last warp out} (globaltimer, ns; words 40..43 of the
+// call's counter block), copied to a pinned ring right behind the kernel: htb_async_kernel_spans()
+static thread_local unsigned long long (*g_async_ts)[2] = nullptr;
 
 struct Call {
     cudaStream_t st = nullptr;
@@ -650,7 +653,13 @@ struct Call {
             cudaEvent_t *pair = g_async_ev[g_async_n % HTB_ASYNC_RING];
             for (int k = 0; k < 2; ++k) if (!pair[k]) HTB_CUDA(cudaEventCreate(&pair[k]));
             HTB_CUDA(cudaEventRecord(pair[i - 2], st));
-            if (i == 3) ++g_async_n;
+            if (i == 3) {
+                if (!g_async_ts) HTB_CUDA(cudaMallocHost((void **)&g_async_ts, sizeof(unsigned long long) * 2 * HTB_ASYNC_RING));
+                unsigned long long *slot = g_async_ts[g_async_n % HTB_ASYNC_RING];
+                slot[0] = slot[1] = 0;
+                if (ctr) HTB_CUDA(cudaMemcpyAsync(slot, ctr + 40, 16, cudaMemcpyDeviceToHost, st));
+                ++g_async_n;
+            }
         }
         return 0;
     }
@@ -2074,6 +2083,41 @@ extern "C" int htb_async_count_times(float *ms_out, int32_t max_out, int32_t *n_
     }
     *n_out = n;
     g_async_n = 0;
+    return 0;
+    HTB_GUARD_END
+}
+// the same launches by their own device-side stamps (first warp in -> last warp out, ms): what the kernel took once its
+// blocks ran, without the time it waited behind the kernels of other streams.  Does not reset the ring: call it BEFORE
+// htb_async_count_times().  -1 where a call launched no count kernel.
+extern "C" int htb_async_kernel_spans(float *ms_out, int32_t max_out, int32_t *n_out)
+{
+    HTB_GUARD_BEGIN
+    if (!ms_out || !n_out || max_out < 0) { htb_set_error("htb_async_kernel_spans: bad arguments"); return 1; }
+    const int have = g_async_n < HTB_ASYNC_RING ? g_async_n : HTB_ASYNC_RING;
+    const int n = have < max_out ? have : max_out;
+    for (int k = 0; k < n; ++k) {
+        const unsigned long long *slot = g_async_ts ? g_async_ts[(g_async_n - n + k) % HTB_ASYNC_RING] : nullptr;
+        ms_out[k] = (slot && slot[0] && slot[1] && slot[1] > ~slot[0]) ? (float)((double)(slot[1] - ~slot[0]) * 1e-6) : -1.f;
+    }
+    *n_out = n;
+    return 0;
+    HTB_GUARD_END
+}
+// ... and the raw stamps {first warp in, last warp out} (globaltimer, ns; 0, 0 where no kernel ran), two words per call:
+// launches of one statistic that run side by side on several streams are measured by the union of their spans
+extern "C" int htb_async_kernel_stamps(uint64_t *ns_out, int32_t max_out, int32_t *n_out)
+{
+    HTB_GUARD_BEGIN
+    if (!ns_out || !n_out || max_out < 0) { htb_set_error("htb_async_kernel_stamps: bad arguments"); return 1; }
+    const int have = g_async_n < HTB_ASYNC_RING ? g_async_n : HTB_ASYNC_RING;
+    const int n = have < max_out ? have : max_out;
+    for (int k = 0; k < n; ++k) {
+        const unsigned long long *slot = g_async_ts ? g_async_ts[(g_async_n - n + k) % HTB_ASYNC_RING] : nullptr;
+        const bool ok = slot && slot[0] && slot[1];
+        ns_out[2 * k] = ok ? (uint64_t)~slot[0] : 0;
+        ns_out[2 * k + 1] = ok ? (uint64_t)slot[1] : 0;
+    }
+    *n_out = n;
     return 0;
     HTB_GUARD_END
 }

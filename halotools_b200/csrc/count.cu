@@ -55,6 +55,76 @@ __device__ __forceinline__ uint32_t htb_column_tiles(const uint32_t *__restrict_
     return n;
 }
 
+// The same cut by ONE WARP per column, for meshes with few columns and many fine cells along the fast dimension
+// (the bench's DD launch: 144 columns of 384 cells): a thread walking its column cell by cell waits a full L2 round
+// trip per cell.  Here the warp keeps a window of the column's offsets in shared memory (coalesced loads), every lane
+// runs the same walk on broadcast shared-memory reads, lane 0 writes.  The window always covers
+// [f, f + G.maxfine + 1]: everything one tile needs.
+#define HTB_TL_WIN 1024
+#define HTB_TL_WARPS 4
+__device__ __forceinline__ uint32_t htb_column_tiles_warp(const uint32_t *__restrict__ off1, const WalkGeom &G, int64_t col,
+                                                          int64_t first_cell1, int64_t last_cell1, uint2 *out, uint32_t base,
+                                                          uint32_t *so, int lane)
+{
+    const int F = G.dim - 1;
+    int64_t rem = col, rid = 0;
+    int fsl[2] = {0, 0};
+    for (int d = F - 1; d >= 0; --d) { fsl[d] = (int)(rem % G.nf1[d]); rem /= G.nf1[d]; }
+    for (int d = 0; d < F; ++d) rid = rid * G.nd1[d] + fsl[d] / G.m1[d];
+    rid *= G.nd1[F];
+    int64_t zlo64 = first_cell1 - rid, zhi64 = last_cell1 - rid;
+    const int zlo = (int)(zlo64 < 0 ? 0 : (zlo64 > G.nd1[F] ? G.nd1[F] : zlo64));
+    const int zhi = (int)(zhi64 < 0 ? 0 : (zhi64 > G.nd1[F] ? G.nd1[F] : zhi64));
+    if (zlo >= zhi) return 0;
+    const uint32_t *o = off1 + col * G.nf1[F];
+    const int mf = G.m1[F], last = zhi * mf;              // offsets o[zlo * mf .. last] are the ones that matter
+    int wb = zlo * mf;                                    // the window holds o[wb .. min(wb + WIN - 1, last)]
+    auto load = [&](int from) {
+        __syncwarp();
+        wb = from;
+        for (int i = lane; i < HTB_TL_WIN && wb + i <= last; i += 32) so[i] = o[wb + i];
+        __syncwarp();
+    };
+    load(wb);
+    uint32_t pos = so[0];
+    const uint32_t end = o[last];
+    uint32_t n = 0;
+    int f = zlo * mf;
+    while (pos < end) {
+        while (true) {                                      // fine cell (fast dim) of the tile's first point
+            if (f + 1 - wb >= HTB_TL_WIN) load(f);
+            if (so[f + 1 - wb] > pos) break;
+            ++f;
+        }
+        const int lim = min(min(zhi, f / mf + G.maxspan) * mf, f + G.maxfine);
+        if (lim - wb >= HTB_TL_WIN) load(f);
+        const uint32_t e = min(pos + (uint32_t)G.tile, so[lim - wb]);
+        if (out && lane == 0) out[base + n] = make_uint2(pos, (uint32_t)col | ((e - pos) << 24));
+        ++n;
+        pos = e;
+    }
+    return n;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(32 * HTB_TL_WARPS)
+k_tiles_warp(const uint32_t *__restrict__ off1, WalkGeom G, int64_t ncol, int64_t first_cell1, int64_t last_cell1,
+             const long long *__restrict__ range, uint32_t *__restrict__ ntile, const uint32_t *__restrict__ tbase,
+             uint2 *__restrict__ tiles)
+{
+    __shared__ uint32_t win[HTB_TL_WARPS][HTB_TL_WIN];
+    if (range) { first_cell1 = range[0]; last_cell1 = range[1]; }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t s = (int64_t)blockIdx.x * HTB_TL_WARPS + warp; s < ncol; s += (int64_t)gridDim.x * HTB_TL_WARPS) {
+        if (FILL) {
+            if (ntile[s]) (void)htb_column_tiles_warp(off1, G, s, first_cell1, last_cell1, tiles, tbase[s], win[warp], lane);
+        } else {
+            const uint32_t n = htb_column_tiles_warp(off1, G, s, first_cell1, last_cell1, nullptr, 0u, win[warp], lane);
+            if (lane == 0) ntile[s] = n;
+        }
+    }
+}
+
 __global__ void k_seg_tiles(const uint32_t *__restrict__ off1, WalkGeom G, int64_t ncol,
                             int64_t first_cell1, int64_t last_cell1, const long long *__restrict__ range,
                             uint32_t *__restrict__ ntile)
@@ -1916,13 +1986,25 @@ int htb_build_tiles(cudaStream_t st, Workspace &ws, const WalkGeom &G, const Sor
     const int64_t max_tiles = s1.n / G.tile + nseg * G.nd1[F] + 1;
     uint2 *tiles = nullptr;
     if (ws.alloc((void **)&tiles, sizeof(uint2) * (size_t)max_tiles)) return 1;
-    int blocks = (int)((nseg + 127) / 128);
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    k_seg_tiles<<<blocks, 128, 0, st>>>(s1.off, G, nseg, first_cell1, last_cell1, range_dev, ntile);
-    if (launches) *launches += 1;
-    if (htb_exclusive_scan_u32(st, ws, ntile, tbase, nseg, total, launches)) return 1;
-    k_fill_tiles<<<blocks, 128, 0, st>>>(s1.off, G, nseg, first_cell1, last_cell1, range_dev, ntile, tbase, tiles);
-    if (launches) *launches += 1;
+    // few columns with many fine cells each: one warp per column (see k_tiles_warp); many columns: one thread each
+    const bool by_warp = nseg < 148 * 16 * 32 && G.nf1[F] >= 64 && G.maxfine + 2 < HTB_TL_WIN && !getenv("HTB_TILES_BY_THREAD");
+    if (by_warp) {
+        int blocks = (int)((nseg + HTB_TL_WARPS - 1) / HTB_TL_WARPS);
+        if (blocks > 148 * 4) blocks = 148 * 4;
+        k_tiles_warp<false><<<blocks, 32 * HTB_TL_WARPS, 0, st>>>(s1.off, G, nseg, first_cell1, last_cell1, range_dev, ntile, nullptr, nullptr);
+        if (launches) *launches += 1;
+        if (htb_exclusive_scan_u32(st, ws, ntile, tbase, nseg, total, launches)) return 1;
+        k_tiles_warp<true><<<blocks, 32 * HTB_TL_WARPS, 0, st>>>(s1.off, G, nseg, first_cell1, last_cell1, range_dev, ntile, tbase, tiles);
+        if (launches) *launches += 1;
+    } else {
+        int blocks = (int)((nseg + 127) / 128);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        k_seg_tiles<<<blocks, 128, 0, st>>>(s1.off, G, nseg, first_cell1, last_cell1, range_dev, ntile);
+        if (launches) *launches += 1;
+        if (htb_exclusive_scan_u32(st, ws, ntile, tbase, nseg, total, launches)) return 1;
+        k_fill_tiles<<<blocks, 128, 0, st>>>(s1.off, G, nseg, first_cell1, last_cell1, range_dev, ntile, tbase, tiles);
+        if (launches) *launches += 1;
+    }
     HTB_CUDA(cudaGetLastError());
     *tiles_out = tiles;
     *ntiles_dev_out = total;

@@ -9,6 +9,13 @@
 template <class V, class = void> struct HtbPerCell { static constexpr bool value = false; };
 template <class V> struct HtbPerCell<V, std::void_t<decltype(V::PER_CELL)>> { static constexpr bool value = V::PER_CELL; };
 
+__device__ __forceinline__ unsigned long long htb_globaltimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 template <class V>
 __global__ void __launch_bounds__(V::WARPS * 32, V::MINBLOCKS)
 k_count(const __grid_constant__ WalkGeom G, const __grid_constant__ WalkArrays A,
@@ -77,6 +84,11 @@ k_count(const __grid_constant__ WalkGeom G, const __grid_constant__ WalkArrays A
         const long long blocks_needed = (needed + V::WARPS - 1) / V::WARPS;
         if ((long long)blockIdx.x >= blocks_needed) return;
     }
+
+    // Device-side time stamps of the launch's own execution (first warp in, last warp out; words 40..43 of the counter
+    // block, zeroed by the host): with several count kernels of a statistic in flight on different streams a CUDA-event
+    // bracket around this launch also measures the time its blocks WAIT for the other kernels' blocks to retire.
+    if (lane == 0) atomicMax((unsigned long long *)(A.tile_counter + 40), ~htb_globaltimer());
 
     // One work item: slice `slice` of `nsl` of tile t.  redo_sub < 0: the normal evaluation (both weight passes in
     // symmetric mode).  A fast kernel that finds it cannot decide a tile from its 32-bit keys asks for an exact
@@ -211,6 +223,7 @@ k_count(const __grid_constant__ WalkGeom G, const __grid_constant__ WalkArrays A
     if (lane == 0) {
         if (pairs) atomicAdd(A.pairs_evaluated, pairs);
         if (redone) atomicAdd(A.tiles_redone, redone);
+        atomicMax((unsigned long long *)(A.tile_counter + 42), htb_globaltimer());
     }
 }
 

@@ -282,6 +282,13 @@ int htb_stream_synchronize(void);
 /* CUDA-event durations (ms) of the counting kernels of this thread's HTB_FLAG_DEVICE_OUTPUT calls since the previous
  * query, oldest first (a ring of 16); call after htb_stream_synchronize().                                    */
 int htb_async_count_times(float *ms_out, int32_t max_out, int32_t *n_out);
+/* The same launches by the kernels' own device-side time stamps (first warp in -> last warp out, ms): without the time a
+ * launch waits for the blocks of kernels on other streams to retire.  Does not reset the ring: query it BEFORE
+ * htb_async_count_times().  -1 where a call launched no counting kernel.                                        */
+int htb_async_kernel_spans(float *ms_out, int32_t max_out, int32_t *n_out);
+/* ... and the raw stamps, two words per call {first warp in, last warp out} in ns of the device's globaltimer (0, 0: no
+ * kernel): counts of one statistic that run side by side on several streams are measured by the union of their spans. */
+int htb_async_kernel_stamps(uint64_t *ns_out, int32_t max_out, int32_t *n_out);
 
 /* The input step before the path, for samples that live in HBM: return_xyz_formatted_array
  * (catalog_analysis_helpers.py:108-265) and apply_zspace_distortion (:268-327) as one elementwise kernel each, enqueued on

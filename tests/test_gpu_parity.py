@@ -941,8 +941,11 @@ def test_asynchronous_engine_calls_leave_counts_on_the_device():
         finally:
             _lib.default_flags = old
         got = [t.cpu().numpy() for t in (t1, t2, t3, t4, t5)]
+    spans = _lib.async_kernel_spans()                  # the kernels' own device-side stamps (ask before the ring is reset)
     times = _lib.async_count_times()
     assert len(times) == 5 and all(t > 0 for t in times)
+    # first warp in -> last warp out lies inside the CUDA-event bracket of the launch (the stamps tick in ~1 us steps)
+    assert len(spans) == 5 and all(0 < s <= t + 0.01 for s, t in zip(spans, times)), (spans, times)
     assert np.array_equal(got[0], hb.npairs_3d(s1, s2, rb, period=50.0))
     assert np.array_equal(got[1], hb.npairs_3d(s1, s1, many, period=50.0))
     assert np.array_equal(got[2].reshape(len(rb), 2), hb.npairs_xy_z(s1, s2, rb, [0.0, 9.0], period=50.0))
