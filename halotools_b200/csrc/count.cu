@@ -202,29 +202,33 @@ __global__ void k_wref(const uint32_t *__restrict__ rc1, const uint32_t *__restr
 // [first, last) whose exclusive cumulative predicted work lies in [total * r / world, total * (r + 1) / world) - the
 // reference's contiguous cell ranges (mesh_helpers.py:183-221) with the cut points moved so that every rank gets
 // the same number of pair evaluations instead of the same number of cells.  One block; range_out = {first, last}.
-__global__ void __launch_bounds__(1024) k_shard_range(const double *__restrict__ work, long long first, long long last,
+// 256 threads, not 1024: at 39 registers a 1024-thread block needs 40 K registers of ONE SM, which no SM has free while a
+// persistent count kernel of another stream is resident (two 32 K-register blocks per SM) - the set-up of the second and
+// third count of a sharded statistic then waited for the first count to END (timeline in DESIGN section 5).
+#define HTB_SR_THREADS 256
+__global__ void __launch_bounds__(HTB_SR_THREADS) k_shard_range(const double *__restrict__ work, long long first, long long last,
                                                        int rank, int world, long long *__restrict__ range_out)
 {
-    __shared__ double part[1024];
+    __shared__ double part[HTB_SR_THREADS];
     __shared__ long long below[2];
     const int t = threadIdx.x;
     const long long n = last > first ? last - first : 0;
-    const long long per = (n + 1023) / 1024;
+    const long long per = (n + HTB_SR_THREADS - 1) / HTB_SR_THREADS;
     const long long a = first + min(n, per * t), b = first + min(n, per * (t + 1));
     double s = 0.0;
     for (long long c = a; c < b; ++c) s += work[c];
     part[t] = s;
     if (t < 2) below[t] = 0;
     __syncthreads();
-    // exclusive scan of the 1024 partial sums (the values are integers below 2^53: the sums are exact, so
+    // exclusive scan of the partial sums (the values are integers below 2^53: the sums are exact, so
     // the order of the additions does not matter)
-    for (int o = 1; o < 1024; o <<= 1) {
+    for (int o = 1; o < HTB_SR_THREADS; o <<= 1) {
         const double v = t >= o ? part[t - o] : 0.0;
         __syncthreads();
         part[t] += v;
         __syncthreads();
     }
-    const double total = part[1023];
+    const double total = part[HTB_SR_THREADS - 1];
     double cum = part[t] - s;
     const double lo = total * (double)rank / (double)world, hi = total * (double)(rank + 1) / (double)world;
     long long nlo = 0, nhi = 0;
@@ -1963,7 +1967,7 @@ int htb_shard_windows(cudaStream_t st, const long long *range_dev, const WalkGeo
 int htb_shard_range(cudaStream_t st, const double *work_dev, int64_t first_cell1, int64_t last_cell1,
                     int rank, int world, long long *range_dev, int *launches)
 {
-    k_shard_range<<<1, 1024, 0, st>>>(work_dev, (long long)first_cell1, (long long)last_cell1, rank, world, range_dev);
+    k_shard_range<<<1, HTB_SR_THREADS, 0, st>>>(work_dev, (long long)first_cell1, (long long)last_cell1, rank, world, range_dev);
     if (launches) *launches += 1;
     HTB_CUDA(cudaGetLastError());
     return 0;

@@ -142,20 +142,22 @@ k_scan_partial(const uint32_t *__restrict__ in, int64_t n, uint32_t *__restrict_
     }
 }
 
-// single block: exclusive scan of the block sums in place, total to *total
-__global__ void __launch_bounds__(1024)
+// single block: exclusive scan of the block sums in place, total to *total.  256 threads: single-block kernels must fit
+// beside the resident blocks of a persistent count kernel of another stream (see k_shard_range)
+#define SCAN_ONE 256
+__global__ void __launch_bounds__(SCAN_ONE)
 k_scan_bsums(uint32_t *__restrict__ bsum, int64_t nb, uint32_t *__restrict__ total)
 {
-    __shared__ uint32_t sh[1024];
+    __shared__ uint32_t sh[SCAN_ONE];
     __shared__ uint32_t carry;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    for (int64_t base = 0; base < nb; base += 1024) {
+    for (int64_t base = 0; base < nb; base += SCAN_ONE) {
         int64_t i = base + threadIdx.x;
         uint32_t v = (i < nb) ? bsum[i] : 0u;
         sh[threadIdx.x] = v;
         __syncthreads();
-        for (int o = 1; o < 1024; o <<= 1) {
+        for (int o = 1; o < SCAN_ONE; o <<= 1) {
             uint32_t t = (threadIdx.x >= (unsigned)o) ? sh[threadIdx.x - o] : 0u;
             __syncthreads();
             sh[threadIdx.x] += t;
@@ -165,7 +167,7 @@ k_scan_bsums(uint32_t *__restrict__ bsum, int64_t nb, uint32_t *__restrict__ tot
         const uint32_t c = carry;
         if (i < nb) bsum[i] = c + incl - v;
         __syncthreads();
-        if (threadIdx.x == 1023) carry = c + incl;
+        if (threadIdx.x == SCAN_ONE - 1) carry = c + incl;
         __syncthreads();
     }
     if (threadIdx.x == 0 && total) *total = carry;
@@ -213,17 +215,19 @@ k_scan_final(uint32_t *__restrict__ in, int64_t n, const uint32_t *__restrict__ 
 __global__ void k_set_u32(uint32_t *dst, const uint32_t *src) { *dst = *src; }
 
 // one launch instead of three for small inputs (a 1e5-point call spends its time between kernels, not in them): one
-// block walks the array in chunks of 1024 x SCAN_SMALL_ITEMS, warp-shuffle scan inside a chunk, running carry across
-#define SCAN_SMALL_ITEMS 4
+// block (256 threads, see k_scan_bsums) walks the array in chunks of 256 x SCAN_SMALL_ITEMS, warp-shuffle scan inside a
+// chunk, running carry across
+#define SCAN_SMALL_ITEMS 16
+#define SCAN_SMALL_THREADS 256
 #define SCAN_SMALL_MAX (1 << 15)
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(SCAN_SMALL_THREADS)
 k_scan_small(uint32_t *__restrict__ in, int64_t n, uint32_t *__restrict__ out, uint32_t *__restrict__ total, int zero_in)
 {
     __shared__ uint32_t wsum[32];
     __shared__ uint32_t carry_s;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t carry = 0;
-    for (int64_t base = 0; base < n; base += 1024 * SCAN_SMALL_ITEMS) {
+    for (int64_t base = 0; base < n; base += SCAN_SMALL_THREADS * SCAN_SMALL_ITEMS) {
         const int64_t i0 = base + (int64_t)threadIdx.x * SCAN_SMALL_ITEMS;
         uint32_t v[SCAN_SMALL_ITEMS], s = 0;
 #pragma unroll
@@ -241,7 +245,7 @@ k_scan_small(uint32_t *__restrict__ in, int64_t n, uint32_t *__restrict__ out, u
         if (lane == 31) wsum[wid] = inc;
         __syncthreads();
         if (wid == 0) {
-            uint32_t w = wsum[lane], winc = w;
+            uint32_t w = lane < SCAN_SMALL_THREADS / 32 ? wsum[lane] : 0u, winc = w;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
@@ -272,7 +276,7 @@ int htb_exclusive_scan_u32(cudaStream_t st, Workspace &ws, uint32_t *in, uint32_
         return 0;
     }
     if (n <= SCAN_SMALL_MAX) {
-        k_scan_small<<<1, 1024, 0, st>>>(in, n, out, total_dev, zero_in ? 1 : 0);
+        k_scan_small<<<1, SCAN_SMALL_THREADS, 0, st>>>(in, n, out, total_dev, zero_in ? 1 : 0);
         if (launches) *launches += 1;
         HTB_CUDA(cudaGetLastError());
         return 0;
@@ -281,7 +285,7 @@ int htb_exclusive_scan_u32(cudaStream_t st, Workspace &ws, uint32_t *in, uint32_
     uint32_t *bsum = nullptr;
     if (ws.alloc((void **)&bsum, sizeof(uint32_t) * (size_t)nblk)) return 1;
     k_scan_partial<<<(unsigned)nblk, SCAN_THREADS, 0, st>>>(in, n, bsum);
-    k_scan_bsums<<<1, 1024, 0, st>>>(bsum, nblk, total_dev);
+    k_scan_bsums<<<1, SCAN_ONE, 0, st>>>(bsum, nblk, total_dev);
     k_scan_final<<<(unsigned)nblk, SCAN_THREADS, 0, st>>>(in, n, bsum, out, zero_in ? 1 : 0);
     if (launches) *launches += 3;
     HTB_CUDA(cudaGetLastError());
