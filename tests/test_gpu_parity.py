@@ -211,6 +211,33 @@ def test_mesh_cell_ids_and_offsets_match_numpy_semantics(L, nd):
     assert np.array_equal(cii, m.cell_id_indices)
 
 
+@pytest.mark.parametrize("switch", ["HTB_TILES_BY_THREAD=1", "HTB_FZ=8", "HTB_FZ=48", "HTB_M2=3,2,5", "HTB_M1=2,3,9",
+                                    "HTB_MAXSLICES=7", "HTB_ITEMS_PER_WARP=9", "HTB_TAIL_EIGHTHS=16", "HTB_EARLY_EXIT=1",
+                                    "HTB_REDO_INPLACE=1", "HTB_NO_STRADDLE=1", "HTB_MAXFINE=3", "HTB_NO_SYM=1",
+                                    "HTB_NO_SORT_CACHE=1", "HTB_NO_STAGED_UPLOAD=1"])
+def test_environment_switches_do_not_change_results(switch):
+    """The A/B switches behind the sweeps under profiles/ (DESIGN: "Environment switches") select schedules, mesh
+    refinements and work-item shapes - never results."""
+    import os
+    s1, s2 = cases.pts(21, 60000, 120.0), cases.pts(22, 90000, 120.0)
+    rb = np.logspace(-1, np.log10(14.0), 13)
+    w = np.linspace(0.5, 1.5, len(s1))
+    want = (hb.npairs_3d(s1, s1, rb, period=120.0), hb.npairs_3d(s1, s2, rb, period=120.0),
+            hb.npairs_xy_z(s1, s1, rb, [0.0, 20.0], period=120.0),
+            hb.marked_npairs_3d(s1, s1, rb, 1, period=120.0, weights1=w, weights2=w))
+    name, value = switch.split("=")
+    os.environ[name] = value
+    try:
+        got = (hb.npairs_3d(s1, s1, rb, period=120.0), hb.npairs_3d(s1, s2, rb, period=120.0),
+               hb.npairs_xy_z(s1, s1, rb, [0.0, 20.0], period=120.0),
+               hb.marked_npairs_3d(s1, s1, rb, 1, period=120.0, weights1=w, weights2=w))
+    finally:
+        del os.environ[name]
+    for a, b in zip(want[:3], got[:3]):
+        assert np.array_equal(a, b)
+    assert np.allclose(want[3], got[3], rtol=1e-12, atol=0)
+
+
 def test_linearity_and_symmetry_properties_large():
     """Size-independent properties at a size the oracle would take long for: counts are additive over
     a split of sample2 and symmetric under swapping the samples."""
