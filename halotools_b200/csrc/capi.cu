@@ -868,7 +868,6 @@ struct Call {
             if (K < 1 || (fl & HTB_FLAG_NO_CULL) || getenv("HTB_NO_STRADDLE")) K = 1;
             G.maxspan = K;
             G.maxfine = m1[Fd];           // a tile is never longer than one reference cell
-            if (const char *e = getenv("HTB_MAXFINE")) { const int v = atoi(e); if (v >= 1) G.maxfine = v; }
             G.cs1f = g->cell1_size[Fd];
             // slicing a tile only pays if a slice still holds enough pair evaluations to amortise the per-item
             // latencies (tile fetch, point loads, first TMA): about 2e5 pairs per item

@@ -213,7 +213,7 @@ def test_mesh_cell_ids_and_offsets_match_numpy_semantics(L, nd):
 
 @pytest.mark.parametrize("switch", ["HTB_TILES_BY_THREAD=1", "HTB_FZ=8", "HTB_FZ=48", "HTB_M2=3,2,5", "HTB_M1=2,3,9",
                                     "HTB_MAXSLICES=7", "HTB_ITEMS_PER_WARP=9", "HTB_TAIL_EIGHTHS=16", "HTB_EARLY_EXIT=1",
-                                    "HTB_REDO_INPLACE=1", "HTB_NO_STRADDLE=1", "HTB_MAXFINE=3", "HTB_NO_SYM=1",
+                                    "HTB_REDO_INPLACE=1", "HTB_NO_STRADDLE=1", "HTB_NO_SYM=1",
                                     "HTB_NO_SORT_CACHE=1", "HTB_NO_STAGED_UPLOAD=1"])
 def test_environment_switches_do_not_change_results(switch):
     """The A/B switches behind the sweeps under profiles/ (DESIGN: "Environment switches") select schedules, mesh
