@@ -278,6 +278,23 @@ def test_host_minmax_helper_matches_numpy():
                                ctypes.c_int32(3), lo, hi) == 0
     assert all(np.isnan(v) for v in lo) and all(np.isnan(v) for v in hi)
 
+    def extrema(m):
+        assert lib.htb_host_minmax(ctypes.c_void_p(m.ctypes.data), ctypes.c_int64(len(m)), ctypes.c_int64(m.strides[0] // 8),
+                                   ctypes.c_int32(3), lo, hi) == 0
+        return list(lo), list(hi)
+    # the vectorised scan of contiguous (n, 3) rows: every remainder of the 8-row trips, an infinity (its NaN detector fires
+    # on inf - inf: the rows are then re-checked one by one), a NaN in the tail rows, and strided rows (the generic loop)
+    for n in (1, 7, 8, 9, 1000, 100003):
+        m = rng.uniform(-3, 1000, (n, 3))
+        assert extrema(m) == (list(m.min(axis=0)), list(m.max(axis=0)))
+    m = rng.uniform(0, 10, (100001, 3))
+    m[5000, 1] = np.inf
+    assert extrema(m) == (list(m.min(axis=0)), list(m.max(axis=0)))
+    m[100000, 0] = np.nan
+    assert all(np.isnan(v) for v in extrema(m)[0])
+    m = rng.uniform(0, 10, (70000, 4))[:, :3]
+    assert extrema(m) == (list(m.min(axis=0)), list(m.max(axis=0)))
+
 
 def test_pbc_check_messages_on_large_samples():
     from halotools_b200.helpers import enforce_sample_respects_pbcs
