@@ -8,4 +8,4 @@ echo "== smoke" ; timeout 300 python -c "import __graft_entry__ as g; g.smoke()"
 echo "== pytest gpu"; timeout 2400 python -m pytest tests -m gpu -q --timeout 900 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_gpu.log
 echo "== bench"; timeout 1200 python bench.py > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -1 gpurun_out/bench.log | cut -c1-400; tail -3 gpurun_out/bench.err
 echo "== bench reference arm"; timeout 1200 python bench.py --impl reference > gpurun_out/bench_ref.log 2> gpurun_out/bench_ref.err; echo "rc=$?"; tail -1 gpurun_out/bench_ref.log | cut -c1-400
-echo "== configs"; timeout 900 python scripts/gpu_configs.py > gpurun_out/configs.json 2> gpurun_out/configs.err; echo "rc=$?"; tail -2 gpurun_out/configs.err
+
