@@ -238,6 +238,33 @@ def test_environment_switches_do_not_change_results(switch):
     assert np.allclose(want[3], got[3], rtol=1e-12, atol=0)
 
 
+def test_tile_list_by_warp_walks_long_columns_through_several_windows():
+    """More than 1024 fine cells along the fast dimension (a 40 x 40 x 4000 box: 2000 reference cells per column):
+    k_tiles_warp reloads its shared-memory window of column offsets on the way.  Same counts as the one-thread-per-column
+    builder, as the sum over a split of sample2 and with the samples exchanged; a clustered part puts many tiles into a
+    few columns."""
+    import os
+    period = [40.0, 40.0, 4000.0]
+    rng = np.random.RandomState(31)
+    uni = rng.uniform(0, 1.0, (400000, 3)) * period
+    blob = np.mod(np.array([20.0, 20.0, 0.0]) + rng.normal(0, 1.0, (60000, 3)) * np.array([1.5, 1.5, 900.0]), period)
+    s1 = np.concatenate([uni, blob])
+    s2 = rng.uniform(0, 1.0, (300000, 3)) * period
+    rb = np.logspace(-1.5, np.log10(2.0), 9)
+    auto = hb.npairs_3d(s1, s1, rb, period=period)
+    assert _lib.last_stats["refine1"][2] * 2000 > 1024
+    cross = hb.npairs_3d(s1, s2, rb, period=period)
+    os.environ["HTB_TILES_BY_THREAD"] = "1"
+    try:
+        assert np.array_equal(auto, hb.npairs_3d(s1, s1, rb, period=period))
+        assert np.array_equal(cross, hb.npairs_3d(s1, s2, rb, period=period))
+    finally:
+        del os.environ["HTB_TILES_BY_THREAD"]
+    assert np.array_equal(cross, hb.npairs_3d(s1, s2[:90000], rb, period=period) + hb.npairs_3d(s1, s2[90000:], rb, period=period))
+    assert np.array_equal(cross, hb.npairs_3d(s2, s1, rb, period=period))
+    assert auto[-1] > len(s1) and cross[-1] > 0
+
+
 def test_linearity_and_symmetry_properties_large():
     """Size-independent properties at a size the oracle would take long for: counts are additive over
     a split of sample2 and symmetric under swapping the samples."""
