@@ -1114,9 +1114,6 @@ struct MarkedQ {
     // w1 of the entry's point times w2 of its sample2 point
     __device__ __forceinline__ double weight_of(uint32_t j) const
     {
-#ifdef MQ_DEBUG
-        if ((j & 0x7fffffffu) > 200000000u) { printf("MQ bad j %08x lane %d qbase %u qs %u qptr %u qsave %u\n", j, lane, qbase, qs, qptr, qsave); return 0.0; }
-#endif
         const double wj = __ldg(w2g + (j & 0x7fffffffu));
         return ((j >> 31) ? w1[1] : w1[0]) * wj;
     }
@@ -1218,9 +1215,6 @@ struct MarkedQ {
         umin = min(umin, (unsigned)key);
         hmin = min(hmin, hi);
         add_if_neg(Wtop[q], key, wj);
-#ifdef MQ_DEBUG
-        if ((jtag & 0x7fffffffu) > 200000000u && key <= P.F[TOP - 1]) printf("MQ push bad jtag %08x lane %d\n", jtag, lane);
-#endif
         if (key <= P.F[TOP - 1]) { sts_kj(qptr, key, jtag); qptr += 256u; }
     }
     // Five levels of the exact scan: if (dsq <= e_s && no lower level took the pair) a_s += w.  Per level one DSETP (the
