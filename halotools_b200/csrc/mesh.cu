@@ -3,13 +3,16 @@
 //
 // Replaces RectangularMesh.__init__ (digitize -> argsort -> searchsorted,
 // /root/reference/halotools/mock_observables/pair_counters/rectangular_mesh.py:118-222)
-// by: k_assign (fine cell id of every point + points per cell through fire-and-forget atomics: RED, no round trip), a
-// 3-pass exclusive scan of the per-cell counts, and k_scatter (position = first position of the cell + arrival rank from
-// one returning atomic on the cell's fill counter).  O(N) HBM traffic: read 24 B + write 4 B per point in k_assign, read
-// 28 B + write 24 B (+ payload) in k_scatter.  1e8 particles (2-D): 7.6 ms (round 1, with the arrival rank taken and stored
-// in k_assign: 10.4 ms).  A two-pass variant (block-local partition into <= 256 buckets of consecutive cells, then an
-// L2-resident scatter per bucket) was measured at 10.7 ms and dropped: the returning atomics, not the scattered 8-byte
-// writes, are what the scatter waits for.
+// by: k_assign (fine cell id of every point + points per cell through fire-and-forget atomics: RED, no round trip), an
+// exclusive scan of the per-cell counts (one block for small meshes, three passes otherwise; it zeroes the counters on the
+// way, which then serve as fill counters), and k_scatter (position = first position of the cell + arrival rank from one
+// returning atomic on the cell's fill counter; it also writes the pad entries).  O(N) HBM traffic: read 24 B + write 4 B
+// per point in k_assign, read 28 B + write 24 B (+ payload) in k_scatter.  1e8 particles (2-D): 5.9 ms = 0.73 ms assign
+// (FP64 bound until the fmod-based floor division was replaced by an exact floor from a reciprocal estimate and one fma,
+// htb_ref_digitize) + 4.7 ms scatter (bound by the 8-byte stores into random 32-byte sectors: 7.3 GB of DRAM traffic for
+// 3.6 GB of algorithmic bytes; profiles/r02_k1_ncu.txt).  Round 1: 10.4 ms with the arrival rank taken and stored in
+// k_assign.  A first two-pass variant (block-local partition into <= 256 buckets of consecutive cells, then an
+// L2-resident scatter per bucket) measured 10.7 ms.
 #include <cstdlib>
 #include "htb_internal.cuh"
 
