@@ -15,7 +15,11 @@ same unit of work.
             host arrays, H2D of every sample inside the timed region
   roofline  FP64 non-FMA issue roofline of the dominant kernel (k_count<Fast3>): 8 f64 ops per
             evaluated pair (3 sub, 3 mul, 2 add) x pairs evaluated / kernel time, against the FP64
-            DADD/DMUL issue rate measured live on the same GPU (MEASURED_PEAKS.json has no FP64 entry)
+            DADD/DMUL issue rate measured live on the same GPU (MEASURED_PEAKS.json has no FP64 entry).
+            The step's three launches (DD, DR, RR) run co-resident on three streams, so the time is the
+            window in which they ran inside the timed steps (first warp in of any -> last warp out of
+            any, from stamps the kernels write themselves) and the pairs are those of all three; the RR
+            launch run alone is reported beside it (roofline.rr_launch)
   e2e_pageable   the same from ordinary (pageable) numpy arrays - what a drop-in caller passes
   cpu_baseline / --impl reference   the reference's own compiled Cython engine (oracle/_ref) — or the
             C oracle port when it is absent — on all host cores, on a bounded sample (a range of
