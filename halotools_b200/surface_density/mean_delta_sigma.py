@@ -27,10 +27,14 @@ def mean_delta_sigma(galaxies, particles, effective_particle_masses,
     uniform_mass = len(np.atleast_1d(effective_particle_masses)) == 1
     use_scalar = uniform_mass and not _lib.default_flags & _lib.FLAG_GENERIC
     keep = None
-    if (period is not None and use_scalar and _dist.device_collective()
-            and _lib.uploadable(galaxies) and _lib.uploadable(particles)):
+    if (period is not None and use_scalar and _lib.uploadable(galaxies) and _lib.uploadable(particles)
+            and (_dist.device_collective() or (len(particles) >= 1000000 and _lib.library_present()
+                                               and _lib.load().htb_device_count() >= 1))):
         # multi-GPU: every rank sends 1/world of each sample across PCIe, an all-gather over NVLink completes the copies
-        # (instead of every rank uploading all 1e8 particles: 8 x 1.6 GB through the host's PCIe root)
+        # (instead of every rank uploading all 1e8 particles: 8 x 1.6 GB through the host's PCIe root).
+        # One GPU, large samples: start the copies NOW, asynchronously, and let the bounds checks of the argument
+        # processing run on the device copy (one HBM-bound pass) instead of scanning 2.4 GB on the host before the first
+        # byte moves (config 5 end to end: 359 -> 340 ms)
         import torch
         keep = (galaxies, particles)
         with torch.cuda.stream(_lib.engine_stream()):
