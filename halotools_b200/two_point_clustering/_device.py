@@ -69,6 +69,10 @@ class DeviceStatistic(object):
             self.tables = torch.zeros((MAX_TABLES, self.ncum), dtype=torch.int64, device="cuda")
             # xi rows, then one row whose first entries are the zero-division flags (int32 view)
             self.xi = torch.zeros((max_xi + 1, max(self.nout, 2)), dtype=torch.float64, device="cuda")
+            # uploads that follow on this stream are awaited per sample, not wholesale (launch): the tables' own event
+            self.tables_ready = torch.cuda.Event()
+            self.tables_ready.record(self.stream)
+        self.uploaded = {}      # data_ptr of a sample uploaded by inputs() -> (order of arrival, event behind its copy)
         self.flags = self.xi[max_xi].view(torch.int32)
         self.used = 0
         self.nxi = 0
@@ -97,8 +101,11 @@ class DeviceStatistic(object):
             with self.torch.cuda.stream(self.stream):
                 for a, c in zip(arrays, on_device):
                     if not c:
-                        distinct[id(a)] = _dist.to_device(a)
+                        dev = distinct[id(a)] = _dist.to_device(a)
                         self.keep.append(a)
+                        ev = self.torch.cuda.Event()
+                        ev.record(self.stream)
+                        self.uploaded[int(dev.data_ptr())] = (len(self.uploaded), ev)
             self.multi = not os.environ.get("HTB_ONE_STREAM")
         return tuple(None if a is None else distinct[id(a)] for a in samples)
 
@@ -137,16 +144,32 @@ class DeviceStatistic(object):
         set-up kernels and count kernels of the smaller counts run beside the big one - in the SM slots its last,
         partly filled round of tiles would have left idle - instead of before or after it)."""
         deferred, self.deferred = self.deferred, []
+
+        def arrival(d):
+            # order in which the samples of a count arrive on the device (0: resident, or the first upload)
+            return max([self.uploaded[int(t.data_ptr())][0] for t in d[4][:2]
+                        if getattr(t, "is_cuda", False) and int(t.data_ptr()) in self.uploaded] or [0])
+
         if not os.environ.get("HTB_ISSUE_ORDER"):
-            deferred.sort(key=lambda d: -d[0])
+            # largest first; while samples are still crossing PCIe, the counts whose samples arrive first go first (tpcf
+            # from host arrays: DD runs while the randoms are being copied)
+            deferred.sort(key=lambda d: (arrival(d), -d[0]) if self.uploaded else -d[0])
         sides = []
         for i in range(len(deferred)):
             side = _side_streams(self.torch)[i % SIDE_STREAMS]
             if side not in self.forked:
-                side.wait_stream(self.stream)      # the samples and the zeroed tables were produced on the main stream
+                if self.uploaded:
+                    side.wait_event(self.tables_ready)
+                else:
+                    side.wait_stream(self.stream)      # the samples and the zeroed tables were produced on the main stream
                 self.forked.append(side)
             sides.append(side)
         for i, (_size, _k, enqueue, out, args, kwargs) in enumerate(deferred):
+            if self.uploaded:
+                # wait for THIS count's samples only (a sample that was not uploaded here was resident before the call)
+                for t in args[:2]:
+                    if getattr(t, "is_cuda", False) and int(t.data_ptr()) in self.uploaded:
+                        sides[i].wait_event(self.uploaded[int(t.data_ptr())][1])
             self._enqueue(sides[i], _lib.FLAG_EARLY_EXIT, enqueue, out, args, kwargs)
 
     def analytic(self, array):
